@@ -1,0 +1,188 @@
+/*
+ * termdaw_b200.h — C ABI of the B200-native offline renderer for termdaw's audio graph.
+ *
+ * This is the drop-in boundary.  termdaw (Rust) has no FFI seam of its own for
+ * this path; the seam is cut exactly where `State` touches `Graph` / the banks, so every entry
+ * point below names the reference call it replaces (paths relative to the reference repo).  A
+ * Rust `extern "C"` block binding these symbols is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; the context owns all device memory; the caller owns every host array and
+ *     no pointer is retained past a call (mirrors `graph.rs:189`, where `Graph` lends `&Sample`).
+ *   - functions returning `int` return >= 0 on success (an index where one is produced) and a
+ *     negative `TDG_ERR_*` on failure; `tdg_last_error(ctx)` gives the message.  Nothing aborts.
+ *   - one context == one termdaw project (`State`: sample bank + floww bank + buffer bank + graph),
+ *     single-threaded like the reference (all graph access is from the main thread,
+ *     `ui_workflow.rs:17-21`), bound to one CUDA device.
+ *   - there is NO CPU fallback: every call that renders fails with TDG_ERR_CUDA when no sm_100
+ *     device is usable.
+ *
+ * The CPU oracle under oracle/ exports the same shape with the prefix `tdo_` (test infrastructure).
+ */
+#ifndef TERMDAW_B200_H
+#define TERMDAW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tdg_ctx tdg_ctx;
+
+enum {
+    TDG_OK = 0,
+    TDG_ERR_INVALID = -1,            /* bad argument / unknown index                                  */
+    TDG_ERR_CUDA = -2,               /* CUDA runtime failure or no usable device                      */
+    TDG_ERR_UNSUPPORTED_VERTEX = -3, /* add_lv2fx: arbitrary native plugin code is outside the path   */
+    TDG_ERR_ADSR_CONF = -4,          /* adsr array is not 0, 6 or 9 floats (reference panics, state.rs:393) */
+    TDG_ERR_SAMPLE = -5,             /* Sample::from / SampleBank::add error paths (sample.rs:38-77,241-254) */
+    TDG_ERR_BITDEPTH = -6,           /* bitdepth not in {8,16,24,32} (state.rs:495-501)               */
+    TDG_ERR_NO_OUTPUT = -7,          /* no output vertex set (graph.rs:186-192 returns None)          */
+    TDG_ERR_TOO_WIDE = -8,           /* 8/24-bit sample out of range: hound TooWide -> reference panics (state.rs:521) */
+    TDG_ERR_CAPACITY = -9,           /* caller's output array too small                               */
+    TDG_ERR_UNSORTED = -10           /* floww events not sorted by frame (GPU path requires sorted)   */
+};
+
+/* SampleLoadMethod (sample.rs:200-215).  tdg_sample_mode_from_string mirrors `SampleLoadMethod::from`. */
+enum {
+    TDG_MODE_STEREO = 0, TDG_MODE_LEFT = 1, TDG_MODE_RIGHT = 2, TDG_MODE_LOUDEST = 3,
+    TDG_MODE_NORM = 4 /* "normalize-seperate" */, TDG_MODE_MIX = 5 /* "mix-down" */
+};
+int tdg_sample_mode_from_string(const char* s);
+
+/* ---- context ------------------------------------------------------------------------------------
+ * Replaces Graph::new(max_buffer_len, sr) (graph.rs:25), SampleBank::new(sr) (sample.rs:213),
+ * FlowwBank::new(sr, bl) (floww.rs:17), BufferBank::new() (bufferbank.rs:18) as built in main.rs:77-83. */
+int tdg_ctx_create(uint32_t project_sr, uint32_t buffer_len, int device, tdg_ctx** out);
+void tdg_ctx_destroy(tdg_ctx* ctx);
+const char* tdg_last_error(tdg_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
+uint64_t tdg_kernel_launches(tdg_ctx* ctx);
+
+/* ---- banks --------------------------------------------------------------------------------------
+ * Numeric part of SampleBank::add (sample.rs:262-310): `linear` is the decoded WAV sample stream
+ * (integer PCM cast `as f32` UNSCALED, or float samples), channel-interleaved, `n_values` values.
+ * The device de-interleaves, applies the load mode, peak-normalises and sinc-resamples to the
+ * project rate.  Returns the sample index (SampleBank::get_index, sample.rs:338). */
+int tdg_sample_add(tdg_ctx* ctx, const float* linear, uint64_t n_values, uint32_t channels,
+                   uint32_t src_sr, int mode);
+/* Frames of a loaded sample at project rate (Sample::len, sample.rs:79). */
+int64_t tdg_sample_frames(tdg_ctx* ctx, int sample);
+/* Debug tap: copy a loaded sample (after normalise + resample) back to the host. */
+int tdg_sample_read(tdg_ctx* ctx, int sample, float* l, float* r, uint64_t cap_frames);
+
+/* BufferBank::add (bufferbank.rs:26) + parse_wavetable_from_buffer at graph build (state.rs:415). */
+int tdg_resource_add(tdg_ctx* ctx, const uint8_t* bytes, uint64_t n);
+
+/* FlowwBank::declare_floww / add_floww / declare_stream (floww.rs:32-53): one floww = time-sorted
+ * events (t seconds, note, vel); vel <= 0.001 is a note-off (floww.rs:114,134). n may be 0. */
+int tdg_floww_add(tdg_ctx* ctx, const float* t_sec, const float* note, const float* vel, uint64_t n);
+/* FlowwBank::reset (floww.rs:21) — State::refresh reloads every floww (state.rs:240). */
+int tdg_floww_reset(tdg_ctx* ctx);
+
+/* ---- graph construction -------------------------------------------------------------------------
+ * Graph::reset (graph.rs:39).  Vertices get indices in call order (graph.rs:49-56). */
+int tdg_graph_reset(tdg_ctx* ctx);
+/* Graph::add(Vertex::new(bl, gain, angle, wet, VertexExt::…)) — graph.rs:49, ctors extensions.rs:83-194,
+ * argument clamps of state.rs:341-457 are applied by the CALLER's front-end except where noted. */
+int tdg_add_sum(tdg_ctx* ctx, float gain, float angle);                                   /* state.rs:341 */
+int tdg_add_normalize(tdg_ctx* ctx, float gain, float angle);                             /* state.rs:344 */
+int tdg_add_sample_loop(tdg_ctx* ctx, float gain, float angle, int sample);               /* state.rs:349 */
+/* note < 0 => None (state.rs:358) */
+int tdg_add_sample_multi(tdg_ctx* ctx, float gain, float angle, int sample, int floww, int note);
+/* lerp_len is clamped to >= 0 (state.rs:370) */
+int tdg_add_sample_lerp(tdg_ctx* ctx, float gain, float angle, int sample, int floww, int note,
+                        int lerp_len);
+int tdg_add_debug_sine(tdg_ctx* ctx, float gain, float angle, int floww);                 /* state.rs:378 */
+/* square z is clamped to >= 0.0001 (state.rs:400); adsr arrays: 0, 6 or 9 floats (adsr.rs:94-114) */
+int tdg_add_synth(tdg_ctx* ctx, float gain, float angle, int floww,
+                  float sq_vol, float sq_z, const float* sq_adsr, int sq_n,
+                  float tf_vol, float tf_z, const float* tf_adsr, int tf_n,
+                  float tr_vol, const float* tr_adsr, int tr_n);
+int tdg_add_sampsyn(tdg_ctx* ctx, float gain, float angle, int floww, const float* adsr, int n,
+                    int resource);                                                        /* state.rs:406 */
+/* Always TDG_ERR_UNSUPPORTED_VERTEX: the GPU renderer rejects graphs with LV2 fx vertices. */
+int tdg_add_lv2fx(tdg_ctx* ctx, float gain, float angle, float wet, int plugin);         /* state.rs:429 */
+int tdg_add_adsr(tdg_ctx* ctx, float gain, float angle, float wet, int floww, int use_off,
+                 int use_max, int note, const float* conf, int n);                        /* state.rs:437 */
+int tdg_add_bandpass(tdg_ctx* ctx, float gain, float angle, float wet, float cut_off_hz_low,
+                     float cut_off_hz_high, int pass);                                    /* state.rs:453 */
+/* Graph::connect_internal (graph.rs:58-78): 1 = connected, 0 = refused (self edge, unknown index,
+ * target takes no input, would close a cycle).  Duplicate edges are legal. */
+int tdg_connect(tdg_ctx* ctx, int a, int b);
+int tdg_set_output(tdg_ctx* ctx, int vertex);                                             /* graph.rs:141 */
+/* Graph::check_graph (graph.rs:150-174): 1 ok / 0 failed; lists vertices that do not reach output. */
+int tdg_check_graph(tdg_ctx* ctx, int* unreachable, int cap, int* n_unreachable);
+int tdg_reset_normalize(tdg_ctx* ctx);                                                    /* graph.rs:207 */
+float tdg_get_normalize_value(tdg_ctx* ctx, int vertex);            /* extensions.rs:301; -1 if not one */
+
+/* ---- transport ----------------------------------------------------------------------------------*/
+int tdg_set_time(tdg_ctx* ctx, uint64_t frame);                      /* Graph::set_time, graph.rs:123 */
+uint64_t tdg_change_time(tdg_ctx* ctx, uint64_t delta, int plus);    /* Graph::change_time, graph.rs:130 */
+uint64_t tdg_get_time(tdg_ctx* ctx);                                 /* Graph::get_time, graph.rs:137 */
+int tdg_floww_set_time(tdg_ctx* ctx, uint64_t frame);                /* FlowwBank::set_time, floww.rs:83 */
+
+/* ---- the hot path -------------------------------------------------------------------------------
+ * Graph::true_normalize_scan(sb, fb, host, chunks) (graph.rs:222-237), called by State::scan_exact. */
+int tdg_normalize_scan(tdg_ctx* ctx, uint64_t chunks);
+/* The chunk loop of State::render (state.rs:477-577): `chunks` × Graph::render, optional sinc
+ * down-sampling when project_sr > render_sr, quantisation to `bitdepth` and interleaving (L,R) into
+ * `out_pcm` exactly as hound would lay the data chunk out (little endian; 8-bit is offset binary).
+ * `out_pcm` may be NULL to render without a device->host copy (frames_written is still set).
+ * Ends like the reference: graph time rewound to 0, floww cursor NOT rewound (state.rs:575). */
+int tdg_render(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth,
+               uint8_t* out_pcm, uint64_t cap_bytes, uint64_t* frames_written);
+/* Upper bound of the PCM bytes tdg_render will write for these arguments. */
+uint64_t tdg_render_bound_bytes(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth);
+
+/* Batched forms (independent projects): the same two calls over `n` contexts on
+ * the same device, merged into one device schedule (one launch per DAG level and kernel class for
+ * ALL projects).  Results are identical to calling the single forms in a loop. */
+int tdg_normalize_scan_many(tdg_ctx** ctxs, int n, const uint64_t* chunks);
+int tdg_render_many(tdg_ctx** ctxs, int n, const uint64_t* chunks, const uint32_t* render_sr,
+                    const uint32_t* bitdepth, uint8_t** out_pcm, const uint64_t* cap_bytes,
+                    uint64_t* frames_written);
+
+/* ---- parity taps (pre-quantisation fp32 buffers) -------------------------------------------------
+ * The reference keeps one chunk per vertex (graph.rs:242); the device keeps the whole pass.  With
+ * taps enabled the buffers of the LAST pass (scan or render) stay readable. */
+int tdg_enable_taps(tdg_ctx* ctx, int on);
+int tdg_read_vertex_buffer(tdg_ctx* ctx, int vertex, uint64_t frame0, uint64_t n_frames,
+                           float* l, float* r);
+
+/* ---- time sharding -----------------------------------------------------------
+ * Render chunks [chunk0, chunk0+chunks) of a pass that started at the current transport position:
+ * the event-driven vertex state at chunk0 is rebuilt by replaying the floww events (and the per-chunk
+ * f32 clock additions) from the pass start without rendering audio; `warmup_chunks` extra chunks are
+ * rendered before chunk0 and discarded so that band-pass state has converged at the boundary.
+ * Normalize peaks are exchanged by the caller (NCCL max-allreduce) through the two calls below. */
+int tdg_scan_segment(tdg_ctx* ctx, uint64_t chunk0, uint64_t chunks, uint64_t warmup_chunks);
+int tdg_render_segment(tdg_ctx* ctx, uint64_t chunk0, uint64_t chunks, uint64_t warmup_chunks,
+                       uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes,
+                       uint64_t* frames_written);
+/* Normalize state as (max, scan_max) pairs, one per vertex (non-normalize vertices: -1, -1). */
+int tdg_get_normalize_state(tdg_ctx* ctx, float* max_out, float* scan_max_out, int cap);
+int tdg_set_normalize_state(tdg_ctx* ctx, const float* max_in, const float* scan_max_in, int n);
+/* Device pointer to the per-vertex (max, scan_max) float pairs, for an in-place NCCL all-reduce. */
+void* tdg_normalize_state_device_ptr(tdg_ctx* ctx, int* n_floats);
+
+/* ---- measurement ---------------------------------------------------------------------------------
+ * Device time (ms, CUDA events on the context's stream) and kernel count of the last scan/render
+ * call, and the algorithmic HBM bytes it moved (DESIGN.md "algorithmic bytes"). */
+typedef struct tdg_pass_stats {
+    double device_ms;        /* first kernel -> last kernel of the pass, CUDA events                */
+    double plan_ms;          /* host planning (event -> voice tables)                               */
+    double h2d_ms, d2h_ms;   /* host-side wall time spent in the copies                             */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t kernel_launches;
+    uint64_t algorithmic_bytes;
+    uint64_t frames;         /* project-rate frames rendered                                        */
+    uint64_t voice_frames;   /* voice-frames evaluated by the synth kernels                         */
+} tdg_pass_stats;
+int tdg_last_pass_stats(tdg_ctx* ctx, tdg_pass_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TERMDAW_B200_H */

@@ -1,0 +1,356 @@
+"""ctypes binding of the C ABI declared in include/termdaw_b200.h.
+
+The binder is parameterised by (shared library path, symbol prefix) because the CPU oracle under
+oracle/ exports the same shape with the prefix ``tdo_``; only tests/, bench.py's cpu_baseline leg
+and __graft_entry__.smoke() ever construct it with the oracle library.  The product
+(`termdaw_b200.load_library()`) always binds `libtermdaw_b200.so` with prefix ``tdg_`` and raises if
+the CUDA extension has not been built — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+c_f32p = C.POINTER(C.c_float)
+c_u8p = C.POINTER(C.c_uint8)
+c_u64p = C.POINTER(C.c_uint64)
+c_u32p = C.POINTER(C.c_uint32)
+c_i32p = C.POINTER(C.c_int)
+
+ERRORS = {
+    -1: "INVALID", -2: "CUDA", -3: "UNSUPPORTED_VERTEX", -4: "ADSR_CONF", -5: "SAMPLE",
+    -6: "BITDEPTH", -7: "NO_OUTPUT", -8: "TOO_WIDE", -9: "CAPACITY", -10: "UNSORTED",
+}
+
+
+class TermdawError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class PassStats(C.Structure):
+    _fields_ = [("device_ms", C.c_double), ("plan_ms", C.c_double), ("h2d_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+                ("frames", C.c_uint64), ("voice_frames", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a: np.ndarray, t=c_f32p):
+    return a.ctypes.data_as(t)
+
+
+class Library:
+    """One loaded shared library exposing <prefix>* symbols."""
+
+    SIGS = {
+        # name: (restype, argtypes)
+        "sample_mode_from_string": (C.c_int, [C.c_char_p]),
+        "ctx_create": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]),
+        "ctx_destroy": (None, [C.c_void_p]),
+        "last_error": (C.c_char_p, [C.c_void_p]),
+        "kernel_launches": (C.c_uint64, [C.c_void_p]),
+        "sample_add": (C.c_int, [C.c_void_p, c_f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]),
+        "sample_frames": (C.c_int64, [C.c_void_p, C.c_int]),
+        "sample_read": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_uint64]),
+        "resource_add": (C.c_int, [C.c_void_p, c_u8p, C.c_uint64]),
+        "floww_add": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_uint64]),
+        "floww_reset": (C.c_int, [C.c_void_p]),
+        "graph_reset": (C.c_int, [C.c_void_p]),
+        "add_sum": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+        "add_normalize": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+        "add_sample_loop": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int]),
+        "add_sample_multi": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]),
+        "add_sample_lerp": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "add_debug_sine": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int]),
+        "add_synth": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int,
+                                C.c_float, C.c_float, c_f32p, C.c_int,
+                                C.c_float, C.c_float, c_f32p, C.c_int,
+                                C.c_float, c_f32p, C.c_int]),
+        "add_sampsyn": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, c_f32p, C.c_int, C.c_int]),
+        "add_lv2fx": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]),
+        "add_adsr": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                               C.c_int, c_f32p, C.c_int]),
+        "add_bandpass": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]),
+        "connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+        "set_output": (C.c_int, [C.c_void_p, C.c_int]),
+        "check_graph": (C.c_int, [C.c_void_p, c_i32p, C.c_int, c_i32p]),
+        "reset_normalize": (C.c_int, [C.c_void_p]),
+        "get_normalize_value": (C.c_float, [C.c_void_p, C.c_int]),
+        "set_time": (C.c_int, [C.c_void_p, C.c_uint64]),
+        "change_time": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_int]),
+        "get_time": (C.c_uint64, [C.c_void_p]),
+        "floww_set_time": (C.c_int, [C.c_void_p, C.c_uint64]),
+        "normalize_scan": (C.c_int, [C.c_void_p, C.c_uint64]),
+        "render": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, c_u8p, C.c_uint64, c_u64p]),
+        "render_bound_bytes": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]),
+        "normalize_scan_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_u64p]),
+        "render_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_u64p, c_u32p, c_u32p,
+                                  C.POINTER(c_u8p), c_u64p, c_u64p]),
+        "enable_taps": (C.c_int, [C.c_void_p, C.c_int]),
+        "read_vertex_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, c_f32p, c_f32p]),
+        "get_normalize_state": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int]),
+    }
+    # symbols only the CUDA library has (time sharding + measurement)
+    GPU_ONLY = {
+        "scan_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+        "render_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, c_u8p,
+                                     C.c_uint64, c_u64p]),
+        "set_normalize_state": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int]),
+        "normalize_state_device_ptr": (C.c_void_p, [C.c_void_p, c_i32p]),
+        "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
+    }
+    # symbols only the oracle has (scalar maths for the reference's known-answer tests)
+    ORACLE_ONLY = {
+        "adsr_eval": (C.c_float, [c_f32p, C.c_int, C.c_int, C.c_float, C.c_float]),
+        "osc_eval": (C.c_float, [C.c_int, C.c_float, C.c_float, C.c_float]),
+        "set_length_chunks": (C.c_uint64, [C.c_uint32, C.c_float, C.c_uint32]),
+        "resample_whole": (C.c_int64, [c_f32p, c_f32p, C.c_uint64, C.c_uint32, C.c_uint32, c_f32p, c_f32p, C.c_uint64]),
+    }
+
+    def __init__(self, path: str, prefix: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing — build it first (python -c 'import __graft_entry__ as g; g.build()')")
+        self.path, self.prefix = path, prefix
+        self.dll = C.CDLL(path)
+        extra = self.GPU_ONLY if prefix == "tdg_" else self.ORACLE_ONLY
+        for name, (res, args) in {**self.SIGS, **extra}.items():
+            fn = getattr(self.dll, prefix + name)      # AttributeError == missing export
+            fn.restype, fn.argtypes = res, args
+            setattr(self, name, fn)
+
+    def exported(self) -> Sequence[str]:
+        extra = self.GPU_ONLY if self.prefix == "tdg_" else self.ORACLE_ONLY
+        return [self.prefix + n for n in {**self.SIGS, **extra}]
+
+
+class Context:
+    """One termdaw project on one device: the objects `State` owns (state.rs:27-47)."""
+
+    def __init__(self, lib: Library, project_sr: int, buffer_len: int, device: int = 0):
+        self.lib = lib
+        self.sr, self.bl = int(project_sr), int(buffer_len)
+        h = C.c_void_p()
+        rc = lib.ctx_create(self.sr, self.bl, device, C.byref(h))
+        if rc < 0 or not h:
+            raise TermdawError(rc, "ctx_create failed (is a CUDA device visible and the extension built?)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers
+    def _chk(self, rc: int) -> int:
+        if rc < 0:
+            raise TermdawError(rc, (self.lib.last_error(self.h) or b"").decode())
+        return rc
+
+    # -- banks
+    def sample_add(self, linear, channels: int, src_sr: int, mode: int = 0) -> int:
+        a = _f32(linear).ravel()
+        return self._chk(self.lib.sample_add(self.h, _p(a), a.size, channels, src_sr, mode))
+
+    def sample_frames(self, s: int) -> int:
+        return self._chk(self.lib.sample_frames(self.h, s))
+
+    def sample_read(self, s: int):
+        n = self.sample_frames(s)
+        l, r = np.empty(n, np.float32), np.empty(n, np.float32)
+        self._chk(self.lib.sample_read(self.h, s, _p(l), _p(r), n))
+        return l, r
+
+    def resource_add(self, blob: bytes) -> int:
+        a = np.frombuffer(blob, dtype=np.uint8).copy()
+        return self._chk(self.lib.resource_add(self.h, _p(a, c_u8p), a.size))
+
+    def floww_add(self, t, note, vel) -> int:
+        t, note, vel = _f32(t), _f32(note), _f32(vel)
+        assert t.size == note.size == vel.size
+        return self._chk(self.lib.floww_add(self.h, _p(t), _p(note), _p(vel), t.size))
+
+    def floww_reset(self):
+        self._chk(self.lib.floww_reset(self.h))
+
+    # -- graph
+    def graph_reset(self):
+        self._chk(self.lib.graph_reset(self.h))
+
+    def add_sum(self, gain, angle):
+        return self._chk(self.lib.add_sum(self.h, gain, angle))
+
+    def add_normalize(self, gain, angle):
+        return self._chk(self.lib.add_normalize(self.h, gain, angle))
+
+    def add_sample_loop(self, gain, angle, sample):
+        return self._chk(self.lib.add_sample_loop(self.h, gain, angle, sample))
+
+    def add_sample_multi(self, gain, angle, sample, floww, note):
+        return self._chk(self.lib.add_sample_multi(self.h, gain, angle, sample, floww, note))
+
+    def add_sample_lerp(self, gain, angle, sample, floww, note, lerp_len):
+        return self._chk(self.lib.add_sample_lerp(self.h, gain, angle, sample, floww, note, lerp_len))
+
+    def add_debug_sine(self, gain, angle, floww):
+        return self._chk(self.lib.add_debug_sine(self.h, gain, angle, floww))
+
+    def add_synth(self, gain, angle, floww, sq_vol, sq_z, sq_adsr, tf_vol, tf_z, tf_adsr, tr_vol, tr_adsr):
+        a, b, c = _f32(sq_adsr), _f32(tf_adsr), _f32(tr_adsr)
+        return self._chk(self.lib.add_synth(self.h, gain, angle, floww, sq_vol, sq_z, _p(a), a.size,
+                                            tf_vol, tf_z, _p(b), b.size, tr_vol, _p(c), c.size))
+
+    def add_sampsyn(self, gain, angle, floww, adsr, resource):
+        a = _f32(adsr)
+        return self._chk(self.lib.add_sampsyn(self.h, gain, angle, floww, _p(a), a.size, resource))
+
+    def add_lv2fx(self, gain, angle, wet, plugin):
+        return self._chk(self.lib.add_lv2fx(self.h, gain, angle, wet, plugin))
+
+    def add_adsr(self, gain, angle, wet, floww, use_off, use_max, note, conf):
+        a = _f32(conf)
+        return self._chk(self.lib.add_adsr(self.h, gain, angle, wet, floww, int(bool(use_off)),
+                                           int(bool(use_max)), note, _p(a), a.size))
+
+    def add_bandpass(self, gain, angle, wet, lo, hi, pass_):
+        return self._chk(self.lib.add_bandpass(self.h, gain, angle, wet, lo, hi, int(bool(pass_))))
+
+    def connect(self, a: int, b: int) -> bool:
+        return bool(self.lib.connect(self.h, a, b))
+
+    def set_output(self, v: int):
+        self._chk(self.lib.set_output(self.h, v))
+
+    def check_graph(self):
+        cap = 4096
+        arr = (C.c_int * cap)()
+        n = C.c_int(0)
+        ok = self.lib.check_graph(self.h, arr, cap, C.byref(n))
+        return bool(ok), [arr[i] for i in range(min(n.value, cap))]
+
+    def reset_normalize(self):
+        self._chk(self.lib.reset_normalize(self.h))
+
+    def get_normalize_value(self, v: int) -> float:
+        return float(self.lib.get_normalize_value(self.h, v))
+
+    # -- transport
+    def set_time(self, frame: int):
+        self._chk(self.lib.set_time(self.h, frame))
+
+    def change_time(self, delta: int, plus: bool) -> int:
+        return int(self.lib.change_time(self.h, delta, int(plus)))
+
+    def get_time(self) -> int:
+        return int(self.lib.get_time(self.h))
+
+    def floww_set_time(self, frame: int):
+        self._chk(self.lib.floww_set_time(self.h, frame))
+
+    # -- hot path
+    def normalize_scan(self, chunks: int):
+        self._chk(self.lib.normalize_scan(self.h, chunks))
+
+    def render(self, chunks: int, render_sr: int, bitdepth: int, want_pcm: bool = True) -> Optional[np.ndarray]:
+        """Returns the PCM data-chunk bytes (uint8 array) the reference would hand to hound."""
+        cap = int(self.lib.render_bound_bytes(self.h, chunks, render_sr, bitdepth))
+        frames = C.c_uint64(0)
+        if want_pcm:
+            out = np.empty(cap, np.uint8)
+            self._chk(self.lib.render(self.h, chunks, render_sr, bitdepth, _p(out, c_u8p), cap, C.byref(frames)))
+            return out[: frames.value * 2 * (bitdepth // 8)]
+        self._chk(self.lib.render(self.h, chunks, render_sr, bitdepth, None, 0, C.byref(frames)))
+        self.last_frames = frames.value
+        return None
+
+    def enable_taps(self, on: bool = True):
+        self._chk(self.lib.enable_taps(self.h, int(on)))
+
+    def read_vertex_buffer(self, vertex: int, frame0: int, n: int):
+        l, r = np.empty(n, np.float32), np.empty(n, np.float32)
+        self._chk(self.lib.read_vertex_buffer(self.h, vertex, frame0, n, _p(l), _p(r)))
+        return l, r
+
+    def get_normalize_state(self, n_vertices: int):
+        mx, sm = np.empty(n_vertices, np.float32), np.empty(n_vertices, np.float32)
+        self._chk(self.lib.get_normalize_state(self.h, _p(mx), _p(sm), n_vertices))
+        return mx, sm
+
+    # -- CUDA library only
+    def scan_segment(self, chunk0: int, chunks: int, warmup_chunks: int):
+        self._chk(self.lib.scan_segment(self.h, chunk0, chunks, warmup_chunks))
+
+    def render_segment(self, chunk0: int, chunks: int, warmup_chunks: int, bitdepth: int, want_pcm=True):
+        cap = chunks * self.bl * 2 * (bitdepth // 8)
+        frames = C.c_uint64(0)
+        out = np.empty(cap if want_pcm else 0, np.uint8)
+        self._chk(self.lib.render_segment(self.h, chunk0, chunks, warmup_chunks, bitdepth,
+                                          _p(out, c_u8p) if want_pcm else None, cap, C.byref(frames)))
+        return out[: frames.value * 2 * (bitdepth // 8)] if want_pcm else None
+
+    def set_normalize_state(self, mx, sm):
+        mx, sm = _f32(mx), _f32(sm)
+        self._chk(self.lib.set_normalize_state(self.h, _p(mx), _p(sm), mx.size))
+
+    def normalize_state_device_ptr(self):
+        n = C.c_int(0)
+        p = self.lib.normalize_state_device_ptr(self.h, C.byref(n))
+        return p, n.value
+
+    def last_pass_stats(self) -> dict:
+        st = PassStats()
+        self._chk(self.lib.last_pass_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+
+def render_many(lib: Library, ctxs: Sequence[Context], chunks: Sequence[int], render_sr: Sequence[int],
+                bitdepth: Sequence[int], want_pcm: bool = True, outs: Optional[Sequence[np.ndarray]] = None):
+    """tdg_render_many: one merged device schedule for `ctxs` (independent projects)."""
+    n = len(ctxs)
+    hs = (C.c_void_p * n)(*[c.h for c in ctxs])
+    ch = (C.c_uint64 * n)(*chunks)
+    rs = (C.c_uint32 * n)(*render_sr)
+    bd = (C.c_uint32 * n)(*bitdepth)
+    fw = (C.c_uint64 * n)()
+    if want_pcm:
+        caps = [int(lib.render_bound_bytes(ctxs[i].h, chunks[i], render_sr[i], bitdepth[i])) for i in range(n)]
+        if outs is None:
+            outs = [np.empty(c, np.uint8) for c in caps]
+        ptrs = (c_u8p * n)(*[_p(o, c_u8p) for o in outs])
+        cp = (C.c_uint64 * n)(*caps)
+        rc = lib.render_many(hs, n, ch, rs, bd, ptrs, cp, fw)
+    else:
+        rc = lib.render_many(hs, n, ch, rs, bd, None, None, fw)
+    if rc < 0:
+        msgs = [(lib.last_error(c.h) or b"").decode() for c in ctxs]
+        raise TermdawError(rc, next((m for m in msgs if m), ""))
+    if want_pcm:
+        return [outs[i][: fw[i] * 2 * (bitdepth[i] // 8)] for i in range(n)]
+    return [int(x) for x in fw]
+
+
+def normalize_scan_many(lib: Library, ctxs: Sequence[Context], chunks: Sequence[int]):
+    n = len(ctxs)
+    hs = (C.c_void_p * n)(*[c.h for c in ctxs])
+    ch = (C.c_uint64 * n)(*chunks)
+    rc = lib.normalize_scan_many(hs, n, ch)
+    if rc < 0:
+        msgs = [(lib.last_error(c.h) or b"").decode() for c in ctxs]
+        raise TermdawError(rc, next((m for m in msgs if m), ""))
