@@ -152,15 +152,19 @@ int tdg_read_vertex_buffer(tdg_ctx* ctx, int vertex, uint64_t frame0, uint64_t n
                            float* l, float* r);
 
 /* ---- time sharding -----------------------------------------------------------
- * Render chunks [chunk0, chunk0+chunks) of a pass that started at the current transport position:
- * the event-driven vertex state at chunk0 is rebuilt by replaying the floww events (and the per-chunk
- * f32 clock additions) from the pass start without rendering audio; `warmup_chunks` extra chunks are
- * rendered before chunk0 and discarded so that band-pass state has converged at the boundary.
- * Normalize peaks are exchanged by the caller (NCCL max-allreduce) through the two calls below. */
-int tdg_scan_segment(tdg_ctx* ctx, uint64_t chunk0, uint64_t chunks, uint64_t warmup_chunks);
-int tdg_render_segment(tdg_ctx* ctx, uint64_t chunk0, uint64_t chunks, uint64_t warmup_chunks,
-                       uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes,
-                       uint64_t* frames_written);
+ * Evaluate chunks [chunk0, chunk0+chunks) of a pass of `total_chunks` chunks that starts at the
+ * current transport position.  The event-driven vertex state at chunk0 is rebuilt by replaying the
+ * floww events (and the per-chunk f32 clock additions) from the pass start without rendering audio,
+ * and after the call the context's state is what a FULL pass would have left (so that a render after
+ * a sharded scan starts from the same leaked state as the reference, graph.rs:228-236).
+ * `warmup_chunks` extra chunks are rendered before chunk0 and discarded so that band-pass state has
+ * converged at the boundary.  Normalize peaks are combined by the caller with an NCCL max-allreduce
+ * over tdg_normalize_state_device_ptr().  No render-time resampling in segment mode. */
+int tdg_scan_segment(tdg_ctx* ctx, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks,
+                     uint64_t warmup_chunks);
+int tdg_render_segment(tdg_ctx* ctx, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks,
+                       uint64_t warmup_chunks, uint32_t bitdepth, uint8_t* out_pcm,
+                       uint64_t cap_bytes, uint64_t* frames_written);
 /* Normalize state as (max, scan_max) pairs, one per vertex (non-normalize vertices: -1, -1). */
 int tdg_get_normalize_state(tdg_ctx* ctx, float* max_out, float* scan_max_out, int cap);
 int tdg_set_normalize_state(tdg_ctx* ctx, const float* max_in, const float* scan_max_in, int n);

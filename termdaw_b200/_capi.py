@@ -103,8 +103,8 @@ class Library:
     }
     # symbols only the CUDA library has (time sharding + measurement)
     GPU_ONLY = {
-        "scan_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
-        "render_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, c_u8p,
+        "scan_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+        "render_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, c_u8p,
                                      C.c_uint64, c_u64p]),
         "set_normalize_state": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int]),
         "normalize_state_device_ptr": (C.c_void_p, [C.c_void_p, c_i32p]),
@@ -294,14 +294,15 @@ class Context:
         return mx, sm
 
     # -- CUDA library only
-    def scan_segment(self, chunk0: int, chunks: int, warmup_chunks: int):
-        self._chk(self.lib.scan_segment(self.h, chunk0, chunks, warmup_chunks))
+    def scan_segment(self, total_chunks: int, chunk0: int, chunks: int, warmup_chunks: int):
+        self._chk(self.lib.scan_segment(self.h, total_chunks, chunk0, chunks, warmup_chunks))
 
-    def render_segment(self, chunk0: int, chunks: int, warmup_chunks: int, bitdepth: int, want_pcm=True):
+    def render_segment(self, total_chunks: int, chunk0: int, chunks: int, warmup_chunks: int, bitdepth: int,
+                       want_pcm=True):
         cap = chunks * self.bl * 2 * (bitdepth // 8)
         frames = C.c_uint64(0)
         out = np.empty(cap if want_pcm else 0, np.uint8)
-        self._chk(self.lib.render_segment(self.h, chunk0, chunks, warmup_chunks, bitdepth,
+        self._chk(self.lib.render_segment(self.h, total_chunks, chunk0, chunks, warmup_chunks, bitdepth,
                                           _p(out, c_u8p) if want_pcm else None, cap, C.byref(frames)))
         return out[: frames.value * 2 * (bitdepth // 8)] if want_pcm else None
 

@@ -1,0 +1,51 @@
+"""In-tree build of libtermdaw_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCES = ["kernels.cu", "engine.cu"]
+HEADERS = ["tdg_types.h", "tdg_math.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "termdaw_b200.h")]
+OUT = os.path.join(HERE, "libtermdaw_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# -fmad=false / -ffp-contract=off: the reference rounds after every f32 operation (DESIGN.md "arithmetic")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+         "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math"]
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    objs = []
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        os.makedirs(os.path.dirname(obj), exist_ok=True)
+        objs.append(obj)
+        if force or _stale(obj, [src] + HEADERS):
+            jobs.append([NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj])
+    if jobs:
+        def run(cmd):
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            subprocess.check_call(cmd)
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            list(ex.map(run, jobs))
+    if jobs or not os.path.exists(OUT):
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT, *objs]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

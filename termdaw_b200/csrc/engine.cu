@@ -1,0 +1,1303 @@
+// engine.cu — device graph executor, host planner and the C ABI of include/termdaw_b200.h.
+//
+// Replaces graph.rs's per-buffer_length vertex evaluation (graph.rs:98-121,182-237) with a
+// whole-pass schedule: reachable vertices are grouped by DAG depth, every vertex buffer lives in HBM
+// for the pass, and each (depth, kernel class) pair is ONE launch covering all projects of the
+// batch.  Host work is limited to control data: floww events -> integer frames and per-chunk voice /
+// envelope tables (the sequential f32 clock additions of extensions.rs:525-527,649-650 are replayed
+// here, exactly), and glibc powf/cosf/sinf for per-voice / per-vertex constants.  No audio sample is
+// ever computed on the host; without a CUDA device every entry point fails with TDG_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <chrono>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/termdaw_b200.h"
+#include "engine.h"
+#include "kernels.h"
+#include "tdg_math.cuh"
+
+namespace tdg {
+
+static const float kE = 2.71828182845904523536f;
+static const float kFrac1Sqrt2 = 0.70710678118654752440f;
+
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+// Rust `f32 as usize`
+static inline uint64_t f32_as_usize(float x) {
+    if (!(x == x) || x <= 0.0f) return 0;
+    if (x >= 18446744073709551616.0f) return UINT64_MAX;
+    return (uint64_t)x;
+}
+
+// ------------------------------------------------------------------------------------ engine
+struct DevBuf {
+    uint8_t* p = nullptr; uint64_t cap = 0;
+    cudaError_t ensure(uint64_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        uint64_t want = align_up(bytes + bytes / 8, 1 << 20);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+};
+struct PinnedBuf {                 // growable pinned staging buffer for the plan blob
+    uint8_t* p = nullptr; uint64_t cap = 0, size = 0;
+    bool reserve(uint64_t bytes) {
+        if (bytes <= cap) return true;
+        uint64_t want = std::max<uint64_t>(align_up(bytes, 1 << 20), cap * 2);
+        uint8_t* q = nullptr;
+        if (cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess) return false;
+        if (p) { memcpy(q, p, size); cudaFreeHost(p); }
+        p = q; cap = want;
+        return true;
+    }
+    // returns the byte offset of `bytes` fresh bytes aligned to 16
+    uint64_t alloc(uint64_t bytes) {
+        uint64_t off = align_up(size, 16);
+        if (!reserve(off + bytes)) return UINT64_MAX;
+        if (off > size) memset(p + size, 0, off - size);
+        size = off + bytes;
+        return off;
+    }
+    template <typename T> T* at(uint64_t off) { return reinterpret_cast<T*>(p + off); }
+};
+
+struct Engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf work, blob_dev;
+    PinnedBuf blob;
+    std::map<uint32_t, float*> sinc_tables;     // keyed by the f32 bits of the cutoff
+    uint64_t epoch = 0;                          // bumped by every pass (taps of older passes are stale)
+    int refs = 0;
+};
+static std::mutex g_mu;
+static std::map<int, Engine*> g_engines;
+
+static Engine* engine_get(int device, std::string* err) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_engines.find(device);
+    if (it != g_engines.end()) { it->second->refs++; return it->second; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { *err = std::string("no CUDA device: ") + cudaGetErrorString(e); return nullptr; }
+    if (device < 0 || device >= n) { *err = "device index out of range"; return nullptr; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { *err = cudaGetErrorString(e); return nullptr; }
+    if (prop.major != 10) {
+        *err = "termdaw_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return nullptr;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { *err = cudaGetErrorString(e); return nullptr; }
+    Engine* g = new Engine();
+    g->device = device;
+    if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess) {
+        *err = "could not create stream/events"; delete g; return nullptr;
+    }
+    g->refs = 1;
+    g_engines[device] = g;
+    return g;
+}
+
+#define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return c->fail(TDG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } while (0)
+
+// ------------------------------------------------------------------------------------ sinc table
+// rubato make_sincs (BlackmanHarris2, f32) — see DESIGN.md "resampler"; [UNVERIFIED-RECALL] upstream.
+static void build_sinc_table(float cutoff, std::vector<float>& out) {
+    const size_t npoints = 256, factor = 256, tot = npoints * factor;
+    std::vector<float> y(tot);
+    const float pi = TDG_PI_F, pi2 = 2.0f * pi, pi4 = 4.0f * pi, pi6 = 6.0f * pi, np_f = (float)tot;
+    float sum = 0.0f;
+    for (size_t x = 0; x < tot; ++x) {
+        const float xf = (float)x;
+        float w = 0.35875f - 0.48829f * cosf(pi2 * xf / np_f) + 0.14128f * cosf(pi4 * xf / np_f) -
+                  0.01168f * cosf(pi6 * xf / np_f);
+        w = w * w;
+        const float v = (xf - (float)(tot / 2)) * cutoff / (float)factor;
+        float s = 1.0f;
+        if (v != 0.0f) { const float a = v * pi; s = sinf(a) / a; }
+        const float val = w * s;
+        sum += val;
+        y[x] = val;
+    }
+    sum /= (float)factor;
+    out.assign(tot, 0.0f);
+    for (size_t p = 0; p < npoints; ++p)
+        for (size_t n = 0; n < factor; ++n) out[(factor - n - 1) * npoints + p] = y[factor * p + n] / sum;
+}
+static float* sinc_table_dev(Ctx* c, double ratio) {
+    const float cutoff = ratio >= 1.0 ? 0.95f : 0.95f * (float)ratio;
+    uint32_t key; memcpy(&key, &cutoff, 4);
+    Engine* g = c->eng;
+    auto it = g->sinc_tables.find(key);
+    if (it != g->sinc_tables.end()) return it->second;
+    std::vector<float> tab;
+    build_sinc_table(cutoff, tab);
+    float* d = nullptr;
+    if (cudaMalloc(&d, tab.size() * 4) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    g->sinc_tables[key] = d;
+    return d;
+}
+// exact f64 replay of SincFixedIn's index loop: per call, how many frames come out and where it starts
+static void resample_replay(double ratio, uint64_t chunk, uint64_t n_chunks, std::vector<ResampleChunk>& out, uint64_t* total) {
+    const double t_ratio = 1.0 / ratio;
+    const int64_t end_idx = (int64_t)chunk - 257 - (int64_t)ceil(t_ratio);
+    double last = -128.0;
+    uint64_t off = 0;
+    out.resize(n_chunks);
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        double idx = last; uint32_t n = 0;
+        while (idx < (double)end_idx) { idx += t_ratio; ++n; }
+        out[k].last_index = last; out[k].out_off = off; out[k].n_out = n; out[k].pad = 0;
+        off += n;
+        last = idx - (double)chunk;
+    }
+    *total = off;
+}
+
+// ------------------------------------------------------------------------------------ vertex state sync
+static int vstate_to_host(Ctx* c) {
+    if (c->vstate_host_newer || !c->vstate_dev) return TDG_OK;
+    cudaSetDevice(c->eng->device);
+    size_t n = std::min(c->vstate_cap, c->vstate_host.size());
+    CU(cudaMemcpyAsync(c->vstate_host.data(), c->vstate_dev, n * 4, cudaMemcpyDeviceToHost, c->eng->stream));
+    CU(cudaStreamSynchronize(c->eng->stream));
+    return TDG_OK;
+}
+static int vstate_to_dev(Ctx* c) {
+    const size_t need = c->verts.size() * 8;
+    if (c->vstate_host.size() != need) c->vstate_host.resize(need, 0.0f);
+    if (c->vstate_cap < need || !c->vstate_dev) {
+        if (int r = vstate_to_host(c)) return r;
+        if (c->vstate_dev) cudaFree(c->vstate_dev);
+        c->vstate_dev = nullptr;
+        CU(cudaMalloc(&c->vstate_dev, std::max<size_t>(need, 8) * 4));
+        c->vstate_cap = std::max<size_t>(need, 8);
+        c->vstate_host_newer = true;
+    }
+    if (c->vstate_host_newer && need) {
+        CU(cudaMemcpyAsync(c->vstate_dev, c->vstate_host.data(), need * 4, cudaMemcpyHostToDevice, c->eng->stream));
+        CU(cudaStreamSynchronize(c->eng->stream));   // vstate_host may be touched right after
+    }
+    c->vstate_host_newer = false;
+    return TDG_OK;
+}
+
+// ------------------------------------------------------------------------------------ planner
+struct PassParams {
+    uint64_t F0;        // FlowwBank.frame at pass chunk 0
+    uint64_t t0;        // graph time handed to generate() at pass chunk 0
+    uint64_t total;     // chunks of the whole pass (state always advances over all of them)
+    uint64_t emit0, emit_n;   // chunks whose audio is evaluated on this device
+    uint32_t bl, sr;
+};
+
+struct EvCursor {       // events of one floww in pass order (sorted => equals the reference's cursor, floww.rs:70-141)
+    const Floww* f; size_t j;
+    EvCursor(const Floww* fl, uint64_t F0) : f(fl) { j = std::lower_bound(fl->fe.begin(), fl->fe.end(), F0) - fl->fe.begin(); }
+};
+
+static PanGain make_pg(float gain, float angle) {
+    PanGain pg{1.0f, 1.0f, gain, 0};
+    if (!(fabsf(angle) < 0.001f)) {                                 // sample.rs:98-101
+        const float ar = angle * 0.5f * 0.01745329f;
+        pg.l_amp = kFrac1Sqrt2 * (cosf(ar) + sinf(ar));
+        pg.r_amp = kFrac1Sqrt2 * (cosf(ar) - sinf(ar));
+        pg.flags |= 1u;
+    }
+    if (!(fabsf(gain - 1.0f) < 0.001f)) pg.flags |= 2u;             // sample.rs:109
+    return pg;
+}
+static inline float note_hz(float note) { return 440.0f * powf(2.0f, (note - 69.0f) / 12.0f); }   // extensions.rs:451
+
+// get_block_drum over one chunk (floww.rs:99-121): first event of a frame with vel > 0.001 is the hit
+template <typename F>
+static void drum_chunk(EvCursor& cur, uint64_t Fk, uint32_t bl, F&& on_hit) {
+    const Floww& f = *cur.f;
+    uint64_t done = UINT64_MAX;
+    while (cur.j < f.fe.size() && f.fe[cur.j] < Fk + bl) {
+        const size_t j = cur.j++;
+        if (f.fe[j] < Fk || f.fe[j] == done) continue;
+        if (f.vel[j] > 0.001f) { done = f.fe[j]; on_hit((uint32_t)(f.fe[j] - Fk), f.note[j], f.vel[j]); }
+    }
+}
+// get_block_simple over one chunk (floww.rs:124-141): every event, in order
+template <typename F>
+static void simple_chunk(EvCursor& cur, uint64_t Fk, uint32_t bl, F&& on_ev) {
+    const Floww& f = *cur.f;
+    while (cur.j < f.fe.size() && f.fe[cur.j] < Fk + bl) {
+        const size_t j = cur.j++;
+        if (f.fe[j] < Fk) continue;
+        on_ev((uint32_t)(f.fe[j] - Fk), f.vel[j] > 0.001f, f.note[j], f.vel[j]);
+    }
+}
+static inline bool note_ok(const HVertex& v, float note) {          // extensions.rs:353-356
+    return v.has_note ? fabsf(note - (float)v.note) < 0.01f : true;
+}
+
+// sample_multi_gen: hit list for the pass + end-of-pass deque (extensions.rs:344-381)
+static void plan_multi(HVertex& v, const Floww& fl, uint64_t L, const PassParams& pp, std::vector<MultiHit>& hits) {
+    hits.clear();
+    for (const MultiEntry& e : v.ts) hits.push_back({-e.t, e.vel, 0.0f});
+    EvCursor cur(&fl, pp.F0);
+    for (uint64_t k = 0; k < pp.total; ++k)
+        drum_chunk(cur, pp.F0 + k * pp.bl, pp.bl, [&](uint32_t i, float note, float vel) {
+            if (note_ok(v, note)) hits.push_back({(int64_t)(k * pp.bl + i), vel, 0.0f});
+        });
+    const int64_t n = (int64_t)(pp.total * pp.bl);
+    v.ts.clear();
+    for (const MultiHit& h : hits) if (h.start + (int64_t)L >= n) v.ts.push_back({n - h.start, h.vel});
+    const int64_t shift = (int64_t)(pp.emit0 * pp.bl);
+    if (shift) for (MultiHit& h : hits) h.start -= shift;
+}
+// sample_lerp_gen (extensions.rs:384-421): [carried ghost, carried primary, hits...]
+static void plan_lerp(HVertex& v, const Floww& fl, const PassParams& pp, std::vector<LerpHit>& hits) {
+    hits.clear();
+    const int64_t far = INT64_MIN / 4;
+    hits.push_back({far, -v.ghost.t, far, v.ghost.vel, 0.0f});
+    hits.push_back({far + 1, -v.primary.t, (int64_t)v.countdown - (int64_t)v.lerp_len, v.primary.vel, 0.0f});
+    EvCursor cur(&fl, pp.F0);
+    for (uint64_t k = 0; k < pp.total; ++k)
+        drum_chunk(cur, pp.F0 + k * pp.bl, pp.bl, [&](uint32_t i, float note, float vel) {
+            if (note_ok(v, note)) { const int64_t p = (int64_t)(k * pp.bl + i); hits.push_back({p, p, p, vel, 0.0f}); }
+        });
+    const int64_t n = (int64_t)(pp.total * pp.bl);
+    const LerpHit &P = hits[hits.size() - 1], &G = hits[hits.size() - 2];
+    v.primary = {n - P.pos_origin, P.vel};
+    v.ghost = {n - G.pos_origin, G.vel};
+    const int64_t cd = (int64_t)v.lerp_len - (n - P.cd_origin);
+    v.countdown = cd > 0 ? (uint64_t)cd : 0;
+    const int64_t shift = (int64_t)(pp.emit0 * pp.bl);
+    if (shift) for (size_t h = 0; h < hits.size(); ++h) {
+        if (h >= 2) hits[h].frame -= shift;
+        hits[h].pos_origin -= shift; hits[h].cd_origin -= shift;
+    }
+}
+
+struct SegOut {                     // per-chunk CSR of voice / envelope segments
+    std::vector<uint32_t> ptr;
+    std::vector<VoiceSeg> vseg;
+    std::vector<AdsrSeg> aseg;
+    uint64_t voice_frames = 0;
+};
+struct KeyedSeg { uint64_t seq; VoiceSeg s; };
+
+// debug_sine_gen / synth_gen / sampsyn_gen voice lifecycle (extensions.rs:429-445, 481-496, 525-528)
+static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, SegOut& out) {
+    out.ptr.assign(1, 0); out.vseg.clear(); out.voice_frames = 0;
+    const float fsr = (float)pp.sr;
+    const float d = (float)pp.bl / fsr;                              // len as f32 / sr as f32
+    float release_sec = 0.0f;
+    if (v.kind == K_SYNTH) {                                         // extensions.rs:469-478
+        if (v.sq.volume > 0.0f) release_sec = v.sq.adsr.release_sec;
+        if (v.tf.volume > 0.0f) release_sec = fmaxf(release_sec, v.tf.adsr.release_sec);
+        if (v.tr.volume > 0.0f) release_sec = fmaxf(release_sec, v.tr.adsr.release_sec);
+    } else if (v.kind == K_SAMPSYN) release_sec = v.adsr.release_sec;
+    std::vector<KeyedSeg> chunk;
+    EvCursor cur(&fl, pp.F0);
+    for (uint64_t k = 0; k < pp.total; ++k) {
+        const bool emit = k >= pp.emit0 && k < pp.emit0 + pp.emit_n;
+        chunk.clear();
+        bool had_event = false;
+        auto close_d = [&](DNote& n, uint32_t ib) {
+            if (emit && ib > n.ia) chunk.push_back({n.seq, VoiceSeg{n.hz, n.vel, 0.0f, 0.0f, n.ia, ib, 0, 0}});
+        };
+        auto close_s = [&](SNote& n, uint32_t ib) {
+            if (emit && ib > n.ia) chunk.push_back({n.seq, VoiceSeg{n.hz, n.vel, n.env_t, n.rel_t, n.ia, ib, 0, 0}});
+        };
+        simple_chunk(cur, pp.F0 + k * pp.bl, pp.bl, [&](uint32_t i, bool on, float note, float vel) {
+            had_event = true;
+            const float fi = (float)i / fsr;
+            if (v.kind == K_DEBUG_SINE) {
+                if (on) {
+                    bool has = false;
+                    for (DNote& n : v.dnotes)
+                        if (fabsf(n.note - note) < 0.001f) { close_d(n, i); n.vel = vel; n.ia = i; has = true; break; }
+                    if (!has) v.dnotes.push_back({note, vel, note_hz(note), v.seq++, i});
+                } else {
+                    size_t w = 0;
+                    for (size_t q = 0; q < v.dnotes.size(); ++q) {
+                        if (fabsf(v.dnotes[q].note - note) > 0.001f) v.dnotes[w++] = v.dnotes[q];
+                        else close_d(v.dnotes[q], i);
+                    }
+                    v.dnotes.resize(w);
+                }
+            } else {
+                if (on) {
+                    v.notes.push_back({note, vel, -fi, 0.0f, note_hz(note), v.seq++, i});
+                } else {
+                    size_t w = 0;
+                    for (size_t q = 0; q < v.notes.size(); ++q) {           // retain (extensions.rs:485)
+                        SNote& n = v.notes[q];
+                        if (fabsf(n.note - note) > 0.001f || n.rel_t == 0.0f) { if (w != q) v.notes[w] = n; ++w; }
+                        else close_s(n, i);
+                    }
+                    v.notes.resize(w);
+                    for (SNote& n : v.notes) {                              // extensions.rs:486-494
+                        if (fabsf(n.note - note) > 0.001f) continue;
+                        if (n.rel_t == 0.0f) {
+                            close_s(n, i);
+                            n.rel_t = n.env_t + fi;
+                            n.env_t = -fi;
+                            n.ia = i;
+                        }
+                    }
+                }
+            }
+        });
+        if (v.kind == K_DEBUG_SINE) {
+            for (DNote& n : v.dnotes) { close_d(n, pp.bl); n.ia = 0; }
+        } else {
+            for (SNote& n : v.notes) { close_s(n, pp.bl); n.ia = 0; }
+            for (SNote& n : v.notes) n.env_t += d;                          // extensions.rs:525-527
+            size_t w = 0;
+            for (size_t q = 0; q < v.notes.size(); ++q)                     // extensions.rs:528
+                if (v.notes[q].rel_t == 0.0f || v.notes[q].env_t <= release_sec) { if (w != q) v.notes[w] = v.notes[q]; ++w; }
+            v.notes.resize(w);
+        }
+        if (emit) {
+            if (had_event)
+                std::stable_sort(chunk.begin(), chunk.end(), [](const KeyedSeg& a, const KeyedSeg& b) {
+                    return a.seq != b.seq ? a.seq < b.seq : a.s.ia < b.s.ia; });
+            for (const KeyedSeg& ks : chunk) { out.vseg.push_back(ks.s); out.voice_frames += ks.s.ib - ks.s.ia; }
+            out.ptr.push_back((uint32_t)out.vseg.size());
+        }
+    }
+}
+
+// adsr_gen state machine (extensions.rs:593-651)
+static void plan_adsr(HVertex& v, const Floww& fl, const PassParams& pp, SegOut& out) {
+    out.ptr.assign(1, 0); out.aseg.clear();
+    const float fsr = (float)pp.sr;
+    const float d = (float)pp.bl / fsr;
+    A3 &P = v.aprimary, &G = v.aghost;
+    EvCursor cur(&fl, pp.F0);
+    for (uint64_t k = 0; k < pp.total; ++k) {
+        const bool emit = k >= pp.emit0 && k < pp.emit0 + pp.emit_n;
+        const size_t base = out.aseg.size();
+        auto push = [&](uint32_t ia, uint32_t flags) {
+            if (!emit || ia >= pp.bl) return;
+            AdsrSeg s{ia, flags, P.t, P.vel, P.rel, G.t, G.vel, G.rel};
+            if (out.aseg.size() > base && out.aseg.back().ia == ia) out.aseg.back() = s; else out.aseg.push_back(s);
+        };
+        push(0, 0);
+        if (v.use_off) {
+            simple_chunk(cur, pp.F0 + k * pp.bl, pp.bl, [&](uint32_t i, bool on, float note, float vel) {
+                if (v.has_note && fabsf((float)v.note - note) > 0.01f) return;
+                const float fi = (float)i / fsr;
+                const float offset = fi;
+                if (on) { G = P; P = {-fi, vel, 0.0f}; }
+                else if (G.rel == 0.0f) { G.t = -fi; G.rel = m_apply_ads(v.adsr, G.t + offset) * G.vel; }
+                else { P.t = -fi; P.rel = m_apply_ads(v.adsr, P.t + offset) * P.vel; }
+                push(i, 0);
+            });
+        } else {
+            drum_chunk(cur, pp.F0 + k * pp.bl, pp.bl, [&](uint32_t i, float note, float vel) {
+                if (v.has_note && fabsf((float)v.note - note) > 0.01f) {    // `continue` on the frame loop
+                    push(i, 1); push(i + 1, 0);
+                    return;
+                }
+                const float fi = (float)i / fsr;
+                G = P; P = {-fi, vel, 0.0f};
+                push(i, 0);
+            });
+        }
+        P.t += d; G.t += d;                                                 // extensions.rs:649-650
+        if (emit) out.ptr.push_back((uint32_t)out.aseg.size());
+    }
+}
+
+// ------------------------------------------------------------------------------------ pass executor
+struct PassReq {
+    Ctx* c = nullptr;
+    bool is_scan = false;
+    uint64_t total = 0, emit0 = 0, emit_n = 0, keep0 = 0;   // keep0: first emitted chunk that is output
+    uint32_t render_sr = 0, bd = 16;
+    uint8_t* out = nullptr; uint64_t cap = 0; uint64_t* frames_written = nullptr;
+    bool segment = false;
+    // derived
+    std::vector<int> level;            // per vertex, -1 unreachable
+    std::vector<int> last_use;
+    std::vector<int64_t> buf_off, aux_off;   // work-arena byte offsets
+    uint64_t n_frames = 0, n_pad = 0;
+    uint64_t pcm_off = 0, pcm_bytes = 0, err_off = 0, rs_off = 0, rs_total = 0;
+    bool resample = false;
+    std::vector<ResampleChunk> rs_chunks;
+    uint64_t out_frames = 0;
+    uint32_t err_flag = 0;
+};
+
+template <typename T> struct TaskList { std::vector<T> v; uint32_t max_chunks = 0; };
+struct LevelTasks {
+    TaskList<FxTask> fx; TaskList<NormPrefixTask> nprefix; TaskList<NormScaleTask> nscale;
+    TaskList<LoopTask> loop; TaskList<MultiTask> multi; TaskList<LerpTask> lerp;
+    TaskList<VoiceTask> dsine, synth, sampsyn; TaskList<BpTask> bp;
+    size_t sampsyn_smem = 0; bool sampsyn_smem_ok = true;
+};
+
+static void compute_levels(PassReq& r) {
+    Ctx* c = r.c;
+    const int V = (int)c->verts.size();
+    r.level.assign(V, -1); r.last_use.assign(V, -1);
+    if (c->output < 0) return;
+    // iterative post-order DFS from the output (graph.rs:98-121 evaluates exactly this set)
+    std::vector<std::pair<int, size_t>> st;
+    std::vector<char> seen(V, 0);
+    st.push_back({c->output, 0}); seen[c->output] = 1;
+    while (!st.empty()) {
+        const int v = st.back().first;
+        const size_t ei = st.back().second;
+        const auto& e = c->verts[v].edges;
+        if (ei < e.size()) { st.back().second++; const int u = e[ei]; if (!seen[u]) { seen[u] = 1; st.push_back({u, 0}); } }
+        else {
+            int lv = 0;
+            for (int u : e) lv = std::max(lv, r.level[u] + 1);
+            r.level[v] = lv;
+            for (int u : e) r.last_use[u] = std::max(r.last_use[u], lv);
+            st.pop_back();
+        }
+    }
+}
+
+struct Bump { uint64_t off = 0; uint64_t alloc(uint64_t bytes) { off = align_up(off, 256); uint64_t r = off; off += bytes; return r; } };
+
+static int run_pass(std::vector<PassReq>& reqs) {
+    if (reqs.empty()) return TDG_OK;
+    Ctx* c = reqs[0].c;                       // error sink for CU()
+    Engine* g = c->eng;
+    for (auto& r : reqs) if (r.c->eng != g) return r.c->fail(TDG_ERR_INVALID, "all contexts of a batch must be on one device");
+    cudaSetDevice(g->device);
+    const double t_start = now_ms();
+    g->epoch++;
+
+    // ---- 1. graph analysis + work-arena layout -------------------------------------------------
+    Bump bump;
+    int max_level = -1;
+    for (auto& r : reqs) {
+        Ctx* x = r.c;
+        compute_levels(r);
+        const int V = (int)x->verts.size();
+        r.n_frames = r.emit_n * x->bl;
+        r.n_pad = align_up(std::max<uint64_t>(r.n_frames, 1), kBpTile);
+        r.buf_off.assign(V, -1); r.aux_off.assign(V, -1);
+        for (int v = 0; v < V; ++v) max_level = std::max(max_level, r.level[v]);
+    }
+    for (auto& r : reqs) {
+        Ctx* x = r.c;
+        const int V = (int)x->verts.size();
+        const uint64_t slot_bytes = r.n_pad * 2 * 4;
+        std::vector<uint64_t> free_slots;
+        std::vector<std::vector<int>> by_level(max_level + 1);
+        for (int v = 0; v < V; ++v) if (r.level[v] >= 0) by_level[r.level[v]].push_back(v);
+        std::vector<char> freed(V, 0);
+        for (int L = 0; L <= max_level; ++L) {
+            for (int v : by_level[L]) {
+                if (!free_slots.empty()) { r.buf_off[v] = (int64_t)free_slots.back(); free_slots.pop_back(); }
+                else r.buf_off[v] = (int64_t)bump.alloc(slot_bytes);
+                const HVertex& hv = x->verts[v];
+                if (hv.kind == K_NORMALIZE) r.aux_off[v] = (int64_t)bump.alloc(r.emit_n * 2 * 4 + 16);     // peaks, runmax
+                if (hv.kind == K_BANDPASS) r.aux_off[v] = (int64_t)bump.alloc((r.n_pad / kBpTile) * 12 * 4 + 16); // agg[8], carry[4]
+            }
+            if (!x->taps)
+                for (int v : by_level[L])
+                    for (int u : x->verts[v].edges)
+                        if (!freed[u] && r.last_use[u] == L && u != x->output) { freed[u] = 1; free_slots.push_back((uint64_t)r.buf_off[u]); }
+        }
+        if (!r.is_scan && x->output >= 0) {
+            r.resample = !r.segment && x->sr > r.render_sr;                    // state.rs:533
+            r.out_frames = (r.emit0 + r.emit_n - r.keep0) * x->bl;
+            if (r.resample) {
+                resample_replay((double)r.render_sr / (double)x->sr, x->bl, r.emit_n, r.rs_chunks, &r.rs_total);
+                r.rs_off = bump.alloc(align_up(r.rs_total, 4) * 2 * 4 + 64);
+                r.out_frames = r.rs_total;
+            }
+            r.pcm_bytes = r.out_frames * 2 * (r.bd / 8);
+            r.pcm_off = bump.alloc(align_up(r.pcm_bytes, 64) + 64);
+            r.err_off = bump.alloc(16);
+        }
+    }
+    CU(g->work.ensure(bump.off + 256));
+    uint8_t* W = g->work.p;
+
+    // ---- 2. plan: tasks + tables into the pinned blob ------------------------------------------
+    std::vector<LevelTasks> levels(max_level + 1);
+    std::vector<QuantTask> quants; uint64_t quant_max = 0;
+    std::vector<ResampleTask> resamps; uint64_t resamp_max = 0;
+    PinnedBuf& B = g->blob;
+    B.size = 0;
+    uint64_t algo_bytes_total = 0;
+    std::vector<MultiHit> mhits; std::vector<LerpHit> lhits; SegOut so;
+    bool all_vec = true;
+    for (auto& r : reqs) {
+        Ctx* x = r.c;
+        if (int e = vstate_to_dev(x)) return e;
+        x->stats = PassStats();
+        const int V = (int)x->verts.size();
+        if (x->bl % 4 != 0) all_vec = false;
+        PassParams pp{r.is_scan ? 0 : x->fb_frame, r.is_scan ? 0 : x->t, r.total, r.emit0, r.emit_n, x->bl, x->sr};
+        // (true_normalize_scan: fb.set_time(0) and t = j*bl, graph.rs:228-231)
+        uint64_t algo = 0;
+        for (int v = 0; v < V; ++v) {
+            if (r.level[v] < 0) continue;
+            HVertex& hv = x->verts[v];
+            LevelTasks& LT = levels[r.level[v]];
+            TaskHdr h;
+            h.out_l = reinterpret_cast<float*>(W + r.buf_off[v]);
+            h.out_r = h.out_l + r.n_pad;
+            h.n_frames = r.n_frames; h.n_chunks = (uint32_t)r.emit_n; h.bl = x->bl;
+            h.pg = make_pg(hv.gain, hv.angle);
+            const uint32_t nch = (uint32_t)r.emit_n;
+            uint64_t in_off = 0;
+            if (hv.has_input()) {
+                in_off = B.alloc(std::max<size_t>(hv.edges.size(), 1) * 2 * sizeof(float*));
+                if (in_off == UINT64_MAX) return x->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
+                const float** ip = B.at<const float*>(in_off);
+                for (size_t a = 0; a < hv.edges.size(); ++a) {
+                    const float* il = reinterpret_cast<const float*>(W + r.buf_off[hv.edges[a]]);
+                    ip[2 * a] = il; ip[2 * a + 1] = il + r.n_pad;
+                }
+            }
+            const uint64_t io_bytes = 8ull * (hv.edges.size() + 1) * r.n_frames;
+            auto fx_task = [&](uint32_t mode) {
+                FxTask t; memset(&t, 0, sizeof t);
+                t.h = h; t.mode = mode; t.n_in = (uint32_t)hv.edges.size(); t.in_off = in_off; t.sr = x->sr;
+                return t;
+            };
+            switch (hv.kind) {
+                case K_SUM: { LT.fx.v.push_back(fx_task(FX_SUM)); LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch); algo += io_bytes; break; }
+                case K_NORMALIZE: {
+                    FxTask t = fx_task(FX_NORM_PEAK);
+                    float* peaks = reinterpret_cast<float*>(W + r.aux_off[v]);
+                    float* runmax = peaks + r.emit_n;
+                    t.peaks = peaks;
+                    LT.fx.v.push_back(t); LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch);
+                    NormPrefixTask np{peaks, runmax, x->vstate_dev + (size_t)v * 8, nch, r.is_scan ? 1u : 0u};
+                    LT.nprefix.v.push_back(np);
+                    NormScaleTask ns; ns.h = h; ns.runmax = runmax;
+                    LT.nscale.v.push_back(ns); LT.nscale.max_chunks = std::max(LT.nscale.max_chunks, nch);
+                    algo += io_bytes + 16ull * r.n_frames;
+                    break;
+                }
+                case K_ADSR: {
+                    if (hv.wet < 0.0001f) { LT.fx.v.push_back(fx_task(FX_SUM)); }      // extensions.rs:598
+                    else {
+                        plan_adsr(hv, x->flowws[hv.floww], pp, so);
+                        FxTask t = fx_task(FX_ADSR);
+                        t.conf = hv.adsr; t.wet = hv.wet; t.use_off = hv.use_off; t.use_max = hv.use_max;
+                        t.seg_ptr_off = B.alloc(so.ptr.size() * 4);
+                        memcpy(B.at<uint8_t>(t.seg_ptr_off), so.ptr.data(), so.ptr.size() * 4);
+                        t.seg_off = B.alloc(std::max<size_t>(so.aseg.size(), 1) * sizeof(AdsrSeg));
+                        memcpy(B.at<uint8_t>(t.seg_off), so.aseg.data(), so.aseg.size() * sizeof(AdsrSeg));
+                        LT.fx.v.push_back(t);
+                    }
+                    LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch); algo += io_bytes;
+                    break;
+                }
+                case K_BANDPASS: {
+                    if (hv.wet < 0.0001f || (hv.lgamma == 0.0f && hv.hgamma == 0.0f)) {   // extensions.rs:657-658
+                        LT.fx.v.push_back(fx_task(FX_SUM)); LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch);
+                        algo += io_bytes;
+                        break;
+                    }
+                    BpTask t; memset(&t, 0, sizeof t);
+                    t.h = h; t.n_in = (uint32_t)hv.edges.size(); t.in_off = in_off; t.pass = hv.pass;
+                    t.lgamma = hv.lgamma; t.hgamma = hv.hgamma;
+                    // a segment that does not start at the pass start has no true state: seed from its first frame
+                    t.first = (hv.bp_first || r.emit0 > 0) ? 1u : 0u;
+                    t.n_tiles = (uint32_t)((r.n_frames + kBpTile - 1) / kBpTile);
+                    t.state = x->vstate_dev + (size_t)v * 8 + 2;
+                    t.agg = reinterpret_cast<float*>(W + r.aux_off[v]);
+                    t.carry = t.agg + (size_t)(r.n_pad / kBpTile) * 8;
+                    LT.bp.v.push_back(t); LT.bp.max_chunks = std::max(LT.bp.max_chunks, t.n_tiles);
+                    hv.bp_first = false;
+                    algo += io_bytes + 8ull * hv.edges.size() * r.n_frames;     // inputs are read by both scan passes
+                    break;
+                }
+                case K_SAMPLE_LOOP: {
+                    const DevSample& s = x->samples[hv.sample];
+                    LoopTask t; t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.t0 = hv.loop_t + r.emit0 * x->bl;
+                    LT.loop.v.push_back(t); LT.loop.max_chunks = std::max(LT.loop.max_chunks, nch);
+                    hv.loop_t += r.total * x->bl;                                 // extensions.rs:340
+                    algo += 16ull * r.n_frames;
+                    break;
+                }
+                case K_SAMPLE_MULTI: {
+                    const DevSample& s = x->samples[hv.sample];
+                    plan_multi(hv, x->flowws[hv.floww], s.frames, pp, mhits);
+                    MultiTask t; memset(&t, 0, sizeof t);
+                    t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.n_hits = (uint32_t)mhits.size();
+                    t.hits_off = B.alloc(std::max<size_t>(mhits.size(), 1) * sizeof(MultiHit));
+                    memcpy(B.at<uint8_t>(t.hits_off), mhits.data(), mhits.size() * sizeof(MultiHit));
+                    LT.multi.v.push_back(t); LT.multi.max_chunks = std::max(LT.multi.max_chunks, nch);
+                    uint64_t gathered = 0;                                        // live hit-frames inside the emitted range
+                    for (const MultiHit& mh : mhits) {
+                        int64_t a = std::max<int64_t>(mh.start, 0), b = std::min<int64_t>(mh.start + (int64_t)s.frames, (int64_t)r.n_frames);
+                        if (b > a) gathered += (uint64_t)(b - a);
+                    }
+                    algo += 8ull * r.n_frames + 8ull * gathered;
+                    break;
+                }
+                case K_SAMPLE_LERP: {
+                    const DevSample& s = x->samples[hv.sample];
+                    plan_lerp(hv, x->flowws[hv.floww], pp, lhits);
+                    LerpTask t; memset(&t, 0, sizeof t);
+                    t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.n_hits = (uint32_t)lhits.size(); t.lerp_len = hv.lerp_len;
+                    t.hits_off = B.alloc(lhits.size() * sizeof(LerpHit));
+                    memcpy(B.at<uint8_t>(t.hits_off), lhits.data(), lhits.size() * sizeof(LerpHit));
+                    LT.lerp.v.push_back(t); LT.lerp.max_chunks = std::max(LT.lerp.max_chunks, nch);
+                    algo += 16ull * r.n_frames;
+                    break;
+                }
+                case K_DEBUG_SINE: case K_SYNTH: case K_SAMPSYN: {
+                    plan_voices(hv, x->flowws[hv.floww], pp, so);
+                    VoiceTask t; memset(&t, 0, sizeof t);
+                    t.h = h; t.sr = x->sr; t.t0 = pp.t0 + r.emit0 * x->bl;
+                    t.seg_ptr_off = B.alloc(so.ptr.size() * 4);
+                    memcpy(B.at<uint8_t>(t.seg_ptr_off), so.ptr.data(), so.ptr.size() * 4);
+                    t.seg_off = B.alloc(std::max<size_t>(so.vseg.size(), 1) * sizeof(VoiceSeg));
+                    memcpy(B.at<uint8_t>(t.seg_off), so.vseg.data(), so.vseg.size() * sizeof(VoiceSeg));
+                    x->stats.voice_frames += so.voice_frames;
+                    if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nch); }
+                    else if (hv.kind == K_SYNTH) {
+                        t.kind = VOICE_SYNTH;
+                        t.sq_vol = hv.sq.volume; t.sq_z = hv.sq.param; t.tf_vol = hv.tf.volume; t.tf_z = hv.tf.param;
+                        t.tr_vol = hv.tr.volume; t.sq = hv.sq.adsr; t.tf = hv.tf.adsr; t.tr = hv.tr.adsr;
+                        t.amp_mul = 1.0f / (hv.sq.volume * m_max_vel(hv.sq.adsr) + hv.tf.volume * m_max_vel(hv.tf.adsr) +
+                                            hv.tr.volume * m_max_vel(hv.tr.adsr));           // extensions.rs:465-468
+                        LT.synth.v.push_back(t); LT.synth.max_chunks = std::max(LT.synth.max_chunks, nch);
+                    } else {
+                        const DevTable& tb = x->tables[hv.table];
+                        t.kind = VOICE_SAMPSYN; t.adsr = hv.adsr; t.amp_mul = 1.0f / m_max_vel(hv.adsr);   // extensions.rs:537
+                        t.table = tb.data; t.n_frames = tb.n_frames; t.n_phase = tb.n_phase; t.fps = tb.fps;
+                        const size_t tb_bytes = (size_t)tb.n_frames * tb.n_phase * 4;
+                        if (tb_bytes > 160 * 1024) LT.sampsyn_smem_ok = false;
+                        LT.sampsyn_smem = std::max(LT.sampsyn_smem, tb_bytes);
+                        LT.sampsyn.v.push_back(t); LT.sampsyn.max_chunks = std::max(LT.sampsyn.max_chunks, nch);
+                    }
+                    algo += 8ull * r.n_frames;
+                    break;
+                }
+            }
+        }
+        // output stage (state.rs:515-574)
+        if (!r.is_scan && x->output >= 0) {
+            const float* ol = reinterpret_cast<const float*>(W + r.buf_off[x->output]);
+            const float* orr = ol + r.n_pad;
+            QuantTask q; memset(&q, 0, sizeof q);
+            q.bd = r.bd;
+            q.amp = r.bd < 32 ? (float)((1 << (r.bd - 1)) - 1) : (float)INT32_MAX;
+            q.out = W + r.pcm_off; q.err = reinterpret_cast<uint32_t*>(W + r.err_off);
+            if (r.resample) {
+                ResampleTask rt; memset(&rt, 0, sizeof rt);
+                rt.in_l = ol; rt.in_r = orr;
+                rt.out_l = reinterpret_cast<float*>(W + r.rs_off); rt.out_r = rt.out_l + align_up(r.rs_total, 4);
+                rt.sincs = sinc_table_dev(x, (double)r.render_sr / (double)x->sr);
+                if (!rt.sincs) return x->fail(TDG_ERR_CUDA, "could not build the sinc table");
+                rt.n_in = r.n_frames; rt.n_chunks = (uint32_t)r.emit_n; rt.chunk = x->bl;
+                rt.t_ratio = 1.0 / ((double)r.render_sr / (double)x->sr);
+                rt.chunk_off = B.alloc(std::max<size_t>(r.rs_chunks.size(), 1) * sizeof(ResampleChunk));
+                memcpy(B.at<uint8_t>(rt.chunk_off), r.rs_chunks.data(), r.rs_chunks.size() * sizeof(ResampleChunk));
+                resamps.push_back(rt); resamp_max = std::max(resamp_max, r.rs_total);
+                q.in_l = rt.out_l; q.in_r = rt.out_r; q.n = r.rs_total;
+                algo += 8ull * r.n_frames + 8ull * r.rs_total;
+            } else {
+                const uint64_t skip = (r.keep0 - r.emit0) * x->bl;
+                q.in_l = ol + skip; q.in_r = orr + skip; q.n = r.out_frames;
+            }
+            quants.push_back(q); quant_max = std::max(quant_max, q.n);
+            algo += 8ull * q.n + r.pcm_bytes;
+        }
+        x->stats.algorithmic_bytes = algo; x->stats.frames = r.n_frames;
+        algo_bytes_total += algo;
+        x->last_buf_off = r.buf_off; x->last_n_frames = r.n_frames; x->last_n_pad = r.n_pad; x->last_epoch = g->epoch;
+    }
+    // task arrays go into the blob too: one H2D for the whole pass
+    struct Off { uint64_t fx, nprefix, nscale, loop, multi, lerp, dsine, synth, sampsyn, bp; };
+    std::vector<Off> offs(levels.size());
+    auto put = [&](const void* src, size_t bytes) -> uint64_t {
+        uint64_t o = B.alloc(std::max<size_t>(bytes, 16));
+        if (o != UINT64_MAX && bytes) memcpy(B.p + o, src, bytes);
+        return o;
+    };
+    for (size_t L = 0; L < levels.size(); ++L) {
+        LevelTasks& T = levels[L];
+        offs[L].fx = put(T.fx.v.data(), T.fx.v.size() * sizeof(FxTask));
+        offs[L].nprefix = put(T.nprefix.v.data(), T.nprefix.v.size() * sizeof(NormPrefixTask));
+        offs[L].nscale = put(T.nscale.v.data(), T.nscale.v.size() * sizeof(NormScaleTask));
+        offs[L].loop = put(T.loop.v.data(), T.loop.v.size() * sizeof(LoopTask));
+        offs[L].multi = put(T.multi.v.data(), T.multi.v.size() * sizeof(MultiTask));
+        offs[L].lerp = put(T.lerp.v.data(), T.lerp.v.size() * sizeof(LerpTask));
+        offs[L].dsine = put(T.dsine.v.data(), T.dsine.v.size() * sizeof(VoiceTask));
+        offs[L].synth = put(T.synth.v.data(), T.synth.v.size() * sizeof(VoiceTask));
+        offs[L].sampsyn = put(T.sampsyn.v.data(), T.sampsyn.v.size() * sizeof(VoiceTask));
+        offs[L].bp = put(T.bp.v.data(), T.bp.v.size() * sizeof(BpTask));
+    }
+    const uint64_t quant_off = put(quants.data(), quants.size() * sizeof(QuantTask));
+    const uint64_t resamp_off = put(resamps.data(), resamps.size() * sizeof(ResampleTask));
+    if (quant_off == UINT64_MAX || resamp_off == UINT64_MAX) return c->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
+    const double t_planned = now_ms();
+
+    // ---- 3. upload + launches ------------------------------------------------------------------
+    CU(g->blob_dev.ensure(B.size + 256));
+    const uint8_t* D = g->blob_dev.p;
+    cudaStream_t s = g->stream;
+    CU(cudaMemcpyAsync(g->blob_dev.p, B.p, B.size, cudaMemcpyHostToDevice, s));
+    for (auto& r : reqs) if (!r.is_scan && r.c->output >= 0) CU(cudaMemsetAsync(W + r.err_off, 0, 4, s));
+    const double t_h2d_issued = now_ms();
+    CU(cudaEventRecord(g->ev0, s));
+    uint64_t launches = 0;
+    const uint32_t kMaxY = 65535;
+    // gridDim.y is limited to 65535 tasks per launch
+#define LAUNCH_SPLIT(list, T, off, expr) \
+    for (size_t b0 = 0; b0 < (list).v.size(); b0 += kMaxY) { \
+        const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, (list).v.size() - b0); \
+        const T* tp = reinterpret_cast<const T*>(D + (off)) + b0; \
+        CU(expr); ++launches; }
+    for (size_t L = 0; L < levels.size(); ++L) {
+        LevelTasks& T = levels[L];
+        const bool vec = all_vec;
+        LAUNCH_SPLIT(T.loop, LoopTask, offs[L].loop, launch_sample_loop(tp, nb, T.loop.max_chunks, vec, s));
+        LAUNCH_SPLIT(T.multi, MultiTask, offs[L].multi, launch_sample_multi(tp, nb, T.multi.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(T.lerp, LerpTask, offs[L].lerp, launch_sample_lerp(tp, nb, T.lerp.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(T.dsine, VoiceTask, offs[L].dsine, launch_voice(VOICE_DEBUG_SINE, tp, nb, T.dsine.max_chunks, vec, 0, D, s));
+        LAUNCH_SPLIT(T.synth, VoiceTask, offs[L].synth, launch_voice(VOICE_SYNTH, tp, nb, T.synth.max_chunks, vec, 0, D, s));
+        LAUNCH_SPLIT(T.sampsyn, VoiceTask, offs[L].sampsyn,
+                     launch_voice(VOICE_SAMPSYN, tp, nb, T.sampsyn.max_chunks, vec, T.sampsyn_smem_ok ? T.sampsyn_smem : 0, D, s));
+        LAUNCH_SPLIT(T.fx, FxTask, offs[L].fx, launch_fx(tp, nb, T.fx.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(T.nprefix, NormPrefixTask, offs[L].nprefix, launch_norm_prefix(tp, nb, s));
+        LAUNCH_SPLIT(T.nscale, NormScaleTask, offs[L].nscale, launch_norm_scale(tp, nb, T.nscale.max_chunks, vec, s));
+        for (size_t b0 = 0; b0 < T.bp.v.size(); b0 += kMaxY) {
+            const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, T.bp.v.size() - b0);
+            CU(launch_bp(reinterpret_cast<const BpTask*>(D + offs[L].bp) + b0, nb, T.bp.max_chunks, vec, D, s));
+            launches += 3;
+        }
+    }
+    for (size_t b0 = 0; b0 < resamps.size(); b0 += kMaxY) {
+        const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, resamps.size() - b0);
+        CU(launch_resample(reinterpret_cast<const ResampleTask*>(D + resamp_off) + b0, nb, resamp_max, D, s)); ++launches;
+    }
+    for (size_t b0 = 0; b0 < quants.size(); b0 += kMaxY) {
+        const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, quants.size() - b0);
+        CU(launch_quantise(reinterpret_cast<const QuantTask*>(D + quant_off) + b0, nb, quant_max, s)); ++launches;
+    }
+    CU(cudaEventRecord(g->ev1, s));
+
+    // ---- 4. results back -------------------------------------------------------------------------
+    const double t_d2h0 = now_ms();
+    uint64_t d2h_bytes = 0;
+    for (auto& r : reqs) {
+        if (r.is_scan || r.c->output < 0) continue;
+        if (r.out) {
+            if (r.cap < r.pcm_bytes) return r.c->fail(TDG_ERR_CAPACITY, "output buffer too small");
+            CU(cudaMemcpyAsync(r.out, W + r.pcm_off, r.pcm_bytes, cudaMemcpyDeviceToHost, s));
+            d2h_bytes += r.pcm_bytes;
+        }
+        CU(cudaMemcpyAsync(&r.err_flag, W + r.err_off, 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    const double t_end = now_ms();
+    float dev_ms = 0.0f;
+    cudaEventElapsedTime(&dev_ms, g->ev0, g->ev1);
+
+    // ---- 5. end-of-pass transport state (graph.rs:235-236 / state.rs:575) -------------------------
+    int rc = TDG_OK;
+    for (auto& r : reqs) {
+        Ctx* x = r.c;
+        x->vstate_host_newer = false;
+        if (r.is_scan) {
+            if (x->output >= 0) { x->fb_frame = 0; }
+        } else if (x->output >= 0) x->fb_frame += r.total * x->bl;      // set_time_to_next_block per chunk, never rewound
+        if (x->output >= 0 || !r.is_scan) {
+            x->t = 0;                                                   // Graph::set_time(0)
+            for (HVertex& hv : x->verts) {                              // VertexExt::set_time, extensions.rs:196-204
+                if (hv.kind == K_SAMPLE_LOOP) hv.loop_t = 0;
+                else if (hv.kind == K_DEBUG_SINE) hv.dnotes.clear();
+                else if (hv.kind == K_SYNTH) hv.notes.clear();
+                else if (hv.kind == K_BANDPASS) hv.bp_first = true;
+            }
+        }
+        if (r.frames_written) *r.frames_written = (r.is_scan || x->output < 0) ? 0 : r.out_frames;
+        x->stats.device_ms = dev_ms;
+        x->stats.plan_ms = t_planned - t_start;
+        x->stats.h2d_ms = t_h2d_issued - t_planned;
+        x->stats.d2h_ms = t_end - t_d2h0;
+        x->stats.h2d_bytes = B.size; x->stats.d2h_bytes = d2h_bytes;
+        x->stats.kernel_launches = launches;
+        x->launches += launches;
+        if (reqs.size() > 1) x->stats.algorithmic_bytes = algo_bytes_total;
+        if (r.err_flag) rc = x->fail(TDG_ERR_TOO_WIDE, "sample too wide for bit depth (hound TooWide; the reference panics)");
+    }
+    return rc;
+}
+
+}  // namespace tdg
+
+// ====================================================================================== C ABI
+using namespace tdg;
+struct tdg_ctx { Ctx c; };
+#define C_ (&h->c)
+
+extern "C" {
+
+int tdg_sample_mode_from_string(const char* s) {
+    std::string m = s ? s : "";
+    if (m == "left") return TDG_MODE_LEFT;
+    if (m == "right") return TDG_MODE_RIGHT;
+    if (m == "loudest") return TDG_MODE_LOUDEST;
+    if (m == "normalize-seperate") return TDG_MODE_NORM;
+    if (m == "mix-down") return TDG_MODE_MIX;
+    return TDG_MODE_STEREO;
+}
+
+int tdg_ctx_create(uint32_t project_sr, uint32_t buffer_len, int device, tdg_ctx** out) {
+    if (!out || project_sr == 0 || buffer_len == 0) return TDG_ERR_INVALID;
+    *out = nullptr;
+    std::string err;
+    Engine* g = engine_get(device, &err);
+    if (!g) { fprintf(stderr, "termdaw_b200: %s\n", err.c_str()); return TDG_ERR_CUDA; }
+    tdg_ctx* h = new tdg_ctx();
+    h->c.eng = g; h->c.sr = project_sr; h->c.bl = buffer_len;
+    *out = h;
+    return TDG_OK;
+}
+void tdg_ctx_destroy(tdg_ctx* h) {
+    if (!h) return;
+    Ctx* c = C_;
+    cudaSetDevice(c->eng->device);
+    cudaStreamSynchronize(c->eng->stream);
+    for (auto& s : c->samples) { if (s.l) cudaFree(s.l); }
+    for (auto& t : c->tables) if (t.data) cudaFree(t.data);
+    if (c->vstate_dev) cudaFree(c->vstate_dev);
+    { std::lock_guard<std::mutex> lk(g_mu); c->eng->refs--; }
+    delete h;
+}
+const char* tdg_last_error(tdg_ctx* h) { return h ? h->c.err.c_str() : "null context"; }
+uint64_t tdg_kernel_launches(tdg_ctx* h) { return h ? h->c.launches : 0; }
+
+// SampleBank::add numeric part (sample.rs:262-310) on the device
+int tdg_sample_add(tdg_ctx* h, const float* linear, uint64_t n_values, uint32_t channels, uint32_t src_sr, int mode) {
+    Ctx* c = C_;
+    Engine* g = c->eng;
+    cudaSetDevice(g->device);
+    if (mode == TDG_MODE_STEREO && channels != 2)
+        return c->fail(TDG_ERR_SAMPLE, "only 2 channel samples are supported for stereo samples");
+    if (mode != TDG_MODE_STEREO && (channels > 2 || channels < 1))
+        return c->fail(TDG_ERR_SAMPLE, "only 1,2 channel samples are supported for left or right samples");
+    // channel lengths after de-interleaving (sample.rs:275-292)
+    uint64_t nl, nr;
+    if (channels == 1) { nl = mode == TDG_MODE_LEFT ? n_values : 0; nr = mode == TDG_MODE_LEFT ? 0 : n_values; }
+    else { nl = n_values / 2 + (n_values & 1); nr = n_values / 2; }
+    uint32_t stride = channels, off_l = 0, off_r = channels == 2 ? 1 : 0, mix = 0;
+    uint64_t frames = 0;
+    switch (mode) {                                                        // Sample::from, sample.rs:38-77
+        case TDG_MODE_LEFT: if (nl == 0) return c->fail(TDG_ERR_SAMPLE, "Sample::from: l has length 0");
+            frames = nl; off_r = off_l = 0; break;
+        case TDG_MODE_RIGHT: if (nr == 0) return c->fail(TDG_ERR_SAMPLE, "Sample::from: r has length 0");
+            frames = nr; off_l = off_r = channels == 2 ? 1 : 0; break;
+        case TDG_MODE_LOUDEST: {
+            // mean_energy is a sequential f32 sum (sample.rs:16-22): a decision, taken on the host
+            float sl = 0.0f, sr = 0.0f;
+            if (channels == 2) { for (uint64_t i = 0; i < nl; ++i) sl += fabsf(linear[i * 2]);
+                                 for (uint64_t i = 0; i < nr; ++i) sr += fabsf(linear[i * 2 + 1]); }
+            else { for (uint64_t i = 0; i < nr; ++i) sr += fabsf(linear[i]); }
+            const float lm = nl ? sl / (float)nl : 0.0f, rm = nr ? sr / (float)nr : 0.0f;
+            if (lm > rm) { frames = nl; off_l = off_r = 0; } else { frames = nr; off_l = off_r = channels == 2 ? 1 : 0; }
+            break;
+        }
+        default:
+            if (nl != nr) return c->fail(TDG_ERR_SAMPLE, "Sample::from: l and r do not have the same length");
+            if (nl == 0) return c->fail(TDG_ERR_SAMPLE, "Sample::from: l and r have length 0");
+            frames = nl; mix = mode == TDG_MODE_MIX ? 1 : 0;
+    }
+    if (frames == 0) return c->fail(TDG_ERR_SAMPLE, "empty sample");
+    cudaStream_t s = g->stream;
+    float* lin_d = nullptr; float* buf = nullptr; int* mx = nullptr;
+    const uint64_t fpad = align_up(frames, 4);
+    CU(cudaMalloc(&lin_d, std::max<uint64_t>(n_values, 1) * 4));
+    CU(cudaMalloc(&buf, fpad * 2 * 4));
+    CU(cudaMalloc(&mx, 8));
+    CU(cudaMemcpyAsync(lin_d, linear, n_values * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(mx, 0, 8, s));
+    CU(cudaMemsetAsync(buf, 0, fpad * 2 * 4, s));
+    float* dl = buf; float* dr = buf + fpad;
+    CU(launch_deinterleave(lin_d, frames, stride, off_l, off_r, mix, dl, dr, s));
+    CU(launch_absmax(dl, frames, mx, s));
+    CU(launch_absmax(dr, frames, mx + 1, s));
+    const float* ma = reinterpret_cast<const float*>(mx);
+    if (mode == TDG_MODE_NORM) {                                           // normalize_seperate, sample.rs:132-137
+        CU(launch_scale_by_inv(dl, frames, ma, nullptr, s));
+        CU(launch_scale_by_inv(dr, frames, ma + 1, nullptr, s));
+    } else {                                                               // normalize / mix_down (l == r there)
+        CU(launch_scale_by_inv(dl, frames, ma, ma + 1, s));
+        CU(launch_scale_by_inv(dr, frames, ma, ma + 1, s));
+    }
+    c->launches += 5;
+    DevSample out;
+    if (src_sr != c->sr) {                                                 // Sample::resample, sample.rs:150-175
+        const double ratio = (double)c->sr / (double)src_sr;
+        std::vector<ResampleChunk> ch; uint64_t total = 0;
+        resample_replay(ratio, frames, 1, ch, &total);
+        if (total == 0) { cudaFree(lin_d); cudaFree(buf); cudaFree(mx); return c->fail(TDG_ERR_SAMPLE, "sample too short to resample"); }
+        const uint64_t opad = align_up(total, 4);
+        float* ob = nullptr; uint8_t* mini = nullptr;
+        CU(cudaMalloc(&ob, opad * 2 * 4));
+        CU(cudaMemsetAsync(ob, 0, opad * 2 * 4, s));
+        CU(cudaMalloc(&mini, 256));
+        ResampleTask rt; memset(&rt, 0, sizeof rt);
+        rt.in_l = dl; rt.in_r = dr; rt.out_l = ob; rt.out_r = ob + opad;
+        rt.sincs = sinc_table_dev(c, ratio);
+        if (!rt.sincs) return c->fail(TDG_ERR_CUDA, "could not build the sinc table");
+        rt.n_in = frames; rt.chunk_off = 128; rt.n_chunks = 1; rt.chunk = (uint32_t)frames; rt.t_ratio = 1.0 / ratio;
+        uint8_t host[256]; memset(host, 0, sizeof host);
+        memcpy(host, &rt, sizeof rt); memcpy(host + 128, &ch[0], sizeof(ResampleChunk));
+        static_assert(sizeof(ResampleTask) <= 128, "mini blob layout");
+        CU(cudaMemcpyAsync(mini, host, 256, cudaMemcpyHostToDevice, s));
+        CU(launch_resample(reinterpret_cast<const ResampleTask*>(mini), 1, total, mini, s));
+        c->launches += 1;
+        CU(cudaStreamSynchronize(s));
+        cudaFree(mini); cudaFree(buf);
+        out.l = ob; out.r = ob + opad; out.frames = total;
+    } else {
+        CU(cudaStreamSynchronize(s));
+        out.l = dl; out.r = dr; out.frames = frames;
+    }
+    cudaFree(lin_d); cudaFree(mx);
+    c->samples.push_back(out);
+    return (int)c->samples.size() - 1;
+}
+int64_t tdg_sample_frames(tdg_ctx* h, int sample) {
+    if (sample < 0 || (size_t)sample >= h->c.samples.size()) return TDG_ERR_INVALID;
+    return (int64_t)h->c.samples[sample].frames;
+}
+int tdg_sample_read(tdg_ctx* h, int sample, float* l, float* r, uint64_t cap) {
+    Ctx* c = C_;
+    if (sample < 0 || (size_t)sample >= c->samples.size()) return c->fail(TDG_ERR_INVALID, "unknown sample");
+    const DevSample& s = c->samples[sample];
+    if (cap < s.frames) return c->fail(TDG_ERR_CAPACITY, "sample_read: capacity too small");
+    cudaSetDevice(c->eng->device);
+    CU(cudaMemcpy(l, s.l, s.frames * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(r, s.r, s.frames * 4, cudaMemcpyDeviceToHost));
+    return TDG_OK;
+}
+int tdg_resource_add(tdg_ctx* h, const uint8_t* bytes, uint64_t n) {
+    h->c.resources.emplace_back(bytes, bytes + n);
+    return (int)h->c.resources.size() - 1;
+}
+int tdg_floww_add(tdg_ctx* h, const float* t, const float* note, const float* vel, uint64_t n) {
+    Ctx* c = C_;
+    Floww f;
+    f.t.assign(t, t + n); f.note.assign(note, note + n); f.vel.assign(vel, vel + n);
+    f.fe.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        f.fe[i] = f32_as_usize(t[i] * (float)c->sr);                       // floww.rs:75
+        if (i && f.fe[i] < f.fe[i - 1]) return c->fail(TDG_ERR_UNSORTED, "floww events must be sorted by time");
+    }
+    c->flowws.push_back(std::move(f));
+    return (int)c->flowws.size() - 1;
+}
+int tdg_floww_reset(tdg_ctx* h) { h->c.flowws.clear(); h->c.fb_frame = 0; return TDG_OK; }     // floww.rs:21-28
+
+int tdg_graph_reset(tdg_ctx* h) {                                           // graph.rs:39-47
+    Ctx* c = C_;
+    c->verts.clear(); c->output = -1; c->t = 0;
+    c->vstate_host.clear(); c->vstate_host_newer = true;
+    c->last_buf_off.clear();
+    return TDG_OK;
+}
+
+static int add_vertex(Ctx* c, HVertex v, float gain, float angle, float wet) {
+    v.gain = gain;
+    v.angle = fmaxf(fminf(angle, 90.0f), -90.0f);                           // graph.rs:255
+    v.wet = fmaxf(fminf(wet, 1.0f), 0.0f);                                  // graph.rs:256
+    if (vstate_to_host(c) != TDG_OK) return TDG_ERR_CUDA;
+    c->verts.push_back(std::move(v));
+    c->vstate_host.resize(c->verts.size() * 8, 0.0f);
+    float* st = &c->vstate_host[(c->verts.size() - 1) * 8];
+    for (int i = 0; i < 8; ++i) st[i] = 0.0f;
+    if (c->verts.back().kind != K_NORMALIZE) { st[0] = -1.0f; st[1] = -1.0f; }
+    c->vstate_host_newer = true;
+    return (int)c->verts.size() - 1;
+}
+static bool parse_adsr(const float* a, int n, AdsrConfD* o) {               // adsr.rs:94-114
+    memset(o, 0, sizeof *o);
+    if (n == 0) return true;
+    if (n == 6) { o->std_vel = 0.0f; o->attack_sec = a[0]; o->attack_vel = 1.0f; o->decay_sec = a[1]; o->decay_vel = a[2];
+                  o->sustain_sec = a[3]; o->sustain_vel = a[4]; o->release_sec = a[5]; o->release_vel = 0.0f; return true; }
+    if (n == 9) { o->std_vel = a[0]; o->attack_sec = a[1]; o->attack_vel = a[2]; o->decay_sec = a[3]; o->decay_vel = a[4];
+                  o->sustain_sec = a[5]; o->sustain_vel = a[6]; o->release_sec = a[7]; o->release_vel = a[8]; return true; }
+    return false;
+}
+#define NEED_SAMPLE(s) if ((s) < 0 || (size_t)(s) >= c->samples.size()) return c->fail(TDG_ERR_INVALID, "unknown sample index")
+#define NEED_FLOWW(f) if ((f) < 0 || (size_t)(f) >= c->flowws.size()) return c->fail(TDG_ERR_INVALID, "unknown floww index")
+
+int tdg_add_sum(tdg_ctx* h, float gain, float angle) { HVertex v; v.kind = K_SUM; return add_vertex(C_, v, gain, angle, 0.0f); }
+int tdg_add_normalize(tdg_ctx* h, float gain, float angle) { HVertex v; v.kind = K_NORMALIZE; return add_vertex(C_, v, gain, angle, 0.0f); }
+int tdg_add_sample_loop(tdg_ctx* h, float gain, float angle, int sample) {
+    Ctx* c = C_; NEED_SAMPLE(sample);
+    HVertex v; v.kind = K_SAMPLE_LOOP; v.sample = sample; return add_vertex(c, v, gain, angle, 0.0f);
+}
+int tdg_add_sample_multi(tdg_ctx* h, float gain, float angle, int sample, int floww, int note) {
+    Ctx* c = C_; NEED_SAMPLE(sample); NEED_FLOWW(floww);
+    HVertex v; v.kind = K_SAMPLE_MULTI; v.sample = sample; v.floww = floww; v.has_note = note >= 0; v.note = note >= 0 ? note : 0;
+    return add_vertex(c, v, gain, angle, 0.0f);
+}
+int tdg_add_sample_lerp(tdg_ctx* h, float gain, float angle, int sample, int floww, int note, int lerp_len) {
+    Ctx* c = C_; NEED_SAMPLE(sample); NEED_FLOWW(floww);
+    HVertex v; v.kind = K_SAMPLE_LERP; v.sample = sample; v.floww = floww; v.has_note = note >= 0; v.note = note >= 0 ? note : 0;
+    v.lerp_len = (uint32_t)std::max(lerp_len, 0);                           // state.rs:370
+    return add_vertex(c, v, gain, angle, 0.0f);
+}
+int tdg_add_debug_sine(tdg_ctx* h, float gain, float angle, int floww) {
+    Ctx* c = C_; NEED_FLOWW(floww);
+    HVertex v; v.kind = K_DEBUG_SINE; v.floww = floww; return add_vertex(c, v, gain, angle, 0.0f);
+}
+int tdg_add_synth(tdg_ctx* h, float gain, float angle, int floww, float sq_vol, float sq_z, const float* sq_adsr, int sq_n,
+                  float tf_vol, float tf_z, const float* tf_adsr, int tf_n, float tr_vol, const float* tr_adsr, int tr_n) {
+    Ctx* c = C_; NEED_FLOWW(floww);
+    HVertex v; v.kind = K_SYNTH; v.floww = floww;
+    if (!parse_adsr(sq_adsr, sq_n, &v.sq.adsr) || !parse_adsr(tf_adsr, tf_n, &v.tf.adsr) || !parse_adsr(tr_adsr, tr_n, &v.tr.adsr))
+        return c->fail(TDG_ERR_ADSR_CONF, "ADSR config must have 6 or 9 elements");
+    v.sq.volume = sq_vol; v.sq.param = fmaxf(sq_z, 0.0001f);                // state.rs:400
+    v.tf.volume = tf_vol; v.tf.param = tf_z;
+    v.tr.volume = tr_vol; v.tr.param = 0.0f;
+    return add_vertex(c, v, gain, angle, 0.0f);
+}
+int tdg_add_sampsyn(tdg_ctx* h, float gain, float angle, int floww, const float* adsr, int n, int resource) {
+    Ctx* c = C_; NEED_FLOWW(floww);
+    if (resource < 0 || (size_t)resource >= c->resources.size()) return c->fail(TDG_ERR_INVALID, "unknown resource index");
+    HVertex v; v.kind = K_SAMPSYN; v.floww = floww;
+    if (!parse_adsr(adsr, n, &v.adsr)) return c->fail(TDG_ERR_ADSR_CONF, "ADSR config must have 6 or 9 elements");
+    // parse_wavetable_from_buffer (state.rs:415): "WTB1", u32 n_frames, u32 n_phase, f32 fps, f32 data[][]
+    const std::vector<uint8_t>& b = c->resources[resource];
+    DevTable tb; std::vector<float> data;
+    bool ok = b.size() >= 16 && memcmp(b.data(), "WTB1", 4) == 0;
+    if (ok) {
+        uint32_t nf, np; float fps;
+        memcpy(&nf, b.data() + 4, 4); memcpy(&np, b.data() + 8, 4); memcpy(&fps, b.data() + 12, 4);
+        ok = nf >= 1 && np >= 2 && (uint64_t)nf * np * 4 + 16 == b.size();
+        if (ok) { tb.n_frames = nf; tb.n_phase = np; tb.fps = fps; data.resize((size_t)nf * np); memcpy(data.data(), b.data() + 16, data.size() * 4); }
+    }
+    if (!ok) {                                                              // WaveTable::default() stand-in (state.rs:421)
+        tb.n_frames = 1; tb.n_phase = 1024; tb.fps = 1.0f; data.resize(1024);
+        for (uint32_t p = 0; p < 1024; ++p) data[p] = sinf(6.2831855f * ((float)p / 1024.0f));
+    }
+    cudaSetDevice(c->eng->device);
+    CU(cudaMalloc(&tb.data, data.size() * 4));
+    CU(cudaMemcpy(tb.data, data.data(), data.size() * 4, cudaMemcpyHostToDevice));
+    c->tables.push_back(tb);
+    v.table = (int)c->tables.size() - 1;
+    return add_vertex(c, v, gain, angle, 0.0f);
+}
+int tdg_add_lv2fx(tdg_ctx* h, float, float, float, int) {
+    return h->c.fail(TDG_ERR_UNSUPPORTED_VERTEX, "lv2fx vertices run arbitrary native plugin code and are rejected by the GPU renderer");
+}
+int tdg_add_adsr(tdg_ctx* h, float gain, float angle, float wet, int floww, int use_off, int use_max, int note, const float* conf, int n) {
+    Ctx* c = C_; NEED_FLOWW(floww);
+    HVertex v; v.kind = K_ADSR; v.floww = floww; v.use_off = use_off != 0; v.use_max = use_max != 0;
+    v.has_note = note >= 0; v.note = note >= 0 ? note : 0;
+    if (!parse_adsr(conf, n, &v.adsr)) return c->fail(TDG_ERR_ADSR_CONF, "ADSR config must have 6 or 9 elements");
+    return add_vertex(c, v, gain, angle, wet);
+}
+int tdg_add_bandpass(tdg_ctx* h, float gain, float angle, float wet, float lo, float hi, int pass) {
+    Ctx* c = C_;
+    HVertex v; v.kind = K_BANDPASS;                                         // extensions.rs:173-194
+    const float lco = fmaxf(fminf(lo, 20000.0f), 0.0f), hco = fmaxf(fminf(hi, 20000.0f), 0.0f);
+    v.lgamma = 1.0f - powf(kE, -2.0f * TDG_PI_F * lco / (float)c->sr);
+    v.hgamma = 1.0f - powf(kE, -2.0f * TDG_PI_F * hco / (float)c->sr);
+    v.pass = pass != 0; v.bp_first = true;
+    return add_vertex(c, v, gain, angle, wet);
+}
+static bool has_loop(const Ctx* c, int x, int b) {                          // graph.rs:65-71
+    if (x == b) return true;
+    for (int y : c->verts[x].edges) if (has_loop(c, y, b)) return true;
+    return false;
+}
+int tdg_connect(tdg_ctx* h, int a, int b) {                                 // graph.rs:58-78
+    Ctx* c = C_;
+    const int n = (int)c->verts.size();
+    if (a < 0 || b < 0 || a == b || a >= n || b >= n) return 0;
+    if (!c->verts[b].has_input()) return 0;
+    if (has_loop(c, a, b)) return 0;
+    c->verts[b].edges.push_back(a);
+    return 1;
+}
+int tdg_set_output(tdg_ctx* h, int v) {
+    if (v < 0 || (size_t)v >= h->c.verts.size()) return h->c.fail(TDG_ERR_INVALID, "unknown vertex");
+    h->c.output = v; return TDG_OK;
+}
+int tdg_check_graph(tdg_ctx* h, int* unreachable, int cap, int* n_unreachable) {   // graph.rs:150-174
+    Ctx* c = C_;
+    if (n_unreachable) *n_unreachable = 0;
+    if (c->output < 0) { c->err = "output vertex not found"; return 0; }
+    if (c->verts[c->output].edges.empty() && c->verts[c->output].has_input()) { c->err = "output receives no inputs"; return 0; }
+    std::vector<char> set(c->verts.size(), 0);
+    std::vector<int> st{c->output};
+    while (!st.empty()) { int v = st.back(); st.pop_back(); if (set[v]) continue; set[v] = 1; for (int y : c->verts[v].edges) st.push_back(y); }
+    int n = 0;
+    for (size_t i = 0; i < set.size(); ++i) if (!set[i]) { if (unreachable && n < cap) unreachable[n] = (int)i; ++n; }
+    if (n_unreachable) *n_unreachable = n;
+    return 1;
+}
+int tdg_reset_normalize(tdg_ctx* h) {                                       // extensions.rs:295-299
+    Ctx* c = C_;
+    if (int r = vstate_to_host(c)) return r;
+    c->vstate_host.resize(c->verts.size() * 8, 0.0f);
+    for (size_t v = 0; v < c->verts.size(); ++v) if (c->verts[v].kind == K_NORMALIZE) c->vstate_host[v * 8] = 0.000001f;
+    c->vstate_host_newer = true;
+    return TDG_OK;
+}
+float tdg_get_normalize_value(tdg_ctx* h, int v) {                          // extensions.rs:301-307
+    Ctx* c = C_;
+    if (v < 0 || (size_t)v >= c->verts.size() || c->verts[v].kind != K_NORMALIZE) return -1.0f;
+    if (vstate_to_host(c) != TDG_OK) return -1.0f;
+    return c->vstate_host[(size_t)v * 8];
+}
+int tdg_get_normalize_state(tdg_ctx* h, float* mx, float* smx, int cap) {
+    Ctx* c = C_;
+    if (int r = vstate_to_host(c)) return r;
+    const int n = (int)c->verts.size();
+    for (int i = 0; i < n && i < cap; ++i) { mx[i] = c->vstate_host[(size_t)i * 8]; smx[i] = c->vstate_host[(size_t)i * 8 + 1]; }
+    return n;
+}
+int tdg_set_normalize_state(tdg_ctx* h, const float* mx, const float* smx, int n) {
+    Ctx* c = C_;
+    if (int r = vstate_to_host(c)) return r;
+    for (int i = 0; i < n && (size_t)i < c->verts.size(); ++i)
+        if (c->verts[i].kind == K_NORMALIZE) { c->vstate_host[(size_t)i * 8] = mx[i]; c->vstate_host[(size_t)i * 8 + 1] = smx[i]; }
+    c->vstate_host_newer = true;
+    return TDG_OK;
+}
+void* tdg_normalize_state_device_ptr(tdg_ctx* h, int* n_floats) {
+    Ctx* c = C_;
+    cudaSetDevice(c->eng->device);
+    if (vstate_to_dev(c) != TDG_OK) return nullptr;
+    if (n_floats) *n_floats = (int)c->verts.size() * 8;
+    // the caller may modify the device copy (NCCL all-reduce): it is the authoritative one from now on
+    return c->vstate_dev;
+}
+
+static void graph_set_time(Ctx* c, uint64_t time) {                         // graph.rs:123-128 + extensions.rs:196-204
+    c->t = time;
+    for (HVertex& hv : c->verts) {
+        if (hv.kind == K_SAMPLE_LOOP) hv.loop_t = time;
+        else if (hv.kind == K_DEBUG_SINE) hv.dnotes.clear();
+        else if (hv.kind == K_SYNTH) hv.notes.clear();
+        else if (hv.kind == K_BANDPASS) hv.bp_first = true;
+    }
+}
+int tdg_set_time(tdg_ctx* h, uint64_t frame) { graph_set_time(C_, frame); return TDG_OK; }
+uint64_t tdg_change_time(tdg_ctx* h, uint64_t delta, int plus) {            // graph.rs:130-135
+    Ctx* c = C_;
+    const uint64_t nt = plus ? c->t + delta : c->t - std::min(delta, c->t);
+    graph_set_time(c, nt);
+    return nt;
+}
+uint64_t tdg_get_time(tdg_ctx* h) { return h->c.t; }
+int tdg_floww_set_time(tdg_ctx* h, uint64_t frame) { h->c.fb_frame = frame; return TDG_OK; }   // floww.rs:83-86
+
+int tdg_enable_taps(tdg_ctx* h, int on) { h->c.taps = on != 0; return TDG_OK; }
+int tdg_read_vertex_buffer(tdg_ctx* h, int vertex, uint64_t frame0, uint64_t n, float* l, float* r) {
+    Ctx* c = C_;
+    if (vertex < 0 || (size_t)vertex >= c->last_buf_off.size() || c->last_buf_off[vertex] < 0)
+        return c->fail(TDG_ERR_INVALID, "vertex was not evaluated by the last pass");
+    if (!c->taps || c->last_epoch != c->eng->epoch) return c->fail(TDG_ERR_INVALID, "taps are only valid right after a pass with taps enabled");
+    if (frame0 + n > c->last_n_frames) return c->fail(TDG_ERR_CAPACITY, "tap shorter than request");
+    cudaSetDevice(c->eng->device);
+    const float* bl_ = reinterpret_cast<const float*>(c->eng->work.p + c->last_buf_off[vertex]);
+    CU(cudaMemcpy(l, bl_ + frame0, n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(r, bl_ + c->last_n_pad + frame0, n * 4, cudaMemcpyDeviceToHost));
+    return TDG_OK;
+}
+
+uint64_t tdg_render_bound_bytes(tdg_ctx* h, uint64_t chunks, uint32_t, uint32_t bd) { return chunks * h->c.bl * 2 * (bd / 8); }
+
+static int valid_bd(Ctx* c, uint32_t bd) {
+    if (!(bd == 8 || bd == 16 || bd == 24 || bd == 32)) return c->fail(TDG_ERR_BITDEPTH, "bitdepth not supported: choose 8, 16, 24 or 32");
+    return TDG_OK;
+}
+
+int tdg_normalize_scan_many(tdg_ctx** hs, int n, const uint64_t* chunks) {
+    std::vector<PassReq> reqs;
+    for (int i = 0; i < n; ++i) {
+        if (hs[i]->c.output < 0) continue;                                  // graph.rs:225-226: no output, no scan
+        PassReq r; r.c = &hs[i]->c; r.is_scan = true; r.total = chunks[i]; r.emit0 = 0; r.emit_n = chunks[i]; r.keep0 = 0;
+        reqs.push_back(std::move(r));
+    }
+    return run_pass(reqs);
+}
+int tdg_normalize_scan(tdg_ctx* h, uint64_t chunks) { return tdg_normalize_scan_many(&h, 1, &chunks); }
+
+int tdg_render_many(tdg_ctx** hs, int n, const uint64_t* chunks, const uint32_t* render_sr, const uint32_t* bitdepth,
+                    uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written) {
+    std::vector<PassReq> reqs;
+    for (int i = 0; i < n; ++i) {
+        Ctx* c = &hs[i]->c;
+        if (int e = valid_bd(c, bitdepth[i])) return e;
+        if (frames_written) frames_written[i] = 0;
+        PassReq r; r.c = c; r.is_scan = false; r.total = chunks[i]; r.emit0 = 0; r.emit_n = chunks[i]; r.keep0 = 0;
+        r.render_sr = render_sr[i]; r.bd = bitdepth[i];
+        r.out = out_pcm ? out_pcm[i] : nullptr; r.cap = cap_bytes ? cap_bytes[i] : 0;
+        r.frames_written = frames_written ? frames_written + i : nullptr;
+        reqs.push_back(std::move(r));
+    }
+    return run_pass(reqs);
+}
+int tdg_render(tdg_ctx* h, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes,
+               uint64_t* frames_written) {
+    return tdg_render_many(&h, 1, &chunks, &render_sr, &bitdepth, out_pcm ? &out_pcm : nullptr, &cap_bytes, frames_written);
+}
+
+// time sharding: audio is evaluated for [chunk0 - warmup, chunk0 + chunks) only; the event-driven
+// state advances over the whole pass of `total_chunks` chunks, exactly as a full pass would leave it
+int tdg_scan_segment(tdg_ctx* h, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks, uint64_t warmup_chunks) {
+    Ctx* c = C_;
+    if (c->output < 0) return TDG_OK;
+    if (chunk0 + chunks > total_chunks) return c->fail(TDG_ERR_INVALID, "segment exceeds the pass");
+    const uint64_t w = std::min(warmup_chunks, chunk0);
+    std::vector<PassReq> reqs(1);
+    PassReq& r = reqs[0];
+    r.c = c; r.is_scan = true; r.segment = true; r.emit0 = chunk0 - w; r.emit_n = chunks + w; r.keep0 = chunk0;
+    r.total = total_chunks;
+    return run_pass(reqs);
+}
+int tdg_render_segment(tdg_ctx* h, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks, uint64_t warmup_chunks,
+                       uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes, uint64_t* frames_written) {
+    Ctx* c = C_;
+    if (int e = valid_bd(c, bitdepth)) return e;
+    if (chunk0 + chunks > total_chunks) return c->fail(TDG_ERR_INVALID, "segment exceeds the pass");
+    const uint64_t w = std::min(warmup_chunks, chunk0);
+    std::vector<PassReq> reqs(1);
+    PassReq& r = reqs[0];
+    r.c = c; r.is_scan = false; r.segment = true; r.emit0 = chunk0 - w; r.emit_n = chunks + w; r.keep0 = chunk0;
+    r.total = total_chunks; r.render_sr = c->sr; r.bd = bitdepth;
+    r.out = out_pcm; r.cap = cap_bytes; r.frames_written = frames_written;
+    return run_pass(reqs);
+}
+
+int tdg_last_pass_stats(tdg_ctx* h, tdg_pass_stats* out) {
+    if (!h || !out) return TDG_ERR_INVALID;
+    const PassStats& s = h->c.stats;
+    out->device_ms = s.device_ms; out->plan_ms = s.plan_ms; out->h2d_ms = s.h2d_ms; out->d2h_ms = s.d2h_ms;
+    out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes; out->kernel_launches = s.kernel_launches;
+    out->algorithmic_bytes = s.algorithmic_bytes; out->frames = s.frames; out->voice_frames = s.voice_frames;
+    return TDG_OK;
+}
+
+}  // extern "C"

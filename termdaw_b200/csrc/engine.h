@@ -1,0 +1,85 @@
+// engine.h — host-side structures of the device graph executor (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <deque>
+#include <string>
+#include <vector>
+#include "tdg_types.h"
+
+namespace tdg {
+
+enum Kind { K_SUM, K_NORMALIZE, K_SAMPLE_LOOP, K_SAMPLE_MULTI, K_SAMPLE_LERP, K_DEBUG_SINE, K_SYNTH, K_SAMPSYN,
+            K_ADSR, K_BANDPASS };
+
+struct DevSample { float* l = nullptr; float* r = nullptr; uint64_t frames = 0; };
+struct DevTable { float* data = nullptr; uint32_t n_frames = 1, n_phase = 1024; float fps = 1.0f; };
+
+struct Floww {
+    std::vector<float> t, note, vel;
+    std::vector<uint64_t> fe;        // (t * sr as f32) as usize, floww.rs:75
+};
+
+struct MultiEntry { int64_t t; float vel; };                       // extensions.rs:29
+struct DNote { float note, vel, hz; uint64_t seq; uint32_t ia; };  // extensions.rs:42
+struct SNote { float note, vel, env_t, rel_t, hz; uint64_t seq; uint32_t ia; };   // extensions.rs:49,55
+struct A3 { float t, vel, rel; };                                  // extensions.rs:67-68
+
+struct OscConfH { float volume = 0, param = 0; AdsrConfD adsr{}; };
+
+struct HVertex {
+    int kind = K_SUM;
+    float gain = 1, angle = 0, wet = 0;
+    int sample = -1, floww = -1, table = -1;
+    bool has_note = false; uint32_t note = 0; uint32_t lerp_len = 0;
+    OscConfH sq, tf, tr;
+    AdsrConfD adsr{};
+    bool use_off = false, use_max = false;
+    float lgamma = 0, hgamma = 0; bool pass = true;
+    // ---- state carried between passes (mirrors VertexExt's mutable fields)
+    uint64_t loop_t = 0;
+    std::deque<MultiEntry> ts;
+    uint64_t countdown = 0; MultiEntry primary{0, 0.0f}, ghost{0, 0.0f};
+    std::vector<DNote> dnotes;
+    std::vector<SNote> notes;
+    uint64_t seq = 0;
+    A3 aprimary{0, 0, 0}, aghost{0, 0, 0};
+    bool bp_first = true;
+    std::vector<int> edges;          // inputs, in connect() order (graph.rs:76)
+    bool has_input() const { return kind == K_SUM || kind == K_NORMALIZE || kind == K_ADSR || kind == K_BANDPASS; }
+};
+
+struct PassStats {
+    double device_ms = 0, plan_ms = 0, h2d_ms = 0, d2h_ms = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0, kernel_launches = 0, algorithmic_bytes = 0, frames = 0, voice_frames = 0;
+};
+
+struct Engine;
+
+struct Ctx {
+    Engine* eng = nullptr;
+    uint32_t sr = 0, bl = 0;
+    std::string err;
+    std::vector<DevSample> samples;
+    std::vector<std::vector<uint8_t>> resources;
+    std::vector<DevTable> tables;            // one per SampSyn vertex built from a resource
+    std::vector<Floww> flowws;
+    std::vector<HVertex> verts;
+    int output = -1;
+    uint64_t t = 0;                          // Graph.t
+    uint64_t fb_frame = 0;                   // FlowwBank.frame
+    // per-vertex device state: [v*8 + {0:max, 1:scan_max, 2..5: lprevl,lprevr,hprevl,hprevr}]
+    std::vector<float> vstate_host;
+    float* vstate_dev = nullptr; size_t vstate_cap = 0;
+    bool vstate_host_newer = true;
+    bool taps = false;
+    // layout of the last pass (for taps)
+    std::vector<int64_t> last_buf_off;       // per vertex, -1 if not evaluated
+    uint64_t last_n_frames = 0, last_n_pad = 0;
+    uint64_t last_epoch = 0;
+    PassStats stats;
+    uint64_t launches = 0;
+    int fail(int code, const std::string& m) { err = m; return code; }
+};
+
+}  // namespace tdg

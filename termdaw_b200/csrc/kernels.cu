@@ -1,0 +1,843 @@
+// kernels.cu — the sm_100a kernels of the termdaw render path and their launchers.
+//
+// Layout: every vertex buffer is planar stereo fp32 in HBM for the whole pass; a block evaluates one
+// chunk (buffer_length frames) of one task, a thread four consecutive frames (float4 loads/stores),
+// grid = (chunks, tasks) so that one launch covers a whole DAG level of a batch of projects.
+// All kernels are HBM-streaming (no dense contraction anywhere => no tensor cores); the voice
+// kernels are FP32/SFU bound and say so in DESIGN.md.
+//
+// Compiled with -fmad=false: the reference rounds after every f32 operation.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tdg_types.h"
+#include "tdg_math.cuh"
+#include "kernels.h"
+
+namespace tdg {
+
+#define TDG_THREADS 256
+
+// ------------------------------------------------------------------------------------ helpers
+template <typename T>
+__device__ __forceinline__ void load_task(T* dst, const T* src) {
+    static_assert(sizeof(T) % 4 == 0, "task structs are word multiples");
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(T) / 4); i += blockDim.x) d[i] = s[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void apply_pg(float& l, float& r, const PanGain& pg) {
+    if (pg.flags & 1u) { l *= pg.l_amp; r *= pg.r_amp; }       // apply_angle, sample.rs:97-106
+    if (pg.flags & 2u) { l *= pg.gain; r *= pg.gain; }         // apply_gain,  sample.rs:108-114
+}
+
+template <bool VEC>
+__device__ __forceinline__ void ld4(const float* __restrict__ p, uint64_t idx, int nv, float (&v)[4]) {
+    if (VEC) {
+        float4 a = *reinterpret_cast<const float4*>(p + idx);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = j < nv ? p[idx + j] : 0.0f;
+    }
+}
+template <bool VEC>
+__device__ __forceinline__ void st4(float* __restrict__ p, uint64_t idx, int nv, const float (&v)[4]) {
+    if (VEC) {
+        *reinterpret_cast<float4*>(p + idx) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < nv) p[idx + j] = v[j];
+    }
+}
+
+// absmaxlen's fold (sample.rs:12-14): NaN never wins because `a > max` is false for NaN
+__device__ __forceinline__ float absmax_fold(float m, float x) { float a = fabsf(x); return a > m ? a : m; }
+
+__device__ __forceinline__ float block_max(float m) {
+    __shared__ float wm[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    if (ln == 0) wm[w] = m;
+    __syncthreads();
+    if (w == 0) {
+        m = ln < (int)(blockDim.x >> 5) ? wm[ln] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    return m;   // valid in thread 0
+}
+
+// ------------------------------------------------------------------------------------ K4: fx
+// sum_inputs (extensions.rs:310-319) + { nothing | adsr_gen (:593-651) | per-chunk peak for
+// normalize_gen (:321-329) } + apply_angle + apply_gain (:262-263), one pass over HBM.
+template <bool VEC>
+__global__ void __launch_bounds__(TDG_THREADS) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    __shared__ FxTask T;
+    load_task(&T, tasks + blockIdx.y);
+    const uint32_t k = blockIdx.x;
+    if (k >= T.h.n_chunks) return;
+    const uint32_t bl = T.h.bl;
+    const uint64_t p0 = (uint64_t)k * bl;
+    const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
+    const AdsrSeg* segs = nullptr;
+    uint32_t s_lo = 0, s_hi = 0;
+    if (T.mode == FX_ADSR) {
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
+        s_lo = sp[k]; s_hi = sp[k + 1];
+        segs = reinterpret_cast<const AdsrSeg*>(blob + T.seg_off);
+    }
+    const float maxmul = T.use_max ? 1.0f : 0.0f, minmul = 1.0f - maxmul;
+    float peak = 0.0f;
+    for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
+        const int nv = min(4u, bl - i);
+        const uint64_t p = p0 + i;
+        float l[4] = {0.0f, 0.0f, 0.0f, 0.0f}, r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (uint32_t a = 0; a < T.n_in; ++a) {
+            float x[4], y[4];
+            ld4<VEC>(ins[2 * a], p, nv, x);
+            ld4<VEC>(ins[2 * a + 1], p, nv, y);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { l[j] += x[j]; r[j] += y[j]; }
+        }
+        if (T.mode == FX_ADSR) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nv) break;
+                const uint32_t fi = i + j;
+                uint32_t s = s_lo;                       // last segment starting at or before this frame
+                while (s + 1 < s_hi && segs[s + 1].ia <= fi) ++s;
+                const AdsrSeg sg = segs[s];
+                if (sg.flags & 1u) continue;             // un-enveloped frame (extensions.rs:633-635)
+                const float offset = (float)fi / (float)T.sr;
+                float pvel, gvel;
+                if (T.use_off) {                         // extensions.rs:620-623
+                    pvel = sg.pr == 0.0f ? m_apply_ads(T.conf, sg.pt + offset) * sg.pv
+                                         : m_apply_r(T.conf, sg.pt + offset, sg.pr) * sg.pv;
+                    gvel = sg.gr == 0.0f ? m_apply_ads(T.conf, sg.gt + offset) * sg.gv
+                                         : m_apply_r(T.conf, sg.gt + offset, sg.gr) * sg.gv;
+                } else {                                 // extensions.rs:640-641
+                    pvel = m_apply_adsr(T.conf, sg.pt + offset) * sg.pv;
+                    gvel = m_apply_adsr(T.conf, sg.gt + offset) * sg.gv;
+                }
+                const float adsr_vel = fmaxf(pvel, gvel) * maxmul + fminf(pvel, gvel) * minmul;
+                const float vel = m_lerp(1.0f, adsr_vel, T.wet);
+                l[j] *= vel; r[j] *= vel;
+            }
+        }
+        if (T.mode == FX_NORM_PEAK) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nv) { peak = absmax_fold(peak, l[j]); peak = absmax_fold(peak, r[j]); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) apply_pg(l[j], r[j], T.h.pg);
+        }
+        st4<VEC>(T.h.out_l, p, nv, l);
+        st4<VEC>(T.h.out_r, p, nv, r);
+    }
+    if (T.mode == FX_NORM_PEAK) {
+        peak = block_max(peak);
+        if (threadIdx.x == 0) T.peaks[k] = peak;
+    }
+}
+
+// ------------------------------------------------------------------------------------ K8: normalize max bookkeeping
+// One block per normalize vertex.  Scan pass: every chunk is scaled by the OLD max while scan_max
+// collects the peak (extensions.rs:323-324, graph.rs:227-234).  Render pass: running max
+// (extensions.rs:326).  max() is exact, so the parallel prefix is bit-identical to the fold.
+__global__ void __launch_bounds__(1024) k_norm_prefix(const NormPrefixTask* __restrict__ tasks) {
+    const NormPrefixTask T = tasks[blockIdx.x];
+    __shared__ float part[1024];
+    const uint32_t n = T.n_chunks, tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t per = (n + nt - 1) / nt;
+    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
+    const float old_max = T.state[0];
+    float m = 0.0f;
+    for (uint32_t k = lo; k < hi; ++k) m = fmaxf(T.peaks[k], m);
+    part[tid] = m;
+    __syncthreads();
+    for (uint32_t o = 1; o < nt; o <<= 1) {           // inclusive Hillis-Steele over per-thread maxima
+        float v = tid >= o ? part[tid - o] : 0.0f;
+        __syncthreads();
+        part[tid] = fmaxf(part[tid], v);
+        __syncthreads();
+    }
+    const float total = part[nt - 1];
+    if (T.is_scan) {
+        for (uint32_t k = lo; k < hi; ++k) T.runmax[k] = old_max;
+        __syncthreads();
+        if (tid == 0) { const float sm = fmaxf(total, 0.0f); T.state[1] = sm; T.state[0] = sm; }
+    } else {
+        float run = fmaxf(tid > 0 ? part[tid - 1] : 0.0f, old_max);   // buf_max.max(*max)
+        for (uint32_t k = lo; k < hi; ++k) { run = fmaxf(T.peaks[k], run); T.runmax[k] = run; }
+        __syncthreads();
+        if (tid == 0) T.state[0] = fmaxf(total, old_max);
+    }
+}
+
+// K9a: buf.scale(len, 1.0 / max) (extensions.rs:328) + pan + gain, in place
+template <bool VEC>
+__global__ void __launch_bounds__(TDG_THREADS) k_norm_scale(const NormScaleTask* __restrict__ tasks) {
+    __shared__ NormScaleTask T;
+    load_task(&T, tasks + blockIdx.y);
+    const uint32_t k = blockIdx.x;
+    if (k >= T.h.n_chunks) return;
+    const uint32_t bl = T.h.bl;
+    const uint64_t p0 = (uint64_t)k * bl;
+    const float f = 1.0f / T.runmax[k];
+    for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
+        const int nv = min(4u, bl - i);
+        float l[4], r[4];
+        ld4<VEC>(T.h.out_l, p0 + i, nv, l);
+        ld4<VEC>(T.h.out_r, p0 + i, nv, r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { l[j] *= f; r[j] *= f; apply_pg(l[j], r[j], T.h.pg); }
+        st4<VEC>(T.h.out_l, p0 + i, nv, l);
+        st4<VEC>(T.h.out_r, p0 + i, nv, r);
+    }
+}
+
+// ------------------------------------------------------------------------------------ K2: sample gathers
+// sample_loop_gen (extensions.rs:331-341): buf[i] = sample[(t + i) % L]
+template <bool VEC>
+__global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __restrict__ tasks) {
+    __shared__ LoopTask T;
+    load_task(&T, tasks + blockIdx.y);
+    const uint32_t k = blockIdx.x;
+    if (k >= T.h.n_chunks) return;
+    const uint32_t bl = T.h.bl;
+    const uint64_t p0 = (uint64_t)k * bl;
+    for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
+        const int nv = min(4u, bl - i);
+        uint64_t s = (T.t0 + p0 + i) % T.len;
+        float l[4], r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            l[j] = __ldg(T.sl + s); r[j] = __ldg(T.sr + s);
+            apply_pg(l[j], r[j], T.h.pg);
+            if (++s == T.len) s = 0;
+        }
+        st4<VEC>(T.h.out_l, p0 + i, nv, l);
+        st4<VEC>(T.h.out_r, p0 + i, nv, r);
+    }
+}
+
+// sample_multi_gen (extensions.rs:344-381): every live hit adds sample[pos]*vel in deque order.
+// All hits share one sample length, so the live set at frame p is the contiguous range of hits with
+// start in (p - L, p]; hits are sorted by start (push order).
+template <bool VEC>
+__global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    __shared__ MultiTask T;
+    load_task(&T, tasks + blockIdx.y);
+    const uint32_t k = blockIdx.x;
+    if (k >= T.h.n_chunks) return;
+    const uint32_t bl = T.h.bl;
+    const int64_t p0 = (int64_t)k * bl;
+    const MultiHit* hits = reinterpret_cast<const MultiHit*>(blob + T.hits_off);
+    // candidates for this chunk: start > p0 - L  and  start <= p0 + bl - 1
+    uint32_t lo = 0, hi = T.n_hits;
+    { uint32_t a = 0, b = T.n_hits; const int64_t key = p0 - (int64_t)T.len;
+      while (a < b) { uint32_t m = (a + b) >> 1; if (hits[m].start > key) b = m; else a = m + 1; } lo = a; }
+    { uint32_t a = lo, b = T.n_hits; const int64_t key = p0 + (int64_t)bl - 1;
+      while (a < b) { uint32_t m = (a + b) >> 1; if (hits[m].start > key) b = m; else a = m + 1; } hi = a; }
+    for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
+        const int nv = min(4u, bl - i);
+        float l[4] = {0.0f, 0.0f, 0.0f, 0.0f}, r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (uint32_t h = lo; h < hi; ++h) {
+            const int64_t start = hits[h].start; const float vel = hits[h].vel;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t pos = p0 + i + j - start;
+                if (pos >= 0 && pos < (int64_t)T.len) {
+                    l[j] += __ldg(T.sl + pos) * vel;
+                    r[j] += __ldg(T.sr + pos) * vel;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) apply_pg(l[j], r[j], T.h.pg);
+        st4<VEC>(T.h.out_l, (uint64_t)p0 + i, nv, l);
+        st4<VEC>(T.h.out_r, (uint64_t)p0 + i, nv, r);
+    }
+}
+
+// sample_lerp_gen (extensions.rs:384-421): primary = last hit at or before the frame, ghost = the
+// one before it, cross-faded while the countdown (reset by each hit) runs.
+template <bool VEC>
+__global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    __shared__ LerpTask T;
+    load_task(&T, tasks + blockIdx.y);
+    const uint32_t k = blockIdx.x;
+    if (k >= T.h.n_chunks) return;
+    const uint32_t bl = T.h.bl;
+    const int64_t p0 = (int64_t)k * bl;
+    const LerpHit* hits = reinterpret_cast<const LerpHit*>(blob + T.hits_off);
+    // index of the last hit with frame <= p0 (entries 0 and 1 are the carried ghost / primary)
+    uint32_t base;
+    { uint32_t a = 0, b = T.n_hits;
+      while (a < b) { uint32_t m = (a + b) >> 1; if (hits[m].frame > p0) b = m; else a = m + 1; } base = a - 1; }
+    const int64_t lm1 = (int64_t)T.len - 1;
+    for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
+        const int nv = min(4u, bl - i);
+        float l[4], r[4];
+        uint32_t idx = base;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t p = p0 + i + j;
+            while (idx + 1 < T.n_hits && hits[idx + 1].frame <= p) ++idx;
+            const LerpHit P = hits[idx];
+            const int64_t ppos = min(max(p - P.pos_origin, (int64_t)0), lm1);
+            float lv = __ldg(T.sl + ppos) * P.vel;
+            float rv = __ldg(T.sr + ppos) * P.vel;
+            const int64_t c_before = (int64_t)T.lerp_len - (p - P.cd_origin);
+            if (c_before > 0) {
+                const LerpHit G = hits[idx - 1];
+                const float t = (float)(c_before - 1) / (float)T.lerp_len;
+                const int64_t gpos = min(max(p - G.pos_origin, (int64_t)0), lm1);
+                const float gl = __ldg(T.sl + gpos) * G.vel;
+                const float gr = __ldg(T.sr + gpos) * G.vel;
+                lv = gl * t + lv * (1.0f - t);
+                rv = gr * t + rv * (1.0f - t);
+            }
+            apply_pg(lv, rv, T.h.pg);
+            l[j] = lv; r[j] = rv;
+        }
+        st4<VEC>(T.h.out_l, (uint64_t)p0 + i, nv, l);
+        st4<VEC>(T.h.out_r, (uint64_t)p0 + i, nv, r);
+    }
+}
+
+// ------------------------------------------------------------------------------------ K5: voices
+// debug_sine_gen / synth_gen / sampsyn_gen (extensions.rs:423-578).  The host planner turns the
+// floww events into per-chunk voice segments in push order; every frame sums its live voices
+// sequentially in that order (f32 summation order is part of the contract).  Segments are staged
+// through shared memory in batches; a SampSyn wavetable is staged in shared memory when it fits.
+#define TDG_SEG_BATCH 64
+
+__device__ __forceinline__ float wavetable_eval(const float* __restrict__ tab, uint32_t n_frames,
+                                                uint32_t n_phase, float fps, float hz, float t) {
+    float ph = t * hz;
+    ph = ph - floorf(ph);
+    const float x = ph * (float)n_phase;
+    uint32_t i0 = (uint32_t)x;
+    if (i0 >= n_phase) i0 = n_phase - 1;
+    const float fx = x - (float)i0;
+    uint32_t i1 = i0 + 1; if (i1 >= n_phase) i1 = 0;
+    float y = t * fps;
+    const float ymax = (float)(n_frames - 1);
+    if (!(y > 0.0f)) y = 0.0f;
+    if (y > ymax) y = ymax;
+    const uint32_t j0 = (uint32_t)y;
+    uint32_t j1 = j0 + 1; if (j1 >= n_frames) j1 = n_frames - 1;
+    const float fy = y - (float)j0;
+    const float* r0 = tab + (size_t)j0 * n_phase;
+    const float* r1 = tab + (size_t)j1 * n_phase;
+    const float a = r0[i0] + fx * (r0[i1] - r0[i0]);
+    const float b = r1[i0] + fx * (r1[i1] - r1[i0]);
+    return a + fy * (b - a);
+}
+
+template <int KIND, bool VEC, bool TAB_SMEM>
+__global__ void __launch_bounds__(TDG_THREADS) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    extern __shared__ __align__(16) float dyn_smem[];
+    __shared__ VoiceTask T;
+    __shared__ VoiceSeg segs[TDG_SEG_BATCH];
+    load_task(&T, tasks + blockIdx.y);
+    const uint32_t k = blockIdx.x;
+    if (k >= T.h.n_chunks) return;
+    const uint32_t bl = T.h.bl;
+    const uint64_t p0 = (uint64_t)k * bl;
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
+    const uint32_t s_lo = sp[k], s_hi = sp[k + 1];
+    const VoiceSeg* gsegs = reinterpret_cast<const VoiceSeg*>(blob + T.seg_off);
+    const float* tab = T.table;
+    if (KIND == VOICE_SAMPSYN && TAB_SMEM) {
+        const uint32_t n = T.n_frames * T.n_phase;
+        for (uint32_t i = threadIdx.x; i < n; i += TDG_THREADS) dyn_smem[i] = T.table[i];
+        tab = dyn_smem;
+        __syncthreads();
+    }
+    const float fsr = (float)T.sr;
+    for (uint32_t i = threadIdx.x * 4; i < bl || (i - threadIdx.x * 4) < bl; i += TDG_THREADS * 4) {
+        // (loop bound is block-uniform: every thread takes part in the staging barriers)
+        const bool active = i < bl;
+        const int nv = active ? (int)min(4u, bl - i) : 0;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float time[4], off[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            time[j] = (float)(T.t0 + p0 + i + j) / fsr;        // (t + i) as f32 / sr as f32
+            off[j] = (float)(i + j) / fsr;                     // i as f32 / sr as f32
+        }
+        for (uint32_t sb = s_lo; sb < s_hi; sb += TDG_SEG_BATCH) {
+            const uint32_t nb = min((uint32_t)TDG_SEG_BATCH, s_hi - sb);
+            __syncthreads();
+            {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(gsegs + sb);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(segs);
+                for (uint32_t w = threadIdx.x; w < nb * (uint32_t)(sizeof(VoiceSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
+            }
+            __syncthreads();
+            if (!active) continue;
+            for (uint32_t s = 0; s < nb; ++s) {
+                const VoiceSeg sg = segs[s];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t fi = i + j;
+                    if (fi < sg.ia || fi >= sg.ib) continue;
+                    float smp;
+                    if (KIND == VOICE_DEBUG_SINE) {                       // extensions.rs:450-454
+                        smp = sinf(m_osc_arg(time[j], sg.hz)) * sg.vel;
+                    } else if (KIND == VOICE_SYNTH) {                     // extensions.rs:500-522
+                        const float env_time = sg.env_t + off[j];
+                        float sn = 0.0f;
+                        if (T.sq_vol > 0.0f || T.tf_vol > 0.0f) sn = sinf(m_osc_arg(time[j], sg.hz));
+                        smp = 0.0f;
+                        if (T.sq_vol > 0.0f) {
+                            const float e = sg.rel_t == 0.0f ? m_apply_ads(T.sq, env_time) : m_apply_r_rt(T.sq, env_time, sg.rel_t);
+                            smp += m_square_from_sin(sn, T.sq_z) * sg.vel * e * T.sq_vol;
+                        }
+                        if (T.tf_vol > 0.0f) {
+                            const float e = sg.rel_t == 0.0f ? m_apply_ads(T.tf, env_time) : m_apply_r_rt(T.tf, env_time, sg.rel_t);
+                            smp += m_topflat_from_sin(sn, T.tf_z) * sg.vel * e * T.tf_vol;
+                        }
+                        if (T.tr_vol > 0.0f) {
+                            const float e = sg.rel_t == 0.0f ? m_apply_ads(T.tr, env_time) : m_apply_r_rt(T.tr, env_time, sg.rel_t);
+                            smp += m_triangle(time[j], sg.hz) * sg.vel * e * T.tr_vol;
+                        }
+                        smp *= T.amp_mul;
+                    } else {                                              // extensions.rs:560-571
+                        const float env_time = sg.env_t + off[j];
+                        const float e = sg.rel_t == 0.0f ? m_apply_ads(T.adsr, env_time) : m_apply_r_rt(T.adsr, env_time, sg.rel_t);
+                        const float vel = sg.vel * e * T.amp_mul;
+                        smp = 0.0f;
+                        smp += wavetable_eval(tab, T.n_frames, T.n_phase, T.fps, sg.hz, env_time + sg.rel_t) * vel;
+                    }
+                    acc[j] += smp;
+                }
+            }
+        }
+        if (active) {
+            float l[4], r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { l[j] = acc[j]; r[j] = acc[j]; apply_pg(l[j], r[j], T.h.pg); }
+            st4<VEC>(T.h.out_l, p0 + i, nv, l);
+            st4<VEC>(T.h.out_r, p0 + i, nv, r);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ K7: band pass scan
+// y <- y + g*(x - y) is the affine map y -> (1-g)*y + g*x.  A thread owns 8 consecutive frames: it
+// folds them from a zero state (B) with decay A = (1-g)^8, a warp-shuffle scan composes the maps
+// across the block, tile aggregates are scanned across blocks, and the final pass re-runs the
+// reference's exact operation sequence from the carried-in state.  Only the carried-in state is
+// reassociated (tolerance in DESIGN.md); inside a run the arithmetic is the reference's.
+struct Aff { float al, ah, b0, b1, b2, b3; };       // (lprevl, lprevr) decay al; (hprevl, hprevr) decay ah
+__device__ __forceinline__ Aff aff_id() { return Aff{1.0f, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f}; }
+__device__ __forceinline__ Aff aff_then(const Aff& f, const Aff& g) {   // apply f first, then g
+    return Aff{f.al * g.al, f.ah * g.ah, fmaf(g.al, f.b0, g.b0), fmaf(g.al, f.b1, g.b1),
+               fmaf(g.ah, f.b2, g.b2), fmaf(g.ah, f.b3, g.b3)};
+}
+__device__ __forceinline__ Aff aff_shfl_up(const Aff& a, int d) {
+    return Aff{__shfl_up_sync(0xffffffffu, a.al, d), __shfl_up_sync(0xffffffffu, a.ah, d),
+               __shfl_up_sync(0xffffffffu, a.b0, d), __shfl_up_sync(0xffffffffu, a.b1, d),
+               __shfl_up_sync(0xffffffffu, a.b2, d), __shfl_up_sync(0xffffffffu, a.b3, d)};
+}
+// exclusive prefix of per-thread maps over the block (thread order), plus the block total
+__device__ __forceinline__ Aff block_aff_scan(const Aff& mine, Aff* total) {
+    __shared__ Aff wtot[32];
+    const int ln = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    Aff inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Aff up = aff_shfl_up(inc, d);
+        if (ln >= d) inc = aff_then(up, inc);
+    }
+    if (ln == 31) wtot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        Aff t = ln < nw ? wtot[ln] : aff_id();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Aff up = aff_shfl_up(t, d);
+            if (ln >= d) t = aff_then(up, t);
+        }
+        if (ln < nw) wtot[ln] = t;     // inclusive over warps
+    }
+    __syncthreads();
+    Aff exc = aff_shfl_up(inc, 1);
+    if (ln == 0) exc = aff_id();
+    if (w > 0) exc = aff_then(wtot[w - 1], exc);
+    if (total) *total = wtot[nw - 1];
+    __syncthreads();
+    return exc;
+}
+
+template <bool VEC>
+__device__ __forceinline__ void bp_load_run(const BpTask& T, const float* const* ins, uint64_t p, int nv,
+                                            float (&xl)[8], float (&xr)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { xl[j] = 0.0f; xr[j] = 0.0f; }
+    for (uint32_t a = 0; a < T.n_in; ++a) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float x[4], y[4];
+            const int nvh = max(0, min(4, nv - 4 * h));
+            if (VEC || nvh > 0) {
+                ld4<VEC>(ins[2 * a], p + 4 * h, nvh, x);
+                ld4<VEC>(ins[2 * a + 1], p + 4 * h, nvh, y);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { xl[4 * h + j] += x[j]; xr[4 * h + j] += y[j]; }
+            }
+        }
+    }
+}
+__device__ __forceinline__ Aff bp_fold_run(const BpTask& T, const float (&xl)[8], const float (&xr)[8], int nv) {
+    float ll = 0.0f, lr = 0.0f, hl = 0.0f, hr = 0.0f, al = 1.0f, ah = 1.0f;
+    const float dl = 1.0f - T.lgamma, dh = 1.0f - T.hgamma;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < nv) {
+            ll = ll + T.lgamma * (xl[j] - ll); lr = lr + T.lgamma * (xr[j] - lr);
+            hl = hl + T.hgamma * (xl[j] - hl); hr = hr + T.hgamma * (xr[j] - hr);
+            al *= dl; ah *= dh;
+        }
+    }
+    return Aff{al, ah, ll, lr, hl, hr};
+}
+
+// pass A: per-tile aggregate (end state from zero, decay)
+template <bool VEC>
+__global__ void __launch_bounds__(kBpThreads) k_bp_aggregate(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    __shared__ BpTask T;
+    load_task(&T, tasks + blockIdx.y);
+    if (blockIdx.x >= T.n_tiles) return;
+    const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
+    const uint64_t p = (uint64_t)blockIdx.x * kBpTile + (uint64_t)threadIdx.x * 8;
+    const int nv = p >= T.h.n_frames ? 0 : (int)min((uint64_t)8, T.h.n_frames - p);
+    float xl[8], xr[8];
+    bp_load_run<VEC>(T, ins, p, nv, xl, xr);
+    Aff mine = bp_fold_run(T, xl, xr, nv), total;
+    block_aff_scan(mine, &total);
+    if (threadIdx.x == 0) {
+        float* a = T.agg + (size_t)blockIdx.x * 8;
+        a[0] = total.b0; a[1] = total.b1; a[2] = total.b2; a[3] = total.b3; a[4] = total.al; a[5] = total.ah;
+    }
+}
+// pass B: scan of tile aggregates -> state entering every tile; one block per filter vertex
+__global__ void __launch_bounds__(kBpThreads) k_bp_carry(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    __shared__ BpTask T;
+    __shared__ float init[4];
+    load_task(&T, tasks + blockIdx.x);
+    if (threadIdx.x == 0) {
+        if (T.first) {                                          // extensions.rs:664-670
+            const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
+            float l = 0.0f, r = 0.0f;
+            for (uint32_t a = 0; a < T.n_in; ++a) { l += ins[2 * a][0]; r += ins[2 * a + 1][0]; }
+            init[0] = l; init[1] = r; init[2] = l; init[3] = r;
+        } else {
+            init[0] = T.state[0]; init[1] = T.state[1]; init[2] = T.state[2]; init[3] = T.state[3];
+        }
+    }
+    __syncthreads();
+    const uint32_t n = T.n_tiles, per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+    Aff mine = aff_id();
+    for (uint32_t t = lo; t < hi; ++t) {
+        const float* a = T.agg + (size_t)t * 8;
+        mine = aff_then(mine, Aff{a[4], a[5], a[0], a[1], a[2], a[3]});
+    }
+    Aff exc = block_aff_scan(mine, nullptr);
+    float c0 = fmaf(exc.al, init[0], exc.b0), c1 = fmaf(exc.al, init[1], exc.b1);
+    float c2 = fmaf(exc.ah, init[2], exc.b2), c3 = fmaf(exc.ah, init[3], exc.b3);
+    for (uint32_t t = lo; t < hi; ++t) {
+        float* c = T.carry + (size_t)t * 4;
+        c[0] = c0; c[1] = c1; c[2] = c2; c[3] = c3;
+        const float* a = T.agg + (size_t)t * 8;
+        c0 = fmaf(a[4], c0, a[0]); c1 = fmaf(a[4], c1, a[1]); c2 = fmaf(a[5], c2, a[2]); c3 = fmaf(a[5], c3, a[3]);
+    }
+}
+// pass C: exact recurrence from the carried-in state + cut/pass mix + pan + gain
+template <bool VEC>
+__global__ void __launch_bounds__(kBpThreads) k_bp_apply(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    __shared__ BpTask T;
+    load_task(&T, tasks + blockIdx.y);
+    if (blockIdx.x >= T.n_tiles) return;
+    const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
+    const uint64_t p = (uint64_t)blockIdx.x * kBpTile + (uint64_t)threadIdx.x * 8;
+    const int nv = p >= T.h.n_frames ? 0 : (int)min((uint64_t)8, T.h.n_frames - p);
+    float xl[8], xr[8];
+    bp_load_run<VEC>(T, ins, p, nv, xl, xr);
+    const Aff mine = bp_fold_run(T, xl, xr, nv);
+    const Aff exc = block_aff_scan(mine, nullptr);
+    const float* c = T.carry + (size_t)blockIdx.x * 4;
+    float ll = fmaf(exc.al, c[0], exc.b0), lr = fmaf(exc.al, c[1], exc.b1);
+    float hl = fmaf(exc.ah, c[2], exc.b2), hr = fmaf(exc.ah, c[3], exc.b3);
+    const float lmul = T.lgamma == 0.0f ? 0.0f : 1.0f, hmul = T.hgamma == 0.0f ? 0.0f : 1.0f;
+    const float pass_mul = T.pass ? 1.0f : 0.0f, cut_mul = 1.0f - pass_mul;
+    float ol[8], orr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < nv) {                                           // extensions.rs:671-688
+            const float l = xl[j], r = xr[j];
+            ll = ll + T.lgamma * (l - ll); lr = lr + T.lgamma * (r - lr);
+            hl = hl + T.hgamma * (l - hl); hr = hr + T.hgamma * (r - hr);
+            const float cutl = (lmul * ll + hmul * (l - hl)) * 0.5f;
+            const float cutr = (lmul * lr + hmul * (r - hr)) * 0.5f;
+            const float passl = l - cutl;
+            const float passr = r - cutl;                       // sic (extensions.rs:685)
+            float a = cutl * cut_mul + passl * pass_mul;
+            float b = cutr * cut_mul + passr * pass_mul;
+            apply_pg(a, b, T.h.pg);
+            ol[j] = a; orr[j] = b;
+        } else { ol[j] = 0.0f; orr[j] = 0.0f; }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int nvh = max(0, min(4, nv - 4 * h));
+        if (nvh == 0) continue;
+        float a[4] = {ol[4 * h], ol[4 * h + 1], ol[4 * h + 2], ol[4 * h + 3]};
+        float b[4] = {orr[4 * h], orr[4 * h + 1], orr[4 * h + 2], orr[4 * h + 3]};
+        if (VEC && nvh == 4) { st4<true>(T.h.out_l, p + 4 * h, 4, a); st4<true>(T.h.out_r, p + 4 * h, 4, b); }
+        else { st4<false>(T.h.out_l, p + 4 * h, nvh, a); st4<false>(T.h.out_r, p + 4 * h, nvh, b); }
+    }
+    // the run holding the last frame of the pass leaves the state for the next pass
+    if (nv > 0 && p + nv == T.h.n_frames) { T.state[0] = ll; T.state[1] = lr; T.state[2] = hl; T.state[3] = hr; }
+}
+
+// ------------------------------------------------------------------------------------ K9b: quantise
+// (x * amplitude) as i16 | i32 (state.rs:517-532): toward zero, saturating, NaN -> 0; bytes laid out
+// as hound writes them (8-bit offset binary, 16/24/32-bit little endian, L then R).
+__device__ __forceinline__ int quant16(float x, float amp) {
+    int v = __float2int_rz(x * amp);
+    return max(-32768, min(32767, v));
+}
+__global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __restrict__ tasks) {
+    const QuantTask T = tasks[blockIdx.y];
+    const uint64_t f0 = ((uint64_t)blockIdx.x * TDG_THREADS + threadIdx.x) * 4;
+    if (f0 >= T.n) return;
+    const int nv = (int)min((uint64_t)4, T.n - f0);
+    int v[8];
+    bool wide = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float l = j < nv ? T.in_l[f0 + j] : 0.0f, r = j < nv ? T.in_r[f0 + j] : 0.0f;
+        if (T.bd <= 16) { v[2 * j] = quant16(l, T.amp); v[2 * j + 1] = quant16(r, T.amp); }
+        else { v[2 * j] = __float2int_rz(l * T.amp); v[2 * j + 1] = __float2int_rz(r * T.amp); }
+    }
+    if (T.bd == 8) {
+        uint8_t* o = T.out + f0 * 2;
+        uint32_t w[2] = {0, 0};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            wide |= (v[q] < -128 || v[q] > 127);
+            w[q >> 2] |= (uint32_t)((v[q] + 128) & 0xff) << (8 * (q & 3));
+        }
+        if (nv == 4) *reinterpret_cast<uint2*>(o) = make_uint2(w[0], w[1]);
+        else for (int q = 0; q < nv * 2; ++q) o[q] = (uint8_t)((v[q] + 128) & 0xff);
+    } else if (T.bd == 16) {
+        uint8_t* o = T.out + f0 * 4;
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = (uint32_t)(v[2 * q] & 0xffff) | ((uint32_t)(v[2 * q + 1] & 0xffff) << 16);
+        if (nv == 4) *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+        else for (int q = 0; q < nv; ++q) reinterpret_cast<uint32_t*>(o)[q] = w[q];
+    } else if (T.bd == 24) {
+        uint8_t* o = T.out + f0 * 6;
+        uint8_t b[24];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            wide |= (v[q] < -8388608 || v[q] > 8388607);
+            b[3 * q] = (uint8_t)(v[q] & 0xff); b[3 * q + 1] = (uint8_t)((v[q] >> 8) & 0xff); b[3 * q + 2] = (uint8_t)((v[q] >> 16) & 0xff);
+        }
+        if (nv == 4) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                uint32_t lo = b[8 * q] | (b[8 * q + 1] << 8) | (b[8 * q + 2] << 16) | ((uint32_t)b[8 * q + 3] << 24);
+                uint32_t hi = b[8 * q + 4] | (b[8 * q + 5] << 8) | (b[8 * q + 6] << 16) | ((uint32_t)b[8 * q + 7] << 24);
+                reinterpret_cast<uint2*>(o)[q] = make_uint2(lo, hi);
+            }
+        } else for (int q = 0; q < nv * 6; ++q) o[q] = b[q];
+    } else {
+        uint8_t* o = T.out + f0 * 8;
+        if (nv == 4) {
+            reinterpret_cast<uint4*>(o)[0] = make_uint4((uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]);
+            reinterpret_cast<uint4*>(o)[1] = make_uint4((uint32_t)v[4], (uint32_t)v[5], (uint32_t)v[6], (uint32_t)v[7]);
+        } else for (int q = 0; q < nv * 2; ++q) reinterpret_cast<uint32_t*>(o)[q] = (uint32_t)v[q];
+    }
+    if (wide) {
+        // only frames that exist count (padding lanes were zeroed above)
+        atomicOr(T.err, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------ K3: sinc resampler
+// rubato SincFixedIn<f32>, Linear, as restated in DESIGN.md: output j of chunk c sits at
+// idx = last_index_c + (j+1)*t_ratio (f64), interpolating two 256-tap windows of neighbouring
+// sub-phases.  The per-chunk (last_index, n_out) come from the host's exact f64 replay.
+__global__ void __launch_bounds__(128) k_resample(const ResampleTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint64_t n_out_total) {
+    const ResampleTask T = tasks[blockIdx.y];
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const ResampleChunk* ch = reinterpret_cast<const ResampleChunk*>(blob + T.chunk_off);
+    if (T.n_chunks == 0) return;
+    const uint64_t total = ch[T.n_chunks - 1].out_off + ch[T.n_chunks - 1].n_out;
+    if (g >= total || g >= n_out_total) return;
+    uint32_t a = 0, b = T.n_chunks;                  // last chunk with out_off <= g
+    while (b - a > 1) { uint32_t m = (a + b) >> 1; if (ch[m].out_off <= g) a = m; else b = m; }
+    const ResampleChunk C = ch[a];
+    const uint32_t j = (uint32_t)(g - C.out_off);
+    const int sinc_len = 256, factor = 256;
+    const double idx = fma((double)(j + 1), T.t_ratio, C.last_index);
+    const double fl = floor(idx);
+    int64_t i0 = (int64_t)fl;
+    int64_t s0 = (int64_t)floor((idx - fl) * (double)factor);
+    int64_t i1 = i0, s1 = s0 + 1;
+    if (s1 >= factor) { s1 -= factor; i1 += 1; }
+    const double xf = idx * (double)factor;
+    const float frac = (float)(xf - floor(xf));
+    const int64_t base = (int64_t)a * (int64_t)T.chunk;
+    float out[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float* in = c == 0 ? T.in_l : T.in_r;
+        float pts[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int64_t pos = base + (q == 0 ? i0 : i1);
+            const float* sn = T.sincs + (size_t)(q == 0 ? s0 : s1) * sinc_len;
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int t = 0; t < sinc_len; t += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t ps = pos + t + u;
+                    const float w = (ps >= 0 && ps < (int64_t)T.n_in) ? __ldg(in + ps) : 0.0f;
+                    acc[u] += w * __ldg(sn + t + u);
+                }
+            }
+            pts[q] = acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7];
+        }
+        out[c] = (1.0f - frac) * pts[0] + frac * pts[1];
+    }
+    T.out_l[g] = out[0];
+    T.out_r[g] = out[1];
+}
+
+// ------------------------------------------------------------------------------------ sample loading
+// numeric part of SampleBank::add (sample.rs:275-303)
+__global__ void k_deinterleave(const float* __restrict__ lin, uint64_t n_frames, uint32_t stride, uint32_t off_l,
+                               uint32_t off_r, uint32_t mix, float* __restrict__ out_l, float* __restrict__ out_r) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frames) return;
+    if (mix) { const float m = lin[i * 2] + lin[i * 2 + 1]; out_l[i] = m; out_r[i] = m; }   // mix_down, sample.rs:139-147
+    else { out_l[i] = lin[i * stride + off_l]; out_r[i] = lin[i * stride + off_r]; }
+}
+__global__ void k_absmax(const float* __restrict__ x, uint64_t n, int* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        m = absmax_fold(m, x[i]);
+    m = block_max(m);
+    if (threadIdx.x == 0) atomicMax(out_bits, __float_as_int(m));    // m >= 0 and never NaN
+}
+__global__ void k_scale_by_inv(float* __restrict__ x, uint64_t n, const float* __restrict__ max_a, const float* __restrict__ max_b) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float m = max_b ? fmaxf(*max_a, *max_b) : *max_a;          // scan_max (sample.rs:116-118)
+    x[i] *= (1.0f / m);                                              // scale(len, 1.0 / max)
+}
+
+// ------------------------------------------------------------------------------------ launchers
+static inline dim3 grid2(uint64_t x, uint32_t y) { return dim3((unsigned)x, y, 1); }
+
+#define TDG_VEC_DISPATCH(vec, K, ...) do { if (vec) K<true> __VA_ARGS__; else K<false> __VA_ARGS__; } while (0)
+
+cudaError_t launch_fx(const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
+    TDG_VEC_DISPATCH(vec, k_fx, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t, blob));
+    return cudaGetLastError();
+}
+cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s) {
+    k_norm_prefix<<<n, 1024, 0, s>>>(t);
+    return cudaGetLastError();
+}
+cudaError_t launch_norm_scale(const NormScaleTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s) {
+    TDG_VEC_DISPATCH(vec, k_norm_scale, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t));
+    return cudaGetLastError();
+}
+cudaError_t launch_sample_loop(const LoopTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s) {
+    TDG_VEC_DISPATCH(vec, k_sample_loop, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t));
+    return cudaGetLastError();
+}
+cudaError_t launch_sample_multi(const MultiTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
+    TDG_VEC_DISPATCH(vec, k_sample_multi, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t, blob));
+    return cudaGetLastError();
+}
+cudaError_t launch_sample_lerp(const LerpTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
+    TDG_VEC_DISPATCH(vec, k_sample_lerp, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t, blob));
+    return cudaGetLastError();
+}
+
+template <int KIND, bool VEC, bool TS>
+static cudaError_t launch_voice_t(const VoiceTask* t, uint32_t n, uint32_t max_chunks, size_t smem, const uint8_t* blob, cudaStream_t s) {
+    if (smem > 0) {
+        cudaError_t e = cudaFuncSetAttribute(k_voice<KIND, VEC, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_voice<KIND, VEC, TS><<<grid2(max_chunks, n), TDG_THREADS, smem, s>>>(t, blob);
+    return cudaGetLastError();
+}
+cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool vec, size_t table_smem_bytes,
+                         const uint8_t* blob, cudaStream_t s) {
+    if (kind == VOICE_DEBUG_SINE)
+        return vec ? launch_voice_t<VOICE_DEBUG_SINE, true, false>(t, n, max_chunks, 0, blob, s)
+                   : launch_voice_t<VOICE_DEBUG_SINE, false, false>(t, n, max_chunks, 0, blob, s);
+    if (kind == VOICE_SYNTH)
+        return vec ? launch_voice_t<VOICE_SYNTH, true, false>(t, n, max_chunks, 0, blob, s)
+                   : launch_voice_t<VOICE_SYNTH, false, false>(t, n, max_chunks, 0, blob, s);
+    if (table_smem_bytes > 0)
+        return vec ? launch_voice_t<VOICE_SAMPSYN, true, true>(t, n, max_chunks, table_smem_bytes, blob, s)
+                   : launch_voice_t<VOICE_SAMPSYN, false, true>(t, n, max_chunks, table_smem_bytes, blob, s);
+    return vec ? launch_voice_t<VOICE_SAMPSYN, true, false>(t, n, max_chunks, 0, blob, s)
+               : launch_voice_t<VOICE_SAMPSYN, false, false>(t, n, max_chunks, 0, blob, s);
+}
+
+cudaError_t launch_bp(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {
+    TDG_VEC_DISPATCH(vec, k_bp_aggregate, <<<grid2(max_tiles, n), kBpThreads, 0, s>>>(t, blob));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_bp_carry<<<n, kBpThreads, 0, s>>>(t, blob);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    TDG_VEC_DISPATCH(vec, k_bp_apply, <<<grid2(max_tiles, n), kBpThreads, 0, s>>>(t, blob));
+    return cudaGetLastError();
+}
+cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_frames, cudaStream_t s) {
+    const uint64_t blocks = (max_frames + TDG_THREADS * 4 - 1) / (TDG_THREADS * 4);
+    k_quantise<<<grid2(blocks ? blocks : 1, n), TDG_THREADS, 0, s>>>(t);
+    return cudaGetLastError();
+}
+cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, const uint8_t* blob, cudaStream_t s) {
+    const uint64_t blocks = (max_out + 127) / 128;
+    k_resample<<<grid2(blocks ? blocks : 1, n), 128, 0, s>>>(t, blob, max_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_deinterleave(const float* lin, uint64_t n_frames, uint32_t stride, uint32_t off_l, uint32_t off_r,
+                                uint32_t mix, float* out_l, float* out_r, cudaStream_t s) {
+    if (n_frames == 0) return cudaSuccess;
+    k_deinterleave<<<(unsigned)((n_frames + 255) / 256), 256, 0, s>>>(lin, n_frames, stride, off_l, off_r, mix, out_l, out_r);
+    return cudaGetLastError();
+}
+cudaError_t launch_absmax(const float* x, uint64_t n, int* out_bits, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)min((uint64_t)1184, (n + 255) / 256);
+    k_absmax<<<blocks, 256, 0, s>>>(x, n, out_bits);
+    return cudaGetLastError();
+}
+cudaError_t launch_scale_by_inv(float* x, uint64_t n, const float* max_a, const float* max_b, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    k_scale_by_inv<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, max_a, max_b);
+    return cudaGetLastError();
+}
+
+}  // namespace tdg

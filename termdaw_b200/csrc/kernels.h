@@ -1,0 +1,27 @@
+// kernels.h — launchers of the sm_100a kernels in kernels.cu (one launch = one kernel class at one
+// DAG level for every task in the batch).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tdg_types.h"
+
+namespace tdg {
+
+cudaError_t launch_fx(const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s);
+cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s);
+cudaError_t launch_norm_scale(const NormScaleTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s);
+cudaError_t launch_sample_loop(const LoopTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s);
+cudaError_t launch_sample_multi(const MultiTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s);
+cudaError_t launch_sample_lerp(const LerpTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s);
+cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool vec, size_t table_smem_bytes,
+                         const uint8_t* blob, cudaStream_t s);
+// three launches: tile aggregates, carry scan, apply
+cudaError_t launch_bp(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
+cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_frames, cudaStream_t s);
+cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, const uint8_t* blob, cudaStream_t s);
+cudaError_t launch_deinterleave(const float* lin, uint64_t n_frames, uint32_t stride, uint32_t off_l, uint32_t off_r,
+                                uint32_t mix, float* out_l, float* out_r, cudaStream_t s);
+cudaError_t launch_absmax(const float* x, uint64_t n, int* out_bits, cudaStream_t s);
+cudaError_t launch_scale_by_inv(float* x, uint64_t n, const float* max_a, const float* max_b, cudaStream_t s);
+
+}  // namespace tdg

@@ -1,0 +1,137 @@
+// tdg_types.h — plain structs shared by the host planner and the sm_100a kernels.
+//
+// A "pass" is one whole-timeline evaluation of a project's graph (a normalize scan or a render):
+// `n_chunks` chunks of `bl` frames.  Every reachable vertex owns one planar stereo fp32 buffer
+// [L: n_pad][R: n_pad] resident in HBM for the pass; a "task" is one vertex evaluated over the whole
+// pass by one kernel class, and a launch covers all tasks of one class at one DAG level for every
+// project in the batch (grid.y = task, grid.x = chunk / tile).
+//
+// Offsets named *_off are byte offsets into the per-pass "plan blob" (tables the host planner
+// derives from floww events), which the kernels receive as a base pointer.
+#pragma once
+#include <stdint.h>
+
+namespace tdg {
+
+struct PanGain {            // Sample::apply_angle / apply_gain (sample.rs:97-114), constants from the host
+    float l_amp, r_amp, gain;
+    uint32_t flags;         // bit0: apply angle (|angle| >= 0.001), bit1: apply gain (|gain-1| >= 0.001)
+};
+
+struct AdsrConfD {          // adsr.rs:2-12
+    float std_vel, attack_sec, attack_vel, decay_sec, decay_vel, sustain_sec, sustain_vel, release_sec,
+        release_vel;
+};
+
+struct TaskHdr {
+    float* out_l;
+    float* out_r;
+    uint64_t n_frames;      // n_chunks * bl
+    uint32_t n_chunks, bl;
+    PanGain pg;
+};
+
+// ---- per-chunk tables -------------------------------------------------------------------------
+struct AdsrSeg {            // Adsr vertex state valid from frame offset `ia` of its chunk (extensions.rs:61-69)
+    uint32_t ia, flags;     // flags bit0: this single frame is passed through un-enveloped (extensions.rs:633-635)
+    float pt, pv, pr, gt, gv, gr;   // primary (t, vel, release_val), ghost (t, vel, release_val)
+};
+struct VoiceSeg {           // one voice over frames [ia, ib) of one chunk, in voice (push) order
+    float hz, vel, env_t, rel_t;
+    uint32_t ia, ib, pad0, pad1;
+};
+struct MultiHit { int64_t start; float vel, pad; };                       // pass-relative first frame
+struct LerpHit { int64_t frame, pos_origin, cd_origin; float vel, pad; }; // see plan_sample_lerp
+
+// ---- tasks ------------------------------------------------------------------------------------
+enum FxMode : uint32_t { FX_SUM = 0, FX_ADSR = 1, FX_NORM_PEAK = 2 };
+
+struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan + gain, one kernel
+    TaskHdr h;
+    uint32_t mode, n_in;
+    uint64_t in_off;        // blob: n_in pairs of (const float* l, const float* r)
+    AdsrConfD conf;
+    float wet;
+    uint32_t use_off, use_max, sr;
+    uint64_t seg_ptr_off;   // blob: uint32[n_chunks+1], indices into the AdsrSeg array
+    uint64_t seg_off;       // blob: AdsrSeg[]
+    float* peaks;           // FX_NORM_PEAK: [n_chunks] max |x| over L and R of the summed chunk
+};
+
+struct NormPrefixTask {     // normalize_gen's max bookkeeping (extensions.rs:321-329), one block per task
+    const float* peaks;
+    float* runmax;          // [n_chunks] the `max` each chunk is scaled by
+    float* state;           // device-resident (max, scan_max) of this vertex
+    uint32_t n_chunks, is_scan;
+};
+struct NormScaleTask {      // buf *= 1/max, then pan + gain, in place
+    TaskHdr h;
+    const float* runmax;
+};
+
+struct LoopTask { TaskHdr h; const float* sl; const float* sr; uint64_t len, t0; };
+struct MultiTask { TaskHdr h; const float* sl; const float* sr; uint64_t len; uint64_t hits_off; uint32_t n_hits, pad; };
+struct LerpTask {
+    TaskHdr h; const float* sl; const float* sr; uint64_t len; uint64_t hits_off;
+    uint32_t n_hits, lerp_len;
+};
+
+enum VoiceKind : uint32_t { VOICE_DEBUG_SINE = 0, VOICE_SYNTH = 1, VOICE_SAMPSYN = 2 };
+struct VoiceTask {
+    TaskHdr h;
+    uint32_t kind, sr;
+    uint64_t t0;            // graph time of pass frame 0 (time = (t0 + p) as f32 / sr as f32)
+    uint64_t seg_ptr_off;   // blob: uint32[n_chunks+1]
+    uint64_t seg_off;       // blob: VoiceSeg[]
+    // Synth (extensions.rs:44-50)
+    float sq_vol, sq_z, tf_vol, tf_z, tr_vol, amp_mul;
+    AdsrConfD sq, tf, tr;
+    // SampSyn (extensions.rs:51-56): adsr + wavetable [n_frames][n_phase]
+    AdsrConfD adsr;
+    const float* table;
+    uint32_t n_frames, n_phase;
+    float fps;
+    uint32_t table_in_smem;
+};
+
+struct BpTask {             // band_pass_gen (extensions.rs:654-689) as a chunked linear-recurrence scan
+    TaskHdr h;
+    uint32_t n_in, pass;
+    uint64_t in_off;
+    float lgamma, hgamma;
+    uint32_t first;         // seed the four states with frame 0 of this pass (extensions.rs:664-670)
+    uint32_t n_tiles;
+    float* state;           // device-resident lprevl, lprevr, hprevl, hprevr (carried between passes)
+    float* agg;             // [n_tiles][4] end state of each tile started from zero
+    float* carry;           // [n_tiles][4] true state entering each tile
+};
+
+struct QuantTask {          // write_16s / write_32s (state.rs:517-532) + hound's byte layout
+    const float* in_l;
+    const float* in_r;
+    uint8_t* out;
+    uint64_t n;
+    uint32_t bd;
+    float amp;
+    uint32_t* err;          // set non-zero when an 8/24-bit value is too wide
+    uint32_t pad;
+};
+
+struct ResampleTask {       // rubato SincFixedIn restated: one output frame per thread
+    const float* in_l;      // stream; positions < 0 read as 0 (initial zero buffer)
+    const float* in_r;
+    float* out_l;
+    float* out_r;
+    const float* sincs;     // [factor][sinc_len]
+    uint64_t n_in;
+    uint64_t chunk_off;     // blob: ResampleChunk[n_chunks]
+    uint32_t n_chunks, chunk;
+    double t_ratio;
+};
+struct ResampleChunk { double last_index; uint64_t out_off; uint32_t n_out, pad; };
+
+static const int kBpFramesPerThread = 8;
+static const int kBpThreads = 256;
+static const int kBpTile = kBpFramesPerThread * kBpThreads;     // 2048 frames
+
+}  // namespace tdg

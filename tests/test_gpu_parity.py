@@ -1,0 +1,147 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star):
+  * sample indexing / note timing: bit-exact -> graphs without transcendentals must match bit for bit
+    before the IIR (sample_loop / sample_multi / sample_lerp / sampsyn / sum / adsr / normalize);
+  * fp32 pre-quantisation buffers: max-abs <= 1e-5 (relative to max(1, peak) of the buffer, since
+    pre-normalize buffers exceed 1.0); oscillators differ only by CUDA sinf vs glibc sinf (<= 2 ulp);
+  * band pass: the carried-in state of each 8-frame run is a reassociated scan, everything else is
+    the reference's operation order -> stated tolerance 2e-5 * max(1, peak);
+  * PCM: <= 1 LSB at 16 bit; at 24 bit one LSB (1.2e-7) is below one f32 ulp of a full-scale sample,
+    so the 1e-5 fp32 tolerance is what bounds it: <= 96 LSB (1.1e-5 of full scale), and bit-exact
+    graphs are still required to be <= 1 LSB.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, max_abs_diff, pcm_to_int, run_project
+from termdaw_b200 import synthetic as S
+from termdaw_b200.state import Assets, Project
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_IIR = 2e-5
+
+
+def compare(got, want, label, exact_kinds=(), tol=TOL_F32, pcm_lsb=1, report=None):
+    assert got["cs"] == want["cs"]
+    worst = {}
+    for name, (l, r) in want["taps"].items():
+        gl, gr = got["taps"][name]
+        peak = max(1.0, float(np.nanmax(np.abs(np.concatenate([l, r])))))
+        d = max(max_abs_diff(gl, l), max_abs_diff(gr, r))
+        worst[name] = d / peak
+        if any(k in name for k in exact_kinds):
+            assert np.array_equal(gl, l, equal_nan=True) and np.array_equal(gr, r, equal_nan=True), \
+                (label, name, "expected bit-exact", d)
+        else:
+            assert d / peak <= tol, (label, name, d, peak)
+    a, b = pcm_to_int(got["pcm"], got["bd"]), pcm_to_int(want["pcm"], want["bd"])
+    assert a.shape == b.shape, (label, a.shape, b.shape)
+    lsb = int(np.abs(a - b).max()) if a.size else 0
+    if report is not None:
+        report[label] = {"worst_rel_fp32": max(worst.values()) if worst else 0.0, "pcm_lsb": lsb,
+                         "per_vertex": worst}
+    assert lsb <= pcm_lsb, (label, lsb)
+    for k, v in want["norm"].items():
+        assert abs(got["norm"][k] - v) <= tol * max(1.0, abs(v)), (label, k, got["norm"][k], v)
+    return worst, lsb
+
+
+@pytest.fixture(scope="module")
+def report():
+    rep = {}
+    yield rep
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
+        json.dump(rep, f, indent=1, sort_keys=True)
+
+
+def test_config1_readme_example(gpulib, oracle, report):
+    """2 x sampleloop -> normalize, 3 s, sinc down-sampled to 44.1 kHz, 16 bit (configs[0])."""
+    cfg = S.config_1(1.0)
+    got, want = run_project(gpulib, *cfg), run_project(oracle, *cfg)
+    compare(got, want, "config1", exact_kinds=("one", "two"), report=report)
+
+
+def test_config1_flow_a_running_max(gpulib, oracle, report):
+    """refresh -> render without a scan: normalize uses a running max (extensions.rs:326-328)."""
+    cfg = S.config_1(0.5)
+    got, want = run_project(gpulib, *cfg, flow="A"), run_project(oracle, *cfg, flow="A")
+    compare(got, want, "config1_flowA", exact_kinds=("one", "two", "sum"), report=report)
+
+
+def test_config2_synth_adsr_bandpass(gpulib, oracle, report):
+    """floww-driven synth + adsr -> band pass -> normalize, 24 bit (configs[1]), 6 s slice."""
+    cfg = S.config_2(0.1)
+    got, want = run_project(gpulib, *cfg), run_project(oracle, *cfg)
+    compare(got, want, "config2", tol=TOL_IIR, pcm_lsb=96, report=report)
+
+
+def test_config3_wavetable_lerp(gpulib, oracle, report):
+    """wavetable voices + 2 sample_lerp from 44.1/96 kHz sources (configs[2]) scaled to 64 voices, 6 s."""
+    cfg = S.config_3(0.01, voices=64)
+    got, want = run_project(gpulib, *cfg), run_project(oracle, *cfg)
+    compare(got, want, "config3", report=report)
+
+
+def test_config4_mixed_graph(gpulib, oracle, report):
+    """64-vertex mixed graph (configs[3]), 7 s slice, 24 bit."""
+    cfg = S.config_4(0.002, 64)
+    got, want = run_project(gpulib, *cfg), run_project(oracle, *cfg)
+    compare(got, want, "config4", tol=TOL_IIR, pcm_lsb=96, report=report)
+
+
+@pytest.mark.parametrize("index", [0, 1, 2, 3, 4, 5, 6, 7])
+def test_config5_batch_projects(gpulib, oracle, report, index):
+    """projects of the algorithmic-composition batch (configs[4]), 3 s each, 16 bit."""
+    cfg = S.config_5_project(index, 0.1)
+    got, want = run_project(gpulib, *cfg), run_project(oracle, *cfg)
+    compare(got, want, f"config5_{index}", tol=TOL_IIR, report=report)
+
+
+def test_render_many_equals_single(gpulib, oracle):
+    """tdg_render_many over 6 projects == the oracle's per-project renders (scan + render)."""
+    from termdaw_b200 import normalize_scan_many, render_many
+    from termdaw_b200.state import State
+    cfgs = [S.config_5_project(i, 0.05) for i in range(6)]
+    states = []
+    for p, a, s in cfgs:
+        st = State(gpulib, s["psr"], s["bl"], assets=a)
+        assert st.refresh(p), st.messages
+        states.append(st)
+    ctxs = [st.ctx for st in states]
+    normalize_scan_many(gpulib, ctxs, [st.cs for st in states])
+    pcms = render_many(gpulib, ctxs, [st.cs for st in states], [st.render_sr for st in states],
+                       [st.bd for st in states])
+    for (p, a, s), st, pcm in zip(cfgs, states, pcms):
+        want = run_project(oracle, p, a, s, taps=False)
+        x, y = pcm_to_int(pcm, st.bd), pcm_to_int(want["pcm"], want["bd"])
+        assert x.shape == y.shape and np.abs(x - y).max() <= 1
+        st.close()
+
+
+@pytest.mark.parametrize("bd", [8, 16, 24, 32])
+def test_bitdepths(gpulib, oracle, bd):
+    """quantisation to every supported depth (state.rs:515-532) on a bit-exact graph."""
+    p, a, s = S.config_1(0.3)
+    p.set_render_samplerate(48000)
+    p.set_render_bitdepth(bd)
+    got, want = run_project(gpulib, p, a, s), run_project(oracle, p, a, s)
+    assert np.array_equal(got["pcm"], want["pcm"])
+
+
+def test_unsupported_and_errors(gpulib):
+    from termdaw_b200 import Context, TermdawError
+    c = Context(gpulib, 48000, 1024)
+    with pytest.raises(TermdawError) as e:
+        c.add_lv2fx(1.0, 0.0, 1.0, 0)
+    assert e.value.code == -3
+    with pytest.raises(TermdawError) as e:
+        c.add_adsr(1.0, 0.0, 1.0, c.floww_add([], [], []), False, True, -1, [1, 2, 3])
+    assert e.value.code == -4
+    c.close()
