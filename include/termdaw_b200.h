@@ -185,6 +185,16 @@ typedef struct tdg_pass_stats {
     uint64_t voice_frames;   /* voice-frames evaluated by the synth kernels                         */
 } tdg_pass_stats;
 int tdg_last_pass_stats(tdg_ctx* ctx, tdg_pass_stats* out);
+/* Per kernel class figures of the last pass (CUDA events around every launch on the context's
+ * stream; enable with tdg_set_profiling).  For a batched pass they cover the whole batch. */
+typedef struct tdg_kernel_stat {
+    const char* name;        /* kernel (class) name as it appears in ncu                            */
+    uint64_t launches;
+    double device_ms;        /* summed over the launches                                            */
+    uint64_t algorithmic_bytes;
+} tdg_kernel_stat;
+int tdg_set_profiling(tdg_ctx* ctx, int on);
+int tdg_last_pass_kernel_stats(tdg_ctx* ctx, tdg_kernel_stat* out, int cap);
 
 #ifdef __cplusplus
 }

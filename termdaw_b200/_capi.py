@@ -42,6 +42,11 @@ class PassStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_uint64), ("device_ms", C.c_double),
+                ("algorithmic_bytes", C.c_uint64)]
+
+
 def _f32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
 
@@ -109,6 +114,8 @@ class Library:
         "set_normalize_state": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int]),
         "normalize_state_device_ptr": (C.c_void_p, [C.c_void_p, c_i32p]),
         "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
+        "set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+        "last_pass_kernel_stats": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_int]),
     }
     # symbols only the oracle has (scalar maths for the reference's known-answer tests)
     ORACLE_ONLY = {
@@ -314,6 +321,15 @@ class Context:
         n = C.c_int(0)
         p = self.lib.normalize_state_device_ptr(self.h, C.byref(n))
         return p, n.value
+
+    def set_profiling(self, on: bool = True):
+        self._chk(self.lib.set_profiling(self.h, int(on)))
+
+    def last_pass_kernel_stats(self) -> dict:
+        arr = (KernelStat * 32)()
+        n = self.lib.last_pass_kernel_stats(self.h, arr, 32)
+        return {arr[i].name.decode(): {"launches": int(arr[i].launches), "ms": float(arr[i].device_ms),
+                                       "bytes": int(arr[i].algorithmic_bytes)} for i in range(n)}
 
     def last_pass_stats(self) -> dict:
         st = PassStats()

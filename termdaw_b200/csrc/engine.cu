@@ -85,6 +85,8 @@ struct Engine {
     std::map<uint32_t, float*> sinc_tables;     // keyed by the f32 bits of the cutoff
     uint64_t epoch = 0;                          // bumped by every pass (taps of older passes are stale)
     int refs = 0;
+    bool profiling = false;                      // CUDA events around every launch (per-class roofline)
+    std::vector<cudaEvent_t> evpool;
 };
 static std::mutex g_mu;
 static std::map<int, Engine*> g_engines;
@@ -444,12 +446,13 @@ struct PassReq {
     uint32_t err_flag = 0;
 };
 
-template <typename T> struct TaskList { std::vector<T> v; uint32_t max_chunks = 0; };
+template <typename T> struct TaskList { std::vector<T> v; uint32_t max_chunks = 0; uint64_t bytes = 0; };
 struct LevelTasks {
     TaskList<FxTask> fx; TaskList<NormPrefixTask> nprefix; TaskList<NormScaleTask> nscale;
     TaskList<LoopTask> loop; TaskList<MultiTask> multi; TaskList<LerpTask> lerp;
     TaskList<VoiceTask> dsine, synth, sampsyn; TaskList<BpTask> bp;
     size_t sampsyn_smem = 0; bool sampsyn_smem_ok = true;
+    uint64_t bp_agg_bytes = 0;
 };
 
 static void compute_levels(PassReq& r) {
@@ -538,8 +541,8 @@ static int run_pass(std::vector<PassReq>& reqs) {
 
     // ---- 2. plan: tasks + tables into the pinned blob ------------------------------------------
     std::vector<LevelTasks> levels(max_level + 1);
-    std::vector<QuantTask> quants; uint64_t quant_max = 0;
-    std::vector<ResampleTask> resamps; uint64_t resamp_max = 0;
+    std::vector<QuantTask> quants; uint64_t quant_max = 0, quant_bytes = 0;
+    std::vector<ResampleTask> resamps; uint64_t resamp_max = 0, resamp_bytes = 0;
     PinnedBuf& B = g->blob;
     B.size = 0;
     uint64_t algo_bytes_total = 0;
@@ -581,7 +584,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
                 return t;
             };
             switch (hv.kind) {
-                case K_SUM: { LT.fx.v.push_back(fx_task(FX_SUM)); LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch); algo += io_bytes; break; }
+                case K_SUM: { LT.fx.v.push_back(fx_task(FX_SUM)); LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch); algo += io_bytes; LT.fx.bytes += io_bytes; break; }
                 case K_NORMALIZE: {
                     FxTask t = fx_task(FX_NORM_PEAK);
                     float* peaks = reinterpret_cast<float*>(W + r.aux_off[v]);
@@ -593,6 +596,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     NormScaleTask ns; ns.h = h; ns.runmax = runmax;
                     LT.nscale.v.push_back(ns); LT.nscale.max_chunks = std::max(LT.nscale.max_chunks, nch);
                     algo += io_bytes + 16ull * r.n_frames;
+                    LT.fx.bytes += io_bytes; LT.nscale.bytes += 16ull * r.n_frames; LT.nprefix.bytes += 8ull * r.emit_n;
                     break;
                 }
                 case K_ADSR: {
@@ -607,13 +611,13 @@ static int run_pass(std::vector<PassReq>& reqs) {
                         memcpy(B.at<uint8_t>(t.seg_off), so.aseg.data(), so.aseg.size() * sizeof(AdsrSeg));
                         LT.fx.v.push_back(t);
                     }
-                    LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch); algo += io_bytes;
+                    LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch); algo += io_bytes; LT.fx.bytes += io_bytes;
                     break;
                 }
                 case K_BANDPASS: {
                     if (hv.wet < 0.0001f || (hv.lgamma == 0.0f && hv.hgamma == 0.0f)) {   // extensions.rs:657-658
                         LT.fx.v.push_back(fx_task(FX_SUM)); LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch);
-                        algo += io_bytes;
+                        algo += io_bytes; LT.fx.bytes += io_bytes;
                         break;
                     }
                     BpTask t; memset(&t, 0, sizeof t);
@@ -628,6 +632,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     LT.bp.v.push_back(t); LT.bp.max_chunks = std::max(LT.bp.max_chunks, t.n_tiles);
                     hv.bp_first = false;
                     algo += io_bytes + 8ull * hv.edges.size() * r.n_frames;     // inputs are read by both scan passes
+                    LT.bp.bytes += io_bytes; LT.bp_agg_bytes += 8ull * hv.edges.size() * r.n_frames;
                     break;
                 }
                 case K_SAMPLE_LOOP: {
@@ -635,7 +640,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     LoopTask t; t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.t0 = hv.loop_t + r.emit0 * x->bl;
                     LT.loop.v.push_back(t); LT.loop.max_chunks = std::max(LT.loop.max_chunks, nch);
                     hv.loop_t += r.total * x->bl;                                 // extensions.rs:340
-                    algo += 16ull * r.n_frames;
+                    algo += 16ull * r.n_frames; LT.loop.bytes += 16ull * r.n_frames;
                     break;
                 }
                 case K_SAMPLE_MULTI: {
@@ -651,7 +656,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
                         int64_t a = std::max<int64_t>(mh.start, 0), b = std::min<int64_t>(mh.start + (int64_t)s.frames, (int64_t)r.n_frames);
                         if (b > a) gathered += (uint64_t)(b - a);
                     }
-                    algo += 8ull * r.n_frames + 8ull * gathered;
+                    algo += 8ull * r.n_frames + 8ull * gathered; LT.multi.bytes += 8ull * r.n_frames + 8ull * gathered;
                     break;
                 }
                 case K_SAMPLE_LERP: {
@@ -662,7 +667,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     t.hits_off = B.alloc(lhits.size() * sizeof(LerpHit));
                     memcpy(B.at<uint8_t>(t.hits_off), lhits.data(), lhits.size() * sizeof(LerpHit));
                     LT.lerp.v.push_back(t); LT.lerp.max_chunks = std::max(LT.lerp.max_chunks, nch);
-                    algo += 16ull * r.n_frames;
+                    algo += 16ull * r.n_frames; LT.lerp.bytes += 16ull * r.n_frames;
                     break;
                 }
                 case K_DEBUG_SINE: case K_SYNTH: case K_SAMPSYN: {
@@ -674,14 +679,15 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     t.seg_off = B.alloc(std::max<size_t>(so.vseg.size(), 1) * sizeof(VoiceSeg));
                     memcpy(B.at<uint8_t>(t.seg_off), so.vseg.data(), so.vseg.size() * sizeof(VoiceSeg));
                     x->stats.voice_frames += so.voice_frames;
-                    if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nch); }
+                    const uint64_t vbytes = 8ull * r.n_frames + so.vseg.size() * sizeof(VoiceSeg);
+                    if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nch); LT.dsine.bytes += vbytes; }
                     else if (hv.kind == K_SYNTH) {
                         t.kind = VOICE_SYNTH;
                         t.sq_vol = hv.sq.volume; t.sq_z = hv.sq.param; t.tf_vol = hv.tf.volume; t.tf_z = hv.tf.param;
                         t.tr_vol = hv.tr.volume; t.sq = hv.sq.adsr; t.tf = hv.tf.adsr; t.tr = hv.tr.adsr;
                         t.amp_mul = 1.0f / (hv.sq.volume * m_max_vel(hv.sq.adsr) + hv.tf.volume * m_max_vel(hv.tf.adsr) +
                                             hv.tr.volume * m_max_vel(hv.tr.adsr));           // extensions.rs:465-468
-                        LT.synth.v.push_back(t); LT.synth.max_chunks = std::max(LT.synth.max_chunks, nch);
+                        LT.synth.v.push_back(t); LT.synth.max_chunks = std::max(LT.synth.max_chunks, nch); LT.synth.bytes += vbytes;
                     } else {
                         const DevTable& tb = x->tables[hv.table];
                         t.kind = VOICE_SAMPSYN; t.adsr = hv.adsr; t.amp_mul = 1.0f / m_max_vel(hv.adsr);   // extensions.rs:537
@@ -689,7 +695,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
                         const size_t tb_bytes = (size_t)tb.n_frames * tb.n_phase * 4;
                         if (tb_bytes > 160 * 1024) LT.sampsyn_smem_ok = false;
                         LT.sampsyn_smem = std::max(LT.sampsyn_smem, tb_bytes);
-                        LT.sampsyn.v.push_back(t); LT.sampsyn.max_chunks = std::max(LT.sampsyn.max_chunks, nch);
+                        LT.sampsyn.v.push_back(t); LT.sampsyn.max_chunks = std::max(LT.sampsyn.max_chunks, nch); LT.sampsyn.bytes += vbytes;
                     }
                     algo += 8ull * r.n_frames;
                     break;
@@ -716,13 +722,13 @@ static int run_pass(std::vector<PassReq>& reqs) {
                 memcpy(B.at<uint8_t>(rt.chunk_off), r.rs_chunks.data(), r.rs_chunks.size() * sizeof(ResampleChunk));
                 resamps.push_back(rt); resamp_max = std::max(resamp_max, r.rs_total);
                 q.in_l = rt.out_l; q.in_r = rt.out_r; q.n = r.rs_total;
-                algo += 8ull * r.n_frames + 8ull * r.rs_total;
+                algo += 8ull * r.n_frames + 8ull * r.rs_total; resamp_bytes += 8ull * r.n_frames + 8ull * r.rs_total;
             } else {
                 const uint64_t skip = (r.keep0 - r.emit0) * x->bl;
                 q.in_l = ol + skip; q.in_r = orr + skip; q.n = r.out_frames;
             }
             quants.push_back(q); quant_max = std::max(quant_max, q.n);
-            algo += 8ull * q.n + r.pcm_bytes;
+            algo += 8ull * q.n + r.pcm_bytes; quant_bytes += 8ull * q.n + r.pcm_bytes;
         }
         x->stats.algorithmic_bytes = algo; x->stats.frames = r.n_frames;
         algo_bytes_total += algo;
@@ -763,40 +769,42 @@ static int run_pass(std::vector<PassReq>& reqs) {
     const double t_h2d_issued = now_ms();
     CU(cudaEventRecord(g->ev0, s));
     uint64_t launches = 0;
-    const uint32_t kMaxY = 65535;
-    // gridDim.y is limited to 65535 tasks per launch
-#define LAUNCH_SPLIT(list, T, off, expr) \
+    const uint32_t kMaxY = 65535;          // gridDim.y limit: tasks per launch
+    struct Timed { int cls; uint64_t bytes; };
+    std::vector<Timed> timed;
+    auto ev_at = [&](size_t i) -> cudaEvent_t {
+        while (g->evpool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); g->evpool.push_back(e); }
+        return g->evpool[i];
+    };
+#define LAUNCH_SPLIT(cls, list, T, off, bytes_, expr) \
     for (size_t b0 = 0; b0 < (list).v.size(); b0 += kMaxY) { \
         const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, (list).v.size() - b0); \
         const T* tp = reinterpret_cast<const T*>(D + (off)) + b0; \
-        CU(expr); ++launches; }
+        if (g->profiling) CU(cudaEventRecord(ev_at(2 * timed.size()), s)); \
+        CU(expr); ++launches; \
+        if (g->profiling) { CU(cudaEventRecord(ev_at(2 * timed.size() + 1), s)); \
+                            timed.push_back({cls, (bytes_) * nb / std::max<size_t>((list).v.size(), 1)}); } }
     for (size_t L = 0; L < levels.size(); ++L) {
         LevelTasks& T = levels[L];
         const bool vec = all_vec;
-        LAUNCH_SPLIT(T.loop, LoopTask, offs[L].loop, launch_sample_loop(tp, nb, T.loop.max_chunks, vec, s));
-        LAUNCH_SPLIT(T.multi, MultiTask, offs[L].multi, launch_sample_multi(tp, nb, T.multi.max_chunks, vec, D, s));
-        LAUNCH_SPLIT(T.lerp, LerpTask, offs[L].lerp, launch_sample_lerp(tp, nb, T.lerp.max_chunks, vec, D, s));
-        LAUNCH_SPLIT(T.dsine, VoiceTask, offs[L].dsine, launch_voice(VOICE_DEBUG_SINE, tp, nb, T.dsine.max_chunks, vec, 0, D, s));
-        LAUNCH_SPLIT(T.synth, VoiceTask, offs[L].synth, launch_voice(VOICE_SYNTH, tp, nb, T.synth.max_chunks, vec, 0, D, s));
-        LAUNCH_SPLIT(T.sampsyn, VoiceTask, offs[L].sampsyn,
+        LAUNCH_SPLIT(KC_LOOP, T.loop, LoopTask, offs[L].loop, T.loop.bytes, launch_sample_loop(tp, nb, T.loop.max_chunks, vec, s));
+        LAUNCH_SPLIT(KC_MULTI, T.multi, MultiTask, offs[L].multi, T.multi.bytes, launch_sample_multi(tp, nb, T.multi.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(KC_LERP, T.lerp, LerpTask, offs[L].lerp, T.lerp.bytes, launch_sample_lerp(tp, nb, T.lerp.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(KC_DSINE, T.dsine, VoiceTask, offs[L].dsine, T.dsine.bytes, launch_voice(VOICE_DEBUG_SINE, tp, nb, T.dsine.max_chunks, vec, 0, D, s));
+        LAUNCH_SPLIT(KC_SYNTH, T.synth, VoiceTask, offs[L].synth, T.synth.bytes, launch_voice(VOICE_SYNTH, tp, nb, T.synth.max_chunks, vec, 0, D, s));
+        LAUNCH_SPLIT(KC_SAMPSYN, T.sampsyn, VoiceTask, offs[L].sampsyn, T.sampsyn.bytes,
                      launch_voice(VOICE_SAMPSYN, tp, nb, T.sampsyn.max_chunks, vec, T.sampsyn_smem_ok ? T.sampsyn_smem : 0, D, s));
-        LAUNCH_SPLIT(T.fx, FxTask, offs[L].fx, launch_fx(tp, nb, T.fx.max_chunks, vec, D, s));
-        LAUNCH_SPLIT(T.nprefix, NormPrefixTask, offs[L].nprefix, launch_norm_prefix(tp, nb, s));
-        LAUNCH_SPLIT(T.nscale, NormScaleTask, offs[L].nscale, launch_norm_scale(tp, nb, T.nscale.max_chunks, vec, s));
-        for (size_t b0 = 0; b0 < T.bp.v.size(); b0 += kMaxY) {
-            const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, T.bp.v.size() - b0);
-            CU(launch_bp(reinterpret_cast<const BpTask*>(D + offs[L].bp) + b0, nb, T.bp.max_chunks, vec, D, s));
-            launches += 3;
-        }
+        LAUNCH_SPLIT(KC_FX, T.fx, FxTask, offs[L].fx, T.fx.bytes, launch_fx(tp, nb, T.fx.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(KC_NORM_PREFIX, T.nprefix, NormPrefixTask, offs[L].nprefix, T.nprefix.bytes, launch_norm_prefix(tp, nb, s));
+        LAUNCH_SPLIT(KC_NORM_SCALE, T.nscale, NormScaleTask, offs[L].nscale, T.nscale.bytes, launch_norm_scale(tp, nb, T.nscale.max_chunks, vec, s));
+        LAUNCH_SPLIT(KC_BP_AGG, T.bp, BpTask, offs[L].bp, T.bp_agg_bytes, launch_bp_aggregate(tp, nb, T.bp.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(KC_BP_CARRY, T.bp, BpTask, offs[L].bp, (uint64_t)0, launch_bp_carry(tp, nb, D, s));
+        LAUNCH_SPLIT(KC_BP_APPLY, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_apply(tp, nb, T.bp.max_chunks, vec, D, s));
     }
-    for (size_t b0 = 0; b0 < resamps.size(); b0 += kMaxY) {
-        const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, resamps.size() - b0);
-        CU(launch_resample(reinterpret_cast<const ResampleTask*>(D + resamp_off) + b0, nb, resamp_max, D, s)); ++launches;
-    }
-    for (size_t b0 = 0; b0 < quants.size(); b0 += kMaxY) {
-        const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, quants.size() - b0);
-        CU(launch_quantise(reinterpret_cast<const QuantTask*>(D + quant_off) + b0, nb, quant_max, s)); ++launches;
-    }
+    { TaskList<ResampleTask> rl; rl.v.swap(resamps);
+      LAUNCH_SPLIT(KC_RESAMPLE, rl, ResampleTask, resamp_off, resamp_bytes, launch_resample(tp, nb, resamp_max, D, s)); }
+    { TaskList<QuantTask> ql; ql.v.swap(quants);
+      LAUNCH_SPLIT(KC_QUANT, ql, QuantTask, quant_off, quant_bytes, launch_quantise(tp, nb, quant_max, s)); }
     CU(cudaEventRecord(g->ev1, s));
 
     // ---- 4. results back -------------------------------------------------------------------------
@@ -815,6 +823,12 @@ static int run_pass(std::vector<PassReq>& reqs) {
     const double t_end = now_ms();
     float dev_ms = 0.0f;
     cudaEventElapsedTime(&dev_ms, g->ev0, g->ev1);
+    KStat ks[KC_COUNT];
+    for (size_t i = 0; i < timed.size(); ++i) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, g->evpool[2 * i], g->evpool[2 * i + 1]);
+        ks[timed[i].cls].launches++; ks[timed[i].cls].ms += ms; ks[timed[i].cls].bytes += timed[i].bytes;
+    }
 
     // ---- 5. end-of-pass transport state (graph.rs:235-236 / state.rs:575) -------------------------
     int rc = TDG_OK;
@@ -841,6 +855,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
         x->stats.h2d_bytes = B.size; x->stats.d2h_bytes = d2h_bytes;
         x->stats.kernel_launches = launches;
         x->launches += launches;
+        for (int k = 0; k < KC_COUNT; ++k) x->kstats[k] = ks[k];
         if (reqs.size() > 1) x->stats.algorithmic_bytes = algo_bytes_total;
         if (r.err_flag) rc = x->fail(TDG_ERR_TOO_WIDE, "sample too wide for bit depth (hound TooWide; the reference panics)");
     }
@@ -1291,6 +1306,19 @@ int tdg_render_segment(tdg_ctx* h, uint64_t total_chunks, uint64_t chunk0, uint6
     return run_pass(reqs);
 }
 
+int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; return TDG_OK; }
+int tdg_last_pass_kernel_stats(tdg_ctx* h, tdg_kernel_stat* out, int cap) {
+    static const char* names[KC_COUNT] = {"k_sample_loop", "k_sample_multi", "k_sample_lerp", "k_voice<debug_sine>", "k_voice<synth>",
+        "k_voice<sampsyn>", "k_fx", "k_norm_prefix", "k_norm_scale", "k_bp_aggregate", "k_bp_carry", "k_bp_apply", "k_resample", "k_quantise"};
+    int n = 0;
+    for (int k = 0; k < KC_COUNT && n < cap; ++k) {
+        const KStat& s = h->c.kstats[k];
+        if (!s.launches) continue;
+        out[n].name = names[k]; out[n].launches = s.launches; out[n].device_ms = s.ms; out[n].algorithmic_bytes = s.bytes;
+        ++n;
+    }
+    return n;
+}
 int tdg_last_pass_stats(tdg_ctx* h, tdg_pass_stats* out) {
     if (!h || !out) return TDG_ERR_INVALID;
     const PassStats& s = h->c.stats;

@@ -49,6 +49,10 @@ struct HVertex {
     bool has_input() const { return kind == K_SUM || kind == K_NORMALIZE || kind == K_ADSR || kind == K_BANDPASS; }
 };
 
+enum KClass { KC_LOOP, KC_MULTI, KC_LERP, KC_DSINE, KC_SYNTH, KC_SAMPSYN, KC_FX, KC_NORM_PREFIX, KC_NORM_SCALE,
+              KC_BP_AGG, KC_BP_CARRY, KC_BP_APPLY, KC_RESAMPLE, KC_QUANT, KC_COUNT };
+struct KStat { uint64_t launches = 0, bytes = 0; double ms = 0; };
+
 struct PassStats {
     double device_ms = 0, plan_ms = 0, h2d_ms = 0, d2h_ms = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0, kernel_launches = 0, algorithmic_bytes = 0, frames = 0, voice_frames = 0;
@@ -78,6 +82,7 @@ struct Ctx {
     uint64_t last_n_frames = 0, last_n_pad = 0;
     uint64_t last_epoch = 0;
     PassStats stats;
+    KStat kstats[KC_COUNT];                  // per kernel class, last pass (profiling on)
     uint64_t launches = 0;
     int fail(int code, const std::string& m) { err = m; return code; }
 };

@@ -802,13 +802,15 @@ cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_
                : launch_voice_t<VOICE_SAMPSYN, false, false>(t, n, max_chunks, 0, blob, s);
 }
 
-cudaError_t launch_bp(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {
+cudaError_t launch_bp_aggregate(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {
     TDG_VEC_DISPATCH(vec, k_bp_aggregate, <<<grid2(max_tiles, n), kBpThreads, 0, s>>>(t, blob));
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+cudaError_t launch_bp_carry(const BpTask* t, uint32_t n, const uint8_t* blob, cudaStream_t s) {
     k_bp_carry<<<n, kBpThreads, 0, s>>>(t, blob);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {
     TDG_VEC_DISPATCH(vec, k_bp_apply, <<<grid2(max_tiles, n), kBpThreads, 0, s>>>(t, blob));
     return cudaGetLastError();
 }

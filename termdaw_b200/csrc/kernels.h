@@ -15,8 +15,10 @@ cudaError_t launch_sample_multi(const MultiTask* t, uint32_t n, uint32_t max_chu
 cudaError_t launch_sample_lerp(const LerpTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool vec, size_t table_smem_bytes,
                          const uint8_t* blob, cudaStream_t s);
-// three launches: tile aggregates, carry scan, apply
-cudaError_t launch_bp(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
+// band pass = three launches: tile aggregates, carry scan, apply
+cudaError_t launch_bp_aggregate(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
+cudaError_t launch_bp_carry(const BpTask* t, uint32_t n, const uint8_t* blob, cudaStream_t s);
+cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_frames, cudaStream_t s);
 cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_deinterleave(const float* lin, uint64_t n_frames, uint32_t stride, uint32_t off_l, uint32_t off_r,
