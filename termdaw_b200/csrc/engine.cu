@@ -16,7 +16,9 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/termdaw_b200.h"
@@ -226,6 +228,9 @@ static PanGain make_pg(float gain, float angle) {
     }
     if (!(fabsf(gain - 1.0f) < 0.001f)) pg.flags |= 2u;             // sample.rs:109
     return pg;
+}
+static inline AdsrRcp make_rcp(const AdsrConfD& c) {
+    return AdsrRcp{1.0f / c.attack_sec, 1.0f / c.decay_sec, 1.0f / c.sustain_sec, 1.0f / c.release_sec};
 }
 static inline float note_hz(float note) { return 440.0f * powf(2.0f, (note - 69.0f) / 12.0f); }   // extensions.rs:451
 
@@ -441,6 +446,7 @@ struct PassReq {
     uint64_t n_frames = 0, n_pad = 0;
     uint64_t pcm_off = 0, pcm_bytes = 0, err_off = 0, rs_off = 0, rs_total = 0;
     bool resample = false;
+    const float* sincs = nullptr;
     std::vector<ResampleChunk> rs_chunks;
     uint64_t out_frames = 0;
     uint32_t err_flag = 0;
@@ -448,7 +454,7 @@ struct PassReq {
 
 template <typename T> struct TaskList { std::vector<T> v; uint32_t max_chunks = 0; uint64_t bytes = 0; };
 struct LevelTasks {
-    TaskList<FxTask> fx; TaskList<NormPrefixTask> nprefix; TaskList<NormScaleTask> nscale;
+    TaskList<FxTask> fx, fx_adsr, fx_norm; TaskList<NormPrefixTask> nprefix; TaskList<NormScaleTask> nscale;
     TaskList<LoopTask> loop; TaskList<MultiTask> multi; TaskList<LerpTask> lerp;
     TaskList<VoiceTask> dsine, synth, sampsyn; TaskList<BpTask> bp;
     size_t sampsyn_smem = 0; bool sampsyn_smem_ok = true;
@@ -477,6 +483,22 @@ static void compute_levels(PassReq& r) {
             st.pop_back();
         }
     }
+}
+
+struct HeapBlob {                   // per-project plan fragment (same alloc/at interface as PinnedBuf)
+    std::vector<uint8_t> v;
+    uint64_t alloc(uint64_t bytes) { const uint64_t off = align_up(v.size(), 16); v.resize(off + bytes, 0); return off; }
+    template <typename T> T* at(uint64_t off) { return reinterpret_cast<T*>(v.data() + off); }
+};
+struct Frag {
+    HeapBlob blob; uint64_t base = 0;
+    std::vector<LevelTasks> levels;
+    std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
+    uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, algo = 0;
+};
+template <typename T> static void append_list(TaskList<T>& d, TaskList<T>& s) {
+    d.v.insert(d.v.end(), s.v.begin(), s.v.end());
+    d.max_chunks = std::max(d.max_chunks, s.max_chunks); d.bytes += s.bytes;
 }
 
 struct Bump { uint64_t off = 0; uint64_t alloc(uint64_t bytes) { off = align_up(off, 256); uint64_t r = off; off += bytes; return r; } };
@@ -540,20 +562,31 @@ static int run_pass(std::vector<PassReq>& reqs) {
     uint8_t* W = g->work.p;
 
     // ---- 2. plan: tasks + tables into the pinned blob ------------------------------------------
-    std::vector<LevelTasks> levels(max_level + 1);
-    std::vector<QuantTask> quants; uint64_t quant_max = 0, quant_bytes = 0;
-    std::vector<ResampleTask> resamps; uint64_t resamp_max = 0, resamp_bytes = 0;
-    PinnedBuf& B = g->blob;
-    B.size = 0;
-    uint64_t algo_bytes_total = 0;
-    std::vector<MultiHit> mhits; std::vector<LerpHit> lhits; SegOut so;
+    // Each project is planned independently (host threads) into its own fragment: a private blob and
+    // private task lists whose *_off fields are relative to that blob; fragments are then copied into
+    // the pinned blob and the offsets rebased.
     bool all_vec = true;
     for (auto& r : reqs) {
         Ctx* x = r.c;
         if (int e = vstate_to_dev(x)) return e;
         x->stats = PassStats();
-        const int V = (int)x->verts.size();
         if (x->bl % 4 != 0) all_vec = false;
+        r.sincs = nullptr;
+        if (r.resample) {
+            r.sincs = sinc_table_dev(x, (double)r.render_sr / (double)x->sr);
+            if (!r.sincs) return x->fail(TDG_ERR_CUDA, "could not build the sinc table");
+        }
+    }
+    std::vector<Frag> frags(reqs.size());
+    auto plan_one = [&](PassReq& r, Frag& F) -> int {
+        Ctx* x = r.c;
+        HeapBlob& B = F.blob;
+        std::vector<LevelTasks>& levels = F.levels;
+        levels.resize(max_level + 1);
+        std::vector<QuantTask>& quants = F.quants; uint64_t& quant_max = F.quant_max; uint64_t& quant_bytes = F.quant_bytes;
+        std::vector<ResampleTask>& resamps = F.resamps; uint64_t& resamp_max = F.resamp_max; uint64_t& resamp_bytes = F.resamp_bytes;
+        std::vector<MultiHit> mhits; std::vector<LerpHit> lhits; SegOut so;
+        const int V = (int)x->verts.size();
         PassParams pp{r.is_scan ? 0 : x->fb_frame, r.is_scan ? 0 : x->t, r.total, r.emit0, r.emit_n, x->bl, x->sr};
         // (true_normalize_scan: fb.set_time(0) and t = j*bl, graph.rs:228-231)
         uint64_t algo = 0;
@@ -590,28 +623,30 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     float* peaks = reinterpret_cast<float*>(W + r.aux_off[v]);
                     float* runmax = peaks + r.emit_n;
                     t.peaks = peaks;
-                    LT.fx.v.push_back(t); LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch);
+                    LT.fx_norm.v.push_back(t); LT.fx_norm.max_chunks = std::max(LT.fx_norm.max_chunks, nch);
                     NormPrefixTask np{peaks, runmax, x->vstate_dev + (size_t)v * 8, nch, r.is_scan ? 1u : 0u};
                     LT.nprefix.v.push_back(np);
                     NormScaleTask ns; ns.h = h; ns.runmax = runmax;
                     LT.nscale.v.push_back(ns); LT.nscale.max_chunks = std::max(LT.nscale.max_chunks, nch);
                     algo += io_bytes + 16ull * r.n_frames;
-                    LT.fx.bytes += io_bytes; LT.nscale.bytes += 16ull * r.n_frames; LT.nprefix.bytes += 8ull * r.emit_n;
+                    LT.fx_norm.bytes += io_bytes; LT.nscale.bytes += 16ull * r.n_frames; LT.nprefix.bytes += 8ull * r.emit_n;
                     break;
                 }
                 case K_ADSR: {
-                    if (hv.wet < 0.0001f) { LT.fx.v.push_back(fx_task(FX_SUM)); }      // extensions.rs:598
-                    else {
+                    if (hv.wet < 0.0001f) {                                              // extensions.rs:598
+                        LT.fx.v.push_back(fx_task(FX_SUM)); LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch); LT.fx.bytes += io_bytes;
+                    } else {
                         plan_adsr(hv, x->flowws[hv.floww], pp, so);
                         FxTask t = fx_task(FX_ADSR);
-                        t.conf = hv.adsr; t.wet = hv.wet; t.use_off = hv.use_off; t.use_max = hv.use_max;
+                        t.conf = hv.adsr; t.rcp = make_rcp(hv.adsr); t.wet = hv.wet; t.use_off = hv.use_off; t.use_max = hv.use_max;
                         t.seg_ptr_off = B.alloc(so.ptr.size() * 4);
                         memcpy(B.at<uint8_t>(t.seg_ptr_off), so.ptr.data(), so.ptr.size() * 4);
                         t.seg_off = B.alloc(std::max<size_t>(so.aseg.size(), 1) * sizeof(AdsrSeg));
                         memcpy(B.at<uint8_t>(t.seg_off), so.aseg.data(), so.aseg.size() * sizeof(AdsrSeg));
-                        LT.fx.v.push_back(t);
+                        LT.fx_adsr.v.push_back(t); LT.fx_adsr.max_chunks = std::max(LT.fx_adsr.max_chunks, nch);
+                        LT.fx_adsr.bytes += io_bytes + so.aseg.size() * sizeof(AdsrSeg);
                     }
-                    LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch); algo += io_bytes; LT.fx.bytes += io_bytes;
+                    algo += io_bytes;
                     break;
                 }
                 case K_BANDPASS: {
@@ -685,12 +720,13 @@ static int run_pass(std::vector<PassReq>& reqs) {
                         t.kind = VOICE_SYNTH;
                         t.sq_vol = hv.sq.volume; t.sq_z = hv.sq.param; t.tf_vol = hv.tf.volume; t.tf_z = hv.tf.param;
                         t.tr_vol = hv.tr.volume; t.sq = hv.sq.adsr; t.tf = hv.tf.adsr; t.tr = hv.tr.adsr;
+                        t.sq_r = make_rcp(hv.sq.adsr); t.tf_r = make_rcp(hv.tf.adsr); t.tr_r = make_rcp(hv.tr.adsr);
                         t.amp_mul = 1.0f / (hv.sq.volume * m_max_vel(hv.sq.adsr) + hv.tf.volume * m_max_vel(hv.tf.adsr) +
                                             hv.tr.volume * m_max_vel(hv.tr.adsr));           // extensions.rs:465-468
                         LT.synth.v.push_back(t); LT.synth.max_chunks = std::max(LT.synth.max_chunks, nch); LT.synth.bytes += vbytes;
                     } else {
                         const DevTable& tb = x->tables[hv.table];
-                        t.kind = VOICE_SAMPSYN; t.adsr = hv.adsr; t.amp_mul = 1.0f / m_max_vel(hv.adsr);   // extensions.rs:537
+                        t.kind = VOICE_SAMPSYN; t.adsr = hv.adsr; t.adsr_r = make_rcp(hv.adsr); t.amp_mul = 1.0f / m_max_vel(hv.adsr);   // extensions.rs:537
                         t.table = tb.data; t.n_frames = tb.n_frames; t.n_phase = tb.n_phase; t.fps = tb.fps;
                         const size_t tb_bytes = (size_t)tb.n_frames * tb.n_phase * 4;
                         if (tb_bytes > 160 * 1024) LT.sampsyn_smem_ok = false;
@@ -714,8 +750,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
                 ResampleTask rt; memset(&rt, 0, sizeof rt);
                 rt.in_l = ol; rt.in_r = orr;
                 rt.out_l = reinterpret_cast<float*>(W + r.rs_off); rt.out_r = rt.out_l + align_up(r.rs_total, 4);
-                rt.sincs = sinc_table_dev(x, (double)r.render_sr / (double)x->sr);
-                if (!rt.sincs) return x->fail(TDG_ERR_CUDA, "could not build the sinc table");
+                rt.sincs = r.sincs;
                 rt.n_in = r.n_frames; rt.n_chunks = (uint32_t)r.emit_n; rt.chunk = x->bl;
                 rt.t_ratio = 1.0 / ((double)r.render_sr / (double)x->sr);
                 rt.chunk_off = B.alloc(std::max<size_t>(r.rs_chunks.size(), 1) * sizeof(ResampleChunk));
@@ -731,11 +766,91 @@ static int run_pass(std::vector<PassReq>& reqs) {
             algo += 8ull * q.n + r.pcm_bytes; quant_bytes += 8ull * q.n + r.pcm_bytes;
         }
         x->stats.algorithmic_bytes = algo; x->stats.frames = r.n_frames;
-        algo_bytes_total += algo;
+        F.algo = algo;
         x->last_buf_off = r.buf_off; x->last_n_frames = r.n_frames; x->last_n_pad = r.n_pad; x->last_epoch = g->epoch;
+        return TDG_OK;
+    };
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned nthreads = (unsigned)std::min<size_t>(std::min(hw, 32u), reqs.size());
+        std::atomic<size_t> next{0};
+        std::atomic<int> first_err{TDG_OK};
+        auto worker = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= reqs.size()) break;
+                const int e = plan_one(reqs[i], frags[i]);
+                if (e != TDG_OK) { int z = TDG_OK; first_err.compare_exchange_strong(z, e); }
+            }
+        };
+        if (nthreads <= 1) worker();
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+            for (auto& th : pool) th.join();
+        }
+        if (first_err.load() != TDG_OK) return first_err.load();
+    }
+    // merge: reserve the pinned blob, rebase offsets, concatenate the task lists (project order)
+    PinnedBuf& B = g->blob;
+    B.size = 0;
+    std::vector<LevelTasks> levels(max_level + 1);
+    std::vector<QuantTask> quants; uint64_t quant_max = 0, quant_bytes = 0;
+    std::vector<ResampleTask> resamps; uint64_t resamp_max = 0, resamp_bytes = 0;
+    uint64_t algo_bytes_total = 0;
+    {
+        uint64_t tot = 0;
+        for (Frag& F : frags) { F.base = align_up(tot, 256); tot = F.base + F.blob.v.size(); }
+        if (!B.reserve(tot + 256)) return c->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
+        B.size = tot;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned nthreads = (unsigned)std::min<size_t>(std::min(hw, 16u), frags.size());
+        std::atomic<size_t> next{0};
+        auto copier = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= frags.size()) break;
+                if (!frags[i].blob.v.empty()) memcpy(B.p + frags[i].base, frags[i].blob.v.data(), frags[i].blob.v.size());
+            }
+        };
+        if (nthreads <= 1 || tot < (8u << 20)) copier();
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(copier);
+            for (auto& th : pool) th.join();
+        }
+        for (Frag& F : frags) {
+            const uint64_t b = F.base;
+            for (size_t L = 0; L < F.levels.size(); ++L) {
+                LevelTasks& S = F.levels[L]; LevelTasks& Dst = levels[L];
+                for (FxTask& t : S.fx.v) t.in_off += b;
+                for (FxTask& t : S.fx_adsr.v) { t.in_off += b; t.seg_ptr_off += b; t.seg_off += b; }
+                for (FxTask& t : S.fx_norm.v) t.in_off += b;
+                for (MultiTask& t : S.multi.v) t.hits_off += b;
+                for (LerpTask& t : S.lerp.v) t.hits_off += b;
+                for (VoiceTask& t : S.dsine.v) { t.seg_ptr_off += b; t.seg_off += b; }
+                for (VoiceTask& t : S.synth.v) { t.seg_ptr_off += b; t.seg_off += b; }
+                for (VoiceTask& t : S.sampsyn.v) { t.seg_ptr_off += b; t.seg_off += b; }
+                for (BpTask& t : S.bp.v) t.in_off += b;
+                append_list(Dst.fx, S.fx); append_list(Dst.fx_adsr, S.fx_adsr); append_list(Dst.fx_norm, S.fx_norm);
+                append_list(Dst.nprefix, S.nprefix); append_list(Dst.nscale, S.nscale);
+                append_list(Dst.loop, S.loop); append_list(Dst.multi, S.multi); append_list(Dst.lerp, S.lerp);
+                append_list(Dst.dsine, S.dsine); append_list(Dst.synth, S.synth); append_list(Dst.sampsyn, S.sampsyn);
+                append_list(Dst.bp, S.bp);
+                Dst.sampsyn_smem = std::max(Dst.sampsyn_smem, S.sampsyn_smem);
+                Dst.sampsyn_smem_ok = Dst.sampsyn_smem_ok && S.sampsyn_smem_ok;
+                Dst.bp_agg_bytes += S.bp_agg_bytes;
+            }
+            for (ResampleTask& t : F.resamps) { t.chunk_off += b; resamps.push_back(t); }
+            for (QuantTask& t : F.quants) quants.push_back(t);
+            quant_max = std::max(quant_max, F.quant_max); quant_bytes += F.quant_bytes;
+            resamp_max = std::max(resamp_max, F.resamp_max); resamp_bytes += F.resamp_bytes;
+            algo_bytes_total += F.algo;
+            F.blob.v.clear(); F.blob.v.shrink_to_fit();
+        }
     }
     // task arrays go into the blob too: one H2D for the whole pass
-    struct Off { uint64_t fx, nprefix, nscale, loop, multi, lerp, dsine, synth, sampsyn, bp; };
+    struct Off { uint64_t fx, fx_adsr, fx_norm, nprefix, nscale, loop, multi, lerp, dsine, synth, sampsyn, bp; };
     std::vector<Off> offs(levels.size());
     auto put = [&](const void* src, size_t bytes) -> uint64_t {
         uint64_t o = B.alloc(std::max<size_t>(bytes, 16));
@@ -745,6 +860,8 @@ static int run_pass(std::vector<PassReq>& reqs) {
     for (size_t L = 0; L < levels.size(); ++L) {
         LevelTasks& T = levels[L];
         offs[L].fx = put(T.fx.v.data(), T.fx.v.size() * sizeof(FxTask));
+        offs[L].fx_adsr = put(T.fx_adsr.v.data(), T.fx_adsr.v.size() * sizeof(FxTask));
+        offs[L].fx_norm = put(T.fx_norm.v.data(), T.fx_norm.v.size() * sizeof(FxTask));
         offs[L].nprefix = put(T.nprefix.v.data(), T.nprefix.v.size() * sizeof(NormPrefixTask));
         offs[L].nscale = put(T.nscale.v.data(), T.nscale.v.size() * sizeof(NormScaleTask));
         offs[L].loop = put(T.loop.v.data(), T.loop.v.size() * sizeof(LoopTask));
@@ -794,7 +911,9 @@ static int run_pass(std::vector<PassReq>& reqs) {
         LAUNCH_SPLIT(KC_SYNTH, T.synth, VoiceTask, offs[L].synth, T.synth.bytes, launch_voice(VOICE_SYNTH, tp, nb, T.synth.max_chunks, vec, 0, D, s));
         LAUNCH_SPLIT(KC_SAMPSYN, T.sampsyn, VoiceTask, offs[L].sampsyn, T.sampsyn.bytes,
                      launch_voice(VOICE_SAMPSYN, tp, nb, T.sampsyn.max_chunks, vec, T.sampsyn_smem_ok ? T.sampsyn_smem : 0, D, s));
-        LAUNCH_SPLIT(KC_FX, T.fx, FxTask, offs[L].fx, T.fx.bytes, launch_fx(tp, nb, T.fx.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(KC_FX_SUM, T.fx, FxTask, offs[L].fx, T.fx.bytes, launch_fx(FX_SUM, tp, nb, T.fx.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(KC_FX_ADSR, T.fx_adsr, FxTask, offs[L].fx_adsr, T.fx_adsr.bytes, launch_fx(FX_ADSR, tp, nb, T.fx_adsr.max_chunks, vec, D, s));
+        LAUNCH_SPLIT(KC_FX_NORM, T.fx_norm, FxTask, offs[L].fx_norm, T.fx_norm.bytes, launch_fx(FX_NORM_PEAK, tp, nb, T.fx_norm.max_chunks, vec, D, s));
         LAUNCH_SPLIT(KC_NORM_PREFIX, T.nprefix, NormPrefixTask, offs[L].nprefix, T.nprefix.bytes, launch_norm_prefix(tp, nb, s));
         LAUNCH_SPLIT(KC_NORM_SCALE, T.nscale, NormScaleTask, offs[L].nscale, T.nscale.bytes, launch_norm_scale(tp, nb, T.nscale.max_chunks, vec, s));
         LAUNCH_SPLIT(KC_BP_AGG, T.bp, BpTask, offs[L].bp, T.bp_agg_bytes, launch_bp_aggregate(tp, nb, T.bp.max_chunks, vec, D, s));
@@ -1309,7 +1428,7 @@ int tdg_render_segment(tdg_ctx* h, uint64_t total_chunks, uint64_t chunk0, uint6
 int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; return TDG_OK; }
 int tdg_last_pass_kernel_stats(tdg_ctx* h, tdg_kernel_stat* out, int cap) {
     static const char* names[KC_COUNT] = {"k_sample_loop", "k_sample_multi", "k_sample_lerp", "k_voice<debug_sine>", "k_voice<synth>",
-        "k_voice<sampsyn>", "k_fx", "k_norm_prefix", "k_norm_scale", "k_bp_aggregate", "k_bp_carry", "k_bp_apply", "k_resample", "k_quantise"};
+        "k_voice<sampsyn>", "k_fx<sum>", "k_fx<adsr>", "k_fx<norm_peak>", "k_norm_prefix", "k_norm_scale", "k_bp_aggregate", "k_bp_carry", "k_bp_apply", "k_resample", "k_quantise"};
     int n = 0;
     for (int k = 0; k < KC_COUNT && n < cap; ++k) {
         const KStat& s = h->c.kstats[k];

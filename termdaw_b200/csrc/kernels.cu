@@ -73,36 +73,55 @@ __device__ __forceinline__ float block_max(float m) {
 // ------------------------------------------------------------------------------------ K4: fx
 // sum_inputs (extensions.rs:310-319) + { nothing | adsr_gen (:593-651) | per-chunk peak for
 // normalize_gen (:321-329) } + apply_angle + apply_gain (:262-263), one pass over HBM.
-template <bool VEC>
-__global__ void __launch_bounds__(TDG_THREADS) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ FxTask T;
+    __shared__ const float* s_in[16];
     load_task(&T, tasks + blockIdx.y);
+    if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
     const uint32_t k = blockIdx.x;
     if (k >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
     const uint64_t p0 = (uint64_t)k * bl;
     const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
+    const bool staged = T.n_in <= 8;
+    if (staged) {                                        // pointer table into shared memory: no dependent global load per input
+        if (threadIdx.x < 2 * T.n_in) s_in[threadIdx.x] = ins[threadIdx.x];
+        __syncthreads();
+    }
     const AdsrSeg* segs = nullptr;
     uint32_t s_lo = 0, s_hi = 0;
-    if (T.mode == FX_ADSR) {
+    float maxmul = 0.0f, minmul = 0.0f;
+    if (MODE == FX_ADSR) {
         const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
         s_lo = sp[k]; s_hi = sp[k + 1];
         segs = reinterpret_cast<const AdsrSeg*>(blob + T.seg_off);
+        maxmul = T.use_max ? 1.0f : 0.0f; minmul = 1.0f - maxmul;
     }
-    const float maxmul = T.use_max ? 1.0f : 0.0f, minmul = 1.0f - maxmul;
     float peak = 0.0f;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
         const int nv = min(4u, bl - i);
         const uint64_t p = p0 + i;
         float l[4] = {0.0f, 0.0f, 0.0f, 0.0f}, r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (uint32_t a = 0; a < T.n_in; ++a) {
-            float x[4], y[4];
-            ld4<VEC>(ins[2 * a], p, nv, x);
-            ld4<VEC>(ins[2 * a + 1], p, nv, y);
+        if (staged) {
+#pragma unroll 2
+            for (uint32_t a = 0; a < T.n_in; ++a) {
+                float x[4], y[4];
+                ld4<VEC>(s_in[2 * a], p, nv, x);
+                ld4<VEC>(s_in[2 * a + 1], p, nv, y);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { l[j] += x[j]; r[j] += y[j]; }
+                for (int j = 0; j < 4; ++j) { l[j] += x[j]; r[j] += y[j]; }
+            }
+        } else {
+            for (uint32_t a = 0; a < T.n_in; ++a) {
+                float x[4], y[4];
+                ld4<VEC>(ins[2 * a], p, nv, x);
+                ld4<VEC>(ins[2 * a + 1], p, nv, y);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { l[j] += x[j]; r[j] += y[j]; }
+            }
         }
-        if (T.mode == FX_ADSR) {
+        if (MODE == FX_ADSR) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (j >= nv) break;
@@ -127,7 +146,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_fx(const FxTask* __restrict__ t
                 l[j] *= vel; r[j] *= vel;
             }
         }
-        if (T.mode == FX_NORM_PEAK) {
+        if (MODE == FX_NORM_PEAK) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (j < nv) { peak = absmax_fold(peak, l[j]); peak = absmax_fold(peak, r[j]); }
         } else {
@@ -137,7 +156,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_fx(const FxTask* __restrict__ t
         st4<VEC>(T.h.out_l, p, nv, l);
         st4<VEC>(T.h.out_r, p, nv, r);
     }
-    if (T.mode == FX_NORM_PEAK) {
+    if (MODE == FX_NORM_PEAK) {
         peak = block_max(peak);
         if (threadIdx.x == 0) T.peaks[k] = peak;
     }
@@ -360,73 +379,71 @@ __global__ void __launch_bounds__(TDG_THREADS) k_voice(const VoiceTask* __restri
         __syncthreads();
     }
     const float fsr = (float)T.sr;
-    for (uint32_t i = threadIdx.x * 4; i < bl || (i - threadIdx.x * 4) < bl; i += TDG_THREADS * 4) {
-        // (loop bound is block-uniform: every thread takes part in the staging barriers)
-        const bool active = i < bl;
-        const int nv = active ? (int)min(4u, bl - i) : 0;
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        float time[4], off[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            time[j] = (float)(T.t0 + p0 + i + j) / fsr;        // (t + i) as f32 / sr as f32
-            off[j] = (float)(i + j) / fsr;                     // i as f32 / sr as f32
+    // One frame per thread per inner iteration, loops kept rolled: the per-voice body is large and the
+    // kernel is instruction-issue bound, so code size (I-cache) matters more than store width.
+    // Segment batches beyond the first accumulate through out_l (same thread, same address).
+    uint32_t sb = s_lo;
+    bool first = true;
+    do {
+        const uint32_t nb = min((uint32_t)TDG_SEG_BATCH, s_hi - sb);
+        const bool last = sb + nb >= s_hi;
+        __syncthreads();
+        {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(gsegs + sb);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(segs);
+            for (uint32_t w = threadIdx.x; w < nb * (uint32_t)(sizeof(VoiceSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
         }
-        for (uint32_t sb = s_lo; sb < s_hi; sb += TDG_SEG_BATCH) {
-            const uint32_t nb = min((uint32_t)TDG_SEG_BATCH, s_hi - sb);
-            __syncthreads();
-            {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(gsegs + sb);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(segs);
-                for (uint32_t w = threadIdx.x; w < nb * (uint32_t)(sizeof(VoiceSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
-            }
-            __syncthreads();
-            if (!active) continue;
+        __syncthreads();
+#pragma unroll 1
+        for (uint32_t i = threadIdx.x; i < bl; i += TDG_THREADS) {
+            const uint64_t p = p0 + i;
+            float acc = first ? 0.0f : T.h.out_l[p];
+            const float time = (float)(T.t0 + p) / fsr;            // (t + i) as f32 / sr as f32
+            const float off = (float)i / fsr;                      // i as f32 / sr as f32
+#pragma unroll 1
             for (uint32_t s = 0; s < nb; ++s) {
                 const VoiceSeg sg = segs[s];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t fi = i + j;
-                    if (fi < sg.ia || fi >= sg.ib) continue;
-                    float smp;
-                    if (KIND == VOICE_DEBUG_SINE) {                       // extensions.rs:450-454
-                        smp = sinf(m_osc_arg(time[j], sg.hz)) * sg.vel;
-                    } else if (KIND == VOICE_SYNTH) {                     // extensions.rs:500-522
-                        const float env_time = sg.env_t + off[j];
-                        float sn = 0.0f;
-                        if (T.sq_vol > 0.0f || T.tf_vol > 0.0f) sn = sinf(m_osc_arg(time[j], sg.hz));
-                        smp = 0.0f;
-                        if (T.sq_vol > 0.0f) {
-                            const float e = sg.rel_t == 0.0f ? m_apply_ads(T.sq, env_time) : m_apply_r_rt(T.sq, env_time, sg.rel_t);
-                            smp += m_square_from_sin(sn, T.sq_z) * sg.vel * e * T.sq_vol;
-                        }
-                        if (T.tf_vol > 0.0f) {
-                            const float e = sg.rel_t == 0.0f ? m_apply_ads(T.tf, env_time) : m_apply_r_rt(T.tf, env_time, sg.rel_t);
-                            smp += m_topflat_from_sin(sn, T.tf_z) * sg.vel * e * T.tf_vol;
-                        }
-                        if (T.tr_vol > 0.0f) {
-                            const float e = sg.rel_t == 0.0f ? m_apply_ads(T.tr, env_time) : m_apply_r_rt(T.tr, env_time, sg.rel_t);
-                            smp += m_triangle(time[j], sg.hz) * sg.vel * e * T.tr_vol;
-                        }
-                        smp *= T.amp_mul;
-                    } else {                                              // extensions.rs:560-571
-                        const float env_time = sg.env_t + off[j];
-                        const float e = sg.rel_t == 0.0f ? m_apply_ads(T.adsr, env_time) : m_apply_r_rt(T.adsr, env_time, sg.rel_t);
-                        const float vel = sg.vel * e * T.amp_mul;
-                        smp = 0.0f;
-                        smp += wavetable_eval(tab, T.n_frames, T.n_phase, T.fps, sg.hz, env_time + sg.rel_t) * vel;
+                if (i < sg.ia || i >= sg.ib) continue;
+                const bool rel = sg.rel_t != 0.0f;
+                float smp;
+                if (KIND == VOICE_DEBUG_SINE) {                           // extensions.rs:450-454
+                    smp = d_sin(m_osc_arg(time, sg.hz)) * sg.vel;
+                } else if (KIND == VOICE_SYNTH) {                         // extensions.rs:500-522
+                    const float env_time = sg.env_t + off;
+                    float sn = 0.0f;
+                    if (T.sq_vol > 0.0f || T.tf_vol > 0.0f) sn = d_sin(m_osc_arg(time, sg.hz));
+                    smp = 0.0f;
+                    if (T.sq_vol > 0.0f) {
+                        const float e = rel ? m_apply_r_rt(T.sq, env_time, sg.rel_t) : m_apply_ads(T.sq, env_time);
+                        smp += m_square_from_sin(sn, T.sq_z) * sg.vel * e * T.sq_vol;
                     }
-                    acc[j] += smp;
+                    if (T.tf_vol > 0.0f) {
+                        const float e = rel ? m_apply_r_rt(T.tf, env_time, sg.rel_t) : m_apply_ads(T.tf, env_time);
+                        smp += m_topflat_from_sin(sn, T.tf_z) * sg.vel * e * T.tf_vol;
+                    }
+                    if (T.tr_vol > 0.0f) {
+                        const float e = rel ? m_apply_r_rt(T.tr, env_time, sg.rel_t) : m_apply_ads(T.tr, env_time);
+                        smp += m_triangle(time, sg.hz) * sg.vel * e * T.tr_vol;
+                    }
+                    smp *= T.amp_mul;
+                } else {                                                  // extensions.rs:560-571
+                    const float env_time = sg.env_t + off;
+                    const float e = rel ? m_apply_r_rt(T.adsr, env_time, sg.rel_t) : m_apply_ads(T.adsr, env_time);
+                    const float vel = sg.vel * e * T.amp_mul;
+                    smp = 0.0f;
+                    smp += wavetable_eval(tab, T.n_frames, T.n_phase, T.fps, sg.hz, env_time + sg.rel_t) * vel;
                 }
+                acc += smp;
             }
+            if (last) {
+                float l = acc, r = acc;
+                apply_pg(l, r, T.h.pg);
+                T.h.out_l[p] = l; T.h.out_r[p] = r;
+            } else T.h.out_l[p] = acc;
         }
-        if (active) {
-            float l[4], r[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { l[j] = acc[j]; r[j] = acc[j]; apply_pg(l[j], r[j], T.h.pg); }
-            st4<VEC>(T.h.out_l, p0 + i, nv, l);
-            st4<VEC>(T.h.out_r, p0 + i, nv, r);
-        }
-    }
+        first = false;
+        sb += nb;
+    } while (sb < s_hi);
 }
 
 // ------------------------------------------------------------------------------------ K7: band pass scan
@@ -753,8 +770,11 @@ static inline dim3 grid2(uint64_t x, uint32_t y) { return dim3((unsigned)x, y, 1
 
 #define TDG_VEC_DISPATCH(vec, K, ...) do { if (vec) K<true> __VA_ARGS__; else K<false> __VA_ARGS__; } while (0)
 
-cudaError_t launch_fx(const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_fx, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t, blob));
+cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
+    const dim3 g = grid2(max_chunks, n);
+    if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_SUM, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
+    else if (mode == FX_ADSR) { if (vec) k_fx<FX_ADSR, true><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
+    else { if (vec) k_fx<FX_NORM_PEAK, true><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_NORM_PEAK, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
     return cudaGetLastError();
 }
 cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s) {

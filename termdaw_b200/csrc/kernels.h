@@ -7,7 +7,7 @@
 
 namespace tdg {
 
-cudaError_t launch_fx(const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s);
+cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s);
 cudaError_t launch_norm_scale(const NormScaleTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s);
 cudaError_t launch_sample_loop(const LoopTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s);

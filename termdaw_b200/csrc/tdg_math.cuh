@@ -59,4 +59,91 @@ TDG_HD float m_triangle(float t, float hz) {
     return 4.0f * fabsf((t * hz) - floorf((t * hz) + 0.5f)) - 1.0f;
 }
 
+
+// ---- device-only fast forms --------------------------------------------------------------------
+#ifdef __CUDACC__
+// t / d for a per-vertex constant d with rcp = 1/d precomputed on the host: one Newton step on the
+// exact FMA residual gives the correctly rounded quotient (Markstein) without MUFU.RCP; anything
+// unusual (d == 0, inf/nan, zero or extreme quotients) takes the IEEE division.
+__device__ __forceinline__ float d_div(float t, float d, float rcp) {
+    const float q = t * rcp;
+    const float e = fmaf(-q, d, t);
+    const float q1 = fmaf(e, rcp, q);
+    const float aq = fabsf(q);
+    return (aq > 1e-30f && aq < 1e30f && fabsf(rcp) < 1e30f) ? q1 : t / d;
+}
+__device__ __forceinline__ float d_ads_internal(const AdsrConfD& c, const AdsrRcp& r, float t) {   // adsr.rs:46-60
+    if (t <= c.attack_sec) return m_lerp(c.std_vel, c.attack_vel, d_div(t, c.attack_sec, r.attack));
+    if (t <= c.attack_sec + c.decay_sec)
+        return m_lerp(c.attack_vel, c.decay_vel, d_div(t - c.attack_sec, c.decay_sec, r.decay));
+    if (t <= c.attack_sec + c.decay_sec + c.sustain_sec)
+        return m_lerp(c.decay_vel, c.sustain_vel, d_div(t - c.attack_sec - c.decay_sec, c.sustain_sec, r.sustain));
+    return -1000.0f;
+}
+__device__ __forceinline__ float d_apply_ads(const AdsrConfD& c, const AdsrRcp& r, float t) {
+    const float res = d_ads_internal(c, r, t);
+    return res <= -1.0f ? c.sustain_vel : res;
+}
+__device__ __forceinline__ float d_apply_r(const AdsrConfD& c, const AdsrRcp& r, float t, float old_val) {
+    return m_lerp(old_val, c.release_vel, fminf(d_div(t, c.release_sec, r.release), 1.0f));
+}
+__device__ __forceinline__ float d_apply_adsr(const AdsrConfD& c, const AdsrRcp& r, float t) {
+    const float res = d_ads_internal(c, r, t);
+    if (res <= -1.0f)
+        return m_lerp(c.sustain_vel, c.release_vel,
+                      fminf(d_div(t - c.attack_sec - c.decay_sec - c.sustain_sec, c.release_sec, r.release), 1.0f));
+    return res;
+}
+// floorf without the conversion pipe: exact for every finite input
+__device__ __forceinline__ float d_floor(float y) {
+    if (fabsf(y) < 4194304.0f) {
+        float r = (y + 12582912.0f) - 12582912.0f;      // round to nearest integer (|y| < 2^22)
+        return r > y ? r - 1.0f : r;
+    }
+    return floorf(y);
+}
+__device__ __forceinline__ float d_triangle(float t, float hz) {                             // synth.rs:32-34
+    const float y = t * hz;
+    return 4.0f * fabsf(y - d_floor(y + 0.5f)) - 1.0f;
+}
+// sin(x) of an f32 argument to ~7e-8 absolute (|x| < 2e6: 3-term Cody-Waite in FMAs, magic-number
+// rounding, the usual degree 7/8 minimax pair) — the reference calls libm sinf on the same f32
+// argument, so only the evaluation differs, not the (chaotic) argument.  Larger arguments reduce in
+// f64; nothing here touches the conversion/transcendental pipe on the common path.
+__device__ __forceinline__ float d_sin_poly(float r, int q) {
+    const float s = r * r;
+    float v;
+    if (q & 1) {
+        v = fmaf(s, 2.44331571e-5f, -1.38873163e-3f); v = fmaf(v, s, 4.16666457e-2f);
+        v = fmaf(v, s, -0.5f); v = fmaf(v, s, 1.0f);
+    } else {
+        v = fmaf(s, -1.95152959e-4f, 8.33216087e-3f); v = fmaf(v, s, -1.66666546e-1f);
+        v = v * s; v = fmaf(v, r, r);
+    }
+    return (q & 2) ? -v : v;
+}
+static __device__ __noinline__ float d_sin_big(float x) {           // |x| >= 2e6: reduce in f64 (rare on short renders)
+    if (fabsf(x) < 1.0e15f) {
+        const double xd = (double)x;
+        const double kd = rint(xd * 0.63661977236758134308);
+        double rd = fma(-kd, 1.57079632679489655800, xd);
+        rd = fma(-kd, 6.12323399573676603587e-17, rd);
+        return d_sin_poly((float)rd, (int)((long long)kd & 3));
+    }
+    return sinf(x);
+}
+__device__ __forceinline__ float d_sin(float x) {
+    if (fabsf(x) < 2.0e6f) {
+        const float kf = fmaf(x, 0.636619772367581343f, 12582912.0f);
+        const int q = __float_as_int(kf);
+        const float k = kf - 12582912.0f;
+        float r = fmaf(k, -1.57079601e+00f, x);
+        r = fmaf(k, -3.13916473e-07f, r);
+        r = fmaf(k, -5.39030253e-15f, r);
+        return d_sin_poly(r, q);
+    }
+    return d_sin_big(x);
+}
+#endif
+
 }  // namespace tdg

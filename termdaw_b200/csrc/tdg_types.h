@@ -23,6 +23,8 @@ struct AdsrConfD {          // adsr.rs:2-12
         release_vel;
 };
 
+struct AdsrRcp { float attack, decay, sustain, release; };   // 1/x of the four durations (host division)
+
 struct TaskHdr {
     float* out_l;
     float* out_r;
@@ -51,6 +53,7 @@ struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan 
     uint32_t mode, n_in;
     uint64_t in_off;        // blob: n_in pairs of (const float* l, const float* r)
     AdsrConfD conf;
+    AdsrRcp rcp;
     float wet;
     uint32_t use_off, use_max, sr;
     uint64_t seg_ptr_off;   // blob: uint32[n_chunks+1], indices into the AdsrSeg array
@@ -86,6 +89,7 @@ struct VoiceTask {
     // Synth (extensions.rs:44-50)
     float sq_vol, sq_z, tf_vol, tf_z, tr_vol, amp_mul;
     AdsrConfD sq, tf, tr;
+    AdsrRcp sq_r, tf_r, tr_r, adsr_r;
     // SampSyn (extensions.rs:51-56): adsr + wavetable [n_frames][n_phase]
     AdsrConfD adsr;
     const float* table;
