@@ -153,18 +153,39 @@ int tdg_read_vertex_buffer(tdg_ctx* ctx, int vertex, uint64_t frame0, uint64_t n
 
 /* ---- time sharding -----------------------------------------------------------
  * Evaluate chunks [chunk0, chunk0+chunks) of a pass of `total_chunks` chunks that starts at the
- * current transport position.  The event-driven vertex state at chunk0 is rebuilt by replaying the
- * floww events (and the per-chunk f32 clock additions) from the pass start without rendering audio,
- * and after the call the context's state is what a FULL pass would have left (so that a render after
- * a sharded scan starts from the same leaked state as the reference, graph.rs:228-236).
- * `warmup_chunks` extra chunks are rendered before chunk0 and discarded so that band-pass state has
- * converged at the boundary.  Normalize peaks are combined by the caller with an NCCL max-allreduce
- * over tdg_normalize_state_device_ptr().  No render-time resampling in segment mode. */
+ * current transport position.  The event-driven vertex state at chunk0 (voices, envelope clocks, hit
+ * lists: extensions.rs:23-69) is rebuilt by replaying the floww events and the per-chunk f32 clock
+ * additions from the pass start without rendering audio, and after the call the context's state is
+ * what a FULL pass would have left (so that a render after a sharded scan starts from the same leaked
+ * state as the reference, graph.rs:228-236).  The two true data dependencies cross the segment
+ * boundaries through a communicator:
+ *   - Normalize (extensions.rs:321-329): segment peaks — ncclAllReduce(max) in the scan pass,
+ *     ncclAllGather + exclusive prefix max in the render pass (running max);
+ *   - BandPass (extensions.rs:654-689): each segment publishes its affine map ((1-g)^n, y_end from
+ *     zero) per filter vertex, ncclAllGather, and every rank composes the maps of the earlier segments
+ *     onto rank 0's initial state — one exchange per DAG level that holds such vertices.
+ * One process per GPU: rank 0 calls tdg_comm_unique_id, the launcher broadcasts the 128 bytes
+ * (torch.distributed / MPI / a file), every rank calls tdg_comm_init_rank on its context.
+ * Without a communicator tdg_*_segment falls back to re-rendering `warmup_chunks` chunks before
+ * chunk0 so that filter state converges (approximate; normalize state is then the caller's job via
+ * tdg_get/set_normalize_state).  No render-time resampling in segment mode. */
+int tdg_comm_unique_id(uint8_t* out128);
+int tdg_comm_init_rank(tdg_ctx* ctx, int nranks, int rank, const uint8_t* id128);
+int tdg_comm_destroy(tdg_ctx* ctx);
+uint64_t tdg_collectives(tdg_ctx* ctx);        /* NCCL exchange rounds issued so far */
 int tdg_scan_segment(tdg_ctx* ctx, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks,
                      uint64_t warmup_chunks);
 int tdg_render_segment(tdg_ctx* ctx, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks,
                        uint64_t warmup_chunks, uint32_t bitdepth, uint8_t* out_pcm,
                        uint64_t cap_bytes, uint64_t* frames_written);
+/* "Virtual ranks": n contexts holding the SAME project on ONE device evaluate n consecutive segments
+ * (chunk0[0] == 0, contiguous, covering total_chunks) in one launch sequence and exchange through
+ * device memory exactly what NCCL carries between GPUs.  Same kernels, same hand-off arithmetic. */
+int tdg_scan_segments_local(tdg_ctx** ctxs, int n, uint64_t total_chunks, const uint64_t* chunk0,
+                            const uint64_t* chunks);
+int tdg_render_segments_local(tdg_ctx** ctxs, int n, uint64_t total_chunks, const uint64_t* chunk0,
+                              const uint64_t* chunks, uint32_t bitdepth, uint8_t** out_pcm,
+                              const uint64_t* cap_bytes, uint64_t* frames_written);
 /* Normalize state as (max, scan_max) pairs, one per vertex (non-normalize vertices: -1, -1). */
 int tdg_get_normalize_state(tdg_ctx* ctx, float* max_out, float* scan_max_out, int cap);
 int tdg_set_normalize_state(tdg_ctx* ctx, const float* max_in, const float* scan_max_in, int n);

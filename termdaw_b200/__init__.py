@@ -9,11 +9,12 @@ from __future__ import annotations
 
 import os
 
-from ._capi import Context, Library, TermdawError, normalize_scan_many, render_many  # noqa: F401
+from ._capi import (Context, Library, TermdawError, comm_unique_id, normalize_scan_many, render_many,  # noqa: F401
+                    render_segments_local, scan_segments_local)
 from .state import Assets, DecodedWav, Project, State, set_length_chunks  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtermdaw_b200.so")
+LIB_PATH = os.environ.get("TDG_LIB_PATH", os.path.join(_HERE, "csrc", "libtermdaw_b200.so"))   # override: tuning variants only
 _lib = None
 
 

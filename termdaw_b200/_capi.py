@@ -112,6 +112,13 @@ class Library:
         "render_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, c_u8p,
                                      C.c_uint64, c_u64p]),
         "set_normalize_state": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int]),
+        "comm_unique_id": (C.c_int, [c_u8p]),
+        "comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_u8p]),
+        "comm_destroy": (C.c_int, [C.c_void_p]),
+        "collectives": (C.c_uint64, [C.c_void_p]),
+        "scan_segments_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint64, c_u64p, c_u64p]),
+        "render_segments_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint64, c_u64p, c_u64p, C.c_uint32,
+                                            C.POINTER(c_u8p), c_u64p, c_u64p]),
         "normalize_state_device_ptr": (C.c_void_p, [C.c_void_p, c_i32p]),
         "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
         "set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
@@ -322,6 +329,17 @@ class Context:
         p = self.lib.normalize_state_device_ptr(self.h, C.byref(n))
         return p, n.value
 
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes):
+        a = np.frombuffer(unique_id, dtype=np.uint8).copy()
+        assert a.size == 128
+        self._chk(self.lib.comm_init_rank(self.h, nranks, rank, _p(a, c_u8p)))
+
+    def comm_destroy(self):
+        self._chk(self.lib.comm_destroy(self.h))
+
+    def collectives(self) -> int:
+        return int(self.lib.collectives(self.h))
+
     def set_profiling(self, on: bool = True):
         self._chk(self.lib.set_profiling(self.h, int(on)))
 
@@ -371,3 +389,42 @@ def normalize_scan_many(lib: Library, ctxs: Sequence[Context], chunks: Sequence[
     if rc < 0:
         msgs = [(lib.last_error(c.h) or b"").decode() for c in ctxs]
         raise TermdawError(rc, next((m for m in msgs if m), ""))
+
+
+def comm_unique_id(lib: Library) -> bytes:
+    """ncclGetUniqueId through the library (rank 0 of a time-sharded render); 128 bytes to broadcast."""
+    a = np.zeros(128, np.uint8)
+    rc = lib.comm_unique_id(_p(a, c_u8p))
+    if rc < 0:
+        raise TermdawError(rc, "NCCL is not available (libnccl.so.2 could not be loaded)")
+    return a.tobytes()
+
+
+def scan_segments_local(lib: Library, ctxs: Sequence[Context], total_chunks: int, bounds: Sequence[Sequence[int]]):
+    """tdg_scan_segments_local: `ctxs` hold the same project; bounds = [(chunk0, chunks), ...]."""
+    n = len(ctxs)
+    hs = (C.c_void_p * n)(*[c.h for c in ctxs])
+    c0 = (C.c_uint64 * n)(*[b[0] for b in bounds])
+    cn = (C.c_uint64 * n)(*[b[1] for b in bounds])
+    rc = lib.scan_segments_local(hs, n, total_chunks, c0, cn)
+    if rc < 0:
+        msgs = [(lib.last_error(c.h) or b"").decode() for c in ctxs]
+        raise TermdawError(rc, next((m for m in msgs if m), ""))
+
+
+def render_segments_local(lib: Library, ctxs: Sequence[Context], total_chunks: int, bounds, bitdepth: int):
+    """tdg_render_segments_local; returns the per-segment PCM byte arrays (concatenate for the file)."""
+    n = len(ctxs)
+    hs = (C.c_void_p * n)(*[c.h for c in ctxs])
+    c0 = (C.c_uint64 * n)(*[b[0] for b in bounds])
+    cn = (C.c_uint64 * n)(*[b[1] for b in bounds])
+    caps = [b[1] * ctxs[i].bl * 2 * (bitdepth // 8) for i, b in enumerate(bounds)]
+    outs = [np.empty(max(c, 1), np.uint8) for c in caps]
+    ptrs = (c_u8p * n)(*[_p(o, c_u8p) for o in outs])
+    cp = (C.c_uint64 * n)(*caps)
+    fw = (C.c_uint64 * n)()
+    rc = lib.render_segments_local(hs, n, total_chunks, c0, cn, bitdepth, ptrs, cp, fw)
+    if rc < 0:
+        msgs = [(lib.last_error(c.h) or b"").decode() for c in ctxs]
+        raise TermdawError(rc, next((m for m in msgs if m), ""))
+    return [outs[i][: fw[i] * 2 * (bitdepth // 8)] for i in range(n)]

@@ -9,7 +9,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["kernels.cu", "engine.cu"]
 HEADERS = ["tdg_types.h", "tdg_math.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "termdaw_b200.h")]
-OUT = os.path.join(HERE, "libtermdaw_b200.so")
+OUT = os.environ.get("TDG_OUT", os.path.join(HERE, "libtermdaw_b200.so"))       # tuning variants: TDG_OUT + TDG_DEFS
+DEFS = os.environ.get("TDG_DEFS", "").split()
+BUILD_DIR = os.path.join(HERE, "build" + ("_" + os.path.basename(OUT).replace(".so", "") if DEFS else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false / -ffp-contract=off: the reference rounds after every f32 operation (DESIGN.md "arithmetic")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
@@ -27,11 +29,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     jobs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
         os.makedirs(os.path.dirname(obj), exist_ok=True)
         objs.append(obj)
         if force or _stale(obj, [src] + HEADERS):
-            jobs.append([NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj])
+            jobs.append([NVCC, *FLAGS, *DEFS, "-c", os.path.join(HERE, src), "-o", obj])
     if jobs:
         def run(cmd):
             if verbose:

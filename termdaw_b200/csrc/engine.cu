@@ -8,6 +8,7 @@
 // here, exactly), and glibc powf/cosf/sinf for per-voice / per-vertex constants.  No audio sample is
 // ever computed on the host; without a CUDA device every entry point fails with TDG_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -119,6 +120,41 @@ static Engine* engine_get(int device, std::string* err) {
     return g;
 }
 
+// ------------------------------------------------------------------------------------ NCCL (time sharding)
+// Bound at run time (dlopen) so that the library loads on boxes without NCCL and shares whichever
+// libnccl.so.2 the process already holds (torch's).  Only the handful of entry points used.
+struct Id128 { char b[128]; };          // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed by value
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+    bool ok() const { return lib && GetUniqueId && CommInitRank && CommDestroy && AllGather && AllReduce; }
+};
+static const int kNcclFloat32 = 7, kNcclMax = 2;       // ncclFloat32 / ncclMax of nccl.h (stable ABI values)
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+        if (!api.lib) { api.err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return; }
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+        if (!api.ok()) api.err = "libnccl is missing an expected symbol";
+    });
+    return &api;
+}
+#define NC(call) do { int _e = (call); if (_e != 0) return c->fail(TDG_ERR_CUDA, std::string(#call) + ": " + (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(_e) : "nccl error")); } while (0)
+
 #define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return c->fail(TDG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } while (0)
 
 // ------------------------------------------------------------------------------------ sinc table
@@ -228,9 +264,6 @@ static PanGain make_pg(float gain, float angle) {
     }
     if (!(fabsf(gain - 1.0f) < 0.001f)) pg.flags |= 2u;             // sample.rs:109
     return pg;
-}
-static inline AdsrRcp make_rcp(const AdsrConfD& c) {
-    return AdsrRcp{1.0f / c.attack_sec, 1.0f / c.decay_sec, 1.0f / c.sustain_sec, 1.0f / c.release_sec};
 }
 static inline float note_hz(float note) { return 440.0f * powf(2.0f, (note - 69.0f) / 12.0f); }   // extensions.rs:451
 
@@ -439,7 +472,12 @@ struct PassReq {
     uint32_t render_sr = 0, bd = 16;
     uint8_t* out = nullptr; uint64_t cap = 0; uint64_t* frames_written = nullptr;
     bool segment = false;
+    int x_mode = 0;                    // 0: no exchange, 1: virtual ranks in this launch, 2: NCCL
+    int x_ranks = 1, x_rank = 0;
     // derived
+    std::vector<uint32_t> x_stride, x_norms;       // per level: floats per rank slot, normalize vertices
+    std::vector<int64_t> x_off, x_red_off;         // per level: exchange buffer / all-reduce buffer (arena offsets)
+    std::vector<uint32_t> x_index;                 // per vertex: offset inside the rank slot
     std::vector<int> level;            // per vertex, -1 unreachable
     std::vector<int> last_use;
     std::vector<int64_t> buf_off, aux_off;   // work-arena byte offsets
@@ -457,7 +495,7 @@ struct LevelTasks {
     TaskList<FxTask> fx, fx_adsr, fx_norm; TaskList<NormPrefixTask> nprefix; TaskList<NormScaleTask> nscale;
     TaskList<LoopTask> loop; TaskList<MultiTask> multi; TaskList<LerpTask> lerp;
     TaskList<VoiceTask> dsine, synth, sampsyn; TaskList<BpTask> bp;
-    size_t sampsyn_smem = 0; bool sampsyn_smem_ok = true;
+    bool fx_adsr_exact = false, dsine_exact = false, synth_exact = false, sampsyn_exact = false;
     uint64_t bp_agg_bytes = 0;
 };
 
@@ -545,6 +583,25 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     for (int u : x->verts[v].edges)
                         if (!freed[u] && r.last_use[u] == L && u != x->output) { freed[u] = 1; free_slots.push_back((uint64_t)r.buf_off[u]); }
         }
+        if (r.x_ranks > 1) {
+            // exchange slots: per level [normalize peaks][band-pass maps]; identical on every rank
+            // because every rank holds the same graph
+            r.x_stride.assign(max_level + 1, 0); r.x_norms.assign(max_level + 1, 0);
+            r.x_off.assign(max_level + 1, -1); r.x_red_off.assign(max_level + 1, -1);
+            r.x_index.assign(V, 0);
+            auto is_bp = [&](const HVertex& hv) { return hv.kind == K_BANDPASS && !(hv.wet < 0.0001f || (hv.lgamma == 0.0f && hv.hgamma == 0.0f)); };
+            for (int v = 0; v < V; ++v) if (r.level[v] >= 0 && x->verts[v].kind == K_NORMALIZE) r.x_index[v] = r.x_norms[r.level[v]]++;
+            for (int L = 0; L <= max_level; ++L) r.x_stride[L] = r.x_norms[L];
+            for (int v = 0; v < V; ++v) if (r.level[v] >= 0 && is_bp(x->verts[v])) { r.x_index[v] = r.x_stride[r.level[v]]; r.x_stride[r.level[v]] += kBpXchgFloats; }
+            PassReq* leader = &r;
+            if (r.x_mode == 1) for (auto& q : reqs) if (q.x_mode == 1) { leader = &q; break; }
+            if (leader == &r) {
+                for (int L = 0; L <= max_level; ++L) if (r.x_stride[L]) {
+                    r.x_off[L] = (int64_t)bump.alloc((uint64_t)r.x_ranks * r.x_stride[L] * 4);
+                    r.x_red_off[L] = (int64_t)bump.alloc(std::max<uint32_t>(r.x_norms[L], 1) * 4);
+                }
+            } else { r.x_off = leader->x_off; r.x_red_off = leader->x_red_off; }
+        }
         if (!r.is_scan && x->output >= 0) {
             r.resample = !r.segment && x->sr > r.render_sr;                    // state.rs:533
             r.out_frames = (r.emit0 + r.emit_n - r.keep0) * x->bl;
@@ -614,6 +671,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
             auto fx_task = [&](uint32_t mode) {
                 FxTask t; memset(&t, 0, sizeof t);
                 t.h = h; t.mode = mode; t.n_in = (uint32_t)hv.edges.size(); t.in_off = in_off; t.sr = x->sr;
+                t.fsr = (float)x->sr; t.rsr = 1.0f / t.fsr;
                 return t;
             };
             switch (hv.kind) {
@@ -624,7 +682,12 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     float* runmax = peaks + r.emit_n;
                     t.peaks = peaks;
                     LT.fx_norm.v.push_back(t); LT.fx_norm.max_chunks = std::max(LT.fx_norm.max_chunks, nch);
-                    NormPrefixTask np{peaks, runmax, x->vstate_dev + (size_t)v * 8, nch, r.is_scan ? 1u : 0u};
+                    NormPrefixTask np{peaks, runmax, x->vstate_dev + (size_t)v * 8, nch, r.is_scan ? 1u : 0u, Xchg{nullptr, 0, 0, 1, 0}, nullptr};
+                    if (r.x_ranks > 1) {
+                        const int L = r.level[v];
+                        np.x = Xchg{reinterpret_cast<float*>(W + r.x_off[L]), r.x_stride[L], r.x_index[v], (uint32_t)r.x_ranks, (uint32_t)r.x_rank};
+                        if (r.x_mode == 2 && r.is_scan) np.reduced = reinterpret_cast<const float*>(W + r.x_red_off[L]);
+                    }
                     LT.nprefix.v.push_back(np);
                     NormScaleTask ns; ns.h = h; ns.runmax = runmax;
                     LT.nscale.v.push_back(ns); LT.nscale.max_chunks = std::max(LT.nscale.max_chunks, nch);
@@ -638,7 +701,8 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     } else {
                         plan_adsr(hv, x->flowws[hv.floww], pp, so);
                         FxTask t = fx_task(FX_ADSR);
-                        t.conf = hv.adsr; t.rcp = make_rcp(hv.adsr); t.wet = hv.wet; t.use_off = hv.use_off; t.use_max = hv.use_max;
+                        t.conf = make_adsr_k(hv.adsr); t.wet = hv.wet; t.use_off = hv.use_off; t.use_max = hv.use_max;
+                        if (t.conf.exotic || adsr_duration_exotic(t.fsr)) LT.fx_adsr_exact = true;
                         t.seg_ptr_off = B.alloc(so.ptr.size() * 4);
                         memcpy(B.at<uint8_t>(t.seg_ptr_off), so.ptr.data(), so.ptr.size() * 4);
                         t.seg_off = B.alloc(std::max<size_t>(so.aseg.size(), 1) * sizeof(AdsrSeg));
@@ -664,6 +728,11 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     t.state = x->vstate_dev + (size_t)v * 8 + 2;
                     t.agg = reinterpret_cast<float*>(W + r.aux_off[v]);
                     t.carry = t.agg + (size_t)(r.n_pad / kBpTile) * 8;
+                    t.x = Xchg{nullptr, 0, 0, 1, 0};
+                    if (r.x_ranks > 1) {
+                        const int L = r.level[v];
+                        t.x = Xchg{reinterpret_cast<float*>(W + r.x_off[L]), r.x_stride[L], r.x_index[v], (uint32_t)r.x_ranks, (uint32_t)r.x_rank};
+                    }
                     LT.bp.v.push_back(t); LT.bp.max_chunks = std::max(LT.bp.max_chunks, t.n_tiles);
                     hv.bp_first = false;
                     algo += io_bytes + 8ull * hv.edges.size() * r.n_frames;     // inputs are read by both scan passes
@@ -709,28 +778,33 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     plan_voices(hv, x->flowws[hv.floww], pp, so);
                     VoiceTask t; memset(&t, 0, sizeof t);
                     t.h = h; t.sr = x->sr; t.t0 = pp.t0 + r.emit0 * x->bl;
+                    t.fsr = (float)x->sr; t.rsr = 1.0f / t.fsr;
+                    bool exotic = adsr_duration_exotic(t.fsr);
                     t.seg_ptr_off = B.alloc(so.ptr.size() * 4);
                     memcpy(B.at<uint8_t>(t.seg_ptr_off), so.ptr.data(), so.ptr.size() * 4);
                     t.seg_off = B.alloc(std::max<size_t>(so.vseg.size(), 1) * sizeof(VoiceSeg));
                     memcpy(B.at<uint8_t>(t.seg_off), so.vseg.data(), so.vseg.size() * sizeof(VoiceSeg));
                     x->stats.voice_frames += so.voice_frames;
                     const uint64_t vbytes = 8ull * r.n_frames + so.vseg.size() * sizeof(VoiceSeg);
-                    if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nch); LT.dsine.bytes += vbytes; }
+                    if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; if (exotic) LT.dsine_exact = true; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nch); LT.dsine.bytes += vbytes; }
                     else if (hv.kind == K_SYNTH) {
                         t.kind = VOICE_SYNTH;
                         t.sq_vol = hv.sq.volume; t.sq_z = hv.sq.param; t.tf_vol = hv.tf.volume; t.tf_z = hv.tf.param;
-                        t.tr_vol = hv.tr.volume; t.sq = hv.sq.adsr; t.tf = hv.tf.adsr; t.tr = hv.tr.adsr;
-                        t.sq_r = make_rcp(hv.sq.adsr); t.tf_r = make_rcp(hv.tf.adsr); t.tr_r = make_rcp(hv.tr.adsr);
+                        t.tr_vol = hv.tr.volume;
+                        t.sq_iz = 1.0f / t.sq_z;                                             // synth.rs:23
+                        t.tf_add = (1.0f - t.tf_z) / 2.0f; t.tf_mul = 2.0f / (1.0f + t.tf_z);  // synth.rs:28
+                        t.env[0] = make_adsr_k(hv.sq.adsr); t.env[1] = make_adsr_k(hv.tf.adsr); t.env[2] = make_adsr_k(hv.tr.adsr);
+                        if (exotic || (t.sq_vol > 0.0f && t.env[0].exotic) || (t.tf_vol > 0.0f && t.env[1].exotic) ||
+                            (t.tr_vol > 0.0f && t.env[2].exotic)) LT.synth_exact = true;
                         t.amp_mul = 1.0f / (hv.sq.volume * m_max_vel(hv.sq.adsr) + hv.tf.volume * m_max_vel(hv.tf.adsr) +
                                             hv.tr.volume * m_max_vel(hv.tr.adsr));           // extensions.rs:465-468
                         LT.synth.v.push_back(t); LT.synth.max_chunks = std::max(LT.synth.max_chunks, nch); LT.synth.bytes += vbytes;
                     } else {
                         const DevTable& tb = x->tables[hv.table];
-                        t.kind = VOICE_SAMPSYN; t.adsr = hv.adsr; t.adsr_r = make_rcp(hv.adsr); t.amp_mul = 1.0f / m_max_vel(hv.adsr);   // extensions.rs:537
+                        t.kind = VOICE_SAMPSYN; t.env[0] = make_adsr_k(hv.adsr); t.amp_mul = 1.0f / m_max_vel(hv.adsr);   // extensions.rs:537
+                        if (exotic || t.env[0].exotic) LT.sampsyn_exact = true;
                         t.table = tb.data; t.n_frames = tb.n_frames; t.n_phase = tb.n_phase; t.fps = tb.fps;
-                        const size_t tb_bytes = (size_t)tb.n_frames * tb.n_phase * 4;
-                        if (tb_bytes > 160 * 1024) LT.sampsyn_smem_ok = false;
-                        LT.sampsyn_smem = std::max(LT.sampsyn_smem, tb_bytes);
+                        t.table_floats = tb.n_frames * tb.n_phase;
                         LT.sampsyn.v.push_back(t); LT.sampsyn.max_chunks = std::max(LT.sampsyn.max_chunks, nch); LT.sampsyn.bytes += vbytes;
                     }
                     algo += 8ull * r.n_frames;
@@ -837,8 +911,8 @@ static int run_pass(std::vector<PassReq>& reqs) {
                 append_list(Dst.loop, S.loop); append_list(Dst.multi, S.multi); append_list(Dst.lerp, S.lerp);
                 append_list(Dst.dsine, S.dsine); append_list(Dst.synth, S.synth); append_list(Dst.sampsyn, S.sampsyn);
                 append_list(Dst.bp, S.bp);
-                Dst.sampsyn_smem = std::max(Dst.sampsyn_smem, S.sampsyn_smem);
-                Dst.sampsyn_smem_ok = Dst.sampsyn_smem_ok && S.sampsyn_smem_ok;
+                Dst.fx_adsr_exact |= S.fx_adsr_exact; Dst.dsine_exact |= S.dsine_exact;
+                Dst.synth_exact |= S.synth_exact; Dst.sampsyn_exact |= S.sampsyn_exact;
                 Dst.bp_agg_bytes += S.bp_agg_bytes;
             }
             for (ResampleTask& t : F.resamps) { t.chunk_off += b; resamps.push_back(t); }
@@ -885,7 +959,10 @@ static int run_pass(std::vector<PassReq>& reqs) {
     for (auto& r : reqs) if (!r.is_scan && r.c->output >= 0) CU(cudaMemsetAsync(W + r.err_off, 0, 4, s));
     const double t_h2d_issued = now_ms();
     CU(cudaEventRecord(g->ev0, s));
-    uint64_t launches = 0;
+    uint64_t launches = 0, collectives = 0;
+    const int x_mode = reqs[0].x_mode;
+    for (auto& r : reqs) if (r.x_mode != x_mode || (x_mode == 2 && reqs.size() != 1))
+        return r.c->fail(TDG_ERR_INVALID, "time-sharded and plain passes cannot share a launch sequence");
     const uint32_t kMaxY = 65535;          // gridDim.y limit: tasks per launch
     struct Timed { int cls; uint64_t bytes; };
     std::vector<Timed> timed;
@@ -907,16 +984,30 @@ static int run_pass(std::vector<PassReq>& reqs) {
         LAUNCH_SPLIT(KC_LOOP, T.loop, LoopTask, offs[L].loop, T.loop.bytes, launch_sample_loop(tp, nb, T.loop.max_chunks, vec, s));
         LAUNCH_SPLIT(KC_MULTI, T.multi, MultiTask, offs[L].multi, T.multi.bytes, launch_sample_multi(tp, nb, T.multi.max_chunks, vec, D, s));
         LAUNCH_SPLIT(KC_LERP, T.lerp, LerpTask, offs[L].lerp, T.lerp.bytes, launch_sample_lerp(tp, nb, T.lerp.max_chunks, vec, D, s));
-        LAUNCH_SPLIT(KC_DSINE, T.dsine, VoiceTask, offs[L].dsine, T.dsine.bytes, launch_voice(VOICE_DEBUG_SINE, tp, nb, T.dsine.max_chunks, vec, 0, D, s));
-        LAUNCH_SPLIT(KC_SYNTH, T.synth, VoiceTask, offs[L].synth, T.synth.bytes, launch_voice(VOICE_SYNTH, tp, nb, T.synth.max_chunks, vec, 0, D, s));
+        LAUNCH_SPLIT(KC_DSINE, T.dsine, VoiceTask, offs[L].dsine, T.dsine.bytes, launch_voice(VOICE_DEBUG_SINE, tp, nb, T.dsine.max_chunks, T.dsine_exact, D, s));
+        LAUNCH_SPLIT(KC_SYNTH, T.synth, VoiceTask, offs[L].synth, T.synth.bytes, launch_voice(VOICE_SYNTH, tp, nb, T.synth.max_chunks, T.synth_exact, D, s));
         LAUNCH_SPLIT(KC_SAMPSYN, T.sampsyn, VoiceTask, offs[L].sampsyn, T.sampsyn.bytes,
-                     launch_voice(VOICE_SAMPSYN, tp, nb, T.sampsyn.max_chunks, vec, T.sampsyn_smem_ok ? T.sampsyn_smem : 0, D, s));
-        LAUNCH_SPLIT(KC_FX_SUM, T.fx, FxTask, offs[L].fx, T.fx.bytes, launch_fx(FX_SUM, tp, nb, T.fx.max_chunks, vec, D, s));
-        LAUNCH_SPLIT(KC_FX_ADSR, T.fx_adsr, FxTask, offs[L].fx_adsr, T.fx_adsr.bytes, launch_fx(FX_ADSR, tp, nb, T.fx_adsr.max_chunks, vec, D, s));
-        LAUNCH_SPLIT(KC_FX_NORM, T.fx_norm, FxTask, offs[L].fx_norm, T.fx_norm.bytes, launch_fx(FX_NORM_PEAK, tp, nb, T.fx_norm.max_chunks, vec, D, s));
+                     launch_voice(VOICE_SAMPSYN, tp, nb, T.sampsyn.max_chunks, T.sampsyn_exact, D, s));
+        LAUNCH_SPLIT(KC_FX_SUM, T.fx, FxTask, offs[L].fx, T.fx.bytes, launch_fx(FX_SUM, tp, nb, T.fx.max_chunks, vec, false, D, s));
+        LAUNCH_SPLIT(KC_FX_ADSR, T.fx_adsr, FxTask, offs[L].fx_adsr, T.fx_adsr.bytes, launch_fx(FX_ADSR, tp, nb, T.fx_adsr.max_chunks, vec, T.fx_adsr_exact, D, s));
+        LAUNCH_SPLIT(KC_FX_NORM, T.fx_norm, FxTask, offs[L].fx_norm, T.fx_norm.bytes, launch_fx(FX_NORM_PEAK, tp, nb, T.fx_norm.max_chunks, vec, false, D, s));
+        LAUNCH_SPLIT(KC_BP_AGG, T.bp, BpTask, offs[L].bp, T.bp_agg_bytes, launch_bp_aggregate(tp, nb, T.bp.max_chunks, vec, D, s));
+        if (x_mode && (!T.nprefix.v.empty() || !T.bp.v.empty())) {
+            // time sharding: publish this segment's peaks / filter maps, then fetch the other ranks'
+            const PassReq& r0 = reqs[0];
+            float* red = (x_mode == 2 && r0.is_scan && r0.x_red_off[L] >= 0) ? reinterpret_cast<float*>(W + r0.x_red_off[L]) : nullptr;
+            LAUNCH_SPLIT(KC_NORM_PREFIX, T.nprefix, NormPrefixTask, offs[L].nprefix, (uint64_t)0, launch_norm_total(tp, nb, red, s));
+            LAUNCH_SPLIT(KC_BP_CARRY, T.bp, BpTask, offs[L].bp, (uint64_t)0, launch_bp_total(tp, nb, D, s));
+            if (x_mode == 2 && r0.x_stride[L]) {
+                NcclApi* na = nccl_api();
+                float* xb = reinterpret_cast<float*>(W + r0.x_off[L]);
+                NC(na->AllGather(xb + (size_t)r0.x_rank * r0.x_stride[L], xb, r0.x_stride[L], kNcclFloat32, r0.c->nccl_comm, s));
+                if (red && r0.x_norms[L]) NC(na->AllReduce(red, red, r0.x_norms[L], kNcclFloat32, kNcclMax, r0.c->nccl_comm, s));
+                ++collectives;
+            }
+        }
         LAUNCH_SPLIT(KC_NORM_PREFIX, T.nprefix, NormPrefixTask, offs[L].nprefix, T.nprefix.bytes, launch_norm_prefix(tp, nb, s));
         LAUNCH_SPLIT(KC_NORM_SCALE, T.nscale, NormScaleTask, offs[L].nscale, T.nscale.bytes, launch_norm_scale(tp, nb, T.nscale.max_chunks, vec, s));
-        LAUNCH_SPLIT(KC_BP_AGG, T.bp, BpTask, offs[L].bp, T.bp_agg_bytes, launch_bp_aggregate(tp, nb, T.bp.max_chunks, vec, D, s));
         LAUNCH_SPLIT(KC_BP_CARRY, T.bp, BpTask, offs[L].bp, (uint64_t)0, launch_bp_carry(tp, nb, D, s));
         LAUNCH_SPLIT(KC_BP_APPLY, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_apply(tp, nb, T.bp.max_chunks, vec, D, s));
     }
@@ -972,7 +1063,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
         x->stats.h2d_ms = t_h2d_issued - t_planned;
         x->stats.d2h_ms = t_end - t_d2h0;
         x->stats.h2d_bytes = B.size; x->stats.d2h_bytes = d2h_bytes;
-        x->stats.kernel_launches = launches;
+        x->stats.kernel_launches = launches; x->collectives += collectives;
         x->launches += launches;
         for (int k = 0; k < KC_COUNT; ++k) x->kstats[k] = ks[k];
         if (reqs.size() > 1) x->stats.algorithmic_bytes = algo_bytes_total;
@@ -1019,6 +1110,7 @@ void tdg_ctx_destroy(tdg_ctx* h) {
     for (auto& s : c->samples) { if (s.l) cudaFree(s.l); }
     for (auto& t : c->tables) if (t.data) cudaFree(t.data);
     if (c->vstate_dev) cudaFree(c->vstate_dev);
+    if (c->nccl_comm) { nccl_api()->CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; }
     { std::lock_guard<std::mutex> lk(g_mu); c->eng->refs--; }
     delete h;
 }
@@ -1399,31 +1491,102 @@ int tdg_render(tdg_ctx* h, uint64_t chunks, uint32_t render_sr, uint32_t bitdept
 }
 
 // time sharding: audio is evaluated for [chunk0 - warmup, chunk0 + chunks) only; the event-driven
-// state advances over the whole pass of `total_chunks` chunks, exactly as a full pass would leave it
+// state advances over the whole pass of `total_chunks` chunks, exactly as a full pass would leave it.
+// With a communicator (tdg_comm_init_rank) or virtual ranks (…_segments_local) normalize peaks and
+// band-pass state cross the segment boundaries exactly; without one, `warmup_chunks` re-rendered
+// chunks let the filters converge (legacy, approximate).
+static int make_segment_req(Ctx* c, PassReq& r, bool is_scan, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks,
+                            uint64_t warmup_chunks) {
+    if (chunk0 + chunks > total_chunks) return c->fail(TDG_ERR_INVALID, "segment exceeds the pass");
+    const uint64_t w = std::min(warmup_chunks, chunk0);
+    r.c = c; r.is_scan = is_scan; r.segment = true; r.emit0 = chunk0 - w; r.emit_n = chunks + w; r.keep0 = chunk0;
+    r.total = total_chunks; r.render_sr = c->sr;
+    return TDG_OK;
+}
 int tdg_scan_segment(tdg_ctx* h, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks, uint64_t warmup_chunks) {
     Ctx* c = C_;
     if (c->output < 0) return TDG_OK;
-    if (chunk0 + chunks > total_chunks) return c->fail(TDG_ERR_INVALID, "segment exceeds the pass");
-    const uint64_t w = std::min(warmup_chunks, chunk0);
     std::vector<PassReq> reqs(1);
-    PassReq& r = reqs[0];
-    r.c = c; r.is_scan = true; r.segment = true; r.emit0 = chunk0 - w; r.emit_n = chunks + w; r.keep0 = chunk0;
-    r.total = total_chunks;
+    if (c->nccl_comm) warmup_chunks = 0;
+    if (int e = make_segment_req(c, reqs[0], true, total_chunks, chunk0, chunks, warmup_chunks)) return e;
+    if (c->nccl_comm) { reqs[0].x_mode = 2; reqs[0].x_ranks = c->x_ranks; reqs[0].x_rank = c->x_rank; }
     return run_pass(reqs);
 }
 int tdg_render_segment(tdg_ctx* h, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks, uint64_t warmup_chunks,
                        uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes, uint64_t* frames_written) {
     Ctx* c = C_;
     if (int e = valid_bd(c, bitdepth)) return e;
-    if (chunk0 + chunks > total_chunks) return c->fail(TDG_ERR_INVALID, "segment exceeds the pass");
-    const uint64_t w = std::min(warmup_chunks, chunk0);
     std::vector<PassReq> reqs(1);
+    if (c->nccl_comm) warmup_chunks = 0;
+    if (int e = make_segment_req(c, reqs[0], false, total_chunks, chunk0, chunks, warmup_chunks)) return e;
     PassReq& r = reqs[0];
-    r.c = c; r.is_scan = false; r.segment = true; r.emit0 = chunk0 - w; r.emit_n = chunks + w; r.keep0 = chunk0;
-    r.total = total_chunks; r.render_sr = c->sr; r.bd = bitdepth;
-    r.out = out_pcm; r.cap = cap_bytes; r.frames_written = frames_written;
+    r.bd = bitdepth; r.out = out_pcm; r.cap = cap_bytes; r.frames_written = frames_written;
+    if (c->nccl_comm) { r.x_mode = 2; r.x_ranks = c->x_ranks; r.x_rank = c->x_rank; }
     return run_pass(reqs);
 }
+// virtual ranks: n contexts holding the SAME project on one device evaluate n consecutive segments
+// in one launch sequence, exchanging through device memory what NCCL would carry between GPUs
+static int segments_local(tdg_ctx** hs, int n, bool is_scan, uint64_t total_chunks, const uint64_t* chunk0, const uint64_t* chunks,
+                          uint32_t bitdepth, uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written) {
+    if (n <= 0) return TDG_ERR_INVALID;
+    std::vector<PassReq> reqs(n);
+    uint64_t expect = 0;
+    for (int i = 0; i < n; ++i) {
+        Ctx* c = &hs[i]->c;
+        if (is_scan && c->output < 0) return TDG_OK;
+        if (!is_scan) if (int e = valid_bd(c, bitdepth)) return e;
+        if (chunk0[i] != expect) return c->fail(TDG_ERR_INVALID, "segments must be consecutive and start at chunk 0");
+        expect += chunks[i];
+        if (int e = make_segment_req(c, reqs[i], is_scan, total_chunks, chunk0[i], chunks[i], 0)) return e;
+        reqs[i].x_mode = n > 1 ? 1 : 0; reqs[i].x_ranks = n; reqs[i].x_rank = i; reqs[i].bd = bitdepth;
+        if (!is_scan) {
+            reqs[i].out = out_pcm ? out_pcm[i] : nullptr; reqs[i].cap = cap_bytes ? cap_bytes[i] : 0;
+            reqs[i].frames_written = frames_written ? frames_written + i : nullptr;
+        }
+    }
+    if (expect != total_chunks) return hs[0]->c.fail(TDG_ERR_INVALID, "segments must cover the whole pass");
+    return run_pass(reqs);
+}
+int tdg_scan_segments_local(tdg_ctx** hs, int n, uint64_t total_chunks, const uint64_t* chunk0, const uint64_t* chunks) {
+    return segments_local(hs, n, true, total_chunks, chunk0, chunks, 16, nullptr, nullptr, nullptr);
+}
+int tdg_render_segments_local(tdg_ctx** hs, int n, uint64_t total_chunks, const uint64_t* chunk0, const uint64_t* chunks,
+                              uint32_t bitdepth, uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written) {
+    return segments_local(hs, n, false, total_chunks, chunk0, chunks, bitdepth, out_pcm, cap_bytes, frames_written);
+}
+
+// NCCL communicator of a time-sharded render: one rank per GPU / process
+int tdg_comm_unique_id(uint8_t* out128) {
+    NcclApi* na = nccl_api();
+    if (!na->ok() || !out128) return TDG_ERR_CUDA;
+    Id128 id; memset(&id, 0, sizeof id);
+    if (na->GetUniqueId(&id) != 0) return TDG_ERR_CUDA;
+    memcpy(out128, id.b, 128);
+    return TDG_OK;
+}
+int tdg_comm_init_rank(tdg_ctx* h, int nranks, int rank, const uint8_t* id128) {
+    Ctx* c = C_;
+    NcclApi* na = nccl_api();
+    if (!na->ok()) return c->fail(TDG_ERR_CUDA, "NCCL unavailable: " + na->err);
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id128) return c->fail(TDG_ERR_INVALID, "bad communicator arguments");
+    if (c->nccl_comm) return c->fail(TDG_ERR_INVALID, "context already has a communicator");
+    cudaSetDevice(c->eng->device);
+    Id128 id; memcpy(id.b, id128, 128);
+    void* comm = nullptr;
+    NC(na->CommInitRank(&comm, nranks, id, rank));
+    c->nccl_comm = comm; c->x_ranks = nranks; c->x_rank = rank;
+    return TDG_OK;
+}
+int tdg_comm_destroy(tdg_ctx* h) {
+    Ctx* c = C_;
+    if (!c->nccl_comm) return TDG_OK;
+    cudaSetDevice(c->eng->device);
+    cudaStreamSynchronize(c->eng->stream);
+    nccl_api()->CommDestroy(c->nccl_comm);
+    c->nccl_comm = nullptr; c->x_ranks = 1; c->x_rank = 0;
+    return TDG_OK;
+}
+uint64_t tdg_collectives(tdg_ctx* h) { return h ? h->c.collectives : 0; }
 
 int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; return TDG_OK; }
 int tdg_last_pass_kernel_stats(tdg_ctx* h, tdg_kernel_stat* out, int cap) {

@@ -83,7 +83,8 @@ struct Ctx {
     uint64_t last_epoch = 0;
     PassStats stats;
     KStat kstats[KC_COUNT];                  // per kernel class, last pass (profiling on)
-    uint64_t launches = 0;
+    uint64_t launches = 0, collectives = 0;
+    void* nccl_comm = nullptr; int x_ranks = 1, x_rank = 0;      // time sharding over NCCL (tdg_comm_init_rank)
     int fail(int code, const std::string& m) { err = m; return code; }
 };
 

@@ -73,10 +73,26 @@ __device__ __forceinline__ float block_max(float m) {
 // ------------------------------------------------------------------------------------ K4: fx
 // sum_inputs (extensions.rs:310-319) + { nothing | adsr_gen (:593-651) | per-chunk peak for
 // normalize_gen (:321-329) } + apply_angle + apply_gain (:262-263), one pass over HBM.
-template <int MODE, bool VEC>
+#define TDG_FX_SEGS 24
+template <bool EXACT>
+__device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& sg, float offset, float maxmul, float minmul) {
+    float pvel, gvel;
+    if (T.use_off) {                                     // extensions.rs:620-623
+        pvel = (sg.pr == 0.0f ? k_apply_ads<EXACT>(T.conf, sg.pt + offset) : k_apply_r<EXACT>(T.conf, sg.pt + offset, sg.pr)) * sg.pv;
+        gvel = (sg.gr == 0.0f ? k_apply_ads<EXACT>(T.conf, sg.gt + offset) : k_apply_r<EXACT>(T.conf, sg.gt + offset, sg.gr)) * sg.gv;
+    } else {                                             // extensions.rs:640-641
+        pvel = k_apply_adsr<EXACT>(T.conf, sg.pt + offset) * sg.pv;
+        gvel = k_apply_adsr<EXACT>(T.conf, sg.gt + offset) * sg.gv;
+    }
+    const float adsr_vel = fmaxf(pvel, gvel) * maxmul + fminf(pvel, gvel) * minmul;
+    return 1.0f + T.wet * (adsr_vel - 1.0f);             // lerp(1.0, adsr_vel, wet)
+}
+
+template <int MODE, bool VEC, bool EXACT>
 __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ FxTask T;
     __shared__ const float* s_in[16];
+    __shared__ AdsrSeg s_seg[MODE == FX_ADSR ? TDG_FX_SEGS : 1];
     load_task(&T, tasks + blockIdx.y);
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
     const uint32_t k = blockIdx.x;
@@ -85,19 +101,24 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(con
     const uint64_t p0 = (uint64_t)k * bl;
     const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
     const bool staged = T.n_in <= 8;
-    if (staged) {                                        // pointer table into shared memory: no dependent global load per input
-        if (threadIdx.x < 2 * T.n_in) s_in[threadIdx.x] = ins[threadIdx.x];
-        __syncthreads();
-    }
     const AdsrSeg* segs = nullptr;
-    uint32_t s_lo = 0, s_hi = 0;
+    uint32_t n_seg = 0;
     float maxmul = 0.0f, minmul = 0.0f;
     if (MODE == FX_ADSR) {
         const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
-        s_lo = sp[k]; s_hi = sp[k + 1];
-        segs = reinterpret_cast<const AdsrSeg*>(blob + T.seg_off);
+        const uint32_t s_lo = sp[k];
+        n_seg = sp[k + 1] - s_lo;
+        segs = reinterpret_cast<const AdsrSeg*>(blob + T.seg_off) + s_lo;
         maxmul = T.use_max ? 1.0f : 0.0f; minmul = 1.0f - maxmul;
+        if (n_seg <= TDG_FX_SEGS) {                      // chunk's envelope states into shared memory
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(segs);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(s_seg);
+            for (uint32_t w = threadIdx.x; w < n_seg * (uint32_t)(sizeof(AdsrSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
+            segs = s_seg;
+        }
     }
+    if (staged && threadIdx.x < 2 * T.n_in) s_in[threadIdx.x] = ins[threadIdx.x];   // no dependent global load per input
+    if (staged || MODE == FX_ADSR) __syncthreads();
     float peak = 0.0f;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
         const int nv = min(4u, bl - i);
@@ -122,28 +143,30 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(con
             }
         }
         if (MODE == FX_ADSR) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j >= nv) break;
-                const uint32_t fi = i + j;
-                uint32_t s = s_lo;                       // last segment starting at or before this frame
-                while (s + 1 < s_hi && segs[s + 1].ia <= fi) ++s;
+            // last segment starting at or before the thread's first frame; the common case is that the
+            // same state covers all four frames
+            uint32_t s = 0;
+            while (s + 1 < n_seg && segs[s + 1].ia <= i) ++s;
+            const bool one = s + 1 >= n_seg || segs[s + 1].ia >= i + 4;
+            if (one) {
                 const AdsrSeg sg = segs[s];
-                if (sg.flags & 1u) continue;             // un-enveloped frame (extensions.rs:633-635)
-                const float offset = (float)fi / (float)T.sr;
-                float pvel, gvel;
-                if (T.use_off) {                         // extensions.rs:620-623
-                    pvel = sg.pr == 0.0f ? m_apply_ads(T.conf, sg.pt + offset) * sg.pv
-                                         : m_apply_r(T.conf, sg.pt + offset, sg.pr) * sg.pv;
-                    gvel = sg.gr == 0.0f ? m_apply_ads(T.conf, sg.gt + offset) * sg.gv
-                                         : m_apply_r(T.conf, sg.gt + offset, sg.gr) * sg.gv;
-                } else {                                 // extensions.rs:640-641
-                    pvel = m_apply_adsr(T.conf, sg.pt + offset) * sg.pv;
-                    gvel = m_apply_adsr(T.conf, sg.gt + offset) * sg.gv;
+                if (!(sg.flags & 1u)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float vel = adsr_frame_vel<EXACT>(T, sg, k_div<EXACT>((float)(i + j), T.fsr, T.rsr), maxmul, minmul);
+                        l[j] *= vel; r[j] *= vel;
+                    }
                 }
-                const float adsr_vel = fmaxf(pvel, gvel) * maxmul + fminf(pvel, gvel) * minmul;
-                const float vel = m_lerp(1.0f, adsr_vel, T.wet);
-                l[j] *= vel; r[j] *= vel;
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    while (s + 1 < n_seg && segs[s + 1].ia <= i + j) ++s;
+                    const AdsrSeg sg = segs[s];
+                    if (sg.flags & 1u) continue;             // un-enveloped frame (extensions.rs:633-635)
+                    const float vel = adsr_frame_vel<EXACT>(T, sg, k_div<EXACT>((float)(i + j), T.fsr, T.rsr), maxmul, minmul);
+                    if (j == 0) { l[0] *= vel; r[0] *= vel; } else if (j == 1) { l[1] *= vel; r[1] *= vel; }
+                    else if (j == 2) { l[2] *= vel; r[2] *= vel; } else { l[3] *= vel; r[3] *= vel; }
+                }
             }
         }
         if (MODE == FX_NORM_PEAK) {
@@ -166,6 +189,17 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(con
 // One block per normalize vertex.  Scan pass: every chunk is scaled by the OLD max while scan_max
 // collects the peak (extensions.rs:323-324, graph.rs:227-234).  Render pass: running max
 // (extensions.rs:326).  max() is exact, so the parallel prefix is bit-identical to the fold.
+// segment peak into the exchange slot (time sharding only)
+__global__ void __launch_bounds__(256) k_norm_total(const NormPrefixTask* __restrict__ tasks, float* __restrict__ reduce_buf) {
+    const NormPrefixTask T = tasks[blockIdx.x];
+    float m = 0.0f;
+    for (uint32_t k = threadIdx.x; k < T.n_chunks; k += blockDim.x) m = fmaxf(T.peaks[k], m);
+    m = block_max(m);
+    if (threadIdx.x == 0) {
+        T.x.buf[(size_t)T.x.rank * T.x.stride + T.x.index] = m;
+        if (reduce_buf) reduce_buf[T.x.index] = m;
+    }
+}
 __global__ void __launch_bounds__(1024) k_norm_prefix(const NormPrefixTask* __restrict__ tasks) {
     const NormPrefixTask T = tasks[blockIdx.x];
     __shared__ float part[1024];
@@ -183,13 +217,22 @@ __global__ void __launch_bounds__(1024) k_norm_prefix(const NormPrefixTask* __re
         part[tid] = fmaxf(part[tid], v);
         __syncthreads();
     }
-    const float total = part[nt - 1];
+    float total = part[nt - 1];                       // peak of the whole pass
+    float before = old_max;                           // max entering this segment's first chunk (render)
+    if (T.x.ranks > 1) {                              // segments of other ranks (max is exact: order is free)
+        for (uint32_t q = 0; q < T.x.ranks; ++q) {
+            const float v = T.x.buf[(size_t)q * T.x.stride + T.x.index];
+            total = fmaxf(total, v);
+            if (q < T.x.rank) before = fmaxf(before, v);
+        }
+        if (T.reduced) total = fmaxf(total, T.reduced[T.x.index]);
+    }
     if (T.is_scan) {
         for (uint32_t k = lo; k < hi; ++k) T.runmax[k] = old_max;
         __syncthreads();
         if (tid == 0) { const float sm = fmaxf(total, 0.0f); T.state[1] = sm; T.state[0] = sm; }
     } else {
-        float run = fmaxf(tid > 0 ? part[tid - 1] : 0.0f, old_max);   // buf_max.max(*max)
+        float run = fmaxf(tid > 0 ? part[tid - 1] : 0.0f, before);   // buf_max.max(*max)
         for (uint32_t k = lo; k < hi; ++k) { run = fmaxf(T.peaks[k], run); T.runmax[k] = run; }
         __syncthreads();
         if (tid == 0) T.state[0] = fmaxf(total, old_max);
@@ -331,38 +374,59 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
 // ------------------------------------------------------------------------------------ K5: voices
 // debug_sine_gen / synth_gen / sampsyn_gen (extensions.rs:423-578).  The host planner turns the
 // floww events into per-chunk voice segments in push order; every frame sums its live voices
-// sequentially in that order (f32 summation order is part of the contract).  Segments are staged
-// through shared memory in batches; a SampSyn wavetable is staged in shared memory when it fits.
+// sequentially in that order (f32 summation order is part of the contract).
+//
+// These kernels are FP32-issue bound, not HBM bound (8 B of output per frame against ~60-90
+// instructions per voice-frame), so the design minimises instructions per voice-frame:
+//   * a thread owns 4 consecutive frames and walks the chunk's segments once (segment-major), so the
+//     segment fetch, the held/released decision and every per-voice constant are paid once per 4
+//     frames and the four dependent chains overlap;
+//   * every loop-invariant f32 value (envelope thresholds / deltas / reciprocals, shape constants,
+//     1/sr) is computed once on the host with the reference's operations (AdsrK, VoiceTask);
+//   * the release start value apply_ads(conf, rel_t) of adsr.rs:89-92 is constant per segment and is
+//     evaluated once per (segment, oscillator) while the segments are staged in shared memory;
+//   * divisions by those constants use the exact-quotient FMA form (k_div) instead of MUFU.RCP +
+//     Newton + slow path; sin is a Cody-Waite + minimax evaluation on the FMA pipe (d_sin).
+// Accumulators stay in registers across segment batches; one float4 store per channel at the end.
 #define TDG_SEG_BATCH 64
+#ifndef TDG_SYNTH_F
+#define TDG_SYNTH_F 2           // frames per thread of the synth kernel (tuning knob, see profiles/)
+#endif
+#ifndef TDG_SYNTH_MINB
+#define TDG_SYNTH_MINB 3        // min resident blocks per SM of the synth kernel (register cap)
+#endif
 
-__device__ __forceinline__ float wavetable_eval(const float* __restrict__ tab, uint32_t n_frames,
-                                                uint32_t n_phase, float fps, float hz, float t) {
+// wavetable_act_state as DEFINED by the oracle (sampsyn is not vendored): bilinear in (time, phase).
+// floor / truncation use the conversion pipe (FRND / F2I / I2F: one issue slot each, and that pipe is
+// otherwise idle here); the table is read through the read-only path and stays L1 resident.
+__device__ __forceinline__ float wavetable_eval(const float* __restrict__ tab, float n_phase_f, int n_phase, float ymax,
+                                                int last_row_off, float fps, float hz, float t) {
     float ph = t * hz;
     ph = ph - floorf(ph);
-    const float x = ph * (float)n_phase;
-    uint32_t i0 = (uint32_t)x;
+    const float x = ph * n_phase_f;
+    int i0 = __float2int_rz(x);
     if (i0 >= n_phase) i0 = n_phase - 1;
     const float fx = x - (float)i0;
-    uint32_t i1 = i0 + 1; if (i1 >= n_phase) i1 = 0;
+    int i1 = i0 + 1; if (i1 >= n_phase) i1 = 0;
     float y = t * fps;
-    const float ymax = (float)(n_frames - 1);
     if (!(y > 0.0f)) y = 0.0f;
     if (y > ymax) y = ymax;
-    const uint32_t j0 = (uint32_t)y;
-    uint32_t j1 = j0 + 1; if (j1 >= n_frames) j1 = n_frames - 1;
+    const int j0 = __float2int_rz(y);
     const float fy = y - (float)j0;
-    const float* r0 = tab + (size_t)j0 * n_phase;
-    const float* r1 = tab + (size_t)j1 * n_phase;
-    const float a = r0[i0] + fx * (r0[i1] - r0[i0]);
-    const float b = r1[i0] + fx * (r1[i1] - r1[i0]);
+    const int r0 = j0 * n_phase;
+    const int r1 = min(r0 + n_phase, last_row_off);
+    const float a0 = __ldg(tab + r0 + i0), a1 = __ldg(tab + r0 + i1), b0 = __ldg(tab + r1 + i0), b1 = __ldg(tab + r1 + i1);
+    const float a = a0 + fx * (a1 - a0);
+    const float b = b0 + fx * (b1 - b0);
     return a + fy * (b - a);
 }
 
-template <int KIND, bool VEC, bool TAB_SMEM>
-__global__ void __launch_bounds__(TDG_THREADS) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
-    extern __shared__ __align__(16) float dyn_smem[];
+// F = consecutive frames per thread (register pressure: the three-oscillator synth body runs 2-wide)
+template <int KIND, bool EXACT, int F>
+__global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : 4) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ VoiceTask T;
-    __shared__ VoiceSeg segs[TDG_SEG_BATCH];
+    __shared__ __align__(16) VoiceSeg segs[TDG_SEG_BATCH];
+    __shared__ float relv[3][TDG_SEG_BATCH];       // apply_ads(conf_o, rel_t) per (oscillator, segment)
     load_task(&T, tasks + blockIdx.y);
     const uint32_t k = blockIdx.x;
     if (k >= T.h.n_chunks) return;
@@ -371,79 +435,107 @@ __global__ void __launch_bounds__(TDG_THREADS) k_voice(const VoiceTask* __restri
     const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
     const uint32_t s_lo = sp[k], s_hi = sp[k + 1];
     const VoiceSeg* gsegs = reinterpret_cast<const VoiceSeg*>(blob + T.seg_off);
-    const float* tab = T.table;
-    if (KIND == VOICE_SAMPSYN && TAB_SMEM) {
-        const uint32_t n = T.n_frames * T.n_phase;
-        for (uint32_t i = threadIdx.x; i < n; i += TDG_THREADS) dyn_smem[i] = T.table[i];
-        tab = dyn_smem;
-        __syncthreads();
-    }
-    const float fsr = (float)T.sr;
-    // One frame per thread per inner iteration, loops kept rolled: the per-voice body is large and the
-    // kernel is instruction-issue bound, so code size (I-cache) matters more than store width.
-    // Segment batches beyond the first accumulate through out_l (same thread, same address).
-    uint32_t sb = s_lo;
-    bool first = true;
-    do {
-        const uint32_t nb = min((uint32_t)TDG_SEG_BATCH, s_hi - sb);
-        const bool last = sb + nb >= s_hi;
-        __syncthreads();
-        {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(gsegs + sb);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(segs);
-            for (uint32_t w = threadIdx.x; w < nb * (uint32_t)(sizeof(VoiceSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
+    const float* __restrict__ tab = T.table;
+    const float fsr = T.fsr, rsr = T.rsr;
+    const bool vec = (bl % F) == 0;
+    const float n_phase_f = (float)T.n_phase, ymax = (float)(T.n_frames - 1);
+    const int last_row_off = (int)((T.n_frames - 1) * T.n_phase);
+    for (uint32_t base = 0; base < bl; base += TDG_THREADS * F) {
+        const uint32_t i0 = base + threadIdx.x * F;
+        float acc[F], time[F], off[F];
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+            acc[j] = 0.0f;
+            time[j] = k_div<EXACT>((float)(T.t0 + p0 + i0 + j), fsr, rsr);      // (t + i) as f32 / sr as f32
+            off[j] = k_div<EXACT>((float)(i0 + j), fsr, rsr);                   // i as f32 / sr as f32
         }
-        __syncthreads();
-#pragma unroll 1
-        for (uint32_t i = threadIdx.x; i < bl; i += TDG_THREADS) {
-            const uint64_t p = p0 + i;
-            float acc = first ? 0.0f : T.h.out_l[p];
-            const float time = (float)(T.t0 + p) / fsr;            // (t + i) as f32 / sr as f32
-            const float off = (float)i / fsr;                      // i as f32 / sr as f32
+        for (uint32_t sb = s_lo; sb < s_hi; sb += TDG_SEG_BATCH) {
+            const uint32_t nb = min((uint32_t)TDG_SEG_BATCH, s_hi - sb);
+            __syncthreads();
+            {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(gsegs + sb);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(segs);
+                for (uint32_t w = threadIdx.x; w < nb * (uint32_t)(sizeof(VoiceSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
+            }
+            __syncthreads();
+            if (KIND != VOICE_DEBUG_SINE) {
+                if (threadIdx.x < nb) {
+                    const float rt = segs[threadIdx.x].rel_t;
+                    if (rt != 0.0f) {
+                        relv[0][threadIdx.x] = k_apply_ads<EXACT>(T.env[0], rt);
+                        if (KIND == VOICE_SYNTH) {
+                            relv[1][threadIdx.x] = k_apply_ads<EXACT>(T.env[1], rt);
+                            relv[2][threadIdx.x] = k_apply_ads<EXACT>(T.env[2], rt);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (i0 >= bl) continue;
 #pragma unroll 1
             for (uint32_t s = 0; s < nb; ++s) {
-                const VoiceSeg sg = segs[s];
-                if (i < sg.ia || i >= sg.ib) continue;
-                const bool rel = sg.rel_t != 0.0f;
-                float smp;
-                if (KIND == VOICE_DEBUG_SINE) {                           // extensions.rs:450-454
-                    smp = d_sin(m_osc_arg(time, sg.hz)) * sg.vel;
-                } else if (KIND == VOICE_SYNTH) {                         // extensions.rs:500-522
-                    const float env_time = sg.env_t + off;
-                    float sn = 0.0f;
-                    if (T.sq_vol > 0.0f || T.tf_vol > 0.0f) sn = d_sin(m_osc_arg(time, sg.hz));
-                    smp = 0.0f;
-                    if (T.sq_vol > 0.0f) {
-                        const float e = rel ? m_apply_r_rt(T.sq, env_time, sg.rel_t) : m_apply_ads(T.sq, env_time);
-                        smp += m_square_from_sin(sn, T.sq_z) * sg.vel * e * T.sq_vol;
+                const float4 sa = *reinterpret_cast<const float4*>(&segs[s]);         // hz, vel, env_t, rel_t
+                const uint2 sr_ = *reinterpret_cast<const uint2*>(&segs[s].ia);       // ia, ib
+                if (i0 + F <= sr_.x || i0 >= sr_.y) continue;
+                const float hz = sa.x, vel = sa.y, env_t = sa.z, rel_t = sa.w;
+                const bool rel = rel_t != 0.0f;
+                float smp[F];
+                if (KIND == VOICE_DEBUG_SINE) {                                       // extensions.rs:450-454
+#pragma unroll
+                    for (int j = 0; j < F; ++j) smp[j] = d_sin(m_osc_arg(time[j], hz)) * vel;
+                } else if (KIND == VOICE_SYNTH) {                                     // extensions.rs:500-522
+                    const float r0 = relv[0][s], r1 = relv[1][s], r2 = relv[2][s];
+#pragma unroll
+                    for (int j = 0; j < F; ++j) {
+                        const float env_time = env_t + off[j];
+                        float sn = 0.0f, v = 0.0f;
+                        if (T.sq_vol > 0.0f || T.tf_vol > 0.0f) sn = d_sin(m_osc_arg(time[j], hz));
+                        if (T.sq_vol > 0.0f) {
+                            const float e = rel ? k_apply_r<EXACT>(T.env[0], env_time, r0) : k_apply_ads<EXACT>(T.env[0], env_time);
+                            v = fminf(fmaxf(sn, -T.sq_z), T.sq_z) * T.sq_iz * vel * e * T.sq_vol;
+                        }
+                        if (T.tf_vol > 0.0f) {
+                            const float e = rel ? k_apply_r<EXACT>(T.env[1], env_time, r1) : k_apply_ads<EXACT>(T.env[1], env_time);
+                            v += (fminf(sn, T.tf_z) + T.tf_add) * T.tf_mul * vel * e * T.tf_vol;
+                        }
+                        if (T.tr_vol > 0.0f) {
+                            const float e = rel ? k_apply_r<EXACT>(T.env[2], env_time, r2) : k_apply_ads<EXACT>(T.env[2], env_time);
+                            v += m_triangle(time[j], hz) * vel * e * T.tr_vol;
+                        }
+                        smp[j] = v * T.amp_mul;
                     }
-                    if (T.tf_vol > 0.0f) {
-                        const float e = rel ? m_apply_r_rt(T.tf, env_time, sg.rel_t) : m_apply_ads(T.tf, env_time);
-                        smp += m_topflat_from_sin(sn, T.tf_z) * sg.vel * e * T.tf_vol;
+                } else {                                                              // extensions.rs:560-571
+                    const float r0 = relv[0][s];
+#pragma unroll
+                    for (int j = 0; j < F; ++j) {
+                        const float env_time = env_t + off[j];
+                        const float e = rel ? k_apply_r<EXACT>(T.env[0], env_time, r0) : k_apply_ads<EXACT>(T.env[0], env_time);
+                        const float g = vel * e * T.amp_mul;
+                        smp[j] = wavetable_eval(tab, n_phase_f, (int)T.n_phase, ymax, last_row_off, T.fps, hz, env_time + rel_t) * g;
                     }
-                    if (T.tr_vol > 0.0f) {
-                        const float e = rel ? m_apply_r_rt(T.tr, env_time, sg.rel_t) : m_apply_ads(T.tr, env_time);
-                        smp += m_triangle(time, sg.hz) * sg.vel * e * T.tr_vol;
-                    }
-                    smp *= T.amp_mul;
-                } else {                                                  // extensions.rs:560-571
-                    const float env_time = sg.env_t + off;
-                    const float e = rel ? m_apply_r_rt(T.adsr, env_time, sg.rel_t) : m_apply_ads(T.adsr, env_time);
-                    const float vel = sg.vel * e * T.amp_mul;
-                    smp = 0.0f;
-                    smp += wavetable_eval(tab, T.n_frames, T.n_phase, T.fps, sg.hz, env_time + sg.rel_t) * vel;
                 }
-                acc += smp;
+#pragma unroll
+                for (int j = 0; j < F; ++j)
+                    if (i0 + j >= sr_.x && i0 + j < sr_.y) acc[j] += smp[j];
             }
-            if (last) {
-                float l = acc, r = acc;
-                apply_pg(l, r, T.h.pg);
-                T.h.out_l[p] = l; T.h.out_r[p] = r;
-            } else T.h.out_l[p] = acc;
         }
-        first = false;
-        sb += nb;
-    } while (sb < s_hi);
+        if (i0 < bl) {
+            float l[F], r[F];
+#pragma unroll
+            for (int j = 0; j < F; ++j) { l[j] = acc[j]; r[j] = acc[j]; apply_pg(l[j], r[j], T.h.pg); }
+            float* ol = T.h.out_l + p0 + i0; float* orr = T.h.out_r + p0 + i0;
+            if (vec && F == 4) {
+                *reinterpret_cast<float4*>(ol) = make_float4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<float4*>(orr) = make_float4(r[0], r[1], r[2], r[3]);
+            } else if (vec && F == 2) {
+                *reinterpret_cast<float2*>(ol) = make_float2(l[0], l[1]);
+                *reinterpret_cast<float2*>(orr) = make_float2(r[0], r[1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < F; ++j) if (i0 + j < bl) { ol[j] = l[j]; orr[j] = r[j]; }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------ K7: band pass scan
@@ -545,29 +637,69 @@ __global__ void __launch_bounds__(kBpThreads) k_bp_aggregate(const BpTask* __res
     }
 }
 // pass B: scan of tile aggregates -> state entering every tile; one block per filter vertex
-__global__ void __launch_bounds__(kBpThreads) k_bp_carry(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
-    __shared__ BpTask T;
-    __shared__ float init[4];
-    load_task(&T, tasks + blockIdx.x);
-    if (threadIdx.x == 0) {
-        if (T.first) {                                          // extensions.rs:664-670
-            const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
-            float l = 0.0f, r = 0.0f;
-            for (uint32_t a = 0; a < T.n_in; ++a) { l += ins[2 * a][0]; r += ins[2 * a + 1][0]; }
-            init[0] = l; init[1] = r; init[2] = l; init[3] = r;
-        } else {
-            init[0] = T.state[0]; init[1] = T.state[1]; init[2] = T.state[2]; init[3] = T.state[3];
-        }
+__device__ __forceinline__ void bp_init_state(const BpTask& T, const uint8_t* blob, float (&init)[4]) {
+    if (T.first) {                                              // extensions.rs:664-670
+        const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
+        float l = 0.0f, r = 0.0f;
+        for (uint32_t a = 0; a < T.n_in; ++a) { l += ins[2 * a][0]; r += ins[2 * a + 1][0]; }
+        init[0] = l; init[1] = r; init[2] = l; init[3] = r;
+    } else {
+        init[0] = T.state[0]; init[1] = T.state[1]; init[2] = T.state[2]; init[3] = T.state[3];
     }
-    __syncthreads();
-    const uint32_t n = T.n_tiles, per = (n + blockDim.x - 1) / blockDim.x;
-    const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+}
+__device__ __forceinline__ Aff bp_tiles_fold(const BpTask& T, uint32_t lo, uint32_t hi) {
     Aff mine = aff_id();
     for (uint32_t t = lo; t < hi; ++t) {
         const float* a = T.agg + (size_t)t * 8;
         mine = aff_then(mine, Aff{a[4], a[5], a[0], a[1], a[2], a[3]});
     }
-    Aff exc = block_aff_scan(mine, nullptr);
+    return mine;
+}
+// time sharding: the segment's whole affine map (and, on rank 0, the pass's initial state) into the slot
+__global__ void __launch_bounds__(kBpThreads) k_bp_total(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    __shared__ BpTask T;
+    load_task(&T, tasks + blockIdx.x);
+    const uint32_t n = T.n_tiles, per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+    Aff total;
+    block_aff_scan(bp_tiles_fold(T, lo, hi), &total);
+    if (threadIdx.x == 0) {
+        float* o = T.x.buf + (size_t)T.x.rank * T.x.stride + T.x.index;
+        o[0] = total.al; o[1] = total.ah; o[2] = total.b0; o[3] = total.b1; o[4] = total.b2; o[5] = total.b3;
+        float init[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (T.x.rank == 0) bp_init_state(T, blob, init);
+        o[6] = init[0]; o[7] = init[1]; o[8] = init[2]; o[9] = init[3];
+    }
+}
+__global__ void __launch_bounds__(kBpThreads) k_bp_carry(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    __shared__ BpTask T;
+    __shared__ float init[4];
+    load_task(&T, tasks + blockIdx.x);
+    if (threadIdx.x == 0) {
+        float st[4];
+        if (T.x.ranks > 1) {
+            // state entering this segment: rank 0's initial state pushed through the maps of all earlier
+            // segments; the end-of-pass state (all maps) is what every rank keeps for the next pass
+            const float* g0 = T.x.buf + T.x.index;
+            st[0] = g0[6]; st[1] = g0[7]; st[2] = g0[8]; st[3] = g0[9];
+            float mine[4] = {st[0], st[1], st[2], st[3]};
+            for (uint32_t q = 0; q < T.x.ranks; ++q) {
+                if (q == T.x.rank) { mine[0] = st[0]; mine[1] = st[1]; mine[2] = st[2]; mine[3] = st[3]; }
+                const float* g = T.x.buf + (size_t)q * T.x.stride + T.x.index;
+                st[0] = fmaf(g[0], st[0], g[2]); st[1] = fmaf(g[0], st[1], g[3]);
+                st[2] = fmaf(g[1], st[2], g[4]); st[3] = fmaf(g[1], st[3], g[5]);
+            }
+            T.state[0] = st[0]; T.state[1] = st[1]; T.state[2] = st[2]; T.state[3] = st[3];
+            init[0] = mine[0]; init[1] = mine[1]; init[2] = mine[2]; init[3] = mine[3];
+        } else {
+            bp_init_state(T, blob, st);
+            init[0] = st[0]; init[1] = st[1]; init[2] = st[2]; init[3] = st[3];
+        }
+    }
+    __syncthreads();
+    const uint32_t n = T.n_tiles, per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+    Aff exc = block_aff_scan(bp_tiles_fold(T, lo, hi), nullptr);
     float c0 = fmaf(exc.al, init[0], exc.b0), c1 = fmaf(exc.al, init[1], exc.b1);
     float c2 = fmaf(exc.ah, init[2], exc.b2), c3 = fmaf(exc.ah, init[3], exc.b3);
     for (uint32_t t = lo; t < hi; ++t) {
@@ -622,7 +754,7 @@ __global__ void __launch_bounds__(kBpThreads) k_bp_apply(const BpTask* __restric
         else { st4<false>(T.h.out_l, p + 4 * h, nvh, a); st4<false>(T.h.out_r, p + 4 * h, nvh, b); }
     }
     // the run holding the last frame of the pass leaves the state for the next pass
-    if (nv > 0 && p + nv == T.h.n_frames) { T.state[0] = ll; T.state[1] = lr; T.state[2] = hl; T.state[3] = hr; }
+    if (T.x.ranks <= 1 && nv > 0 && p + nv == T.h.n_frames) { T.state[0] = ll; T.state[1] = lr; T.state[2] = hl; T.state[3] = hr; }
 }
 
 // ------------------------------------------------------------------------------------ K9b: quantise
@@ -770,15 +902,26 @@ static inline dim3 grid2(uint64_t x, uint32_t y) { return dim3((unsigned)x, y, 1
 
 #define TDG_VEC_DISPATCH(vec, K, ...) do { if (vec) K<true> __VA_ARGS__; else K<false> __VA_ARGS__; } while (0)
 
-cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
+cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, const uint8_t* blob, cudaStream_t s) {
     const dim3 g = grid2(max_chunks, n);
-    if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_SUM, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
-    else if (mode == FX_ADSR) { if (vec) k_fx<FX_ADSR, true><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
-    else { if (vec) k_fx<FX_NORM_PEAK, true><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_NORM_PEAK, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
+    if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_SUM, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
+    else if (mode == FX_ADSR) {
+        if (exact) { if (vec) k_fx<FX_ADSR, true, true><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, true><<<g, TDG_THREADS, 0, s>>>(t, blob); }
+        else { if (vec) k_fx<FX_ADSR, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
+    }
+    else { if (vec) k_fx<FX_NORM_PEAK, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_NORM_PEAK, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
     return cudaGetLastError();
 }
 cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s) {
     k_norm_prefix<<<n, 1024, 0, s>>>(t);
+    return cudaGetLastError();
+}
+cudaError_t launch_norm_total(const NormPrefixTask* t, uint32_t n, float* reduce_buf, cudaStream_t s) {
+    k_norm_total<<<n, 256, 0, s>>>(t, reduce_buf);
+    return cudaGetLastError();
+}
+cudaError_t launch_bp_total(const BpTask* t, uint32_t n, const uint8_t* blob, cudaStream_t s) {
+    k_bp_total<<<n, kBpThreads, 0, s>>>(t, blob);
     return cudaGetLastError();
 }
 cudaError_t launch_norm_scale(const NormScaleTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s) {
@@ -798,28 +941,17 @@ cudaError_t launch_sample_lerp(const LerpTask* t, uint32_t n, uint32_t max_chunk
     return cudaGetLastError();
 }
 
-template <int KIND, bool VEC, bool TS>
-static cudaError_t launch_voice_t(const VoiceTask* t, uint32_t n, uint32_t max_chunks, size_t smem, const uint8_t* blob, cudaStream_t s) {
-    if (smem > 0) {
-        cudaError_t e = cudaFuncSetAttribute(k_voice<KIND, VEC, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    k_voice<KIND, VEC, TS><<<grid2(max_chunks, n), TDG_THREADS, smem, s>>>(t, blob);
+template <int KIND, bool EXACT>
+static cudaError_t launch_voice_t(const VoiceTask* t, uint32_t n, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s) {
+    k_voice<KIND, EXACT, KIND == VOICE_SYNTH ? TDG_SYNTH_F : 4><<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t, blob);
     return cudaGetLastError();
 }
-cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool vec, size_t table_smem_bytes,
-                         const uint8_t* blob, cudaStream_t s) {
+cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool exact, const uint8_t* blob, cudaStream_t s) {
     if (kind == VOICE_DEBUG_SINE)
-        return vec ? launch_voice_t<VOICE_DEBUG_SINE, true, false>(t, n, max_chunks, 0, blob, s)
-                   : launch_voice_t<VOICE_DEBUG_SINE, false, false>(t, n, max_chunks, 0, blob, s);
+        return exact ? launch_voice_t<VOICE_DEBUG_SINE, true>(t, n, max_chunks, blob, s) : launch_voice_t<VOICE_DEBUG_SINE, false>(t, n, max_chunks, blob, s);
     if (kind == VOICE_SYNTH)
-        return vec ? launch_voice_t<VOICE_SYNTH, true, false>(t, n, max_chunks, 0, blob, s)
-                   : launch_voice_t<VOICE_SYNTH, false, false>(t, n, max_chunks, 0, blob, s);
-    if (table_smem_bytes > 0)
-        return vec ? launch_voice_t<VOICE_SAMPSYN, true, true>(t, n, max_chunks, table_smem_bytes, blob, s)
-                   : launch_voice_t<VOICE_SAMPSYN, false, true>(t, n, max_chunks, table_smem_bytes, blob, s);
-    return vec ? launch_voice_t<VOICE_SAMPSYN, true, false>(t, n, max_chunks, 0, blob, s)
-               : launch_voice_t<VOICE_SAMPSYN, false, false>(t, n, max_chunks, 0, blob, s);
+        return exact ? launch_voice_t<VOICE_SYNTH, true>(t, n, max_chunks, blob, s) : launch_voice_t<VOICE_SYNTH, false>(t, n, max_chunks, blob, s);
+    return exact ? launch_voice_t<VOICE_SAMPSYN, true>(t, n, max_chunks, blob, s) : launch_voice_t<VOICE_SAMPSYN, false>(t, n, max_chunks, blob, s);
 }
 
 cudaError_t launch_bp_aggregate(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {

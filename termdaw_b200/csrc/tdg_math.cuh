@@ -60,40 +60,65 @@ TDG_HD float m_triangle(float t, float hz) {
 }
 
 
+// ---- AdsrK: host builder (plain C++, same f32 operations as the reference's expressions) ---------
+inline bool adsr_duration_exotic(float d) {
+    if (d == 0.0f) return false;
+    const float a = fabsf(d);
+    return !(a >= 1e-6f && a <= 1e6f);          // NaN, inf, denormal-ish or huge
+}
+inline AdsrK make_adsr_k(const AdsrConfD& c) {
+    AdsrK k;
+    k.a = c.attack_sec; k.ad = c.attack_sec + c.decay_sec; k.ads = c.attack_sec + c.decay_sec + c.sustain_sec;
+    k.dsec = c.decay_sec; k.ssec = c.sustain_sec; k.rsec = c.release_sec;
+    k.ra = 1.0f / c.attack_sec; k.rd = 1.0f / c.decay_sec; k.rs = 1.0f / c.sustain_sec; k.rr = 1.0f / c.release_sec;
+    k.v0 = c.std_vel; k.v1 = c.attack_vel; k.v2 = c.decay_vel; k.v3 = c.sustain_vel; k.v4 = c.release_vel;
+    k.d01 = c.attack_vel - c.std_vel; k.d12 = c.decay_vel - c.attack_vel; k.d23 = c.sustain_vel - c.decay_vel;
+    k.d34 = c.release_vel - c.sustain_vel;
+    k.exotic = (adsr_duration_exotic(c.attack_sec) || adsr_duration_exotic(c.decay_sec) ||
+                adsr_duration_exotic(c.sustain_sec) || adsr_duration_exotic(c.release_sec)) ? 1u : 0u;
+    return k;
+}
+
 // ---- device-only fast forms --------------------------------------------------------------------
 #ifdef __CUDACC__
-// t / d for a per-vertex constant d with rcp = 1/d precomputed on the host: one Newton step on the
-// exact FMA residual gives the correctly rounded quotient (Markstein) without MUFU.RCP; anything
-// unusual (d == 0, inf/nan, zero or extreme quotients) takes the IEEE division.
-__device__ __forceinline__ float d_div(float t, float d, float rcp) {
-    const float q = t * rcp;
-    const float e = fmaf(-q, d, t);
-    const float q1 = fmaf(e, rcp, q);
-    const float aq = fabsf(q);
-    return (aq > 1e-30f && aq < 1e30f && fabsf(rcp) < 1e30f) ? q1 : t / d;
+// t / d for a per-vertex constant d with r = RN(1/d) from the host: one Newton step on the exact FMA
+// residual gives the correctly rounded quotient (Markstein; checked against IEEE division on 1.2e9
+// operand pairs, DESIGN.md "arithmetic") without MUFU.RCP or the division slow path.  d == 0 makes
+// r infinite and q = t*inf is already t/0 (inf, -inf or NaN), which the |q| < inf test passes on.
+// EXACT = plain IEEE division, used for launches holding an exotic duration (AdsrK::exotic).
+template <bool EXACT>
+__device__ __forceinline__ float k_div(float t, float d, float r) {
+    if (EXACT) return t / d;
+    const float q = t * r;
+    const float q1 = fmaf(fmaf(-q, d, t), r, q);
+    return fabsf(q) < __int_as_float(0x7f800000) ? q1 : q;
 }
-__device__ __forceinline__ float d_ads_internal(const AdsrConfD& c, const AdsrRcp& r, float t) {   // adsr.rs:46-60
-    if (t <= c.attack_sec) return m_lerp(c.std_vel, c.attack_vel, d_div(t, c.attack_sec, r.attack));
-    if (t <= c.attack_sec + c.decay_sec)
-        return m_lerp(c.attack_vel, c.decay_vel, d_div(t - c.attack_sec, c.decay_sec, r.decay));
-    if (t <= c.attack_sec + c.decay_sec + c.sustain_sec)
-        return m_lerp(c.decay_vel, c.sustain_vel, d_div(t - c.attack_sec - c.decay_sec, c.sustain_sec, r.sustain));
+template <bool EXACT>
+__device__ __forceinline__ float k_ads_internal(const AdsrK& c, float t) {                   // adsr.rs:46-60
+    if (t <= c.a) return c.v0 + k_div<EXACT>(t, c.a, c.ra) * c.d01;
+    if (t <= c.ad) return c.v1 + k_div<EXACT>(t - c.a, c.dsec, c.rd) * c.d12;
+    if (t <= c.ads) return c.v2 + k_div<EXACT>(t - c.a - c.dsec, c.ssec, c.rs) * c.d23;
     return -1000.0f;
 }
-__device__ __forceinline__ float d_apply_ads(const AdsrConfD& c, const AdsrRcp& r, float t) {
-    const float res = d_ads_internal(c, r, t);
-    return res <= -1.0f ? c.sustain_vel : res;
+template <bool EXACT>
+__device__ __forceinline__ float k_apply_ads(const AdsrK& c, float t) {                      // adsr.rs:62-69
+    const float res = k_ads_internal<EXACT>(c, t);
+    return res <= -1.0f ? c.v3 : res;
 }
-__device__ __forceinline__ float d_apply_r(const AdsrConfD& c, const AdsrRcp& r, float t, float old_val) {
-    return m_lerp(old_val, c.release_vel, fminf(d_div(t, c.release_sec, r.release), 1.0f));
+template <bool EXACT>
+__device__ __forceinline__ float k_apply_r(const AdsrK& c, float t, float old_val) {         // adsr.rs:71-73
+    return old_val + fminf(k_div<EXACT>(t, c.rsec, c.rr), 1.0f) * (c.v4 - old_val);
 }
-__device__ __forceinline__ float d_apply_adsr(const AdsrConfD& c, const AdsrRcp& r, float t) {
-    const float res = d_ads_internal(c, r, t);
+template <bool EXACT>
+__device__ __forceinline__ float k_apply_adsr(const AdsrK& c, float t) {                     // adsr.rs:75-86
+    const float res = k_ads_internal<EXACT>(c, t);
     if (res <= -1.0f)
-        return m_lerp(c.sustain_vel, c.release_vel,
-                      fminf(d_div(t - c.attack_sec - c.decay_sec - c.sustain_sec, c.release_sec, r.release), 1.0f));
+        return c.v3 + fminf(k_div<EXACT>(t - c.a - c.dsec - c.ssec, c.rsec, c.rr), 1.0f) * c.d34;
     return res;
 }
+#endif
+
+#ifdef __CUDACC__
 // floorf without the conversion pipe: exact for every finite input
 __device__ __forceinline__ float d_floor(float y) {
     if (fabsf(y) < 4194304.0f) {

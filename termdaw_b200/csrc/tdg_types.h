@@ -25,6 +25,18 @@ struct AdsrConfD {          // adsr.rs:2-12
 
 struct AdsrRcp { float attack, decay, sustain, release; };   // 1/x of the four durations (host division)
 
+// Device form of an envelope: every loop-invariant f32 value of adsr.rs:46-92 evaluated ONCE on the
+// host with the reference's own operations (thresholds a, a+d, (a+d)+s; lerp deltas b-a; IEEE
+// reciprocals for the exact-division shortcut of tdg_math.cuh).  `exotic` marks a duration that is
+// neither 0 nor in [1e-6, 1e6]: launches containing one use the plain-division kernel variant.
+struct AdsrK {
+    float a, ad, ads, dsec, ssec, rsec;
+    float ra, rd, rs, rr;
+    float v0, v1, v2, v3, v4;
+    float d01, d12, d23, d34;
+    uint32_t exotic;
+};
+
 struct TaskHdr {
     float* out_l;
     float* out_r;
@@ -52,20 +64,28 @@ struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan 
     TaskHdr h;
     uint32_t mode, n_in;
     uint64_t in_off;        // blob: n_in pairs of (const float* l, const float* r)
-    AdsrConfD conf;
-    AdsrRcp rcp;
-    float wet;
+    AdsrK conf;
+    float wet, fsr, rsr;    // fsr = sr as f32, rsr = 1/fsr
     uint32_t use_off, use_max, sr;
     uint64_t seg_ptr_off;   // blob: uint32[n_chunks+1], indices into the AdsrSeg array
     uint64_t seg_off;       // blob: AdsrSeg[]
     float* peaks;           // FX_NORM_PEAK: [n_chunks] max |x| over L and R of the summed chunk
 };
 
+// Time sharding: a pass split into `x_ranks` consecutive segments.  Every DAG level owns
+// an exchange buffer of x_ranks slots of `x_stride` floats; a task's own values live at
+// x_buf[x_rank * x_stride + x_index ...].  The slots of the other ranks arrive by ncclAllGather over
+// NVLink (one process per GPU) or are written by sibling segments of the same launch ("virtual
+// ranks", used to test the hand-off arithmetic on one GPU).
+struct Xchg { float* buf; uint32_t stride, index, ranks, rank; };
+
 struct NormPrefixTask {     // normalize_gen's max bookkeeping (extensions.rs:321-329), one block per task
     const float* peaks;
     float* runmax;          // [n_chunks] the `max` each chunk is scaled by
     float* state;           // device-resident (max, scan_max) of this vertex
     uint32_t n_chunks, is_scan;
+    Xchg x;                 // x.ranks > 1: slot = { segment peak }
+    const float* reduced;   // scan pass over NCCL: global peak from ncclAllReduce(max), else null
 };
 struct NormScaleTask {      // buf *= 1/max, then pan + gain, in place
     TaskHdr h;
@@ -83,19 +103,20 @@ enum VoiceKind : uint32_t { VOICE_DEBUG_SINE = 0, VOICE_SYNTH = 1, VOICE_SAMPSYN
 struct VoiceTask {
     TaskHdr h;
     uint32_t kind, sr;
+    float fsr, rsr;         // sr as f32 and its IEEE reciprocal
     uint64_t t0;            // graph time of pass frame 0 (time = (t0 + p) as f32 / sr as f32)
     uint64_t seg_ptr_off;   // blob: uint32[n_chunks+1]
     uint64_t seg_off;       // blob: VoiceSeg[]
-    // Synth (extensions.rs:44-50)
-    float sq_vol, sq_z, tf_vol, tf_z, tr_vol, amp_mul;
-    AdsrConfD sq, tf, tr;
-    AdsrRcp sq_r, tf_r, tr_r, adsr_r;
-    // SampSyn (extensions.rs:51-56): adsr + wavetable [n_frames][n_phase]
-    AdsrConfD adsr;
+    // Synth (extensions.rs:44-50); shape constants of synth.rs:22-29 evaluated on the host:
+    // sq_iz = 1/z, tf_add = (1-z)/2, tf_mul = 2/(1+z)
+    float sq_vol, sq_z, sq_iz, tf_vol, tf_z, tf_add, tf_mul, tr_vol, amp_mul;
+    uint32_t pad0;
+    AdsrK env[3];           // square, topflat, triangle; SampSyn (extensions.rs:51-56) uses env[0]
+    // SampSyn wavetable [n_frames][n_phase]
     const float* table;
     uint32_t n_frames, n_phase;
     float fps;
-    uint32_t table_in_smem;
+    uint32_t table_floats;
 };
 
 struct BpTask {             // band_pass_gen (extensions.rs:654-689) as a chunked linear-recurrence scan
@@ -106,9 +127,11 @@ struct BpTask {             // band_pass_gen (extensions.rs:654-689) as a chunke
     uint32_t first;         // seed the four states with frame 0 of this pass (extensions.rs:664-670)
     uint32_t n_tiles;
     float* state;           // device-resident lprevl, lprevr, hprevl, hprevr (carried between passes)
-    float* agg;             // [n_tiles][4] end state of each tile started from zero
+    float* agg;             // [n_tiles][8] end state of each tile started from zero + decays
     float* carry;           // [n_tiles][4] true state entering each tile
+    Xchg x;                 // x.ranks > 1: slot = { al, ah, b0..b3 (segment map), init0..3 (rank 0 only) }
 };
+static const int kBpXchgFloats = 10;
 
 struct QuantTask {          // write_16s / write_32s (state.rs:517-532) + hound's byte layout
     const float* in_l;
