@@ -11,7 +11,10 @@ quantisation.  Default workload: BASELINE.json configs[4] — the algorithmic-co
 N=1).  `value` = project-rate frames of rendered audio per second summed over ranks, timed on the
 device (CUDA events around each pass's kernel sequence, max over ranks); `e2e` = the same through
 the C ABI with host buffers (floww events re-uploaded, plan tables H2D, PCM D2H into pinned memory)
-on the host clock.
+on the host clock, with the library's default software pipelining of project groups.
+
+`--workload c4` is BASELINE.json configs[3], the single long 64-vertex graph: at N>1 it is sharded by
+TIME over the ranks (strong scaling; segment hand-off through NCCL inside the library).
 """
 from __future__ import annotations
 
@@ -41,6 +44,8 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="duration scale of the workload")
     ap.add_argument("--cpu-sample", type=int, default=12, help="projects in the cpu_baseline sample (c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-group", type=int, default=0,
+                    help="projects per pipelined group for the device-resident `value` passes (0 = one launch sequence)")
     return ap.parse_args()
 
 
@@ -210,6 +215,123 @@ def run_reference(args, rank: int):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def _merge_kstats(dst, src):
+    for name, v in src.items():
+        d = dst.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+        for f in d:
+            d[f] += v[f]
+
+
+class BatchRunner:
+    """Project sharding: this rank's shard of independent projects, scan + render per step."""
+    scaling = "weak"
+
+    def __init__(self, lib, args, rank, local_rank, world, dist):
+        import torch
+        self.lib, self.torch = lib, torch
+        cfgs = build_projects(args, rank)
+        self.states = make_states(lib, cfgs, local_rank)
+        self.ctxs = [st.ctx for st, _, _ in self.states]
+        self.cs = [st.cs for st, _, _ in self.states]
+        self.rsr = [st.render_sr for st, _, _ in self.states]
+        self.bds = [st.bd for st, _, _ in self.states]
+        self.bl = self.states[0][0].bl
+        self.frames_per_step_rank = sum(c * st.bl for c, (st, _, _) in zip(self.cs, self.states))
+        self.total_frames_per_step = self.frames_per_step_rank * world      # every rank renders an equal shard
+        self.ctxs[0].set_profiling(True)
+        self.value_group = args.value_group
+        self.outs = None
+        self.parallelism = f"project-sharded x{world}" if world > 1 else "single GPU"
+
+    def alloc_outs(self):
+        torch = self.torch
+        self.outs = [torch.empty(int(self.lib.render_bound_bytes(c.h, n, r, b)), dtype=torch.uint8, pin_memory=True).numpy()
+                     for c, n, r, b in zip(self.ctxs, self.cs, self.rsr, self.bds)]
+
+    def step(self, e2e: bool):
+        from termdaw_b200 import normalize_render_many, normalize_scan_many, render_many
+        c0 = self.ctxs[0]
+        ev_bytes = rewind(self.states, reupload_flowws=e2e)
+        if e2e:
+            # the public batched call: scan + render of every project, groups of 64 projects pipelined over
+            # two streams (planning / kernels / PCM D2H of different groups overlap)
+            c0.set_pipeline_group(64)
+            normalize_render_many(self.lib, self.ctxs, self.cs, self.rsr, self.bds, want_pcm=True, outs=self.outs)
+            s2, k2 = c0.last_pass_stats(), c0.last_pass_kernel_stats()
+            s1, k1 = {k: 0 for k in s2}, {}
+        else:
+            # value: one launch sequence per pass for the whole shard (clean per-kernel event timing)
+            c0.set_pipeline_group(self.value_group)
+            normalize_scan_many(self.lib, self.ctxs, self.cs)
+            s1, k1 = c0.last_pass_stats(), c0.last_pass_kernel_stats()
+            render_many(self.lib, self.ctxs, self.cs, self.rsr, self.bds, want_pcm=False)
+            s2, k2 = c0.last_pass_stats(), c0.last_pass_kernel_stats()
+        ks = {}
+        _merge_kstats(ks, k1); _merge_kstats(ks, k2)
+        return {"device_ms": s1["device_ms"] + s2["device_ms"], "launches": s1["kernel_launches"] + s2["kernel_launches"],
+                "h2d": ev_bytes + s1["h2d_bytes"] + s2["h2d_bytes"], "d2h": s2["d2h_bytes"], "kstats": ks,
+                "algo": s1["algorithmic_bytes"] + s2["algorithmic_bytes"], "plan_ms": s1["plan_ms"] + s2["plan_ms"],
+                "collectives": 0}
+
+    def close(self):
+        for st, _, _ in self.states:
+            st.close()
+
+
+class TimeShardRunner:
+    """Time sharding: ONE long project, this rank renders its consecutive range of chunks."""
+    scaling = "strong"
+
+    def __init__(self, lib, args, rank, local_rank, world, dist):
+        import torch
+        from termdaw_b200.timeshard import TimeShardedRender
+        self.lib, self.torch, self.rank, self.world = lib, torch, rank, world
+        cfgs = build_projects(args, 0)                       # the same project on every rank
+        self.states = make_states(lib, cfgs, local_rank)
+        st = self.states[0][0]
+        self.ts = TimeShardedRender(st, rank, world, dist)
+        self.bl = st.bl
+        self.cs = [st.cs]
+        self.total_frames_per_step = st.cs * st.bl
+        self.frames_per_step_rank = self.ts.bounds[rank][1] * st.bl
+        st.ctx.set_profiling(True)
+        self.out = None
+        self.parallelism = f"time-sharded x{world} (segment hand-off over NCCL)" if world > 1 else "single GPU"
+
+    def alloc_outs(self):
+        n = self.ts.bounds[self.rank][1] * self.bl * 2 * (self.states[0][0].bd // 8)
+        self.out = self.torch.empty(max(n, 1), dtype=self.torch.uint8, pin_memory=True).numpy()
+
+    def step(self, e2e: bool):
+        import ctypes as C
+        st = self.states[0][0]
+        c = st.ctx
+        ev_bytes = rewind(self.states, reupload_flowws=e2e)
+        col0 = c.collectives()
+        self.ts.scan_exact()
+        s1, k1 = c.last_pass_stats(), c.last_pass_kernel_stats()
+        c0, n = self.ts.bounds[self.rank]
+        if e2e:
+            frames = C.c_uint64(0)
+            rc = self.lib.render_segment(c.h, st.cs, c0, n, 0, st.bd, self.out.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                         self.out.size, C.byref(frames))
+            assert rc >= 0, self.lib.last_error(c.h)
+        else:
+            self.ts.render(want_pcm=False)
+        s2, k2 = c.last_pass_stats(), c.last_pass_kernel_stats()
+        ks = {}
+        _merge_kstats(ks, k1); _merge_kstats(ks, k2)
+        return {"device_ms": s1["device_ms"] + s2["device_ms"], "launches": s1["kernel_launches"] + s2["kernel_launches"],
+                "h2d": ev_bytes + s1["h2d_bytes"] + s2["h2d_bytes"], "d2h": s2["d2h_bytes"], "kstats": ks,
+                "algo": s1["algorithmic_bytes"] + s2["algorithmic_bytes"], "plan_ms": s1["plan_ms"] + s2["plan_ms"],
+                "collectives": c.collectives() - col0}
+
+    def close(self):
+        self.ts.close()
+        for st, _, _ in self.states:
+            st.close()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -219,10 +341,8 @@ def main():
         run_reference(args, rank)
         return
 
-    import numpy as np
     import torch
     import termdaw_b200
-    from termdaw_b200 import normalize_scan_many, render_many
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the renderer has no CPU fallback")
@@ -232,15 +352,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = termdaw_b200.load_library()
-
-    cfgs = build_projects(args, rank)
-    states = make_states(lib, cfgs, local_rank)
-    ctxs = [st.ctx for st, _, _ in states]
-    cs = [st.cs for st, _, _ in states]
-    rsr = [st.render_sr for st, _, _ in states]
-    bds = [st.bd for st, _, _ in states]
-    frames_per_step = sum(c * st.bl for c, (st, _, _) in zip(cs, states))
-    ctxs[0].set_profiling(True)
+    R = (TimeShardRunner if args.workload == "c4" else BatchRunner)(lib, args, rank, local_rank, world, dist)
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,55 +360,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(e2e: bool, outs=None):
-        """returns (device_ms, launches, h2d_bytes, d2h_bytes, kernel stats)"""
-        ev_bytes = rewind(states, reupload_flowws=e2e)
-        normalize_scan_many(lib, ctxs, cs)
-        s1, k1 = ctxs[0].last_pass_stats(), ctxs[0].last_pass_kernel_stats()
-        if e2e:
-            render_many(lib, ctxs, cs, rsr, bds, want_pcm=True, outs=outs)
-        else:
-            render_many(lib, ctxs, cs, rsr, bds, want_pcm=False)
-        s2, k2 = ctxs[0].last_pass_stats(), ctxs[0].last_pass_kernel_stats()
-        ks = {}
-        for k in (k1, k2):
-            for name, v in k.items():
-                d = ks.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
-                for f in d:
-                    d[f] += v[f]
-        return (s1["device_ms"] + s2["device_ms"], s1["kernel_launches"] + s2["kernel_launches"],
-                ev_bytes + s1["h2d_bytes"] + s2["h2d_bytes"], s2["d2h_bytes"], ks,
-                s1["algorithmic_bytes"] + s2["algorithmic_bytes"], s1["plan_ms"] + s2["plan_ms"])
-
     # ---- device-resident timing (value)
     for _ in range(args.warmup):
-        step(False)
+        R.step(False)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     t0 = time.perf_counter()
-    dev_ms, launches, kstats, algo, plan_ms = 0.0, 0, {}, 0, 0.0
+    dev_ms, launches, kstats, algo, plan_ms, collectives = 0.0, 0, {}, 0, 0.0, 0
     for _ in range(args.steps):
-        d, l, _, _, ks, ab, pm = step(False)
-        dev_ms += d; launches += l; algo += ab; plan_ms += pm
-        for name, v in ks.items():
-            dd = kstats.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
-            for f in dd:
-                dd[f] += v[f]
+        r = R.step(False)
+        dev_ms += r["device_ms"]; launches += r["launches"]; algo += r["algo"]; plan_ms += r["plan_ms"]
+        collectives += r["collectives"]
+        _merge_kstats(kstats, r["kstats"])
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
 
     # ---- end to end through the C ABI with host buffers
-    outs = [torch.empty(int(lib.render_bound_bytes(c.h, n, r, b)), dtype=torch.uint8, pin_memory=True).numpy()
-            for c, n, r, b in zip(ctxs, cs, rsr, bds)]
-    step(True, outs)
+    R.alloc_outs()
+    for _ in range(2):
+        R.step(True)
     barrier()
     t1 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(args.steps):
-        _, _, hb, db, _, _, _ = step(True, outs)
-        h2d += hb; d2h += db
+        r = R.step(True)
+        h2d += r["h2d"]; d2h += r["d2h"]
     barrier()
     e2e_wall = time.perf_counter() - t1
 
@@ -305,7 +395,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_max, e2e_max = t.tolist()
-    total_frames = frames_per_step * world          # weak scaling: every rank renders an equal shard
+    total_frames = R.total_frames_per_step
     value = total_frames * args.steps / (dev_ms_max / 1e3)
     e2e_value = total_frames * args.steps / e2e_max
 
@@ -315,34 +405,47 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        # MEASURED_PEAKS.json is driver-written and git-ignored; the figure it held at round start (6532.9 GB/s
+        # copy bandwidth on this pool) is recorded in BASELINE.md / SURVEY.md and used when the file is absent
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else \
-            (6650.0, "fallback (B200_PROFILING.md)")
+            (6532.9, "measured (MEASURED_PEAKS.json value recorded in BASELINE.md; file absent on this box)")
         dom = max(kstats, key=lambda k: kstats[k]["ms"])
         ach = kstats[dom]["bytes"] / (kstats[dom]["ms"] / 1e3) / 1e9 if kstats[dom]["ms"] > 0 else 0.0
+        traffic = None
+        try:                                             # per-launch DRAM bytes of the dominant kernel from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tr.get(dom)
+        except (OSError, ValueError):
+            pass
         line = {
             "metric": "rendered frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": R.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": WORKLOAD_NAMES[args.workload], "projects_per_gpu": len(states),
-                "seconds_per_project": cs[0] * states[0][0].bl / PSR, "flow": "refresh -> normalize scan -> render",
-                "project_sr": PSR, "buffer_length": states[0][0].bl,
+                "workload": WORKLOAD_NAMES[args.workload], "projects_per_gpu": len(R.states), "parallelism": R.parallelism,
+                "seconds_per_project": R.cs[0] * R.bl / PSR, "flow": "refresh -> normalize scan -> render",
+                "project_sr": PSR, "buffer_length": R.bl,
                 "realtime_factor": value / PSR, "l2": "per-step working set >> 126 MB L2 (no flush needed)"
-                if frames_per_step * 8 * 4 > 4e8 else "working set fits L2: numbers are L2-assisted",
+                if R.frames_per_step_rank * 8 * 4 > 4e8 else "working set fits L2: numbers are L2-assisted",
                 "value_timing": "CUDA events around each pass's kernel sequence (plan tables already uploaded)",
                 "host_wall_ms_per_step": wall_max / args.steps * 1e3, "host_plan_ms_per_step": plan_ms / args.steps,
                 "algorithmic_gb_per_step": algo / args.steps / 1e9,
                 "whole_step_algorithmic_gbs": algo / (dev_ms / 1e3) / 1e9,
+                "nccl_exchange_rounds_per_step": collectives // args.steps,
             },
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d // args.steps,
-                    "d2h_bytes_per_step": d2h // args.steps, "realtime_factor": e2e_value / PSR},
+                    "d2h_bytes_per_step": d2h // args.steps, "realtime_factor": e2e_value / PSR,
+                    "ms_per_step": e2e_max / args.steps * 1e3},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                          "share_of_step": kstats[dom]["ms"] / dev_ms,
+                         "note": "k_voice<*> kernels are FP32-issue bound, not HBM bound (DESIGN.md §5): their HBM "
+                                 "fraction is reported as the contract asks; every streaming kernel is listed in per_kernel",
                          "per_kernel": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] // args.steps,
-                                            "achieved_gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 else 0.0}
+                                            "achieved_gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 else 0.0,
+                                            "frac": (v["bytes"] / (v["ms"] / 1e3) / 1e9 / peak) if v["ms"] > 0 else 0.0}
                                         for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -352,8 +455,7 @@ def main():
                                     "sample": sample + f" ({dt:.1f} s of CPU work; restatement of the reference, not the Rust build)",
                                     "host_cores_available": os.cpu_count()}
         print(json.dumps(line))
-    for st, _, _ in states:
-        st.close()
+    R.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -144,6 +144,15 @@ int tdg_render_many(tdg_ctx** ctxs, int n, const uint64_t* chunks, const uint32_
                     const uint32_t* bitdepth, uint8_t** out_pcm, const uint64_t* cap_bytes,
                     uint64_t* frames_written);
 
+/* "normalize" then "render" (ui_workflow.rs:120-135) for n projects in ONE pipelined call: each group of
+ * projects runs its scan pass and its render pass back to back on one stream while the other stream
+ * works on the next group, so host planning, kernels and the PCM device->host copies of different
+ * groups overlap (give pinned `out_pcm` buffers for the copies to be asynchronous).  Results are
+ * identical to tdg_normalize_scan_many followed by tdg_render_many. */
+int tdg_normalize_render_many(tdg_ctx** ctxs, int n, const uint64_t* chunks, const uint32_t* render_sr,
+                              const uint32_t* bitdepth, uint8_t** out_pcm, const uint64_t* cap_bytes,
+                              uint64_t* frames_written);
+
 /* ---- parity taps (pre-quantisation fp32 buffers) -------------------------------------------------
  * The reference keeps one chunk per vertex (graph.rs:242); the device keeps the whole pass.  With
  * taps enabled the buffers of the LAST pass (scan or render) stay readable. */
@@ -215,6 +224,11 @@ typedef struct tdg_kernel_stat {
     uint64_t algorithmic_bytes;
 } tdg_kernel_stat;
 int tdg_set_profiling(tdg_ctx* ctx, int on);
+/* Batched calls (tdg_*_many) over more than `projects_per_group` projects are software-pipelined in
+ * groups of that size over two streams: host planning of group g+1 and the PCM device->host copy of
+ * group g-1 overlap the kernels of group g.  0 = one launch sequence for the whole batch (what the
+ * per-kernel roofline numbers are measured on).  Default 64.  Device-wide setting. */
+int tdg_set_pipeline_group(tdg_ctx* ctx, uint32_t projects_per_group);
 int tdg_last_pass_kernel_stats(tdg_ctx* ctx, tdg_kernel_stat* out, int cap);
 
 #ifdef __cplusplus

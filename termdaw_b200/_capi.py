@@ -112,6 +112,8 @@ class Library:
         "render_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, c_u8p,
                                      C.c_uint64, c_u64p]),
         "set_normalize_state": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int]),
+        "normalize_render_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_u64p, c_u32p, c_u32p,
+                                            C.POINTER(c_u8p), c_u64p, c_u64p]),
         "comm_unique_id": (C.c_int, [c_u8p]),
         "comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_u8p]),
         "comm_destroy": (C.c_int, [C.c_void_p]),
@@ -122,6 +124,7 @@ class Library:
         "normalize_state_device_ptr": (C.c_void_p, [C.c_void_p, c_i32p]),
         "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
         "set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+        "set_pipeline_group": (C.c_int, [C.c_void_p, C.c_uint32]),
         "last_pass_kernel_stats": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_int]),
     }
     # symbols only the oracle has (scalar maths for the reference's known-answer tests)
@@ -343,6 +346,9 @@ class Context:
     def set_profiling(self, on: bool = True):
         self._chk(self.lib.set_profiling(self.h, int(on)))
 
+    def set_pipeline_group(self, n: int):
+        self._chk(self.lib.set_pipeline_group(self.h, int(n)))
+
     def last_pass_kernel_stats(self) -> dict:
         arr = (KernelStat * 32)()
         n = self.lib.last_pass_kernel_stats(self.h, arr, 32)
@@ -355,9 +361,16 @@ class Context:
         return st.as_dict()
 
 
+def normalize_render_many(lib: Library, ctxs, chunks, render_sr, bitdepth, want_pcm: bool = True, outs=None):
+    """tdg_normalize_render_many: scan + render of every project, pipelined over project groups."""
+    return render_many(lib, ctxs, chunks, render_sr, bitdepth, want_pcm, outs, fn="normalize_render_many")
+
+
 def render_many(lib: Library, ctxs: Sequence[Context], chunks: Sequence[int], render_sr: Sequence[int],
-                bitdepth: Sequence[int], want_pcm: bool = True, outs: Optional[Sequence[np.ndarray]] = None):
+                bitdepth: Sequence[int], want_pcm: bool = True, outs: Optional[Sequence[np.ndarray]] = None,
+                fn: str = "render_many"):
     """tdg_render_many: one merged device schedule for `ctxs` (independent projects)."""
+    call = getattr(lib, fn)
     n = len(ctxs)
     hs = (C.c_void_p * n)(*[c.h for c in ctxs])
     ch = (C.c_uint64 * n)(*chunks)
@@ -370,9 +383,9 @@ def render_many(lib: Library, ctxs: Sequence[Context], chunks: Sequence[int], re
             outs = [np.empty(c, np.uint8) for c in caps]
         ptrs = (c_u8p * n)(*[_p(o, c_u8p) for o in outs])
         cp = (C.c_uint64 * n)(*caps)
-        rc = lib.render_many(hs, n, ch, rs, bd, ptrs, cp, fw)
+        rc = call(hs, n, ch, rs, bd, ptrs, cp, fw)
     else:
-        rc = lib.render_many(hs, n, ch, rs, bd, None, None, fw)
+        rc = call(hs, n, ch, rs, bd, None, None, fw)
     if rc < 0:
         msgs = [(lib.last_error(c.h) or b"").decode() for c in ctxs]
         raise TermdawError(rc, next((m for m in msgs if m), ""))

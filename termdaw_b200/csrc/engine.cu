@@ -36,6 +36,7 @@ static inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+static bool trace_on() { static int v = -1; if (v < 0) { const char* e = getenv("TDG_TRACE"); v = (e && *e && *e != '0') ? 1 : 0; } return v == 1; }
 // Rust `f32 as usize`
 static inline uint64_t f32_as_usize(float x) {
     if (!(x == x) || x <= 0.0f) return 0;
@@ -79,17 +80,42 @@ struct PinnedBuf {                 // growable pinned staging buffer for the pla
     template <typename T> T* at(uint64_t off) { return reinterpret_cast<T*>(p + off); }
 };
 
+// A lane = one stream + one work arena; a slot = the per-pass plan blob (pinned + device), events and
+// pinned error flags.  Two lanes x two slots let a batched call keep four passes in flight
+// (run_jobs_pipelined): host planning, H2D, kernels and the PCM D2H of consecutive project groups
+// overlap, and a group's render pass can be planned while its scan pass still runs.  Single passes
+// use lane 0 / slot 0.
+struct Slot {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
+    DevBuf blob_dev;
+    PinnedBuf blob;
+    std::vector<cudaEvent_t> evpool;
+    uint32_t* err_host = nullptr; size_t err_cap = 0;      // pinned: TooWide flags come back without a pageable copy
+    bool ensure_err(size_t n) {
+        if (n <= err_cap) return true;
+        if (err_host) cudaFreeHost(err_host);
+        err_host = nullptr; err_cap = 0;
+        const size_t want = std::max<size_t>(n, 1024);
+        if (cudaHostAlloc(&err_host, want * 4, cudaHostAllocDefault) != cudaSuccess) return false;
+        err_cap = want;
+        return true;
+    }
+};
+struct Lane {
+    cudaStream_t stream = nullptr;
+    DevBuf work;
+    Slot slots[2];
+};
 struct Engine {
     int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf work, blob_dev;
-    PinnedBuf blob;
+    Lane lanes[2];
+    cudaStream_t stream = nullptr;               // == lanes[0].stream (bank uploads, state sync)
     std::map<uint32_t, float*> sinc_tables;     // keyed by the f32 bits of the cutoff
     uint64_t epoch = 0;                          // bumped by every pass (taps of older passes are stale)
     int refs = 0;
     bool profiling = false;                      // CUDA events around every launch (per-class roofline)
-    std::vector<cudaEvent_t> evpool;
+    uint32_t pipeline_group = 64;                // projects per pipelined group (0 = never pipeline)
+    cudaEvent_t ev_batch0 = nullptr, ev_batch1[2] = {nullptr, nullptr};   // span of a pipelined call
 };
 static std::mutex g_mu;
 static std::map<int, Engine*> g_engines;
@@ -111,10 +137,15 @@ static Engine* engine_get(int device, std::string* err) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) { *err = cudaGetErrorString(e); return nullptr; }
     Engine* g = new Engine();
     g->device = device;
-    if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess) {
-        *err = "could not create stream/events"; delete g; return nullptr;
+    for (Lane& ln : g->lanes) {
+        bool ok = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (Slot& sl : ln.slots)
+            ok = ok && cudaEventCreate(&sl.ev0) == cudaSuccess && cudaEventCreate(&sl.ev1) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { *err = "could not create stream/events"; delete g; return nullptr; }
     }
+    g->stream = g->lanes[0].stream;
+    cudaEventCreate(&g->ev_batch0); cudaEventCreate(&g->ev_batch1[0]); cudaEventCreate(&g->ev_batch1[1]);
     g->refs = 1;
     g_engines[device] = g;
     return g;
@@ -221,7 +252,8 @@ static int vstate_to_host(Ctx* c) {
     CU(cudaStreamSynchronize(c->eng->stream));
     return TDG_OK;
 }
-static int vstate_to_dev(Ctx* c) {
+static int vstate_to_dev(Ctx* c, cudaStream_t stream = nullptr) {
+    if (!stream) stream = c->eng->stream;
     const size_t need = c->verts.size() * 8;
     if (c->vstate_host.size() != need) c->vstate_host.resize(need, 0.0f);
     if (c->vstate_cap < need || !c->vstate_dev) {
@@ -233,8 +265,9 @@ static int vstate_to_dev(Ctx* c) {
         c->vstate_host_newer = true;
     }
     if (c->vstate_host_newer && need) {
-        CU(cudaMemcpyAsync(c->vstate_dev, c->vstate_host.data(), need * 4, cudaMemcpyHostToDevice, c->eng->stream));
-        CU(cudaStreamSynchronize(c->eng->stream));   // vstate_host may be touched right after
+        // pageable source: the runtime stages the bytes before returning, so vstate_host may be touched
+        // right after; stream order makes the pass's kernels see them
+        CU(cudaMemcpyAsync(c->vstate_dev, c->vstate_host.data(), need * 4, cudaMemcpyHostToDevice, stream));
     }
     c->vstate_host_newer = false;
     return TDG_OK;
@@ -541,18 +574,45 @@ template <typename T> static void append_list(TaskList<T>& d, TaskList<T>& s) {
 
 struct Bump { uint64_t off = 0; uint64_t alloc(uint64_t bytes) { off = align_up(off, 256); uint64_t r = off; off += bytes; return r; } };
 
-static int run_pass(std::vector<PassReq>& reqs) {
+struct Off { uint64_t fx, fx_adsr, fx_norm, nprefix, nscale, loop, multi, lerp, dsine, synth, sampsyn, bp; };
+struct Timed { int cls; uint64_t bytes; };
+// One pass over a batch of requests, in three phases so that consecutive groups can overlap:
+// plan (host: layout, event tables, task lists), submit (async: H2D, launches, D2H), finish (sync,
+// statistics, end-of-pass transport state).
+struct PassJob {
+    std::vector<PassReq> reqs;
+    Lane* lane = nullptr;
+    int slot = 0;
+    bool submitted = false, waited = false;
+    KStat ks[KC_COUNT];                 // per kernel class, filled by pass_wait
+    int max_level = -1;
+    bool all_vec = true;
+    uint8_t* W = nullptr;
+    std::vector<LevelTasks> levels;
+    std::vector<Off> offs;
+    std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
+    uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, quant_off = 0, resamp_off = 0;
+    uint64_t algo_bytes_total = 0;
+    double t_start = 0, t_planned = 0, t_h2d_issued = 0, t_d2h0 = 0;
+    uint64_t launches = 0, collectives = 0, d2h_bytes = 0, h2d_bytes = 0;
+    std::vector<Timed> timed;
+};
+
+static int pass_plan(PassJob& J) {
+    std::vector<PassReq>& reqs = J.reqs;
+    Lane& ln = *J.lane;
     if (reqs.empty()) return TDG_OK;
     Ctx* c = reqs[0].c;                       // error sink for CU()
     Engine* g = c->eng;
     for (auto& r : reqs) if (r.c->eng != g) return r.c->fail(TDG_ERR_INVALID, "all contexts of a batch must be on one device");
     cudaSetDevice(g->device);
-    const double t_start = now_ms();
+    J.t_start = now_ms();
     g->epoch++;
 
     // ---- 1. graph analysis + work-arena layout -------------------------------------------------
     Bump bump;
-    int max_level = -1;
+    int& max_level = J.max_level;
+    max_level = -1;
     for (auto& r : reqs) {
         Ctx* x = r.c;
         compute_levels(r);
@@ -615,17 +675,20 @@ static int run_pass(std::vector<PassReq>& reqs) {
             r.err_off = bump.alloc(16);
         }
     }
-    CU(g->work.ensure(bump.off + 256));
-    uint8_t* W = g->work.p;
+    const double tr_layout = now_ms();
+    CU(ln.work.ensure(bump.off + 256));
+    uint8_t* W = J.W = ln.work.p;
+    const double tr_arena = now_ms();
 
     // ---- 2. plan: tasks + tables into the pinned blob ------------------------------------------
     // Each project is planned independently (host threads) into its own fragment: a private blob and
     // private task lists whose *_off fields are relative to that blob; fragments are then copied into
     // the pinned blob and the offsets rebased.
-    bool all_vec = true;
+    bool& all_vec = J.all_vec;
+    all_vec = true;
     for (auto& r : reqs) {
         Ctx* x = r.c;
-        if (int e = vstate_to_dev(x)) return e;
+        if (int e = vstate_to_dev(x, ln.stream)) return e;
         x->stats = PassStats();
         if (x->bl % 4 != 0) all_vec = false;
         r.sincs = nullptr;
@@ -634,6 +697,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
             if (!r.sincs) return x->fail(TDG_ERR_CUDA, "could not build the sinc table");
         }
     }
+    const double tr_vstate = now_ms();
     std::vector<Frag> frags(reqs.size());
     auto plan_one = [&](PassReq& r, Frag& F) -> int {
         Ctx* x = r.c;
@@ -647,6 +711,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
         PassParams pp{r.is_scan ? 0 : x->fb_frame, r.is_scan ? 0 : x->t, r.total, r.emit0, r.emit_n, x->bl, x->sr};
         // (true_normalize_scan: fb.set_time(0) and t = j*bl, graph.rs:228-231)
         uint64_t algo = 0;
+        const float* fused_runmax = nullptr; PanGain fused_pg{1.0f, 1.0f, 1.0f, 0};
         for (int v = 0; v < V; ++v) {
             if (r.level[v] < 0) continue;
             HVertex& hv = x->verts[v];
@@ -681,6 +746,11 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     float* peaks = reinterpret_cast<float*>(W + r.aux_off[v]);
                     float* runmax = peaks + r.emit_n;
                     t.peaks = peaks;
+                    // Output Normalize without taps: the scan pass needs only its peaks (no buffer is consumed),
+                    // the render pass scales inside the quantiser; with a render-time resampler the scaled
+                    // buffer is still needed
+                    const bool fuse_out = v == x->output && !x->taps && !r.resample;
+                    if (fuse_out && r.is_scan) t.no_store = 1;
                     LT.fx_norm.v.push_back(t); LT.fx_norm.max_chunks = std::max(LT.fx_norm.max_chunks, nch);
                     NormPrefixTask np{peaks, runmax, x->vstate_dev + (size_t)v * 8, nch, r.is_scan ? 1u : 0u, Xchg{nullptr, 0, 0, 1, 0}, nullptr};
                     if (r.x_ranks > 1) {
@@ -689,10 +759,15 @@ static int run_pass(std::vector<PassReq>& reqs) {
                         if (r.x_mode == 2 && r.is_scan) np.reduced = reinterpret_cast<const float*>(W + r.x_red_off[L]);
                     }
                     LT.nprefix.v.push_back(np);
-                    NormScaleTask ns; ns.h = h; ns.runmax = runmax;
-                    LT.nscale.v.push_back(ns); LT.nscale.max_chunks = std::max(LT.nscale.max_chunks, nch);
+                    if (!fuse_out) {
+                        NormScaleTask ns; ns.h = h; ns.runmax = runmax;
+                        LT.nscale.v.push_back(ns); LT.nscale.max_chunks = std::max(LT.nscale.max_chunks, nch);
+                        LT.nscale.bytes += 16ull * r.n_frames;
+                    } else { fused_runmax = runmax; fused_pg = h.pg; }
+                    // algorithmic bytes stay those of the reference's vertex model (inputs once, output once,
+                    // scale in place), so a fused pass reads as > 100 % of the per-vertex roofline
                     algo += io_bytes + 16ull * r.n_frames;
-                    LT.fx_norm.bytes += io_bytes; LT.nscale.bytes += 16ull * r.n_frames; LT.nprefix.bytes += 8ull * r.emit_n;
+                    LT.fx_norm.bytes += io_bytes - (t.no_store ? 8ull * r.n_frames : 0); LT.nprefix.bytes += 8ull * r.emit_n;
                     break;
                 }
                 case K_ADSR: {
@@ -789,13 +864,13 @@ static int run_pass(std::vector<PassReq>& reqs) {
                     if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; if (exotic) LT.dsine_exact = true; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nch); LT.dsine.bytes += vbytes; }
                     else if (hv.kind == K_SYNTH) {
                         t.kind = VOICE_SYNTH;
-                        t.sq_vol = hv.sq.volume; t.sq_z = hv.sq.param; t.tf_vol = hv.tf.volume; t.tf_z = hv.tf.param;
-                        t.tr_vol = hv.tr.volume;
+                        t.vol[0] = hv.sq.volume; t.sq_z = hv.sq.param; t.vol[1] = hv.tf.volume; t.tf_z = hv.tf.param;
+                        t.vol[2] = hv.tr.volume;
                         t.sq_iz = 1.0f / t.sq_z;                                             // synth.rs:23
                         t.tf_add = (1.0f - t.tf_z) / 2.0f; t.tf_mul = 2.0f / (1.0f + t.tf_z);  // synth.rs:28
                         t.env[0] = make_adsr_k(hv.sq.adsr); t.env[1] = make_adsr_k(hv.tf.adsr); t.env[2] = make_adsr_k(hv.tr.adsr);
-                        if (exotic || (t.sq_vol > 0.0f && t.env[0].exotic) || (t.tf_vol > 0.0f && t.env[1].exotic) ||
-                            (t.tr_vol > 0.0f && t.env[2].exotic)) LT.synth_exact = true;
+                        if (exotic || (t.vol[0] > 0.0f && t.env[0].exotic) || (t.vol[1] > 0.0f && t.env[1].exotic) ||
+                            (t.vol[2] > 0.0f && t.env[2].exotic)) LT.synth_exact = true;
                         t.amp_mul = 1.0f / (hv.sq.volume * m_max_vel(hv.sq.adsr) + hv.tf.volume * m_max_vel(hv.tf.adsr) +
                                             hv.tr.volume * m_max_vel(hv.tr.adsr));           // extensions.rs:465-468
                         LT.synth.v.push_back(t); LT.synth.max_chunks = std::max(LT.synth.max_chunks, nch); LT.synth.bytes += vbytes;
@@ -835,13 +910,14 @@ static int run_pass(std::vector<PassReq>& reqs) {
             } else {
                 const uint64_t skip = (r.keep0 - r.emit0) * x->bl;
                 q.in_l = ol + skip; q.in_r = orr + skip; q.n = r.out_frames;
+                q.runmax = fused_runmax; q.frame0 = skip; q.bl = x->bl; q.pg = fused_pg;
             }
             quants.push_back(q); quant_max = std::max(quant_max, q.n);
             algo += 8ull * q.n + r.pcm_bytes; quant_bytes += 8ull * q.n + r.pcm_bytes;
         }
         x->stats.algorithmic_bytes = algo; x->stats.frames = r.n_frames;
         F.algo = algo;
-        x->last_buf_off = r.buf_off; x->last_n_frames = r.n_frames; x->last_n_pad = r.n_pad; x->last_epoch = g->epoch;
+        x->last_buf_off = r.buf_off; x->last_n_frames = r.n_frames; x->last_n_pad = r.n_pad; x->last_epoch = g->epoch; x->last_lane = (int)(J.lane - g->lanes);
         return TDG_OK;
     };
     {
@@ -865,13 +941,17 @@ static int run_pass(std::vector<PassReq>& reqs) {
         }
         if (first_err.load() != TDG_OK) return first_err.load();
     }
+    const double tr_planned = now_ms();
     // merge: reserve the pinned blob, rebase offsets, concatenate the task lists (project order)
-    PinnedBuf& B = g->blob;
+    Slot& sl = ln.slots[J.slot];
+    PinnedBuf& B = sl.blob;
     B.size = 0;
-    std::vector<LevelTasks> levels(max_level + 1);
-    std::vector<QuantTask> quants; uint64_t quant_max = 0, quant_bytes = 0;
-    std::vector<ResampleTask> resamps; uint64_t resamp_max = 0, resamp_bytes = 0;
-    uint64_t algo_bytes_total = 0;
+    std::vector<LevelTasks>& levels = J.levels;
+    levels.assign(max_level + 1, LevelTasks());
+    std::vector<QuantTask>& quants = J.quants; uint64_t &quant_max = J.quant_max, &quant_bytes = J.quant_bytes;
+    std::vector<ResampleTask>& resamps = J.resamps; uint64_t &resamp_max = J.resamp_max, &resamp_bytes = J.resamp_bytes;
+    uint64_t& algo_bytes_total = J.algo_bytes_total;
+    quants.clear(); resamps.clear(); quant_max = quant_bytes = resamp_max = resamp_bytes = algo_bytes_total = 0;
     {
         uint64_t tot = 0;
         for (Frag& F : frags) { F.base = align_up(tot, 256); tot = F.base + F.blob.v.size(); }
@@ -924,8 +1004,8 @@ static int run_pass(std::vector<PassReq>& reqs) {
         }
     }
     // task arrays go into the blob too: one H2D for the whole pass
-    struct Off { uint64_t fx, fx_adsr, fx_norm, nprefix, nscale, loop, multi, lerp, dsine, synth, sampsyn, bp; };
-    std::vector<Off> offs(levels.size());
+    std::vector<Off>& offs = J.offs;
+    offs.assign(levels.size(), Off());
     auto put = [&](const void* src, size_t bytes) -> uint64_t {
         uint64_t o = B.alloc(std::max<size_t>(bytes, 16));
         if (o != UINT64_MAX && bytes) memcpy(B.p + o, src, bytes);
@@ -946,29 +1026,55 @@ static int run_pass(std::vector<PassReq>& reqs) {
         offs[L].sampsyn = put(T.sampsyn.v.data(), T.sampsyn.v.size() * sizeof(VoiceTask));
         offs[L].bp = put(T.bp.v.data(), T.bp.v.size() * sizeof(BpTask));
     }
-    const uint64_t quant_off = put(quants.data(), quants.size() * sizeof(QuantTask));
-    const uint64_t resamp_off = put(resamps.data(), resamps.size() * sizeof(ResampleTask));
-    if (quant_off == UINT64_MAX || resamp_off == UINT64_MAX) return c->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
-    const double t_planned = now_ms();
+    J.quant_off = put(quants.data(), quants.size() * sizeof(QuantTask));
+    J.resamp_off = put(resamps.data(), resamps.size() * sizeof(ResampleTask));
+    if (J.quant_off == UINT64_MAX || J.resamp_off == UINT64_MAX) return c->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
+    const double tr_merged = now_ms();
+    CU(sl.blob_dev.ensure(B.size + 256));
+    if (!sl.ensure_err(reqs.size())) return c->fail(TDG_ERR_CUDA, "pinned flag buffer allocation failed");
+    J.t_planned = now_ms();
+    if (trace_on())
+        fprintf(stderr, "[tdg] plan lane %d reqs %zu: layout %.2f arena %.2f vstate %.2f plan %.2f merge %.2f blobdev %.2f ms (blob %.1f MB)\n",
+                (int)(J.lane - g->lanes), reqs.size(), tr_layout - J.t_start, tr_arena - tr_layout, tr_vstate - tr_arena,
+                tr_planned - tr_vstate, tr_merged - tr_planned, J.t_planned - tr_merged, B.size / 1e6);
+    return TDG_OK;
+}
 
+static int pass_submit(PassJob& J) {
+    std::vector<PassReq>& reqs = J.reqs;
+    if (reqs.empty()) return TDG_OK;
+    Lane& ln = *J.lane;
+    Ctx* c = reqs[0].c;
+    Engine* g = c->eng;
+    cudaSetDevice(g->device);
+    Slot& sl = ln.slots[J.slot];
+    PinnedBuf& B = sl.blob;
+    uint8_t* W = J.W;
+    std::vector<LevelTasks>& levels = J.levels;
+    std::vector<Off>& offs = J.offs;
+    std::vector<QuantTask>& quants = J.quants; std::vector<ResampleTask>& resamps = J.resamps;
+    const uint64_t quant_max = J.quant_max, quant_bytes = J.quant_bytes, resamp_max = J.resamp_max, resamp_bytes = J.resamp_bytes;
+    const uint64_t quant_off = J.quant_off, resamp_off = J.resamp_off;
+    const bool all_vec = J.all_vec;
     // ---- 3. upload + launches ------------------------------------------------------------------
-    CU(g->blob_dev.ensure(B.size + 256));
-    const uint8_t* D = g->blob_dev.p;
-    cudaStream_t s = g->stream;
-    CU(cudaMemcpyAsync(g->blob_dev.p, B.p, B.size, cudaMemcpyHostToDevice, s));
+    const uint8_t* D = sl.blob_dev.p;
+    cudaStream_t s = ln.stream;
+    CU(cudaMemcpyAsync(sl.blob_dev.p, B.p, B.size, cudaMemcpyHostToDevice, s));
+    J.h2d_bytes = B.size;
     for (auto& r : reqs) if (!r.is_scan && r.c->output >= 0) CU(cudaMemsetAsync(W + r.err_off, 0, 4, s));
-    const double t_h2d_issued = now_ms();
-    CU(cudaEventRecord(g->ev0, s));
-    uint64_t launches = 0, collectives = 0;
+    J.t_h2d_issued = now_ms();
+    CU(cudaEventRecord(sl.ev0, s));
+    uint64_t &launches = J.launches, &collectives = J.collectives;
+    launches = collectives = 0;
     const int x_mode = reqs[0].x_mode;
     for (auto& r : reqs) if (r.x_mode != x_mode || (x_mode == 2 && reqs.size() != 1))
         return r.c->fail(TDG_ERR_INVALID, "time-sharded and plain passes cannot share a launch sequence");
     const uint32_t kMaxY = 65535;          // gridDim.y limit: tasks per launch
-    struct Timed { int cls; uint64_t bytes; };
-    std::vector<Timed> timed;
+    std::vector<Timed>& timed = J.timed;
+    timed.clear();
     auto ev_at = [&](size_t i) -> cudaEvent_t {
-        while (g->evpool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); g->evpool.push_back(e); }
-        return g->evpool[i];
+        while (sl.evpool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); sl.evpool.push_back(e); }
+        return sl.evpool[i];
     };
 #define LAUNCH_SPLIT(cls, list, T, off, bytes_, expr) \
     for (size_t b0 = 0; b0 < (list).v.size(); b0 += kMaxY) { \
@@ -1015,34 +1121,35 @@ static int run_pass(std::vector<PassReq>& reqs) {
       LAUNCH_SPLIT(KC_RESAMPLE, rl, ResampleTask, resamp_off, resamp_bytes, launch_resample(tp, nb, resamp_max, D, s)); }
     { TaskList<QuantTask> ql; ql.v.swap(quants);
       LAUNCH_SPLIT(KC_QUANT, ql, QuantTask, quant_off, quant_bytes, launch_quantise(tp, nb, quant_max, s)); }
-    CU(cudaEventRecord(g->ev1, s));
+    CU(cudaEventRecord(sl.ev1, s));
 
     // ---- 4. results back -------------------------------------------------------------------------
-    const double t_d2h0 = now_ms();
-    uint64_t d2h_bytes = 0;
-    for (auto& r : reqs) {
+    J.t_d2h0 = now_ms();
+    uint64_t& d2h_bytes = J.d2h_bytes;
+    d2h_bytes = 0;
+    for (size_t i = 0; i < reqs.size(); ++i) {
+        PassReq& r = reqs[i];
+        sl.err_host[i] = 0;
         if (r.is_scan || r.c->output < 0) continue;
         if (r.out) {
             if (r.cap < r.pcm_bytes) return r.c->fail(TDG_ERR_CAPACITY, "output buffer too small");
+            // asynchronous when the caller's buffer is pinned (cudaHostAlloc / cudaHostRegister)
             CU(cudaMemcpyAsync(r.out, W + r.pcm_off, r.pcm_bytes, cudaMemcpyDeviceToHost, s));
             d2h_bytes += r.pcm_bytes;
         }
-        CU(cudaMemcpyAsync(&r.err_flag, W + r.err_off, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(sl.err_host + i, W + r.err_off, 4, cudaMemcpyDeviceToHost, s));
     }
-    CU(cudaStreamSynchronize(s));
-    const double t_end = now_ms();
-    float dev_ms = 0.0f;
-    cudaEventElapsedTime(&dev_ms, g->ev0, g->ev1);
-    KStat ks[KC_COUNT];
-    for (size_t i = 0; i < timed.size(); ++i) {
-        float ms = 0.0f;
-        cudaEventElapsedTime(&ms, g->evpool[2 * i], g->evpool[2 * i + 1]);
-        ks[timed[i].cls].launches++; ks[timed[i].cls].ms += ms; ks[timed[i].cls].bytes += timed[i].bytes;
-    }
+    CU(cudaEventRecord(sl.ev_done, s));
+    J.submitted = true;
+    if (trace_on()) fprintf(stderr, "[tdg] submit lane %d: enqueue %.2f ms, %llu launches\n", (int)(J.lane - g->lanes), now_ms() - J.t_planned, (unsigned long long)launches);
+    return TDG_OK;
+}
 
-    // ---- 5. end-of-pass transport state (graph.rs:235-236 / state.rs:575) -------------------------
-    int rc = TDG_OK;
-    for (auto& r : reqs) {
+// end-of-pass transport state (graph.rs:235-236 / state.rs:575): host bookkeeping that does not depend
+// on device results, applied right after submission so that the next pass of the same contexts can
+// be planned while this one still runs
+static void pass_end_state(PassJob& J) {
+    for (auto& r : J.reqs) {
         Ctx* x = r.c;
         x->vstate_host_newer = false;
         if (r.is_scan) {
@@ -1057,6 +1164,42 @@ static int run_pass(std::vector<PassReq>& reqs) {
                 else if (hv.kind == K_BANDPASS) hv.bp_first = true;
             }
         }
+    }
+}
+
+// wait for the pass's device work (its own completion event: later passes may already be queued on
+// the same stream), then statistics and error flags
+static int pass_wait(PassJob& J) {
+    std::vector<PassReq>& reqs = J.reqs;
+    if (reqs.empty() || !J.submitted || J.waited) return TDG_OK;
+    J.waited = true;
+    Lane& ln = *J.lane;
+    Slot& sl = ln.slots[J.slot];
+    Ctx* c = reqs[0].c;
+    Engine* g = c->eng;
+    cudaSetDevice(g->device);
+    PinnedBuf& B = sl.blob;
+    std::vector<Timed>& timed = J.timed;
+    const uint64_t launches = J.launches, collectives = J.collectives, d2h_bytes = J.d2h_bytes, algo_bytes_total = J.algo_bytes_total;
+    const double t_start = J.t_start, t_planned = J.t_planned, t_h2d_issued = J.t_h2d_issued, t_d2h0 = J.t_d2h0;
+    const double t_sync0 = now_ms();
+    CU(cudaEventSynchronize(sl.ev_done));
+    const double t_end = now_ms();
+    float dev_ms = 0.0f;
+    cudaEventElapsedTime(&dev_ms, sl.ev0, sl.ev1);
+    if (trace_on()) fprintf(stderr, "[tdg] wait lane %d slot %d: waited %.2f ms, device %.2f ms\n", (int)(J.lane - g->lanes), J.slot, t_end - t_sync0, dev_ms);
+    KStat* ks = J.ks;
+    for (int k = 0; k < KC_COUNT; ++k) ks[k] = KStat();
+    for (size_t i = 0; i < timed.size(); ++i) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, sl.evpool[2 * i], sl.evpool[2 * i + 1]);
+        ks[timed[i].cls].launches++; ks[timed[i].cls].ms += ms; ks[timed[i].cls].bytes += timed[i].bytes;
+    }
+    int rc = TDG_OK;
+    for (size_t i = 0; i < reqs.size(); ++i) {
+        PassReq& r = reqs[i];
+        Ctx* x = r.c;
+        r.err_flag = sl.err_host[i];
         if (r.frames_written) *r.frames_written = (r.is_scan || x->output < 0) ? 0 : r.out_frames;
         x->stats.device_ms = dev_ms;
         x->stats.plan_ms = t_planned - t_start;
@@ -1069,6 +1212,118 @@ static int run_pass(std::vector<PassReq>& reqs) {
         if (reqs.size() > 1) x->stats.algorithmic_bytes = algo_bytes_total;
         if (r.err_flag) rc = x->fail(TDG_ERR_TOO_WIDE, "sample too wide for bit depth (hound TooWide; the reference panics)");
     }
+    return rc;
+}
+
+static int run_pass(std::vector<PassReq>& reqs) {
+    if (reqs.empty()) return TDG_OK;
+    PassJob J;
+    J.reqs.swap(reqs);
+    J.lane = &J.reqs[0].c->eng->lanes[0];
+    J.slot = 0;
+    int e = pass_plan(J);
+    if (e == TDG_OK) e = pass_submit(J);
+    if (e == TDG_OK) { pass_end_state(J); e = pass_wait(J); }
+    else cudaStreamSynchronize(J.lane->stream);
+    reqs.swap(J.reqs);
+    return e;
+}
+
+// Batches of independent projects, software-pipelined.  `jobs` are passes in host order; job j runs on
+// lane/slot (jobs[j].lane, jobs[j].slot).  Before a job is planned, the previous job that used the
+// same slot must have completed (its pinned and device blobs are reused); everything else overlaps:
+// the host plans job j+1 while the SMs run job j and the copy engine drains job j-1's PCM.
+// Results are identical to unpipelined passes (projects are independent; passes of one project stay
+// in order on one stream).
+static int run_jobs_pipelined(Engine* g, std::vector<PassJob>& jobs, PassStats* tot_out, KStat* ks_out) {
+    int rc = TDG_OK;
+    PassJob* last_in_slot[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool first = true, used[2] = {false, false};
+    for (size_t k = 0; k < jobs.size() && rc == TDG_OK; ++k) {
+        PassJob& J = jobs[k];
+        const int li = (int)(J.lane - g->lanes);
+        if (PassJob* prev = last_in_slot[li][J.slot]) { rc = pass_wait(*prev); if (rc != TDG_OK) break; }
+        rc = pass_plan(J);
+        if (rc != TDG_OK) break;
+        if (first) { cudaEventRecord(g->ev_batch0, J.lane->stream); first = false; }
+        rc = pass_submit(J);
+        if (rc != TDG_OK) break;
+        pass_end_state(J);
+        cudaEventRecord(g->ev_batch1[li], J.lane->stream);          // after this job's kernels and copies
+        used[li] = true;
+        last_in_slot[li][J.slot] = &J;
+    }
+    for (PassJob& J : jobs) { const int e = pass_wait(J); if (rc == TDG_OK) rc = e; }
+    if (rc != TDG_OK) { for (Lane& ln : g->lanes) cudaStreamSynchronize(ln.stream); return rc; }
+    // whole-call figures: device time from the first job's start to the last job's end (both lanes)
+    float span = 0.0f;
+    for (int li = 0; li < 2; ++li) if (used[li]) { float v = 0.0f; cudaEventElapsedTime(&v, g->ev_batch0, g->ev_batch1[li]); span = std::max(span, v); }
+    PassStats tot;
+    for (PassJob& J : jobs) {
+        const Ctx* x = J.reqs[0].c;          // every context of a job carries the job's figures
+        // a context may appear in two jobs (scan, render): its stats hold the later one; per-job numbers were
+        // accumulated below from the job records instead
+        (void)x;
+        tot.plan_ms += J.t_planned - J.t_start; tot.h2d_ms += J.t_h2d_issued - J.t_planned;
+        tot.h2d_bytes += J.h2d_bytes; tot.d2h_bytes += J.d2h_bytes; tot.kernel_launches += J.launches;
+        tot.algorithmic_bytes += J.algo_bytes_total;
+        for (PassReq& r : J.reqs) { tot.frames += r.n_frames; }
+        for (int q = 0; q < KC_COUNT; ++q) { ks_out[q].launches += J.ks[q].launches; ks_out[q].ms += J.ks[q].ms; ks_out[q].bytes += J.ks[q].bytes; }
+    }
+    tot.device_ms = span;
+    *tot_out = tot;
+    return TDG_OK;
+}
+static void publish_batch_stats(std::vector<PassJob>& jobs, const PassStats& tot, const KStat* ks) {
+    for (PassJob& J : jobs) for (PassReq& r : J.reqs) {
+        const uint64_t fr = r.c->stats.frames, vf = r.c->stats.voice_frames;
+        r.c->stats = tot; r.c->stats.frames = fr; r.c->stats.voice_frames = vf;
+        r.c->batch_frames = tot.frames;
+        for (int q = 0; q < KC_COUNT; ++q) r.c->kstats[q] = ks[q];
+    }
+}
+
+static int run_pass_pipelined(std::vector<PassReq>& reqs) {
+    if (reqs.empty()) return TDG_OK;
+    Engine* g = reqs[0].c->eng;
+    const size_t group = g->pipeline_group;
+    if (group == 0 || reqs.size() <= group || reqs[0].x_mode != 0) return run_pass(reqs);
+    for (auto& r : reqs) if (r.c->eng != g) return r.c->fail(TDG_ERR_INVALID, "all contexts of a batch must be on one device");
+    cudaSetDevice(g->device);
+    const size_t n_groups = (reqs.size() + group - 1) / group;
+    std::vector<PassJob> jobs(n_groups);
+    for (size_t i = 0; i < reqs.size(); ++i) jobs[i / group].reqs.push_back(std::move(reqs[i]));
+    for (size_t k = 0; k < n_groups; ++k) { jobs[k].lane = &g->lanes[k & 1]; jobs[k].slot = (int)((k >> 1) & 1); }
+    PassStats tot; KStat ks[KC_COUNT];
+    const int rc = run_jobs_pipelined(g, jobs, &tot, ks);
+    if (rc == TDG_OK) publish_batch_stats(jobs, tot, ks);
+    size_t i = 0;
+    for (PassJob& J : jobs) for (PassReq& r : J.reqs) reqs[i++] = std::move(r);
+    return rc;
+}
+
+// scan + render of every project in one pipelined call (the manual workflow's "normalize" then
+// "render", ui_workflow.rs:120-135): group g's two passes run back to back on one lane while the other
+// lane works on group g+1, so the PCM of group g-1 crosses PCIe under the kernels of both passes.
+static int run_scan_render_pipelined(std::vector<PassReq>& scans, std::vector<PassReq>& renders) {
+    Engine* g = renders[0].c->eng;
+    for (auto& r : renders) if (r.c->eng != g) return r.c->fail(TDG_ERR_INVALID, "all contexts of a batch must be on one device");
+    cudaSetDevice(g->device);
+    const size_t group = g->pipeline_group ? g->pipeline_group : renders.size();
+    const size_t n_groups = (renders.size() + group - 1) / group;
+    std::vector<PassJob> jobs(n_groups * 2);
+    for (size_t i = 0; i < renders.size(); ++i) {
+        const size_t gi = i / group;
+        if (scans[i].c->output >= 0) jobs[2 * gi].reqs.push_back(std::move(scans[i]));     // graph.rs:225: no output, no scan
+        jobs[2 * gi + 1].reqs.push_back(std::move(renders[i]));
+    }
+    for (size_t k = 0; k < jobs.size(); ++k) { jobs[k].lane = &g->lanes[(k >> 1) & 1]; jobs[k].slot = (int)(k & 1); }
+    std::vector<PassJob> live;
+    live.reserve(jobs.size());
+    for (PassJob& J : jobs) if (!J.reqs.empty()) live.push_back(std::move(J));
+    PassStats tot; KStat ks[KC_COUNT];
+    const int rc = run_jobs_pipelined(g, live, &tot, ks);
+    if (rc == TDG_OK) publish_batch_stats(live, tot, ks);
     return rc;
 }
 
@@ -1414,6 +1669,7 @@ void* tdg_normalize_state_device_ptr(tdg_ctx* h, int* n_floats) {
     Ctx* c = C_;
     cudaSetDevice(c->eng->device);
     if (vstate_to_dev(c) != TDG_OK) return nullptr;
+    cudaStreamSynchronize(c->eng->stream);
     if (n_floats) *n_floats = (int)c->verts.size() * 8;
     // the caller may modify the device copy (NCCL all-reduce): it is the authoritative one from now on
     return c->vstate_dev;
@@ -1446,7 +1702,7 @@ int tdg_read_vertex_buffer(tdg_ctx* h, int vertex, uint64_t frame0, uint64_t n, 
     if (!c->taps || c->last_epoch != c->eng->epoch) return c->fail(TDG_ERR_INVALID, "taps are only valid right after a pass with taps enabled");
     if (frame0 + n > c->last_n_frames) return c->fail(TDG_ERR_CAPACITY, "tap shorter than request");
     cudaSetDevice(c->eng->device);
-    const float* bl_ = reinterpret_cast<const float*>(c->eng->work.p + c->last_buf_off[vertex]);
+    const float* bl_ = reinterpret_cast<const float*>(c->eng->lanes[c->last_lane].work.p + c->last_buf_off[vertex]);
     CU(cudaMemcpy(l, bl_ + frame0, n * 4, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(r, bl_ + c->last_n_pad + frame0, n * 4, cudaMemcpyDeviceToHost));
     return TDG_OK;
@@ -1466,7 +1722,7 @@ int tdg_normalize_scan_many(tdg_ctx** hs, int n, const uint64_t* chunks) {
         PassReq r; r.c = &hs[i]->c; r.is_scan = true; r.total = chunks[i]; r.emit0 = 0; r.emit_n = chunks[i]; r.keep0 = 0;
         reqs.push_back(std::move(r));
     }
-    return run_pass(reqs);
+    return run_pass_pipelined(reqs);
 }
 int tdg_normalize_scan(tdg_ctx* h, uint64_t chunks) { return tdg_normalize_scan_many(&h, 1, &chunks); }
 
@@ -1483,7 +1739,25 @@ int tdg_render_many(tdg_ctx** hs, int n, const uint64_t* chunks, const uint32_t*
         r.frames_written = frames_written ? frames_written + i : nullptr;
         reqs.push_back(std::move(r));
     }
-    return run_pass(reqs);
+    return run_pass_pipelined(reqs);
+}
+int tdg_normalize_render_many(tdg_ctx** hs, int n, const uint64_t* chunks, const uint32_t* render_sr, const uint32_t* bitdepth,
+                              uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written) {
+    if (n <= 0) return TDG_OK;
+    std::vector<PassReq> scans(n), renders(n);
+    for (int i = 0; i < n; ++i) {
+        Ctx* c = &hs[i]->c;
+        if (int e = valid_bd(c, bitdepth[i])) return e;
+        if (frames_written) frames_written[i] = 0;
+        PassReq& a = scans[i];
+        a.c = c; a.is_scan = true; a.total = chunks[i]; a.emit0 = 0; a.emit_n = chunks[i]; a.keep0 = 0;
+        PassReq& r = renders[i];
+        r.c = c; r.is_scan = false; r.total = chunks[i]; r.emit0 = 0; r.emit_n = chunks[i]; r.keep0 = 0;
+        r.render_sr = render_sr[i]; r.bd = bitdepth[i];
+        r.out = out_pcm ? out_pcm[i] : nullptr; r.cap = cap_bytes ? cap_bytes[i] : 0;
+        r.frames_written = frames_written ? frames_written + i : nullptr;
+    }
+    return run_scan_render_pipelined(scans, renders);
 }
 int tdg_render(tdg_ctx* h, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes,
                uint64_t* frames_written) {
@@ -1589,6 +1863,7 @@ int tdg_comm_destroy(tdg_ctx* h) {
 uint64_t tdg_collectives(tdg_ctx* h) { return h ? h->c.collectives : 0; }
 
 int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; return TDG_OK; }
+int tdg_set_pipeline_group(tdg_ctx* h, uint32_t projects_per_group) { h->c.eng->pipeline_group = projects_per_group; return TDG_OK; }
 int tdg_last_pass_kernel_stats(tdg_ctx* h, tdg_kernel_stat* out, int cap) {
     static const char* names[KC_COUNT] = {"k_sample_loop", "k_sample_multi", "k_sample_lerp", "k_voice<debug_sine>", "k_voice<synth>",
         "k_voice<sampsyn>", "k_fx<sum>", "k_fx<adsr>", "k_fx<norm_peak>", "k_norm_prefix", "k_norm_scale", "k_bp_aggregate", "k_bp_carry", "k_bp_apply", "k_resample", "k_quantise"};

@@ -81,6 +81,8 @@ struct Ctx {
     std::vector<int64_t> last_buf_off;       // per vertex, -1 if not evaluated
     uint64_t last_n_frames = 0, last_n_pad = 0;
     uint64_t last_epoch = 0;
+    int last_lane = 0;
+    uint64_t batch_frames = 0, batch_voice_frames = 0;   // whole-call totals of the last batched pass
     PassStats stats;
     KStat kstats[KC_COUNT];                  // per kernel class, last pass (profiling on)
     uint64_t launches = 0, collectives = 0;

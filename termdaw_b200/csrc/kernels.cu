@@ -9,6 +9,7 @@
 // Compiled with -fmad=false: the reference rounds after every f32 operation.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "tdg_types.h"
 #include "tdg_math.cuh"
 #include "kernels.h"
@@ -151,9 +152,24 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(con
             if (one) {
                 const AdsrSeg sg = segs[s];
                 if (!(sg.flags & 1u)) {
+                    float tp[4], tg[4], ep[4], eg[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float vel = adsr_frame_vel<EXACT>(T, sg, k_div<EXACT>((float)(i + j), T.fsr, T.rsr), maxmul, minmul);
+                        const float offset = k_div<EXACT>((float)(i + j), T.fsr, T.rsr);
+                        tp[j] = sg.pt + offset; tg[j] = sg.gt + offset;
+                    }
+                    if (T.use_off) {                     // extensions.rs:620-623
+                        if (sg.pr == 0.0f) k_apply_ads_n<EXACT, 4>(T.conf, tp, ep); else k_apply_r_n<EXACT, 4>(T.conf, tp, sg.pr, ep);
+                        if (sg.gr == 0.0f) k_apply_ads_n<EXACT, 4>(T.conf, tg, eg); else k_apply_r_n<EXACT, 4>(T.conf, tg, sg.gr, eg);
+                    } else {                             // extensions.rs:640-641
+                        k_apply_adsr_n<EXACT, 4>(T.conf, tp, ep);
+                        k_apply_adsr_n<EXACT, 4>(T.conf, tg, eg);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float pvel = ep[j] * sg.pv, gvel = eg[j] * sg.gv;
+                        const float adsr_vel = fmaxf(pvel, gvel) * maxmul + fminf(pvel, gvel) * minmul;
+                        const float vel = 1.0f + T.wet * (adsr_vel - 1.0f);      // lerp(1.0, adsr_vel, wet)
                         l[j] *= vel; r[j] *= vel;
                     }
                 }
@@ -176,8 +192,10 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(con
 #pragma unroll
             for (int j = 0; j < 4; ++j) apply_pg(l[j], r[j], T.h.pg);
         }
-        st4<VEC>(T.h.out_l, p, nv, l);
-        st4<VEC>(T.h.out_r, p, nv, r);
+        if (MODE != FX_NORM_PEAK || !T.no_store) {
+            st4<VEC>(T.h.out_l, p, nv, l);
+            st4<VEC>(T.h.out_r, p, nv, r);
+        }
     }
     if (MODE == FX_NORM_PEAK) {
         peak = block_max(peak);
@@ -390,7 +408,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
 // Accumulators stay in registers across segment batches; one float4 store per channel at the end.
 #define TDG_SEG_BATCH 64
 #ifndef TDG_SYNTH_F
-#define TDG_SYNTH_F 2           // frames per thread of the synth kernel (tuning knob, see profiles/)
+#define TDG_SYNTH_F 4           // frames per thread of the synth kernel (tuning knob, see profiles/)
 #endif
 #ifndef TDG_SYNTH_MINB
 #define TDG_SYNTH_MINB 3        // min resident blocks per SM of the synth kernel (register cap)
@@ -483,35 +501,43 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
                 if (KIND == VOICE_DEBUG_SINE) {                                       // extensions.rs:450-454
 #pragma unroll
                     for (int j = 0; j < F; ++j) smp[j] = d_sin(m_osc_arg(time[j], hz)) * vel;
-                } else if (KIND == VOICE_SYNTH) {                                     // extensions.rs:500-522
-                    const float r0 = relv[0][s], r1 = relv[1][s], r2 = relv[2][s];
+                } else {
+                    float et[F], e[F];
 #pragma unroll
-                    for (int j = 0; j < F; ++j) {
-                        const float env_time = env_t + off[j];
-                        float sn = 0.0f, v = 0.0f;
-                        if (T.sq_vol > 0.0f || T.tf_vol > 0.0f) sn = d_sin(m_osc_arg(time[j], hz));
-                        if (T.sq_vol > 0.0f) {
-                            const float e = rel ? k_apply_r<EXACT>(T.env[0], env_time, r0) : k_apply_ads<EXACT>(T.env[0], env_time);
-                            v = fminf(fmaxf(sn, -T.sq_z), T.sq_z) * T.sq_iz * vel * e * T.sq_vol;
-                        }
-                        if (T.tf_vol > 0.0f) {
-                            const float e = rel ? k_apply_r<EXACT>(T.env[1], env_time, r1) : k_apply_ads<EXACT>(T.env[1], env_time);
-                            v += (fminf(sn, T.tf_z) + T.tf_add) * T.tf_mul * vel * e * T.tf_vol;
-                        }
-                        if (T.tr_vol > 0.0f) {
-                            const float e = rel ? k_apply_r<EXACT>(T.env[2], env_time, r2) : k_apply_ads<EXACT>(T.env[2], env_time);
-                            v += m_triangle(time[j], hz) * vel * e * T.tr_vol;
-                        }
-                        smp[j] = v * T.amp_mul;
-                    }
-                } else {                                                              // extensions.rs:560-571
-                    const float r0 = relv[0][s];
+                    for (int j = 0; j < F; ++j) et[j] = env_t + off[j];               // env_time
+                    if (KIND == VOICE_SYNTH) {                                        // extensions.rs:500-522
+                        float sn[F];
+                        if (T.vol[0] > 0.0f || T.vol[1] > 0.0f) {
 #pragma unroll
-                    for (int j = 0; j < F; ++j) {
-                        const float env_time = env_t + off[j];
-                        const float e = rel ? k_apply_r<EXACT>(T.env[0], env_time, r0) : k_apply_ads<EXACT>(T.env[0], env_time);
-                        const float g = vel * e * T.amp_mul;
-                        smp[j] = wavetable_eval(tab, n_phase_f, (int)T.n_phase, ymax, last_row_off, T.fps, hz, env_time + rel_t) * g;
+                            for (int j = 0; j < F; ++j) sn[j] = d_sin(m_osc_arg(time[j], hz));
+                        }
+#pragma unroll
+                        for (int j = 0; j < F; ++j) smp[j] = 0.0f;
+#pragma unroll 1
+                        for (int o = 0; o < 3; ++o) {                                 // square, topflat, triangle in this order
+                            const float vol = T.vol[o];
+                            if (!(vol > 0.0f)) continue;
+                            if (rel) k_apply_r_n<EXACT, F>(T.env[o], et, relv[o][s], e); else k_apply_ads_n<EXACT, F>(T.env[o], et, e);
+                            if (o == 0) {
+#pragma unroll
+                                for (int j = 0; j < F; ++j) smp[j] += fminf(fmaxf(sn[j], -T.sq_z), T.sq_z) * T.sq_iz * vel * e[j] * vol;
+                            } else if (o == 1) {
+#pragma unroll
+                                for (int j = 0; j < F; ++j) smp[j] += (fminf(sn[j], T.tf_z) + T.tf_add) * T.tf_mul * vel * e[j] * vol;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < F; ++j) smp[j] += m_triangle(time[j], hz) * vel * e[j] * vol;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < F; ++j) smp[j] *= T.amp_mul;
+                    } else {                                                          // extensions.rs:560-571
+                        if (rel) k_apply_r_n<EXACT, F>(T.env[0], et, relv[0][s], e); else k_apply_ads_n<EXACT, F>(T.env[0], et, e);
+#pragma unroll
+                        for (int j = 0; j < F; ++j) {
+                            const float g = vel * e[j] * T.amp_mul;
+                            smp[j] = wavetable_eval(tab, n_phase_f, (int)T.n_phase, ymax, last_row_off, T.fps, hz, et[j] + rel_t) * g;
+                        }
                     }
                 }
 #pragma unroll
@@ -771,9 +797,16 @@ __global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __res
     const int nv = (int)min((uint64_t)4, T.n - f0);
     int v[8];
     bool wide = false;
+    uint32_t kc = 0, rem = 0;
+    if (T.runmax) { const uint64_t pf = T.frame0 + f0; kc = (uint32_t)(pf / T.bl); rem = (uint32_t)(pf - (uint64_t)kc * T.bl); }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float l = j < nv ? T.in_l[f0 + j] : 0.0f, r = j < nv ? T.in_r[f0 + j] : 0.0f;
+        float l = j < nv ? T.in_l[f0 + j] : 0.0f, r = j < nv ? T.in_r[f0 + j] : 0.0f;
+        if (T.runmax) {                                   // fused normalize_gen scale + pan + gain of the output vertex
+            const float f = 1.0f / T.runmax[kc + (rem + j >= T.bl ? 1u : 0u)];
+            l *= f; r *= f;
+            apply_pg(l, r, T.pg);
+        }
         if (T.bd <= 16) { v[2 * j] = quant16(l, T.amp); v[2 * j + 1] = quant16(r, T.amp); }
         else { v[2 * j] = __float2int_rz(l * T.amp); v[2 * j + 1] = __float2int_rz(r * T.amp); }
     }
@@ -941,9 +974,22 @@ cudaError_t launch_sample_lerp(const LerpTask* t, uint32_t n, uint32_t max_chunk
     return cudaGetLastError();
 }
 
+// Occupancy cap of the voice kernels: they are FP32-issue bound and need no bandwidth, the streaming
+// kernels of the other lane are the opposite, so leaving part of every SM to the latter lets the two
+// co-reside (DESIGN.md "co-scheduling").  The cap is expressed as reserved dynamic shared memory.
+static int g_voice_smem = -1;
+void set_voice_reserved_smem(int bytes) { g_voice_smem = bytes; }
 template <int KIND, bool EXACT>
 static cudaError_t launch_voice_t(const VoiceTask* t, uint32_t n, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s) {
-    k_voice<KIND, EXACT, KIND == VOICE_SYNTH ? TDG_SYNTH_F : 4><<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t, blob);
+    if (g_voice_smem < 0) { const char* e = getenv("TDG_VOICE_SMEM"); g_voice_smem = e ? atoi(e) : 0; }
+    auto kfn = k_voice<KIND, EXACT, KIND == VOICE_SYNTH ? TDG_SYNTH_F : 4>;
+    static int attr_set = -1;
+    if (g_voice_smem > 48 * 1024 - 8192 && attr_set != g_voice_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_voice_smem);
+        if (e != cudaSuccess) return e;
+        attr_set = g_voice_smem;
+    }
+    kfn<<<grid2(max_chunks, n), TDG_THREADS, (size_t)g_voice_smem, s>>>(t, blob);
     return cudaGetLastError();
 }
 cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool exact, const uint8_t* blob, cudaStream_t s) {

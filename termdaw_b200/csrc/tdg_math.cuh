@@ -63,8 +63,7 @@ TDG_HD float m_triangle(float t, float hz) {
 // ---- AdsrK: host builder (plain C++, same f32 operations as the reference's expressions) ---------
 inline bool adsr_duration_exotic(float d) {
     if (d == 0.0f) return false;
-    const float a = fabsf(d);
-    return !(a >= 1e-6f && a <= 1e6f);          // NaN, inf, denormal-ish or huge
+    return !(d >= 1e-6f && d <= 1e6f);          // negative, NaN, inf, denormal-ish or huge
 }
 inline AdsrK make_adsr_k(const AdsrConfD& c) {
     AdsrK k;
@@ -109,12 +108,81 @@ template <bool EXACT>
 __device__ __forceinline__ float k_apply_r(const AdsrK& c, float t, float old_val) {         // adsr.rs:71-73
     return old_val + fminf(k_div<EXACT>(t, c.rsec, c.rr), 1.0f) * (c.v4 - old_val);
 }
+// The same two functions over the F consecutive frames of one thread.  env_time is non-decreasing over
+// those frames and (for non-exotic envelopes: durations >= 0) so are the thresholds, hence when the
+// first and the last frame sit in the same segment of the envelope all F do: the segment's constants
+// are selected once and the F quotients/lerps are straight-line code that the scheduler can overlap.
+template <bool EXACT, int F>
+__device__ __forceinline__ void k_apply_ads_n(const AdsrK& c, const float (&t)[F], float (&e)[F]) {
+    if (!EXACT) {
+        const float tf = t[0], tl = t[F - 1];
+        const int s0 = (tf <= c.a) ? 0 : (tf <= c.ad) ? 1 : (tf <= c.ads) ? 2 : 3;
+        const int s1 = (tl <= c.a) ? 0 : (tl <= c.ad) ? 1 : (tl <= c.ads) ? 2 : 3;
+        if (s0 == s1) {
+            if (s0 == 3) {
+#pragma unroll
+                for (int j = 0; j < F; ++j) e[j] = c.v3;
+                return;
+            }
+            const float sub1 = s0 >= 1 ? c.a : 0.0f, sub2 = s0 == 2 ? c.dsec : 0.0f;    // x - 0.0f == x
+            const float d = s0 == 0 ? c.a : s0 == 1 ? c.dsec : c.ssec;
+            const float r = s0 == 0 ? c.ra : s0 == 1 ? c.rd : c.rs;
+            const float base = s0 == 0 ? c.v0 : s0 == 1 ? c.v1 : c.v2;
+            const float dl = s0 == 0 ? c.d01 : s0 == 1 ? c.d12 : c.d23;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                const float res = base + k_div<false>(t[j] - sub1 - sub2, d, r) * dl;
+                e[j] = res <= -1.0f ? c.v3 : res;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < F; ++j) e[j] = k_apply_ads<EXACT>(c, t[j]);
+}
+template <bool EXACT, int F>
+__device__ __forceinline__ void k_apply_r_n(const AdsrK& c, const float (&t)[F], float old_val, float (&e)[F]) {
+    const float dl = c.v4 - old_val;
+#pragma unroll
+    for (int j = 0; j < F; ++j) e[j] = old_val + fminf(k_div<EXACT>(t[j], c.rsec, c.rr), 1.0f) * dl;
+}
 template <bool EXACT>
 __device__ __forceinline__ float k_apply_adsr(const AdsrK& c, float t) {                     // adsr.rs:75-86
     const float res = k_ads_internal<EXACT>(c, t);
     if (res <= -1.0f)
         return c.v3 + fminf(k_div<EXACT>(t - c.a - c.dsec - c.ssec, c.rsec, c.rr), 1.0f) * c.d34;
     return res;
+}
+template <bool EXACT, int F>
+__device__ __forceinline__ void k_apply_adsr_n(const AdsrK& c, const float (&t)[F], float (&e)[F]) {
+    if (!EXACT) {
+        const float tf = t[0], tl = t[F - 1];
+        const int s0 = (tf <= c.a) ? 0 : (tf <= c.ad) ? 1 : (tf <= c.ads) ? 2 : 3;
+        const int s1 = (tl <= c.a) ? 0 : (tl <= c.ad) ? 1 : (tl <= c.ads) ? 2 : 3;
+        if (s0 == s1) {
+            if (s0 == 3) {
+#pragma unroll
+                for (int j = 0; j < F; ++j)
+                    e[j] = c.v3 + fminf(k_div<false>(t[j] - c.a - c.dsec - c.ssec, c.rsec, c.rr), 1.0f) * c.d34;
+                return;
+            }
+            const float sub1 = s0 >= 1 ? c.a : 0.0f, sub2 = s0 == 2 ? c.dsec : 0.0f;
+            const float d = s0 == 0 ? c.a : s0 == 1 ? c.dsec : c.ssec;
+            const float r = s0 == 0 ? c.ra : s0 == 1 ? c.rd : c.rs;
+            const float base = s0 == 0 ? c.v0 : s0 == 1 ? c.v1 : c.v2;
+            const float dl = s0 == 0 ? c.d01 : s0 == 1 ? c.d12 : c.d23;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                const float res = base + k_div<false>(t[j] - sub1 - sub2, d, r) * dl;
+                e[j] = res;
+                if (res <= -1.0f)                        // adsr.rs:77: falls through to the release lerp
+                    e[j] = c.v3 + fminf(k_div<false>(t[j] - c.a - c.dsec - c.ssec, c.rsec, c.rr), 1.0f) * c.d34;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < F; ++j) e[j] = k_apply_adsr<EXACT>(c, t[j]);
 }
 #endif
 

@@ -70,6 +70,7 @@ struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan 
     uint64_t seg_ptr_off;   // blob: uint32[n_chunks+1], indices into the AdsrSeg array
     uint64_t seg_off;       // blob: AdsrSeg[]
     float* peaks;           // FX_NORM_PEAK: [n_chunks] max |x| over L and R of the summed chunk
+    uint32_t no_store, pad1; // FX_NORM_PEAK of the output vertex in a scan pass: only the peaks are needed
 };
 
 // Time sharding: a pass split into `x_ranks` consecutive segments.  Every DAG level owns
@@ -109,7 +110,8 @@ struct VoiceTask {
     uint64_t seg_off;       // blob: VoiceSeg[]
     // Synth (extensions.rs:44-50); shape constants of synth.rs:22-29 evaluated on the host:
     // sq_iz = 1/z, tf_add = (1-z)/2, tf_mul = 2/(1+z)
-    float sq_vol, sq_z, sq_iz, tf_vol, tf_z, tf_add, tf_mul, tr_vol, amp_mul;
+    float vol[3];           // square, topflat, triangle volumes
+    float sq_z, sq_iz, tf_z, tf_add, tf_mul, amp_mul;
     uint32_t pad0;
     AdsrK env[3];           // square, topflat, triangle; SampSyn (extensions.rs:51-56) uses env[0]
     // SampSyn wavetable [n_frames][n_phase]
@@ -141,7 +143,13 @@ struct QuantTask {          // write_16s / write_32s (state.rs:517-532) + hound'
     uint32_t bd;
     float amp;
     uint32_t* err;          // set non-zero when an 8/24-bit value is too wide
-    uint32_t pad;
+    uint32_t bl;            // frames per chunk (fused normalize only)
+    // Output vertex = Normalize (the usual termdaw project): its scale pass is fused in here instead of
+    // a separate read-modify-write of the whole buffer: x * (1/max_of_chunk), pan, gain, then quantise
+    // (extensions.rs:328,262-263 then state.rs:517-532 — same operations, same order, in registers).
+    const float* runmax;    // null: input is already final
+    uint64_t frame0;        // pass frame of input frame 0 (chunk = (frame0 + f) / bl)
+    PanGain pg;
 };
 
 struct ResampleTask {       // rubato SincFixedIn restated: one output frame per thread

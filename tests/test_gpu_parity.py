@@ -125,6 +125,37 @@ def test_render_many_equals_single(gpulib, oracle):
         st.close()
 
 
+@pytest.mark.parametrize("group", [0, 2, 3])
+def test_pipelined_batches_equal_oracle(gpulib, oracle, group):
+    """tdg_normalize_render_many / tdg_*_many with software pipelining (groups of `group` projects over two
+    streams, two plan slots each; 0 = one launch sequence) == the oracle's per-project scan + render."""
+    from termdaw_b200 import normalize_render_many, normalize_scan_many, render_many
+    from termdaw_b200.state import State
+    cfgs = [S.config_5_project(i, 0.04) for i in range(11)]
+    wants = [run_project(oracle, p, a, s, taps=False) for p, a, s in cfgs]
+    for combined in (True, False):
+        states = []
+        for p, a, s in cfgs:
+            st = State(gpulib, s["psr"], s["bl"], assets=a)
+            assert st.refresh(p), st.messages
+            states.append(st)
+        ctxs = [st.ctx for st in states]
+        ctxs[0].set_pipeline_group(group)
+        args = ([st.cs for st in states], [st.render_sr for st in states], [st.bd for st in states])
+        if combined:
+            pcms = normalize_render_many(gpulib, ctxs, *args)
+        else:
+            normalize_scan_many(gpulib, ctxs, args[0])
+            pcms = render_many(gpulib, ctxs, *args)
+        ctxs[0].set_pipeline_group(64)
+        for st, pcm, want in zip(states, pcms, wants):
+            x, y = pcm_to_int(pcm, st.bd), pcm_to_int(want["pcm"], want["bd"])
+            assert x.shape == y.shape and np.abs(x - y).max() <= 1, (group, combined)
+            for k, v in want["norm"].items():
+                assert abs(st.normalization_values()[k] - v) <= TOL_IIR * max(1.0, abs(v))
+            st.close()
+
+
 @pytest.mark.parametrize("bd", [8, 16, 24, 32])
 def test_bitdepths(gpulib, oracle, bd):
     """quantisation to every supported depth (state.rs:515-532) on a bit-exact graph."""
