@@ -84,6 +84,12 @@ int tdg_floww_reset(tdg_ctx* ctx);
 /* ---- graph construction -------------------------------------------------------------------------
  * Graph::reset (graph.rs:39).  Vertices get indices in call order (graph.rs:49-56). */
 int tdg_graph_reset(tdg_ctx* ctx);
+/* State::refresh on an UNCHANGED project: the reference drops the graph and re-adds every vertex
+ * (state.rs:328-457), so all per-vertex state (loop counters, hit deques, voices, envelope slots,
+ * filter state, normalize maxima) returns to its constructor value (extensions.rs:83-194) and the
+ * transport to 0.  Same result as tdg_graph_reset + re-adding the same vertices and edges, without
+ * the calls; device-resident samples, resources and flowws are kept (state.rs:201-219). */
+int tdg_reset_vertex_state(tdg_ctx* ctx);
 /* Graph::add(Vertex::new(bl, gain, angle, wet, VertexExt::…)) — graph.rs:49, ctors extensions.rs:83-194,
  * argument clamps of state.rs:341-457 are applied by the CALLER's front-end except where noted. */
 int tdg_add_sum(tdg_ctx* ctx, float gain, float angle);                                   /* state.rs:341 */

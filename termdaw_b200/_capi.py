@@ -124,6 +124,7 @@ class Library:
         "normalize_state_device_ptr": (C.c_void_p, [C.c_void_p, c_i32p]),
         "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
         "set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+        "reset_vertex_state": (C.c_int, [C.c_void_p]),
         "set_pipeline_group": (C.c_int, [C.c_void_p, C.c_uint32]),
         "last_pass_kernel_stats": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_int]),
     }
@@ -261,6 +262,10 @@ class Context:
         n = C.c_int(0)
         ok = self.lib.check_graph(self.h, arr, cap, C.byref(n))
         return bool(ok), [arr[i] for i in range(min(n.value, cap))]
+
+    def reset_vertex_state(self):
+        """State::refresh on an unchanged project: every vertex back to its constructor state."""
+        self._chk(self.lib.reset_vertex_state(self.h))
 
     def reset_normalize(self):
         self._chk(self.lib.reset_normalize(self.h))

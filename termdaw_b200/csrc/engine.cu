@@ -14,6 +14,8 @@
 #include <string.h>
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -47,25 +49,32 @@ static inline uint64_t f32_as_usize(float x) {
 // ------------------------------------------------------------------------------------ engine
 struct DevBuf {
     uint8_t* p = nullptr; uint64_t cap = 0;
-    cudaError_t ensure(uint64_t bytes) {
+    // `hint`: the engine's high-water mark for this kind of buffer.  Growing means cudaFree (a device-wide
+    // sync) + cudaMalloc in the middle of a pipelined batch, so every buffer of a kind is sized from the
+    // largest request any of them has seen, with 25 % headroom: after the first batch nothing regrows.
+    cudaError_t ensure(uint64_t bytes, uint64_t hint = 0) {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        uint64_t want = align_up(bytes + bytes / 8, 1 << 20);
+        const uint64_t base = hint <= 2 * bytes ? std::max(bytes, hint) : bytes;   // a much larger mark belongs to another batch shape
+        uint64_t want = align_up(base + base / 4, 1 << 20);
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
         if (e == cudaSuccess) cap = want;
+        if (trace_on()) fprintf(stderr, "[tdg] grow device buffer to %.1f MB (request %.1f MB)\n", want / 1e6, bytes / 1e6);
         return e;
     }
 };
 struct PinnedBuf {                 // growable pinned staging buffer for the plan blob
     uint8_t* p = nullptr; uint64_t cap = 0, size = 0;
-    bool reserve(uint64_t bytes) {
+    bool reserve(uint64_t bytes, uint64_t hint = 0) {
         if (bytes <= cap) return true;
-        uint64_t want = std::max<uint64_t>(align_up(bytes, 1 << 20), cap * 2);
+        const uint64_t base = hint <= 2 * bytes ? std::max(bytes, hint) : bytes;
+        uint64_t want = std::max<uint64_t>(align_up(base + base / 4, 1 << 20), cap * 2);
         uint8_t* q = nullptr;
         if (cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess) return false;
         if (p) { memcpy(q, p, size); cudaFreeHost(p); }
+        if (trace_on()) fprintf(stderr, "[tdg] grow pinned buffer %.1f -> %.1f MB (request %.1f MB)\n", cap / 1e6, want / 1e6, bytes / 1e6);
         p = q; cap = want;
         return true;
     }
@@ -81,13 +90,18 @@ struct PinnedBuf {                 // growable pinned staging buffer for the pla
 };
 
 // A lane = one stream + one work arena; a slot = the per-pass plan blob (pinned + device), events and
-// pinned error flags.  Two lanes x two slots let a batched call keep four passes in flight
+// pinned error flags.  kLanes lanes x two slots let a batched call keep eight passes in flight
 // (run_jobs_pipelined): host planning, H2D, kernels and the PCM D2H of consecutive project groups
-// overlap, and a group's render pass can be planned while its scan pass still runs.  Single passes
-// use lane 0 / slot 0.
+// overlap, and a group's render pass can be planned while its scan pass still runs.  With only two
+// lanes both finish their kernels together and then both wait on PCIe (the D2H sits in the lane's
+// stream because the PCM lives in the lane's arena): the measured timeline (profiles/) showed kernels
+// and D2H alternating instead of overlapping; with four, two lanes compute while two drain.
+// Single passes use lane 0 / slot 0.
 struct Slot {
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr, ev_h2d = nullptr;
     DevBuf blob_dev;
+    DevBuf pcm;                    // quantised output + TooWide flags of the pass: NOT in the lane's arena, so the
+                                   // next pass of the lane may start while the copy stream still drains this one
     PinnedBuf blob;
     std::vector<cudaEvent_t> evpool;
     uint32_t* err_host = nullptr; size_t err_cap = 0;      // pinned: TooWide flags come back without a pageable copy
@@ -101,21 +115,82 @@ struct Slot {
         return true;
     }
 };
+static const int kLanes = 4, kSlots = 6;
 struct Lane {
     cudaStream_t stream = nullptr;
     DevBuf work;
-    Slot slots[2];
+    Slot slots[kSlots];
 };
+// Persistent host workers for the planner: projects of a batch are planned independently, and a job of a
+// pipelined batch is short (a few ms), so threads are created once per engine, not once per job.
+struct WorkerPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::function<void(size_t, unsigned)> fn;    // (item, worker index)
+    std::atomic<size_t> next{0};
+    size_t n = 0;
+    uint64_t gen = 0;
+    unsigned busy = 0;
+    bool stop = false;
+    unsigned workers() const { return (unsigned)th.size() + 1; }     // + the calling thread
+    void start(unsigned k) {
+        for (unsigned i = 0; i < k; ++i)
+            th.emplace_back([this, i]() {
+                uint64_t seen = 0;
+                for (;;) {
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&]() { return stop || gen != seen; });
+                        if (stop) return;
+                        seen = gen;
+                    }
+                    for (;;) { const size_t j = next.fetch_add(1); if (j >= n) break; fn(j, i + 1); }
+                    { std::lock_guard<std::mutex> lk(mu); if (--busy == 0) cv_done.notify_one(); }
+                }
+            });
+    }
+    // fn(item, worker) for item in [0, count); returns when all are done.  One caller at a time.
+    void parallel_for(size_t count, unsigned max_workers, std::function<void(size_t, unsigned)> f) {
+        if (count == 0) return;
+        const unsigned use = (unsigned)std::min<size_t>(std::min<size_t>(max_workers, workers()), count);
+        if (use <= 1 || th.empty()) { for (size_t j = 0; j < count; ++j) f(j, 0); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = std::move(f); n = count; next.store(0); busy = (unsigned)th.size(); ++gen;
+        }
+        cv.notify_all();
+        for (;;) { const size_t j = next.fetch_add(1); if (j >= n) break; fn(j, 0); }
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&]() { return busy == 0; });
+    }
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+};
+
+struct Frag;
+struct PlanScratch;
 struct Engine {
     int device = 0;
-    Lane lanes[2];
+    Lane lanes[kLanes];
+    bool taper = true;                           // TDG_TAPER=0: equal groups (A/B measurements)
+    int n_lanes = 2;                             // lanes a pipelined batch rotates over (TDG_LANES=1..4; measured best: 2)
     cudaStream_t stream = nullptr;               // == lanes[0].stream (bank uploads, state sync)
+    cudaStream_t copy_stream = nullptr;          // PCM device->host copies of every lane (one PCIe direction, one queue)
+    cudaStream_t h2d_stream = nullptr;           // plan-blob uploads: run ahead of the lane's kernels instead of between them
     std::map<uint32_t, float*> sinc_tables;     // keyed by the f32 bits of the cutoff
     uint64_t epoch = 0;                          // bumped by every pass (taps of older passes are stale)
     int refs = 0;
     bool profiling = false;                      // CUDA events around every launch (per-class roofline)
     uint32_t pipeline_group = 64;                // projects per pipelined group (0 = never pipeline)
-    cudaEvent_t ev_batch0 = nullptr, ev_batch1[2] = {nullptr, nullptr};   // span of a pipelined call
+    uint64_t hwm_work = 0, hwm_blob = 0, hwm_pcm = 0;         // largest work arena / plan blob any lane or slot has needed
+    WorkerPool* pool = nullptr;                  // planner threads (created on first batched pass)
+    std::vector<Frag>* frags = nullptr;          // pooled per-project plan fragments (capacity is kept between jobs)
+    std::vector<PlanScratch>* scratch = nullptr; // per worker: event-table scratch vectors
+    cudaEvent_t ev_batch0 = nullptr, ev_batch1[kLanes] = {}, ev_copy_end = nullptr;   // span of a pipelined call
 };
 static std::mutex g_mu;
 static std::map<int, Engine*> g_engines;
@@ -141,11 +216,16 @@ static Engine* engine_get(int device, std::string* err) {
         bool ok = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) == cudaSuccess;
         for (Slot& sl : ln.slots)
             ok = ok && cudaEventCreate(&sl.ev0) == cudaSuccess && cudaEventCreate(&sl.ev1) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming) == cudaSuccess;
+                 cudaEventCreate(&sl.ev_done) == cudaSuccess && cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { *err = "could not create stream/events"; delete g; return nullptr; }
     }
     g->stream = g->lanes[0].stream;
-    cudaEventCreate(&g->ev_batch0); cudaEventCreate(&g->ev_batch1[0]); cudaEventCreate(&g->ev_batch1[1]);
+    if (cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&g->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) { *err = "could not create the copy stream"; delete g; return nullptr; }
+    cudaEventCreate(&g->ev_batch0); cudaEventCreate(&g->ev_copy_end);
+    for (int i = 0; i < kLanes; ++i) cudaEventCreate(&g->ev_batch1[i]);
+    if (const char* e = getenv("TDG_LANES")) g->n_lanes = std::max(1, std::min(kLanes, atoi(e)));
+    if (const char* e = getenv("TDG_TAPER")) g->taper = atoi(e) != 0;
     g->refs = 1;
     g_engines[device] = g;
     return g;
@@ -523,13 +603,18 @@ struct PassReq {
     uint32_t err_flag = 0;
 };
 
-template <typename T> struct TaskList { std::vector<T> v; uint32_t max_chunks = 0; uint64_t bytes = 0; };
+template <typename T> struct TaskList { std::vector<T> v; uint32_t max_chunks = 0; uint64_t bytes = 0; void clear() { v.clear(); max_chunks = 0; bytes = 0; } };
 struct LevelTasks {
     TaskList<FxTask> fx, fx_adsr, fx_norm; TaskList<NormPrefixTask> nprefix; TaskList<NormScaleTask> nscale;
     TaskList<LoopTask> loop; TaskList<MultiTask> multi; TaskList<LerpTask> lerp;
     TaskList<VoiceTask> dsine, synth, sampsyn; TaskList<BpTask> bp;
     bool fx_adsr_exact = false, dsine_exact = false, synth_exact = false, sampsyn_exact = false;
     uint64_t bp_agg_bytes = 0;
+    void clear() {                       // keeps the vectors' capacity (pooled fragments)
+        fx.clear(); fx_adsr.clear(); fx_norm.clear(); nprefix.clear(); nscale.clear(); loop.clear(); multi.clear(); lerp.clear();
+        dsine.clear(); synth.clear(); sampsyn.clear(); bp.clear();
+        fx_adsr_exact = dsine_exact = synth_exact = sampsyn_exact = false; bp_agg_bytes = 0;
+    }
 };
 
 static void compute_levels(PassReq& r) {
@@ -566,7 +651,16 @@ struct Frag {
     std::vector<LevelTasks> levels;
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, algo = 0;
+    void reset(size_t n_levels) {        // pooled on the engine: capacities survive from job to job
+        blob.v.clear(); base = 0;
+        if (levels.size() > n_levels) levels.resize(n_levels);
+        for (LevelTasks& L : levels) L.clear();
+        levels.resize(n_levels);
+        quants.clear(); resamps.clear();
+        quant_max = quant_bytes = resamp_max = resamp_bytes = algo = 0;
+    }
 };
+struct PlanScratch { std::vector<MultiHit> mhits; std::vector<LerpHit> lhits; SegOut so; };
 template <typename T> static void append_list(TaskList<T>& d, TaskList<T>& s) {
     d.v.insert(d.v.end(), s.v.begin(), s.v.end());
     d.max_chunks = std::max(d.max_chunks, s.max_chunks); d.bytes += s.bytes;
@@ -583,17 +677,20 @@ struct PassJob {
     std::vector<PassReq> reqs;
     Lane* lane = nullptr;
     int slot = 0;
-    bool submitted = false, waited = false;
+    bool submitted = false, waited = false, in_batch = false;
     KStat ks[KC_COUNT];                 // per kernel class, filled by pass_wait
     int max_level = -1;
     bool all_vec = true;
     uint8_t* W = nullptr;
+    uint8_t* P = nullptr;               // the slot's PCM buffer
+    uint64_t err_base = 0, err_bytes = 0; // TooWide flags: one u32 per request, contiguous inside P
     std::vector<LevelTasks> levels;
     std::vector<Off> offs;
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, quant_off = 0, resamp_off = 0;
     uint64_t algo_bytes_total = 0;
-    double t_start = 0, t_planned = 0, t_h2d_issued = 0, t_d2h0 = 0;
+    double t_start = 0, t_planned = 0, t_h2d_issued = 0, t_d2h0 = 0, t_submitted = 0;
+    float dev_t0 = 0, dev_t1 = 0, dev_tdone = 0;      // device timeline relative to the batch start (trace only)
     uint64_t launches = 0, collectives = 0, d2h_bytes = 0, h2d_bytes = 0;
     std::vector<Timed> timed;
 };
@@ -610,7 +707,7 @@ static int pass_plan(PassJob& J) {
     g->epoch++;
 
     // ---- 1. graph analysis + work-arena layout -------------------------------------------------
-    Bump bump;
+    Bump bump, pbump;
     int& max_level = J.max_level;
     max_level = -1;
     for (auto& r : reqs) {
@@ -622,7 +719,11 @@ static int pass_plan(PassJob& J) {
         r.buf_off.assign(V, -1); r.aux_off.assign(V, -1);
         for (int v = 0; v < V; ++v) max_level = std::max(max_level, r.level[v]);
     }
-    for (auto& r : reqs) {
+    J.err_bytes = reqs.size() * 4;
+    J.err_base = pbump.alloc(J.err_bytes);
+    for (size_t ri = 0; ri < reqs.size(); ++ri) {
+        PassReq& r = reqs[ri];
+        r.err_off = J.err_base + ri * 4;
         Ctx* x = r.c;
         const int V = (int)x->verts.size();
         const uint64_t slot_bytes = r.n_pad * 2 * 4;
@@ -671,13 +772,16 @@ static int pass_plan(PassJob& J) {
                 r.out_frames = r.rs_total;
             }
             r.pcm_bytes = r.out_frames * 2 * (r.bd / 8);
-            r.pcm_off = bump.alloc(align_up(r.pcm_bytes, 64) + 64);
-            r.err_off = bump.alloc(16);
+            r.pcm_off = pbump.alloc(align_up(r.pcm_bytes, 64) + 64);
         }
     }
     const double tr_layout = now_ms();
-    CU(ln.work.ensure(bump.off + 256));
+    g->hwm_work = std::max<uint64_t>(g->hwm_work, bump.off + 256);
+    CU(ln.work.ensure(bump.off + 256, g->hwm_work));
     uint8_t* W = J.W = ln.work.p;
+    g->hwm_pcm = std::max<uint64_t>(g->hwm_pcm, pbump.off + 256);
+    CU(ln.slots[J.slot].pcm.ensure(pbump.off + 256, g->hwm_pcm));
+    uint8_t* P = J.P = ln.slots[J.slot].pcm.p;
     const double tr_arena = now_ms();
 
     // ---- 2. plan: tasks + tables into the pinned blob ------------------------------------------
@@ -698,15 +802,24 @@ static int pass_plan(PassJob& J) {
         }
     }
     const double tr_vstate = now_ms();
-    std::vector<Frag> frags(reqs.size());
-    auto plan_one = [&](PassReq& r, Frag& F) -> int {
+    if (!g->pool) {
+        g->pool = new WorkerPool();
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        g->pool->start(std::min(hw, 32u) - 1);
+        g->frags = new std::vector<Frag>();
+        g->scratch = new std::vector<PlanScratch>(g->pool->workers());
+    }
+    if (g->frags->size() < reqs.size()) g->frags->resize(reqs.size());
+    Frag* frags = g->frags->data();
+    const size_t n_frags = reqs.size();
+    auto plan_one = [&](PassReq& r, Frag& F, PlanScratch& PS) -> int {
         Ctx* x = r.c;
+        F.reset((size_t)max_level + 1);
         HeapBlob& B = F.blob;
         std::vector<LevelTasks>& levels = F.levels;
-        levels.resize(max_level + 1);
         std::vector<QuantTask>& quants = F.quants; uint64_t& quant_max = F.quant_max; uint64_t& quant_bytes = F.quant_bytes;
         std::vector<ResampleTask>& resamps = F.resamps; uint64_t& resamp_max = F.resamp_max; uint64_t& resamp_bytes = F.resamp_bytes;
-        std::vector<MultiHit> mhits; std::vector<LerpHit> lhits; SegOut so;
+        std::vector<MultiHit>& mhits = PS.mhits; std::vector<LerpHit>& lhits = PS.lhits; SegOut& so = PS.so;
         const int V = (int)x->verts.size();
         PassParams pp{r.is_scan ? 0 : x->fb_frame, r.is_scan ? 0 : x->t, r.total, r.emit0, r.emit_n, x->bl, x->sr};
         // (true_normalize_scan: fb.set_time(0) and t = j*bl, graph.rs:228-231)
@@ -894,7 +1007,7 @@ static int pass_plan(PassJob& J) {
             QuantTask q; memset(&q, 0, sizeof q);
             q.bd = r.bd;
             q.amp = r.bd < 32 ? (float)((1 << (r.bd - 1)) - 1) : (float)INT32_MAX;
-            q.out = W + r.pcm_off; q.err = reinterpret_cast<uint32_t*>(W + r.err_off);
+            q.out = P + r.pcm_off; q.err = reinterpret_cast<uint32_t*>(P + r.err_off);
             if (r.resample) {
                 ResampleTask rt; memset(&rt, 0, sizeof rt);
                 rt.in_l = ol; rt.in_r = orr;
@@ -921,24 +1034,11 @@ static int pass_plan(PassJob& J) {
         return TDG_OK;
     };
     {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const unsigned nthreads = (unsigned)std::min<size_t>(std::min(hw, 32u), reqs.size());
-        std::atomic<size_t> next{0};
         std::atomic<int> first_err{TDG_OK};
-        auto worker = [&]() {
-            for (;;) {
-                const size_t i = next.fetch_add(1);
-                if (i >= reqs.size()) break;
-                const int e = plan_one(reqs[i], frags[i]);
-                if (e != TDG_OK) { int z = TDG_OK; first_err.compare_exchange_strong(z, e); }
-            }
-        };
-        if (nthreads <= 1) worker();
-        else {
-            std::vector<std::thread> pool;
-            for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(worker);
-            for (auto& th : pool) th.join();
-        }
+        g->pool->parallel_for(reqs.size(), 32, [&](size_t i, unsigned w) {
+            const int e = plan_one(reqs[i], frags[i], (*g->scratch)[w]);
+            if (e != TDG_OK) { int z = TDG_OK; first_err.compare_exchange_strong(z, e); }
+        });
         if (first_err.load() != TDG_OK) return first_err.load();
     }
     const double tr_planned = now_ms();
@@ -954,26 +1054,15 @@ static int pass_plan(PassJob& J) {
     quants.clear(); resamps.clear(); quant_max = quant_bytes = resamp_max = resamp_bytes = algo_bytes_total = 0;
     {
         uint64_t tot = 0;
-        for (Frag& F : frags) { F.base = align_up(tot, 256); tot = F.base + F.blob.v.size(); }
-        if (!B.reserve(tot + 256)) return c->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
+        for (size_t i = 0; i < n_frags; ++i) { Frag& F = frags[i]; F.base = align_up(tot, 256); tot = F.base + F.blob.v.size(); }
+        g->hwm_blob = std::max<uint64_t>(g->hwm_blob, tot + 256);
+        if (!B.reserve(tot + 256, g->hwm_blob)) return c->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
         B.size = tot;
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const unsigned nthreads = (unsigned)std::min<size_t>(std::min(hw, 16u), frags.size());
-        std::atomic<size_t> next{0};
-        auto copier = [&]() {
-            for (;;) {
-                const size_t i = next.fetch_add(1);
-                if (i >= frags.size()) break;
-                if (!frags[i].blob.v.empty()) memcpy(B.p + frags[i].base, frags[i].blob.v.data(), frags[i].blob.v.size());
-            }
-        };
-        if (nthreads <= 1 || tot < (8u << 20)) copier();
-        else {
-            std::vector<std::thread> pool;
-            for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(copier);
-            for (auto& th : pool) th.join();
-        }
-        for (Frag& F : frags) {
+        g->pool->parallel_for(n_frags, tot < (8u << 20) ? 1 : 16, [&](size_t i, unsigned) {
+            if (!frags[i].blob.v.empty()) memcpy(B.p + frags[i].base, frags[i].blob.v.data(), frags[i].blob.v.size());
+        });
+        for (size_t fi = 0; fi < n_frags; ++fi) {
+            Frag& F = frags[fi];
             const uint64_t b = F.base;
             for (size_t L = 0; L < F.levels.size(); ++L) {
                 LevelTasks& S = F.levels[L]; LevelTasks& Dst = levels[L];
@@ -1000,7 +1089,6 @@ static int pass_plan(PassJob& J) {
             quant_max = std::max(quant_max, F.quant_max); quant_bytes += F.quant_bytes;
             resamp_max = std::max(resamp_max, F.resamp_max); resamp_bytes += F.resamp_bytes;
             algo_bytes_total += F.algo;
-            F.blob.v.clear(); F.blob.v.shrink_to_fit();
         }
     }
     // task arrays go into the blob too: one H2D for the whole pass
@@ -1030,7 +1118,8 @@ static int pass_plan(PassJob& J) {
     J.resamp_off = put(resamps.data(), resamps.size() * sizeof(ResampleTask));
     if (J.quant_off == UINT64_MAX || J.resamp_off == UINT64_MAX) return c->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
     const double tr_merged = now_ms();
-    CU(sl.blob_dev.ensure(B.size + 256));
+    g->hwm_blob = std::max<uint64_t>(g->hwm_blob, B.size + 256);
+    CU(sl.blob_dev.ensure(B.size + 256, g->hwm_blob));
     if (!sl.ensure_err(reqs.size())) return c->fail(TDG_ERR_CUDA, "pinned flag buffer allocation failed");
     J.t_planned = now_ms();
     if (trace_on())
@@ -1059,9 +1148,13 @@ static int pass_submit(PassJob& J) {
     // ---- 3. upload + launches ------------------------------------------------------------------
     const uint8_t* D = sl.blob_dev.p;
     cudaStream_t s = ln.stream;
-    CU(cudaMemcpyAsync(sl.blob_dev.p, B.p, B.size, cudaMemcpyHostToDevice, s));
+    // the blob goes up on the upload stream (it is ready long before the lane reaches this pass); the
+    // slot's previous pass is complete (host-synchronised in run_jobs_pipelined), so the device blob is free
+    CU(cudaMemcpyAsync(sl.blob_dev.p, B.p, B.size, cudaMemcpyHostToDevice, g->h2d_stream));
+    CU(cudaEventRecord(sl.ev_h2d, g->h2d_stream));
+    CU(cudaStreamWaitEvent(s, sl.ev_h2d, 0));
     J.h2d_bytes = B.size;
-    for (auto& r : reqs) if (!r.is_scan && r.c->output >= 0) CU(cudaMemsetAsync(W + r.err_off, 0, 4, s));
+    if (J.err_bytes) CU(cudaMemsetAsync(J.P + J.err_base, 0, J.err_bytes, s));      // TooWide flags of every request, contiguous
     J.t_h2d_issued = now_ms();
     CU(cudaEventRecord(sl.ev0, s));
     uint64_t &launches = J.launches, &collectives = J.collectives;
@@ -1124,9 +1217,15 @@ static int pass_submit(PassJob& J) {
     CU(cudaEventRecord(sl.ev1, s));
 
     // ---- 4. results back -------------------------------------------------------------------------
+    // PCM and TooWide flags leave on the engine's copy stream once the kernels are done (ev1): the lane's
+    // stream is free for its next pass immediately, so kernels of group g+1 run under the D2H of group g.
     J.t_d2h0 = now_ms();
     uint64_t& d2h_bytes = J.d2h_bytes;
     d2h_bytes = 0;
+    bool any_out = false;
+    for (auto& r : reqs) if (!r.is_scan && r.c->output >= 0) any_out = true;
+    cudaStream_t cs = any_out ? g->copy_stream : s;
+    if (any_out) CU(cudaStreamWaitEvent(cs, sl.ev1, 0));
     for (size_t i = 0; i < reqs.size(); ++i) {
         PassReq& r = reqs[i];
         sl.err_host[i] = 0;
@@ -1134,13 +1233,14 @@ static int pass_submit(PassJob& J) {
         if (r.out) {
             if (r.cap < r.pcm_bytes) return r.c->fail(TDG_ERR_CAPACITY, "output buffer too small");
             // asynchronous when the caller's buffer is pinned (cudaHostAlloc / cudaHostRegister)
-            CU(cudaMemcpyAsync(r.out, W + r.pcm_off, r.pcm_bytes, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(r.out, J.P + r.pcm_off, r.pcm_bytes, cudaMemcpyDeviceToHost, cs));
             d2h_bytes += r.pcm_bytes;
         }
-        CU(cudaMemcpyAsync(sl.err_host + i, W + r.err_off, 4, cudaMemcpyDeviceToHost, s));
     }
-    CU(cudaEventRecord(sl.ev_done, s));
+    if (any_out) CU(cudaMemcpyAsync(sl.err_host, J.P + J.err_base, J.err_bytes, cudaMemcpyDeviceToHost, cs));
+    CU(cudaEventRecord(sl.ev_done, cs));
     J.submitted = true;
+    J.t_submitted = now_ms();
     if (trace_on()) fprintf(stderr, "[tdg] submit lane %d: enqueue %.2f ms, %llu launches\n", (int)(J.lane - g->lanes), now_ms() - J.t_planned, (unsigned long long)launches);
     return TDG_OK;
 }
@@ -1187,6 +1287,10 @@ static int pass_wait(PassJob& J) {
     const double t_end = now_ms();
     float dev_ms = 0.0f;
     cudaEventElapsedTime(&dev_ms, sl.ev0, sl.ev1);
+    if (trace_on() && J.in_batch) {
+        cudaEventElapsedTime(&J.dev_t0, g->ev_batch0, sl.ev0); cudaEventElapsedTime(&J.dev_t1, g->ev_batch0, sl.ev1);
+        cudaEventElapsedTime(&J.dev_tdone, g->ev_batch0, sl.ev_done);
+    }
     if (trace_on()) fprintf(stderr, "[tdg] wait lane %d slot %d: waited %.2f ms, device %.2f ms\n", (int)(J.lane - g->lanes), J.slot, t_end - t_sync0, dev_ms);
     KStat* ks = J.ks;
     for (int k = 0; k < KC_COUNT; ++k) ks[k] = KStat();
@@ -1224,7 +1328,7 @@ static int run_pass(std::vector<PassReq>& reqs) {
     int e = pass_plan(J);
     if (e == TDG_OK) e = pass_submit(J);
     if (e == TDG_OK) { pass_end_state(J); e = pass_wait(J); }
-    else cudaStreamSynchronize(J.lane->stream);
+    else { cudaStreamSynchronize(J.lane->stream); cudaStreamSynchronize(J.lane == nullptr ? nullptr : J.reqs[0].c->eng->copy_stream); }
     reqs.swap(J.reqs);
     return e;
 }
@@ -1237,12 +1341,13 @@ static int run_pass(std::vector<PassReq>& reqs) {
 // in order on one stream).
 static int run_jobs_pipelined(Engine* g, std::vector<PassJob>& jobs, PassStats* tot_out, KStat* ks_out) {
     int rc = TDG_OK;
-    PassJob* last_in_slot[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    bool first = true, used[2] = {false, false};
+    PassJob* last_in_slot[kLanes][kSlots] = {};
+    bool first = true, used[kLanes] = {};
     for (size_t k = 0; k < jobs.size() && rc == TDG_OK; ++k) {
         PassJob& J = jobs[k];
         const int li = (int)(J.lane - g->lanes);
         if (PassJob* prev = last_in_slot[li][J.slot]) { rc = pass_wait(*prev); if (rc != TDG_OK) break; }
+        J.in_batch = true;
         rc = pass_plan(J);
         if (rc != TDG_OK) break;
         if (first) { cudaEventRecord(g->ev_batch0, J.lane->stream); first = false; }
@@ -1253,11 +1358,22 @@ static int run_jobs_pipelined(Engine* g, std::vector<PassJob>& jobs, PassStats* 
         used[li] = true;
         last_in_slot[li][J.slot] = &J;
     }
+    if (!first) cudaEventRecord(g->ev_copy_end, g->copy_stream);     // after the last PCM copy
     for (PassJob& J : jobs) { const int e = pass_wait(J); if (rc == TDG_OK) rc = e; }
-    if (rc != TDG_OK) { for (Lane& ln : g->lanes) cudaStreamSynchronize(ln.stream); return rc; }
-    // whole-call figures: device time from the first job's start to the last job's end (both lanes)
+    if (rc != TDG_OK) { for (Lane& ln : g->lanes) cudaStreamSynchronize(ln.stream); cudaStreamSynchronize(g->copy_stream); return rc; }
+    if (trace_on()) {
+        const double h0 = jobs[0].t_start;
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            const PassJob& J = jobs[k];
+            fprintf(stderr, "[tdg] timeline job %2zu lane %d slot %d %s: host plan %.1f..%.1f submit ..%.1f | device kernels %.1f..%.1f d2h ..%.1f\n",
+                    k, (int)(J.lane - g->lanes), J.slot, J.reqs[0].is_scan ? "scan  " : "render", J.t_start - h0, J.t_planned - h0,
+                    J.t_submitted - h0, J.dev_t0, J.dev_t1, J.dev_tdone);
+        }
+    }
+    // whole-call figures: device time from the first job's start to the last job's end (all lanes)
     float span = 0.0f;
-    for (int li = 0; li < 2; ++li) if (used[li]) { float v = 0.0f; cudaEventElapsedTime(&v, g->ev_batch0, g->ev_batch1[li]); span = std::max(span, v); }
+    for (int li = 0; li < kLanes; ++li) if (used[li]) { float v = 0.0f; cudaEventElapsedTime(&v, g->ev_batch0, g->ev_batch1[li]); span = std::max(span, v); }
+    { cudaStreamSynchronize(g->copy_stream); float v = 0.0f; if (cudaEventElapsedTime(&v, g->ev_batch0, g->ev_copy_end) == cudaSuccess) span = std::max(span, v); else cudaGetLastError(); }
     PassStats tot;
     for (PassJob& J : jobs) {
         const Ctx* x = J.reqs[0].c;          // every context of a job carries the job's figures
@@ -1293,7 +1409,7 @@ static int run_pass_pipelined(std::vector<PassReq>& reqs) {
     const size_t n_groups = (reqs.size() + group - 1) / group;
     std::vector<PassJob> jobs(n_groups);
     for (size_t i = 0; i < reqs.size(); ++i) jobs[i / group].reqs.push_back(std::move(reqs[i]));
-    for (size_t k = 0; k < n_groups; ++k) { jobs[k].lane = &g->lanes[k & 1]; jobs[k].slot = (int)((k >> 1) & 1); }
+    for (size_t k = 0; k < n_groups; ++k) { jobs[k].lane = &g->lanes[k % g->n_lanes]; jobs[k].slot = (int)((k / g->n_lanes) % kSlots); }
     PassStats tot; KStat ks[KC_COUNT];
     const int rc = run_jobs_pipelined(g, jobs, &tot, ks);
     if (rc == TDG_OK) publish_batch_stats(jobs, tot, ks);
@@ -1310,17 +1426,36 @@ static int run_scan_render_pipelined(std::vector<PassReq>& scans, std::vector<Pa
     for (auto& r : renders) if (r.c->eng != g) return r.c->fail(TDG_ERR_INVALID, "all contexts of a batch must be on one device");
     cudaSetDevice(g->device);
     const size_t group = g->pipeline_group ? g->pipeline_group : renders.size();
-    const size_t n_groups = (renders.size() + group - 1) / group;
+    // group boundaries: full groups, then a geometric taper (G/2, G/4, ... >= 8 projects): what is left after
+    // the last kernel is only the last group's PCM crossing PCIe, so the last groups are made small
+    std::vector<size_t> start;                 // first project of every group, plus the end
+    {
+        const size_t n = renders.size(), floor_sz = std::min<size_t>(8, group);
+        size_t at = 0;
+        while (at < n) {
+            start.push_back(at);
+            const size_t rem = n - at;
+            size_t sz = group;
+            if (g->taper && rem <= 2 * group) sz = std::max(floor_sz, std::min(group, (rem + 1) / 2));
+            at += std::min(sz, rem);
+        }
+        start.push_back(n);
+    }
+    const size_t n_groups = start.size() - 1;
     std::vector<PassJob> jobs(n_groups * 2);
-    for (size_t i = 0; i < renders.size(); ++i) {
-        const size_t gi = i / group;
+    for (size_t gi = 0; gi < n_groups; ++gi) for (size_t i = start[gi]; i < start[gi + 1]; ++i) {
         if (scans[i].c->output >= 0) jobs[2 * gi].reqs.push_back(std::move(scans[i]));     // graph.rs:225: no output, no scan
         jobs[2 * gi + 1].reqs.push_back(std::move(renders[i]));
     }
-    for (size_t k = 0; k < jobs.size(); ++k) { jobs[k].lane = &g->lanes[(k >> 1) & 1]; jobs[k].slot = (int)(k & 1); }
     std::vector<PassJob> live;
     live.reserve(jobs.size());
-    for (PassJob& J : jobs) if (!J.reqs.empty()) live.push_back(std::move(J));
+    int next_slot[kLanes] = {};
+    for (size_t k = 0; k < jobs.size(); ++k) {
+        if (jobs[k].reqs.empty()) continue;
+        const int li = (int)((k >> 1) % g->n_lanes);
+        jobs[k].lane = &g->lanes[li]; jobs[k].slot = next_slot[li]++ % kSlots;       // ring: a slot is reused kSlots passes later
+        live.push_back(std::move(jobs[k]));
+    }
     PassStats tot; KStat ks[KC_COUNT];
     const int rc = run_jobs_pipelined(g, live, &tot, ks);
     if (rc == TDG_OK) publish_batch_stats(live, tot, ks);
@@ -1503,6 +1638,26 @@ int tdg_graph_reset(tdg_ctx* h) {                                           // g
     return TDG_OK;
 }
 
+static void vstate_init(float* st, int kind) {
+    for (int i = 0; i < 8; ++i) st[i] = 0.0f;
+    if (kind != K_NORMALIZE) { st[0] = -1.0f; st[1] = -1.0f; }
+}
+int tdg_reset_vertex_state(tdg_ctx* h) {                                    // state.rs:328-457 on an unchanged project
+    Ctx* c = C_;
+    c->vstate_host.assign(c->verts.size() * 8, 0.0f);
+    for (size_t i = 0; i < c->verts.size(); ++i) {
+        HVertex& v = c->verts[i];
+        v.loop_t = 0; v.ts.clear(); v.countdown = 0; v.primary = {0, 0.0f}; v.ghost = {0, 0.0f};
+        v.dnotes.clear(); v.notes.clear(); v.seq = 0;
+        v.aprimary = {0, 0, 0}; v.aghost = {0, 0, 0};
+        v.bp_first = true;
+        vstate_init(&c->vstate_host[i * 8], v.kind);
+    }
+    c->vstate_host_newer = true;         // the device copy is stale; no read-back needed
+    c->t = 0;
+    return TDG_OK;
+}
+
 static int add_vertex(Ctx* c, HVertex v, float gain, float angle, float wet) {
     v.gain = gain;
     v.angle = fmaxf(fminf(angle, 90.0f), -90.0f);                           // graph.rs:255
@@ -1510,9 +1665,7 @@ static int add_vertex(Ctx* c, HVertex v, float gain, float angle, float wet) {
     if (vstate_to_host(c) != TDG_OK) return TDG_ERR_CUDA;
     c->verts.push_back(std::move(v));
     c->vstate_host.resize(c->verts.size() * 8, 0.0f);
-    float* st = &c->vstate_host[(c->verts.size() - 1) * 8];
-    for (int i = 0; i < 8; ++i) st[i] = 0.0f;
-    if (c->verts.back().kind != K_NORMALIZE) { st[0] = -1.0f; st[1] = -1.0f; }
+    vstate_init(&c->vstate_host[(c->verts.size() - 1) * 8], c->verts.back().kind);
     c->vstate_host_newer = true;
     return (int)c->verts.size() - 1;
 }

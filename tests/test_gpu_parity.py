@@ -176,3 +176,26 @@ def test_unsupported_and_errors(gpulib):
         c.add_adsr(1.0, 0.0, 1.0, c.floww_add([], [], []), False, True, -1, [1, 2, 3])
     assert e.value.code == -4
     c.close()
+
+
+def test_refresh_cycle_is_idempotent(gpulib, oracle):
+    """refresh -> scan -> render twice on one context: with tdg_reset_vertex_state in between (what
+    State::refresh does to an unchanged project, state.rs:328-467) the second render is byte-identical to
+    the first and to the oracle's fresh render; without it vertex state leaks and the two
+    differ for a graph with stateful vertices."""
+    from termdaw_b200.state import State
+    p, a, s = S.config_5_project(3, 0.1)
+    want = run_project(oracle, p, a, s, taps=False)
+    st = State(gpulib, s["psr"], s["bl"], assets=a)
+    assert st.refresh(p), st.messages
+    st.scan_exact()
+    first = st.render().copy()
+    st.ctx.reset_vertex_state()
+    st.ctx.floww_set_time(0)
+    st.ctx.reset_normalize()
+    st.scan_exact()
+    second = st.render().copy()
+    assert np.array_equal(first, second)
+    x, y = pcm_to_int(first, st.bd), pcm_to_int(want["pcm"], want["bd"])
+    assert x.shape == y.shape and np.abs(x - y).max() <= 1
+    st.close()
