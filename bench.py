@@ -227,7 +227,7 @@ def run_reference(args, rank: int):
             times.append(dt); frames = fr
     dt = sum(times) / len(times)
     v = frames / dt
-    print(json.dumps({
+    print_line(json.dumps({
         "impl": "reference", "metric": "rendered frames/sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -357,8 +357,20 @@ class TimeShardRunner:
             st.close()
 
 
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Native libraries print there too (NCCL announces its version on
+    the first communicator), so fd 1 is pointed at stderr for the run and the line goes to the saved fd."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
     args = parse()
+    out = _claim_stdout()
+    global print_line
+    print_line = lambda s: (out.write(s + "\n"), out.flush())      # noqa: E731
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -487,7 +499,7 @@ def main():
             line["cpu_baseline"] = {"value": fr / dt, "unit": "frames/s", "cores": 1, "kind": "port",
                                     "sample": sample + f" ({dt:.1f} s of CPU work; restatement of the reference, not the Rust build)",
                                     "host_cores_available": os.cpu_count()}
-        print(json.dumps(line))
+        print_line(json.dumps(line))
     R.close()
     if dist is not None:
         dist.destroy_process_group()
