@@ -849,6 +849,7 @@ static int pass_plan(PassJob& J) {
             auto fx_task = [&](uint32_t mode) {
                 FxTask t; memset(&t, 0, sizeof t);
                 t.h = h; t.mode = mode; t.n_in = (uint32_t)hv.edges.size(); t.in_off = in_off; t.sr = x->sr;
+                if (hv.edges.size() <= (size_t)kInlineInputs) memcpy(t.ins, B.at<const float*>(in_off), hv.edges.size() * 2 * sizeof(float*));
                 t.fsr = (float)x->sr; t.rsr = 1.0f / t.fsr;
                 return t;
             };
@@ -909,6 +910,7 @@ static int pass_plan(PassJob& J) {
                     }
                     BpTask t; memset(&t, 0, sizeof t);
                     t.h = h; t.n_in = (uint32_t)hv.edges.size(); t.in_off = in_off; t.pass = hv.pass;
+                    if (hv.edges.size() <= (size_t)kInlineInputs) memcpy(t.ins, B.at<const float*>(in_off), hv.edges.size() * 2 * sizeof(float*));
                     t.lgamma = hv.lgamma; t.hgamma = hv.hgamma;
                     // a segment that does not start at the pass start has no true state: seed from its first frame
                     t.first = (hv.bp_first || r.emit0 > 0) ? 1u : 0u;
@@ -942,6 +944,18 @@ static int pass_plan(PassJob& J) {
                     t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.n_hits = (uint32_t)mhits.size();
                     t.hits_off = B.alloc(std::max<size_t>(mhits.size(), 1) * sizeof(MultiHit));
                     memcpy(B.at<uint8_t>(t.hits_off), mhits.data(), mhits.size() * sizeof(MultiHit));
+                    {   // per chunk: hits with start in (p0 - L, p0 + bl - 1]; both bounds only move forward
+                        t.range_off = B.alloc(std::max<uint64_t>(r.emit_n, 1) * 8);
+                        uint32_t* rg = B.at<uint32_t>(t.range_off);
+                        size_t lo = 0, hi = 0;
+                        for (uint64_t k = 0; k < r.emit_n; ++k) {
+                            const int64_t c0 = (int64_t)(k * x->bl);
+                            while (lo < mhits.size() && mhits[lo].start <= c0 - (int64_t)s.frames) ++lo;
+                            if (hi < lo) hi = lo;
+                            while (hi < mhits.size() && mhits[hi].start <= c0 + (int64_t)x->bl - 1) ++hi;
+                            rg[2 * k] = (uint32_t)lo; rg[2 * k + 1] = (uint32_t)hi;
+                        }
+                    }
                     LT.multi.v.push_back(t); LT.multi.max_chunks = std::max(LT.multi.max_chunks, nch);
                     uint64_t gathered = 0;                                        // live hit-frames inside the emitted range
                     for (const MultiHit& mh : mhits) {
@@ -958,6 +972,16 @@ static int pass_plan(PassJob& J) {
                     t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.n_hits = (uint32_t)lhits.size(); t.lerp_len = hv.lerp_len;
                     t.hits_off = B.alloc(lhits.size() * sizeof(LerpHit));
                     memcpy(B.at<uint8_t>(t.hits_off), lhits.data(), lhits.size() * sizeof(LerpHit));
+                    {   // per chunk: last hit with frame <= first frame of the chunk (entries 0 and 1 are the carried pair)
+                        t.base_off = B.alloc(std::max<uint64_t>(r.emit_n, 1) * 4);
+                        uint32_t* bs = B.at<uint32_t>(t.base_off);
+                        size_t a = 0;
+                        for (uint64_t k = 0; k < r.emit_n; ++k) {
+                            const int64_t c0 = (int64_t)(k * x->bl);
+                            while (a < lhits.size() && lhits[a].frame <= c0) ++a;
+                            bs[k] = (uint32_t)(a - 1);
+                        }
+                    }
                     LT.lerp.v.push_back(t); LT.lerp.max_chunks = std::max(LT.lerp.max_chunks, nch);
                     algo += 16ull * r.n_frames; LT.lerp.bytes += 16ull * r.n_frames;
                     break;
@@ -1025,7 +1049,8 @@ static int pass_plan(PassJob& J) {
                 q.in_l = ol + skip; q.in_r = orr + skip; q.n = r.out_frames;
                 q.runmax = fused_runmax; q.frame0 = skip; q.bl = x->bl; q.pg = fused_pg;
             }
-            quants.push_back(q); quant_max = std::max(quant_max, q.n);
+            q.span = q.runmax ? x->bl : 1024u; q.chunk0 = q.runmax ? (uint32_t)(q.frame0 / x->bl) : 0u;
+            quants.push_back(q); quant_max = std::max<uint64_t>(quant_max, (q.n + q.span - 1) / q.span);   // blocks
             algo += 8ull * q.n + r.pcm_bytes; quant_bytes += 8ull * q.n + r.pcm_bytes;
         }
         x->stats.algorithmic_bytes = algo; x->stats.frames = r.n_frames;
@@ -1069,8 +1094,8 @@ static int pass_plan(PassJob& J) {
                 for (FxTask& t : S.fx.v) t.in_off += b;
                 for (FxTask& t : S.fx_adsr.v) { t.in_off += b; t.seg_ptr_off += b; t.seg_off += b; }
                 for (FxTask& t : S.fx_norm.v) t.in_off += b;
-                for (MultiTask& t : S.multi.v) t.hits_off += b;
-                for (LerpTask& t : S.lerp.v) t.hits_off += b;
+                for (MultiTask& t : S.multi.v) { t.hits_off += b; t.range_off += b; }
+                for (LerpTask& t : S.lerp.v) { t.hits_off += b; t.base_off += b; }
                 for (VoiceTask& t : S.dsine.v) { t.seg_ptr_off += b; t.seg_off += b; }
                 for (VoiceTask& t : S.synth.v) { t.seg_ptr_off += b; t.seg_off += b; }
                 for (VoiceTask& t : S.sampsyn.v) { t.seg_ptr_off += b; t.seg_off += b; }

@@ -89,10 +89,15 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
     return 1.0f + T.wet * (adsr_vel - 1.0f);             // lerp(1.0, adsr_vel, wet)
 }
 
+#ifndef TDG_ADSR_MINB
+#define TDG_ADSR_MINB 5      // measured: 4 -> 9.0 ms, 5 -> 8.3 ms, 6 -> 8.5 ms per bench step
+#endif
+#ifndef TDG_BP_MINB
+#define TDG_BP_MINB 5        // measured: 4 -> 6.66 ms, 5 -> 6.48 ms, 6 -> 6.95 ms
+#endif
 template <int MODE, bool VEC, bool EXACT>
-__global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ FxTask T;
-    __shared__ const float* s_in[16];
     __shared__ AdsrSeg s_seg[MODE == FX_ADSR ? TDG_FX_SEGS : 1];
     load_task(&T, tasks + blockIdx.y);
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
@@ -100,37 +105,20 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(con
     if (k >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
     const uint64_t p0 = (uint64_t)k * bl;
-    const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
-    const bool staged = T.n_in <= 8;
-    const AdsrSeg* segs = nullptr;
-    uint32_t n_seg = 0;
-    float maxmul = 0.0f, minmul = 0.0f;
-    if (MODE == FX_ADSR) {
-        const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
-        const uint32_t s_lo = sp[k];
-        n_seg = sp[k + 1] - s_lo;
-        segs = reinterpret_cast<const AdsrSeg*>(blob + T.seg_off) + s_lo;
-        maxmul = T.use_max ? 1.0f : 0.0f; minmul = 1.0f - maxmul;
-        if (n_seg <= TDG_FX_SEGS) {                      // chunk's envelope states into shared memory
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(segs);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(s_seg);
-            for (uint32_t w = threadIdx.x; w < n_seg * (uint32_t)(sizeof(AdsrSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
-            segs = s_seg;
-        }
-    }
-    if (staged && threadIdx.x < 2 * T.n_in) s_in[threadIdx.x] = ins[threadIdx.x];   // no dependent global load per input
-    if (staged || MODE == FX_ADSR) __syncthreads();
-    float peak = 0.0f;
-    for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
+    const bool staged = T.n_in <= (uint32_t)kInlineInputs;     // input pointers arrived with the task (shared memory)
+    const float* const* ins = staged ? T.ins : reinterpret_cast<const float* const*>(blob + T.in_off);
+    // sum_inputs for the four frames at chunk offset i (edge order: the f32 sum is order dependent)
+    auto load_sum = [&](uint32_t i, float (&l)[4], float (&r)[4]) {
         const int nv = min(4u, bl - i);
         const uint64_t p = p0 + i;
-        float l[4] = {0.0f, 0.0f, 0.0f, 0.0f}, r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { l[j] = 0.0f; r[j] = 0.0f; }
         if (staged) {
 #pragma unroll 2
             for (uint32_t a = 0; a < T.n_in; ++a) {
                 float x[4], y[4];
-                ld4<VEC>(s_in[2 * a], p, nv, x);
-                ld4<VEC>(s_in[2 * a + 1], p, nv, y);
+                ld4<VEC>(T.ins[2 * a], p, nv, x);
+                ld4<VEC>(T.ins[2 * a + 1], p, nv, y);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { l[j] += x[j]; r[j] += y[j]; }
             }
@@ -143,6 +131,36 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(con
                 for (int j = 0; j < 4; ++j) { l[j] += x[j]; r[j] += y[j]; }
             }
         }
+    };
+    float l[4], r[4];
+    const uint32_t i_first = threadIdx.x * 4;
+    bool have = false;
+    const AdsrSeg* segs = nullptr;
+    uint32_t n_seg = 0;
+    float maxmul = 0.0f, minmul = 0.0f;
+    if (MODE == FX_ADSR) {
+        // the chunk's envelope states are fetched (segment pointers -> states -> shared memory) while the
+        // audio loads of the first run are already in flight: both chains start right after the task load
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
+        const uint32_t s_lo = sp[k];
+        n_seg = sp[k + 1] - s_lo;
+        if (i_first < bl) { load_sum(i_first, l, r); have = true; }
+        segs = reinterpret_cast<const AdsrSeg*>(blob + T.seg_off) + s_lo;
+        maxmul = T.use_max ? 1.0f : 0.0f; minmul = 1.0f - maxmul;
+        if (n_seg <= TDG_FX_SEGS) {                      // chunk's envelope states into shared memory
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(segs);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(s_seg);
+            for (uint32_t w = threadIdx.x; w < n_seg * (uint32_t)(sizeof(AdsrSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
+            segs = s_seg;
+        }
+        __syncthreads();
+    }
+    float peak = 0.0f;
+    for (uint32_t i = i_first; i < bl; i += TDG_THREADS * 4) {
+        const int nv = min(4u, bl - i);
+        const uint64_t p = p0 + i;
+        if (!have) load_sum(i, l, r);
+        have = false;
         if (MODE == FX_ADSR) {
             // last segment starting at or before the thread's first frame; the common case is that the
             // same state covers all four frames
@@ -152,25 +170,39 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? 4 : 6) k_fx(con
             if (one) {
                 const AdsrSeg sg = segs[s];
                 if (!(sg.flags & 1u)) {
-                    float tp[4], tg[4], ep[4], eg[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float offset = k_div<EXACT>((float)(i + j), T.fsr, T.rsr);
-                        tp[j] = sg.pt + offset; tg[j] = sg.gt + offset;
-                    }
-                    if (T.use_off) {                     // extensions.rs:620-623
-                        if (sg.pr == 0.0f) k_apply_ads_n<EXACT, 4>(T.conf, tp, ep); else k_apply_r_n<EXACT, 4>(T.conf, tp, sg.pr, ep);
-                        if (sg.gr == 0.0f) k_apply_ads_n<EXACT, 4>(T.conf, tg, eg); else k_apply_r_n<EXACT, 4>(T.conf, tg, sg.gr, eg);
-                    } else {                             // extensions.rs:640-641
-                        k_apply_adsr_n<EXACT, 4>(T.conf, tp, ep);
-                        k_apply_adsr_n<EXACT, 4>(T.conf, tg, eg);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float pvel = ep[j] * sg.pv, gvel = eg[j] * sg.gv;
+                    // plateau test on the run's first frame only: most runs sit between two hits with both
+                    // envelopes finished (or held), and then the whole run has one gain
+                    const float o0 = k_div<EXACT>((float)i, T.fsr, T.rsr);
+                    const int pm = T.use_off ? (sg.pr == 0.0f ? 1 : 2) : 0, gm = T.use_off ? (sg.gr == 0.0f ? 1 : 2) : 0;
+                    float pval, gval;
+                    if (k_env_plateau<EXACT>(T.conf, pm, sg.pr, sg.pt + o0, &pval) &&
+                        k_env_plateau<EXACT>(T.conf, gm, sg.gr, sg.gt + o0, &gval)) {
+                        const float pvel = pval * sg.pv, gvel = gval * sg.gv;
                         const float adsr_vel = fmaxf(pvel, gvel) * maxmul + fminf(pvel, gvel) * minmul;
                         const float vel = 1.0f + T.wet * (adsr_vel - 1.0f);      // lerp(1.0, adsr_vel, wet)
-                        l[j] *= vel; r[j] *= vel;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { l[j] *= vel; r[j] *= vel; }
+                    } else {
+                        float tp[4], tg[4], ep[4], eg[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float offset = k_div<EXACT>((float)(i + j), T.fsr, T.rsr);
+                            tp[j] = sg.pt + offset; tg[j] = sg.gt + offset;
+                        }
+                        if (T.use_off) {                     // extensions.rs:620-623
+                            if (sg.pr == 0.0f) k_apply_ads_n<EXACT, 4>(T.conf, tp, ep); else k_apply_r_n<EXACT, 4>(T.conf, tp, sg.pr, ep);
+                            if (sg.gr == 0.0f) k_apply_ads_n<EXACT, 4>(T.conf, tg, eg); else k_apply_r_n<EXACT, 4>(T.conf, tg, sg.gr, eg);
+                        } else {                             // extensions.rs:640-641
+                            k_apply_adsr_n<EXACT, 4>(T.conf, tp, ep);
+                            k_apply_adsr_n<EXACT, 4>(T.conf, tg, eg);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float pvel = ep[j] * sg.pv, gvel = eg[j] * sg.gv;
+                            const float adsr_vel = fmaxf(pvel, gvel) * maxmul + fminf(pvel, gvel) * minmul;
+                            const float vel = 1.0f + T.wet * (adsr_vel - 1.0f);      // lerp(1.0, adsr_vel, wet)
+                            l[j] *= vel; r[j] *= vel;
+                        }
                     }
                 }
             } else {
@@ -316,23 +348,29 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* _
     const uint32_t bl = T.h.bl;
     const int64_t p0 = (int64_t)k * bl;
     const MultiHit* hits = reinterpret_cast<const MultiHit*>(blob + T.hits_off);
-    // candidates for this chunk: start > p0 - L  and  start <= p0 + bl - 1
-    uint32_t lo = 0, hi = T.n_hits;
-    { uint32_t a = 0, b = T.n_hits; const int64_t key = p0 - (int64_t)T.len;
-      while (a < b) { uint32_t m = (a + b) >> 1; if (hits[m].start > key) b = m; else a = m + 1; } lo = a; }
-    { uint32_t a = lo, b = T.n_hits; const int64_t key = p0 + (int64_t)bl - 1;
-      while (a < b) { uint32_t m = (a + b) >> 1; if (hits[m].start > key) b = m; else a = m + 1; } hi = a; }
+    // candidates for this chunk: start > p0 - L  and  start <= p0 + bl - 1 (range table from the host planner)
+    const uint2 rg = reinterpret_cast<const uint2*>(blob + T.range_off)[k];
+    const uint32_t lo = rg.x, hi = rg.y;
+    const int64_t len = (int64_t)T.len;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
         const int nv = min(4u, bl - i);
         float l[4] = {0.0f, 0.0f, 0.0f, 0.0f}, r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (uint32_t h = lo; h < hi; ++h) {
-            const int64_t start = hits[h].start; const float vel = hits[h].vel;
+            const int64_t base = p0 + i - hits[h].start;          // sample position of the thread's first frame
+            const float vel = hits[h].vel;
+            if (base >= 0 && base + 3 < len) {                    // the hit covers all four frames: no per-frame tests
+                const float* __restrict__ pl = T.sl + base;
+                const float* __restrict__ pr = T.sr + base;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int64_t pos = p0 + i + j - start;
-                if (pos >= 0 && pos < (int64_t)T.len) {
-                    l[j] += __ldg(T.sl + pos) * vel;
-                    r[j] += __ldg(T.sr + pos) * vel;
+                for (int j = 0; j < 4; ++j) { l[j] += __ldg(pl + j) * vel; r[j] += __ldg(pr + j) * vel; }
+            } else if (base + 3 >= 0 && base < len) {             // starts or ends inside the run
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t pos = base + j;
+                    if (pos >= 0 && pos < len) {
+                        l[j] += __ldg(T.sl + pos) * vel;
+                        r[j] += __ldg(T.sr + pos) * vel;
+                    }
                 }
             }
         }
@@ -354,35 +392,57 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
     const uint32_t bl = T.h.bl;
     const int64_t p0 = (int64_t)k * bl;
     const LerpHit* hits = reinterpret_cast<const LerpHit*>(blob + T.hits_off);
-    // index of the last hit with frame <= p0 (entries 0 and 1 are the carried ghost / primary)
-    uint32_t base;
-    { uint32_t a = 0, b = T.n_hits;
-      while (a < b) { uint32_t m = (a + b) >> 1; if (hits[m].frame > p0) b = m; else a = m + 1; } base = a - 1; }
+    // index of the last hit with frame <= p0 (entries 0 and 1 are the carried ghost / primary); host table
+    const uint32_t base = reinterpret_cast<const uint32_t*>(blob + T.base_off)[k];
     const int64_t lm1 = (int64_t)T.len - 1;
+    const int64_t lerp_len = (int64_t)T.lerp_len;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
         const int nv = min(4u, bl - i);
         float l[4], r[4];
         uint32_t idx = base;
+        const int64_t pf = p0 + i;
+        while (idx + 1 < T.n_hits && hits[idx + 1].frame <= pf) ++idx;
+        const bool one = idx + 1 >= T.n_hits || hits[idx + 1].frame > pf + 3;     // one primary for the whole run
+        const LerpHit P0 = hits[idx];
+        const int64_t pp0 = pf - P0.pos_origin;
+        const int64_t cb0 = lerp_len - (pf - P0.cd_origin);                       // countdown before frame 0 of the run
+        if (one && cb0 <= 0 && (pp0 >= lm1 || (pp0 >= 0 && pp0 + 3 <= lm1))) {
+            // the common run: no hit inside it, cross-fade over; the sample is either being played straight
+            // through or has ended (clamped to its last frame)
+            if (pp0 >= lm1) {
+                const float lv = __ldg(T.sl + lm1) * P0.vel, rv = __ldg(T.sr + lm1) * P0.vel;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t p = p0 + i + j;
-            while (idx + 1 < T.n_hits && hits[idx + 1].frame <= p) ++idx;
-            const LerpHit P = hits[idx];
-            const int64_t ppos = min(max(p - P.pos_origin, (int64_t)0), lm1);
-            float lv = __ldg(T.sl + ppos) * P.vel;
-            float rv = __ldg(T.sr + ppos) * P.vel;
-            const int64_t c_before = (int64_t)T.lerp_len - (p - P.cd_origin);
-            if (c_before > 0) {
-                const LerpHit G = hits[idx - 1];
-                const float t = (float)(c_before - 1) / (float)T.lerp_len;
-                const int64_t gpos = min(max(p - G.pos_origin, (int64_t)0), lm1);
-                const float gl = __ldg(T.sl + gpos) * G.vel;
-                const float gr = __ldg(T.sr + gpos) * G.vel;
-                lv = gl * t + lv * (1.0f - t);
-                rv = gr * t + rv * (1.0f - t);
+                for (int j = 0; j < 4; ++j) { l[j] = lv; r[j] = rv; }
+            } else {
+                const float* __restrict__ pl = T.sl + pp0;
+                const float* __restrict__ pr = T.sr + pp0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { l[j] = __ldg(pl + j) * P0.vel; r[j] = __ldg(pr + j) * P0.vel; }
             }
-            apply_pg(lv, rv, T.h.pg);
-            l[j] = lv; r[j] = rv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) apply_pg(l[j], r[j], T.h.pg);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t p = pf + j;
+                while (idx + 1 < T.n_hits && hits[idx + 1].frame <= p) ++idx;
+                const LerpHit P = hits[idx];
+                const int64_t ppos = min(max(p - P.pos_origin, (int64_t)0), lm1);
+                float lv = __ldg(T.sl + ppos) * P.vel;
+                float rv = __ldg(T.sr + ppos) * P.vel;
+                const int64_t c_before = lerp_len - (p - P.cd_origin);
+                if (c_before > 0) {
+                    const LerpHit G = hits[idx - 1];
+                    const float t = (float)(c_before - 1) / (float)T.lerp_len;
+                    const int64_t gpos = min(max(p - G.pos_origin, (int64_t)0), lm1);
+                    const float gl = __ldg(T.sl + gpos) * G.vel;
+                    const float gr = __ldg(T.sr + gpos) * G.vel;
+                    lv = gl * t + lv * (1.0f - t);
+                    rv = gr * t + rv * (1.0f - t);
+                }
+                apply_pg(lv, rv, T.h.pg);
+                l[j] = lv; r[j] = rv;
+            }
         }
         st4<VEC>(T.h.out_l, (uint64_t)p0 + i, nv, l);
         st4<VEC>(T.h.out_r, (uint64_t)p0 + i, nv, r);
@@ -650,7 +710,7 @@ __global__ void __launch_bounds__(kBpThreads) k_bp_aggregate(const BpTask* __res
     __shared__ BpTask T;
     load_task(&T, tasks + blockIdx.y);
     if (blockIdx.x >= T.n_tiles) return;
-    const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
+    const float* const* ins = T.n_in <= (uint32_t)kInlineInputs ? T.ins : reinterpret_cast<const float* const*>(blob + T.in_off);
     const uint64_t p = (uint64_t)blockIdx.x * kBpTile + (uint64_t)threadIdx.x * 8;
     const int nv = p >= T.h.n_frames ? 0 : (int)min((uint64_t)8, T.h.n_frames - p);
     float xl[8], xr[8];
@@ -737,11 +797,11 @@ __global__ void __launch_bounds__(kBpThreads) k_bp_carry(const BpTask* __restric
 }
 // pass C: exact recurrence from the carried-in state + cut/pass mix + pan + gain
 template <bool VEC>
-__global__ void __launch_bounds__(kBpThreads) k_bp_apply(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(kBpThreads, TDG_BP_MINB) k_bp_apply(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ BpTask T;
     load_task(&T, tasks + blockIdx.y);
     if (blockIdx.x >= T.n_tiles) return;
-    const float* const* ins = reinterpret_cast<const float* const*>(blob + T.in_off);
+    const float* const* ins = T.n_in <= (uint32_t)kInlineInputs ? T.ins : reinterpret_cast<const float* const*>(blob + T.in_off);
     const uint64_t p = (uint64_t)blockIdx.x * kBpTile + (uint64_t)threadIdx.x * 8;
     const int nv = p >= T.h.n_frames ? 0 : (int)min((uint64_t)8, T.h.n_frames - p);
     float xl[8], xr[8];
@@ -790,70 +850,98 @@ __device__ __forceinline__ int quant16(float x, float amp) {
     int v = __float2int_rz(x * amp);
     return max(-32768, min(32767, v));
 }
-__global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __restrict__ tasks) {
-    const QuantTask T = tasks[blockIdx.y];
-    const uint64_t f0 = ((uint64_t)blockIdx.x * TDG_THREADS + threadIdx.x) * 4;
-    if (f0 >= T.n) return;
-    const int nv = (int)min((uint64_t)4, T.n - f0);
-    int v[8];
-    bool wide = false;
-    uint32_t kc = 0, rem = 0;
-    if (T.runmax) { const uint64_t pf = T.frame0 + f0; kc = (uint32_t)(pf / T.bl); rem = (uint32_t)(pf - (uint64_t)kc * T.bl); }
+// A block = `span` consecutive output frames of one task: one chunk when the output Normalize's scale is
+// fused in (its 1/max is then a per-block constant), 1024 frames otherwise.  The bit depth and the fused
+// flag are block-uniform, so the body is compiled once per (depth, fused) pair and picked by one switch.
+template <int BD, bool FUSED>
+__device__ __forceinline__ void quantise_block(const QuantTask& T, uint64_t b0, uint32_t span, float f, bool& wide) {
+    const bool vec_in = ((reinterpret_cast<uintptr_t>(T.in_l + b0) | reinterpret_cast<uintptr_t>(T.in_r + b0)) & 15) == 0;
+    for (uint32_t i = threadIdx.x * 4; i < span; i += TDG_THREADS * 4) {
+        const uint64_t f0 = b0 + i;
+        if (f0 >= T.n) break;
+        const int nv = (int)min((uint64_t)4, min((uint64_t)(span - i), T.n - f0));
+        float l[4], r[4];
+        if (nv == 4 && vec_in) {
+            const float4 a = *reinterpret_cast<const float4*>(T.in_l + f0), b = *reinterpret_cast<const float4*>(T.in_r + f0);
+            l[0] = a.x; l[1] = a.y; l[2] = a.z; l[3] = a.w; r[0] = b.x; r[1] = b.y; r[2] = b.z; r[3] = b.w;
+        } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float l = j < nv ? T.in_l[f0 + j] : 0.0f, r = j < nv ? T.in_r[f0 + j] : 0.0f;
-        if (T.runmax) {                                   // fused normalize_gen scale + pan + gain of the output vertex
-            const float f = 1.0f / T.runmax[kc + (rem + j >= T.bl ? 1u : 0u)];
-            l *= f; r *= f;
-            apply_pg(l, r, T.pg);
+            for (int j = 0; j < 4; ++j) { l[j] = j < nv ? T.in_l[f0 + j] : 0.0f; r[j] = j < nv ? T.in_r[f0 + j] : 0.0f; }
         }
-        if (T.bd <= 16) { v[2 * j] = quant16(l, T.amp); v[2 * j + 1] = quant16(r, T.amp); }
-        else { v[2 * j] = __float2int_rz(l * T.amp); v[2 * j + 1] = __float2int_rz(r * T.amp); }
-    }
-    if (T.bd == 8) {
-        uint8_t* o = T.out + f0 * 2;
-        uint32_t w[2] = {0, 0};
+        int v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            wide |= (v[q] < -128 || v[q] > 127);
-            w[q >> 2] |= (uint32_t)((v[q] + 128) & 0xff) << (8 * (q & 3));
+        for (int j = 0; j < 4; ++j) {
+            if (FUSED) { l[j] *= f; r[j] *= f; apply_pg(l[j], r[j], T.pg); }   // x * (1/max), pan, gain (extensions.rs:328,262-263)
+            if (BD <= 16) { v[2 * j] = quant16(l[j], T.amp); v[2 * j + 1] = quant16(r[j], T.amp); }
+            else { v[2 * j] = __float2int_rz(l[j] * T.amp); v[2 * j + 1] = __float2int_rz(r[j] * T.amp); }
         }
-        if (nv == 4) *reinterpret_cast<uint2*>(o) = make_uint2(w[0], w[1]);
-        else for (int q = 0; q < nv * 2; ++q) o[q] = (uint8_t)((v[q] + 128) & 0xff);
-    } else if (T.bd == 16) {
-        uint8_t* o = T.out + f0 * 4;
-        uint32_t w[4];
+        if (BD == 8) {
+            uint8_t* o = T.out + f0 * 2;
+            uint32_t w[2] = {0, 0};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w[q] = (uint32_t)(v[2 * q] & 0xffff) | ((uint32_t)(v[2 * q + 1] & 0xffff) << 16);
-        if (nv == 4) *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-        else for (int q = 0; q < nv; ++q) reinterpret_cast<uint32_t*>(o)[q] = w[q];
-    } else if (T.bd == 24) {
-        uint8_t* o = T.out + f0 * 6;
-        uint8_t b[24];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            wide |= (v[q] < -8388608 || v[q] > 8388607);
-            b[3 * q] = (uint8_t)(v[q] & 0xff); b[3 * q + 1] = (uint8_t)((v[q] >> 8) & 0xff); b[3 * q + 2] = (uint8_t)((v[q] >> 16) & 0xff);
-        }
-        if (nv == 4) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                uint32_t lo = b[8 * q] | (b[8 * q + 1] << 8) | (b[8 * q + 2] << 16) | ((uint32_t)b[8 * q + 3] << 24);
-                uint32_t hi = b[8 * q + 4] | (b[8 * q + 5] << 8) | (b[8 * q + 6] << 16) | ((uint32_t)b[8 * q + 7] << 24);
-                reinterpret_cast<uint2*>(o)[q] = make_uint2(lo, hi);
+            for (int q = 0; q < 8; ++q) {
+                wide |= (v[q] < -128 || v[q] > 127);
+                w[q >> 2] |= (uint32_t)((v[q] + 128) & 0xff) << (8 * (q & 3));
             }
-        } else for (int q = 0; q < nv * 6; ++q) o[q] = b[q];
+            if (nv == 4 && (f0 & 3) == 0) *reinterpret_cast<uint2*>(o) = make_uint2(w[0], w[1]);
+            else for (int q = 0; q < nv * 2; ++q) o[q] = (uint8_t)((v[q] + 128) & 0xff);
+        } else if (BD == 16) {
+            uint8_t* o = T.out + f0 * 4;
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = (uint32_t)(v[2 * q] & 0xffff) | ((uint32_t)(v[2 * q + 1] & 0xffff) << 16);
+            if (nv == 4 && (f0 & 3) == 0) *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+            else for (int q = 0; q < nv; ++q) reinterpret_cast<uint32_t*>(o)[q] = w[q];
+        } else if (BD == 24) {
+            uint8_t* o = T.out + f0 * 6;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) wide |= (v[q] < -8388608 || v[q] > 8388607);
+            // 8 values x 3 little-endian bytes = six 32-bit words, assembled in registers
+            uint32_t u[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) u[q] = (uint32_t)v[q] & 0xffffffu;
+            const uint32_t w0 = u[0] | (u[1] << 24), w1 = (u[1] >> 8) | (u[2] << 16), w2 = (u[2] >> 16) | (u[3] << 8);
+            const uint32_t w3 = u[4] | (u[5] << 24), w4 = (u[5] >> 8) | (u[6] << 16), w5 = (u[6] >> 16) | (u[7] << 8);
+            if (nv == 4 && (f0 & 3) == 0) {                   // 24-byte records at multiples of 4 frames are 8-byte aligned
+                uint2* o2 = reinterpret_cast<uint2*>(o);
+                o2[0] = make_uint2(w0, w1); o2[1] = make_uint2(w2, w3); o2[2] = make_uint2(w4, w5);
+            } else {
+                const uint32_t ww[6] = {w0, w1, w2, w3, w4, w5};
+                for (int q = 0; q < nv * 6; ++q) o[q] = (uint8_t)(ww[q >> 2] >> (8 * (q & 3)));
+            }
+        } else {
+            uint8_t* o = T.out + f0 * 8;
+            if (nv == 4 && (f0 & 1) == 0) {
+                reinterpret_cast<uint4*>(o)[0] = make_uint4((uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]);
+                reinterpret_cast<uint4*>(o)[1] = make_uint4((uint32_t)v[4], (uint32_t)v[5], (uint32_t)v[6], (uint32_t)v[7]);
+            } else for (int q = 0; q < nv * 2; ++q) reinterpret_cast<uint32_t*>(o)[q] = (uint32_t)v[q];
+        }
+    }
+}
+__global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __restrict__ tasks) {
+    __shared__ QuantTask T;
+    load_task(&T, tasks + blockIdx.y);
+    const uint32_t span = T.span;
+    const uint64_t b0 = (uint64_t)blockIdx.x * span;
+    if (b0 >= T.n) return;
+    bool wide = false;
+    if (T.runmax) {
+        const float f = 1.0f / T.runmax[T.chunk0 + blockIdx.x];      // scale(len, 1.0 / max) of this chunk
+        switch (T.bd) {
+            case 8: quantise_block<8, true>(T, b0, span, f, wide); break;
+            case 16: quantise_block<16, true>(T, b0, span, f, wide); break;
+            case 24: quantise_block<24, true>(T, b0, span, f, wide); break;
+            default: quantise_block<32, true>(T, b0, span, f, wide); break;
+        }
     } else {
-        uint8_t* o = T.out + f0 * 8;
-        if (nv == 4) {
-            reinterpret_cast<uint4*>(o)[0] = make_uint4((uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]);
-            reinterpret_cast<uint4*>(o)[1] = make_uint4((uint32_t)v[4], (uint32_t)v[5], (uint32_t)v[6], (uint32_t)v[7]);
-        } else for (int q = 0; q < nv * 2; ++q) reinterpret_cast<uint32_t*>(o)[q] = (uint32_t)v[q];
+        switch (T.bd) {
+            case 8: quantise_block<8, false>(T, b0, span, 1.0f, wide); break;
+            case 16: quantise_block<16, false>(T, b0, span, 1.0f, wide); break;
+            case 24: quantise_block<24, false>(T, b0, span, 1.0f, wide); break;
+            default: quantise_block<32, false>(T, b0, span, 1.0f, wide); break;
+        }
     }
-    if (wide) {
-        // only frames that exist count (padding lanes were zeroed above)
-        atomicOr(T.err, 1u);
-    }
+    if (wide) atomicOr(T.err, 1u);        // hound's TooWide (8/24 bit); padding lanes were zeroed, only real frames count
 }
 
 // ------------------------------------------------------------------------------------ K3: sinc resampler
@@ -1012,9 +1100,8 @@ cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, boo
     TDG_VEC_DISPATCH(vec, k_bp_apply, <<<grid2(max_tiles, n), kBpThreads, 0, s>>>(t, blob));
     return cudaGetLastError();
 }
-cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_frames, cudaStream_t s) {
-    const uint64_t blocks = (max_frames + TDG_THREADS * 4 - 1) / (TDG_THREADS * 4);
-    k_quantise<<<grid2(blocks ? blocks : 1, n), TDG_THREADS, 0, s>>>(t);
+cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s) {
+    k_quantise<<<grid2(max_blocks ? max_blocks : 1, n), TDG_THREADS, 0, s>>>(t);
     return cudaGetLastError();
 }
 cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, const uint8_t* blob, cudaStream_t s) {

@@ -20,7 +20,7 @@ cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_
 cudaError_t launch_bp_aggregate(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_bp_carry(const BpTask* t, uint32_t n, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
-cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_frames, cudaStream_t s);
+cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s);
 cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_deinterleave(const float* lin, uint64_t n_frames, uint32_t stride, uint32_t off_l, uint32_t off_r,
                                 uint32_t mix, float* out_l, float* out_r, cudaStream_t s);

@@ -112,8 +112,10 @@ __device__ __forceinline__ float k_apply_r(const AdsrK& c, float t, float old_va
 // those frames and (for non-exotic envelopes: durations >= 0) so are the thresholds, hence when the
 // first and the last frame sit in the same segment of the envelope all F do: the segment's constants
 // are selected once and the F quotients/lerps are straight-line code that the scheduler can overlap.
+// Return value: true when all F results are one and the same value (sustain plateau, finished release):
+// callers then do the per-frame work that depends on the envelope once instead of F times.
 template <bool EXACT, int F>
-__device__ __forceinline__ void k_apply_ads_n(const AdsrK& c, const float (&t)[F], float (&e)[F]) {
+__device__ __forceinline__ bool k_apply_ads_n(const AdsrK& c, const float (&t)[F], float (&e)[F]) {
     if (!EXACT) {
         const float tf = t[0], tl = t[F - 1];
         const int s0 = (tf <= c.a) ? 0 : (tf <= c.ad) ? 1 : (tf <= c.ads) ? 2 : 3;
@@ -122,7 +124,7 @@ __device__ __forceinline__ void k_apply_ads_n(const AdsrK& c, const float (&t)[F
             if (s0 == 3) {
 #pragma unroll
                 for (int j = 0; j < F; ++j) e[j] = c.v3;
-                return;
+                return true;
             }
             const float sub1 = s0 >= 1 ? c.a : 0.0f, sub2 = s0 == 2 ? c.dsec : 0.0f;    // x - 0.0f == x
             const float d = s0 == 0 ? c.a : s0 == 1 ? c.dsec : c.ssec;
@@ -134,17 +136,47 @@ __device__ __forceinline__ void k_apply_ads_n(const AdsrK& c, const float (&t)[F
                 const float res = base + k_div<false>(t[j] - sub1 - sub2, d, r) * dl;
                 e[j] = res <= -1.0f ? c.v3 : res;
             }
-            return;
+            return false;
         }
     }
 #pragma unroll
     for (int j = 0; j < F; ++j) e[j] = k_apply_ads<EXACT>(c, t[j]);
+    return false;
 }
+// t is non-decreasing over the F frames and (non-exotic) release_sec >= 0, so the quotient is
+// non-decreasing too: once the first frame's quotient has reached 1 the min() clamps all of them and the
+// result is old + 1.0*(v4 - old) for every frame (1.0f * x is x exactly).
 template <bool EXACT, int F>
-__device__ __forceinline__ void k_apply_r_n(const AdsrK& c, const float (&t)[F], float old_val, float (&e)[F]) {
+__device__ __forceinline__ bool k_apply_r_n(const AdsrK& c, const float (&t)[F], float old_val, float (&e)[F]) {
     const float dl = c.v4 - old_val;
+    if (!EXACT) {
+        const float q0 = k_div<false>(t[0], c.rsec, c.rr);
+        if (q0 >= 1.0f) {
+            const float v = old_val + dl;
+#pragma unroll
+            for (int j = 0; j < F; ++j) e[j] = v;
+            return true;
+        }
+        e[0] = old_val + fminf(q0, 1.0f) * dl;
+#pragma unroll
+        for (int j = 1; j < F; ++j) e[j] = old_val + fminf(k_div<false>(t[j], c.rsec, c.rr), 1.0f) * dl;
+        return false;
+    }
 #pragma unroll
     for (int j = 0; j < F; ++j) e[j] = old_val + fminf(k_div<EXACT>(t[j], c.rsec, c.rr), 1.0f) * dl;
+    return false;
+}
+// Is the envelope one constant from env time t0 on (t only grows inside a run of frames)?  True on the
+// sustain plateau of apply_ads and once a release (apply_r / the release leg of apply_adsr) has reached
+// its end value; `val` is then exactly what the per-frame expressions produce there (see k_apply_r_n).
+// mode: 0 apply_adsr, 1 apply_ads, 2 apply_r(old_val).  Never true for exotic envelopes (EXACT).
+template <bool EXACT>
+__device__ __forceinline__ bool k_env_plateau(const AdsrK& c, int mode, float old_val, float t0, float* val) {
+    if (EXACT) return false;
+    if (mode == 1) { *val = c.v3; return !(t0 <= c.ads) && t0 == t0; }
+    if (mode == 2) { *val = old_val + (c.v4 - old_val); return k_div<false>(t0, c.rsec, c.rr) >= 1.0f; }
+    *val = c.v3 + c.d34;
+    return !(t0 <= c.ads) && t0 == t0 && k_div<false>(t0 - c.a - c.dsec - c.ssec, c.rsec, c.rr) >= 1.0f;
 }
 template <bool EXACT>
 __device__ __forceinline__ float k_apply_adsr(const AdsrK& c, float t) {                     // adsr.rs:75-86
@@ -154,17 +186,26 @@ __device__ __forceinline__ float k_apply_adsr(const AdsrK& c, float t) {        
     return res;
 }
 template <bool EXACT, int F>
-__device__ __forceinline__ void k_apply_adsr_n(const AdsrK& c, const float (&t)[F], float (&e)[F]) {
+__device__ __forceinline__ bool k_apply_adsr_n(const AdsrK& c, const float (&t)[F], float (&e)[F]) {
     if (!EXACT) {
         const float tf = t[0], tl = t[F - 1];
         const int s0 = (tf <= c.a) ? 0 : (tf <= c.ad) ? 1 : (tf <= c.ads) ? 2 : 3;
         const int s1 = (tl <= c.a) ? 0 : (tl <= c.ad) ? 1 : (tl <= c.ads) ? 2 : 3;
         if (s0 == s1) {
             if (s0 == 3) {
+                // same monotonicity argument as k_apply_r_n: a finished release is one constant
+                const float q0 = k_div<false>(t[0] - c.a - c.dsec - c.ssec, c.rsec, c.rr);
+                if (q0 >= 1.0f) {
+                    const float v = c.v3 + c.d34;
 #pragma unroll
-                for (int j = 0; j < F; ++j)
+                    for (int j = 0; j < F; ++j) e[j] = v;
+                    return true;
+                }
+                e[0] = c.v3 + fminf(q0, 1.0f) * c.d34;
+#pragma unroll
+                for (int j = 1; j < F; ++j)
                     e[j] = c.v3 + fminf(k_div<false>(t[j] - c.a - c.dsec - c.ssec, c.rsec, c.rr), 1.0f) * c.d34;
-                return;
+                return false;
             }
             const float sub1 = s0 >= 1 ? c.a : 0.0f, sub2 = s0 == 2 ? c.dsec : 0.0f;
             const float d = s0 == 0 ? c.a : s0 == 1 ? c.dsec : c.ssec;
@@ -178,11 +219,12 @@ __device__ __forceinline__ void k_apply_adsr_n(const AdsrK& c, const float (&t)[
                 if (res <= -1.0f)                        // adsr.rs:77: falls through to the release lerp
                     e[j] = c.v3 + fminf(k_div<false>(t[j] - c.a - c.dsec - c.ssec, c.rsec, c.rr), 1.0f) * c.d34;
             }
-            return;
+            return false;
         }
     }
 #pragma unroll
     for (int j = 0; j < F; ++j) e[j] = k_apply_adsr<EXACT>(c, t[j]);
+    return false;
 }
 #endif
 

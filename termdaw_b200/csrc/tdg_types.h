@@ -58,12 +58,14 @@ struct MultiHit { int64_t start; float vel, pad; };                       // pas
 struct LerpHit { int64_t frame, pos_origin, cd_origin; float vel, pad; }; // see plan_sample_lerp
 
 // ---- tasks ------------------------------------------------------------------------------------
+static const int kInlineInputs = 8;     // the reference's graphs rarely fan in wider; wider vertices read the blob table
 enum FxMode : uint32_t { FX_SUM = 0, FX_ADSR = 1, FX_NORM_PEAK = 2 };
 
 struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan + gain, one kernel
     TaskHdr h;
     uint32_t mode, n_in;
     uint64_t in_off;        // blob: n_in pairs of (const float* l, const float* r)
+    const float* ins[2 * kInlineInputs];   // the same pairs inline when n_in <= kInlineInputs: one dependent load less per block
     AdsrK conf;
     float wet, fsr, rsr;    // fsr = sr as f32, rsr = 1/fsr
     uint32_t use_off, use_max, sr;
@@ -94,10 +96,15 @@ struct NormScaleTask {      // buf *= 1/max, then pan + gain, in place
 };
 
 struct LoopTask { TaskHdr h; const float* sl; const float* sr; uint64_t len, t0; };
-struct MultiTask { TaskHdr h; const float* sl; const float* sr; uint64_t len; uint64_t hits_off; uint32_t n_hits, pad; };
+struct MultiTask {
+    TaskHdr h; const float* sl; const float* sr; uint64_t len; uint64_t hits_off; uint32_t n_hits, pad;
+    uint64_t range_off;     // blob: uint2[n_chunks] = [lo, hi) of the hits that can sound in the chunk (host two-pointer
+                            // sweep; replaces two dependent binary searches at the head of every block)
+};
 struct LerpTask {
     TaskHdr h; const float* sl; const float* sr; uint64_t len; uint64_t hits_off;
     uint32_t n_hits, lerp_len;
+    uint64_t base_off;      // blob: uint32[n_chunks] = index of the last hit at or before the chunk's first frame
 };
 
 enum VoiceKind : uint32_t { VOICE_DEBUG_SINE = 0, VOICE_SYNTH = 1, VOICE_SAMPSYN = 2 };
@@ -125,6 +132,7 @@ struct BpTask {             // band_pass_gen (extensions.rs:654-689) as a chunke
     TaskHdr h;
     uint32_t n_in, pass;
     uint64_t in_off;
+    const float* ins[2 * kInlineInputs];   // inline copy of the input pairs when n_in <= kInlineInputs
     float lgamma, hgamma;
     uint32_t first;         // seed the four states with frame 0 of this pass (extensions.rs:664-670)
     uint32_t n_tiles;
@@ -148,8 +156,9 @@ struct QuantTask {          // write_16s / write_32s (state.rs:517-532) + hound'
     // a separate read-modify-write of the whole buffer: x * (1/max_of_chunk), pan, gain, then quantise
     // (extensions.rs:328,262-263 then state.rs:517-532 — same operations, same order, in registers).
     const float* runmax;    // null: input is already final
-    uint64_t frame0;        // pass frame of input frame 0 (chunk = (frame0 + f) / bl)
+    uint64_t frame0;        // pass frame of input frame 0: always a whole number of chunks
     PanGain pg;
+    uint32_t chunk0, span;  // frame0 / bl; frames per block: bl when fused (a block = one chunk = one max), else 1024
 };
 
 struct ResampleTask {       // rubato SincFixedIn restated: one output frame per thread
