@@ -447,14 +447,15 @@ static void plan_lerp(HVertex& v, const Floww& fl, const PassParams& pp, std::ve
 struct SegOut {                     // per-chunk CSR of voice / envelope segments
     std::vector<uint32_t> ptr;
     std::vector<VoiceSeg> vseg;
+    std::vector<float> relv2;           // parallel to vseg
     std::vector<AdsrSeg> aseg;
     uint64_t voice_frames = 0;
 };
-struct KeyedSeg { uint64_t seq; VoiceSeg s; };
+struct KeyedSeg { uint64_t seq; VoiceSeg s; float r2; };
 
 // debug_sine_gen / synth_gen / sampsyn_gen voice lifecycle (extensions.rs:429-445, 481-496, 525-528)
 static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, SegOut& out) {
-    out.ptr.assign(1, 0); out.vseg.clear(); out.voice_frames = 0;
+    out.ptr.assign(1, 0); out.vseg.clear(); out.relv2.clear(); out.voice_frames = 0;
     const float fsr = (float)pp.sr;
     const float d = (float)pp.bl / fsr;                              // len as f32 / sr as f32
     float release_sec = 0.0f;
@@ -470,10 +471,10 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, SegOu
         chunk.clear();
         bool had_event = false;
         auto close_d = [&](DNote& n, uint32_t ib) {
-            if (emit && ib > n.ia) chunk.push_back({n.seq, VoiceSeg{n.hz, n.vel, 0.0f, 0.0f, n.ia, ib, 0, 0}});
+            if (emit && ib > n.ia) chunk.push_back({n.seq, VoiceSeg{n.hz, n.vel, 0.0f, 0.0f, n.ia, ib, 0.0f, 0.0f}, 0.0f});
         };
         auto close_s = [&](SNote& n, uint32_t ib) {
-            if (emit && ib > n.ia) chunk.push_back({n.seq, VoiceSeg{n.hz, n.vel, n.env_t, n.rel_t, n.ia, ib, 0, 0}});
+            if (emit && ib > n.ia) chunk.push_back({n.seq, VoiceSeg{n.hz, n.vel, n.env_t, n.rel_t, n.ia, ib, n.relv[0], n.relv[1]}, n.relv[2]});
         };
         simple_chunk(cur, pp.F0 + k * pp.bl, pp.bl, [&](uint32_t i, bool on, float note, float vel) {
             had_event = true;
@@ -494,7 +495,7 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, SegOu
                 }
             } else {
                 if (on) {
-                    v.notes.push_back({note, vel, -fi, 0.0f, note_hz(note), v.seq++, i});
+                    v.notes.push_back(SNote{note, vel, -fi, 0.0f, note_hz(note), v.seq++, i});
                 } else {
                     size_t w = 0;
                     for (size_t q = 0; q < v.notes.size(); ++q) {           // retain (extensions.rs:485)
@@ -510,6 +511,11 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, SegOu
                             n.rel_t = n.env_t + fi;
                             n.env_t = -fi;
                             n.ia = i;
+                            // apply_r_rt's start value apply_ads(conf, rel_t) (adsr.rs:89-92): constant from here on
+                            if (v.kind == K_SYNTH) {
+                                n.relv[0] = m_apply_ads(v.sq.adsr, n.rel_t); n.relv[1] = m_apply_ads(v.tf.adsr, n.rel_t);
+                                n.relv[2] = m_apply_ads(v.tr.adsr, n.rel_t);
+                            } else n.relv[0] = m_apply_ads(v.adsr, n.rel_t);
                         }
                     }
                 }
@@ -529,7 +535,7 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, SegOu
             if (had_event)
                 std::stable_sort(chunk.begin(), chunk.end(), [](const KeyedSeg& a, const KeyedSeg& b) {
                     return a.seq != b.seq ? a.seq < b.seq : a.s.ia < b.s.ia; });
-            for (const KeyedSeg& ks : chunk) { out.vseg.push_back(ks.s); out.voice_frames += ks.s.ib - ks.s.ia; }
+            for (const KeyedSeg& ks : chunk) { out.vseg.push_back(ks.s); out.relv2.push_back(ks.r2); out.voice_frames += ks.s.ib - ks.s.ia; }
             out.ptr.push_back((uint32_t)out.vseg.size());
         }
     }
@@ -996,6 +1002,10 @@ static int pass_plan(PassJob& J) {
                     memcpy(B.at<uint8_t>(t.seg_ptr_off), so.ptr.data(), so.ptr.size() * 4);
                     t.seg_off = B.alloc(std::max<size_t>(so.vseg.size(), 1) * sizeof(VoiceSeg));
                     memcpy(B.at<uint8_t>(t.seg_off), so.vseg.data(), so.vseg.size() * sizeof(VoiceSeg));
+                    if (hv.kind == K_SYNTH) {
+                        t.relv2_off = B.alloc(std::max<size_t>(so.relv2.size(), 1) * sizeof(float));
+                        memcpy(B.at<uint8_t>(t.relv2_off), so.relv2.data(), so.relv2.size() * sizeof(float));
+                    }
                     x->stats.voice_frames += so.voice_frames;
                     const uint64_t vbytes = 8ull * r.n_frames + so.vseg.size() * sizeof(VoiceSeg);
                     if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; if (exotic) LT.dsine_exact = true; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nch); LT.dsine.bytes += vbytes; }
@@ -1006,6 +1016,7 @@ static int pass_plan(PassJob& J) {
                         t.sq_iz = 1.0f / t.sq_z;                                             // synth.rs:23
                         t.tf_add = (1.0f - t.tf_z) / 2.0f; t.tf_mul = 2.0f / (1.0f + t.tf_z);  // synth.rs:28
                         t.env[0] = make_adsr_k(hv.sq.adsr); t.env[1] = make_adsr_k(hv.tf.adsr); t.env[2] = make_adsr_k(hv.tr.adsr);
+                        t.env12_same = memcmp(&hv.tf.adsr, &hv.tr.adsr, sizeof(AdsrConfD)) == 0 ? 1u : 0u;
                         if (exotic || (t.vol[0] > 0.0f && t.env[0].exotic) || (t.vol[1] > 0.0f && t.env[1].exotic) ||
                             (t.vol[2] > 0.0f && t.env[2].exotic)) LT.synth_exact = true;
                         t.amp_mul = 1.0f / (hv.sq.volume * m_max_vel(hv.sq.adsr) + hv.tf.volume * m_max_vel(hv.tf.adsr) +
@@ -1097,7 +1108,7 @@ static int pass_plan(PassJob& J) {
                 for (MultiTask& t : S.multi.v) { t.hits_off += b; t.range_off += b; }
                 for (LerpTask& t : S.lerp.v) { t.hits_off += b; t.base_off += b; }
                 for (VoiceTask& t : S.dsine.v) { t.seg_ptr_off += b; t.seg_off += b; }
-                for (VoiceTask& t : S.synth.v) { t.seg_ptr_off += b; t.seg_off += b; }
+                for (VoiceTask& t : S.synth.v) { t.seg_ptr_off += b; t.seg_off += b; t.relv2_off += b; }
                 for (VoiceTask& t : S.sampsyn.v) { t.seg_ptr_off += b; t.seg_off += b; }
                 for (BpTask& t : S.bp.v) t.in_off += b;
                 append_list(Dst.fx, S.fx); append_list(Dst.fx_adsr, S.fx_adsr); append_list(Dst.fx_norm, S.fx_norm);

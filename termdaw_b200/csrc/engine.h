@@ -22,7 +22,7 @@ struct Floww {
 
 struct MultiEntry { int64_t t; float vel; };                       // extensions.rs:29
 struct DNote { float note, vel, hz; uint64_t seq; uint32_t ia; };  // extensions.rs:42
-struct SNote { float note, vel, env_t, rel_t, hz; uint64_t seq; uint32_t ia; };   // extensions.rs:49,55
+struct SNote { float note, vel, env_t, rel_t, hz; uint64_t seq; uint32_t ia; float relv[3] = {0, 0, 0}; };   // extensions.rs:49,55; relv: apply_ads(conf_o, rel_t)
 struct A3 { float t, vel, rel; };                                  // extensions.rs:67-68
 
 struct OscConfH { float volume = 0, param = 0; AdsrConfD adsr{}; };

@@ -466,12 +466,14 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
 //   * divisions by those constants use the exact-quotient FMA form (k_div) instead of MUFU.RCP +
 //     Newton + slow path; sin is a Cody-Waite + minimax evaluation on the FMA pipe (d_sin).
 // Accumulators stay in registers across segment batches; one float4 store per channel at the end.
-#define TDG_SEG_BATCH 64
 #ifndef TDG_SYNTH_F
 #define TDG_SYNTH_F 4           // frames per thread of the synth kernel (tuning knob, see profiles/)
 #endif
 #ifndef TDG_SYNTH_MINB
-#define TDG_SYNTH_MINB 3        // min resident blocks per SM of the synth kernel (register cap)
+#define TDG_SYNTH_MINB 5        // min resident blocks per SM (register cap); measured per 256-project step: 2: 9.9, 3: 9.9, 4: 8.2, 5: 7.7, 6: 7.7 ms
+#endif
+#ifndef TDG_SAMPSYN_MINB
+#define TDG_SAMPSYN_MINB 5      // 4: 5.77, 5: 5.58, 6: 5.63 ms
 #endif
 
 // wavetable_act_state as DEFINED by the oracle (sampsyn is not vendored): bilinear in (time, phase).
@@ -500,11 +502,15 @@ __device__ __forceinline__ float wavetable_eval(const float* __restrict__ tab, f
 }
 
 // F = consecutive frames per thread (register pressure: the three-oscillator synth body runs 2-wide)
+//
+// No block-wide staging and no barrier after the task load: every thread walks the chunk's segments
+// straight from the plan blob (32 B per segment, the same address for the whole block, so each read is
+// one L1-resident broadcast), and the per-voice release start values come precomputed in the segment.
+// The barrier-per-batch version spent a quarter of its stall cycles waiting for the two warps that
+// staged and pre-evaluated the segments (profiles/: stall_barrier).
 template <int KIND, bool EXACT, int F>
-__global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : 4) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : TDG_SAMPSYN_MINB) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ VoiceTask T;
-    __shared__ __align__(16) VoiceSeg segs[TDG_SEG_BATCH];
-    __shared__ float relv[3][TDG_SEG_BATCH];       // apply_ads(conf_o, rel_t) per (oscillator, segment)
     load_task(&T, tasks + blockIdx.y);
     const uint32_t k = blockIdx.x;
     if (k >= T.h.n_chunks) return;
@@ -512,7 +518,8 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
     const uint64_t p0 = (uint64_t)k * bl;
     const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
     const uint32_t s_lo = sp[k], s_hi = sp[k + 1];
-    const VoiceSeg* gsegs = reinterpret_cast<const VoiceSeg*>(blob + T.seg_off);
+    const float4* __restrict__ gsegs = reinterpret_cast<const float4*>(blob + T.seg_off);
+    const float* __restrict__ grelv2 = reinterpret_cast<const float*>(blob + T.relv2_off);
     const float* __restrict__ tab = T.table;
     const float fsr = T.fsr, rsr = T.rsr;
     const bool vec = (bl % F) == 0;
@@ -520,6 +527,7 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
     const int last_row_off = (int)((T.n_frames - 1) * T.n_phase);
     for (uint32_t base = 0; base < bl; base += TDG_THREADS * F) {
         const uint32_t i0 = base + threadIdx.x * F;
+        if (i0 >= bl) break;
         float acc[F], time[F], off[F];
 #pragma unroll
         for (int j = 0; j < F; ++j) {
@@ -527,85 +535,71 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
             time[j] = k_div<EXACT>((float)(T.t0 + p0 + i0 + j), fsr, rsr);      // (t + i) as f32 / sr as f32
             off[j] = k_div<EXACT>((float)(i0 + j), fsr, rsr);                   // i as f32 / sr as f32
         }
-        for (uint32_t sb = s_lo; sb < s_hi; sb += TDG_SEG_BATCH) {
-            const uint32_t nb = min((uint32_t)TDG_SEG_BATCH, s_hi - sb);
-            __syncthreads();
-            {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(gsegs + sb);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(segs);
-                for (uint32_t w = threadIdx.x; w < nb * (uint32_t)(sizeof(VoiceSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
-            }
-            __syncthreads();
-            if (KIND != VOICE_DEBUG_SINE) {
-                if (threadIdx.x < nb) {
-                    const float rt = segs[threadIdx.x].rel_t;
-                    if (rt != 0.0f) {
-                        relv[0][threadIdx.x] = k_apply_ads<EXACT>(T.env[0], rt);
-                        if (KIND == VOICE_SYNTH) {
-                            relv[1][threadIdx.x] = k_apply_ads<EXACT>(T.env[1], rt);
-                            relv[2][threadIdx.x] = k_apply_ads<EXACT>(T.env[2], rt);
+#pragma unroll 1
+        for (uint32_t s = s_lo; s < s_hi; ++s) {
+            const float4 sb = __ldg(gsegs + 2 * (size_t)s + 1);                   // ia, ib, relv0, relv1
+            const uint32_t ia = __float_as_uint(sb.x), ib = __float_as_uint(sb.y);
+            if (i0 + F <= ia || i0 >= ib) continue;
+            const float4 sa = __ldg(gsegs + 2 * (size_t)s);                       // hz, vel, env_t, rel_t
+            const float hz = sa.x, vel = sa.y, env_t = sa.z, rel_t = sa.w;
+            const bool rel = rel_t != 0.0f;
+            float smp[F];
+            if (KIND == VOICE_DEBUG_SINE) {                                       // extensions.rs:450-454
+#pragma unroll
+                for (int j = 0; j < F; ++j) smp[j] = d_sin(m_osc_arg(time[j], hz)) * vel;
+            } else {
+                float et[F], e[F];
+#pragma unroll
+                for (int j = 0; j < F; ++j) et[j] = env_t + off[j];               // env_time
+                if (KIND == VOICE_SYNTH) {                                        // extensions.rs:500-522
+                    float sn[F];
+                    if (T.vol[0] > 0.0f || T.vol[1] > 0.0f) {
+#pragma unroll
+                        for (int j = 0; j < F; ++j) sn[j] = d_sin(m_osc_arg(time[j], hz));
+                    }
+#pragma unroll
+                    for (int j = 0; j < F; ++j) smp[j] = 0.0f;
+                    bool flat = false;
+#pragma unroll 1
+                    for (int o = 0; o < 3; ++o) {                                 // square, topflat, triangle in this order
+                        const float vol = T.vol[o];
+                        if (!(vol > 0.0f)) continue;
+                        // topflat and triangle sharing one ADSR table (project.lua does): same env time, same
+                        // release start value => the values just computed for oscillator 1 are oscillator 2's
+                        const bool reuse = o == 2 && T.env12_same && T.vol[1] > 0.0f;
+                        if (!reuse)
+                            flat = rel ? k_apply_r_n<EXACT, F>(T.env[o], et, o == 0 ? sb.z : o == 1 ? sb.w : __ldg(grelv2 + s), e)
+                                       : k_apply_ads_n<EXACT, F>(T.env[o], et, e);
+                        // envelope sitting at exactly 0 (a percussive oscillator after its decay): every term is
+                        // shape*vel*0*vol = +-0 for finite factors, and adding +-0 to the running sum changes nothing
+                        if (flat && e[0] == 0.0f && fabsf(vel) < __int_as_float(0x7f800000) && vol < __int_as_float(0x7f800000)) continue;
+                        if (o == 0) {
+#pragma unroll
+                            for (int j = 0; j < F; ++j) smp[j] += fminf(fmaxf(sn[j], -T.sq_z), T.sq_z) * T.sq_iz * vel * e[j] * vol;
+                        } else if (o == 1) {
+#pragma unroll
+                            for (int j = 0; j < F; ++j) smp[j] += (fminf(sn[j], T.tf_z) + T.tf_add) * T.tf_mul * vel * e[j] * vol;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < F; ++j) smp[j] += m_triangle(time[j], hz) * vel * e[j] * vol;
                         }
                     }
-                }
-                __syncthreads();
-            }
-            if (i0 >= bl) continue;
-#pragma unroll 1
-            for (uint32_t s = 0; s < nb; ++s) {
-                const float4 sa = *reinterpret_cast<const float4*>(&segs[s]);         // hz, vel, env_t, rel_t
-                const uint2 sr_ = *reinterpret_cast<const uint2*>(&segs[s].ia);       // ia, ib
-                if (i0 + F <= sr_.x || i0 >= sr_.y) continue;
-                const float hz = sa.x, vel = sa.y, env_t = sa.z, rel_t = sa.w;
-                const bool rel = rel_t != 0.0f;
-                float smp[F];
-                if (KIND == VOICE_DEBUG_SINE) {                                       // extensions.rs:450-454
 #pragma unroll
-                    for (int j = 0; j < F; ++j) smp[j] = d_sin(m_osc_arg(time[j], hz)) * vel;
-                } else {
-                    float et[F], e[F];
+                    for (int j = 0; j < F; ++j) smp[j] *= T.amp_mul;
+                } else {                                                          // extensions.rs:560-571
+                    if (rel) k_apply_r_n<EXACT, F>(T.env[0], et, sb.z, e); else k_apply_ads_n<EXACT, F>(T.env[0], et, e);
 #pragma unroll
-                    for (int j = 0; j < F; ++j) et[j] = env_t + off[j];               // env_time
-                    if (KIND == VOICE_SYNTH) {                                        // extensions.rs:500-522
-                        float sn[F];
-                        if (T.vol[0] > 0.0f || T.vol[1] > 0.0f) {
-#pragma unroll
-                            for (int j = 0; j < F; ++j) sn[j] = d_sin(m_osc_arg(time[j], hz));
-                        }
-#pragma unroll
-                        for (int j = 0; j < F; ++j) smp[j] = 0.0f;
-#pragma unroll 1
-                        for (int o = 0; o < 3; ++o) {                                 // square, topflat, triangle in this order
-                            const float vol = T.vol[o];
-                            if (!(vol > 0.0f)) continue;
-                            if (rel) k_apply_r_n<EXACT, F>(T.env[o], et, relv[o][s], e); else k_apply_ads_n<EXACT, F>(T.env[o], et, e);
-                            if (o == 0) {
-#pragma unroll
-                                for (int j = 0; j < F; ++j) smp[j] += fminf(fmaxf(sn[j], -T.sq_z), T.sq_z) * T.sq_iz * vel * e[j] * vol;
-                            } else if (o == 1) {
-#pragma unroll
-                                for (int j = 0; j < F; ++j) smp[j] += (fminf(sn[j], T.tf_z) + T.tf_add) * T.tf_mul * vel * e[j] * vol;
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < F; ++j) smp[j] += m_triangle(time[j], hz) * vel * e[j] * vol;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < F; ++j) smp[j] *= T.amp_mul;
-                    } else {                                                          // extensions.rs:560-571
-                        if (rel) k_apply_r_n<EXACT, F>(T.env[0], et, relv[0][s], e); else k_apply_ads_n<EXACT, F>(T.env[0], et, e);
-#pragma unroll
-                        for (int j = 0; j < F; ++j) {
-                            const float g = vel * e[j] * T.amp_mul;
-                            smp[j] = wavetable_eval(tab, n_phase_f, (int)T.n_phase, ymax, last_row_off, T.fps, hz, et[j] + rel_t) * g;
-                        }
+                    for (int j = 0; j < F; ++j) {
+                        const float g = vel * e[j] * T.amp_mul;
+                        smp[j] = wavetable_eval(tab, n_phase_f, (int)T.n_phase, ymax, last_row_off, T.fps, hz, et[j] + rel_t) * g;
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < F; ++j)
-                    if (i0 + j >= sr_.x && i0 + j < sr_.y) acc[j] += smp[j];
             }
+#pragma unroll
+            for (int j = 0; j < F; ++j)
+                if (i0 + j >= ia && i0 + j < ib) acc[j] += smp[j];
         }
-        if (i0 < bl) {
+        {
             float l[F], r[F];
 #pragma unroll
             for (int j = 0; j < F; ++j) { l[j] = acc[j]; r[j] = acc[j]; apply_pg(l[j], r[j], T.h.pg); }

@@ -75,6 +75,9 @@ inline AdsrK make_adsr_k(const AdsrConfD& c) {
     k.d34 = c.release_vel - c.sustain_vel;
     k.exotic = (adsr_duration_exotic(c.attack_sec) || adsr_duration_exotic(c.decay_sec) ||
                 adsr_duration_exotic(c.sustain_sec) || adsr_duration_exotic(c.release_sec)) ? 1u : 0u;
+    const float lo = fminf(fminf(fminf(fminf(c.std_vel, c.attack_vel), c.decay_vel), c.sustain_vel), c.release_vel);
+    k.simple = (!k.exotic && c.attack_sec != 0.0f && c.decay_sec != 0.0f && c.sustain_sec != 0.0f && c.release_sec != 0.0f &&
+                lo > -0.5f) ? 1u : 0u;
     return k;
 }
 
@@ -91,6 +94,12 @@ __device__ __forceinline__ float k_div(float t, float d, float r) {
     const float q = t * r;
     const float q1 = fmaf(fmaf(-q, d, t), r, q);
     return fabsf(q) < __int_as_float(0x7f800000) ? q1 : q;
+}
+// the same quotient without the overflow / zero-divisor test: for AdsrK::simple envelopes (d in [1e-6, 1e6],
+// finite env time) t*r is finite, so the test can never fire
+__device__ __forceinline__ float k_div_fast(float t, float d, float r) {
+    const float q = t * r;
+    return fmaf(fmaf(-q, d, t), r, q);
 }
 template <bool EXACT>
 __device__ __forceinline__ float k_ads_internal(const AdsrK& c, float t) {                   // adsr.rs:46-60
@@ -131,6 +140,11 @@ __device__ __forceinline__ bool k_apply_ads_n(const AdsrK& c, const float (&t)[F
             const float r = s0 == 0 ? c.ra : s0 == 1 ? c.rd : c.rs;
             const float base = s0 == 0 ? c.v0 : s0 == 1 ? c.v1 : c.v2;
             const float dl = s0 == 0 ? c.d01 : s0 == 1 ? c.d12 : c.d23;
+            if (c.simple) {
+#pragma unroll
+                for (int j = 0; j < F; ++j) e[j] = base + k_div_fast(t[j] - sub1 - sub2, d, r) * dl;
+                return false;
+            }
 #pragma unroll
             for (int j = 0; j < F; ++j) {
                 const float res = base + k_div<false>(t[j] - sub1 - sub2, d, r) * dl;
@@ -150,6 +164,13 @@ template <bool EXACT, int F>
 __device__ __forceinline__ bool k_apply_r_n(const AdsrK& c, const float (&t)[F], float old_val, float (&e)[F]) {
     const float dl = c.v4 - old_val;
     if (!EXACT) {
+        // release towards the value it starts from (e.g. a percussive envelope that has already decayed to
+        // its end value): old + q*0 is old for every finite q (old == -0.0 excluded: -0 + +0 is +0)
+        if (dl == 0.0f && c.rsec > 0.0f && fabsf(t[F - 1]) < __int_as_float(0x7f800000) && __float_as_uint(old_val) != 0x80000000u) {
+#pragma unroll
+            for (int j = 0; j < F; ++j) e[j] = old_val;
+            return true;
+        }
         const float q0 = k_div<false>(t[0], c.rsec, c.rr);
         if (q0 >= 1.0f) {
             const float v = old_val + dl;
@@ -158,6 +179,11 @@ __device__ __forceinline__ bool k_apply_r_n(const AdsrK& c, const float (&t)[F],
             return true;
         }
         e[0] = old_val + fminf(q0, 1.0f) * dl;
+        if (c.simple) {
+#pragma unroll
+            for (int j = 1; j < F; ++j) e[j] = old_val + fminf(k_div_fast(t[j], c.rsec, c.rr), 1.0f) * dl;
+            return false;
+        }
 #pragma unroll
         for (int j = 1; j < F; ++j) e[j] = old_val + fminf(k_div<false>(t[j], c.rsec, c.rr), 1.0f) * dl;
         return false;
@@ -212,6 +238,11 @@ __device__ __forceinline__ bool k_apply_adsr_n(const AdsrK& c, const float (&t)[
             const float r = s0 == 0 ? c.ra : s0 == 1 ? c.rd : c.rs;
             const float base = s0 == 0 ? c.v0 : s0 == 1 ? c.v1 : c.v2;
             const float dl = s0 == 0 ? c.d01 : s0 == 1 ? c.d12 : c.d23;
+            if (c.simple) {
+#pragma unroll
+                for (int j = 0; j < F; ++j) e[j] = base + k_div_fast(t[j] - sub1 - sub2, d, r) * dl;
+                return false;
+            }
 #pragma unroll
             for (int j = 0; j < F; ++j) {
                 const float res = base + k_div<false>(t[j] - sub1 - sub2, d, r) * dl;

@@ -35,6 +35,9 @@ struct AdsrK {
     float v0, v1, v2, v3, v4;
     float d01, d12, d23, d34;
     uint32_t exotic;
+    uint32_t simple;        // every duration in [1e-6, 1e6] and every level > -0.5: quotients are finite and the
+                            // -1000 'past the sustain' sentinel of adsr.rs:59 cannot be hit by a lerp result, so the
+                            // per-frame inf / sentinel tests are dropped (same values, fewer instructions)
 };
 
 struct TaskHdr {
@@ -52,7 +55,9 @@ struct AdsrSeg {            // Adsr vertex state valid from frame offset `ia` of
 };
 struct VoiceSeg {           // one voice over frames [ia, ib) of one chunk, in voice (push) order
     float hz, vel, env_t, rel_t;
-    uint32_t ia, ib, pad0, pad1;
+    uint32_t ia, ib;
+    float relv0, relv1;     // released voices: apply_ads(conf, rel_t) of adsr.rs:89-92 for oscillator 0 / 1 (constant per
+                            // voice, evaluated once by the host planner with the reference's own operations)
 };
 struct MultiHit { int64_t start; float vel, pad; };                       // pass-relative first frame
 struct LerpHit { int64_t frame, pos_origin, cd_origin; float vel, pad; }; // see plan_sample_lerp
@@ -115,11 +120,12 @@ struct VoiceTask {
     uint64_t t0;            // graph time of pass frame 0 (time = (t0 + p) as f32 / sr as f32)
     uint64_t seg_ptr_off;   // blob: uint32[n_chunks+1]
     uint64_t seg_off;       // blob: VoiceSeg[]
+    uint64_t relv2_off;     // blob: float[] parallel to the segments: the same release start value for oscillator 2 (Synth)
     // Synth (extensions.rs:44-50); shape constants of synth.rs:22-29 evaluated on the host:
     // sq_iz = 1/z, tf_add = (1-z)/2, tf_mul = 2/(1+z)
     float vol[3];           // square, topflat, triangle volumes
+    uint32_t env12_same;    // topflat and triangle share one ADSR table (as in the reference's project.lua): evaluate once
     float sq_z, sq_iz, tf_z, tf_add, tf_mul, amp_mul;
-    uint32_t pad0;
     AdsrK env[3];           // square, topflat, triangle; SampSyn (extensions.rs:51-56) uses env[0]
     // SampSyn wavetable [n_frames][n_phase]
     const float* table;
