@@ -884,9 +884,10 @@ static int pass_plan(PassJob& J) {
                         LT.nscale.v.push_back(ns); LT.nscale.max_chunks = std::max(LT.nscale.max_chunks, nch);
                         LT.nscale.bytes += 16ull * r.n_frames;
                     } else { fused_runmax = runmax; fused_pg = h.pg; }
-                    // algorithmic bytes stay those of the reference's vertex model (inputs once, output once,
-                    // scale in place), so a fused pass reads as > 100 % of the per-vertex roofline
-                    algo += io_bytes + 16ull * r.n_frames;
+                    // the pass's algorithmic bytes follow SURVEY.md §8(d): every vertex reads each input once and
+                    // writes its output once.  The in-place scale of a non-output Normalize (k_norm_scale) is this
+                    // design's own extra traffic: it is counted for that kernel's own roofline line, not here
+                    algo += io_bytes;
                     LT.fx_norm.bytes += io_bytes - (t.no_store ? 8ull * r.n_frames : 0); LT.nprefix.bytes += 8ull * r.emit_n;
                     break;
                 }
@@ -931,7 +932,7 @@ static int pass_plan(PassJob& J) {
                     }
                     LT.bp.v.push_back(t); LT.bp.max_chunks = std::max(LT.bp.max_chunks, t.n_tiles);
                     hv.bp_first = false;
-                    algo += io_bytes + 8ull * hv.edges.size() * r.n_frames;     // inputs are read by both scan passes
+                    algo += io_bytes;      // §8(d) model; the aggregate pass's second read of the inputs is design overhead
                     LT.bp.bytes += io_bytes; LT.bp_agg_bytes += 8ull * hv.edges.size() * r.n_frames;
                     break;
                 }

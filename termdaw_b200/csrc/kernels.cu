@@ -321,15 +321,25 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __r
     if (k >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
     const uint64_t p0 = (uint64_t)k * bl;
+    const uint64_t len = T.len;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
         const int nv = min(4u, bl - i);
-        uint64_t s = (T.t0 + p0 + i) % T.len;
+        // (a per-chunk phase table from the host was measured slower than this modulo: the extra dependent
+        // load at the head of every block costs more than the arithmetic it saves)
+        uint64_t s = (T.t0 + p0 + i) % len;
         float l[4], r[4];
+        if (s + 3 < len) {                                        // no wrap inside the run
+            const float* __restrict__ pl = T.sl + s;
+            const float* __restrict__ pr = T.sr + s;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            l[j] = __ldg(T.sl + s); r[j] = __ldg(T.sr + s);
-            apply_pg(l[j], r[j], T.h.pg);
-            if (++s == T.len) s = 0;
+            for (int j = 0; j < 4; ++j) { l[j] = __ldg(pl + j); r[j] = __ldg(pr + j); apply_pg(l[j], r[j], T.h.pg); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                l[j] = __ldg(T.sl + s); r[j] = __ldg(T.sr + s);
+                apply_pg(l[j], r[j], T.h.pg);
+                if (++s == len) s = 0;
+            }
         }
         st4<VEC>(T.h.out_l, p0 + i, nv, l);
         st4<VEC>(T.h.out_r, p0 + i, nv, r);
@@ -1013,7 +1023,7 @@ __global__ void k_scale_by_inv(float* __restrict__ x, uint64_t n, const float* _
 }
 
 // ------------------------------------------------------------------------------------ launchers
-static inline dim3 grid2(uint64_t x, uint32_t y) { return dim3((unsigned)x, y, 1); }
+static inline dim3 grid2(uint64_t x, uint32_t y) { return dim3((unsigned)(x ? x : 1), y, 1); }   // zero-length pass: blocks find nothing to do
 
 #define TDG_VEC_DISPATCH(vec, K, ...) do { if (vec) K<true> __VA_ARGS__; else K<false> __VA_ARGS__; } while (0)
 
