@@ -338,7 +338,7 @@ class TimeShardRunner:
         c0, n = self.ts.bounds[self.rank]
         if e2e:
             frames = C.c_uint64(0)
-            rc = self.lib.render_segment(c.h, st.cs, c0, n, 0, st.bd, self.out.ctypes.data_as(C.POINTER(C.c_uint8)),
+            rc = self.lib.render_segment(c.h, st.cs, c0, n, 0, 0, st.bd, self.out.ctypes.data_as(C.POINTER(C.c_uint8)),
                                          self.out.size, C.byref(frames))
             assert rc >= 0, self.lib.last_error(c.h)
         else:

@@ -183,7 +183,13 @@ int tdg_read_vertex_buffer(tdg_ctx* ctx, int vertex, uint64_t frame0, uint64_t n
  * (torch.distributed / MPI / a file), every rank calls tdg_comm_init_rank on its context.
  * Without a communicator tdg_*_segment falls back to re-rendering `warmup_chunks` chunks before
  * chunk0 so that filter state converges (approximate; normalize state is then the caller's job via
- * tdg_get/set_normalize_state).  No render-time resampling in segment mode. */
+ * tdg_get/set_normalize_state).
+ *   - Render-time resampler (state.rs:533-550): rubato keeps 2*sinc_len = 512 frames of history in
+ *     front of each chunk and an f64 index carried from call to call.  `render_sr` below the project
+ *     rate (0 = project rate) resamples the segment exactly as the full pass would: the index is
+ *     replayed on the host from chunk 0, and the previous segment's last 512 output-vertex frames
+ *     arrive as a halo (one more ncclAllGather, 4 KiB per rank).  Segments must then be >= 512 frames.
+ *     tdg_segment_output_frames tells the caller where the segment's frames land in the file. */
 int tdg_comm_unique_id(uint8_t* out128);
 int tdg_comm_init_rank(tdg_ctx* ctx, int nranks, int rank, const uint8_t* id128);
 int tdg_comm_destroy(tdg_ctx* ctx);
@@ -191,16 +197,19 @@ uint64_t tdg_collectives(tdg_ctx* ctx);        /* NCCL exchange rounds issued so
 int tdg_scan_segment(tdg_ctx* ctx, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks,
                      uint64_t warmup_chunks);
 int tdg_render_segment(tdg_ctx* ctx, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks,
-                       uint64_t warmup_chunks, uint32_t bitdepth, uint8_t* out_pcm,
-                       uint64_t cap_bytes, uint64_t* frames_written);
+                       uint64_t warmup_chunks, uint32_t render_sr, uint32_t bitdepth,
+                       uint8_t* out_pcm, uint64_t cap_bytes, uint64_t* frames_written);
+int tdg_segment_output_frames(uint32_t project_sr, uint32_t buffer_len, uint32_t render_sr,
+                              uint64_t chunk0, uint64_t chunks, uint64_t* first_frame,
+                              uint64_t* n_frames);   /* host only: no device needed */
 /* "Virtual ranks": n contexts holding the SAME project on ONE device evaluate n consecutive segments
  * (chunk0[0] == 0, contiguous, covering total_chunks) in one launch sequence and exchange through
  * device memory exactly what NCCL carries between GPUs.  Same kernels, same hand-off arithmetic. */
 int tdg_scan_segments_local(tdg_ctx** ctxs, int n, uint64_t total_chunks, const uint64_t* chunk0,
                             const uint64_t* chunks);
 int tdg_render_segments_local(tdg_ctx** ctxs, int n, uint64_t total_chunks, const uint64_t* chunk0,
-                              const uint64_t* chunks, uint32_t bitdepth, uint8_t** out_pcm,
-                              const uint64_t* cap_bytes, uint64_t* frames_written);
+                              const uint64_t* chunks, uint32_t render_sr, uint32_t bitdepth,
+                              uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written);
 /* Normalize state as (max, scan_max) pairs, one per vertex (non-normalize vertices: -1, -1). */
 int tdg_get_normalize_state(tdg_ctx* ctx, float* max_out, float* scan_max_out, int cap);
 int tdg_set_normalize_state(tdg_ctx* ctx, const float* max_in, const float* scan_max_in, int n);

@@ -10,7 +10,7 @@ from __future__ import annotations
 import os
 
 from ._capi import (Context, Library, TermdawError, comm_unique_id, normalize_render_many, normalize_scan_many, render_many,  # noqa: F401
-                    render_segments_local, scan_segments_local)
+                    render_segments_local, scan_segments_local, segment_output_frames)
 from .state import Assets, DecodedWav, Project, State, set_length_chunks  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -109,8 +109,9 @@ class Library:
     # symbols only the CUDA library has (time sharding + measurement)
     GPU_ONLY = {
         "scan_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
-        "render_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, c_u8p,
-                                     C.c_uint64, c_u64p]),
+        "render_segment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                     c_u8p, C.c_uint64, c_u64p]),
+        "segment_output_frames": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, c_u64p, c_u64p]),
         "set_normalize_state": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int]),
         "normalize_render_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_u64p, c_u32p, c_u32p,
                                             C.POINTER(c_u8p), c_u64p, c_u64p]),
@@ -120,7 +121,7 @@ class Library:
         "collectives": (C.c_uint64, [C.c_void_p]),
         "scan_segments_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint64, c_u64p, c_u64p]),
         "render_segments_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint64, c_u64p, c_u64p, C.c_uint32,
-                                            C.POINTER(c_u8p), c_u64p, c_u64p]),
+                                            C.c_uint32, C.POINTER(c_u8p), c_u64p, c_u64p]),
         "normalize_state_device_ptr": (C.c_void_p, [C.c_void_p, c_i32p]),
         "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
         "set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
@@ -320,11 +321,12 @@ class Context:
         self._chk(self.lib.scan_segment(self.h, total_chunks, chunk0, chunks, warmup_chunks))
 
     def render_segment(self, total_chunks: int, chunk0: int, chunks: int, warmup_chunks: int, bitdepth: int,
-                       want_pcm=True):
-        cap = chunks * self.bl * 2 * (bitdepth // 8)
+                       want_pcm=True, render_sr: int = 0):
+        """tdg_render_segment; render_sr = 0 (or >= the project rate) renders at the project rate."""
+        cap = chunks * self.bl * 2 * (bitdepth // 8)            # the resampler only ever shortens
         frames = C.c_uint64(0)
         out = np.empty(cap if want_pcm else 0, np.uint8)
-        self._chk(self.lib.render_segment(self.h, total_chunks, chunk0, chunks, warmup_chunks, bitdepth,
+        self._chk(self.lib.render_segment(self.h, total_chunks, chunk0, chunks, warmup_chunks, render_sr, bitdepth,
                                           _p(out, c_u8p) if want_pcm else None, cap, C.byref(frames)))
         return out[: frames.value * 2 * (bitdepth // 8)] if want_pcm else None
 
@@ -430,7 +432,18 @@ def scan_segments_local(lib: Library, ctxs: Sequence[Context], total_chunks: int
         raise TermdawError(rc, next((m for m in msgs if m), ""))
 
 
-def render_segments_local(lib: Library, ctxs: Sequence[Context], total_chunks: int, bounds, bitdepth: int):
+def segment_output_frames(lib: Library, project_sr: int, buffer_len: int, render_sr: int, chunk0: int, chunks: int):
+    """tdg_segment_output_frames: (first output frame, frame count) of chunks [chunk0, chunk0 + chunks) in the
+    rendered file — the host's f64 replay of the resampler index when render_sr < project_sr."""
+    first, n = C.c_uint64(0), C.c_uint64(0)
+    rc = lib.segment_output_frames(project_sr, buffer_len, render_sr, chunk0, chunks, C.byref(first), C.byref(n))
+    if rc < 0:
+        raise TermdawError(rc, "tdg_segment_output_frames")
+    return first.value, n.value
+
+
+def render_segments_local(lib: Library, ctxs: Sequence[Context], total_chunks: int, bounds, bitdepth: int,
+                          render_sr: int = 0):
     """tdg_render_segments_local; returns the per-segment PCM byte arrays (concatenate for the file)."""
     n = len(ctxs)
     hs = (C.c_void_p * n)(*[c.h for c in ctxs])
@@ -441,7 +454,7 @@ def render_segments_local(lib: Library, ctxs: Sequence[Context], total_chunks: i
     ptrs = (c_u8p * n)(*[_p(o, c_u8p) for o in outs])
     cp = (C.c_uint64 * n)(*caps)
     fw = (C.c_uint64 * n)()
-    rc = lib.render_segments_local(hs, n, total_chunks, c0, cn, bitdepth, ptrs, cp, fw)
+    rc = lib.render_segments_local(hs, n, total_chunks, c0, cn, render_sr, bitdepth, ptrs, cp, fw)
     if rc < 0:
         msgs = [(lib.last_error(c.h) or b"").decode() for c in ctxs]
         raise TermdawError(rc, next((m for m in msgs if m), ""))

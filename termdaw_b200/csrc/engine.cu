@@ -323,6 +323,20 @@ static void resample_replay(double ratio, uint64_t chunk, uint64_t n_chunks, std
     *total = off;
 }
 
+// chunks [chunk0, chunk0 + n) of a pass that started at chunk 0: SincFixedIn's index is carried from call
+// to call (f64, sequential), so a segment replays the calls in front of it; out_off is rebased to the
+// segment and *first_out is the output frame the segment starts at in the file
+static void resample_replay_slice(double ratio, uint64_t chunk, uint64_t chunk0, uint64_t n, std::vector<ResampleChunk>& out,
+                                  uint64_t* first_out, uint64_t* total) {
+    std::vector<ResampleChunk> all;
+    uint64_t tot = 0;
+    resample_replay(ratio, chunk, chunk0 + n, all, &tot);
+    const uint64_t first = n ? all[chunk0].out_off : tot;
+    out.assign(all.begin() + (ptrdiff_t)chunk0, all.end());
+    for (ResampleChunk& c : out) c.out_off -= first;
+    *first_out = first; *total = tot - first;
+}
+
 // ------------------------------------------------------------------------------------ vertex state sync
 static int vstate_to_host(Ctx* c) {
     if (c->vstate_host_newer || !c->vstate_dev) return TDG_OK;
@@ -605,6 +619,7 @@ struct PassReq {
     bool resample = false;
     const float* sincs = nullptr;
     std::vector<ResampleChunk> rs_chunks;
+    int64_t halo_off = -1;             // time-sharded resampling: [x_ranks][2][kResampleHalo] floats (arena offset)
     uint64_t out_frames = 0;
     uint32_t err_flag = 0;
 };
@@ -770,12 +785,30 @@ static int pass_plan(PassJob& J) {
             } else { r.x_off = leader->x_off; r.x_red_off = leader->x_red_off; }
         }
         if (!r.is_scan && x->output >= 0) {
-            r.resample = !r.segment && x->sr > r.render_sr;                    // state.rs:533
+            r.resample = x->sr > r.render_sr;                                  // state.rs:533
             r.out_frames = (r.emit0 + r.emit_n - r.keep0) * x->bl;
             if (r.resample) {
-                resample_replay((double)r.render_sr / (double)x->sr, x->bl, r.emit_n, r.rs_chunks, &r.rs_total);
+                const uint64_t keep_n = r.emit0 + r.emit_n - r.keep0;
+                uint64_t first_out = 0;
+                if (r.segment) resample_replay_slice((double)r.render_sr / (double)x->sr, x->bl, r.keep0, keep_n, r.rs_chunks, &first_out, &r.rs_total);
+                else resample_replay((double)r.render_sr / (double)x->sr, x->bl, r.emit_n, r.rs_chunks, &r.rs_total);
                 r.rs_off = bump.alloc(align_up(r.rs_total, 4) * 2 * 4 + 64);
                 r.out_frames = r.rs_total;
+                // the resampler's history in front of a segment (512-frame halo): warm-up chunks of
+                // this segment if there are enough of them, else the previous rank's tail through the exchange
+                const uint64_t before = (r.keep0 - r.emit0) * x->bl;
+                if (r.keep0 > 0 && before < (uint64_t)kResampleHalo) {
+                    if (r.x_ranks <= 1)
+                        return x->fail(TDG_ERR_INVALID, "a resampled segment needs a communicator, virtual ranks or >= 512 warm-up frames");
+                }
+                if (r.x_ranks > 1) {
+                    if (keep_n * x->bl < (uint64_t)kResampleHalo)
+                        return x->fail(TDG_ERR_INVALID, "resampled segments must be at least 512 frames long");
+                    PassReq* leader = &r;
+                    if (r.x_mode == 1) for (auto& q : reqs) if (q.x_mode == 1) { leader = &q; break; }
+                    if (leader == &r) r.halo_off = (int64_t)bump.alloc((uint64_t)r.x_ranks * 2 * kResampleHalo * 4);
+                    else r.halo_off = leader->halo_off;
+                }
             }
             r.pcm_bytes = r.out_frames * 2 * (r.bd / 8);
             r.pcm_off = pbump.alloc(align_up(r.pcm_bytes, 64) + 64);
@@ -1049,7 +1082,13 @@ static int pass_plan(PassJob& J) {
                 rt.in_l = ol; rt.in_r = orr;
                 rt.out_l = reinterpret_cast<float*>(W + r.rs_off); rt.out_r = rt.out_l + align_up(r.rs_total, 4);
                 rt.sincs = r.sincs;
-                rt.n_in = r.n_frames; rt.n_chunks = (uint32_t)r.emit_n; rt.chunk = x->bl;
+                const uint64_t before = (r.keep0 - r.emit0) * x->bl;
+                rt.in_l += before; rt.in_r += before; rt.n_before = before;
+                rt.n_in = r.n_frames - before; rt.n_chunks = (uint32_t)r.rs_chunks.size(); rt.chunk = x->bl;
+                if (r.halo_off >= 0 && r.x_rank > 0 && before < (uint64_t)kResampleHalo) {
+                    rt.halo_l = reinterpret_cast<const float*>(W + r.halo_off) + (size_t)(r.x_rank - 1) * 2 * kResampleHalo;
+                    rt.halo_r = rt.halo_l + kResampleHalo;
+                }
                 rt.t_ratio = 1.0 / ((double)r.render_sr / (double)x->sr);
                 rt.chunk_off = B.alloc(std::max<size_t>(r.rs_chunks.size(), 1) * sizeof(ResampleChunk));
                 memcpy(B.at<uint8_t>(rt.chunk_off), r.rs_chunks.data(), r.rs_chunks.size() * sizeof(ResampleChunk));
@@ -1246,6 +1285,26 @@ static int pass_submit(PassJob& J) {
         LAUNCH_SPLIT(KC_NORM_SCALE, T.nscale, NormScaleTask, offs[L].nscale, T.nscale.bytes, launch_norm_scale(tp, nb, T.nscale.max_chunks, vec, s));
         LAUNCH_SPLIT(KC_BP_CARRY, T.bp, BpTask, offs[L].bp, (uint64_t)0, launch_bp_carry(tp, nb, D, s));
         LAUNCH_SPLIT(KC_BP_APPLY, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_apply(tp, nb, T.bp.max_chunks, vec, D, s));
+    }
+    if (x_mode) {
+        // time-sharded resampling: every segment publishes the last 512 frames of the output vertex; the next
+        // segment's resampler reads them as its history (state.rs:533-550 keeps that history inside rubato)
+        bool any = false;
+        for (auto& r : reqs) {
+            if (r.halo_off < 0 || !r.resample) continue;
+            const float* ol = reinterpret_cast<const float*>(W + r.buf_off[r.c->output]);
+            float* slot = reinterpret_cast<float*>(W + r.halo_off) + (size_t)r.x_rank * 2 * kResampleHalo;
+            CU(cudaMemcpyAsync(slot, ol + r.n_frames - kResampleHalo, kResampleHalo * 4, cudaMemcpyDeviceToDevice, s));
+            CU(cudaMemcpyAsync(slot + kResampleHalo, ol + r.n_pad + r.n_frames - kResampleHalo, kResampleHalo * 4, cudaMemcpyDeviceToDevice, s));
+            any = true;
+        }
+        if (any && x_mode == 2) {
+            const PassReq& r0 = reqs[0];
+            NcclApi* na = nccl_api();
+            float* hb = reinterpret_cast<float*>(W + r0.halo_off);
+            NC(na->AllGather(hb + (size_t)r0.x_rank * 2 * kResampleHalo, hb, 2 * kResampleHalo, kNcclFloat32, r0.c->nccl_comm, s));
+            ++collectives;
+        }
     }
     { TaskList<ResampleTask> rl; rl.v.swap(resamps);
       LAUNCH_SPLIT(KC_RESAMPLE, rl, ResampleTask, resamp_off, resamp_bytes, launch_resample(tp, nb, resamp_max, D, s)); }
@@ -1977,13 +2036,14 @@ int tdg_scan_segment(tdg_ctx* h, uint64_t total_chunks, uint64_t chunk0, uint64_
     return run_pass(reqs);
 }
 int tdg_render_segment(tdg_ctx* h, uint64_t total_chunks, uint64_t chunk0, uint64_t chunks, uint64_t warmup_chunks,
-                       uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes, uint64_t* frames_written) {
+                       uint32_t render_sr, uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes, uint64_t* frames_written) {
     Ctx* c = C_;
     if (int e = valid_bd(c, bitdepth)) return e;
     std::vector<PassReq> reqs(1);
     if (c->nccl_comm) warmup_chunks = 0;
     if (int e = make_segment_req(c, reqs[0], false, total_chunks, chunk0, chunks, warmup_chunks)) return e;
     PassReq& r = reqs[0];
+    if (render_sr) r.render_sr = render_sr;
     r.bd = bitdepth; r.out = out_pcm; r.cap = cap_bytes; r.frames_written = frames_written;
     if (c->nccl_comm) { r.x_mode = 2; r.x_ranks = c->x_ranks; r.x_rank = c->x_rank; }
     return run_pass(reqs);
@@ -1991,7 +2051,7 @@ int tdg_render_segment(tdg_ctx* h, uint64_t total_chunks, uint64_t chunk0, uint6
 // virtual ranks: n contexts holding the SAME project on one device evaluate n consecutive segments
 // in one launch sequence, exchanging through device memory what NCCL would carry between GPUs
 static int segments_local(tdg_ctx** hs, int n, bool is_scan, uint64_t total_chunks, const uint64_t* chunk0, const uint64_t* chunks,
-                          uint32_t bitdepth, uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written) {
+                          uint32_t render_sr, uint32_t bitdepth, uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written) {
     if (n <= 0) return TDG_ERR_INVALID;
     std::vector<PassReq> reqs(n);
     uint64_t expect = 0;
@@ -2003,6 +2063,7 @@ static int segments_local(tdg_ctx** hs, int n, bool is_scan, uint64_t total_chun
         expect += chunks[i];
         if (int e = make_segment_req(c, reqs[i], is_scan, total_chunks, chunk0[i], chunks[i], 0)) return e;
         reqs[i].x_mode = n > 1 ? 1 : 0; reqs[i].x_ranks = n; reqs[i].x_rank = i; reqs[i].bd = bitdepth;
+        if (render_sr) reqs[i].render_sr = render_sr;
         if (!is_scan) {
             reqs[i].out = out_pcm ? out_pcm[i] : nullptr; reqs[i].cap = cap_bytes ? cap_bytes[i] : 0;
             reqs[i].frames_written = frames_written ? frames_written + i : nullptr;
@@ -2012,11 +2073,26 @@ static int segments_local(tdg_ctx** hs, int n, bool is_scan, uint64_t total_chun
     return run_pass(reqs);
 }
 int tdg_scan_segments_local(tdg_ctx** hs, int n, uint64_t total_chunks, const uint64_t* chunk0, const uint64_t* chunks) {
-    return segments_local(hs, n, true, total_chunks, chunk0, chunks, 16, nullptr, nullptr, nullptr);
+    return segments_local(hs, n, true, total_chunks, chunk0, chunks, 0, 16, nullptr, nullptr, nullptr);
 }
 int tdg_render_segments_local(tdg_ctx** hs, int n, uint64_t total_chunks, const uint64_t* chunk0, const uint64_t* chunks,
-                              uint32_t bitdepth, uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written) {
-    return segments_local(hs, n, false, total_chunks, chunk0, chunks, bitdepth, out_pcm, cap_bytes, frames_written);
+                              uint32_t render_sr, uint32_t bitdepth, uint8_t** out_pcm, const uint64_t* cap_bytes,
+                              uint64_t* frames_written) {
+    return segments_local(hs, n, false, total_chunks, chunk0, chunks, render_sr, bitdepth, out_pcm, cap_bytes, frames_written);
+}
+// where a segment's frames land in the rendered file: the host-side f64 replay of the resampler's index
+// (no device work); render_sr >= project_sr (or 0) means no resampling (state.rs:533)
+int tdg_segment_output_frames(uint32_t project_sr, uint32_t buffer_len, uint32_t render_sr, uint64_t chunk0, uint64_t chunks,
+                              uint64_t* first_frame, uint64_t* n_frames) {
+    if (!project_sr || !buffer_len) return TDG_ERR_INVALID;
+    uint64_t first = chunk0 * buffer_len, n = chunks * buffer_len;
+    if (render_sr && project_sr > render_sr) {
+        std::vector<ResampleChunk> ch;
+        resample_replay_slice((double)render_sr / (double)project_sr, buffer_len, chunk0, chunks, ch, &first, &n);
+    }
+    if (first_frame) *first_frame = first;
+    if (n_frames) *n_frames = n;
+    return TDG_OK;
 }
 
 // NCCL communicator of a time-sharded render: one rank per GPU / process

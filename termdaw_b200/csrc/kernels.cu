@@ -983,12 +983,26 @@ __global__ void __launch_bounds__(128) k_resample(const ResampleTask* __restrict
             const int64_t pos = base + (q == 0 ? i0 : i1);
             const float* sn = T.sincs + (size_t)(q == 0 ? s0 : s1) * sinc_len;
             float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int t = 0; t < sinc_len; t += 8) {
+            if (pos >= -(int64_t)T.n_before && pos + sinc_len <= (int64_t)T.n_in) {
+                // whole window inside this segment's buffer (warm-up chunks sit at negative offsets)
+                for (int t = 0; t < sinc_len; t += 8) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int64_t ps = pos + t + u;
-                    const float w = (ps >= 0 && ps < (int64_t)T.n_in) ? __ldg(in + ps) : 0.0f;
-                    acc[u] += w * __ldg(sn + t + u);
+                    for (int u = 0; u < 8; ++u) acc[u] += __ldg(in + pos + t + u) * __ldg(sn + t + u);
+                }
+            } else {
+                // window reaches in front of the buffer: the previous segment's tail (time sharding) or the
+                // zeros SincFixedIn's buffer starts with; behind the end there is nothing (never reached:
+                // end_idx keeps the window inside the chunk)
+                const float* halo = c == 0 ? T.halo_l : T.halo_r;
+                for (int t = 0; t < sinc_len; t += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t ps = pos + t + u;
+                        float w = 0.0f;
+                        if (ps >= -(int64_t)T.n_before) { if (ps < (int64_t)T.n_in) w = __ldg(in + ps); }
+                        else if (halo && ps >= -(int64_t)kResampleHalo) w = halo[kResampleHalo + ps];
+                        acc[u] += w * __ldg(sn + t + u);
+                    }
                 }
             }
             pts[q] = acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7];

@@ -177,7 +177,14 @@ struct ResampleTask {       // rubato SincFixedIn restated: one output frame per
     uint64_t chunk_off;     // blob: ResampleChunk[n_chunks]
     uint32_t n_chunks, chunk;
     double t_ratio;
+    // time-sharded render: frames in front of in_*[0].  `n_before` of them sit in the same buffer (warm-up
+    // chunks of this segment); otherwise the previous segment's last kResampleHalo frames arrive through
+    // the exchange buffer (halo_l/halo_r, frame -1 is halo[kResampleHalo - 1]); null => zeros (pass start)
+    const float* halo_l;
+    const float* halo_r;
+    uint64_t n_before;
 };
+static const int kResampleHalo = 512;   // 2 * sinc_len: the history SincFixedIn keeps in front of a chunk
 struct ResampleChunk { double last_index; uint64_t out_off; uint32_t n_out, pad; };
 
 static const int kBpFramesPerThread = 8;

@@ -13,7 +13,7 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from ._capi import Library, comm_unique_id
+from ._capi import Library, comm_unique_id, segment_output_frames
 from .state import State
 
 
@@ -31,8 +31,14 @@ def shard_chunks(total_chunks: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
-def pcm_offset_bytes(bounds: List[Tuple[int, int]], rank: int, buffer_len: int, bitdepth: int) -> int:
-    """Byte offset of a rank's segment inside the WAV data chunk (2 channels, no resampling)."""
+def pcm_offset_bytes(bounds: List[Tuple[int, int]], rank: int, buffer_len: int, bitdepth: int,
+                     lib: Optional[Library] = None, project_sr: int = 0, render_sr: int = 0) -> int:
+    """Byte offset of a rank's segment inside the WAV data chunk (2 channels).  With a render rate below
+    the project rate (state.rs:533) the segment's first output frame comes from the library's replay of
+    the resampler index (`tdg_segment_output_frames`)."""
+    if lib is not None and render_sr and project_sr > render_sr:
+        first, _ = segment_output_frames(lib, project_sr, buffer_len, render_sr, bounds[rank][0], bounds[rank][1])
+        return first * 2 * (bitdepth // 8)
     return bounds[rank][0] * buffer_len * 2 * (bitdepth // 8)
 
 
@@ -67,10 +73,10 @@ class TimeShardedRender:
 
     def render(self, want_pcm: bool = True) -> Optional[np.ndarray]:
         c0, n = self.bounds[self.rank]
-        return self.st.ctx.render_segment(self.st.cs, c0, n, 0, self.st.bd, want_pcm=want_pcm)
+        return self.st.ctx.render_segment(self.st.cs, c0, n, 0, self.st.bd, want_pcm=want_pcm, render_sr=self.st.render_sr)
 
     def offset_bytes(self) -> int:
-        return pcm_offset_bytes(self.bounds, self.rank, self.st.bl, self.st.bd)
+        return pcm_offset_bytes(self.bounds, self.rank, self.st.bl, self.st.bd, self.st.lib, self.st.psr, self.st.render_sr)
 
     def close(self):
         if self.has_comm:

@@ -35,10 +35,10 @@ def main():
     info = {"rank": rank, "world": world}
     if kind == "timeshard":
         from termdaw_b200.timeshard import TimeShardedRender
-        cfg = {"c1": S.config_1, "c2": S.config_2, "c4": S.config_4}[a1](float(a2))
+        cfg = {"c1": S.config_1, "c1r": S.config_1, "c2": S.config_2, "c4": S.config_4}[a1](float(a2))
         p, a, s = cfg
         if a1 == "c1":
-            p.set_render_samplerate(48000)          # segment mode does not resample
+            p.set_render_samplerate(48000)          # project rate; "c1r" keeps the README's 44.1 kHz (resampler halo)
         st = State(lib, s["psr"], s["bl"], device=local, assets=a)
         assert st.refresh(p), st.messages
         ts = TimeShardedRender(st, rank, world, dist)

@@ -52,6 +52,20 @@ def test_nccl_time_sharded_bit_exact_graph(oracle, tmp_path):
             assert inf["norm"][name] == v
 
 
+def test_nccl_time_sharded_resampled_render(oracle, tmp_path):
+    """configs[0] at 44.1 kHz split by time over real ranks: the resampler's 512-frame history crosses the
+    boundary by ncclAllGather, the f64 index by host replay; every rank writes at the replayed offset."""
+    world = _world()
+    infos = _torchrun(world, tmp_path, "timeshard:c1r:1.0")
+    want = run_project(oracle, *S.config_1(1.0), taps=False)
+    pcm = np.concatenate([np.load(tmp_path / f"pcm_{k}.npy") for k in range(world)])
+    x, y = pcm_to_int(pcm, infos[0]["bd"]), pcm_to_int(want["pcm"], want["bd"])
+    assert x.shape == y.shape and int(np.abs(x - y).max()) <= 1
+    for k, inf in enumerate(infos):
+        assert inf["collectives"] >= 2          # normalize peak + halo
+        assert inf["offset"] == sum(np.load(tmp_path / f"pcm_{q}.npy").size for q in range(k))
+
+
 @pytest.mark.parametrize("case,lsb", [("c2:0.1", 96), ("c4:0.002", 96)])
 def test_nccl_time_sharded_filters_and_voices(oracle, tmp_path, case, lsb):
     """configs[1] and configs[3] split by time: band-pass state crosses ranks as affine maps (all-gather),

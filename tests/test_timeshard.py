@@ -28,6 +28,31 @@ def test_shard_chunks_partition():
     assert pcm_offset_bytes(shard_chunks(100, 4), 2, 1024, 24) == 50 * 1024 * 6
 
 
+def test_segment_output_frames_partition():
+    """tdg_segment_output_frames is host arithmetic (the f64 replay of SincFixedIn's index, state.rs:533-550):
+    segments tile the file, and the total is what the golden configs[0] render holds."""
+    from termdaw_b200 import load_library, segment_output_frames
+    lib = load_library()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "config1_readme_44k1_16bit.npz"))
+    total_frames = g["pcm"].size // 4
+    cs = int(g["cs"]) if "cs" in g.files else None
+    for sr, bl, rsr, chunks in [(48000, 1024, 44100, cs or 141), (48000, 1024, 32000, 37), (96000, 256, 44100, 50),
+                                (48000, 64, 44100, 40), (48000, 1024, 48000, 9), (48000, 1024, 0, 9)]:
+        f0, n0 = segment_output_frames(lib, sr, bl, rsr, 0, chunks)
+        assert f0 == 0
+        for world in (1, 2, 3, 8):
+            off = 0
+            for c0, n in shard_chunks(chunks, world):
+                first, cnt = segment_output_frames(lib, sr, bl, rsr, c0, n)
+                assert first == off
+                off += cnt
+            assert off == n0
+        if rsr == 0 or rsr >= sr:
+            assert n0 == chunks * bl
+    if cs is not None:
+        assert segment_output_frames(lib, 48000, 1024, 44100, 0, cs)[1] == total_frames
+
+
 def _gloo_worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -77,7 +102,7 @@ def _sharded(gpulib, cfg, n_seg, flow="B"):
     ctxs = [st.ctx for st in states]
     if flow == "B":
         scan_segments_local(gpulib, ctxs, cs, bounds)
-    pcms = render_segments_local(gpulib, ctxs, cs, bounds, states[0].bd)
+    pcms = render_segments_local(gpulib, ctxs, cs, bounds, states[0].bd, states[0].render_sr)
     norms = [st.normalization_values() for st in states]
     bd = states[0].bd
     for st in states:
@@ -90,13 +115,72 @@ def _sharded(gpulib, cfg, n_seg, flow="B"):
 def test_virtual_ranks_bit_exact_graph(gpulib, oracle, n_seg):
     """No IIR in the graph: sharded render == oracle's unsharded render, bit for bit, both flows."""
     cfg = S.config_1(0.5)
-    cfg[0].set_render_samplerate(48000)          # segment mode does not resample
+    cfg[0].set_render_samplerate(48000)          # project rate; the resampled case is tested below
     for flow in ("B", "A"):
         want = run_project(oracle, *cfg, flow=flow, taps=False)
         pcm, norms, bd = _sharded(gpulib, cfg, n_seg, flow)
         assert np.array_equal(pcm, want["pcm"]), (n_seg, flow)
         for nv in norms:
             assert nv == pytest.approx(want["norm"], rel=0, abs=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_seg", [2, 3, 8])
+def test_virtual_ranks_resampled_render(gpulib, oracle, n_seg):
+    """configs[0] at its real 44.1 kHz render rate, split by time (last row): the f64 resampler
+    index is replayed from chunk 0 and the previous segment's last 512 frames arrive as a halo, so the
+    sharded file is the unsharded GPU file bit for bit (and the oracle's within 1 LSB)."""
+    from termdaw_b200 import segment_output_frames
+    from termdaw_b200.state import State
+    cfg = S.config_1(0.5)
+    assert cfg[0].render_samplerate == 44100
+    for flow in ("B", "A"):
+        p, a, s = cfg
+        st = State(gpulib, s["psr"], s["bl"], assets=a)
+        assert st.refresh(p), st.messages
+        if flow == "B":
+            st.scan_exact()
+        full = st.render()
+        cs, bl, psr, bd = st.cs, st.bl, st.psr, st.bd
+        st.close()
+        pcm, norms, _ = _sharded(gpulib, cfg, n_seg, flow)
+        assert np.array_equal(pcm, full), (n_seg, flow)
+        want = run_project(oracle, *cfg, flow=flow, taps=False)
+        x, y = pcm_to_int(pcm, bd), pcm_to_int(want["pcm"], want["bd"])
+        assert x.shape == y.shape and int(np.abs(x - y).max()) <= 1
+        # the file offsets the ranks would write at
+        bounds = shard_chunks(cs, n_seg)
+        off = 0
+        for r, (c0, n) in enumerate(bounds):
+            first, cnt = segment_output_frames(gpulib, psr, bl, 44100, c0, n)
+            assert first == off and pcm_offset_bytes(bounds, r, bl, bd, gpulib, psr, 44100) == off * 2 * (bd // 8)
+            off += cnt
+        assert off * 2 * (bd // 8) == full.size
+
+
+@pytest.mark.gpu
+def test_resampled_segment_with_filter_and_errors(gpulib, oracle):
+    """band pass in front of the resampler (state hand-off + halo together), and the documented refusals."""
+    from termdaw_b200 import TermdawError
+    from termdaw_b200.state import State
+    cfg = S.config_2(0.05)
+    cfg[0].set_render_samplerate(32000)
+    want = run_project(oracle, *cfg, taps=False)
+    pcm, norms, bd = _sharded(gpulib, cfg, 4)
+    a, b = pcm_to_int(pcm, bd), pcm_to_int(want["pcm"], want["bd"])
+    assert a.shape == b.shape
+    assert int(np.abs(a - b).max()) <= 96
+    # a lone resampled segment that does not start the pass has no history to read
+    p, a_, s = cfg
+    st = State(gpulib, s["psr"], s["bl"], assets=a_)
+    assert st.refresh(p)
+    with pytest.raises(TermdawError):
+        st.ctx.render_segment(st.cs, 4, 4, 0, st.bd, render_sr=32000)
+    # ... unless enough warm-up chunks are rendered in front of it (approximate mode, still resampled)
+    out = st.ctx.render_segment(st.cs, 4, 4, 1, st.bd, render_sr=32000)
+    from termdaw_b200 import segment_output_frames
+    assert out.size == segment_output_frames(gpulib, s["psr"], s["bl"], 32000, 4, 4)[1] * 2 * (st.bd // 8)
+    st.close()
 
 
 @pytest.mark.gpu

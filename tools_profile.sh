@@ -4,7 +4,7 @@
 TAG=${1:-s1}
 PASS='regex:k_(fx|voice|bp_|norm_|sample_|quant|resample|scan)'
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -c 400 gpurun_out/bench_$TAG.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>&1
+[ -n "$SKIP_REF" ] || python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>&1
 # launch list of the SAME command line as the bench (per-launch device time, cold cache, serialised)
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$PASS" -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
