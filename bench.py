@@ -296,6 +296,7 @@ class BatchRunner:
         return {"device_ms": s1["device_ms"] + s2["device_ms"], "launches": s1["kernel_launches"] + s2["kernel_launches"],
                 "h2d": ev_bytes + s1["h2d_bytes"] + s2["h2d_bytes"], "d2h": s2["d2h_bytes"], "kstats": ks,
                 "algo": s1["algorithmic_bytes"] + s2["algorithmic_bytes"], "plan_ms": s1["plan_ms"] + s2["plan_ms"],
+                "reused_v": s2.get("reused_vertices", 0), "reused_b": s2.get("reused_bytes", 0),
                 "collectives": 0}
 
     def close(self):
@@ -349,6 +350,7 @@ class TimeShardRunner:
         return {"device_ms": s1["device_ms"] + s2["device_ms"], "launches": s1["kernel_launches"] + s2["kernel_launches"],
                 "h2d": ev_bytes + s1["h2d_bytes"] + s2["h2d_bytes"], "d2h": s2["d2h_bytes"], "kstats": ks,
                 "algo": s1["algorithmic_bytes"] + s2["algorithmic_bytes"], "plan_ms": s1["plan_ms"] + s2["plan_ms"],
+                "reused_v": s2.get("reused_vertices", 0), "reused_b": s2.get("reused_bytes", 0),
                 "collectives": c.collectives() - col0}
 
     def close(self):
@@ -405,9 +407,11 @@ def main():
     sampler.start()
     t0 = time.perf_counter()
     dev_ms, launches, kstats, algo, plan_ms, collectives = 0.0, 0, {}, 0, 0.0, 0
+    reused_v = reused_b = 0
     for _ in range(args.steps):
         r = R.step(False)
         dev_ms += r["device_ms"]; launches += r["launches"]; algo += r["algo"]; plan_ms += r["plan_ms"]
+        reused_v += r.get("reused_v", 0); reused_b += r.get("reused_b", 0)
         collectives += r["collectives"]
         _merge_kstats(kstats, r["kstats"])
     barrier()
@@ -476,6 +480,12 @@ def main():
                 "algorithmic_gb_per_step": algo / args.steps / 1e9,
                 "whole_step_algorithmic_gbs": algo / (dev_ms / 1e3) / 1e9,
                 "nccl_exchange_rounds_per_step": collectives // args.steps,
+                # the render reads vertices whose whole cone Graph::set_time resets from the scan before it instead
+                # of evaluating them twice (tdg_set_pass_reuse): algorithmic_gb_per_step is what the
+                # launched kernels move; SURVEY 8(d)'s both-passes-evaluate-everything figure is that plus the skipped
+                "pass_reuse": {"vertices_read_from_scan_per_step": reused_v // args.steps,
+                               "algorithmic_gb_not_moved_per_step": reused_b / args.steps / 1e9,
+                               "survey_8d_algorithmic_gb_per_step": (algo + reused_b) / args.steps / 1e9},
             },
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "realtime_factor": e2e_value / PSR,

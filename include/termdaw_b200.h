@@ -228,6 +228,8 @@ typedef struct tdg_pass_stats {
     uint64_t algorithmic_bytes;
     uint64_t frames;         /* project-rate frames rendered                                        */
     uint64_t voice_frames;   /* voice-frames evaluated by the synth kernels                         */
+    uint64_t reused_vertices;/* render after a scan: vertices read from the scan's resident buffers  */
+    uint64_t reused_bytes;   /* ... and the algorithmic bytes their evaluation would have moved      */
 } tdg_pass_stats;
 int tdg_last_pass_stats(tdg_ctx* ctx, tdg_pass_stats* out);
 /* Per kernel class figures of the last pass (CUDA events around every launch on the context's
@@ -239,6 +241,13 @@ typedef struct tdg_kernel_stat {
     uint64_t algorithmic_bytes;
 } tdg_kernel_stat;
 int tdg_set_profiling(tdg_ctx* ctx, int on);
+/* Pass-invariant cones: a render that directly follows a normalize scan of the same,
+ * unedited context reads the buffers of vertices whose whole input cone carries no state from pass to
+ * pass (sample loops, synth / debug-sine voices, sums and band passes over such inputs: everything
+ * Graph::set_time resets, extensions.rs:196-204) from the scan instead of evaluating them again; the
+ * values are the scan's own, so the result is bit-identical.  On by default; 0 evaluates every vertex in
+ * both passes as the reference does (graph.rs:222-237 then state.rs:545-574).  Device-wide setting. */
+int tdg_set_pass_reuse(tdg_ctx* ctx, int on);
 /* Batched calls (tdg_*_many) over more than `projects_per_group` projects are software-pipelined in
  * groups of that size over two streams: host planning of group g+1 and the PCM device->host copy of
  * group g-1 overlap the kernels of group g.  0 = one launch sequence for the whole batch (what the

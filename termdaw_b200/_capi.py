@@ -36,7 +36,8 @@ class PassStats(C.Structure):
     _fields_ = [("device_ms", C.c_double), ("plan_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
-                ("frames", C.c_uint64), ("voice_frames", C.c_uint64)]
+                ("frames", C.c_uint64), ("voice_frames", C.c_uint64), ("reused_vertices", C.c_uint64),
+                ("reused_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -125,6 +126,7 @@ class Library:
         "normalize_state_device_ptr": (C.c_void_p, [C.c_void_p, c_i32p]),
         "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
         "set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+        "set_pass_reuse": (C.c_int, [C.c_void_p, C.c_int]),
         "reset_vertex_state": (C.c_int, [C.c_void_p]),
         "set_pipeline_group": (C.c_int, [C.c_void_p, C.c_uint32]),
         "last_pass_kernel_stats": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_int]),
@@ -352,6 +354,10 @@ class Context:
 
     def set_profiling(self, on: bool = True):
         self._chk(self.lib.set_profiling(self.h, int(on)))
+
+    def set_pass_reuse(self, on: bool = True):
+        """tdg_set_pass_reuse: render reads pass-invariant cones from the scan before it (device-wide)."""
+        self._chk(self.lib.set_pass_reuse(self.h, int(on)))
 
     def set_pipeline_group(self, n: int):
         self._chk(self.lib.set_pipeline_group(self.h, int(n)))

@@ -119,6 +119,8 @@ static const int kLanes = 4, kSlots = 6;
 struct Lane {
     cudaStream_t stream = nullptr;
     DevBuf work;
+    DevBuf keep;                       // buffers a normalize scan leaves for the render behind it (KeepRecord)
+    uint64_t keep_epoch = 0;           // bumped whenever a scan job lays its kept buffers out in `keep`
     Slot slots[kSlots];
 };
 // Persistent host workers for the planner: projects of a batch are planned independently, and a job of a
@@ -187,6 +189,8 @@ struct Engine {
     bool profiling = false;                      // CUDA events around every launch (per-class roofline)
     uint32_t pipeline_group = 64;                // projects per pipelined group (0 = never pipeline)
     uint64_t hwm_work = 0, hwm_blob = 0, hwm_pcm = 0;         // largest work arena / plan blob any lane or slot has needed
+    uint64_t hwm_keep = 0;
+    bool reuse = true;                           // render reads pass-invariant cones from the scan (TDG_PASS_REUSE=0 / tdg_set_pass_reuse)
     WorkerPool* pool = nullptr;                  // planner threads (created on first batched pass)
     std::vector<Frag>* frags = nullptr;          // pooled per-project plan fragments (capacity is kept between jobs)
     std::vector<PlanScratch>* scratch = nullptr; // per worker: event-table scratch vectors
@@ -226,6 +230,7 @@ static Engine* engine_get(int device, std::string* err) {
     for (int i = 0; i < kLanes; ++i) cudaEventCreate(&g->ev_batch1[i]);
     if (const char* e = getenv("TDG_LANES")) g->n_lanes = std::max(1, std::min(kLanes, atoi(e)));
     if (const char* e = getenv("TDG_TAPER")) g->taper = atoi(e) != 0;
+    if (const char* e = getenv("TDG_PASS_REUSE")) g->reuse = atoi(e) != 0;
     g->refs = 1;
     g_engines[device] = g;
     return g;
@@ -620,6 +625,11 @@ struct PassReq {
     const float* sincs = nullptr;
     std::vector<ResampleChunk> rs_chunks;
     int64_t halo_off = -1;             // time-sharded resampling: [x_ranks][2][kResampleHalo] floats (arena offset)
+    // pass-invariant cones (KeepRecord): vertices the render pass does not evaluate, and buffers living in the
+    // lane's keep arena (written by the scan pass / read by the render pass)
+    std::vector<char> skip;
+    std::vector<int64_t> keep_rel;     // per vertex: keep-arena offset, -1 = work arena
+    bool keep_write = false, keep_read = false;
     uint64_t out_frames = 0;
     uint32_t err_flag = 0;
 };
@@ -671,14 +681,14 @@ struct Frag {
     HeapBlob blob; uint64_t base = 0;
     std::vector<LevelTasks> levels;
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
-    uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, algo = 0;
+    uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, algo = 0, reused_v = 0, reused_b = 0;
     void reset(size_t n_levels) {        // pooled on the engine: capacities survive from job to job
         blob.v.clear(); base = 0;
         if (levels.size() > n_levels) levels.resize(n_levels);
         for (LevelTasks& L : levels) L.clear();
         levels.resize(n_levels);
         quants.clear(); resamps.clear();
-        quant_max = quant_bytes = resamp_max = resamp_bytes = algo = 0;
+        quant_max = quant_bytes = resamp_max = resamp_bytes = algo = reused_v = reused_b = 0;
     }
 };
 struct PlanScratch { std::vector<MultiHit> mhits; std::vector<LerpHit> lhits; SegOut so; };
@@ -709,7 +719,7 @@ struct PassJob {
     std::vector<Off> offs;
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, quant_off = 0, resamp_off = 0;
-    uint64_t algo_bytes_total = 0;
+    uint64_t algo_bytes_total = 0, reused_v = 0, reused_b = 0;
     double t_start = 0, t_planned = 0, t_h2d_issued = 0, t_d2h0 = 0, t_submitted = 0;
     float dev_t0 = 0, dev_t1 = 0, dev_tdone = 0;      // device timeline relative to the batch start (trace only)
     uint64_t launches = 0, collectives = 0, d2h_bytes = 0, h2d_bytes = 0;
@@ -728,7 +738,8 @@ static int pass_plan(PassJob& J) {
     g->epoch++;
 
     // ---- 1. graph analysis + work-arena layout -------------------------------------------------
-    Bump bump, pbump;
+    Bump bump, pbump, kbump;
+    const int lane_index = (int)(J.lane - g->lanes);
     int& max_level = J.max_level;
     max_level = -1;
     for (auto& r : reqs) {
@@ -752,9 +763,52 @@ static int pass_plan(PassJob& J) {
         std::vector<std::vector<int>> by_level(max_level + 1);
         for (int v = 0; v < V; ++v) if (r.level[v] >= 0) by_level[r.level[v]].push_back(v);
         std::vector<char> freed(V, 0);
+        // ---- pass-invariant cones.  A vertex is pass-invariant when the render pass that follows a normalize
+        // scan evaluates it to the very values the scan produced: its kind carries no state across set_time
+        // (sample loop restarts at 0, synth / debug-sine voices are cleared, band pass re-seeds from its first
+        // frame: extensions.rs:196-204, 664-670), it starts the scan from that reset state, and every input is
+        // pass-invariant.  The scan keeps the buffers such cones hand to the rest of the graph; the render reads
+        // them (same kernels, same bits: they ARE the scan's output) instead of evaluating the cone again.
+        r.skip.assign(V, 0); r.keep_rel.assign(V, -1); r.keep_write = r.keep_read = false;
+        const bool plain = g->reuse && !r.segment && r.x_ranks == 1 && !x->taps && r.emit0 == 0 && r.emit_n == r.total &&
+                           x->output >= 0 && r.emit_n > 0;
+        KeepRecord& K = x->keep;
+        if (!r.is_scan) {
+            r.keep_read = plain && K.valid && K.lane == lane_index && K.epoch == ln.keep_epoch && ln.keep.p != nullptr &&
+                          K.mut_gen == x->mut_gen && K.total == r.total && K.n_pad == r.n_pad && (int)K.inv.size() == V &&
+                          x->t == 0 && x->fb_frame == 0;
+            K.valid = false;                                   // consumed, or stale: the next scan writes a new record
+        } else {
+            K.valid = false;
+            if (plain) {
+                K.inv.assign(V, 0); K.off.assign(V, -1);
+                for (int L = 0; L <= max_level; ++L) for (int v : by_level[L]) {
+                    const HVertex& hv = x->verts[v];
+                    bool inv = false;
+                    switch (hv.kind) {
+                        case K_SAMPLE_LOOP: inv = hv.loop_t == 0; break;
+                        case K_DEBUG_SINE: inv = hv.dnotes.empty(); break;
+                        case K_SYNTH: inv = hv.notes.empty(); break;
+                        case K_SUM: inv = true; break;
+                        case K_BANDPASS: inv = hv.bp_first || hv.wet < 0.0001f || (hv.lgamma == 0.0f && hv.hgamma == 0.0f); break;
+                        default: break;
+                    }
+                    if (inv) for (int u : hv.edges) if (!K.inv[u]) { inv = false; break; }
+                    K.inv[v] = inv ? 1 : 0;
+                }
+                // frontier: invariant vertices consumed by a vertex that is not (or the output itself)
+                std::vector<char> fr(V, 0);
+                for (int v = 0; v < V; ++v) if (r.level[v] >= 0 && !K.inv[v]) for (int u : x->verts[v].edges) if (K.inv[u]) fr[u] = 1;
+                if (K.inv[x->output]) fr[x->output] = 1;
+                for (int v = 0; v < V; ++v) if (fr[v]) { r.keep_rel[v] = (int64_t)kbump.alloc(slot_bytes); K.off[v] = r.keep_rel[v]; r.keep_write = true; }
+                K.lane = lane_index; K.mut_gen = x->mut_gen; K.total = r.total; K.n_pad = r.n_pad;
+            }
+        }
         for (int L = 0; L <= max_level; ++L) {
             for (int v : by_level[L]) {
-                if (!free_slots.empty()) { r.buf_off[v] = (int64_t)free_slots.back(); free_slots.pop_back(); }
+                if (r.keep_read && K.inv[v]) { r.skip[v] = 1; r.keep_rel[v] = K.off[v]; continue; }    // not evaluated; kept buffer if frontier
+                if (r.keep_rel[v] >= 0) { /* scan pass: this buffer lives in the keep arena */ }
+                else if (!free_slots.empty()) { r.buf_off[v] = (int64_t)free_slots.back(); free_slots.pop_back(); }
                 else r.buf_off[v] = (int64_t)bump.alloc(slot_bytes);
                 const HVertex& hv = x->verts[v];
                 if (hv.kind == K_NORMALIZE) r.aux_off[v] = (int64_t)bump.alloc(r.emit_n * 2 * 4 + 16);     // peaks, runmax
@@ -763,7 +817,7 @@ static int pass_plan(PassJob& J) {
             if (!x->taps)
                 for (int v : by_level[L])
                     for (int u : x->verts[v].edges)
-                        if (!freed[u] && r.last_use[u] == L && u != x->output) { freed[u] = 1; free_slots.push_back((uint64_t)r.buf_off[u]); }
+                        if (!freed[u] && r.last_use[u] == L && u != x->output && r.buf_off[u] >= 0) { freed[u] = 1; free_slots.push_back((uint64_t)r.buf_off[u]); }
         }
         if (r.x_ranks > 1) {
             // exchange slots: per level [normalize peaks][band-pass maps]; identical on every rank
@@ -818,6 +872,19 @@ static int pass_plan(PassJob& J) {
     g->hwm_work = std::max<uint64_t>(g->hwm_work, bump.off + 256);
     CU(ln.work.ensure(bump.off + 256, g->hwm_work));
     uint8_t* W = J.W = ln.work.p;
+    if (kbump.off) {
+        // a scan job lays its kept buffers out from the start of the lane's keep arena: whatever an earlier
+        // scan on this lane left there is gone (epoch), and growing it waits for the device (cudaFree)
+        g->hwm_keep = std::max<uint64_t>(g->hwm_keep, kbump.off + 256);
+        CU(ln.keep.ensure(kbump.off + 256, g->hwm_keep));
+        ++ln.keep_epoch;
+    }
+    for (auto& r : reqs) {
+        if (r.keep_write) r.c->keep.epoch = ln.keep_epoch;
+        // kept buffers are addressed like every other buffer, as an offset from the work arena's base
+        for (size_t v = 0; v < r.keep_rel.size(); ++v)
+            if (r.keep_rel[v] >= 0) r.buf_off[v] = (int64_t)((ln.keep.p + r.keep_rel[v]) - W);
+    }
     g->hwm_pcm = std::max<uint64_t>(g->hwm_pcm, pbump.off + 256);
     CU(ln.slots[J.slot].pcm.ensure(pbump.off + 256, g->hwm_pcm));
     uint8_t* P = J.P = ln.slots[J.slot].pcm.p;
@@ -867,6 +934,7 @@ static int pass_plan(PassJob& J) {
         for (int v = 0; v < V; ++v) {
             if (r.level[v] < 0) continue;
             HVertex& hv = x->verts[v];
+            if (r.skip[v]) { ++F.reused_v; F.reused_b += 8ull * (hv.edges.size() + 1) * r.n_frames; continue; }   // the scan's buffer stands
             LevelTasks& LT = levels[r.level[v]];
             TaskHdr h;
             h.out_l = reinterpret_cast<float*>(W + r.buf_off[v]);
@@ -1128,6 +1196,7 @@ static int pass_plan(PassJob& J) {
     std::vector<ResampleTask>& resamps = J.resamps; uint64_t &resamp_max = J.resamp_max, &resamp_bytes = J.resamp_bytes;
     uint64_t& algo_bytes_total = J.algo_bytes_total;
     quants.clear(); resamps.clear(); quant_max = quant_bytes = resamp_max = resamp_bytes = algo_bytes_total = 0;
+    J.reused_v = J.reused_b = 0;
     {
         uint64_t tot = 0;
         for (size_t i = 0; i < n_frags; ++i) { Frag& F = frags[i]; F.base = align_up(tot, 256); tot = F.base + F.blob.v.size(); }
@@ -1164,7 +1233,7 @@ static int pass_plan(PassJob& J) {
             for (QuantTask& t : F.quants) quants.push_back(t);
             quant_max = std::max(quant_max, F.quant_max); quant_bytes += F.quant_bytes;
             resamp_max = std::max(resamp_max, F.resamp_max); resamp_bytes += F.resamp_bytes;
-            algo_bytes_total += F.algo;
+            algo_bytes_total += F.algo; J.reused_v += F.reused_v; J.reused_b += F.reused_b;
         }
     }
     // task arrays go into the blob too: one H2D for the whole pass
@@ -1335,6 +1404,7 @@ static int pass_submit(PassJob& J) {
     }
     if (any_out) CU(cudaMemcpyAsync(sl.err_host, J.P + J.err_base, J.err_bytes, cudaMemcpyDeviceToHost, cs));
     CU(cudaEventRecord(sl.ev_done, cs));
+    for (auto& r : reqs) if (r.keep_write) r.c->keep.valid = true;      // the scan's kernels are queued: the record stands
     J.submitted = true;
     J.t_submitted = now_ms();
     if (trace_on()) fprintf(stderr, "[tdg] submit lane %d: enqueue %.2f ms, %llu launches\n", (int)(J.lane - g->lanes), now_ms() - J.t_planned, (unsigned long long)launches);
@@ -1410,6 +1480,7 @@ static int pass_wait(PassJob& J) {
         x->launches += launches;
         for (int k = 0; k < KC_COUNT; ++k) x->kstats[k] = ks[k];
         if (reqs.size() > 1) x->stats.algorithmic_bytes = algo_bytes_total;
+        x->stats.reused_vertices = J.reused_v; x->stats.reused_bytes = J.reused_b;
         if (r.err_flag) rc = x->fail(TDG_ERR_TOO_WIDE, "sample too wide for bit depth (hound TooWide; the reference panics)");
     }
     return rc;
@@ -1478,7 +1549,7 @@ static int run_jobs_pipelined(Engine* g, std::vector<PassJob>& jobs, PassStats* 
         (void)x;
         tot.plan_ms += J.t_planned - J.t_start; tot.h2d_ms += J.t_h2d_issued - J.t_planned;
         tot.h2d_bytes += J.h2d_bytes; tot.d2h_bytes += J.d2h_bytes; tot.kernel_launches += J.launches;
-        tot.algorithmic_bytes += J.algo_bytes_total;
+        tot.algorithmic_bytes += J.algo_bytes_total; tot.reused_vertices += J.reused_v; tot.reused_bytes += J.reused_b;
         for (PassReq& r : J.reqs) { tot.frames += r.n_frames; }
         for (int q = 0; q < KC_COUNT; ++q) { ks_out[q].launches += J.ks[q].launches; ks_out[q].ms += J.ks[q].ms; ks_out[q].bytes += J.ks[q].bytes; }
     }
@@ -1722,13 +1793,15 @@ int tdg_floww_add(tdg_ctx* h, const float* t, const float* note, const float* ve
         if (i && f.fe[i] < f.fe[i - 1]) return c->fail(TDG_ERR_UNSORTED, "floww events must be sorted by time");
     }
     c->flowws.push_back(std::move(f));
+    ++c->mut_gen;
     return (int)c->flowws.size() - 1;
 }
-int tdg_floww_reset(tdg_ctx* h) { h->c.flowws.clear(); h->c.fb_frame = 0; return TDG_OK; }     // floww.rs:21-28
+int tdg_floww_reset(tdg_ctx* h) { h->c.flowws.clear(); h->c.fb_frame = 0; ++h->c.mut_gen; return TDG_OK; }     // floww.rs:21-28
 
 int tdg_graph_reset(tdg_ctx* h) {                                           // graph.rs:39-47
     Ctx* c = C_;
     c->verts.clear(); c->output = -1; c->t = 0;
+    ++c->mut_gen; c->keep = KeepRecord();
     c->vstate_host.clear(); c->vstate_host_newer = true;
     c->last_buf_off.clear();
     return TDG_OK;
@@ -1751,6 +1824,7 @@ int tdg_reset_vertex_state(tdg_ctx* h) {                                    // s
     }
     c->vstate_host_newer = true;         // the device copy is stale; no read-back needed
     c->t = 0;
+    ++c->mut_gen;
     return TDG_OK;
 }
 
@@ -1759,6 +1833,7 @@ static int add_vertex(Ctx* c, HVertex v, float gain, float angle, float wet) {
     v.angle = fmaxf(fminf(angle, 90.0f), -90.0f);                           // graph.rs:255
     v.wet = fmaxf(fminf(wet, 1.0f), 0.0f);                                  // graph.rs:256
     if (vstate_to_host(c) != TDG_OK) return TDG_ERR_CUDA;
+    ++c->mut_gen;
     c->verts.push_back(std::move(v));
     c->vstate_host.resize(c->verts.size() * 8, 0.0f);
     vstate_init(&c->vstate_host[(c->verts.size() - 1) * 8], c->verts.back().kind);
@@ -1866,11 +1941,12 @@ int tdg_connect(tdg_ctx* h, int a, int b) {                                 // g
     if (!c->verts[b].has_input()) return 0;
     if (has_loop(c, a, b)) return 0;
     c->verts[b].edges.push_back(a);
+    ++c->mut_gen;
     return 1;
 }
 int tdg_set_output(tdg_ctx* h, int v) {
     if (v < 0 || (size_t)v >= h->c.verts.size()) return h->c.fail(TDG_ERR_INVALID, "unknown vertex");
-    h->c.output = v; return TDG_OK;
+    h->c.output = v; ++h->c.mut_gen; return TDG_OK;
 }
 int tdg_check_graph(tdg_ctx* h, int* unreachable, int cap, int* n_unreachable) {   // graph.rs:150-174
     Ctx* c = C_;
@@ -1926,6 +2002,7 @@ void* tdg_normalize_state_device_ptr(tdg_ctx* h, int* n_floats) {
 
 static void graph_set_time(Ctx* c, uint64_t time) {                         // graph.rs:123-128 + extensions.rs:196-204
     c->t = time;
+    ++c->mut_gen;
     for (HVertex& hv : c->verts) {
         if (hv.kind == K_SAMPLE_LOOP) hv.loop_t = time;
         else if (hv.kind == K_DEBUG_SINE) hv.dnotes.clear();
@@ -1941,9 +2018,9 @@ uint64_t tdg_change_time(tdg_ctx* h, uint64_t delta, int plus) {            // g
     return nt;
 }
 uint64_t tdg_get_time(tdg_ctx* h) { return h->c.t; }
-int tdg_floww_set_time(tdg_ctx* h, uint64_t frame) { h->c.fb_frame = frame; return TDG_OK; }   // floww.rs:83-86
+int tdg_floww_set_time(tdg_ctx* h, uint64_t frame) { h->c.fb_frame = frame; ++h->c.mut_gen; return TDG_OK; }   // floww.rs:83-86
 
-int tdg_enable_taps(tdg_ctx* h, int on) { h->c.taps = on != 0; return TDG_OK; }
+int tdg_enable_taps(tdg_ctx* h, int on) { h->c.taps = on != 0; ++h->c.mut_gen; return TDG_OK; }
 int tdg_read_vertex_buffer(tdg_ctx* h, int vertex, uint64_t frame0, uint64_t n, float* l, float* r) {
     Ctx* c = C_;
     if (vertex < 0 || (size_t)vertex >= c->last_buf_off.size() || c->last_buf_off[vertex] < 0)
@@ -2128,6 +2205,7 @@ int tdg_comm_destroy(tdg_ctx* h) {
 }
 uint64_t tdg_collectives(tdg_ctx* h) { return h ? h->c.collectives : 0; }
 
+int tdg_set_pass_reuse(tdg_ctx* h, int on) { h->c.eng->reuse = on != 0; h->c.keep.valid = false; return TDG_OK; }
 int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; return TDG_OK; }
 int tdg_set_pipeline_group(tdg_ctx* h, uint32_t projects_per_group) { h->c.eng->pipeline_group = projects_per_group; return TDG_OK; }
 int tdg_last_pass_kernel_stats(tdg_ctx* h, tdg_kernel_stat* out, int cap) {
@@ -2148,6 +2226,7 @@ int tdg_last_pass_stats(tdg_ctx* h, tdg_pass_stats* out) {
     out->device_ms = s.device_ms; out->plan_ms = s.plan_ms; out->h2d_ms = s.h2d_ms; out->d2h_ms = s.d2h_ms;
     out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes; out->kernel_launches = s.kernel_launches;
     out->algorithmic_bytes = s.algorithmic_bytes; out->frames = s.frames; out->voice_frames = s.voice_frames;
+    out->reused_vertices = s.reused_vertices; out->reused_bytes = s.reused_bytes;
     return TDG_OK;
 }
 

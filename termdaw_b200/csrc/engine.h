@@ -56,6 +56,20 @@ struct KStat { uint64_t launches = 0, bytes = 0; double ms = 0; };
 struct PassStats {
     double device_ms = 0, plan_ms = 0, h2d_ms = 0, d2h_ms = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0, kernel_launches = 0, algorithmic_bytes = 0, frames = 0, voice_frames = 0;
+    uint64_t reused_vertices = 0, reused_bytes = 0;     // render pass: vertices (and their algorithmic bytes) taken from the scan pass
+};
+
+// What a normalize scan leaves behind for the render that follows it (DESIGN.md "pass-invariant cones"):
+// the buffers of vertices whose whole input cone evaluates identically in both passes stay resident in
+// the lane's keep arena, and the render pass reads them instead of evaluating the cone again.
+struct KeepRecord {
+    bool valid = false;
+    int lane = -1;
+    uint64_t epoch = 0;                      // the lane's keep-arena generation the buffers were written in
+    uint64_t mut_gen = 0;                    // Ctx::mut_gen at the scan
+    uint64_t total = 0, n_pad = 0;           // chunks / padded frames of the scan pass
+    std::vector<char> inv;                   // per vertex: pass-invariant
+    std::vector<int64_t> off;                // per vertex: keep-arena offset of a kept (frontier) buffer, else -1
 };
 
 struct Engine;
@@ -87,6 +101,8 @@ struct Ctx {
     KStat kstats[KC_COUNT];                  // per kernel class, last pass (profiling on)
     uint64_t launches = 0, collectives = 0;
     void* nccl_comm = nullptr; int x_ranks = 1, x_rank = 0;      // time sharding over NCCL (tdg_comm_init_rank)
+    uint64_t mut_gen = 0;                    // bumped by every call that edits the project or its transport state
+    KeepRecord keep;
     int fail(int code, const std::string& m) { err = m; return code; }
 };
 
