@@ -63,8 +63,13 @@ class Assets:
     def floww(self, path: str):
         if path in self.flowws:
             return self.flowws[path]
-        raise FileNotFoundError(f"Could not read midi file: \"{path}\" (MIDI parsing is outside the ported path; "
-                                "register the event stream in Assets.flowws)")
+        if os.path.exists(path):                        # FlowwBank::add_floww -> read_floww_from_midi (floww.rs:40-48)
+            from .midi import MidiError, read_floww_from_midi
+            try:
+                return read_floww_from_midi(path)
+            except (MidiError, OSError):
+                pass
+        raise FileNotFoundError(f"Could not read midi file: \"{path}\".")                  # floww.rs:45-46
 
     def blob(self, path: str) -> bytes:
         if path in self.blobs:

@@ -156,6 +156,34 @@ def test_pipelined_batches_equal_oracle(gpulib, oracle, group):
             st.close()
 
 
+def test_pipelined_ramp_and_taper_groups(gpulib, oracle):
+    """41 projects in groups of 16: the call is cut into a ramp group of 8, full groups and a tapered tail
+    (run_scan_render_pipelined); every project must still equal the oracle, and the batch with one launch
+    sequence, bit for bit."""
+    from termdaw_b200 import normalize_render_many
+    from termdaw_b200.state import State
+    cfgs = [S.config_5_project(i, 0.02) for i in range(41)]
+    got = {}
+    for group in (16, 0):
+        states = []
+        for p, a, s in cfgs:
+            st = State(gpulib, s["psr"], s["bl"], assets=a)
+            assert st.refresh(p), st.messages
+            states.append(st)
+        ctxs = [st.ctx for st in states]
+        ctxs[0].set_pipeline_group(group)
+        got[group] = [x.copy() for x in normalize_render_many(gpulib, ctxs, [st.cs for st in states],
+                                                              [st.render_sr for st in states], [st.bd for st in states])]
+        ctxs[0].set_pipeline_group(64)
+        for st in states:
+            st.close()
+    for i, (p, a, s) in enumerate(cfgs):
+        assert np.array_equal(got[16][i], got[0][i]), i
+        want = run_project(oracle, p, a, s, taps=False)
+        x, y = pcm_to_int(got[16][i], want["bd"]), pcm_to_int(want["pcm"], want["bd"])
+        assert x.shape == y.shape and np.abs(x - y).max() <= 1, i
+
+
 @pytest.mark.parametrize("bd", [8, 16, 24, 32])
 def test_bitdepths(gpulib, oracle, bd):
     """quantisation to every supported depth (state.rs:515-532) on a bit-exact graph."""
