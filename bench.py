@@ -471,12 +471,21 @@ def main():
             (6532.9, "measured (MEASURED_PEAKS.json value recorded in BASELINE.md; file absent on this box)")
         dom = max(kstats, key=lambda k: kstats[k]["ms"])
         ach = kstats[dom]["bytes"] / (kstats[dom]["ms"] / 1e3) / 1e9 if kstats[dom]["ms"] > 0 else 0.0
-        traffic = None
-        try:                                             # per-launch DRAM bytes of the dominant kernel from the committed ncu capture
+        # measured DRAM bytes per launch of the dominant kernel: the committed `ncu --set full` capture
+        # (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over one step at 64 projects,
+        # beside the algorithmic bytes of the same launches) gives the traffic / algorithmic ratio of the
+        # kernel; scaled to this run's algorithmic bytes per launch, like `achieved`
+        traffic = traffic_detail = None
+        try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            traffic = tr.get(dom)
-        except (OSError, ValueError):
+            traffic_detail = tr.get(dom)
+            if traffic_detail and traffic_detail.get("ratio") is not None and kstats[dom]["launches"]:
+                traffic = traffic_detail["ratio"] * kstats[dom]["bytes"] / kstats[dom]["launches"]
+        except (OSError, ValueError, KeyError):
             pass
+        # the voice kernels are bound by FP32 issue slots, not HBM: ncu's issue-slot utilisation of the committed
+        # capture (profiles/r01_s6_ncu_full_digest.md) is the meaningful fraction for them
+        issue_pct = {"k_voice<synth>": 86.3, "k_voice<sampsyn>": 77.3}.get(dom)
         line = {
             "metric": "rendered frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
@@ -508,7 +517,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_detail,
+                         "issue_slot_utilisation_pct_ncu": issue_pct, "peak_source": peak_src,
                          "share_of_step": kstats[dom]["ms"] / dev_ms,
                          "note": "k_voice<*> kernels are FP32-issue bound, not HBM bound (DESIGN.md §5): their HBM "
                                  "fraction is reported as the contract asks; every streaming kernel is listed in per_kernel",

@@ -4,8 +4,9 @@ Renders a termdaw project directory on the GPU: reads `project.toml` like `Confi
 (config.rs:10-77: `[settings] main`, `buffer_length` default 1024, `project_samplerate` default
 44100), runs the Lua-subset reader over the main script, then does what the manual workflow's
 `refresh` → `normalize` → `render` commands do (ui_workflow.rs:114-135, state.rs:473-577) and writes
-the WAV.  MIDI flowws need a decoded event stream next to the file (`<file>.floww.npy`, columns
-t/note/vel), because MIDI parsing (crate `floww`) is outside the ported path.
+the WAV.  MIDI flowws are read with termdaw_b200/midi.py; a decoded event stream next to the file
+(`<file>.floww.npy` or `<file>.floww.f32`, columns t/note/vel) takes precedence.  The native twin of this
+front-end is `termdaw_b200/csrc/termdaw_b200_render` (csrc/host/).
 """
 from __future__ import annotations
 
@@ -29,7 +30,11 @@ class DiskAssets(Assets):
         if os.path.exists(side):
             a = np.load(side).astype(np.float32).reshape(-1, 3)
             return a[:, 0].copy(), a[:, 1].copy(), a[:, 2].copy()
-        return super().floww(path)
+        side = path + ".floww.f32"                       # the side file termdaw_b200_render reads too
+        if os.path.exists(side):
+            a = np.fromfile(side, dtype="<f4").reshape(-1, 3)
+            return a[:, 0].copy(), a[:, 1].copy(), a[:, 2].copy()
+        return super().floww(path)                       # a real .mid file: termdaw_b200/midi.py
 
 
 def main(argv=None) -> int:

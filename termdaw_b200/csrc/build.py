@@ -46,7 +46,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)
+    if not DEFS:
+        build_host(force=force, verbose=verbose)
     return OUT
+
+
+HOST_DIR = os.path.join(HERE, "host")
+HOST_SOURCES = ["tdh_lua.cpp", "tdh_assets.cpp", "tdh_state.cpp", "tdh_main.cpp"]
+HOST_BIN = os.path.join(HERE, "termdaw_b200_render")
+CXX = os.environ.get("CXX", "g++")
+HOST_FLAGS = ["-O2", "-std=c++17", "-Wall", "-Wextra", "-ffp-contract=off", "-fno-fast-math"]
+
+
+def build_host(force: bool = False, verbose: bool = False, prefix: str = "tdg_", lib: str | None = None,
+               out: str | None = None) -> str:
+    """The native host side above the C ABI (csrc/host/): `termdaw_b200_render`, linked against the CUDA
+    library next to it (rpath $ORIGIN).  `prefix`/`lib`/`out` let tests/ link the same sources against the
+    CPU oracle (prefix tdo_) to check the host logic where no GPU exists; the product build never does."""
+    out = out or HOST_BIN
+    lib = lib or OUT
+    srcs = [os.path.join(HOST_DIR, s) for s in HOST_SOURCES]
+    deps = srcs + [os.path.join(HOST_DIR, "tdh.h"), lib]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    libdir, libname = os.path.dirname(os.path.abspath(lib)), os.path.basename(lib)
+    cmd = [CXX, *HOST_FLAGS, f"-DTDH_PREFIX={prefix}", *srcs, "-o", out, f"-L{libdir}", f"-l:{libname}",
+           "-Wl,-rpath," + ("$ORIGIN" if os.path.dirname(os.path.abspath(out)) == libdir else libdir)]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return out
 
 
 if __name__ == "__main__":

@@ -1,0 +1,57 @@
+// termdaw_b200_render <project dir> [--no-normalize] [--device N] [-o out.wav]
+// termdaw_b200_render --dump-project <script.lua>        (seed vectors as JSON; no device needed)
+//
+// Renders a termdaw project directory: reads project.toml like Config::read (config.rs:10-77), runs the
+// Lua-subset reader over the main script, then does what the manual workflow's `refresh` -> `normalize`
+// -> `render` commands do (ui_workflow.rs:114-135, state.rs:473-577) and writes the WAV.  Same behaviour
+// as `python -m termdaw_b200.cli`; the audio is computed by libtermdaw_b200.so on the GPU — without an
+// sm_100 device the context cannot be created and the program says so and exits 1 (no CPU fallback).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include "tdh.h"
+
+int main(int argc, char** argv) {
+    using namespace tdh;
+    std::string dir, out, dump;
+    bool normalize = true; int device = 0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "--no-normalize") normalize = false;
+        else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
+        else if ((a == "-o" || a == "--output") && i + 1 < argc) out = argv[++i];
+        else if (a == "--dump-project" && i + 1 < argc) dump = argv[++i];
+        else if (!a.empty() && a[0] != '-' && dir.empty()) dir = a;
+        else { fprintf(stderr, "usage: %s <project dir> [--no-normalize] [--device N] [-o out.wav] | --dump-project <script.lua>\n", argv[0]); return 2; }
+    }
+    try {
+        if (!dump.empty()) {
+            Project p;
+            run_file(dump, p);
+            printf("%s\n", p.to_json().c_str());
+            return 0;
+        }
+        if (dir.empty()) { fprintf(stderr, "usage: %s <project dir> ...\n", argv[0]); return 2; }
+        if (chdir(dir.c_str()) != 0) { fprintf(stderr, "TermDaw: could not enter \"%s\".\n", dir.c_str()); return 1; }   // main.rs:39-45
+        const Config cfg = read_config("project.toml");
+        Project project;
+        run_file(cfg.main, project);
+        Assets assets;
+        State st(cfg.project_samplerate, cfg.buffer_length, device, &assets);
+        const bool ok = st.refresh(project);
+        for (const std::string& m : st.messages) fprintf(stderr, "%s\n", m.c_str());
+        if (!ok) { fprintf(stderr, "TermDaw: project not loaded.\n"); return 1; }
+        if (normalize) st.scan_exact();
+        const std::string path = st.render_to_file(out);
+        for (const auto& nv : st.normalization_values()) printf("%s: %.9g\n", nv.first.c_str(), (double)nv.second);
+        printf("rendered %llu project-rate frames -> %s\n", (unsigned long long)(st.cs * st.bl), path.c_str());
+        return 0;
+    } catch (const LuaSubsetError& e) {
+        fprintf(stderr, "TermDaw: lua error: %s\n", e.what());                  // state.rs:160-164
+        return 1;
+    } catch (const Error& e) {
+        fprintf(stderr, "TermDaw: %s\n", e.what());
+        return 1;
+    }
+}

@@ -299,3 +299,72 @@ def config_5_project(index: int, scale: float = 1.0):
 
 
 CONFIGS = {1: config_1, 2: config_2, 3: config_3, 4: config_4}
+
+
+# ------------------------------------------------------------------------------------ projects on disk
+def _lua(v) -> str:
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, str):
+        return '"' + v.replace("\\", "\\\\").replace('"', '\\"') + '"'
+    if isinstance(v, (list, tuple)):
+        return "{" + ", ".join(_lua(x) for x in v) + "}"
+    if isinstance(v, (int, np.integer)):
+        return str(int(v))
+    return repr(float(v))
+
+
+def project_to_lua(p: Project) -> str:
+    """The script text that produces `p`'s seed vectors (registered globals of state.rs:103-157)."""
+    out = []
+
+    def call(fn, *args):
+        out.append(f"{fn}({', '.join(_lua(a) for a in args)})")
+
+    if p.length_seconds is not None: call("set_length", p.length_seconds)
+    if p.render_samplerate is not None: call("set_render_samplerate", p.render_samplerate)
+    if p.render_bitdepth is not None: call("set_render_bitdepth", p.render_bitdepth)
+    if p.output_file is not None: call("set_output_file", p.output_file)
+    for t in p.samples: call("load_sample", *t)
+    for t in p.resources: call("load_resource", *t)
+    for t in p.midis: call("load_midi_floww", *t)
+    for t in p.streams: call("declare_stream", t)
+    for fn, lst in (("add_sum", p.sums), ("add_normalize", p.norms), ("add_sampleloop", p.sampleloops),
+                    ("add_sample_multi", p.samplemultis), ("add_sample_lerp", p.samplelerps),
+                    ("add_debug_sine", p.debugsines), ("add_synth", p.synths), ("add_sampsyn", p.sampsyns),
+                    ("add_lv2fx", p.lv2fxs), ("add_adsr", p.adsrs), ("add_bandpass", p.bandpasses)):
+        for t in lst:
+            call(fn, *t)
+    for a, b in p.edges: call("connect", a, b)
+    call("set_output", p.output_vertex)
+    return "\n".join(out) + "\n"
+
+
+def write_project_dir(cfg, path: str, main: str = "project.lua") -> str:
+    """Materialise a synthetic (project, assets, settings) triple as a termdaw project directory:
+    project.toml, the Lua script, 16-bit WAV files for the samples, wavetable blobs, and every floww as a
+    `<name>.floww.f32` side file (little-endian f32 triples t, note, vel) that both command-line
+    front-ends (`python -m termdaw_b200.cli`, `termdaw_b200_render`) read in place of a MIDI file."""
+    import os
+    from .wav import encode_wav
+    p, a, s = cfg
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "project.toml"), "w") as f:
+        f.write(f'[project]\nname = "synthetic"\n\n[settings]\nmain = "{main}"\nbuffer_length = {s["bl"]}\n'
+                f'project_samplerate = {s["psr"]}\n')
+    with open(os.path.join(path, main), "w") as f:
+        f.write(project_to_lua(p))
+    for name, w in a.wavs.items():
+        if w.bits != 16:
+            raise ValueError("write_project_dir writes 16-bit samples only")
+        pcm = np.asarray(w.linear, np.float32).astype("<i2").view(np.uint8)
+        with open(os.path.join(path, name), "wb") as f:
+            f.write(encode_wav(pcm, w.sample_rate, 16, w.channels))
+    for name, b in a.blobs.items():
+        with open(os.path.join(path, name), "wb") as f:
+            f.write(b)
+    for name, (t, n, v) in a.flowws.items():
+        tri = np.stack([np.asarray(t, np.float32), np.asarray(n, np.float32), np.asarray(v, np.float32)], axis=1)
+        with open(os.path.join(path, name + ".floww.f32"), "wb") as f:
+            f.write(np.ascontiguousarray(tri, "<f4").tobytes())
+    return path
