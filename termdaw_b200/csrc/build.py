@@ -70,7 +70,8 @@ def build_host(force: bool = False, verbose: bool = False, prefix: str = "tdg_",
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
         return out
     libdir, libname = os.path.dirname(os.path.abspath(lib)), os.path.basename(lib)
-    cmd = [CXX, *HOST_FLAGS, f"-DTDH_PREFIX={prefix}", *srcs, "-o", out, f"-L{libdir}", f"-l:{libname}",
+    defs = [f"-DTDH_PREFIX={prefix}"] + (["-DTDH_ORACLE"] if prefix != "tdg_" else [])
+    cmd = [CXX, *HOST_FLAGS, *defs, *srcs, "-o", out, f"-L{libdir}", f"-l:{libname}",
            "-Wl,-rpath," + ("$ORIGIN" if os.path.dirname(os.path.abspath(out)) == libdir else libdir)]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)

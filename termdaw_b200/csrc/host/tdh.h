@@ -63,6 +63,13 @@ int TDH_FN(normalize_scan)(tdg_ctx* ctx, uint64_t chunks);
 int TDH_FN(render)(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes,
                    uint64_t* frames_written);
 uint64_t TDH_FN(render_bound_bytes)(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth);
+int TDH_FN(normalize_scan_many)(tdg_ctx** ctxs, int n, const uint64_t* chunks);
+int TDH_FN(render_many)(tdg_ctx** ctxs, int n, const uint64_t* chunks, const uint32_t* render_sr, const uint32_t* bitdepth,
+                        uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written);
+#ifndef TDH_ORACLE          // CUDA library only (the oracle-linked test build defines TDH_ORACLE)
+int tdg_normalize_render_many(tdg_ctx** ctxs, int n, const uint64_t* chunks, const uint32_t* render_sr, const uint32_t* bitdepth,
+                              uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written);
+#endif
 }
 
 namespace tdh {
@@ -179,6 +186,10 @@ struct State {
     std::vector<uint8_t> render();                                                // state.rs:477-577: the data-chunk bytes
     std::string render_to_file(const std::string& path = "");
     std::vector<std::pair<std::string, float>> normalization_values();            // graph.rs:213-220
+    // The batch of independent projects (BASELINE configs[4]): "normalize" then "render" of every state in one
+    // call — tdg_normalize_render_many, pipelined over project groups — or render only (`normalize` false).
+    // Returns the data-chunk bytes per state, identical to scan_exact() + render() on each.
+    static std::vector<std::vector<uint8_t>> render_batch(const std::vector<State*>& states, bool normalize);
     void say(const std::string& m) { messages.push_back(m); }
     int chk(int rc);                                                              // rc < 0 -> throws Error(last_error)
 };

@@ -1,4 +1,5 @@
 // termdaw_b200_render <project dir> [--no-normalize] [--device N] [-o out.wav]
+// termdaw_b200_render --batch <project dir>... [--no-normalize] [-o name.wav]   (independent projects, one batched call)
 // termdaw_b200_render --dump-project <script.lua>        (seed vectors as JSON; no device needed)
 //
 // Renders a termdaw project directory: reads project.toml like Config::read (config.rs:10-77), runs the
@@ -10,15 +11,19 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <memory>
 #include "tdh.h"
 
 int main(int argc, char** argv) {
     using namespace tdh;
     std::string dir, out, dump;
-    bool normalize = true; int device = 0;
+    std::vector<std::string> batch;
+    bool normalize = true, batching = false; int device = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "--no-normalize") normalize = false;
+        else if (a == "--batch") batching = true;
+        else if (batching && !a.empty() && a[0] != '-') batch.push_back(a);
         else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
         else if ((a == "-o" || a == "--output") && i + 1 < argc) out = argv[++i];
         else if (a == "--dump-project" && i + 1 < argc) dump = argv[++i];
@@ -30,6 +35,35 @@ int main(int argc, char** argv) {
             Project p;
             run_file(dump, p);
             printf("%s\n", p.to_json().c_str());
+            return 0;
+        }
+        if (batching) {
+            // the algorithmic-composition batch (BASELINE configs[4]): every directory is one independent project;
+            // all of them are loaded, then scanned and rendered in ONE batched call, then written
+            char cwd0[4096];
+            if (!getcwd(cwd0, sizeof cwd0)) return 1;
+            Assets assets;
+            std::vector<std::unique_ptr<State>> owned; std::vector<State*> states; std::vector<std::string> dsts;
+            for (const std::string& d : batch) {
+                if (chdir(cwd0) != 0 || chdir(d.c_str()) != 0) { fprintf(stderr, "TermDaw: could not enter \"%s\".\n", d.c_str()); return 1; }
+                const Config cfg = read_config("project.toml");
+                Project project;
+                run_file(cfg.main, project);
+                owned.emplace_back(new State(cfg.project_samplerate, cfg.buffer_length, device, &assets));
+                State& st = *owned.back();
+                const bool ok = st.refresh(project);
+                for (const std::string& m : st.messages) fprintf(stderr, "%s: %s\n", d.c_str(), m.c_str());
+                if (!ok) { fprintf(stderr, "TermDaw: project \"%s\" not loaded.\n", d.c_str()); return 1; }
+                char here[4096];
+                if (!getcwd(here, sizeof here)) return 1;
+                const std::string f = out.empty() ? st.output_file : out;
+                dsts.push_back(!f.empty() && f[0] == '/' ? f : std::string(here) + "/" + f);
+                states.push_back(&st);
+            }
+            const std::vector<std::vector<uint8_t>> pcms = State::render_batch(states, normalize);
+            uint64_t frames = 0;
+            for (size_t i = 0; i < states.size(); ++i) { write_wav(dsts[i], pcms[i], states[i]->render_sr, states[i]->bd); frames += states[i]->cs * states[i]->bl; }
+            printf("rendered %zu projects, %llu project-rate frames\n", states.size(), (unsigned long long)frames);
             return 0;
         }
         if (dir.empty()) { fprintf(stderr, "usage: %s <project dir> ...\n", argv[0]); return 2; }

@@ -150,6 +150,37 @@ std::vector<uint8_t> State::render() {                                          
     return out;
 }
 
+std::vector<std::vector<uint8_t>> State::render_batch(const std::vector<State*>& states, bool normalize) {
+    const int n = (int)states.size();
+    std::vector<std::vector<uint8_t>> outs((size_t)n);
+    if (n == 0) return outs;
+    std::vector<tdg_ctx*> ctxs; std::vector<uint64_t> chunks, caps, frames((size_t)n, 0); std::vector<uint32_t> rsr, bds; std::vector<uint8_t*> ptrs;
+    for (int i = 0; i < n; ++i) {
+        State* s = states[(size_t)i];
+        ctxs.push_back(s->ctx); chunks.push_back(s->cs); rsr.push_back(s->render_sr); bds.push_back(s->bd);
+        caps.push_back(TDH_FN(render_bound_bytes)(s->ctx, s->cs, s->render_sr, s->bd));
+        outs[(size_t)i].resize(caps.back());
+        ptrs.push_back(outs[(size_t)i].data());
+    }
+    int rc = 0;
+#ifndef TDH_ORACLE
+    // "normalize" then "render" in ONE pipelined call (scan and render of a project group back to back on a
+    // stream, PCM copies of earlier groups under the kernels of later ones)
+    if (normalize) rc = tdg_normalize_render_many(ctxs.data(), n, chunks.data(), rsr.data(), bds.data(), ptrs.data(), caps.data(), frames.data());
+    else rc = TDH_FN(render_many)(ctxs.data(), n, chunks.data(), rsr.data(), bds.data(), ptrs.data(), caps.data(), frames.data());
+#else
+    // the oracle (tests only) has the two plain batched calls
+    if (normalize) rc = TDH_FN(normalize_scan_many)(ctxs.data(), n, chunks.data());
+    if (rc >= 0) rc = TDH_FN(render_many)(ctxs.data(), n, chunks.data(), rsr.data(), bds.data(), ptrs.data(), caps.data(), frames.data());
+#endif
+    if (rc < 0) {                                              // the failing context holds the message
+        for (State* s : states) { const char* e = TDH_FN(last_error)(s->ctx); if (e && *e) throw Error(e); }
+        throw Error("batched render failed");
+    }
+    for (int i = 0; i < n; ++i) outs[(size_t)i].resize(frames[(size_t)i] * 2 * (bds[(size_t)i] / 8));
+    return outs;
+}
+
 std::string State::render_to_file(const std::string& path) {
     const std::vector<uint8_t> pcm = render();
     const std::string dst = path.empty() ? output_file : path;

@@ -131,6 +131,36 @@ def test_native_host_over_the_oracle_equals_python_over_the_oracle(host_oracle_b
             assert norms[k] == pytest.approx(v, rel=1e-7)
 
 
+def _batch(binary, cfgs, root, extra=()):
+    dirs = [S.write_project_dir(c, os.path.join(root, f"proj{i}")) for i, c in enumerate(cfgs)]
+    out = subprocess.run([binary, "--batch", *dirs, "-o", "batch.wav", *extra], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert f"rendered {len(cfgs)} projects" in out.stdout
+    return [open(os.path.join(d, "batch.wav"), "rb").read() for d in dirs]
+
+
+def test_native_batch_over_the_oracle(host_oracle_bin, oracle, tmp_path):
+    """`--batch`: independent project directories through the batched calls == one by one."""
+    cfgs = [S.config_5_project(i, 0.03) for i in range(4)] + [S.config_1(0.1)]
+    for flow, extra in (("B", ()), ("A", ("--no-normalize",))):
+        wavs = _batch(host_oracle_bin, cfgs, str(tmp_path / flow), extra)
+        for cfg, wav in zip(cfgs, wavs):
+            want = run_project(oracle, *cfg, flow=flow, taps=False)
+            sr = cfg[0].render_samplerate if cfg[0].render_samplerate is not None else 48000
+            assert wav == encode_wav(want["pcm"], sr, want["bd"])
+
+
+@pytest.mark.gpu
+def test_native_batch_on_the_gpu(host_bin, gpulib, tmp_path):
+    """The pipelined batched call (tdg_normalize_render_many) driven by the native host: every project's file is
+    the file the single-project path writes."""
+    cfgs = [S.config_5_project(i, 0.05) for i in range(12)]
+    wavs = _batch(host_bin, cfgs, str(tmp_path / "b"))
+    for cfg, wav in zip(cfgs, wavs):
+        got = run_project(gpulib, *cfg, taps=False)
+        assert wav == encode_wav(got["pcm"], 48000, got["bd"])
+
+
 def test_native_host_messages_match_the_python_mirror(host_oracle_bin, oracle, tmp_path):
     """refresh() failures: same messages, project not loaded, exit code 1."""
     from termdaw_b200.cli import DiskAssets
