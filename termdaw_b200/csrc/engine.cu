@@ -753,6 +753,16 @@ static int pass_plan(PassJob& J) {
     }
     J.err_bytes = reqs.size() * 4;
     J.err_base = pbump.alloc(J.err_bytes);
+    uint64_t keep_limit = 0; bool keep_limit_known = false;
+    auto keep_fits = [&](uint64_t bytes) {
+        if (bytes + 256 <= ln.keep.cap) return true;                       // no growth: nothing to ask the driver
+        if (!keep_limit_known) {
+            size_t free_b = 0, total_b = 0;
+            keep_limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? ln.keep.cap + free_b / 2 : 0;
+            keep_limit_known = true;
+        }
+        return bytes + bytes / 4 + (2u << 20) <= keep_limit;               // DevBuf::ensure grows with 25 % headroom
+    };
     for (size_t ri = 0; ri < reqs.size(); ++ri) {
         PassReq& r = reqs[ri];
         r.err_off = J.err_base + ri * 4;
@@ -800,7 +810,12 @@ static int pass_plan(PassJob& J) {
                 std::vector<char> fr(V, 0);
                 for (int v = 0; v < V; ++v) if (r.level[v] >= 0 && !K.inv[v]) for (int u : x->verts[v].edges) if (K.inv[u]) fr[u] = 1;
                 if (K.inv[x->output]) fr[x->output] = 1;
-                for (int v = 0; v < V; ++v) if (fr[v]) { r.keep_rel[v] = (int64_t)kbump.alloc(slot_bytes); K.off[v] = r.keep_rel[v]; r.keep_write = true; }
+                // kept buffers are extra device memory: when the keep arena would have to grow past half of what is
+                // free (an hours-long single render) this project is simply evaluated twice, as before
+                uint64_t n_fr = 0;
+                for (int v = 0; v < V; ++v) n_fr += fr[v] ? 1 : 0;
+                if (n_fr && keep_fits(kbump.off + n_fr * (slot_bytes + 256)))
+                    for (int v = 0; v < V; ++v) if (fr[v]) { r.keep_rel[v] = (int64_t)kbump.alloc(slot_bytes); K.off[v] = r.keep_rel[v]; r.keep_write = true; }
                 K.lane = lane_index; K.mut_gen = x->mut_gen; K.total = r.total; K.n_pad = r.n_pad;
             }
         }
