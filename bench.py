@@ -517,7 +517,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_detail,
+                         "frac": ach / peak, "frac_of_nominal_8000_gbs": ach / 8000.0, "traffic": traffic,
+                         "traffic_source": traffic_detail,
                          "issue_slot_utilisation_pct_ncu": issue_pct, "peak_source": peak_src,
                          "share_of_step": kstats[dom]["ms"] / dev_ms,
                          "note": "k_voice<*> kernels are FP32-issue bound, not HBM bound (DESIGN.md §5): their HBM "
@@ -530,7 +531,13 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             ccfgs, sample = cpu_sample_cfgs(args)
             fr, dt = oracle_render_projects(ccfgs, 1)
-            line["cpu_baseline"] = {"value": fr / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            cpu_model = None
+            try:
+                with open("/proc/cpuinfo") as f:
+                    cpu_model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), None)
+            except OSError:
+                pass
+            line["cpu_baseline"] = {"value": fr / dt, "unit": "frames/s", "cores": 1, "kind": "port", "cpu_model": cpu_model,
                                     "sample": sample + f" ({dt:.1f} s of CPU work; restatement of the reference, not the Rust build)",
                                     "host_cores_available": os.cpu_count()}
         print_line(json.dumps(line))
