@@ -1,6 +1,8 @@
 // termdaw_b200_render <project dir> [--no-normalize] [--device N] [-o out.wav]
 // termdaw_b200_render --batch <project dir>... [--no-normalize] [-o name.wav]   (independent projects, one batched call)
 // termdaw_b200_render --dump-project <script.lua>        (seed vectors as JSON; no device needed)
+// termdaw_b200_render --dump-midi <file.mid>             (the decoded floww; no device needed)
+// termdaw_b200_render --dump-wav <file.wav>              (channels, rate, bits, values, FNV-1a of the decoded f32 stream)
 //
 // Renders a termdaw project directory: reads project.toml like Config::read (config.rs:10-77), runs the
 // Lua-subset reader over the main script, then does what the manual workflow's `refresh` -> `normalize`
@@ -16,7 +18,7 @@
 
 int main(int argc, char** argv) {
     using namespace tdh;
-    std::string dir, out, dump;
+    std::string dir, out, dump, dump_midi, dump_wav;
     std::vector<std::string> batch;
     bool normalize = true, batching = false; int device = 0;
     for (int i = 1; i < argc; ++i) {
@@ -27,10 +29,24 @@ int main(int argc, char** argv) {
         else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
         else if ((a == "-o" || a == "--output") && i + 1 < argc) out = argv[++i];
         else if (a == "--dump-project" && i + 1 < argc) dump = argv[++i];
+        else if (a == "--dump-midi" && i + 1 < argc) dump_midi = argv[++i];
+        else if (a == "--dump-wav" && i + 1 < argc) dump_wav = argv[++i];
         else if (!a.empty() && a[0] != '-' && dir.empty()) dir = a;
         else { fprintf(stderr, "usage: %s <project dir> [--no-normalize] [--device N] [-o out.wav] | --dump-project <script.lua>\n", argv[0]); return 2; }
     }
     try {
+        if (!dump_wav.empty()) {                               // what SampleBank::add would be handed: header + a digest of the f32 stream
+            const DecodedWav w = decode_wav(read_file(dump_wav));
+            uint64_t h = 1469598103934665603ull;                // FNV-1a over the f32 bit patterns
+            for (float v : w.linear) { uint32_t u; memcpy(&u, &v, 4); for (int k = 0; k < 4; ++k) { h ^= (u >> (8 * k)) & 0xFF; h *= 1099511628211ull; } }
+            printf("%u %u %u %zu %llu\n", w.channels, w.sample_rate, w.bits, w.linear.size(), (unsigned long long)h);
+            return 0;
+        }
+        if (!dump_midi.empty()) {                              // the floww a MIDI file decodes to: "t note vel" per event, f32 exact
+            const FlowwEvents f = parse_midi(read_file(dump_midi));
+            for (size_t i = 0; i < f.t.size(); ++i) printf("%.9g %.9g %.9g\n", (double)f.t[i], (double)f.note[i], (double)f.vel[i]);
+            return 0;
+        }
         if (!dump.empty()) {
             Project p;
             run_file(dump, p);

@@ -131,6 +131,50 @@ def test_native_host_over_the_oracle_equals_python_over_the_oracle(host_oracle_b
             assert norms[k] == pytest.approx(v, rel=1e-7)
 
 
+def test_native_wav_decoder_equals_python_decoder(host_bin, tmp_path):
+    """hound's `samples::<i32>()` `as f32` for every PCM width, IEEE float, plain and extensible headers, odd chunk
+    sizes and foreign chunks: csrc/host/tdh_assets.cpp against termdaw_b200/wav.py, by digest of the f32 bits."""
+    import struct
+    from termdaw_b200.wav import KSDATAFORMAT_SUBTYPE_FLOAT, decode_wav, encode_wav, pcm_from_float
+    rng = np.random.default_rng(5)
+
+    def fnv(lin):
+        h = 1469598103934665603
+        for b in np.asarray(lin, "<f4").tobytes():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    files = []
+    for bd in (8, 16, 24, 32):
+        for ch in (1, 2):
+            n = int(rng.integers(1, 300))
+            l, r = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+            pcm = pcm_from_float(l, r, bd) if ch == 2 else pcm_from_float(l, l, bd).reshape(n, 2, bd // 8)[:, 0].reshape(-1)
+            files.append(encode_wav(pcm, int(rng.choice([22050, 44100, 48000, 96000])), bd, ch))
+    # 32-bit float, plain tag 3 and extensible, with a LIST chunk of odd size in front of the data
+    f32 = rng.uniform(-2, 2, 101).astype("<f4").tobytes()
+    fmt3 = struct.pack("<HHIIHH", 3, 1, 48000, 48000 * 4, 4, 32)
+    odd = b"LIST" + struct.pack("<I", 3) + b"abc\x00"
+    files.append(b"RIFF" + struct.pack("<I", 4 + 8 + len(fmt3) + len(odd) + 8 + len(f32)) + b"WAVE" + b"fmt " + struct.pack("<I", len(fmt3)) + fmt3 +
+                 odd + b"data" + struct.pack("<I", len(f32)) + f32)
+    fmte = struct.pack("<HHIIHHHHI", 0xFFFE, 1, 44100, 44100 * 4, 4, 32, 22, 32, 0x4) + KSDATAFORMAT_SUBTYPE_FLOAT
+    files.append(b"RIFF" + struct.pack("<I", 4 + 8 + len(fmte) + 8 + len(f32)) + b"WAVE" + b"fmt " + struct.pack("<I", len(fmte)) + fmte +
+                 b"data" + struct.pack("<I", len(f32)) + f32)
+    for k, data in enumerate(files):
+        path = tmp_path / f"w{k}.wav"
+        path.write_bytes(data)
+        w = decode_wav(data)
+        out = subprocess.run([host_bin, "--dump-wav", str(path)], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0, out.stderr
+        ch, rate, bits, n, h = (int(x) for x in out.stdout.split())
+        assert (ch, rate, bits, n) == (w.channels, w.sample_rate, w.bits, w.linear.size), k
+        assert h == fnv(w.linear), k
+    for bad in (b"RIFFxxxxWAVE", b"junk", files[0][:20]):
+        path = tmp_path / "bad.wav"
+        path.write_bytes(bad)
+        assert subprocess.run([host_bin, "--dump-wav", str(path)], capture_output=True, text=True).returncode == 1
+
+
 def _batch(binary, cfgs, root, extra=()):
     dirs = [S.write_project_dir(c, os.path.join(root, f"proj{i}")) for i, c in enumerate(cfgs)]
     out = subprocess.run([binary, "--batch", *dirs, "-o", "batch.wav", *extra], capture_output=True, text=True, timeout=600)

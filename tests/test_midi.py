@@ -79,3 +79,86 @@ def test_state_loads_a_midi_file_from_disk(tmp_path):
     for path in (str(tmp_path / "junk.mid"), str(tmp_path / "missing.mid")):
         with pytest.raises(FileNotFoundError, match="Could not read midi file"):
             Assets().floww(path)
+
+
+# ------------------------------------------------------------------------------------ native parser == python parser
+def _vlq(v):
+    out = [v & 0x7F]
+    v >>= 7
+    while v:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    return bytes(reversed(out))
+
+
+def _random_smf(rng, fmt, ntracks, division):
+    """A random but well-formed SMF: note on/off with and without running status, note-on velocity 0, tempo
+    changes in any track, controllers / program changes / pitch bend / sysex / text meta events in between."""
+    tracks = []
+    for _ in range(ntracks):
+        body, status = bytearray(), None
+        for _ in range(int(rng.integers(5, 60))):
+            body += _vlq(int(rng.choice([0, 0, 1, 7, 96, 480, 5000, 20000])))
+            kind = int(rng.integers(10))
+            if kind < 5:                                   # note on / off
+                st = (0x90 if rng.random() < 0.6 else 0x80) | int(rng.integers(16))
+                if st != status or rng.random() < 0.3:
+                    body.append(st)
+                    status = st
+                body += bytes([int(rng.integers(128)), int(rng.choice([0, 1, 64, 127]))])
+            elif kind == 5:                                # tempo
+                body += b"\xFF\x51\x03" + int(rng.integers(100000, 2000000)).to_bytes(3, "big")
+                status = None
+            elif kind == 6:                                # controller / pitch bend (two data bytes)
+                st = int(rng.choice([0xB0, 0xE0, 0xA0])) | int(rng.integers(16))
+                body += bytes([st, int(rng.integers(128)), int(rng.integers(128))])
+                status = st
+            elif kind == 7:                                # program change / channel pressure (one data byte)
+                st = int(rng.choice([0xC0, 0xD0])) | int(rng.integers(16))
+                body += bytes([st, int(rng.integers(128))])
+                status = st
+            elif kind == 8:                                # sysex
+                n = int(rng.integers(0, 6))
+                body += b"\xF0" + _vlq(n + 1) + bytes(int(x) for x in rng.integers(0, 128, n)) + b"\xF7"
+                status = None
+            else:                                          # text meta
+                n = int(rng.integers(0, 10))
+                body += b"\xFF\x01" + _vlq(n) + bytes(int(x) for x in rng.integers(32, 127, n))
+                status = None
+        body += b"\x00\xFF\x2F\x00"
+        tracks.append(bytes(body))
+    return _smf(fmt, division, tracks)
+
+
+def test_native_midi_parser_equals_python_parser(tmp_path):
+    """termdaw_b200_render --dump-midi (csrc/host/tdh_assets.cpp) against termdaw_b200/midi.py on random files:
+    the two hosts must hand the library the same f32 triples, bit for bit."""
+    import os
+    import subprocess
+    from helpers import ROOT
+    from termdaw_b200.csrc import build as B
+    host = os.path.join(ROOT, "termdaw_b200", "csrc", "termdaw_b200_render")
+    if not os.path.exists(host):
+        B.build()
+    rng = np.random.default_rng(77)
+    cases = [(0, 1, 480), (1, 3, 96), (1, 5, 960), (2, 3, 480), (0, 1, ((256 - 25) << 8) | 40), (1, 2, ((256 - 29) << 8) | 80)]
+    for k in range(18):
+        fmt, ntr, div = cases[k % len(cases)]
+        data = _random_smf(rng, fmt, ntr, div)
+        path = tmp_path / f"r{k}.mid"
+        path.write_bytes(data)
+        t, n, v = parse_midi(data)
+        out = subprocess.run([host, "--dump-midi", str(path)], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0, out.stderr
+        rows = [ln.split() for ln in out.stdout.splitlines()]
+        assert len(rows) == t.size, k
+        got = np.asarray(rows, np.float64).reshape(-1, 3).astype(np.float32) if rows else np.zeros((0, 3), np.float32)
+        assert np.array_equal(got[:, 0], t) and np.array_equal(got[:, 1], n) and np.array_equal(got[:, 2], v), k
+    # and the same refusals
+    for bad in (b"", b"MThd" + b"\x00" * 10, _smf(0, 480, [bytes([0x00, 0x90, 60])])):
+        path = tmp_path / "bad.mid"
+        path.write_bytes(bad)
+        out = subprocess.run([host, "--dump-midi", str(path)], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 1
+        with pytest.raises(MidiError):
+            parse_midi(bad)
