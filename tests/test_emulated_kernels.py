@@ -1,0 +1,97 @@
+"""The REAL kernels.cu + engine.cu on the CPU (tests/emu): the product sources compiled by g++ against a
+stand-in CUDA runtime whose blocks run one after the other with the threads of a block as fibers.
+
+This is test infrastructure, like the oracle: the emulated library lives in a temporary directory, is
+never importable through `termdaw_b200.load_library()` and is not what any `-m gpu` test or the bench
+measures — the product still refuses to work without an sm_100 device.  What it buys is that the host
+planner, the launch sequences (levels, liveness, keep arena, exchange slots of the time sharding, the
+pipelined group schedule) and the kernels' arithmetic (IEEE f32 with contraction off on both sides, no
+device math library call in any kernel) are checked against the oracle in the `not gpu` run as well.
+What it cannot see is concurrency: races between threads or streams only show on the GPU.
+
+The test bodies are the `-m gpu` tests themselves, called with the emulated library in place of the
+CUDA one — a subset sized for the CPU suite."""
+import os
+import sys
+
+import pytest
+
+from helpers import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+import test_golden as TG  # noqa: E402
+import test_gpu_parity as TP  # noqa: E402
+import test_pass_reuse as TR  # noqa: E402
+import test_timeshard as TS  # noqa: E402
+
+
+@pytest.fixture(scope="session")
+def emulib(tmp_path_factory):
+    import build_emu
+    from termdaw_b200._capi import Library
+    path = build_emu.build(str(tmp_path_factory.mktemp("tdg_emu")))
+    lib = Library(path, "tdg_")
+    assert lib.exported()
+    return lib
+
+
+# ---- parity against the oracle (tests/test_gpu_parity.py) ------------------------------------------------
+def test_emu_config1_readme_example_through_the_resampler(emulib, oracle):
+    TP.test_config1_readme_example(emulib, oracle, {})
+    TP.test_config1_flow_a_running_max(emulib, oracle, {})
+
+
+def test_emu_config2_synth_adsr_bandpass(emulib, oracle):
+    TP.test_config2_synth_adsr_bandpass(emulib, oracle, {})
+
+
+@pytest.mark.parametrize("index", [0, 1, 3, 4])
+def test_emu_config5_projects(emulib, oracle, index):
+    TP.test_config5_batch_projects(emulib, oracle, {}, index)
+
+
+@pytest.mark.parametrize("bd", [8, 16, 24, 32])
+def test_emu_bitdepths(emulib, oracle, bd):
+    TP.test_bitdepths(emulib, oracle, bd)
+
+
+def test_emu_errors_and_refresh_cycle(emulib, oracle):
+    TP.test_unsupported_and_errors(emulib)
+    TP.test_refresh_cycle_is_idempotent(emulib, oracle)
+
+
+def test_emu_pipelined_groups(emulib, oracle):
+    TP.test_pipelined_batches_equal_oracle(emulib, oracle, 3)
+
+
+@pytest.mark.parametrize("name", TG.NAMES)
+def test_emu_matches_golden(emulib, name):
+    TG.test_cuda_path_matches_golden(emulib, name)
+
+
+# ---- time sharding through virtual ranks (tests/test_timeshard.py) ------------------------------------------
+def test_emu_time_sharding_bit_exact_and_resampled(emulib, oracle):
+    TS.test_virtual_ranks_bit_exact_graph(emulib, oracle, 3)
+    TS.test_virtual_ranks_resampled_render(emulib, oracle, 3)
+    TS.test_resampled_segment_with_filter_and_errors(emulib, oracle)
+
+
+def test_emu_time_sharding_filters_and_voices(emulib, oracle):
+    TS.test_virtual_ranks_filters_and_voices(emulib, oracle, 2)
+
+
+# ---- pass-invariant cones (tests/test_pass_reuse.py) -----------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1", "c2", "p0", "p5"])
+def test_emu_pass_reuse_is_bit_identical(emulib, oracle, name):
+    TR.test_reuse_is_bit_identical(emulib, oracle, name)
+
+
+@pytest.mark.parametrize("ops,expect", [(["scan", "render"], [True]), (["scan", ("seek", 3), "render"], [False]),
+                                        (["scan", "render", "render"], [True, False]), (["scan", "shorter", "render"], [False])])
+def test_emu_pass_reuse_invalidation(emulib, oracle, ops, expect):
+    TR.test_reuse_only_when_the_passes_cannot_differ(emulib, oracle, ops, expect)
+
+
+def test_emu_pass_reuse_two_projects_on_one_lane(emulib, oracle):
+    TR.test_two_projects_interleaved_on_one_lane(emulib, oracle)
