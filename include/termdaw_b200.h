@@ -78,6 +78,11 @@ int tdg_resource_add(tdg_ctx* ctx, const uint8_t* bytes, uint64_t n);
 /* FlowwBank::declare_floww / add_floww / declare_stream (floww.rs:32-53): one floww = time-sorted
  * events (t seconds, note, vel); vel <= 0.001 is a note-off (floww.rs:114,134). n may be 0. */
 int tdg_floww_add(tdg_ctx* ctx, const float* t_sec, const float* note, const float* vel, uint64_t n);
+/* FlowwBank::append_streams (floww.rs:55-57; the Feed handler of stream_workflow.rs:63-71): more events for
+ * a declared stream while the transport runs.  Events must not start before the stream's last event
+ * (TDG_ERR_UNSORTED).  Follow with tdg_floww_set_time(ctx, tdg_get_time(ctx)) as the reference does. */
+int tdg_floww_append(tdg_ctx* ctx, int floww, const float* t_sec, const float* note, const float* vel,
+                     uint64_t n);
 /* FlowwBank::reset (floww.rs:21) — State::refresh reloads every floww (state.rs:240). */
 int tdg_floww_reset(tdg_ctx* ctx);
 
@@ -141,6 +146,15 @@ int tdg_render(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitde
                uint8_t* out_pcm, uint64_t cap_bytes, uint64_t* frames_written);
 /* Upper bound of the PCM bytes tdg_render will write for these arguments. */
 uint64_t tdg_render_bound_bytes(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth);
+
+/* Playback / stream feed (ui_workflow.rs:195-210, stream_workflow.rs:86-100):
+ * `chunks` x { Graph::render; Sample::interleave (sample.rs:177-184); FlowwBank::set_time_to_next_block }
+ * as one device pass from the current transport position.  Unlike tdg_render nothing is rewound: time,
+ * floww cursor and all vertex state stay where the last chunk left them, so consecutive calls continue the
+ * stream (a player keeps its half-second render-ahead ring full by asking for a few chunks at a time).
+ * `out_interleaved` receives chunks*buffer_len frames of (L, R) f32 pairs; may be NULL to only advance. */
+int tdg_play(tdg_ctx* ctx, uint64_t chunks, float* out_interleaved, uint64_t cap_frames,
+             uint64_t* frames_written);
 
 /* Batched forms (independent projects): the same two calls over `n` contexts on
  * the same device, merged into one device schedule (one launch per DAG level and kernel class for

@@ -834,6 +834,11 @@ int tdo_floww_add(tdo_ctx* x, const float* t, const float* note, const float* ve
     x->c.fb.start_indices.push_back(0);
     return (int)x->c.fb.flowws.size() - 1;
 }
+int tdo_floww_append(tdo_ctx* x, int floww, const float* t, const float* note, const float* vel, uint64_t n) {   // floww.rs:55-57
+    if (floww < 0 || (size_t)floww >= x->c.fb.flowws.size()) return x->c.fail(ERR_INVALID, "unknown floww");
+    for (uint64_t i = 0; i < n; ++i) x->c.fb.flowws[(size_t)floww].push_back({t[i], note[i], vel[i]});
+    return OK;
+}
 int tdo_floww_reset(tdo_ctx* x) { x->c.fb.reset(); return OK; }
 int tdo_graph_reset(tdo_ctx* x) {                                           // graph.rs:39-47
     Ctx& c = x->c; c.vertices.clear(); c.edges.clear(); c.ran_status.clear(); c.has_output = false; c.t = 0;
@@ -1031,6 +1036,28 @@ int tdo_render(tdo_ctx* x, uint64_t chunks, uint32_t render_sr, uint32_t bd, uin
         if (cap_bytes < out.size()) return c.fail(ERR_CAPACITY, "output buffer too small");
         std::memcpy(out_pcm, out.data(), out.size());
     }
+    return OK;
+}
+
+// Playback feed (ui_workflow.rs:195-210, stream_workflow.rs:86-100): `chunks` x { Graph::render;
+// Sample::interleave (sample.rs:177-184); fb.set_time_to_next_block() }.  Nothing is rewound: the next
+// call continues where this one stopped, with every vertex state as the last chunk left it.
+int tdo_play(tdo_ctx* x, uint64_t chunks, float* out_interleaved, uint64_t cap_frames, uint64_t* frames_written) {
+    Ctx& c = x->c;
+    if (c.taps) c.clear_taps();
+    uint64_t frames = 0;
+    for (uint64_t k = 0; k < chunks; ++k) {
+        const Sample* chunk = c.render_chunk();
+        if (!chunk) return c.fail(ERR_NO_OUTPUT, "no output vertex");       // the reference unwraps the Option (ui_workflow.rs:203)
+        const size_t len = chunk->len();
+        if (out_interleaved) {
+            if (frames + len > cap_frames) return c.fail(ERR_CAPACITY, "output buffer too small");
+            for (size_t i = 0; i < len; ++i) { out_interleaved[2 * (frames + i)] = chunk->l[i]; out_interleaved[2 * (frames + i) + 1] = chunk->r[i]; }
+        }
+        frames += len;
+        c.fb.set_time_to_next_block();
+    }
+    if (frames_written) *frames_written = frames;
     return OK;
 }
 

@@ -106,6 +106,8 @@ class Library:
         "enable_taps": (C.c_int, [C.c_void_p, C.c_int]),
         "read_vertex_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, c_f32p, c_f32p]),
         "get_normalize_state": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int]),
+        "play": (C.c_int, [C.c_void_p, C.c_uint64, c_f32p, C.c_uint64, c_u64p]),
+        "floww_append": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, c_f32p, C.c_uint64]),
     }
     # symbols only the CUDA library has (time sharding + measurement)
     GPU_ONLY = {
@@ -317,6 +319,21 @@ class Context:
         mx, sm = np.empty(n_vertices, np.float32), np.empty(n_vertices, np.float32)
         self._chk(self.lib.get_normalize_state(self.h, _p(mx), _p(sm), n_vertices))
         return mx, sm
+
+    def floww_append(self, floww: int, t, note, vel):
+        """tdg_floww_append + the cursor re-seat of the reference's Feed handler (stream_workflow.rs:63-71)."""
+        t, note, vel = _f32(t), _f32(note), _f32(vel)
+        self._chk(self.lib.floww_append(self.h, floww, _p(t), _p(note), _p(vel), t.size))
+        self.floww_set_time(self.get_time())
+
+    def play(self, chunks: int) -> np.ndarray:
+        """tdg_play: the playback feed — `chunks` more chunks from the current transport position, nothing
+        rewound; returns the interleaved (L, R) f32 stream (ui_workflow.rs:195-210)."""
+        n = chunks * self.bl
+        out = np.empty(2 * n, np.float32)
+        frames = C.c_uint64(0)
+        self._chk(self.lib.play(self.h, chunks, _p(out), n, C.byref(frames)))
+        return out[: 2 * frames.value]
 
     # -- CUDA library only
     def scan_segment(self, total_chunks: int, chunk0: int, chunks: int, warmup_chunks: int):

@@ -630,6 +630,7 @@ struct PassReq {
     std::vector<char> skip;
     std::vector<int64_t> keep_rel;     // per vertex: keep-arena offset, -1 = work arena
     bool keep_write = false, keep_read = false;
+    bool play = false;                 // playback feed: no quantiser, and the pass does not rewind at its end (tdg_play)
     uint64_t out_frames = 0;
     uint32_t err_flag = 0;
 };
@@ -780,7 +781,7 @@ static int pass_plan(PassJob& J) {
         // pass-invariant.  The scan keeps the buffers such cones hand to the rest of the graph; the render reads
         // them (same kernels, same bits: they ARE the scan's output) instead of evaluating the cone again.
         r.skip.assign(V, 0); r.keep_rel.assign(V, -1); r.keep_write = r.keep_read = false;
-        const bool plain = g->reuse && !r.segment && r.x_ranks == 1 && !x->taps && r.emit0 == 0 && r.emit_n == r.total &&
+        const bool plain = g->reuse && !r.segment && !r.play && r.x_ranks == 1 && !x->taps && r.emit0 == 0 && r.emit_n == r.total &&
                            x->output >= 0 && r.emit_n > 0;
         KeepRecord& K = x->keep;
         if (!r.is_scan) {
@@ -854,7 +855,7 @@ static int pass_plan(PassJob& J) {
             } else { r.x_off = leader->x_off; r.x_red_off = leader->x_red_off; }
         }
         if (!r.is_scan && x->output >= 0) {
-            r.resample = x->sr > r.render_sr;                                  // state.rs:533
+            r.resample = !r.play && x->sr > r.render_sr;                       // state.rs:533 (playback is at the project rate)
             r.out_frames = (r.emit0 + r.emit_n - r.keep0) * x->bl;
             if (r.resample) {
                 const uint64_t keep_n = r.emit0 + r.emit_n - r.keep0;
@@ -879,7 +880,7 @@ static int pass_plan(PassJob& J) {
                     else r.halo_off = leader->halo_off;
                 }
             }
-            r.pcm_bytes = r.out_frames * 2 * (r.bd / 8);
+            r.pcm_bytes = r.play ? 0 : r.out_frames * 2 * (r.bd / 8);
             r.pcm_off = pbump.alloc(align_up(r.pcm_bytes, 64) + 64);
         }
     }
@@ -985,7 +986,7 @@ static int pass_plan(PassJob& J) {
                     // Output Normalize without taps: the scan pass needs only its peaks (no buffer is consumed),
                     // the render pass scales inside the quantiser; with a render-time resampler the scaled
                     // buffer is still needed
-                    const bool fuse_out = v == x->output && !x->taps && !r.resample;
+                    const bool fuse_out = v == x->output && !x->taps && !r.resample && !r.play;
                     if (fuse_out && r.is_scan) t.no_store = 1;
                     LT.fx_norm.v.push_back(t); LT.fx_norm.max_chunks = std::max(LT.fx_norm.max_chunks, nch);
                     NormPrefixTask np{peaks, runmax, x->vstate_dev + (size_t)v * 8, nch, r.is_scan ? 1u : 0u, Xchg{nullptr, 0, 0, 1, 0}, nullptr};
@@ -1152,8 +1153,8 @@ static int pass_plan(PassJob& J) {
                 }
             }
         }
-        // output stage (state.rs:515-574)
-        if (!r.is_scan && x->output >= 0) {
+        // output stage (state.rs:515-574); the playback feed hands out the output vertex's f32 buffer instead
+        if (!r.is_scan && x->output >= 0 && !r.play) {
             const float* ol = reinterpret_cast<const float*>(W + r.buf_off[x->output]);
             const float* orr = ol + r.n_pad;
             QuantTask q; memset(&q, 0, sizeof q);
@@ -1436,6 +1437,7 @@ static void pass_end_state(PassJob& J) {
         if (r.is_scan) {
             if (x->output >= 0) { x->fb_frame = 0; }
         } else if (x->output >= 0) x->fb_frame += r.total * x->bl;      // set_time_to_next_block per chunk, never rewound
+        if (r.play) { x->t += r.total * x->bl; continue; }              // Graph::render advanced t; nothing is rewound
         if (x->output >= 0 || !r.is_scan) {
             x->t = 0;                                                   // Graph::set_time(0)
             for (HVertex& hv : x->verts) {                              // VertexExt::set_time, extensions.rs:196-204
@@ -1823,6 +1825,27 @@ int tdg_floww_add(tdg_ctx* h, const float* t, const float* note, const float* ve
     ++c->mut_gen;
     return (int)c->flowws.size() - 1;
 }
+// FlowwBank::append_streams (floww.rs:55-57, stream_workflow.rs:63-71): more events for a declared stream while
+// the transport runs.  The device planner walks sorted events, so the appended events must not start before
+// the stream's last event (TDG_ERR_UNSORTED otherwise, as for tdg_floww_add).  The caller then re-seats the
+// floww cursor like the reference's Feed handler does: tdg_floww_set_time(ctx, tdg_get_time(ctx)).
+int tdg_floww_append(tdg_ctx* h, int floww, const float* t, const float* note, const float* vel, uint64_t n) {
+    Ctx* c = C_;
+    if (floww < 0 || (size_t)floww >= c->flowws.size()) return c->fail(TDG_ERR_INVALID, "unknown floww");
+    Floww& f = c->flowws[(size_t)floww];
+    uint64_t last = f.fe.empty() ? 0 : f.fe.back();
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t fe = f32_as_usize(t[i] * (float)c->sr);                  // floww.rs:75
+        if (fe < last) return c->fail(TDG_ERR_UNSORTED, "appended floww events must be sorted by time");
+        last = fe;
+    }
+    for (uint64_t i = 0; i < n; ++i) {
+        f.t.push_back(t[i]); f.note.push_back(note[i]); f.vel.push_back(vel[i]);
+        f.fe.push_back(f32_as_usize(t[i] * (float)c->sr));
+    }
+    ++c->mut_gen;
+    return TDG_OK;
+}
 int tdg_floww_reset(tdg_ctx* h) { h->c.flowws.clear(); h->c.fb_frame = 0; ++h->c.mut_gen; return TDG_OK; }     // floww.rs:21-28
 
 int tdg_graph_reset(tdg_ctx* h) {                                           // graph.rs:39-47
@@ -2115,6 +2138,39 @@ int tdg_normalize_render_many(tdg_ctx** hs, int n, const uint64_t* chunks, const
 int tdg_render(tdg_ctx* h, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes,
                uint64_t* frames_written) {
     return tdg_render_many(&h, 1, &chunks, &render_sr, &bitdepth, out_pcm ? &out_pcm : nullptr, &cap_bytes, frames_written);
+}
+
+// Playback / stream feed (ui_workflow.rs:195-210, stream_workflow.rs:86-100): `chunks` x { Graph::render,
+// Sample::interleave, FlowwBank::set_time_to_next_block } evaluated as ONE pass from the current transport
+// position.  Nothing is rewound at the end: graph time, floww cursor and every vertex state (loop counters,
+// hit deques, voices, envelope slots, filter state, running normalize max) stay where the last chunk left
+// them, so consecutive calls produce the stream the reference's per-chunk loop produces.  The output vertex's
+// planar f32 buffer is copied back and interleaved (L, R) on the host: the render-ahead ring of a player is
+// filled `chunks` at a time.
+int tdg_play(tdg_ctx* h, uint64_t chunks, float* out_interleaved, uint64_t cap_frames, uint64_t* frames_written) {
+    Ctx* c = C_;
+    if (frames_written) *frames_written = 0;
+    if (c->output < 0) return c->fail(TDG_ERR_NO_OUTPUT, "no output vertex");     // the reference unwraps the Option (ui_workflow.rs:203)
+    if (chunks == 0) return TDG_OK;
+    const uint64_t n = chunks * c->bl;
+    if (out_interleaved && cap_frames < n) return c->fail(TDG_ERR_CAPACITY, "output buffer too small");
+    ++c->mut_gen;                                   // the transport moves: a kept scan no longer describes the next render
+    std::vector<PassReq> reqs(1);
+    PassReq& r = reqs[0];
+    r.c = c; r.is_scan = false; r.play = true; r.total = chunks; r.emit0 = 0; r.emit_n = chunks; r.keep0 = 0;
+    r.render_sr = c->sr; r.bd = 32;
+    if (int e = run_pass(reqs)) return e;
+    if (out_interleaved) {
+        if (c->output >= (int)c->last_buf_off.size() || c->last_buf_off[c->output] < 0) return c->fail(TDG_ERR_INVALID, "output vertex was not evaluated");
+        cudaSetDevice(c->eng->device);
+        const float* dl = reinterpret_cast<const float*>(c->eng->lanes[c->last_lane].work.p + c->last_buf_off[c->output]);
+        std::vector<float> planar(2 * n);
+        CU(cudaMemcpy(planar.data(), dl, n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(planar.data() + n, dl + c->last_n_pad, n * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < n; ++i) { out_interleaved[2 * i] = planar[i]; out_interleaved[2 * i + 1] = planar[n + i]; }   // sample.rs:177-184
+    }
+    if (frames_written) *frames_written = n;
+    return TDG_OK;
 }
 
 // time sharding: audio is evaluated for [chunk0 - warmup, chunk0 + chunks) only; the event-driven

@@ -63,6 +63,10 @@ int TDH_FN(normalize_scan)(tdg_ctx* ctx, uint64_t chunks);
 int TDH_FN(render)(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes,
                    uint64_t* frames_written);
 uint64_t TDH_FN(render_bound_bytes)(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth);
+int TDH_FN(play)(tdg_ctx* ctx, uint64_t chunks, float* out_interleaved, uint64_t cap_frames, uint64_t* frames_written);
+int TDH_FN(floww_append)(tdg_ctx* ctx, int floww, const float* t_sec, const float* note, const float* vel, uint64_t n);
+int TDH_FN(floww_set_time)(tdg_ctx* ctx, uint64_t frame);
+uint64_t TDH_FN(get_time)(tdg_ctx* ctx);
 int TDH_FN(normalize_scan_many)(tdg_ctx** ctxs, int n, const uint64_t* chunks);
 int TDH_FN(render_many)(tdg_ctx** ctxs, int n, const uint64_t* chunks, const uint32_t* render_sr, const uint32_t* bitdepth,
                         uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written);
@@ -185,6 +189,11 @@ struct State {
     void scan_exact();                                                            // state.rs:473-475
     std::vector<uint8_t> render();                                                // state.rs:477-577: the data-chunk bytes
     std::string render_to_file(const std::string& path = "");
+    // playback / stream feed (ui_workflow.rs:195-210, stream_workflow.rs:63-100): `chunks` more chunks from the
+    // current transport position, interleaved (L, R) f32, nothing rewound; feed() appends events to a declared
+    // stream and re-seats the floww cursor at the graph time, as the reference's Feed handler does
+    std::vector<float> play(uint64_t chunks);
+    bool feed(const std::string& stream, const FlowwEvents& events);
     std::vector<std::pair<std::string, float>> normalization_values();            // graph.rs:213-220
     // The batch of independent projects (BASELINE configs[4]): "normalize" then "render" of every state in one
     // call — tdg_normalize_render_many, pipelined over project groups — or render only (`normalize` false).

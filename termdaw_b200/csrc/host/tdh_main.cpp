@@ -1,5 +1,6 @@
 // termdaw_b200_render <project dir> [--no-normalize] [--device N] [-o out.wav]
 // termdaw_b200_render --batch <project dir>... [--no-normalize] [-o name.wav]   (independent projects, one batched call)
+// termdaw_b200_render <project dir> --play N [--ahead M] [-o play.f32]   (playback feed: N chunks, raw interleaved f32)
 // termdaw_b200_render --dump-project <script.lua>        (seed vectors as JSON; no device needed)
 // termdaw_b200_render --dump-midi <file.mid>             (the decoded floww; no device needed)
 // termdaw_b200_render --dump-wav <file.wav>              (channels, rate, bits, values, FNV-1a of the decoded f32 stream)
@@ -13,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <algorithm>
 #include <memory>
 #include "tdh.h"
 
@@ -21,6 +23,7 @@ int main(int argc, char** argv) {
     std::string dir, out, dump, dump_midi, dump_wav;
     std::vector<std::string> batch;
     bool normalize = true, batching = false; int device = 0;
+    uint64_t play_chunks = 0, ahead = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "--no-normalize") normalize = false;
@@ -28,6 +31,8 @@ int main(int argc, char** argv) {
         else if (batching && !a.empty() && a[0] != '-') batch.push_back(a);
         else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
         else if ((a == "-o" || a == "--output") && i + 1 < argc) out = argv[++i];
+        else if (a == "--play" && i + 1 < argc) play_chunks = strtoull(argv[++i], nullptr, 10);
+        else if (a == "--ahead" && i + 1 < argc) ahead = strtoull(argv[++i], nullptr, 10);
         else if (a == "--dump-project" && i + 1 < argc) dump = argv[++i];
         else if (a == "--dump-midi" && i + 1 < argc) dump_midi = argv[++i];
         else if (a == "--dump-wav" && i + 1 < argc) dump_wav = argv[++i];
@@ -92,6 +97,24 @@ int main(int argc, char** argv) {
         const bool ok = st.refresh(project);
         for (const std::string& m : st.messages) fprintf(stderr, "%s\n", m.c_str());
         if (!ok) { fprintf(stderr, "TermDaw: project not loaded.\n"); return 1; }
+        if (play_chunks > 0) {
+            // playback feed to a file: raw interleaved f32 (what the reference queues to SDL), `--play N` chunks in
+            // passes of `--ahead M` chunks (default: half a second, the reference's render-ahead)
+            if (normalize) st.scan_exact();
+            const std::string dst = out.empty() ? "play.f32" : out;
+            FILE* f = fopen(dst.c_str(), "wb");
+            if (!f) { fprintf(stderr, "TermDaw: could not create \"%s\".\n", dst.c_str()); return 1; }
+            const uint64_t step = ahead > 0 ? ahead : (uint64_t)((cfg.project_samplerate / 2 + cfg.buffer_length - 1) / cfg.buffer_length);
+            for (uint64_t done = 0; done < play_chunks;) {
+                const uint64_t n = std::min<uint64_t>(step, play_chunks - done);
+                const std::vector<float> pcm = st.play(n);
+                fwrite(pcm.data(), 4, pcm.size(), f);
+                done += n;
+            }
+            fclose(f);
+            printf("played %llu chunks -> %s\n", (unsigned long long)play_chunks, dst.c_str());
+            return 0;
+        }
         if (normalize) st.scan_exact();
         const std::string path = st.render_to_file(out);
         for (const auto& nv : st.normalization_values()) printf("%s: %.9g\n", nv.first.c_str(), (double)nv.second);

@@ -181,6 +181,22 @@ std::vector<std::vector<uint8_t>> State::render_batch(const std::vector<State*>&
     return outs;
 }
 
+std::vector<float> State::play(uint64_t chunks) {
+    std::vector<float> out(chunks * bl * 2);
+    uint64_t frames = 0;
+    chk(TDH_FN(play)(ctx, chunks, out.data(), chunks * bl, &frames));
+    out.resize(frames * 2);
+    return out;
+}
+
+bool State::feed(const std::string& stream, const FlowwEvents& ev) {
+    auto it = floww_index.find(stream);
+    if (it == floww_index.end()) { say("stream \"" + stream + "\" is not declared."); return false; }
+    chk(TDH_FN(floww_append)(ctx, it->second, ev.t.data(), ev.note.data(), ev.vel.data(), ev.t.size()));
+    chk(TDH_FN(floww_set_time)(ctx, TDH_FN(get_time)(ctx)));              // stream_workflow.rs:67-68
+    return true;
+}
+
 std::string State::render_to_file(const std::string& path) {
     const std::vector<uint8_t> pcm = render();
     const std::string dst = path.empty() ? output_file : path;

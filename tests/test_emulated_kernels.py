@@ -95,3 +95,18 @@ def test_emu_pass_reuse_invalidation(emulib, oracle, ops, expect):
 
 def test_emu_pass_reuse_two_projects_on_one_lane(emulib, oracle):
     TR.test_two_projects_interleaved_on_one_lane(emulib, oracle)
+
+
+# ---- playback / stream feed (tests/test_playback.py) --------------------------------------------------------------
+import test_playback as TPB  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "p3"])
+def test_emu_play_equals_chunkwise_reference(emulib, oracle, name):
+    TPB.check_play_equals_chunkwise_reference(emulib, oracle, name)
+
+
+def test_emu_play_seek_render_and_stream_feed(emulib, oracle):
+    TPB.check_play_then_seek_and_render(emulib, oracle)
+    TPB.check_stream_feed(emulib, oracle)
+    TPB.test_play_errors(emulib)

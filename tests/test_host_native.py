@@ -205,6 +205,25 @@ def test_native_batch_on_the_gpu(host_bin, gpulib, tmp_path):
         assert wav == encode_wav(got["pcm"], 48000, got["bd"])
 
 
+def test_native_play_over_the_oracle(host_oracle_bin, oracle, tmp_path):
+    """`--play N`: the playback feed in half-second passes == the Python mirror playing chunk by chunk."""
+    from termdaw_b200.state import State
+    cfg = S.config_5_project(3, 0.05)
+    d = S.write_project_dir(cfg, str(tmp_path / "play"))
+    for extra in ((), ("--no-normalize",), ("--ahead", "5")):
+        out = subprocess.run([host_oracle_bin, d, "--play", "30", "-o", "p.f32", *extra], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr
+        got = np.fromfile(os.path.join(d, "p.f32"), dtype="<f4")
+        p, a, s = cfg
+        st = State(oracle, s["psr"], s["bl"], assets=a)
+        assert st.refresh(p)
+        if "--no-normalize" not in extra:
+            st.scan_exact()
+        want = np.concatenate([st.ctx.play(1) for _ in range(30)])
+        st.close()
+        assert np.array_equal(got, want), extra
+
+
 def test_native_host_messages_match_the_python_mirror(host_oracle_bin, oracle, tmp_path):
     """refresh() failures: same messages, project not loaded, exit code 1."""
     from termdaw_b200.cli import DiskAssets
