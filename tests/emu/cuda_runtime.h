@@ -116,7 +116,10 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof *p); snprintf(p->name, sizeof p->name, "emulated sm_100 (tests/emu)"); p->major = 10; p->minor = 0;
     p->multiProcessorCount = 148; p->totalGlobalMem = (size_t)64 << 30; return cudaSuccess;
 }
-static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = (size_t)32 << 30; *t = (size_t)64 << 30; return cudaSuccess; }
+static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) {       // EMU_FREE_MB: pretend the device is nearly full
+    const char* e = getenv("EMU_FREE_MB");
+    *f = e ? (size_t)atoll(e) << 20 : (size_t)32 << 30; *t = (size_t)64 << 30; return cudaSuccess;
+}
 template <typename T> static inline cudaError_t cudaMalloc(T** p, size_t n) {
     void* q = nullptr;
     if (posix_memalign(&q, 256, n ? n : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }

@@ -110,3 +110,31 @@ def test_emu_play_seek_render_and_stream_feed(emulib, oracle):
     TPB.check_play_then_seek_and_render(emulib, oracle)
     TPB.check_stream_feed(emulib, oracle)
     TPB.test_play_errors(emulib)
+
+
+def test_emu_keep_arena_never_outgrows_free_memory(emulib, oracle, monkeypatch):
+    """A device with (pretended) 1 MB free: the scan must not try to keep anything, and scan + render still equal
+    the oracle — oversized renders are evaluated twice instead of failing."""
+    import numpy as np
+    from helpers import pcm_to_int, run_project
+    from termdaw_b200 import synthetic as S
+    from termdaw_b200.state import State
+    cfg = S.config_5_project(40, 0.2)                          # 6 s: its kept buffers would need several MB
+    p, a, s = cfg
+    st = State(emulib, s["psr"], s["bl"], assets=a)
+    assert st.refresh(p)
+    st.scan_exact(); st.render()
+    assert st.ctx.last_pass_stats()["reused_vertices"] > 0     # normal device: the cone is kept (and the arena now has this size)
+    st.close()
+    monkeypatch.setenv("EMU_FREE_MB", "1")
+    cfg = S.config_5_project(40, 1.5)                          # a much longer render would have to grow the arena
+    p, a, s = cfg
+    st = State(emulib, s["psr"], s["bl"], assets=a)
+    assert st.refresh(p)
+    st.scan_exact()
+    pcm = st.render()
+    assert st.ctx.last_pass_stats()["reused_vertices"] == 0
+    st.close()
+    want = run_project(oracle, *cfg, taps=False)
+    x, y = pcm_to_int(pcm, 16), pcm_to_int(want["pcm"], 16)
+    assert x.shape == y.shape and int(np.abs(x - y).max()) <= 1
