@@ -111,6 +111,8 @@ void run_block(unsigned n_threads) {
 }  // namespace
 
 void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+    static const bool skip = getenv("EMU_SKIP_KERNELS") != nullptr;      // host-side timing runs: plan and submit only
+    if (skip) return;
     if (block.y != 1 || block.z != 1 || block.x > 1024) { fprintf(stderr, "emu: only 1-D blocks of <= 1024 threads\n"); abort(); }
     t_body = &body; t_blockDim = block; t_gridDim = grid;
     for (unsigned z = 0; z < grid.z; ++z) for (unsigned y = 0; y < grid.y; ++y) for (unsigned x = 0; x < grid.x; ++x) {
