@@ -101,25 +101,34 @@ def rewind(states, reupload_flowws: bool, _cache={}):
     per-vertex state back to its constructor value), rewind the transport, reset the normalize maxima.
     Without the rebuild the reference's vertex state would leak from one step into the next and the steps
     would not be the same work."""
-    nbytes = 0
-    for st, p, a in states:
-        c = st.ctx
-        lib, h = c.lib, c.h
-        if reupload_flowws:
-            args = _cache.get(id(st))
-            if args is None:
-                args = _cache[id(st)] = _rewind_args(st, p, a)
-            if lib.floww_reset(h) < 0:
-                raise RuntimeError("floww_reset failed")
-            for tp, npx, vp, n, nb, _keep in args:
-                if lib.floww_add(h, tp, npx, vp, n) < 0:
-                    raise RuntimeError((lib.last_error(h) or b"").decode())
-                nbytes += nb
-        lib.reset_vertex_state(h)
-        lib.set_time(h, 0)
-        lib.floww_set_time(h, 0)
-        lib.reset_normalize(h)
-    return nbytes
+    import ctypes as C
+    from termdaw_b200._capi import c_f32p
+    key = (id(states), len(states))
+    packed = _cache.get(key)
+    if packed is None:
+        # the batched form of the refresh (tdg_rewind_many): the host pointers of every project's event arrays in
+        # one flattened table, built once; every step still hands the library those host buffers to reload
+        per, ts, ns, vs, counts, keep, nbytes = [], [], [], [], [], [], 0
+        for st, p, a in states:
+            args = _rewind_args(st, p, a)
+            per.append(len(args))
+            for tp, npx, vp, n, nb, k in args:
+                ts.append(tp); ns.append(npx); vs.append(vp); counts.append(n.value); keep.append(k); nbytes += nb
+        m = len(ts)
+        packed = _cache[key] = {
+            "hs": (C.c_void_p * len(states))(*[st.ctx.h for st, _, _ in states]),
+            "t": (c_f32p * max(m, 1))(*ts), "n": (c_f32p * max(m, 1))(*ns), "v": (c_f32p * max(m, 1))(*vs),
+            "counts": (C.c_uint64 * max(m, 1))(*counts), "per": (C.c_uint32 * len(states))(*per), "keep": keep, "nbytes": nbytes}
+    lib = states[0][0].ctx.lib
+    k = packed
+    if reupload_flowws:
+        rc = lib.rewind_many(k["hs"], len(states), k["t"], k["n"], k["v"], k["counts"], k["per"])
+    else:
+        rc = lib.rewind_many(k["hs"], len(states), None, None, None, None, None)
+    if rc < 0:
+        msgs = [(lib.last_error(st.ctx.h) or b"").decode() for st, _, _ in states]
+        raise RuntimeError(next((m_ for m_ in msgs if m_), "tdg_rewind_many failed"))
+    return k["nbytes"] if reupload_flowws else 0
 
 
 class ClockSampler:

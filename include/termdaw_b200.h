@@ -128,6 +128,13 @@ int tdg_check_graph(tdg_ctx* ctx, int* unreachable, int cap, int* n_unreachable)
 int tdg_reset_normalize(tdg_ctx* ctx);                                                    /* graph.rs:207 */
 float tdg_get_normalize_value(tdg_ctx* ctx, int vertex);            /* extensions.rs:301; -1 if not one */
 
+/* 'stop' + 'refresh' of a batch of UNCHANGED projects in one call (ui_workflow.rs:153-160; state.rs:240-250,
+ * 328-467): per context, optionally reload its flowws (t != NULL; flattened arrays, context i owns
+ * flowws_per_ctx[i] consecutive entries, registered in order so that floww ids are unchanged), then
+ * tdg_reset_vertex_state + tdg_set_time(0) + tdg_floww_set_time(0) + tdg_reset_normalize. */
+int tdg_rewind_many(tdg_ctx** ctxs, int n, const float* const* t_sec, const float* const* note,
+                    const float* const* vel, const uint64_t* counts, const uint32_t* flowws_per_ctx);
+
 /* ---- transport ----------------------------------------------------------------------------------*/
 int tdg_set_time(tdg_ctx* ctx, uint64_t frame);                      /* Graph::set_time, graph.rs:123 */
 uint64_t tdg_change_time(tdg_ctx* ctx, uint64_t delta, int plus);    /* Graph::change_time, graph.rs:130 */

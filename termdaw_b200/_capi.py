@@ -129,6 +129,8 @@ class Library:
         "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
         "set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
         "set_pass_reuse": (C.c_int, [C.c_void_p, C.c_int]),
+        "rewind_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(c_f32p), C.POINTER(c_f32p), C.POINTER(c_f32p),
+                                  c_u64p, c_u32p]),
         "reset_vertex_state": (C.c_int, [C.c_void_p]),
         "set_pipeline_group": (C.c_int, [C.c_void_p, C.c_uint32]),
         "last_pass_kernel_stats": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_int]),

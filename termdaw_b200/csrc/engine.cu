@@ -2061,6 +2061,32 @@ static void graph_set_time(Ctx* c, uint64_t time) {                         // g
     }
 }
 int tdg_set_time(tdg_ctx* h, uint64_t frame) { graph_set_time(C_, frame); return TDG_OK; }
+// 'stop' + 'refresh' of a whole batch of unchanged projects in one call (ui_workflow.rs:153-160,
+// state.rs:240-250,328-467): per context the flowws are reloaded (when given), every vertex returns to its
+// constructor state, the transport and the floww cursor rewind to 0 and the normalize maxima reset —
+// exactly tdg_floww_reset + tdg_floww_add... + tdg_reset_vertex_state + tdg_set_time(0) +
+// tdg_floww_set_time(0) + tdg_reset_normalize on each, without 9 calls per project across the FFI.
+// Flowws are flattened: context i owns entries [sum(flowws_per_ctx[0..i)), +flowws_per_ctx[i]) of t/note/vel/counts.
+int tdg_rewind_many(tdg_ctx** hs, int n, const float* const* t, const float* const* note, const float* const* vel,
+                    const uint64_t* counts, const uint32_t* flowws_per_ctx) {
+    if (n < 0 || (n > 0 && !hs)) return TDG_ERR_INVALID;
+    size_t at = 0;
+    for (int i = 0; i < n; ++i) {
+        tdg_ctx* h = hs[i];
+        if (t && flowws_per_ctx) {
+            if (int e = tdg_floww_reset(h)) return e;
+            for (uint32_t k = 0; k < flowws_per_ctx[i]; ++k, ++at) {
+                const int id = tdg_floww_add(h, t[at], note[at], vel[at], counts[at]);
+                if (id < 0) return id;
+            }
+        }
+        if (int e = tdg_reset_vertex_state(h)) return e;
+        if (int e = tdg_set_time(h, 0)) return e;
+        if (int e = tdg_floww_set_time(h, 0)) return e;
+        if (int e = tdg_reset_normalize(h)) return e;
+    }
+    return TDG_OK;
+}
 uint64_t tdg_change_time(tdg_ctx* h, uint64_t delta, int plus) {            // graph.rs:130-135
     Ctx* c = C_;
     const uint64_t nt = plus ? c->t + delta : c->t - std::min(delta, c->t);

@@ -138,3 +138,46 @@ def test_emu_keep_arena_never_outgrows_free_memory(emulib, oracle, monkeypatch):
     want = run_project(oracle, *cfg, taps=False)
     x, y = pcm_to_int(pcm, 16), pcm_to_int(want["pcm"], 16)
     assert x.shape == y.shape and int(np.abs(x - y).max()) <= 1
+
+
+def test_emu_batched_refresh_is_the_per_project_refresh(emulib, oracle):
+    """bench.py's `rewind` (tdg_rewind_many: reload flowws, vertex state, transport, normalize maxima of a whole
+    batch in one call) leaves every project exactly where the reference's stop + refresh would: rendering again
+    gives the first render, bit for bit, and the oracle's."""
+    import numpy as np
+    import bench
+    from helpers import pcm_to_int, run_project
+    from termdaw_b200 import normalize_scan_many, render_many, synthetic as S
+    from termdaw_b200.state import State
+    cfgs = [S.config_5_project(i, 0.04) for i in (0, 3, 5, 7)]
+    states = []
+    for p, a, s in cfgs:
+        st = State(emulib, s["psr"], s["bl"], assets=a)
+        assert st.refresh(p)
+        states.append((st, p, a))
+    ctxs = [st.ctx for st, _, _ in states]
+    args = ([st.cs for st, _, _ in states], [48000] * 4, [16] * 4)
+
+    def render_all(scan):
+        if scan:
+            normalize_scan_many(emulib, ctxs, args[0])
+        return [x.copy() for x in render_many(emulib, ctxs, *args)]
+    first_a = render_all(False)                                # fresh projects, running-max flow
+    bench.rewind(states, reupload_flowws=True)
+    first = render_all(True)                                   # normalize, then render
+    stale_a = render_all(False)                                # no refresh: the scan's maxima are still in the vertices
+    assert any(not np.array_equal(a, b) for a, b in zip(first_a, stale_a))
+    for reupload in (True, False, True):
+        nbytes = bench.rewind(states, reupload_flowws=reupload)
+        assert (nbytes > 0) == reupload
+        for a, b in zip(first_a, render_all(False)):
+            assert np.array_equal(a, b)
+        bench.rewind(states, reupload_flowws=reupload)
+        for a, b in zip(first, render_all(True)):
+            assert np.array_equal(a, b)
+    for (p, a, s), pcm in zip(cfgs, first):
+        want = run_project(oracle, p, a, s, taps=False)
+        x, y = pcm_to_int(pcm, 16), pcm_to_int(want["pcm"], 16)
+        assert x.shape == y.shape and int(np.abs(x - y).max()) <= 1
+    for st, _, _ in states:
+        st.close()
