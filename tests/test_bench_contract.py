@@ -102,3 +102,38 @@ def test_reference_arm_prints_its_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=60, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"}, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_real_runner_on_the_emulated_library(monkeypatch, capfd, tmp_path):
+    """The REAL BatchRunner (rewind, scan, render, pipelined e2e call, kernel statistics, pass-reuse A/B) through
+    bench.main(), with the emulated library (tests/emu) standing in for the CUDA one: two tiny projects, one step.
+    The numbers are meaningless (CPU emulation); what is checked is that every stage runs and the line is complete."""
+    import torch
+    import bench
+    import termdaw_b200
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    from termdaw_b200._capi import Library
+    emu = Library(build_emu.build(str(tmp_path / "emu")), "tdg_")
+    monkeypatch.setattr(termdaw_b200, "load_library", lambda: emu)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    real_tensor, real_empty = torch.tensor, torch.empty
+    monkeypatch.setattr(torch, "tensor", lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items() if k != "device"}))
+    monkeypatch.setattr(torch, "empty", lambda *a, **kw: real_empty(*a, **{k: v for k, v in kw.items() if k != "pin_memory"}))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "1", "--warmup", "1", "--projects", "2", "--scale", "0.02",
+                                      "--cpu-sample", "1"])
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    bench.main()
+    out = capfd.readouterr().out.strip().splitlines()
+    assert len(out) == 1, out
+    d = json.loads(out[0])
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 2 * 29 * 1024 * 4
+    assert d["config"]["projects_per_gpu"] == 2
+    assert d["config"]["pass_reuse"]["vertices_read_from_scan_per_step"] > 0
+    assert d["config"]["pass_reuse"]["ms_per_step_with_reuse_off"] > 0
+    assert d["roofline"]["kernel"] in d["roofline"]["per_kernel"] and d["roofline"]["achieved"] > 0
+    assert d["cpu_baseline"]["value"] > 0
