@@ -629,6 +629,7 @@ struct PassReq {
     // lane's keep arena (written by the scan pass / read by the render pass)
     std::vector<char> skip;
     std::vector<int64_t> keep_rel;     // per vertex: keep-arena offset, -1 = work arena
+    std::vector<uint64_t> prefix;      // per vertex: chunks to evaluate (UINT64_MAX = all); < emit_n only for kept multi / lerp in a render
     bool keep_write = false, keep_read = false;
     bool play = false;                 // playback feed: no quantiser, and the pass does not rewind at its end (tdg_play)
     uint64_t out_frames = 0;
@@ -780,7 +781,7 @@ static int pass_plan(PassJob& J) {
         // frame: extensions.rs:196-204, 664-670), it starts the scan from that reset state, and every input is
         // pass-invariant.  The scan keeps the buffers such cones hand to the rest of the graph; the render reads
         // them (same kernels, same bits: they ARE the scan's output) instead of evaluating the cone again.
-        r.skip.assign(V, 0); r.keep_rel.assign(V, -1); r.keep_write = r.keep_read = false;
+        r.skip.assign(V, 0); r.keep_rel.assign(V, -1); r.prefix.assign(V, UINT64_MAX); r.keep_write = r.keep_read = false;
         const bool plain = g->reuse && !r.segment && !r.play && r.x_ranks == 1 && !x->taps && r.emit0 == 0 && r.emit_n == r.total &&
                            x->output >= 0 && r.emit_n > 0;
         KeepRecord& K = x->keep;
@@ -792,7 +793,7 @@ static int pass_plan(PassJob& J) {
         } else {
             K.valid = false;
             if (plain) {
-                K.inv.assign(V, 0); K.off.assign(V, -1);
+                K.inv.assign(V, 0); K.off.assign(V, -1); K.hz.assign(V, UINT64_MAX);
                 for (int L = 0; L <= max_level; ++L) for (int v : by_level[L]) {
                     const HVertex& hv = x->verts[v];
                     bool inv = false;
@@ -811,6 +812,9 @@ static int pass_plan(PassJob& J) {
                 std::vector<char> fr(V, 0);
                 for (int v = 0; v < V; ++v) if (r.level[v] >= 0 && !K.inv[v]) for (int u : x->verts[v].edges) if (K.inv[u]) fr[u] = 1;
                 if (K.inv[x->output]) fr[x->output] = 1;
+                // prefix candidates: kept whole, the planner below tells how many leading chunks the render must redo
+                for (int v = 0; v < V; ++v)
+                    if (r.level[v] >= 0 && (x->verts[v].kind == K_SAMPLE_MULTI || x->verts[v].kind == K_SAMPLE_LERP)) fr[v] = 1;
                 // kept buffers are extra device memory: when the keep arena would have to grow past half of what is
                 // free (an hours-long single render) this project is simply evaluated twice, as before
                 uint64_t n_fr = 0;
@@ -823,6 +827,7 @@ static int pass_plan(PassJob& J) {
         for (int L = 0; L <= max_level; ++L) {
             for (int v : by_level[L]) {
                 if (r.keep_read && K.inv[v]) { r.skip[v] = 1; r.keep_rel[v] = K.off[v]; continue; }    // not evaluated; kept buffer if frontier
+                if (r.keep_read && K.off[v] >= 0 && (int)K.hz.size() == V) { r.keep_rel[v] = K.off[v]; r.prefix[v] = K.hz[v]; }   // only its head is redone
                 if (r.keep_rel[v] >= 0) { /* scan pass: this buffer lives in the keep arena */ }
                 else if (!free_slots.empty()) { r.buf_off[v] = (int64_t)free_slots.back(); free_slots.pop_back(); }
                 else r.buf_off[v] = (int64_t)bump.alloc(slot_bytes);
@@ -951,13 +956,15 @@ static int pass_plan(PassJob& J) {
             if (r.level[v] < 0) continue;
             HVertex& hv = x->verts[v];
             if (r.skip[v]) { ++F.reused_v; F.reused_b += 8ull * (hv.edges.size() + 1) * r.n_frames; continue; }   // the scan's buffer stands
+            const uint64_t chunks_v = std::min<uint64_t>(r.prefix[v], r.emit_n);    // < emit_n: kept multi / lerp, head only
+            const uint64_t frames_v = chunks_v * x->bl;
             LevelTasks& LT = levels[r.level[v]];
             TaskHdr h;
             h.out_l = reinterpret_cast<float*>(W + r.buf_off[v]);
             h.out_r = h.out_l + r.n_pad;
-            h.n_frames = r.n_frames; h.n_chunks = (uint32_t)r.emit_n; h.bl = x->bl;
+            h.n_frames = r.n_frames; h.n_chunks = (uint32_t)chunks_v; h.bl = x->bl;
             h.pg = make_pg(hv.gain, hv.angle);
-            const uint32_t nch = (uint32_t)r.emit_n;
+            const uint32_t nch = (uint32_t)chunks_v;
             uint64_t in_off = 0;
             if (hv.has_input()) {
                 in_off = B.alloc(std::max<size_t>(hv.edges.size(), 1) * 2 * sizeof(float*));
@@ -1064,6 +1071,16 @@ static int pass_plan(PassJob& J) {
                 case K_SAMPLE_MULTI: {
                     const DevSample& s = x->samples[hv.sample];
                     plan_multi(hv, x->flowws[hv.floww], s.frames, pp, mhits);
+                    if (r.is_scan && r.keep_write && x->keep.off[v] >= 0) {
+                        // the render differs from this scan only while hits carried INTO either pass still play:
+                        // carried entries come first in `mhits` (start < 0), the ones carried out are in hv.ts now
+                        int64_t last = 0;
+                        for (const MultiHit& mh : mhits) { if (mh.start >= 0) break; last = std::max<int64_t>(last, mh.start + (int64_t)s.frames); }
+                        for (const MultiEntry& e : hv.ts) last = std::max<int64_t>(last, (int64_t)s.frames - e.t);
+                        x->keep.hz[v] = ((uint64_t)last + x->bl - 1) / x->bl;
+                    }
+                    if (chunks_v == 0) { ++F.reused_v; F.reused_b += 8ull * r.n_frames; break; }       // nothing leaked: the scan's buffer stands
+                    if (chunks_v < r.emit_n) { ++F.reused_v; F.reused_b += 8ull * (r.n_frames - frames_v); }
                     MultiTask t; memset(&t, 0, sizeof t);
                     t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.n_hits = (uint32_t)mhits.size();
                     t.hits_off = B.alloc(std::max<size_t>(mhits.size(), 1) * sizeof(MultiHit));
@@ -1083,15 +1100,21 @@ static int pass_plan(PassJob& J) {
                     LT.multi.v.push_back(t); LT.multi.max_chunks = std::max(LT.multi.max_chunks, nch);
                     uint64_t gathered = 0;                                        // live hit-frames inside the emitted range
                     for (const MultiHit& mh : mhits) {
-                        int64_t a = std::max<int64_t>(mh.start, 0), b = std::min<int64_t>(mh.start + (int64_t)s.frames, (int64_t)r.n_frames);
+                        int64_t a = std::max<int64_t>(mh.start, 0), b = std::min<int64_t>(mh.start + (int64_t)s.frames, (int64_t)frames_v);
                         if (b > a) gathered += (uint64_t)(b - a);
                     }
-                    algo += 8ull * r.n_frames + 8ull * gathered; LT.multi.bytes += 8ull * r.n_frames + 8ull * gathered;
+                    algo += 8ull * frames_v + 8ull * gathered; LT.multi.bytes += 8ull * frames_v + 8ull * gathered;
                     break;
                 }
                 case K_SAMPLE_LERP: {
                     const DevSample& s = x->samples[hv.sample];
                     plan_lerp(hv, x->flowws[hv.floww], pp, lhits);
+                    if (r.is_scan && r.keep_write && x->keep.off[v] >= 0)
+                        // both passes play the same hits; only the pair carried in differs, and it is audible until the
+                        // first hit of the pass has faded in (entries 0 and 1 are the carried pair)
+                        x->keep.hz[v] = lhits.size() > 2 ? ((uint64_t)lhits[2].frame + hv.lerp_len + x->bl - 1) / x->bl : UINT64_MAX;
+                    if (chunks_v == 0) { ++F.reused_v; F.reused_b += 16ull * r.n_frames; break; }
+                    if (chunks_v < r.emit_n) { ++F.reused_v; F.reused_b += 16ull * (r.n_frames - frames_v); }
                     LerpTask t; memset(&t, 0, sizeof t);
                     t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.n_hits = (uint32_t)lhits.size(); t.lerp_len = hv.lerp_len;
                     t.hits_off = B.alloc(lhits.size() * sizeof(LerpHit));
@@ -1107,7 +1130,7 @@ static int pass_plan(PassJob& J) {
                         }
                     }
                     LT.lerp.v.push_back(t); LT.lerp.max_chunks = std::max(LT.lerp.max_chunks, nch);
-                    algo += 16ull * r.n_frames; LT.lerp.bytes += 16ull * r.n_frames;
+                    algo += 16ull * frames_v; LT.lerp.bytes += 16ull * frames_v;
                     break;
                 }
                 case K_DEBUG_SINE: case K_SYNTH: case K_SAMPSYN: {

@@ -70,6 +70,11 @@ struct KeepRecord {
     uint64_t total = 0, n_pad = 0;           // chunks / padded frames of the scan pass
     std::vector<char> inv;                   // per vertex: pass-invariant
     std::vector<int64_t> off;                // per vertex: keep-arena offset of a kept (frontier) buffer, else -1
+    // per vertex: chunks at the head of the render that still have to be evaluated (UINT64_MAX: all of them).
+    // sample_multi / sample_lerp differ between the two passes only while state leaked from the pass before is
+    // audible: until the leaked hits have played out / until the first hit of the pass has faded in.  Their
+    // scan buffer is kept whole and the render re-evaluates just that prefix into it.
+    std::vector<uint64_t> hz;
 };
 
 struct Engine;
