@@ -181,3 +181,7 @@ def test_emu_batched_refresh_is_the_per_project_refresh(emulib, oracle):
         assert x.shape == y.shape and int(np.abs(x - y).max()) <= 1
     for st, _, _ in states:
         st.close()
+
+
+def test_emu_heads_only_reuse(emulib, oracle):
+    TR.test_heads_only_reuse_of_sample_multi_and_lerp(emulib, oracle)

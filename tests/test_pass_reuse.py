@@ -176,3 +176,44 @@ def test_two_projects_interleaved_on_one_lane(gpulib, oracle):
             assert x.shape == y.shape and int(np.abs(x - y).max()) <= 1
     finally:
         a.close(); b.close()
+
+
+def test_heads_only_reuse_of_sample_multi_and_lerp(gpulib, oracle):
+    """sample_multi / sample_lerp are kept whole by the scan and the render redoes only the chunks in which state
+    leaked from the pass before is audible: the render's algorithmic bytes for them shrink to a few chunks' worth,
+    the result stays bit-identical to evaluate-everything-twice, also when the scan itself started from leaked state."""
+    from termdaw_b200.state import Project, State
+    base, a, s = S.config_5_project(0, 0.2)
+    p = Project()
+    p.set_length(6.0); p.set_render_samplerate(48000); p.set_render_bitdepth(16)
+    for nm in ("s_noise", "s_tone", "s_long"):
+        p.load_sample(nm, nm, "")
+    p.load_midi_floww("hits0", "hits0"); p.load_midi_floww("hits1", "hits1")
+    p.add_sample_multi("m", 0.9, 10.0, "s_long", "hits0", -1)
+    p.add_sample_lerp("l", 0.8, -30.0, "s_tone", "hits1", -1, 200)
+    p.add_normalize("out", 1.0, 0.0)
+    p.connect("m", "out"); p.connect("l", "out"); p.set_output("out")
+    cfg = (p, a, s)
+    res = {}
+    for reuse in (True, False):
+        st = State(gpulib, s["psr"], s["bl"], assets=a)
+        assert st.refresh(p), st.messages
+        st.ctx.set_pass_reuse(reuse)
+        out = []
+        for _ in range(2):                                   # the second scan starts from what the first render leaked
+            st.scan_exact()
+            out.append(st.render().copy())
+            stats = st.ctx.last_pass_stats()
+        res[reuse] = (out, stats, st.cs)
+        st.ctx.set_pass_reuse(True)
+        st.close()
+    (on, s_on, cs), (off, s_off, _) = res[True], res[False]
+    for x, y in zip(on, off):
+        assert np.array_equal(x, y)
+    assert s_on["reused_vertices"] == 2 and s_off["reused_vertices"] == 0
+    frames = cs * s["bl"]
+    # off: multi 8 B out + gathers, lerp 16 B per frame, normalize 24, quantise 12; on: the two generators shrink to their heads
+    assert s_off["algorithmic_bytes"] - s_on["algorithmic_bytes"] > 0.8 * (8 + 16) * frames
+    want = run_project(oracle, *cfg, taps=False)
+    x, y = pcm_to_int(on[0], 16), pcm_to_int(want["pcm"], 16)
+    assert x.shape == y.shape and int(np.abs(x - y).max()) <= 1
