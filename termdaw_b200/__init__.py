@@ -14,7 +14,7 @@ from ._capi import (Context, Library, TermdawError, comm_unique_id, normalize_re
 from .state import Assets, DecodedWav, Project, State, set_length_chunks  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("TDG_LIB_PATH", os.path.join(_HERE, "csrc", "libtermdaw_b200.so"))   # override: tuning variants only
+LIB_PATH = os.path.join(_HERE, "csrc", "libtermdaw_b200.so")     # the in-tree sm_100a build; there is no override and no fallback
 _lib = None
 
 
