@@ -269,6 +269,12 @@ int tdg_set_profiling(tdg_ctx* ctx, int on);
  * values are the scan's own, so the result is bit-identical.  On by default; 0 evaluates every vertex in
  * both passes as the reference does (graph.rs:222-237 then state.rs:545-574).  Device-wide setting. */
 int tdg_set_pass_reuse(tdg_ctx* ctx, int on);
+/* Oscillator sine.  1 (default): glibc's sinf restated operation for operation in double precision on the
+ * device (tdg_math.cuh m_sinf_glibc, checked against the host libm over all 2^32 arguments): synth and
+ * debug_sine buffers are bit-exact against what the reference's f32::sin produces (extensions.rs:452,
+ * synth.rs:23,28) and IIR-free graphs reach <= 1 LSB at 24 bit.  0: an f32 Cody-Waite + minimax sine
+ * (<= 2 ulp of libm, a few LSB at 24 bit), slightly faster.  Device-wide setting. */
+int tdg_set_oscillator_mode(tdg_ctx* ctx, int libm_exact);
 /* Batched calls (tdg_*_many) over more than `projects_per_group` projects are software-pipelined in
  * groups of that size over two streams: host planning of group g+1 and the PCM device->host copy of
  * group g-1 overlap the kernels of group g.  0 = one launch sequence for the whole batch (what the

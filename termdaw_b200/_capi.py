@@ -129,6 +129,7 @@ class Library:
         "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
         "set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
         "set_pass_reuse": (C.c_int, [C.c_void_p, C.c_int]),
+        "set_oscillator_mode": (C.c_int, [C.c_void_p, C.c_int]),
         "rewind_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(c_f32p), C.POINTER(c_f32p), C.POINTER(c_f32p),
                                   c_u64p, c_u32p]),
         "reset_vertex_state": (C.c_int, [C.c_void_p]),
@@ -377,6 +378,10 @@ class Context:
     def set_pass_reuse(self, on: bool = True):
         """tdg_set_pass_reuse: render reads pass-invariant cones from the scan before it (device-wide)."""
         self._chk(self.lib.set_pass_reuse(self.h, int(on)))
+
+    def set_oscillator_mode(self, libm_exact: bool = True):
+        """tdg_set_oscillator_mode: True = glibc's sinf bit for bit (default), False = the 2-ulp f32 sine."""
+        self._chk(self.lib.set_oscillator_mode(self.h, int(libm_exact)))
 
     def set_pipeline_group(self, n: int):
         self._chk(self.lib.set_pipeline_group(self.h, int(n)))

@@ -191,6 +191,7 @@ struct Engine {
     uint64_t hwm_work = 0, hwm_blob = 0, hwm_pcm = 0;         // largest work arena / plan blob any lane or slot has needed
     uint64_t hwm_keep = 0;
     bool reuse = true;                           // render reads pass-invariant cones from the scan (TDG_PASS_REUSE=0 / tdg_set_pass_reuse)
+    bool libm_sin = true;                        // oscillators evaluate glibc's sinf exactly (TDG_FAST_SIN=1 / tdg_set_oscillator_mode(ctx, 0): f32 polynomial, <= 2 ulp)
     WorkerPool* pool = nullptr;                  // planner threads (created on first batched pass)
     std::vector<Frag>* frags = nullptr;          // pooled per-project plan fragments (capacity is kept between jobs)
     std::vector<PlanScratch>* scratch = nullptr; // per worker: event-table scratch vectors
@@ -231,6 +232,7 @@ static Engine* engine_get(int device, std::string* err) {
     if (const char* e = getenv("TDG_LANES")) g->n_lanes = std::max(1, std::min(kLanes, atoi(e)));
     if (const char* e = getenv("TDG_TAPER")) g->taper = atoi(e) != 0;
     if (const char* e = getenv("TDG_PASS_REUSE")) g->reuse = atoi(e) != 0;
+    if (const char* e = getenv("TDG_FAST_SIN")) g->libm_sin = atoi(e) == 0;
     g->refs = 1;
     g_engines[device] = g;
     return g;
@@ -1367,10 +1369,10 @@ static int pass_submit(PassJob& J) {
         LAUNCH_SPLIT(KC_LOOP, T.loop, LoopTask, offs[L].loop, T.loop.bytes, launch_sample_loop(tp, nb, T.loop.max_chunks, vec, s));
         LAUNCH_SPLIT(KC_MULTI, T.multi, MultiTask, offs[L].multi, T.multi.bytes, launch_sample_multi(tp, nb, T.multi.max_chunks, vec, D, s));
         LAUNCH_SPLIT(KC_LERP, T.lerp, LerpTask, offs[L].lerp, T.lerp.bytes, launch_sample_lerp(tp, nb, T.lerp.max_chunks, vec, D, s));
-        LAUNCH_SPLIT(KC_DSINE, T.dsine, VoiceTask, offs[L].dsine, T.dsine.bytes, launch_voice(VOICE_DEBUG_SINE, tp, nb, T.dsine.max_chunks, T.dsine_exact, D, s));
-        LAUNCH_SPLIT(KC_SYNTH, T.synth, VoiceTask, offs[L].synth, T.synth.bytes, launch_voice(VOICE_SYNTH, tp, nb, T.synth.max_chunks, T.synth_exact, D, s));
+        LAUNCH_SPLIT(KC_DSINE, T.dsine, VoiceTask, offs[L].dsine, T.dsine.bytes, launch_voice(VOICE_DEBUG_SINE, tp, nb, T.dsine.max_chunks, T.dsine_exact, g->libm_sin, D, s));
+        LAUNCH_SPLIT(KC_SYNTH, T.synth, VoiceTask, offs[L].synth, T.synth.bytes, launch_voice(VOICE_SYNTH, tp, nb, T.synth.max_chunks, T.synth_exact, g->libm_sin, D, s));
         LAUNCH_SPLIT(KC_SAMPSYN, T.sampsyn, VoiceTask, offs[L].sampsyn, T.sampsyn.bytes,
-                     launch_voice(VOICE_SAMPSYN, tp, nb, T.sampsyn.max_chunks, T.sampsyn_exact, D, s));
+                     launch_voice(VOICE_SAMPSYN, tp, nb, T.sampsyn.max_chunks, T.sampsyn_exact, false, D, s));
         LAUNCH_SPLIT(KC_FX_SUM, T.fx, FxTask, offs[L].fx, T.fx.bytes, launch_fx(FX_SUM, tp, nb, T.fx.max_chunks, vec, false, D, s));
         LAUNCH_SPLIT(KC_FX_ADSR, T.fx_adsr, FxTask, offs[L].fx_adsr, T.fx_adsr.bytes, launch_fx(FX_ADSR, tp, nb, T.fx_adsr.max_chunks, vec, T.fx_adsr_exact, D, s));
         LAUNCH_SPLIT(KC_FX_NORM, T.fx_norm, FxTask, offs[L].fx_norm, T.fx_norm.bytes, launch_fx(FX_NORM_PEAK, tp, nb, T.fx_norm.max_chunks, vec, false, D, s));
@@ -2338,6 +2340,7 @@ int tdg_comm_destroy(tdg_ctx* h) {
 uint64_t tdg_collectives(tdg_ctx* h) { return h ? h->c.collectives : 0; }
 
 int tdg_set_pass_reuse(tdg_ctx* h, int on) { h->c.eng->reuse = on != 0; h->c.keep.valid = false; return TDG_OK; }
+int tdg_set_oscillator_mode(tdg_ctx* h, int libm_exact) { h->c.eng->libm_sin = libm_exact != 0; h->c.keep.valid = false; ++h->c.mut_gen; return TDG_OK; }
 int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; return TDG_OK; }
 int tdg_set_pipeline_group(tdg_ctx* h, uint32_t projects_per_group) { h->c.eng->pipeline_group = projects_per_group; return TDG_OK; }
 int tdg_last_pass_kernel_stats(tdg_ctx* h, tdg_kernel_stat* out, int cap) {

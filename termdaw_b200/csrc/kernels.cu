@@ -518,7 +518,9 @@ __device__ __forceinline__ float wavetable_eval(const float* __restrict__ tab, f
 // one L1-resident broadcast), and the per-voice release start values come precomputed in the segment.
 // The barrier-per-batch version spent a quarter of its stall cycles waiting for the two warps that
 // staged and pre-evaluated the segments (profiles/: stall_barrier).
-template <int KIND, bool EXACT, int F>
+// LIBM: sin is glibc's sinf restated in double precision (m_sinf_glibc: bit-exact against the reference's libm
+// call); false = the f32 Cody-Waite + minimax evaluation d_sin (<= 2 ulp, tdg_set_oscillator_mode(ctx, 0)).
+template <int KIND, bool EXACT, int F, bool LIBM>
 __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : TDG_SAMPSYN_MINB) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ VoiceTask T;
     load_task(&T, tasks + blockIdx.y);
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
             float smp[F];
             if (KIND == VOICE_DEBUG_SINE) {                                       // extensions.rs:450-454
 #pragma unroll
-                for (int j = 0; j < F; ++j) smp[j] = d_sin(m_osc_arg(time[j], hz)) * vel;
+                for (int j = 0; j < F; ++j) smp[j] = (LIBM ? m_sinf_glibc(m_osc_arg(time[j], hz)) : d_sin(m_osc_arg(time[j], hz))) * vel;
             } else {
                 float et[F], e[F];
 #pragma unroll
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
                     float sn[F];
                     if (T.vol[0] > 0.0f || T.vol[1] > 0.0f) {
 #pragma unroll
-                        for (int j = 0; j < F; ++j) sn[j] = d_sin(m_osc_arg(time[j], hz));
+                        for (int j = 0; j < F; ++j) sn[j] = LIBM ? m_sinf_glibc(m_osc_arg(time[j], hz)) : d_sin(m_osc_arg(time[j], hz));
                     }
 #pragma unroll
                     for (int j = 0; j < F; ++j) smp[j] = 0.0f;
@@ -1085,10 +1087,10 @@ cudaError_t launch_sample_lerp(const LerpTask* t, uint32_t n, uint32_t max_chunk
 // co-reside (DESIGN.md "co-scheduling").  The cap is expressed as reserved dynamic shared memory.
 static int g_voice_smem = -1;
 void set_voice_reserved_smem(int bytes) { g_voice_smem = bytes; }
-template <int KIND, bool EXACT>
+template <int KIND, bool EXACT, bool LIBM>
 static cudaError_t launch_voice_t(const VoiceTask* t, uint32_t n, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s) {
     if (g_voice_smem < 0) { const char* e = getenv("TDG_VOICE_SMEM"); g_voice_smem = e ? atoi(e) : 0; }
-    auto kfn = k_voice<KIND, EXACT, KIND == VOICE_SYNTH ? TDG_SYNTH_F : 4>;
+    auto kfn = k_voice<KIND, EXACT, KIND == VOICE_SYNTH ? TDG_SYNTH_F : 4, LIBM>;
     static int attr_set = -1;
     if (g_voice_smem > 48 * 1024 - 8192 && attr_set != g_voice_smem) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_voice_smem);
@@ -1098,12 +1100,15 @@ static cudaError_t launch_voice_t(const VoiceTask* t, uint32_t n, uint32_t max_c
     kfn<<<grid2(max_chunks, n), TDG_THREADS, (size_t)g_voice_smem, s>>>(t, blob);
     return cudaGetLastError();
 }
-cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool exact, const uint8_t* blob, cudaStream_t s) {
-    if (kind == VOICE_DEBUG_SINE)
-        return exact ? launch_voice_t<VOICE_DEBUG_SINE, true>(t, n, max_chunks, blob, s) : launch_voice_t<VOICE_DEBUG_SINE, false>(t, n, max_chunks, blob, s);
-    if (kind == VOICE_SYNTH)
-        return exact ? launch_voice_t<VOICE_SYNTH, true>(t, n, max_chunks, blob, s) : launch_voice_t<VOICE_SYNTH, false>(t, n, max_chunks, blob, s);
-    return exact ? launch_voice_t<VOICE_SAMPSYN, true>(t, n, max_chunks, blob, s) : launch_voice_t<VOICE_SAMPSYN, false>(t, n, max_chunks, blob, s);
+cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool exact, bool libm_sin, const uint8_t* blob, cudaStream_t s) {
+#define TDG_VOICE_DISPATCH(K) \
+    (exact ? (libm_sin ? launch_voice_t<K, true, true>(t, n, max_chunks, blob, s) : launch_voice_t<K, true, false>(t, n, max_chunks, blob, s)) \
+           : (libm_sin ? launch_voice_t<K, false, true>(t, n, max_chunks, blob, s) : launch_voice_t<K, false, false>(t, n, max_chunks, blob, s)))
+    if (kind == VOICE_DEBUG_SINE) return TDG_VOICE_DISPATCH(VOICE_DEBUG_SINE);
+    if (kind == VOICE_SYNTH) return TDG_VOICE_DISPATCH(VOICE_SYNTH);
+    // the wavetable voices evaluate no sine: one instantiation
+    return exact ? launch_voice_t<VOICE_SAMPSYN, true, false>(t, n, max_chunks, blob, s) : launch_voice_t<VOICE_SAMPSYN, false, false>(t, n, max_chunks, blob, s);
+#undef TDG_VOICE_DISPATCH
 }
 
 cudaError_t launch_bp_aggregate(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {

@@ -6,6 +6,7 @@
 // reference computes at event time (e.g. the Adsr vertex's stored release value).
 #pragma once
 #include <math.h>
+#include <string.h>
 #include "tdg_types.h"
 
 #ifdef __CUDACC__
@@ -59,6 +60,85 @@ TDG_HD float m_triangle(float t, float hz) {
     return 4.0f * fabsf((t * hz) - floorf((t * hz) + 0.5f)) - 1.0f;
 }
 
+
+// ---- sinf: glibc's algorithm, operation for operation ------------------------------------------------------
+// The reference's oscillators call Rust's f32::sin, i.e. the platform libm's sinf (extensions.rs:452, synth.rs:23,28).
+// glibc >= 2.28 computes sinf in double precision (sysdeps/ieee754/flt-32/s_sinf.c + sincosf.h, from ARM's
+// optimized routines): three argument ranges (|y| < pi/4, < 120, else), the reduction of large arguments by a
+// 96-bit window of the bits of 2/pi in integer arithmetic, one of two degree-7/8 polynomials in double, one
+// rounding to float at the end.  Restated here with the contraction pattern of the x86-64 FMA build (the ifunc
+// variant every FMA-capable host selects): tests/test_sinf_restatement.py checks this very function against the
+// host's sinf over ALL 2^32 arguments (0 mismatches on glibc 2.39), so on the device the oscillators are bit-exact
+// against the oracle instead of "within 2 ulp".  Constants: __sincosf_table / __inv_pio4 of glibc 2.39.
+#define TDG_INV_PIO4_WORDS {0xa2u, 0xa2f9u, 0xa2f983u, 0xa2f9836eu, 0xf9836e4eu, 0x836e4e44u, 0x6e4e4415u, 0x4e441529u, \
+                            0x441529fcu, 0x1529fc27u, 0x29fc2757u, 0xfc2757d1u, 0x2757d1f5u, 0x57d1f534u, 0xd1f534ddu, 0xf534ddc0u, \
+                            0x34ddc0dbu, 0xddc0db62u, 0xc0db6295u, 0xdb629599u, 0x6295993cu, 0x95993c43u, 0x993c4390u, 0x3c439041u}
+static const uint32_t kInvPio4Host[24] = TDG_INV_PIO4_WORDS;
+#ifdef __NVCC__
+static __constant__ uint32_t kInvPio4Dev[24] = TDG_INV_PIO4_WORDS;     // device copy: constant bank, near-uniform index
+#endif
+#ifdef __CUDA_ARCH__
+#define TDG_INV_PIO4 kInvPio4Dev
+#else
+#define TDG_INV_PIO4 kInvPio4Host
+#endif
+TDG_HD uint32_t m_f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+// sinf_poly (sincosf.h): n even -> sine polynomial of x, n odd -> cosine polynomial of x2; `neg` folds in the
+// quadrant sign (the reference multiplies x by +-1.0 and picks the table with negated cosine coefficients: both
+// polynomials are exactly odd in that sign under round-to-nearest, so negating the result is the same value)
+TDG_HD float m_sinf_poly(double x, double x2, int n, bool neg) {
+    double r;
+    if ((n & 1) == 0) {
+        const double x3 = x * x2;
+        const double s1 = fma(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+        const double x7 = x3 * x2;
+        const double s = fma(x3, -0x1.555545995a603p-3, x);
+        r = fma(x7, s1, s);
+    } else {
+        const double x4 = x2 * x2;
+        const double c2 = fma(x2, 0x1.99343027bf8c3p-16, -0x1.6c087e89a359dp-10);
+        const double c1 = fma(x2, -0x1.ffffffd0c621cp-2, 1.0);
+        const double x6 = x4 * x2;
+        const double c = fma(x4, 0x1.55553e1068f19p-5, c1);
+        r = fma(x6, c2, c);
+    }
+    const float f = (float)r;
+    return neg ? -f : f;
+}
+TDG_HD float m_sinf_glibc(float y) {
+    const uint32_t bits = m_f32_bits(y);
+    const uint32_t top = (bits >> 20) & 0x7ffu;                      // abstop12
+    double x = (double)y;
+    if (top < 0x3f4u) {                                              // |y| < pi/4 (abstop12(0x1.921FB6p-1f))
+        if (top < 0x398u) return y;                                  // |y| < 2^-12
+        return m_sinf_poly(x, x * x, 0, false);
+    }
+    if (top < 0x42fu) {                                              // |y| < 120: reduce_fast
+        const double r = x * 0x1.45F306DC9C883p+23;
+        const int n = ((int32_t)r + 0x800000) >> 24;
+        x = fma(-(double)n, 0x1.921FB54442D18p0, x);
+        const int m = n & 3;
+        return m_sinf_poly(x, x * x, n, (n & 1) ? (m >> 1) != 0 : (m == 1 || m == 2));
+    }
+    if (top < 0x7f8u) {                                              // finite: reduce_large
+        const uint32_t* arr = &TDG_INV_PIO4[(bits >> 26) & 15];
+        const int shift = (int)((bits >> 23) & 7);
+        const int sign = (int)(bits >> 31);
+        uint32_t xi = (bits & 0xffffffu) | 0x800000u;
+        xi <<= shift;
+        uint64_t res0 = (uint64_t)(uint32_t)(xi * arr[0]);
+        const uint64_t res1 = (uint64_t)xi * arr[4];
+        const uint64_t res2 = (uint64_t)xi * arr[8];
+        res0 = (res2 >> 32) | (res0 << 32);
+        res0 += res1;
+        const uint64_t nn = (res0 + (1ULL << 61)) >> 62;
+        res0 -= nn << 62;
+        x = (double)(int64_t)res0 * 0x1.921FB54442D18p-62;
+        const int n = (int)nn, m = (n + sign) & 3;
+        return m_sinf_poly(x, x * x, n, (n & 1) ? (m >> 1) != 0 : (m == 1 || m == 2));
+    }
+    return y - y;                                                    // inf / NaN -> NaN (__math_invalidf)
+}
 
 // ---- AdsrK: host builder (plain C++, same f32 operations as the reference's expressions) ---------
 inline bool adsr_duration_exotic(float d) {

@@ -3,13 +3,16 @@
 Tolerances (BASELINE.json north_star):
   * sample indexing / note timing: bit-exact -> graphs without transcendentals must match bit for bit
     before the IIR (sample_loop / sample_multi / sample_lerp / sampsyn / sum / adsr / normalize);
-  * fp32 pre-quantisation buffers: max-abs <= 1e-5 (relative to max(1, peak) of the buffer, since
-    pre-normalize buffers exceed 1.0); oscillators differ only by CUDA sinf vs glibc sinf (<= 2 ulp);
+  * oscillators: the device evaluates glibc's sinf operation for operation (tdg_math.cuh m_sinf_glibc, pinned
+    against the host libm over all 2^32 arguments by tests/test_sinf_restatement.py), every other f32
+    operation keeps the reference's order with one rounding each -> EVERY vertex whose input cone holds no
+    band pass must match the oracle bit for bit (`exact_outside_iir`), synth / sampsyn / debug_sine / adsr /
+    normalize included, at any bit depth;
   * band pass: the carried-in state of each 8-frame run is a reassociated scan, everything else is
-    the reference's operation order -> stated tolerance 2e-5 * max(1, peak);
-  * PCM: <= 1 LSB at 16 bit; at 24 bit one LSB (1.2e-7) is below one f32 ulp of a full-scale sample,
-    so the 1e-5 fp32 tolerance is what bounds it: <= 96 LSB (1.1e-5 of full scale), and bit-exact
-    graphs are still required to be <= 1 LSB.
+    the reference's operation order -> stated tolerance 2e-5 * max(1, peak) on the f32 buffers of the filter
+    and of everything downstream of it (measured worst: 7.5e-7);
+  * PCM: <= 1 LSB at 16 bit; at 24 bit bit-exact graphs are 0 LSB, graphs with a band pass <= 16 LSB
+    (1.9e-6 of full scale; measured worst 6: one LSB there is 1.2e-7, below one f32 ulp of a full-scale sample).
 """
 import json
 import os
@@ -27,15 +30,32 @@ TOL_F32 = 1e-5
 TOL_IIR = 2e-5
 
 
-def compare(got, want, label, exact_kinds=(), tol=TOL_F32, pcm_lsb=1, report=None):
+def iir_tainted(project):
+    """Names of the band-pass vertices and of everything downstream of one (the only reassociated arithmetic)."""
+    tainted = {t[0] for t in project.bandpasses}
+    grew = True
+    while grew:
+        grew = False
+        for a, b in project.edges:
+            if a in tainted and b not in tainted:
+                tainted.add(b); grew = True
+    return tainted
+
+
+def compare(got, want, label, exact_kinds=(), tol=TOL_F32, pcm_lsb=1, report=None, exact_outside_iir=None):
     assert got["cs"] == want["cs"]
     worst = {}
+    if exact_outside_iir is not None:
+        tainted = iir_tainted(exact_outside_iir)
+        exact_kinds = tuple(exact_kinds) + tuple(n for n in want["taps"] if n not in tainted)
+        if not tainted:
+            pcm_lsb = 0
     for name, (l, r) in want["taps"].items():
         gl, gr = got["taps"][name]
         peak = max(1.0, float(np.nanmax(np.abs(np.concatenate([l, r])))))
         d = max(max_abs_diff(gl, l), max_abs_diff(gr, r))
         worst[name] = d / peak
-        if any(k in name for k in exact_kinds):
+        if any(k == name for k in exact_kinds) or any(k in name for k in exact_kinds if exact_outside_iir is None):
             assert np.array_equal(gl, l, equal_nan=True) and np.array_equal(gr, r, equal_nan=True), \
                 (label, name, "expected bit-exact", d)
         else:
@@ -79,21 +99,21 @@ def test_config2_synth_adsr_bandpass(gpulib, oracle, report):
     """floww-driven synth + adsr -> band pass -> normalize, 24 bit (configs[1]), 6 s slice."""
     cfg = S.config_2(0.1)
     got, want = run_project(gpulib, *cfg), run_project(oracle, *cfg)
-    compare(got, want, "config2", tol=TOL_IIR, pcm_lsb=96, report=report)
+    compare(got, want, "config2", tol=TOL_IIR, pcm_lsb=16, report=report, exact_outside_iir=cfg[0])
 
 
 def test_config3_wavetable_lerp(gpulib, oracle, report):
     """wavetable voices + 2 sample_lerp from 44.1/96 kHz sources (configs[2]) scaled to 64 voices, 6 s."""
     cfg = S.config_3(0.01, voices=64)
     got, want = run_project(gpulib, *cfg), run_project(oracle, *cfg)
-    compare(got, want, "config3", report=report)
+    compare(got, want, "config3", report=report, exact_outside_iir=cfg[0])
 
 
 def test_config4_mixed_graph(gpulib, oracle, report):
     """64-vertex mixed graph (configs[3]), 7 s slice, 24 bit."""
     cfg = S.config_4(0.002, 64)
     got, want = run_project(gpulib, *cfg), run_project(oracle, *cfg)
-    compare(got, want, "config4", tol=TOL_IIR, pcm_lsb=96, report=report)
+    compare(got, want, "config4", tol=TOL_IIR, pcm_lsb=16, report=report, exact_outside_iir=cfg[0])
 
 
 @pytest.mark.parametrize("index", [0, 1, 2, 3, 4, 5, 6, 7])
@@ -101,7 +121,7 @@ def test_config5_batch_projects(gpulib, oracle, report, index):
     """projects of the algorithmic-composition batch (configs[4]), 3 s each, 16 bit."""
     cfg = S.config_5_project(index, 0.1)
     got, want = run_project(gpulib, *cfg), run_project(oracle, *cfg)
-    compare(got, want, f"config5_{index}", tol=TOL_IIR, report=report)
+    compare(got, want, f"config5_{index}", tol=TOL_IIR, report=report, exact_outside_iir=cfg[0])
 
 
 def test_render_many_equals_single(gpulib, oracle):

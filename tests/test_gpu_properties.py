@@ -44,7 +44,7 @@ def test_config2_full_size(gpulib, oracle):
         peak = max(1.0, float(np.nanmax(np.abs(np.concatenate([l, r])))))
         d = max(max_abs_diff(got["taps"][name][0], l), max_abs_diff(got["taps"][name][1], r))
         assert d / peak <= TOL_IIR, (name, d, peak)
-    _pcm_close(got["pcm"], want["pcm"], 24, 96)
+    _pcm_close(got["pcm"], want["pcm"], 24, 16)
 
 
 @pytest.mark.parametrize("index", [0, 5, 11, 300, 4095])
@@ -106,7 +106,7 @@ def test_time_sharding_is_invisible_config4(gpulib):
         for k, v in whole["norm"].items():
             assert abs(st.normalization_values()[k] - v) <= TOL_IIR * max(1.0, abs(v))
         st.close()
-    _pcm_close(pcm, whole["pcm"], 24, 96)
+    _pcm_close(pcm, whole["pcm"], 24, 16)
 
 
 def test_sample_loop_periodicity_and_normalize_peak(gpulib):

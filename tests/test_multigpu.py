@@ -66,7 +66,7 @@ def test_nccl_time_sharded_resampled_render(oracle, tmp_path):
         assert inf["offset"] == sum(np.load(tmp_path / f"pcm_{q}.npy").size for q in range(k))
 
 
-@pytest.mark.parametrize("case,lsb", [("c2:0.1", 96), ("c4:0.002", 96)])
+@pytest.mark.parametrize("case,lsb", [("c2:0.1", 16), ("c4:0.002", 16)])
 def test_nccl_time_sharded_filters_and_voices(oracle, tmp_path, case, lsb):
     """configs[1] and configs[3] split by time: band-pass state crosses ranks as affine maps (all-gather),
     voices / envelopes by event replay, normalize peak by max-allreduce."""

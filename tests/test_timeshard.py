@@ -169,7 +169,7 @@ def test_resampled_segment_with_filter_and_errors(gpulib, oracle):
     pcm, norms, bd = _sharded(gpulib, cfg, 4)
     a, b = pcm_to_int(pcm, bd), pcm_to_int(want["pcm"], want["bd"])
     assert a.shape == b.shape
-    assert int(np.abs(a - b).max()) <= 96
+    assert int(np.abs(a - b).max()) <= 16
     # a lone resampled segment that does not start the pass has no history to read
     p, a_, s = cfg
     st = State(gpulib, s["psr"], s["bl"], assets=a_)
@@ -188,7 +188,7 @@ def test_resampled_segment_with_filter_and_errors(gpulib, oracle):
 def test_virtual_ranks_filters_and_voices(gpulib, oracle, n_seg):
     """synth -> adsr -> band pass -> normalize (configs[1]) and the 64-vertex graph (configs[3]) split by
     time: filter state crosses the boundaries as affine maps, voices/envelopes by event replay."""
-    for cfg, lsb in ((S.config_2(0.1), 96), (S.config_4(0.002, 64), 96)):
+    for cfg, lsb in ((S.config_2(0.1), 16), (S.config_4(0.002, 64), 16)):
         want = run_project(oracle, *cfg, taps=False)
         pcm, norms, bd = _sharded(gpulib, cfg, n_seg)
         a, b = pcm_to_int(pcm, bd), pcm_to_int(want["pcm"], want["bd"])
