@@ -67,6 +67,11 @@ uint64_t tdg_kernel_launches(tdg_ctx* ctx);
  * project rate.  Returns the sample index (SampleBank::get_index, sample.rs:338). */
 int tdg_sample_add(tdg_ctx* ctx, const float* linear, uint64_t n_values, uint32_t channels,
                    uint32_t src_sr, int mode);
+/* SampleBank::mark_dead + refresh (sample.rs:316-336): drop a sample that left the script or changed; its
+ * device memory is freed, the other indices stay valid.  tdg_resource_remove: the same for BufferBank blobs
+ * (state.rs:222-237). */
+int tdg_sample_remove(tdg_ctx* ctx, int sample);
+int tdg_resource_remove(tdg_ctx* ctx, int resource);
 /* Frames of a loaded sample at project rate (Sample::len, sample.rs:79). */
 int64_t tdg_sample_frames(tdg_ctx* ctx, int sample);
 /* Debug tap: copy a loaded sample (after normalise + resample) back to the host. */
@@ -76,7 +81,11 @@ int tdg_sample_read(tdg_ctx* ctx, int sample, float* l, float* r, uint64_t cap_f
 int tdg_resource_add(tdg_ctx* ctx, const uint8_t* bytes, uint64_t n);
 
 /* FlowwBank::declare_floww / add_floww / declare_stream (floww.rs:32-53): one floww = time-sorted
- * events (t seconds, note, vel); vel <= 0.001 is a note-off (floww.rs:114,134). n may be 0. */
+ * events (t seconds, note, vel); vel <= 0.001 is a note-off (floww.rs:114,134). n may be 0.
+ * PRECONDITION: event frames (t * sr) must be non-decreasing, else TDG_ERR_UNSORTED.  What the reference's
+ * crate hands FlowwBank (a MIDI file read in tick order, stream packets in arrival order) is sorted; its
+ * cursor (floww.rs:70-96) walks forward only, so an out-of-order event would merely be skipped or replayed
+ * there — a degradation this ABI refuses to reproduce.  Callers with late packets sort before the call. */
 int tdg_floww_add(tdg_ctx* ctx, const float* t_sec, const float* note, const float* vel, uint64_t n);
 /* FlowwBank::append_streams (floww.rs:55-57; the Feed handler of stream_workflow.rs:63-71): more events for
  * a declared stream while the transport runs.  Events must not start before the stream's last event

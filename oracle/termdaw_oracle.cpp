@@ -823,6 +823,18 @@ int tdo_sample_read(tdo_ctx* x, int sample, float* l, float* r, uint64_t cap) {
     std::memcpy(l, s.l.data(), s.l.size() * 4); std::memcpy(r, s.r.data(), s.r.size() * 4);
     return OK;
 }
+// SampleBank::mark_dead + refresh (sample.rs:316-336) / the resource sweep (state.rs:222-237): slots are emptied,
+// the other indices stay valid (same contract as tdg_sample_remove / tdg_resource_remove)
+int tdo_sample_remove(tdo_ctx* x, int sample) {
+    if (sample < 0 || (size_t)sample >= x->c.samples.size()) return ERR_INVALID;
+    x->c.samples[sample] = Sample();
+    return OK;
+}
+int tdo_resource_remove(tdo_ctx* x, int resource) {
+    if (resource < 0 || (size_t)resource >= x->c.buffers.size()) return ERR_INVALID;
+    std::vector<uint8_t>().swap(x->c.buffers[resource]);
+    return OK;
+}
 int tdo_resource_add(tdo_ctx* x, const uint8_t* bytes, uint64_t n) {
     x->c.buffers.emplace_back(bytes, bytes + n);
     return (int)x->c.buffers.size() - 1;
@@ -845,7 +857,7 @@ int tdo_graph_reset(tdo_ctx* x) {                                           // g
     return OK;
 }
 
-static int chk_sample(Ctx& c, int s) { return (s < 0 || (size_t)s >= c.samples.size()) ? c.fail(ERR_INVALID, "unknown sample") : OK; }
+static int chk_sample(Ctx& c, int s) { return (s < 0 || (size_t)s >= c.samples.size() || c.samples[(size_t)s].l.empty()) ? c.fail(ERR_INVALID, "unknown sample") : OK; }   // emptied slot: removed sample
 static int chk_floww(Ctx& c, int f) { return (f < 0 || (size_t)f >= c.fb.flowws.size()) ? c.fail(ERR_INVALID, "unknown floww") : OK; }
 
 int tdo_add_sum(tdo_ctx* x, float gain, float angle) {

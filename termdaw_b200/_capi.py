@@ -67,6 +67,8 @@ class Library:
         "last_error": (C.c_char_p, [C.c_void_p]),
         "kernel_launches": (C.c_uint64, [C.c_void_p]),
         "sample_add": (C.c_int, [C.c_void_p, c_f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]),
+        "sample_remove": (C.c_int, [C.c_void_p, C.c_int]),
+        "resource_remove": (C.c_int, [C.c_void_p, C.c_int]),
         "sample_frames": (C.c_int64, [C.c_void_p, C.c_int]),
         "sample_read": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_uint64]),
         "resource_add": (C.c_int, [C.c_void_p, c_u8p, C.c_uint64]),
@@ -194,6 +196,13 @@ class Context:
     def sample_add(self, linear, channels: int, src_sr: int, mode: int = 0) -> int:
         a = _f32(linear).ravel()
         return self._chk(self.lib.sample_add(self.h, _p(a), a.size, channels, src_sr, mode))
+
+    def sample_remove(self, s: int):
+        """SampleBank::mark_dead + refresh (sample.rs:316-336): free a sample that left the script or changed."""
+        self._chk(self.lib.sample_remove(self.h, s))
+
+    def resource_remove(self, r: int):
+        self._chk(self.lib.resource_remove(self.h, r))
 
     def sample_frames(self, s: int) -> int:
         return self._chk(self.lib.sample_frames(self.h, s))

@@ -175,6 +175,10 @@ struct WorkerPool {
 
 struct Frag;
 struct PlanScratch;
+struct VPlan;
+// clock table of one (sr, bl) (tdg_types.h): rows are only ever appended while passes are in flight; growing past
+// the allocation waits for the device first
+struct ClockTab { float* p = nullptr; uint32_t depth = 0, cap = 0; cudaEvent_t ev = nullptr; bool ev_set = false; };
 struct Engine {
     int device = 0;
     Lane lanes[kLanes];
@@ -191,10 +195,13 @@ struct Engine {
     uint64_t hwm_work = 0, hwm_blob = 0, hwm_pcm = 0;         // largest work arena / plan blob any lane or slot has needed
     uint64_t hwm_keep = 0;
     bool reuse = true;                           // render reads pass-invariant cones from the scan (TDG_PASS_REUSE=0 / tdg_set_pass_reuse)
+    uint64_t bp_l2_bytes = 48ull << 20;          // band-pass launch groups: inputs + outputs per group (TDG_BP_L2_MB, 0 = one launch triple per level)
     bool libm_sin = true;                        // oscillators evaluate glibc's sinf exactly (TDG_FAST_SIN=1 / tdg_set_oscillator_mode(ctx, 0): f32 polynomial, <= 2 ulp)
     WorkerPool* pool = nullptr;                  // planner threads (created on first batched pass)
     std::vector<Frag>* frags = nullptr;          // pooled per-project plan fragments (capacity is kept between jobs)
     std::vector<PlanScratch>* scratch = nullptr; // per worker: event-table scratch vectors
+    std::vector<std::vector<VPlan>>* vplans = nullptr;   // per request of a job x vertex: event plans (pooled)
+    std::map<uint64_t, ClockTab> clocks;         // key: sr << 32 | bl
     cudaEvent_t ev_batch0 = nullptr, ev_batch1[kLanes] = {}, ev_copy_end = nullptr;   // span of a pipelined call
 };
 static std::mutex g_mu;
@@ -233,6 +240,7 @@ static Engine* engine_get(int device, std::string* err) {
     if (const char* e = getenv("TDG_TAPER")) g->taper = atoi(e) != 0;
     if (const char* e = getenv("TDG_PASS_REUSE")) g->reuse = atoi(e) != 0;
     if (const char* e = getenv("TDG_FAST_SIN")) g->libm_sin = atoi(e) == 0;
+    if (const char* e = getenv("TDG_BP_L2_MB")) g->bp_l2_bytes = (uint64_t)std::max(0, atoi(e)) << 20;
     g->refs = 1;
     g_engines[device] = g;
     return g;
@@ -465,18 +473,61 @@ static void plan_lerp(HVertex& v, const Floww& fl, const PassParams& pp, std::ve
     }
 }
 
-struct SegOut {                     // per-chunk CSR of voice / envelope segments
-    std::vector<uint32_t> ptr;
-    std::vector<VoiceSeg> vseg;
-    std::vector<float> relv2;           // parallel to vseg
-    std::vector<AdsrSeg> aseg;
+// Event plan of one vertex for one pass: O(events) records; the per-chunk tables are made on the device
+// (k_chunk_ranges, the in-kernel staging of k_voice / k_fx<adsr>).  Pooled per (request, vertex).
+struct VPlan {
+    std::vector<VoiceRec> vrecs;
+    std::vector<AdsrRec> arecs;
+    std::vector<MultiHit> mhits;
+    std::vector<LerpHit> lhits;
+    std::vector<float> xenv;            // explicit clocks, concatenated (state carried in from an earlier pass)
     uint64_t voice_frames = 0;
+    uint32_t depth = 0;                 // rows of the clock table this vertex reads
+    bool planned = false;
 };
-struct KeyedSeg { uint64_t seq; VoiceSeg s; float r2; };
+struct PlanScratch {                    // per planner thread
+    std::vector<std::vector<float>> xc; std::vector<size_t> xoff;       // explicit clocks under construction
+    // host copy of the clock table (tdg_types.h) of one (sr, bl), rows appended on demand: a voice's clock at its
+    // note-off in O(1) instead of one addition per chunk it was held
+    std::vector<float> hclk; uint32_t hclk_sr = 0, hclk_bl = 0, hclk_rows = 0;
+    static const uint32_t kHostClockRows = 16384;
+    float clock(uint32_t sr, uint32_t bl, uint32_t i, uint32_t n) {
+        const float fsr = (float)sr, d = (float)bl / fsr;
+        if (n >= kHostClockRows || i >= bl) { float e = -((float)i / fsr); for (uint32_t q = 0; q < n; ++q) e += d; return e; }
+        if (hclk_sr != sr || hclk_bl != bl) { hclk_sr = sr; hclk_bl = bl; hclk_rows = 0; hclk.clear(); }
+        if (n >= hclk_rows) {
+            const uint32_t want = std::min(kHostClockRows, std::max(n + 1, hclk_rows * 2));
+            hclk.resize((size_t)want * bl);
+            for (uint32_t r = hclk_rows; r < want; ++r) {
+                float* row = hclk.data() + (size_t)r * bl;
+                if (r == 0) for (uint32_t c = 0; c < bl; ++c) row[c] = -((float)c / fsr);
+                else { const float* prev = row - bl; for (uint32_t c = 0; c < bl; ++c) row[c] = prev[c] + d; }
+            }
+            hclk_rows = want;
+        }
+        return hclk[(size_t)n * bl + i];
+    }
+};
 
-// debug_sine_gen / synth_gen / sampsyn_gen voice lifecycle (extensions.rs:429-445, 481-496, 525-528)
-static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, SegOut& out) {
-    out.ptr.assign(1, 0); out.vseg.clear(); out.relv2.clear(); out.voice_frames = 0;
+// explicit clocks -> out.xenv; *src words holding (kEnvExplicit | clock id) become (kEnvExplicit | float index)
+static void pack_explicit(PlanScratch& S, size_t n_x, std::vector<float>& xenv) {
+    S.xoff.assign(n_x + 1, 0);
+    xenv.clear();
+    for (size_t c = 0; c < n_x; ++c) { S.xoff[c] = xenv.size(); xenv.insert(xenv.end(), S.xc[c].begin(), S.xc[c].end()); }
+}
+static inline uint32_t patch_src(const PlanScratch& S, uint32_t src) {
+    return (src & kEnvExplicit) ? (kEnvExplicit | (uint32_t)S.xoff[src & ~kEnvExplicit]) : src;
+}
+
+// debug_sine_gen / synth_gen / sampsyn_gen voice lifecycle (extensions.rs:429-445, 481-496, 525-528): one
+// VoiceRec per voice, in Vec order.  Event driven: nothing is done per chunk.  A voice's clock is needed on the
+// host at its note-off only (rel_t = env_t + fi) and for the drop rule after it (env_t > release_sec at the end of
+// a chunk), and both are replayed there with the reference's own sequence of f32 additions.
+static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, VPlan& out, PlanScratch& S) {
+    std::vector<VoiceRec>& R = out.vrecs;
+    R.clear(); out.xenv.clear(); out.voice_frames = 0; out.depth = 0;
+    size_t n_x = 0;
+    auto new_xclk = [&]() -> int { if (S.xc.size() <= n_x) S.xc.emplace_back(); S.xc[n_x].clear(); return (int)n_x++; };
     const float fsr = (float)pp.sr;
     const float d = (float)pp.bl / fsr;                              // len as f32 / sr as f32
     float release_sec = 0.0f;
@@ -485,122 +536,224 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, SegOu
         if (v.tf.volume > 0.0f) release_sec = fmaxf(release_sec, v.tf.adsr.release_sec);
         if (v.tr.volume > 0.0f) release_sec = fmaxf(release_sec, v.tr.adsr.release_sec);
     } else if (v.kind == K_SAMPSYN) release_sec = v.adsr.release_sec;
-    std::vector<KeyedSeg> chunk;
+    if (pp.total == 0) return;
+    const uint32_t total = (uint32_t)pp.total, last = total - 1;
+    auto open_rec = [&](float hz, float vel, uint32_t k, uint32_t i, uint32_t envh) -> int {
+        VoiceRec r; memset(&r, 0, sizeof r);
+        r.hz = hz; r.vel = vel; r.on_chunk = k; r.on_i = i; r.off_chunk = kNever; r.end_chunk = kNever; r.envh = envh;
+        R.push_back(r);
+        return (int)R.size() - 1;
+    };
+    // a record right behind `at`, i.e. in the same place of the reference's Vec (in-place changes of a voice)
+    auto insert_after = [&](int at, const VoiceRec& r) -> int {
+        R.insert(R.begin() + at + 1, r);
+        for (DNote& n : v.dnotes) if (n.rec > at) ++n.rec;
+        for (SNote& n : v.notes) if (n.rec > at) ++n.rec;
+        return at + 1;
+    };
+    auto close_rec = [&](int rec, uint32_t k, uint32_t i) { R[rec].end_chunk = k; R[rec].end_i = i; };
+    // the clock of voice n at the start of pass chunk k (k >= its clk_chunk): explicit clocks grow on demand
+    auto clock_of = [&](const SNote& n, uint32_t k) -> float {
+        if (n.xclk >= 0) {
+            std::vector<float>& x = S.xc[n.xclk];
+            while (x.size() <= k) x.push_back(x.back() + d);
+            return x[k];
+        }
+        return S.clock(pp.sr, pp.bl, n.clk_i, k - n.clk_chunk);
+    };
+    // extensions.rs:528 runs at the end of every chunk: a released voice goes once env_t > release_sec.  From the
+    // clock value e at the start of chunk k: the chunk at whose end it is dropped (kNever: outlives the pass)
+    auto drop_after = [&](float e, uint32_t k) -> uint32_t {
+        for (uint32_t q = k; q < total; ++q) { e += d; if (!(e <= release_sec)) return q; }
+        return kNever;
+    };
+    // voices alive from an earlier pass: their clocks are not of the table's form -> explicit per-chunk values
+    for (DNote& n : v.dnotes) n.rec = open_rec(n.hz, n.vel, 0, 0, 0);
+    for (SNote& n : v.notes) {
+        n.xclk = new_xclk();
+        S.xc[n.xclk].push_back(n.env_t);
+        n.clk_chunk = 0; n.clk_i = 0;
+        n.rec = open_rec(n.hz, n.vel, 0, 0, 0);
+        VoiceRec& r = R[n.rec];
+        if (n.rel_t == 0.0f) { r.envh = kEnvExplicit | (uint32_t)n.xclk; n.drop_chunk = kNever; }
+        else {
+            r.off_chunk = 0; r.off_i = 0; r.envr = kEnvExplicit | (uint32_t)n.xclk; r.rel_t = n.rel_t; r.relv0 = n.relv[0]; r.relv1 = n.relv[1]; r.relv2 = n.relv[2];
+            n.drop_chunk = drop_after(n.env_t, 0);
+        }
+    }
+    uint32_t next_drop = kNever;                                     // earliest pending drop chunk: nothing to purge before it
+    for (const SNote& n : v.notes) next_drop = std::min(next_drop, n.drop_chunk);
+    auto purge = [&](uint32_t k) {                                   // everything dropped at the end of a chunk < k
+        if (next_drop == kNever || next_drop >= k) return;
+        next_drop = kNever;
+        size_t w = 0;
+        for (size_t q = 0; q < v.notes.size(); ++q) {
+            SNote& n = v.notes[q];
+            if (n.drop_chunk != kNever && n.drop_chunk < k) close_rec(n.rec, n.drop_chunk, pp.bl);
+            else { next_drop = std::min(next_drop, n.drop_chunk); if (w != q) v.notes[w] = n; ++w; }
+        }
+        v.notes.resize(w);
+    };
     EvCursor cur(&fl, pp.F0);
-    for (uint64_t k = 0; k < pp.total; ++k) {
-        const bool emit = k >= pp.emit0 && k < pp.emit0 + pp.emit_n;
-        chunk.clear();
-        bool had_event = false;
-        auto close_d = [&](DNote& n, uint32_t ib) {
-            if (emit && ib > n.ia) chunk.push_back({n.seq, VoiceSeg{n.hz, n.vel, 0.0f, 0.0f, n.ia, ib, 0.0f, 0.0f}, 0.0f});
-        };
-        auto close_s = [&](SNote& n, uint32_t ib) {
-            if (emit && ib > n.ia) chunk.push_back({n.seq, VoiceSeg{n.hz, n.vel, n.env_t, n.rel_t, n.ia, ib, n.relv[0], n.relv[1]}, n.relv[2]});
-        };
-        simple_chunk(cur, pp.F0 + k * pp.bl, pp.bl, [&](uint32_t i, bool on, float note, float vel) {
-            had_event = true;
+    for (uint64_t k64 = 0; k64 < pp.total; ++k64) {
+        const uint32_t k = (uint32_t)k64;
+        simple_chunk(cur, pp.F0 + k64 * pp.bl, pp.bl, [&](uint32_t i, bool on, float note, float vel) {
             const float fi = (float)i / fsr;
             if (v.kind == K_DEBUG_SINE) {
                 if (on) {
                     bool has = false;
                     for (DNote& n : v.dnotes)
-                        if (fabsf(n.note - note) < 0.001f) { close_d(n, i); n.vel = vel; n.ia = i; has = true; break; }
-                    if (!has) v.dnotes.push_back({note, vel, note_hz(note), v.seq++, i});
+                        if (fabsf(n.note - note) < 0.001f) {                 // the velocity is replaced in place (extensions.rs:433-438)
+                            close_rec(n.rec, k, i);
+                            VoiceRec c = R[n.rec]; c.vel = vel; c.on_chunk = k; c.on_i = i; c.end_chunk = kNever; c.end_i = 0;
+                            n.rec = insert_after(n.rec, c); n.vel = vel; has = true; break;
+                        }
+                    if (!has) { const float hz = note_hz(note); v.dnotes.push_back({note, vel, hz, open_rec(hz, vel, k, i, 0)}); }
                 } else {
                     size_t w = 0;
                     for (size_t q = 0; q < v.dnotes.size(); ++q) {
                         if (fabsf(v.dnotes[q].note - note) > 0.001f) v.dnotes[w++] = v.dnotes[q];
-                        else close_d(v.dnotes[q], i);
+                        else close_rec(v.dnotes[q].rec, k, i);
                     }
                     v.dnotes.resize(w);
                 }
-            } else {
-                if (on) {
-                    v.notes.push_back(SNote{note, vel, -fi, 0.0f, note_hz(note), v.seq++, i});
+                return;
+            }
+            purge(k);
+            if (on) {
+                const float hz = note_hz(note);
+                SNote n{note, vel, 0.0f, 0.0f, hz, open_rec(hz, vel, k, i, i), -1};
+                n.clk_chunk = k; n.clk_i = i; n.drop_chunk = kNever;
+                v.notes.push_back(n);
+                return;
+            }
+            // retain (extensions.rs:485) drops the voices of this note that are already releasing; the others of this
+            // note start their release (extensions.rs:486-494).  One scan finds the note's voices (usually one).
+            bool any_rel = false, any_held = false;
+            for (const SNote& n : v.notes) if (!(fabsf(n.note - note) > 0.001f)) { if (n.rel_t == 0.0f) any_held = true; else any_rel = true; }
+            if (any_rel) {
+                size_t w = 0;
+                for (size_t q = 0; q < v.notes.size(); ++q) {
+                    SNote& n = v.notes[q];
+                    if (fabsf(n.note - note) > 0.001f || n.rel_t == 0.0f) { if (w != q) v.notes[w] = n; ++w; }
+                    else close_rec(n.rec, k, i);
+                }
+                v.notes.resize(w);
+            }
+            if (any_held) for (SNote& n : v.notes) {
+                if (fabsf(n.note - note) > 0.001f || n.rel_t != 0.0f) continue;
+                n.rel_t = clock_of(n, k) + fi;                              // env_t + i/sr
+                n.xclk = -1; n.clk_chunk = k; n.clk_i = i;                  // env_t = -(i/sr): the clock restarts, column i
+                // apply_r_rt's start value apply_ads(conf, rel_t) (adsr.rs:89-92): constant from here on
+                if (v.kind == K_SYNTH) {
+                    n.relv[0] = m_apply_ads(v.sq.adsr, n.rel_t); n.relv[1] = m_apply_ads(v.tf.adsr, n.rel_t);
+                    n.relv[2] = m_apply_ads(v.tr.adsr, n.rel_t);
+                } else n.relv[0] = m_apply_ads(v.adsr, n.rel_t);
+                if (n.rel_t != 0.0f) {
+                    VoiceRec& r = R[n.rec];
+                    r.off_chunk = k; r.off_i = i; r.envr = i; r.rel_t = n.rel_t;
+                    r.relv0 = n.relv[0]; r.relv1 = n.relv[1]; r.relv2 = n.relv[2];
+                    n.drop_chunk = drop_after(-fi, k);
+                    next_drop = std::min(next_drop, n.drop_chunk);
                 } else {
-                    size_t w = 0;
-                    for (size_t q = 0; q < v.notes.size(); ++q) {           // retain (extensions.rs:485)
-                        SNote& n = v.notes[q];
-                        if (fabsf(n.note - note) > 0.001f || n.rel_t == 0.0f) { if (w != q) v.notes[w] = n; ++w; }
-                        else close_s(n, i);
-                    }
-                    v.notes.resize(w);
-                    for (SNote& n : v.notes) {                              // extensions.rs:486-494
-                        if (fabsf(n.note - note) > 0.001f) continue;
-                        if (n.rel_t == 0.0f) {
-                            close_s(n, i);
-                            n.rel_t = n.env_t + fi;
-                            n.env_t = -fi;
-                            n.ia = i;
-                            // apply_r_rt's start value apply_ads(conf, rel_t) (adsr.rs:89-92): constant from here on
-                            if (v.kind == K_SYNTH) {
-                                n.relv[0] = m_apply_ads(v.sq.adsr, n.rel_t); n.relv[1] = m_apply_ads(v.tf.adsr, n.rel_t);
-                                n.relv[2] = m_apply_ads(v.tr.adsr, n.rel_t);
-                            } else n.relv[0] = m_apply_ads(v.adsr, n.rel_t);
-                        }
-                    }
+                    // env_t + fi == 0.0 exactly (a note-off in the frame of its note-on): the voice still reads as
+                    // held (rel_t == 0.0) but its clock restarted: a continuation record in its place
+                    close_rec(n.rec, k, i);
+                    VoiceRec c = R[n.rec]; c.on_chunk = k; c.on_i = i; c.envh = i; c.off_chunk = kNever; c.end_chunk = kNever; c.end_i = 0;
+                    n.rec = insert_after(n.rec, c);
                 }
             }
         });
-        if (v.kind == K_DEBUG_SINE) {
-            for (DNote& n : v.dnotes) { close_d(n, pp.bl); n.ia = 0; }
-        } else {
-            for (SNote& n : v.notes) { close_s(n, pp.bl); n.ia = 0; }
-            for (SNote& n : v.notes) n.env_t += d;                          // extensions.rs:525-527
-            size_t w = 0;
-            for (size_t q = 0; q < v.notes.size(); ++q)                     // extensions.rs:528
-                if (v.notes[q].rel_t == 0.0f || v.notes[q].env_t <= release_sec) { if (w != q) v.notes[w] = v.notes[q]; ++w; }
-            v.notes.resize(w);
-        }
-        if (emit) {
-            if (had_event)
-                std::stable_sort(chunk.begin(), chunk.end(), [](const KeyedSeg& a, const KeyedSeg& b) {
-                    return a.seq != b.seq ? a.seq < b.seq : a.s.ia < b.s.ia; });
-            for (const KeyedSeg& ks : chunk) { out.vseg.push_back(ks.s); out.relv2.push_back(ks.r2); out.voice_frames += ks.s.ib - ks.s.ia; }
-            out.ptr.push_back((uint32_t)out.vseg.size());
+    }
+    purge(total);
+    for (DNote& n : v.dnotes) close_rec(n.rec, last, pp.bl);
+    for (SNote& n : v.notes) {
+        close_rec(n.rec, last, pp.bl);
+        if (n.xclk >= 0) (void)clock_of(n, last);                           // the device reads the explicit clock up to the last chunk
+        n.env_t = clock_of(n, total);                                        // carried into the next pass
+    }
+    // explicit clocks of voices that ended inside the pass: values up to their last chunk
+    for (const VoiceRec& r : R) {
+        const uint32_t srcs[2] = {r.envh, r.off_chunk != kNever ? r.envr : 0u};
+        for (uint32_t src : srcs) if (src & kEnvExplicit) {
+            std::vector<float>& x = S.xc[src & ~kEnvExplicit];
+            const uint32_t upto = std::min(r.end_chunk, last);
+            while (x.size() <= upto) x.push_back(x.back() + d);
         }
     }
+    pack_explicit(S, n_x, out.xenv);
+    const uint64_t e0 = pp.emit0 * pp.bl, e1 = (pp.emit0 + pp.emit_n) * pp.bl;
+    uint32_t pm = 0;
+    for (VoiceRec& r : R) {
+        r.envh = patch_src(S, r.envh); r.envr = patch_src(S, r.envr);
+        pm = std::max(pm, r.end_chunk); r.pm_end = pm;
+        const uint32_t held_end = std::min(r.off_chunk, r.end_chunk);
+        if (!(r.envh & kEnvExplicit) && held_end >= r.on_chunk) out.depth = std::max(out.depth, held_end - r.on_chunk + 1);
+        if (r.off_chunk != kNever && !(r.envr & kEnvExplicit) && r.end_chunk >= r.off_chunk) out.depth = std::max(out.depth, r.end_chunk - r.off_chunk + 1);
+        const uint64_t a = std::max<uint64_t>((uint64_t)r.on_chunk * pp.bl + r.on_i, e0), b = std::min<uint64_t>((uint64_t)r.end_chunk * pp.bl + r.end_i, e1);
+        if (b > a) out.voice_frames += b - a;
+    }
+    uint32_t sm = kNever;
+    for (size_t q = R.size(); q-- > 0;) { sm = std::min(sm, R[q].on_chunk); R[q].sm_on = sm; }
 }
 
-// adsr_gen state machine (extensions.rs:593-651)
-static void plan_adsr(HVertex& v, const Floww& fl, const PassParams& pp, SegOut& out) {
-    out.ptr.assign(1, 0); out.aseg.clear();
+// adsr_gen state machine (extensions.rs:593-651): one AdsrRec per state change
+static void plan_adsr(HVertex& v, const Floww& fl, const PassParams& pp, VPlan& out, PlanScratch& S) {
+    std::vector<AdsrRec>& R = out.arecs;
+    R.clear(); out.xenv.clear(); out.depth = 0;
+    size_t n_x = 0;
+    auto new_xclk = [&]() -> int { if (S.xc.size() <= n_x) S.xc.emplace_back(); S.xc[n_x].clear(); return (int)n_x++; };
     const float fsr = (float)pp.sr;
     const float d = (float)pp.bl / fsr;
     A3 &P = v.aprimary, &G = v.aghost;
+    struct Clk { uint32_t src, chunk; int x; };
+    // both slots arrive with whatever the pass before left in them: explicit clocks until an event restarts them
+    Clk Pc, Gc;
+    { const int a = new_xclk(), b = new_xclk(); Pc = Clk{kEnvExplicit | (uint32_t)a, 0, a}; Gc = Clk{kEnvExplicit | (uint32_t)b, 0, b}; }
+    auto push = [&](uint64_t start, uint32_t flags) {
+        const AdsrRec r{start, flags, 0, Pc.src, Pc.chunk, P.vel, P.rel, Gc.src, Gc.chunk, G.vel, G.rel};
+        if (!R.empty() && R.back().start == start) R.back() = r; else R.push_back(r);
+    };
+    push(0, 0);
     EvCursor cur(&fl, pp.F0);
-    for (uint64_t k = 0; k < pp.total; ++k) {
-        const bool emit = k >= pp.emit0 && k < pp.emit0 + pp.emit_n;
-        const size_t base = out.aseg.size();
-        auto push = [&](uint32_t ia, uint32_t flags) {
-            if (!emit || ia >= pp.bl) return;
-            AdsrSeg s{ia, flags, P.t, P.vel, P.rel, G.t, G.vel, G.rel};
-            if (out.aseg.size() > base && out.aseg.back().ia == ia) out.aseg.back() = s; else out.aseg.push_back(s);
-        };
-        push(0, 0);
+    for (uint64_t k64 = 0; k64 < pp.total; ++k64) {
+        const uint32_t k = (uint32_t)k64;
+        const uint64_t c0 = k64 * pp.bl;
+        if (Pc.x >= 0) S.xc[Pc.x].push_back(P.t);
+        if (Gc.x >= 0) S.xc[Gc.x].push_back(G.t);
         if (v.use_off) {
-            simple_chunk(cur, pp.F0 + k * pp.bl, pp.bl, [&](uint32_t i, bool on, float note, float vel) {
+            simple_chunk(cur, pp.F0 + c0, pp.bl, [&](uint32_t i, bool on, float note, float vel) {
                 if (v.has_note && fabsf((float)v.note - note) > 0.01f) return;
                 const float fi = (float)i / fsr;
                 const float offset = fi;
-                if (on) { G = P; P = {-fi, vel, 0.0f}; }
-                else if (G.rel == 0.0f) { G.t = -fi; G.rel = m_apply_ads(v.adsr, G.t + offset) * G.vel; }
-                else { P.t = -fi; P.rel = m_apply_ads(v.adsr, P.t + offset) * P.vel; }
-                push(i, 0);
+                if (on) { G = P; Gc = Pc; P = {-fi, vel, 0.0f}; Pc = Clk{i, k, -1}; }
+                else if (G.rel == 0.0f) { G.t = -fi; Gc = Clk{i, k, -1}; G.rel = m_apply_ads(v.adsr, G.t + offset) * G.vel; }
+                else { P.t = -fi; Pc = Clk{i, k, -1}; P.rel = m_apply_ads(v.adsr, P.t + offset) * P.vel; }
+                push(c0 + i, 0);
             });
         } else {
-            drum_chunk(cur, pp.F0 + k * pp.bl, pp.bl, [&](uint32_t i, float note, float vel) {
+            drum_chunk(cur, pp.F0 + c0, pp.bl, [&](uint32_t i, float note, float vel) {
                 if (v.has_note && fabsf((float)v.note - note) > 0.01f) {    // `continue` on the frame loop
-                    push(i, 1); push(i + 1, 0);
+                    push(c0 + i, 1); push(c0 + i + 1, 0);
                     return;
                 }
                 const float fi = (float)i / fsr;
-                G = P; P = {-fi, vel, 0.0f};
-                push(i, 0);
+                G = P; Gc = Pc; P = {-fi, vel, 0.0f}; Pc = Clk{i, k, -1};
+                push(c0 + i, 0);
             });
         }
         P.t += d; G.t += d;                                                 // extensions.rs:649-650
-        if (emit) out.ptr.push_back((uint32_t)out.aseg.size());
+    }
+    pack_explicit(S, n_x, out.xenv);
+    const uint64_t n_frames = pp.total * pp.bl;
+    for (size_t q = 0; q < R.size(); ++q) {
+        AdsrRec& r = R[q];
+        r.p_src = patch_src(S, r.p_src); r.g_src = patch_src(S, r.g_src);
+        const uint64_t until = q + 1 < R.size() ? R[q + 1].start : n_frames;     // the record is read for frames [start, until)
+        if (until == 0 || until <= r.start) continue;
+        const uint32_t lastc = (uint32_t)((until - 1) / pp.bl);
+        if (!(r.p_src & kEnvExplicit) && lastc >= r.p_chunk) out.depth = std::max(out.depth, lastc - r.p_chunk + 1);
+        if (!(r.g_src & kEnvExplicit) && lastc >= r.g_chunk) out.depth = std::max(out.depth, lastc - r.g_chunk + 1);
     }
 }
 
@@ -621,8 +774,9 @@ struct PassReq {
     std::vector<int> level;            // per vertex, -1 unreachable
     std::vector<int> last_use;
     std::vector<int64_t> buf_off, aux_off;   // work-arena byte offsets
+    std::vector<int64_t> rng_off;            // per event-driven vertex: uint2[emit_n] written by k_chunk_ranges
     uint64_t n_frames = 0, n_pad = 0;
-    uint64_t pcm_off = 0, pcm_bytes = 0, err_off = 0, rs_off = 0, rs_total = 0;
+    uint64_t pcm_off = 0, pcm_bytes = 0, err_off = 0, rs_off = 0, rs_total = 0, rs_idx_off = 0;
     bool resample = false;
     const float* sincs = nullptr;
     std::vector<ResampleChunk> rs_chunks;
@@ -685,9 +839,10 @@ struct Frag {
     HeapBlob blob; uint64_t base = 0;
     std::vector<LevelTasks> levels;
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
+    std::vector<RangeTask> ranges; uint32_t range_max = 0, resamp_chunks = 0;
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, algo = 0, reused_v = 0, reused_b = 0;
     void reset(size_t n_levels) {        // pooled on the engine: capacities survive from job to job
-        blob.v.clear(); base = 0;
+        blob.v.clear(); base = 0; ranges.clear(); range_max = 0; resamp_chunks = 0;
         if (levels.size() > n_levels) levels.resize(n_levels);
         for (LevelTasks& L : levels) L.clear();
         levels.resize(n_levels);
@@ -695,7 +850,6 @@ struct Frag {
         quant_max = quant_bytes = resamp_max = resamp_bytes = algo = reused_v = reused_b = 0;
     }
 };
-struct PlanScratch { std::vector<MultiHit> mhits; std::vector<LerpHit> lhits; SegOut so; };
 template <typename T> static void append_list(TaskList<T>& d, TaskList<T>& s) {
     d.v.insert(d.v.end(), s.v.begin(), s.v.end());
     d.max_chunks = std::max(d.max_chunks, s.max_chunks); d.bytes += s.bytes;
@@ -722,6 +876,8 @@ struct PassJob {
     std::vector<LevelTasks> levels;
     std::vector<Off> offs;
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
+    std::vector<RangeTask> ranges; uint32_t range_max = 0, resamp_chunks = 0; uint64_t range_off = 0;
+    std::vector<cudaEvent_t> clock_events;   // clock tables this job reads that were extended on another stream
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, quant_off = 0, resamp_off = 0;
     uint64_t algo_bytes_total = 0, reused_v = 0, reused_b = 0;
     double t_start = 0, t_planned = 0, t_h2d_issued = 0, t_d2h0 = 0, t_submitted = 0;
@@ -752,7 +908,7 @@ static int pass_plan(PassJob& J) {
         const int V = (int)x->verts.size();
         r.n_frames = r.emit_n * x->bl;
         r.n_pad = align_up(std::max<uint64_t>(r.n_frames, 1), kBpTile);
-        r.buf_off.assign(V, -1); r.aux_off.assign(V, -1);
+        r.buf_off.assign(V, -1); r.aux_off.assign(V, -1); r.rng_off.assign(V, -1);
         for (int v = 0; v < V; ++v) max_level = std::max(max_level, r.level[v]);
     }
     J.err_bytes = reqs.size() * 4;
@@ -836,6 +992,8 @@ static int pass_plan(PassJob& J) {
                 const HVertex& hv = x->verts[v];
                 if (hv.kind == K_NORMALIZE) r.aux_off[v] = (int64_t)bump.alloc(r.emit_n * 2 * 4 + 16);     // peaks, runmax
                 if (hv.kind == K_BANDPASS) r.aux_off[v] = (int64_t)bump.alloc((r.n_pad / kBpTile) * 12 * 4 + 16); // agg[8], carry[4]
+                if (hv.kind == K_ADSR || hv.kind == K_SAMPLE_MULTI || hv.kind == K_SAMPLE_LERP || hv.kind == K_DEBUG_SINE ||
+                    hv.kind == K_SYNTH || hv.kind == K_SAMPSYN) r.rng_off[v] = (int64_t)bump.alloc(std::max<uint64_t>(r.emit_n, 1) * 8 + 16);
             }
             if (!x->taps)
                 for (int v : by_level[L])
@@ -870,6 +1028,7 @@ static int pass_plan(PassJob& J) {
                 if (r.segment) resample_replay_slice((double)r.render_sr / (double)x->sr, x->bl, r.keep0, keep_n, r.rs_chunks, &first_out, &r.rs_total);
                 else resample_replay((double)r.render_sr / (double)x->sr, x->bl, r.emit_n, r.rs_chunks, &r.rs_total);
                 r.rs_off = bump.alloc(align_up(r.rs_total, 4) * 2 * 4 + 64);
+                r.rs_idx_off = bump.alloc(std::max<uint64_t>(r.rs_total, 1) * 8);
                 r.out_frames = r.rs_total;
                 // the resampler's history in front of a segment (512-frame halo): warm-up chunks of
                 // this segment if there are enough of them, else the previous rank's tail through the exchange
@@ -933,25 +1092,113 @@ static int pass_plan(PassJob& J) {
     const double tr_vstate = now_ms();
     if (!g->pool) {
         g->pool = new WorkerPool();
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        g->pool->start(std::min(hw, 32u) - 1);
+        // planner threads: the host's cores shared fairly between the ranks of this node (one process per GPU):
+        // 8 ranks x 31 threads on a 32-core host was what bounded the 8-GPU step
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned local_world = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = (unsigned)std::max(1, atoi(e));
+        unsigned want = std::max(1u, std::min(hw / local_world, 32u));
+        if (const char* e = getenv("TDG_PLAN_THREADS")) want = (unsigned)std::max(1, atoi(e));
+        g->pool->start(want - 1);
         g->frags = new std::vector<Frag>();
         g->scratch = new std::vector<PlanScratch>(g->pool->workers());
+        g->vplans = new std::vector<std::vector<VPlan>>();
     }
     if (g->frags->size() < reqs.size()) g->frags->resize(reqs.size());
     Frag* frags = g->frags->data();
     const size_t n_frags = reqs.size();
-    auto plan_one = [&](PassReq& r, Frag& F, PlanScratch& PS) -> int {
+    // ---- 2a. event plans: every event-driven vertex of every project is independent -> one work item each
+    // (a batch of small projects and one long 64-vertex project both spread over the planner threads)
+    if (g->vplans->size() < reqs.size()) g->vplans->resize(reqs.size());
+    std::vector<std::vector<VPlan>>& vplans = *g->vplans;
+    struct Item { uint32_t ri, v; };
+    std::vector<Item> items;
+    for (size_t ri = 0; ri < reqs.size(); ++ri) {
+        PassReq& r = reqs[ri];
+        Ctx* x = r.c;
+        const size_t V = x->verts.size();
+        if (vplans[ri].size() < V) vplans[ri].resize(V);
+        for (size_t v = 0; v < V; ++v) {
+            vplans[ri][v].planned = false;
+            if (r.level[v] < 0 || r.skip[v]) continue;
+            const HVertex& hv = x->verts[v];
+            const bool ev = (hv.kind == K_ADSR && !(hv.wet < 0.0001f)) || hv.kind == K_SAMPLE_MULTI || hv.kind == K_SAMPLE_LERP ||
+                            hv.kind == K_DEBUG_SINE || hv.kind == K_SYNTH || hv.kind == K_SAMPSYN;
+            if (ev) items.push_back({(uint32_t)ri, (uint32_t)v});
+        }
+    }
+    g->pool->parallel_for(items.size(), 64, [&](size_t q, unsigned w) {
+        PassReq& r = reqs[items[q].ri];
+        Ctx* x = r.c;
+        const uint32_t v = items[q].v;
+        HVertex& hv = x->verts[v];
+        VPlan& VP = vplans[items[q].ri][v];
+        PlanScratch& PS = (*g->scratch)[w];
+        const PassParams pp{r.is_scan ? 0 : x->fb_frame, r.is_scan ? 0 : x->t, r.total, r.emit0, r.emit_n, x->bl, x->sr};
+        // (true_normalize_scan: fb.set_time(0) and t = j*bl, graph.rs:228-231)
+        VP.depth = 0; VP.voice_frames = 0;
+        const double t_item = trace_on() ? now_ms() : 0.0;
+        switch (hv.kind) {
+            case K_ADSR: plan_adsr(hv, x->flowws[hv.floww], pp, VP, PS); break;
+            case K_SAMPLE_MULTI: plan_multi(hv, x->flowws[hv.floww], x->samples[hv.sample].frames, pp, VP.mhits); break;
+            case K_SAMPLE_LERP: plan_lerp(hv, x->flowws[hv.floww], pp, VP.lhits); break;
+            default: plan_voices(hv, x->flowws[hv.floww], pp, VP, PS); break;
+        }
+        VP.planned = true;
+        if (trace_on() && now_ms() - t_item > 5.0) fprintf(stderr, "[tdg] slow event plan: vertex %u kind %d %.2f ms (worker %u)\n", v, hv.kind, now_ms() - t_item, w);
+    });
+    // ---- 2b. clock tables: one per (sr, bl), deep enough for the longest-lived clock of this job
+    J.clock_events.clear();
+    {
+        std::map<uint64_t, uint32_t> need;
+        for (const Item& it : items) {
+            const Ctx* x = reqs[it.ri].c;
+            uint32_t& d = need[((uint64_t)x->sr << 32) | x->bl];
+            d = std::max(d, std::max(vplans[it.ri][it.v].depth, 1u));
+        }
+        for (auto& kv : need) {
+            ClockTab& tb = g->clocks[kv.first];
+            const uint32_t sr = (uint32_t)(kv.first >> 32), bl = (uint32_t)kv.first;
+            if (kv.second > tb.cap) {
+                // growing past the allocation: earlier passes may still read the old table -> wait for the device
+                // (once per engine and batch shape: the allocation carries 50 % headroom and at least 2048 rows)
+                CU(cudaDeviceSynchronize());
+                if (tb.p) cudaFree(tb.p);
+                tb.p = nullptr; tb.depth = 0;
+                tb.cap = std::max<uint32_t>(kv.second + kv.second / 2, 2048u);
+                CU(cudaMalloc(&tb.p, (size_t)tb.cap * bl * 4));
+                if (trace_on()) fprintf(stderr, "[tdg] clock table sr %u bl %u: %u rows (%.1f MB)\n", sr, bl, tb.cap, (double)tb.cap * bl * 4 / 1e6);
+            }
+            if (kv.second > tb.depth) {
+                if (!tb.ev) CU(cudaEventCreateWithFlags(&tb.ev, cudaEventDisableTiming));
+                const uint32_t upto = std::min(tb.cap, std::max(kv.second, tb.depth + 256u));          // rows are appended, never rewritten
+                CU(launch_env_table(tb.p, bl, tb.depth, upto, (float)sr, ln.stream));
+                CU(cudaEventRecord(tb.ev, ln.stream));
+                tb.ev_set = true; tb.depth = upto;
+            }
+            if (tb.ev_set) J.clock_events.push_back(tb.ev);
+        }
+    }
+    const double tr_events = now_ms();
+    auto plan_one = [&](PassReq& r, Frag& F, std::vector<VPlan>& VPs) -> int {
         Ctx* x = r.c;
         F.reset((size_t)max_level + 1);
         HeapBlob& B = F.blob;
         std::vector<LevelTasks>& levels = F.levels;
         std::vector<QuantTask>& quants = F.quants; uint64_t& quant_max = F.quant_max; uint64_t& quant_bytes = F.quant_bytes;
         std::vector<ResampleTask>& resamps = F.resamps; uint64_t& resamp_max = F.resamp_max; uint64_t& resamp_bytes = F.resamp_bytes;
-        std::vector<MultiHit>& mhits = PS.mhits; std::vector<LerpHit>& lhits = PS.lhits; SegOut& so = PS.so;
         const int V = (int)x->verts.size();
-        PassParams pp{r.is_scan ? 0 : x->fb_frame, r.is_scan ? 0 : x->t, r.total, r.emit0, r.emit_n, x->bl, x->sr};
-        // (true_normalize_scan: fb.set_time(0) and t = j*bl, graph.rs:228-231)
+        const uint64_t pass_t0 = r.is_scan ? 0 : x->t;       // graph time of pass chunk 0 (true_normalize_scan: t = j*bl, graph.rs:228-231)
+        const float* clock = nullptr;
+        { auto it = g->clocks.find(((uint64_t)x->sr << 32) | x->bl); if (it != g->clocks.end()) clock = it->second.p; }
+        auto range_task = [&](uint32_t kind, int v, uint64_t recs_off, size_t n_recs, int64_t len) -> const Range2* {
+            RangeTask t; memset(&t, 0, sizeof t);
+            t.kind = kind; t.n_chunks = (uint32_t)r.emit_n; t.chunk0 = (uint32_t)r.emit0; t.bl = x->bl;
+            t.recs_off = recs_off; t.n_recs = (uint32_t)n_recs; t.len = len;
+            t.out = reinterpret_cast<Range2*>(W + r.rng_off[v]);
+            F.ranges.push_back(t); F.range_max = std::max(F.range_max, t.n_chunks);
+            return t.out;
+        };
         uint64_t algo = 0;
         const float* fused_runmax = nullptr; PanGain fused_pg{1.0f, 1.0f, 1.0f, 0};
         for (int v = 0; v < V; ++v) {
@@ -1021,16 +1268,18 @@ static int pass_plan(PassJob& J) {
                     if (hv.wet < 0.0001f) {                                              // extensions.rs:598
                         LT.fx.v.push_back(fx_task(FX_SUM)); LT.fx.max_chunks = std::max(LT.fx.max_chunks, nch); LT.fx.bytes += io_bytes;
                     } else {
-                        plan_adsr(hv, x->flowws[hv.floww], pp, so);
+                        VPlan& VP = VPs[v];
                         FxTask t = fx_task(FX_ADSR);
                         t.conf = make_adsr_k(hv.adsr); t.wet = hv.wet; t.use_off = hv.use_off; t.use_max = hv.use_max;
                         if (t.conf.exotic || adsr_duration_exotic(t.fsr)) LT.fx_adsr_exact = true;
-                        t.seg_ptr_off = B.alloc(so.ptr.size() * 4);
-                        memcpy(B.at<uint8_t>(t.seg_ptr_off), so.ptr.data(), so.ptr.size() * 4);
-                        t.seg_off = B.alloc(std::max<size_t>(so.aseg.size(), 1) * sizeof(AdsrSeg));
-                        memcpy(B.at<uint8_t>(t.seg_off), so.aseg.data(), so.aseg.size() * sizeof(AdsrSeg));
+                        t.recs_off = B.alloc(VP.arecs.size() * sizeof(AdsrRec));
+                        memcpy(B.at<uint8_t>(t.recs_off), VP.arecs.data(), VP.arecs.size() * sizeof(AdsrRec));
+                        t.xenv_off = B.alloc(std::max<size_t>(VP.xenv.size(), 1) * 4);
+                        memcpy(B.at<uint8_t>(t.xenv_off), VP.xenv.data(), VP.xenv.size() * 4);
+                        t.n_recs = (uint32_t)VP.arecs.size(); t.chunk0 = (uint32_t)r.emit0; t.clock = clock;
+                        t.ranges = range_task(RK_ADSR, v, t.recs_off, VP.arecs.size(), 0);
                         LT.fx_adsr.v.push_back(t); LT.fx_adsr.max_chunks = std::max(LT.fx_adsr.max_chunks, nch);
-                        LT.fx_adsr.bytes += io_bytes + so.aseg.size() * sizeof(AdsrSeg);
+                        LT.fx_adsr.bytes += io_bytes + VPs[v].arecs.size() * sizeof(AdsrRec);
                     }
                     algo += io_bytes;
                     break;
@@ -1072,7 +1321,7 @@ static int pass_plan(PassJob& J) {
                 }
                 case K_SAMPLE_MULTI: {
                     const DevSample& s = x->samples[hv.sample];
-                    plan_multi(hv, x->flowws[hv.floww], s.frames, pp, mhits);
+                    std::vector<MultiHit>& mhits = VPs[v].mhits;
                     if (r.is_scan && r.keep_write && x->keep.off[v] >= 0) {
                         // the render differs from this scan only while hits carried INTO either pass still play:
                         // carried entries come first in `mhits` (start < 0), the ones carried out are in hv.ts now
@@ -1087,18 +1336,8 @@ static int pass_plan(PassJob& J) {
                     t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.n_hits = (uint32_t)mhits.size();
                     t.hits_off = B.alloc(std::max<size_t>(mhits.size(), 1) * sizeof(MultiHit));
                     memcpy(B.at<uint8_t>(t.hits_off), mhits.data(), mhits.size() * sizeof(MultiHit));
-                    {   // per chunk: hits with start in (p0 - L, p0 + bl - 1]; both bounds only move forward
-                        t.range_off = B.alloc(std::max<uint64_t>(r.emit_n, 1) * 8);
-                        uint32_t* rg = B.at<uint32_t>(t.range_off);
-                        size_t lo = 0, hi = 0;
-                        for (uint64_t k = 0; k < r.emit_n; ++k) {
-                            const int64_t c0 = (int64_t)(k * x->bl);
-                            while (lo < mhits.size() && mhits[lo].start <= c0 - (int64_t)s.frames) ++lo;
-                            if (hi < lo) hi = lo;
-                            while (hi < mhits.size() && mhits[hi].start <= c0 + (int64_t)x->bl - 1) ++hi;
-                            rg[2 * k] = (uint32_t)lo; rg[2 * k + 1] = (uint32_t)hi;
-                        }
-                    }
+                    // per chunk: hits with start in (p0 - L, p0 + bl - 1], found on the device
+                    t.ranges = range_task(RK_MULTI, v, t.hits_off, mhits.size(), (int64_t)s.frames);
                     LT.multi.v.push_back(t); LT.multi.max_chunks = std::max(LT.multi.max_chunks, nch);
                     uint64_t gathered = 0;                                        // live hit-frames inside the emitted range
                     for (const MultiHit& mh : mhits) {
@@ -1110,7 +1349,7 @@ static int pass_plan(PassJob& J) {
                 }
                 case K_SAMPLE_LERP: {
                     const DevSample& s = x->samples[hv.sample];
-                    plan_lerp(hv, x->flowws[hv.floww], pp, lhits);
+                    std::vector<LerpHit>& lhits = VPs[v].lhits;
                     if (r.is_scan && r.keep_write && x->keep.off[v] >= 0)
                         // both passes play the same hits; only the pair carried in differs, and it is audible until the
                         // first hit of the pass has faded in (entries 0 and 1 are the carried pair)
@@ -1121,37 +1360,28 @@ static int pass_plan(PassJob& J) {
                     t.h = h; t.sl = s.l; t.sr = s.r; t.len = s.frames; t.n_hits = (uint32_t)lhits.size(); t.lerp_len = hv.lerp_len;
                     t.hits_off = B.alloc(lhits.size() * sizeof(LerpHit));
                     memcpy(B.at<uint8_t>(t.hits_off), lhits.data(), lhits.size() * sizeof(LerpHit));
-                    {   // per chunk: last hit with frame <= first frame of the chunk (entries 0 and 1 are the carried pair)
-                        t.base_off = B.alloc(std::max<uint64_t>(r.emit_n, 1) * 4);
-                        uint32_t* bs = B.at<uint32_t>(t.base_off);
-                        size_t a = 0;
-                        for (uint64_t k = 0; k < r.emit_n; ++k) {
-                            const int64_t c0 = (int64_t)(k * x->bl);
-                            while (a < lhits.size() && lhits[a].frame <= c0) ++a;
-                            bs[k] = (uint32_t)(a - 1);
-                        }
-                    }
+                    // per chunk: last hit with frame <= first frame of the chunk, found on the device
+                    t.ranges = range_task(RK_LERP, v, t.hits_off, lhits.size(), 0);
                     LT.lerp.v.push_back(t); LT.lerp.max_chunks = std::max(LT.lerp.max_chunks, nch);
                     algo += 16ull * frames_v; LT.lerp.bytes += 16ull * frames_v;
                     break;
                 }
                 case K_DEBUG_SINE: case K_SYNTH: case K_SAMPSYN: {
-                    plan_voices(hv, x->flowws[hv.floww], pp, so);
+                    VPlan& VP = VPs[v];
                     VoiceTask t; memset(&t, 0, sizeof t);
-                    t.h = h; t.sr = x->sr; t.t0 = pp.t0 + r.emit0 * x->bl;
+                    t.h = h; t.sr = x->sr; t.t0 = pass_t0 + r.emit0 * x->bl;
                     t.fsr = (float)x->sr; t.rsr = 1.0f / t.fsr;
                     bool exotic = adsr_duration_exotic(t.fsr);
-                    t.seg_ptr_off = B.alloc(so.ptr.size() * 4);
-                    memcpy(B.at<uint8_t>(t.seg_ptr_off), so.ptr.data(), so.ptr.size() * 4);
-                    t.seg_off = B.alloc(std::max<size_t>(so.vseg.size(), 1) * sizeof(VoiceSeg));
-                    memcpy(B.at<uint8_t>(t.seg_off), so.vseg.data(), so.vseg.size() * sizeof(VoiceSeg));
-                    if (hv.kind == K_SYNTH) {
-                        t.relv2_off = B.alloc(std::max<size_t>(so.relv2.size(), 1) * sizeof(float));
-                        memcpy(B.at<uint8_t>(t.relv2_off), so.relv2.data(), so.relv2.size() * sizeof(float));
-                    }
-                    x->stats.voice_frames += so.voice_frames;
-                    const uint64_t vbytes = 8ull * r.n_frames + so.vseg.size() * sizeof(VoiceSeg);
-                    if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; if (exotic) LT.dsine_exact = true; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nch); LT.dsine.bytes += vbytes; }
+                    t.recs_off = B.alloc(std::max<size_t>(VP.vrecs.size(), 1) * sizeof(VoiceRec));
+                    memcpy(B.at<uint8_t>(t.recs_off), VP.vrecs.data(), VP.vrecs.size() * sizeof(VoiceRec));
+                    t.xenv_off = B.alloc(std::max<size_t>(VP.xenv.size(), 1) * 4);
+                    memcpy(B.at<uint8_t>(t.xenv_off), VP.xenv.data(), VP.xenv.size() * 4);
+                    t.n_recs = (uint32_t)VP.vrecs.size(); t.chunk0 = (uint32_t)r.emit0; t.clock = clock;
+                    t.ranges = range_task(RK_VOICE, v, t.recs_off, VP.vrecs.size(), 0);
+                    x->stats.voice_frames += VP.voice_frames;
+                    const uint64_t vbytes = 8ull * r.n_frames + VP.vrecs.size() * sizeof(VoiceRec);
+                    const uint32_t nblk = nch * voice_tiles(x->bl);            // a block = one 1024-frame tile of one chunk
+                    if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; if (exotic) LT.dsine_exact = true; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nblk); LT.dsine.bytes += vbytes; }
                     else if (hv.kind == K_SYNTH) {
                         t.kind = VOICE_SYNTH;
                         t.vol[0] = hv.sq.volume; t.sq_z = hv.sq.param; t.vol[1] = hv.tf.volume; t.tf_z = hv.tf.param;
@@ -1164,14 +1394,14 @@ static int pass_plan(PassJob& J) {
                             (t.vol[2] > 0.0f && t.env[2].exotic)) LT.synth_exact = true;
                         t.amp_mul = 1.0f / (hv.sq.volume * m_max_vel(hv.sq.adsr) + hv.tf.volume * m_max_vel(hv.tf.adsr) +
                                             hv.tr.volume * m_max_vel(hv.tr.adsr));           // extensions.rs:465-468
-                        LT.synth.v.push_back(t); LT.synth.max_chunks = std::max(LT.synth.max_chunks, nch); LT.synth.bytes += vbytes;
+                        LT.synth.v.push_back(t); LT.synth.max_chunks = std::max(LT.synth.max_chunks, nblk); LT.synth.bytes += vbytes;
                     } else {
                         const DevTable& tb = x->tables[hv.table];
                         t.kind = VOICE_SAMPSYN; t.env[0] = make_adsr_k(hv.adsr); t.amp_mul = 1.0f / m_max_vel(hv.adsr);   // extensions.rs:537
                         if (exotic || t.env[0].exotic) LT.sampsyn_exact = true;
                         t.table = tb.data; t.n_frames = tb.n_frames; t.n_phase = tb.n_phase; t.fps = tb.fps;
                         t.table_floats = tb.n_frames * tb.n_phase;
-                        LT.sampsyn.v.push_back(t); LT.sampsyn.max_chunks = std::max(LT.sampsyn.max_chunks, nch); LT.sampsyn.bytes += vbytes;
+                        LT.sampsyn.v.push_back(t); LT.sampsyn.max_chunks = std::max(LT.sampsyn.max_chunks, nblk); LT.sampsyn.bytes += vbytes;
                     }
                     algo += 8ull * r.n_frames;
                     break;
@@ -1190,7 +1420,7 @@ static int pass_plan(PassJob& J) {
                 ResampleTask rt; memset(&rt, 0, sizeof rt);
                 rt.in_l = ol; rt.in_r = orr;
                 rt.out_l = reinterpret_cast<float*>(W + r.rs_off); rt.out_r = rt.out_l + align_up(r.rs_total, 4);
-                rt.sincs = r.sincs;
+                rt.sincs = r.sincs; rt.idx = reinterpret_cast<double*>(W + r.rs_idx_off);
                 const uint64_t before = (r.keep0 - r.emit0) * x->bl;
                 rt.in_l += before; rt.in_r += before; rt.n_before = before;
                 rt.n_in = r.n_frames - before; rt.n_chunks = (uint32_t)r.rs_chunks.size(); rt.chunk = x->bl;
@@ -1201,7 +1431,7 @@ static int pass_plan(PassJob& J) {
                 rt.t_ratio = 1.0 / ((double)r.render_sr / (double)x->sr);
                 rt.chunk_off = B.alloc(std::max<size_t>(r.rs_chunks.size(), 1) * sizeof(ResampleChunk));
                 memcpy(B.at<uint8_t>(rt.chunk_off), r.rs_chunks.data(), r.rs_chunks.size() * sizeof(ResampleChunk));
-                resamps.push_back(rt); resamp_max = std::max(resamp_max, r.rs_total);
+                resamps.push_back(rt); resamp_max = std::max(resamp_max, r.rs_total); F.resamp_chunks = std::max<uint32_t>(F.resamp_chunks, rt.n_chunks);
                 q.in_l = rt.out_l; q.in_r = rt.out_r; q.n = r.rs_total;
                 algo += 8ull * r.n_frames + 8ull * r.rs_total; resamp_bytes += 8ull * r.n_frames + 8ull * r.rs_total;
             } else {
@@ -1221,7 +1451,8 @@ static int pass_plan(PassJob& J) {
     {
         std::atomic<int> first_err{TDG_OK};
         g->pool->parallel_for(reqs.size(), 32, [&](size_t i, unsigned w) {
-            const int e = plan_one(reqs[i], frags[i], (*g->scratch)[w]);
+            (void)w;
+            const int e = plan_one(reqs[i], frags[i], vplans[i]);
             if (e != TDG_OK) { int z = TDG_OK; first_err.compare_exchange_strong(z, e); }
         });
         if (first_err.load() != TDG_OK) return first_err.load();
@@ -1237,7 +1468,7 @@ static int pass_plan(PassJob& J) {
     std::vector<ResampleTask>& resamps = J.resamps; uint64_t &resamp_max = J.resamp_max, &resamp_bytes = J.resamp_bytes;
     uint64_t& algo_bytes_total = J.algo_bytes_total;
     quants.clear(); resamps.clear(); quant_max = quant_bytes = resamp_max = resamp_bytes = algo_bytes_total = 0;
-    J.reused_v = J.reused_b = 0;
+    J.reused_v = J.reused_b = 0; J.ranges.clear(); J.range_max = 0; J.resamp_chunks = 0;
     {
         uint64_t tot = 0;
         for (size_t i = 0; i < n_frags; ++i) { Frag& F = frags[i]; F.base = align_up(tot, 256); tot = F.base + F.blob.v.size(); }
@@ -1253,13 +1484,13 @@ static int pass_plan(PassJob& J) {
             for (size_t L = 0; L < F.levels.size(); ++L) {
                 LevelTasks& S = F.levels[L]; LevelTasks& Dst = levels[L];
                 for (FxTask& t : S.fx.v) t.in_off += b;
-                for (FxTask& t : S.fx_adsr.v) { t.in_off += b; t.seg_ptr_off += b; t.seg_off += b; }
+                for (FxTask& t : S.fx_adsr.v) { t.in_off += b; t.recs_off += b; t.xenv_off += b; }
                 for (FxTask& t : S.fx_norm.v) t.in_off += b;
-                for (MultiTask& t : S.multi.v) { t.hits_off += b; t.range_off += b; }
-                for (LerpTask& t : S.lerp.v) { t.hits_off += b; t.base_off += b; }
-                for (VoiceTask& t : S.dsine.v) { t.seg_ptr_off += b; t.seg_off += b; }
-                for (VoiceTask& t : S.synth.v) { t.seg_ptr_off += b; t.seg_off += b; t.relv2_off += b; }
-                for (VoiceTask& t : S.sampsyn.v) { t.seg_ptr_off += b; t.seg_off += b; }
+                for (MultiTask& t : S.multi.v) t.hits_off += b;
+                for (LerpTask& t : S.lerp.v) t.hits_off += b;
+                for (VoiceTask& t : S.dsine.v) { t.recs_off += b; t.xenv_off += b; }
+                for (VoiceTask& t : S.synth.v) { t.recs_off += b; t.xenv_off += b; }
+                for (VoiceTask& t : S.sampsyn.v) { t.recs_off += b; t.xenv_off += b; }
                 for (BpTask& t : S.bp.v) t.in_off += b;
                 append_list(Dst.fx, S.fx); append_list(Dst.fx_adsr, S.fx_adsr); append_list(Dst.fx_norm, S.fx_norm);
                 append_list(Dst.nprefix, S.nprefix); append_list(Dst.nscale, S.nscale);
@@ -1270,6 +1501,8 @@ static int pass_plan(PassJob& J) {
                 Dst.synth_exact |= S.synth_exact; Dst.sampsyn_exact |= S.sampsyn_exact;
                 Dst.bp_agg_bytes += S.bp_agg_bytes;
             }
+            for (RangeTask& t : F.ranges) { t.recs_off += b; J.ranges.push_back(t); }
+            J.range_max = std::max(J.range_max, F.range_max); J.resamp_chunks = std::max(J.resamp_chunks, F.resamp_chunks);
             for (ResampleTask& t : F.resamps) { t.chunk_off += b; resamps.push_back(t); }
             for (QuantTask& t : F.quants) quants.push_back(t);
             quant_max = std::max(quant_max, F.quant_max); quant_bytes += F.quant_bytes;
@@ -1302,16 +1535,17 @@ static int pass_plan(PassJob& J) {
     }
     J.quant_off = put(quants.data(), quants.size() * sizeof(QuantTask));
     J.resamp_off = put(resamps.data(), resamps.size() * sizeof(ResampleTask));
-    if (J.quant_off == UINT64_MAX || J.resamp_off == UINT64_MAX) return c->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
+    J.range_off = put(J.ranges.data(), J.ranges.size() * sizeof(RangeTask));
+    if (J.quant_off == UINT64_MAX || J.resamp_off == UINT64_MAX || J.range_off == UINT64_MAX) return c->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
     const double tr_merged = now_ms();
     g->hwm_blob = std::max<uint64_t>(g->hwm_blob, B.size + 256);
     CU(sl.blob_dev.ensure(B.size + 256, g->hwm_blob));
     if (!sl.ensure_err(reqs.size())) return c->fail(TDG_ERR_CUDA, "pinned flag buffer allocation failed");
     J.t_planned = now_ms();
     if (trace_on())
-        fprintf(stderr, "[tdg] plan lane %d reqs %zu: layout %.2f arena %.2f vstate %.2f plan %.2f merge %.2f blobdev %.2f ms (blob %.1f MB)\n",
+        fprintf(stderr, "[tdg] plan lane %d reqs %zu: layout %.2f arena %.2f vstate %.2f events %.2f (%zu vertices) tasks %.2f merge %.2f blobdev %.2f ms (blob %.1f MB)\n",
                 (int)(J.lane - g->lanes), reqs.size(), tr_layout - J.t_start, tr_arena - tr_layout, tr_vstate - tr_arena,
-                tr_planned - tr_vstate, tr_merged - tr_planned, J.t_planned - tr_merged, B.size / 1e6);
+                tr_events - tr_vstate, items.size(), tr_planned - tr_events, tr_merged - tr_planned, J.t_planned - tr_merged, B.size / 1e6);
     return TDG_OK;
 }
 
@@ -1341,10 +1575,20 @@ static int pass_submit(PassJob& J) {
     CU(cudaStreamWaitEvent(s, sl.ev_h2d, 0));
     J.h2d_bytes = B.size;
     if (J.err_bytes) CU(cudaMemsetAsync(J.P + J.err_base, 0, J.err_bytes, s));      // TooWide flags of every request, contiguous
+    for (cudaEvent_t e : J.clock_events) CU(cudaStreamWaitEvent(s, e, 0));          // clock rows appended on another lane's stream
     J.t_h2d_issued = now_ms();
     CU(cudaEventRecord(sl.ev0, s));
     uint64_t &launches = J.launches, &collectives = J.collectives;
     launches = collectives = 0;
+    // per-chunk index ranges of every event-driven vertex of the pass: one launch, before the first level
+    if (!J.ranges.empty()) {
+        const size_t kMaxTasks = 65535;
+        for (size_t b0 = 0; b0 < J.ranges.size(); b0 += kMaxTasks) {
+            const uint32_t nb = (uint32_t)std::min(kMaxTasks, J.ranges.size() - b0);
+            CU(launch_chunk_ranges(reinterpret_cast<const RangeTask*>(D + J.range_off) + b0, nb, J.range_max, D, s));
+            ++launches;
+        }
+    }
     const int x_mode = reqs[0].x_mode;
     for (auto& r : reqs) if (r.x_mode != x_mode || (x_mode == 2 && reqs.size() != 1))
         return r.c->fail(TDG_ERR_INVALID, "time-sharded and plain passes cannot share a launch sequence");
@@ -1376,7 +1620,35 @@ static int pass_submit(PassJob& J) {
         LAUNCH_SPLIT(KC_FX_SUM, T.fx, FxTask, offs[L].fx, T.fx.bytes, launch_fx(FX_SUM, tp, nb, T.fx.max_chunks, vec, false, D, s));
         LAUNCH_SPLIT(KC_FX_ADSR, T.fx_adsr, FxTask, offs[L].fx_adsr, T.fx_adsr.bytes, launch_fx(FX_ADSR, tp, nb, T.fx_adsr.max_chunks, vec, T.fx_adsr_exact, D, s));
         LAUNCH_SPLIT(KC_FX_NORM, T.fx_norm, FxTask, offs[L].fx_norm, T.fx_norm.bytes, launch_fx(FX_NORM_PEAK, tp, nb, T.fx_norm.max_chunks, vec, false, D, s));
+        // band pass = aggregate, carry, apply over the same inputs.  Without an exchange step in between the three
+        // launches run over groups of filters whose inputs + outputs fit the L2 (bp_l2_bytes): the apply pass then
+        // finds the inputs the aggregate pass just streamed in cache instead of fetching them from HBM again
+        const bool bp_grouped = !x_mode && g->bp_l2_bytes > 0 && T.bp.v.size() > 1;
+        if (bp_grouped) {
+            const size_t n = T.bp.v.size();
+            auto io_of = [&](size_t q) { return 8ull * (T.bp.v[q].n_in + 1) * T.bp.v[q].h.n_frames; };
+            for (size_t b0 = 0; b0 < n;) {
+                size_t b1 = b0; uint64_t acc = 0, in_b = 0;
+                do { acc += io_of(b1); in_b += 8ull * T.bp.v[b1].n_in * T.bp.v[b1].h.n_frames; ++b1; }
+                while (b1 < n && b1 - b0 < kMaxY && acc + io_of(b1) <= g->bp_l2_bytes);
+                const uint32_t nb = (uint32_t)(b1 - b0);
+                const BpTask* tp = reinterpret_cast<const BpTask*>(D + offs[L].bp) + b0;
+                auto timed_launch = [&](int cls, uint64_t bytes, cudaError_t (*fn)(const BpTask*, uint32_t, uint32_t, bool, const uint8_t*, cudaStream_t)) -> cudaError_t {
+                    if (g->profiling) cudaEventRecord(ev_at(2 * timed.size()), s);
+                    const cudaError_t e = fn(tp, nb, T.bp.max_chunks, vec, D, s); ++launches;
+                    if (g->profiling) { cudaEventRecord(ev_at(2 * timed.size() + 1), s); timed.push_back({cls, bytes}); }
+                    return e;
+                };
+                CU(timed_launch(KC_BP_AGG, in_b, launch_bp_aggregate));
+                if (g->profiling) CU(cudaEventRecord(ev_at(2 * timed.size()), s));
+                CU(launch_bp_carry(tp, nb, D, s)); ++launches;
+                if (g->profiling) { CU(cudaEventRecord(ev_at(2 * timed.size() + 1), s)); timed.push_back({KC_BP_CARRY, 0}); }
+                CU(timed_launch(KC_BP_APPLY, acc, launch_bp_apply));
+                b0 = b1;
+            }
+        } else {
         LAUNCH_SPLIT(KC_BP_AGG, T.bp, BpTask, offs[L].bp, T.bp_agg_bytes, launch_bp_aggregate(tp, nb, T.bp.max_chunks, vec, D, s));
+        }
         if (x_mode && (!T.nprefix.v.empty() || !T.bp.v.empty())) {
             // time sharding: publish this segment's peaks / filter maps, then fetch the other ranks'
             const PassReq& r0 = reqs[0];
@@ -1393,8 +1665,10 @@ static int pass_submit(PassJob& J) {
         }
         LAUNCH_SPLIT(KC_NORM_PREFIX, T.nprefix, NormPrefixTask, offs[L].nprefix, T.nprefix.bytes, launch_norm_prefix(tp, nb, s));
         LAUNCH_SPLIT(KC_NORM_SCALE, T.nscale, NormScaleTask, offs[L].nscale, T.nscale.bytes, launch_norm_scale(tp, nb, T.nscale.max_chunks, vec, s));
+        if (!bp_grouped) {
         LAUNCH_SPLIT(KC_BP_CARRY, T.bp, BpTask, offs[L].bp, (uint64_t)0, launch_bp_carry(tp, nb, D, s));
         LAUNCH_SPLIT(KC_BP_APPLY, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_apply(tp, nb, T.bp.max_chunks, vec, D, s));
+        }
     }
     if (x_mode) {
         // time-sharded resampling: every segment publishes the last 512 frames of the output vertex; the next
@@ -1417,7 +1691,7 @@ static int pass_submit(PassJob& J) {
         }
     }
     { TaskList<ResampleTask> rl; rl.v.swap(resamps);
-      LAUNCH_SPLIT(KC_RESAMPLE, rl, ResampleTask, resamp_off, resamp_bytes, launch_resample(tp, nb, resamp_max, D, s)); }
+      LAUNCH_SPLIT(KC_RESAMPLE, rl, ResampleTask, resamp_off, resamp_bytes, launch_resample(tp, nb, resamp_max, J.resamp_chunks, D, s)); }
     { TaskList<QuantTask> ql; ql.v.swap(quants);
       LAUNCH_SPLIT(KC_QUANT, ql, QuantTask, quant_off, quant_bytes, launch_quantise(tp, nb, quant_max, s)); }
     CU(cudaEventRecord(sl.ev1, s));
@@ -1766,6 +2040,11 @@ int tdg_sample_add(tdg_ctx* h, const float* linear, uint64_t n_values, uint32_t 
     if (frames == 0) return c->fail(TDG_ERR_SAMPLE, "empty sample");
     cudaStream_t s = g->stream;
     float* lin_d = nullptr; float* buf = nullptr; int* mx = nullptr;
+    float* ob = nullptr; uint8_t* mini = nullptr; double* idxb = nullptr;
+    struct Scratch {                      // every early return (CU) frees what has been allocated so far
+        cudaStream_t s; void** p[6]; int n = 0;
+        ~Scratch() { cudaStreamSynchronize(s); for (int i = 0; i < n; ++i) if (*p[i]) { cudaFree(*p[i]); *p[i] = nullptr; } }
+    } scratch{s, {(void**)&lin_d, (void**)&buf, (void**)&mx, (void**)&ob, (void**)&mini, (void**)&idxb}, 6};
     const uint64_t fpad = align_up(frames, 4);
     CU(cudaMalloc(&lin_d, std::max<uint64_t>(n_values, 1) * 4));
     CU(cudaMalloc(&buf, fpad * 2 * 4));
@@ -1791,33 +2070,53 @@ int tdg_sample_add(tdg_ctx* h, const float* linear, uint64_t n_values, uint32_t 
         const double ratio = (double)c->sr / (double)src_sr;
         std::vector<ResampleChunk> ch; uint64_t total = 0;
         resample_replay(ratio, frames, 1, ch, &total);
-        if (total == 0) { cudaFree(lin_d); cudaFree(buf); cudaFree(mx); return c->fail(TDG_ERR_SAMPLE, "sample too short to resample"); }
+        if (total == 0) return c->fail(TDG_ERR_SAMPLE, "sample too short to resample");
         const uint64_t opad = align_up(total, 4);
-        float* ob = nullptr; uint8_t* mini = nullptr;
         CU(cudaMalloc(&ob, opad * 2 * 4));
+        CU(cudaMalloc(&idxb, total * 8));
         CU(cudaMemsetAsync(ob, 0, opad * 2 * 4, s));
         CU(cudaMalloc(&mini, 256));
         ResampleTask rt; memset(&rt, 0, sizeof rt);
         rt.in_l = dl; rt.in_r = dr; rt.out_l = ob; rt.out_r = ob + opad;
         rt.sincs = sinc_table_dev(c, ratio);
         if (!rt.sincs) return c->fail(TDG_ERR_CUDA, "could not build the sinc table");
-        rt.n_in = frames; rt.chunk_off = 128; rt.n_chunks = 1; rt.chunk = (uint32_t)frames; rt.t_ratio = 1.0 / ratio;
+        rt.n_in = frames; rt.chunk_off = 128; rt.n_chunks = 1; rt.chunk = (uint32_t)frames; rt.t_ratio = 1.0 / ratio; rt.idx = idxb;
         uint8_t host[256]; memset(host, 0, sizeof host);
         memcpy(host, &rt, sizeof rt); memcpy(host + 128, &ch[0], sizeof(ResampleChunk));
         static_assert(sizeof(ResampleTask) <= 128, "mini blob layout");
         CU(cudaMemcpyAsync(mini, host, 256, cudaMemcpyHostToDevice, s));
-        CU(launch_resample(reinterpret_cast<const ResampleTask*>(mini), 1, total, mini, s));
-        c->launches += 1;
+        CU(launch_resample(reinterpret_cast<const ResampleTask*>(mini), 1, total, 1, mini, s));
+        c->launches += 2;
         CU(cudaStreamSynchronize(s));
-        cudaFree(mini); cudaFree(buf);
         out.l = ob; out.r = ob + opad; out.frames = total;
+        ob = nullptr;                                                      // kept: the sample bank owns it now
     } else {
         CU(cudaStreamSynchronize(s));
         out.l = dl; out.r = dr; out.frames = frames;
+        buf = nullptr;
     }
-    cudaFree(lin_d); cudaFree(mx);
     c->samples.push_back(out);
     return (int)c->samples.size() - 1;
+}
+// SampleBank::mark_dead + refresh (sample.rs:316-336): a sample that left the script (or changed) is dropped from the
+// bank.  Indices of the other samples stay valid (the reference re-indexes; here the slot is simply emptied), the
+// device memory is returned.  Vertices are rebuilt by the refresh that follows; a vertex still naming the slot
+// makes the next pass fail instead of reading freed memory.
+int tdg_sample_remove(tdg_ctx* h, int sample) {
+    Ctx* c = C_;
+    if (sample < 0 || (size_t)sample >= c->samples.size()) return c->fail(TDG_ERR_INVALID, "unknown sample");
+    DevSample& s = c->samples[(size_t)sample];
+    if (s.l) { cudaSetDevice(c->eng->device); cudaFree(s.l); }
+    s = DevSample();
+    ++c->mut_gen; c->keep.valid = false;
+    return TDG_OK;
+}
+// BufferBank's dead-resource sweep (state.rs:222-237): the blob of a removed / changed resource is released
+int tdg_resource_remove(tdg_ctx* h, int resource) {
+    Ctx* c = C_;
+    if (resource < 0 || (size_t)resource >= c->resources.size()) return c->fail(TDG_ERR_INVALID, "unknown resource");
+    std::vector<uint8_t>().swap(c->resources[(size_t)resource]);
+    return TDG_OK;
 }
 int64_t tdg_sample_frames(tdg_ctx* h, int sample) {
     if (sample < 0 || (size_t)sample >= h->c.samples.size()) return TDG_ERR_INVALID;
@@ -1875,6 +2174,13 @@ int tdg_floww_reset(tdg_ctx* h) { h->c.flowws.clear(); h->c.fb_frame = 0; ++h->c
 
 int tdg_graph_reset(tdg_ctx* h) {                                           // graph.rs:39-47
     Ctx* c = C_;
+    // the graph is rebuilt from scratch on every refresh (state.rs:328): the wavetables its SampSyn vertices
+    // uploaded go with it (no pass of this context is in flight: every entry point returns after its pass_wait)
+    if (!c->tables.empty()) {
+        cudaSetDevice(c->eng->device);
+        for (auto& t : c->tables) if (t.data) cudaFree(t.data);
+        c->tables.clear();
+    }
     c->verts.clear(); c->output = -1; c->t = 0;
     ++c->mut_gen; c->keep = KeepRecord();
     c->vstate_host.clear(); c->vstate_host_newer = true;
@@ -1924,7 +2230,7 @@ static bool parse_adsr(const float* a, int n, AdsrConfD* o) {               // a
                   o->sustain_sec = a[5]; o->sustain_vel = a[6]; o->release_sec = a[7]; o->release_vel = a[8]; return true; }
     return false;
 }
-#define NEED_SAMPLE(s) if ((s) < 0 || (size_t)(s) >= c->samples.size()) return c->fail(TDG_ERR_INVALID, "unknown sample index")
+#define NEED_SAMPLE(s) if ((s) < 0 || (size_t)(s) >= c->samples.size() || !c->samples[(size_t)(s)].l) return c->fail(TDG_ERR_INVALID, "unknown sample index")
 #define NEED_FLOWW(f) if ((f) < 0 || (size_t)(f) >= c->flowws.size()) return c->fail(TDG_ERR_INVALID, "unknown floww index")
 
 int tdg_add_sum(tdg_ctx* h, float gain, float angle) { HVertex v; v.kind = K_SUM; return add_vertex(C_, v, gain, angle, 0.0f); }

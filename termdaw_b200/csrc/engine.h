@@ -21,8 +21,12 @@ struct Floww {
 };
 
 struct MultiEntry { int64_t t; float vel; };                       // extensions.rs:29
-struct DNote { float note, vel, hz; uint64_t seq; uint32_t ia; };  // extensions.rs:42
-struct SNote { float note, vel, env_t, rel_t, hz; uint64_t seq; uint32_t ia; float relv[3] = {0, 0, 0}; };   // extensions.rs:49,55; relv: apply_ads(conf_o, rel_t)
+// rec / xclk are planner bookkeeping of the pass being planned: the voice's VoiceRec, its explicit clock (-1: none)
+struct DNote { float note, vel, hz; int rec; };                     // extensions.rs:42
+// env_t is the voice's clock at the START of the pass being planned (carried from the pass before); inside a pass the
+// clock is (clk_chunk, clk_i): -(clk_i/sr) + one addition of bl/sr per chunk since clk_chunk, or the explicit clock xclk
+struct SNote { float note, vel, env_t, rel_t, hz; int rec; int xclk; float relv[3] = {0, 0, 0};
+               uint32_t clk_chunk = 0, clk_i = 0, drop_chunk = 0xffffffffu; };   // extensions.rs:49,55; relv: apply_ads(conf_o, rel_t)
 struct A3 { float t, vel, rel; };                                  // extensions.rs:67-68
 
 struct OscConfH { float volume = 0, param = 0; AdsrConfD adsr{}; };

@@ -38,6 +38,8 @@ const char* TDH_FN(last_error)(tdg_ctx* ctx);
 int TDH_FN(sample_mode_from_string)(const char* s);
 int TDH_FN(sample_add)(tdg_ctx* ctx, const float* linear, uint64_t n_values, uint32_t channels, uint32_t src_sr, int mode);
 int TDH_FN(resource_add)(tdg_ctx* ctx, const uint8_t* bytes, uint64_t n);
+int TDH_FN(sample_remove)(tdg_ctx* ctx, int sample);
+int TDH_FN(resource_remove)(tdg_ctx* ctx, int resource);
 int TDH_FN(floww_add)(tdg_ctx* ctx, const float* t_sec, const float* note, const float* vel, uint64_t n);
 int TDH_FN(floww_reset)(tdg_ctx* ctx);
 int TDH_FN(graph_reset)(tdg_ctx* ctx);
@@ -178,6 +180,7 @@ struct State {
     uint32_t render_sr = 48000, bd = 16;                                          // main.rs:75-98
     std::string output_file = "outp.wav", output_vertex;
     std::vector<SampleSeed> cur_samples;
+    std::vector<NamePath> cur_resources;
     std::map<std::string, int> sample_index, resource_index, floww_index, name_map;
     std::vector<std::string> names, messages;
 

@@ -39,12 +39,16 @@ bool State::refresh(const Project& p) {
     if (p.has_output_file) output_file = p.output_file;
     output_vertex = p.output_vertex;
 
-    // samples: keep what did not change (state.rs:201-219).  The bank is append-only on the device; removed
-    // names are just dropped from the name map.
+    // samples: keep what did not change, drop what left the script or changed (state.rs:201-219; SampleBank::mark_dead
+    // + refresh, sample.rs:316-336): the device memory of a dropped sample is freed
     const std::vector<SampleSeed>& fresh = p.samples;
     auto has = [](const std::vector<SampleSeed>& v, const SampleSeed& s) { return std::find(v.begin(), v.end(), s) != v.end(); };
     for (const SampleSeed& t : cur_samples)
-        if (!has(fresh, t)) { say("Info: sample \"" + t.name + "\" will be removed from the sample bank."); sample_index.erase(t.name); }
+        if (!has(fresh, t)) {
+            say("Info: sample \"" + t.name + "\" will be removed from the sample bank.");
+            auto it = sample_index.find(t.name);
+            if (it != sample_index.end()) { TDH_FN(sample_remove)(ctx, it->second); sample_index.erase(it); }
+        }
     std::vector<std::string> excluded;
     for (const SampleSeed& s : fresh) {
         if (has(cur_samples, s) && sample_index.count(s.name)) continue;
@@ -59,13 +63,28 @@ bool State::refresh(const Project& p) {
     for (const SampleSeed& s : fresh) if (std::find(excluded.begin(), excluded.end(), s.name) == excluded.end()) cur_samples.push_back(s);
     if (!excluded.empty()) return false;                       // do_excluding!, state.rs:188-199
 
-    for (const NamePath& r : p.resources) {                    // state.rs:222-237
-        if (resource_index.count(r.name)) continue;
+    // resources: diffed as (name, path) tuples like the samples (state.rs:222-237)
+    auto has_r = [](const std::vector<NamePath>& v, const NamePath& r) {
+        for (const NamePath& q : v) if (q.name == r.name && q.path == r.path) return true;
+        return false;
+    };
+    for (const NamePath& t : cur_resources)
+        if (!has_r(p.resources, t)) {
+            say("Info: resource \"" + t.name + "\" will be removed from the resource bank.");
+            auto it = resource_index.find(t.name);
+            if (it != resource_index.end()) { TDH_FN(resource_remove)(ctx, it->second); resource_index.erase(it); }
+        }
+    std::vector<NamePath> res_loaded;
+    for (const NamePath& r : p.resources) {
+        if (has_r(cur_resources, r) && resource_index.count(r.name)) { res_loaded.push_back(r); continue; }
         try {
+            if (resource_index.count(r.name)) throw Error("there is already a resource with name \"" + r.name + "\" present.");
             const std::vector<uint8_t> b = assets->blob(r.path);
             resource_index[r.name] = chk(TDH_FN(resource_add)(ctx, b.data(), b.size()));
-        } catch (const Error& e) { say(e.what()); return false; }
+            res_loaded.push_back(r);
+        } catch (const Error& e) { say(e.what()); cur_resources = res_loaded; return false; }
     }
+    cur_resources = res_loaded;
 
     TDH_FN(floww_reset)(ctx);                                  // flowws: always reloaded (state.rs:240-250)
     floww_index.clear();

@@ -71,10 +71,65 @@ __device__ __forceinline__ float block_max(float m) {
     return m;   // valid in thread 0
 }
 
+// ------------------------------------------------------------------------------------ K0: clocks and per-chunk ranges
+// clock[n][i] = -(i as f32 / sr as f32) after n additions of (bl as f32 / sr as f32): the env_t of every voice and
+// the t of every Adsr slot n chunks after the event that (re)started it at frame offset i (tdg_types.h).
+// One thread per column, the additions in the reference's order; rows [row0, depth) are (re)built from row0 - 1.
+__global__ void __launch_bounds__(256) k_env_table(float* __restrict__ clock, uint32_t bl, uint32_t row0, uint32_t depth, float fsr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bl) return;
+    const float d = (float)bl / fsr;
+    float v = row0 == 0 ? -((float)i / fsr) : clock[(size_t)(row0 - 1) * bl + i];
+    if (row0 == 0) { clock[i] = v; }
+    for (uint32_t n = row0 == 0 ? 1 : row0; n < depth; ++n) { v += d; clock[(size_t)n * bl + i] = v; }
+}
+__device__ __forceinline__ float clock_at(uint32_t src, uint32_t n, const float* __restrict__ clock, uint32_t bl, const float* __restrict__ xenv) {
+    return (src & kEnvExplicit) ? xenv[(src & ~kEnvExplicit) + n] : __ldg(clock + (size_t)n * bl + src);
+}
+// first index in [0, n) for which pred(index) holds (pred monotone: false... true), n if none
+template <typename P> __device__ __forceinline__ uint32_t first_true(uint32_t n, P pred) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (pred(m)) hi = m; else lo = m + 1; }
+    return lo;
+}
+// The per-chunk index ranges of every event-driven vertex of a pass (voices, adsr, sample_multi, sample_lerp), one
+// thread per (task, chunk): the host uploads O(events) records, the O(chunks) tables are made here.
+__global__ void __launch_bounds__(256) k_chunk_ranges(const RangeTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    const RangeTask T = tasks[blockIdx.y];
+    const uint32_t kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= T.n_chunks) return;
+    const uint32_t n = T.n_recs;
+    Range2 out{0u, 0u};
+    if (T.kind == RK_VOICE) {
+        const VoiceRec* R = reinterpret_cast<const VoiceRec*>(blob + T.recs_off);
+        const uint32_t k = T.chunk0 + kk;
+        out.x = first_true(n, [&](uint32_t v) { return R[v].pm_end >= k; });
+        out.y = first_true(n, [&](uint32_t v) { return R[v].sm_on > k; });
+        if (out.y < out.x) out.y = out.x;
+    } else if (T.kind == RK_ADSR) {
+        const AdsrRec* R = reinterpret_cast<const AdsrRec*>(blob + T.recs_off);
+        const uint64_t c0 = (uint64_t)(T.chunk0 + kk) * T.bl;
+        const uint32_t a = first_true(n, [&](uint32_t v) { return R[v].start > c0; });            // record 0 starts at frame 0
+        const uint32_t b = first_true(n, [&](uint32_t v) { return R[v].start >= c0 + T.bl; });
+        out.x = a - 1; out.y = b - (a - 1);
+    } else if (T.kind == RK_MULTI) {
+        const MultiHit* H = reinterpret_cast<const MultiHit*>(blob + T.recs_off);
+        const int64_t c0 = (int64_t)kk * T.bl;                                                      // hits are relative to the emitted range
+        out.x = first_true(n, [&](uint32_t v) { return H[v].start > c0 - T.len; });
+        out.y = first_true(n, [&](uint32_t v) { return H[v].start > c0 + (int64_t)T.bl - 1; });
+        if (out.y < out.x) out.y = out.x;
+    } else {
+        const LerpHit* H = reinterpret_cast<const LerpHit*>(blob + T.recs_off);
+        const int64_t c0 = (int64_t)kk * T.bl;
+        out.x = first_true(n, [&](uint32_t v) { return H[v].frame > c0; }) - 1;                     // entries 0, 1: the carried pair
+    }
+    T.out[kk] = out;
+}
+
 // ------------------------------------------------------------------------------------ K4: fx
 // sum_inputs (extensions.rs:310-319) + { nothing | adsr_gen (:593-651) | per-chunk peak for
 // normalize_gen (:321-329) } + apply_angle + apply_gain (:262-263), one pass over HBM.
-#define TDG_FX_SEGS 24
+#define TDG_FX_SEGS 32
 template <bool EXACT>
 __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& sg, float offset, float maxmul, float minmul) {
     float pvel, gvel;
@@ -135,24 +190,36 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB :
     float l[4], r[4];
     const uint32_t i_first = threadIdx.x * 4;
     bool have = false;
-    const AdsrSeg* segs = nullptr;
     uint32_t n_seg = 0;
     float maxmul = 0.0f, minmul = 0.0f;
+    const AdsrRec* recs = nullptr; const float* xenv = nullptr; uint32_t kabs = 0; uint64_t c0 = 0;
+    auto build_seg = [&](uint32_t q) {
+        const AdsrRec R = recs[q];
+        AdsrSeg sg;
+        sg.ia = R.start > c0 ? (uint32_t)(R.start - c0) : 0u; sg.flags = R.flags;
+        sg.pt = clock_at(R.p_src, kabs - R.p_chunk, T.clock, bl, xenv); sg.pv = R.pv; sg.pr = R.pr;
+        sg.gt = clock_at(R.g_src, kabs - R.g_chunk, T.clock, bl, xenv); sg.gv = R.gv; sg.gr = R.gr;
+        return sg;
+    };
+    // state s of the chunk: staged in shared memory; a chunk with more state changes than the staging area holds
+    // (a hit every few frames) reads the rest straight from the records
+    auto seg_ia = [&](uint32_t q) -> uint32_t {
+        if (q < (uint32_t)TDG_FX_SEGS) return s_seg[q].ia;
+        const uint64_t st = recs[q].start; return st > c0 ? (uint32_t)(st - c0) : 0u;
+    };
+    auto seg_get = [&](uint32_t q) -> AdsrSeg { if (q < (uint32_t)TDG_FX_SEGS) return s_seg[q]; return build_seg(q); };
     if (MODE == FX_ADSR) {
-        // the chunk's envelope states are fetched (segment pointers -> states -> shared memory) while the
-        // audio loads of the first run are already in flight: both chains start right after the task load
-        const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
-        const uint32_t s_lo = sp[k];
-        n_seg = sp[k + 1] - s_lo;
+        // the chunk's envelope states are built from the event records (index range from k_chunk_ranges, clocks
+        // from the table) into shared memory while the audio loads of the first run are already in flight
+        const Range2 rg = T.ranges[k];
+        n_seg = rg.y;
         if (i_first < bl) { load_sum(i_first, l, r); have = true; }
-        segs = reinterpret_cast<const AdsrSeg*>(blob + T.seg_off) + s_lo;
         maxmul = T.use_max ? 1.0f : 0.0f; minmul = 1.0f - maxmul;
-        if (n_seg <= TDG_FX_SEGS) {                      // chunk's envelope states into shared memory
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(segs);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(s_seg);
-            for (uint32_t w = threadIdx.x; w < n_seg * (uint32_t)(sizeof(AdsrSeg) / 4); w += TDG_THREADS) dst[w] = src[w];
-            segs = s_seg;
-        }
+        recs = reinterpret_cast<const AdsrRec*>(blob + T.recs_off) + rg.x;
+        xenv = reinterpret_cast<const float*>(blob + T.xenv_off);
+        kabs = T.chunk0 + k;
+        c0 = (uint64_t)kabs * bl;
+        for (uint32_t q = threadIdx.x; q < n_seg && q < (uint32_t)TDG_FX_SEGS; q += TDG_THREADS) s_seg[q] = build_seg(q);
         __syncthreads();
     }
     float peak = 0.0f;
@@ -165,10 +232,10 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB :
             // last segment starting at or before the thread's first frame; the common case is that the
             // same state covers all four frames
             uint32_t s = 0;
-            while (s + 1 < n_seg && segs[s + 1].ia <= i) ++s;
-            const bool one = s + 1 >= n_seg || segs[s + 1].ia >= i + 4;
+            while (s + 1 < n_seg && seg_ia(s + 1) <= i) ++s;
+            const bool one = s + 1 >= n_seg || seg_ia(s + 1) >= i + 4;
             if (one) {
-                const AdsrSeg sg = segs[s];
+                const AdsrSeg sg = seg_get(s);
                 if (!(sg.flags & 1u)) {
                     // plateau test on the run's first frame only: most runs sit between two hits with both
                     // envelopes finished (or held), and then the whole run has one gain
@@ -208,8 +275,8 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB :
             } else {
 #pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
-                    while (s + 1 < n_seg && segs[s + 1].ia <= i + j) ++s;
-                    const AdsrSeg sg = segs[s];
+                    while (s + 1 < n_seg && seg_ia(s + 1) <= i + j) ++s;
+                    const AdsrSeg sg = seg_get(s);
                     if (sg.flags & 1u) continue;             // un-enveloped frame (extensions.rs:633-635)
                     const float vel = adsr_frame_vel<EXACT>(T, sg, k_div<EXACT>((float)(i + j), T.fsr, T.rsr), maxmul, minmul);
                     if (j == 0) { l[0] *= vel; r[0] *= vel; } else if (j == 1) { l[1] *= vel; r[1] *= vel; }
@@ -358,8 +425,8 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* _
     const uint32_t bl = T.h.bl;
     const int64_t p0 = (int64_t)k * bl;
     const MultiHit* hits = reinterpret_cast<const MultiHit*>(blob + T.hits_off);
-    // candidates for this chunk: start > p0 - L  and  start <= p0 + bl - 1 (range table from the host planner)
-    const uint2 rg = reinterpret_cast<const uint2*>(blob + T.range_off)[k];
+    // candidates for this chunk: start > p0 - L  and  start <= p0 + bl - 1 (k_chunk_ranges)
+    const Range2 rg = T.ranges[k];
     const uint32_t lo = rg.x, hi = rg.y;
     const int64_t len = (int64_t)T.len;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
@@ -402,8 +469,8 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
     const uint32_t bl = T.h.bl;
     const int64_t p0 = (int64_t)k * bl;
     const LerpHit* hits = reinterpret_cast<const LerpHit*>(blob + T.hits_off);
-    // index of the last hit with frame <= p0 (entries 0 and 1 are the carried ghost / primary); host table
-    const uint32_t base = reinterpret_cast<const uint32_t*>(blob + T.base_off)[k];
+    // index of the last hit with frame <= p0 (entries 0 and 1 are the carried ghost / primary); k_chunk_ranges
+    const uint32_t base = T.ranges[k].x;
     const int64_t lm1 = (int64_t)T.len - 1;
     const int64_t lerp_len = (int64_t)T.lerp_len;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
@@ -511,48 +578,106 @@ __device__ __forceinline__ float wavetable_eval(const float* __restrict__ tab, f
     return a + fy * (b - a);
 }
 
-// F = consecutive frames per thread (register pressure: the three-oscillator synth body runs 2-wide)
+// F = consecutive frames per thread; a block evaluates one tile of TDG_THREADS * F frames of one chunk.
 //
-// No block-wide staging and no barrier after the task load: every thread walks the chunk's segments
-// straight from the plan blob (32 B per segment, the same address for the whole block, so each read is
-// one L1-resident broadcast), and the per-voice release start values come precomputed in the segment.
-// The barrier-per-batch version spent a quarter of its stall cycles waiting for the two warps that
-// staged and pre-evaluated the segments (profiles/: stall_barrier).
+// The chunk's voices are found on the device: the host uploads one VoiceRec per voice (O(events)); the block
+// takes the chunk's candidate range from k_chunk_ranges, and batch by batch (kVoiceBatch records) its threads
+// test one record each, build the (up to two: held part, release part) segments the voice has inside the chunk
+// with their clocks read from the clock table, and compact them in push order into shared memory (warp-shuffle
+// prefix sum).  Then every thread walks the staged segments (same shared address for the whole block: broadcast
+// reads) and sums its frames in that order — f32 summation order is part of the contract.
+static const int kVoiceBatch = 128;                 // candidate records per batch -> at most 256 staged segments
 // LIBM: sin is glibc's sinf restated in double precision (m_sinf_glibc: bit-exact against the reference's libm
 // call); false = the f32 Cody-Waite + minimax evaluation d_sin (<= 2 ulp, tdg_set_oscillator_mode(ctx, 0)).
 template <int KIND, bool EXACT, int F, bool LIBM>
 __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : TDG_SAMPSYN_MINB) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ VoiceTask T;
+    __shared__ float4 s_a[2 * kVoiceBatch];          // hz, vel, env_t, rel_t
+    __shared__ float4 s_b[2 * kVoiceBatch];          // ia, ib, relv0, relv1
+    __shared__ float s_r2[2 * kVoiceBatch];          // relv2
+    __shared__ uint32_t s_wsum[kVoiceBatch / 32];
     load_task(&T, tasks + blockIdx.y);
-    const uint32_t k = blockIdx.x;
-    if (k >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
-    const uint64_t p0 = (uint64_t)k * bl;
-    const uint32_t* sp = reinterpret_cast<const uint32_t*>(blob + T.seg_ptr_off);
-    const uint32_t s_lo = sp[k], s_hi = sp[k + 1];
-    const float4* __restrict__ gsegs = reinterpret_cast<const float4*>(blob + T.seg_off);
-    const float* __restrict__ grelv2 = reinterpret_cast<const float*>(blob + T.relv2_off);
+    const uint32_t tiles = (bl + TDG_THREADS * F - 1) / (TDG_THREADS * F);
+    const uint32_t kk = blockIdx.x / tiles, tile = blockIdx.x - kk * tiles;
+    if (kk >= T.h.n_chunks) return;
+    const uint32_t k = T.chunk0 + kk;                                            // pass chunk
+    const uint64_t p0 = (uint64_t)kk * bl;
+    const Range2 rg = T.ranges[kk];
+    const VoiceRec* __restrict__ recs = reinterpret_cast<const VoiceRec*>(blob + T.recs_off);
+    const float* __restrict__ xenv = reinterpret_cast<const float*>(blob + T.xenv_off);
     const float* __restrict__ tab = T.table;
     const float fsr = T.fsr, rsr = T.rsr;
     const bool vec = (bl % F) == 0;
     const float n_phase_f = (float)T.n_phase, ymax = (float)(T.n_frames - 1);
     const int last_row_off = (int)((T.n_frames - 1) * T.n_phase);
-    for (uint32_t base = 0; base < bl; base += TDG_THREADS * F) {
-        const uint32_t i0 = base + threadIdx.x * F;
-        if (i0 >= bl) break;
-        float acc[F], time[F], off[F];
+    const uint32_t i0 = tile * (TDG_THREADS * F) + threadIdx.x * F;
+    const bool active = i0 < bl;
+    float acc[F], time[F], off[F];
 #pragma unroll
-        for (int j = 0; j < F; ++j) {
-            acc[j] = 0.0f;
-            time[j] = k_div<EXACT>((float)(T.t0 + p0 + i0 + j), fsr, rsr);      // (t + i) as f32 / sr as f32
-            off[j] = k_div<EXACT>((float)(i0 + j), fsr, rsr);                   // i as f32 / sr as f32
+    for (int j = 0; j < F; ++j) {
+        acc[j] = 0.0f;
+        time[j] = k_div<EXACT>((float)(T.t0 + p0 + i0 + j), fsr, rsr);          // (t + i) as f32 / sr as f32
+        off[j] = k_div<EXACT>((float)(i0 + j), fsr, rsr);                       // i as f32 / sr as f32
+    }
+    for (uint32_t b0 = rg.x; b0 < rg.y; b0 += kVoiceBatch) {
+        // ---- stage: one candidate record per thread -> 0, 1 or 2 segments, compacted in record order
+        uint32_t cnt = 0;
+        float4 a0, b0v, a1, b1v; float r20 = 0.0f, r21 = 0.0f;
+        if (threadIdx.x < kVoiceBatch && b0 + threadIdx.x < rg.y) {
+            const VoiceRec R = recs[b0 + threadIdx.x];
+            if (R.on_chunk <= k && k <= R.end_chunk) {
+                const uint32_t end_here = k == R.end_chunk ? R.end_i : bl;
+                if (k <= R.off_chunk) {                                          // held part (off_chunk == kNever: never released)
+                    const uint32_t ia = k == R.on_chunk ? R.on_i : 0u;
+                    const uint32_t ib = k == R.off_chunk ? R.off_i : end_here;
+                    if (ib > ia) {
+                        const float env_t = KIND == VOICE_DEBUG_SINE ? 0.0f : clock_at(R.envh, k - R.on_chunk, T.clock, bl, xenv);
+                        a0 = make_float4(R.hz, R.vel, env_t, 0.0f);
+                        b0v = make_float4(__uint_as_float(ia), __uint_as_float(ib), 0.0f, 0.0f);
+                        cnt = 1;
+                    }
+                }
+                if (R.off_chunk <= k) {                                          // release part
+                    const uint32_t ia = k == R.off_chunk ? R.off_i : 0u;
+                    if (end_here > ia) {
+                        const float env_t = clock_at(R.envr, k - R.off_chunk, T.clock, bl, xenv);
+                        const float4 a = make_float4(R.hz, R.vel, env_t, R.rel_t);
+                        const float4 bb = make_float4(__uint_as_float(ia), __uint_as_float(end_here), R.relv0, R.relv1);
+                        if (cnt) { a1 = a; b1v = bb; r21 = R.relv2; } else { a0 = a; b0v = bb; r20 = R.relv2; }
+                        ++cnt;
+                    }
+                }
+            }
         }
+        uint32_t n_stage = 0;
+        {
+            const uint32_t ln = threadIdx.x & 31, w = threadIdx.x >> 5;
+            uint32_t inc = cnt;
+            if (threadIdx.x < kVoiceBatch) {                                     // whole warps: kVoiceBatch is a multiple of 32
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d); if (ln >= (uint32_t)d) inc += up; }
+                if (ln == 31) s_wsum[w] = inc;
+            }
+            __syncthreads();                                                     // also: the previous batch's readers are done
+            uint32_t base = 0;
+#pragma unroll
+            for (int q = 0; q < kVoiceBatch / 32; ++q) { const uint32_t v = s_wsum[q]; if ((uint32_t)q < w) base += v; n_stage += v; }
+            if (cnt) {
+                const uint32_t pos = base + inc - cnt;
+                s_a[pos] = a0; s_b[pos] = b0v; s_r2[pos] = r20;
+                if (cnt > 1) { s_a[pos + 1] = a1; s_b[pos + 1] = b1v; s_r2[pos + 1] = r21; }
+            }
+            __syncthreads();
+        }
+        // ---- evaluate: every thread walks the staged segments in order
+        if (active) {
 #pragma unroll 1
-        for (uint32_t s = s_lo; s < s_hi; ++s) {
-            const float4 sb = __ldg(gsegs + 2 * (size_t)s + 1);                   // ia, ib, relv0, relv1
+        for (uint32_t s = 0; s < n_stage; ++s) {
+            const float4 sb = s_b[s];                                             // ia, ib, relv0, relv1
             const uint32_t ia = __float_as_uint(sb.x), ib = __float_as_uint(sb.y);
             if (i0 + F <= ia || i0 >= ib) continue;
-            const float4 sa = __ldg(gsegs + 2 * (size_t)s);                       // hz, vel, env_t, rel_t
+            const float4 sa = s_a[s];                                             // hz, vel, env_t, rel_t
             const float hz = sa.x, vel = sa.y, env_t = sa.z, rel_t = sa.w;
             const bool rel = rel_t != 0.0f;
             float smp[F];
@@ -580,7 +705,7 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
                         // release start value => the values just computed for oscillator 1 are oscillator 2's
                         const bool reuse = o == 2 && T.env12_same && T.vol[1] > 0.0f;
                         if (!reuse)
-                            flat = rel ? k_apply_r_n<EXACT, F>(T.env[o], et, o == 0 ? sb.z : o == 1 ? sb.w : __ldg(grelv2 + s), e)
+                            flat = rel ? k_apply_r_n<EXACT, F>(T.env[o], et, o == 0 ? sb.z : o == 1 ? sb.w : s_r2[s], e)
                                        : k_apply_ads_n<EXACT, F>(T.env[o], et, e);
                         // envelope sitting at exactly 0 (a percussive oscillator after its decay): every term is
                         // shape*vel*0*vol = +-0 for finite factors, and adding +-0 to the running sum changes nothing
@@ -611,21 +736,22 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
             for (int j = 0; j < F; ++j)
                 if (i0 + j >= ia && i0 + j < ib) acc[j] += smp[j];
         }
-        {
-            float l[F], r[F];
+        }
+    }
+    if (active) {
+        float l[F], r[F];
 #pragma unroll
-            for (int j = 0; j < F; ++j) { l[j] = acc[j]; r[j] = acc[j]; apply_pg(l[j], r[j], T.h.pg); }
-            float* ol = T.h.out_l + p0 + i0; float* orr = T.h.out_r + p0 + i0;
-            if (vec && F == 4) {
-                *reinterpret_cast<float4*>(ol) = make_float4(l[0], l[1], l[2], l[3]);
-                *reinterpret_cast<float4*>(orr) = make_float4(r[0], r[1], r[2], r[3]);
-            } else if (vec && F == 2) {
-                *reinterpret_cast<float2*>(ol) = make_float2(l[0], l[1]);
-                *reinterpret_cast<float2*>(orr) = make_float2(r[0], r[1]);
-            } else {
+        for (int j = 0; j < F; ++j) { l[j] = acc[j]; r[j] = acc[j]; apply_pg(l[j], r[j], T.h.pg); }
+        float* ol = T.h.out_l + p0 + i0; float* orr = T.h.out_r + p0 + i0;
+        if (vec && F == 4) {
+            *reinterpret_cast<float4*>(ol) = make_float4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<float4*>(orr) = make_float4(r[0], r[1], r[2], r[3]);
+        } else if (vec && F == 2) {
+            *reinterpret_cast<float2*>(ol) = make_float2(l[0], l[1]);
+            *reinterpret_cast<float2*>(orr) = make_float2(r[0], r[1]);
+        } else {
 #pragma unroll
-                for (int j = 0; j < F; ++j) if (i0 + j < bl) { ol[j] = l[j]; orr[j] = r[j]; }
-            }
+            for (int j = 0; j < F; ++j) if (i0 + j < bl) { ol[j] = l[j]; orr[j] = r[j]; }
         }
     }
 }
@@ -954,6 +1080,17 @@ __global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __res
 // rubato SincFixedIn<f32>, Linear, as restated in DESIGN.md: output j of chunk c sits at
 // idx = last_index_c + (j+1)*t_ratio (f64), interpolating two 256-tap windows of neighbouring
 // sub-phases.  The per-chunk (last_index, n_out) come from the host's exact f64 replay.
+// positions first: one thread per chunk repeats the reference's `idx += t_ratio` from the chunk's carried-in index
+// (a closed form (j+1)*t_ratio + last differs in the last bits, and the sub-phase fraction is rounded to f32)
+__global__ void __launch_bounds__(64) k_resample_index(const ResampleTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    const ResampleTask T = tasks[blockIdx.y];
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= T.n_chunks) return;
+    const ResampleChunk C = reinterpret_cast<const ResampleChunk*>(blob + T.chunk_off)[c];
+    double idx = C.last_index;
+    double* out = T.idx + C.out_off;
+    for (uint32_t j = 0; j < C.n_out; ++j) { idx += T.t_ratio; out[j] = idx; }
+}
 __global__ void __launch_bounds__(128) k_resample(const ResampleTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint64_t n_out_total) {
     const ResampleTask T = tasks[blockIdx.y];
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -966,7 +1103,8 @@ __global__ void __launch_bounds__(128) k_resample(const ResampleTask* __restrict
     const ResampleChunk C = ch[a];
     const uint32_t j = (uint32_t)(g - C.out_off);
     const int sinc_len = 256, factor = 256;
-    const double idx = fma((double)(j + 1), T.t_ratio, C.last_index);
+    (void)j;
+    const double idx = T.idx[g];
     const double fl = floor(idx);
     int64_t i0 = (int64_t)fl;
     int64_t s0 = (int64_t)floor((idx - fl) * (double)factor);
@@ -1053,6 +1191,16 @@ cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks
     else { if (vec) k_fx<FX_NORM_PEAK, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_NORM_PEAK, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
     return cudaGetLastError();
 }
+cudaError_t launch_env_table(float* clock, uint32_t bl, uint32_t row0, uint32_t depth, float fsr, cudaStream_t s) {
+    if (depth <= row0 || bl == 0) return cudaSuccess;
+    k_env_table<<<(bl + 255) / 256, 256, 0, s>>>(clock, bl, row0, depth, fsr);
+    return cudaGetLastError();
+}
+cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    k_chunk_ranges<<<grid2((max_chunks + 255) / 256, n), 256, 0, s>>>(t, blob);
+    return cudaGetLastError();
+}
 cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s) {
     k_norm_prefix<<<n, 1024, 0, s>>>(t);
     return cudaGetLastError();
@@ -1127,7 +1275,8 @@ cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks,
     k_quantise<<<grid2(max_blocks ? max_blocks : 1, n), TDG_THREADS, 0, s>>>(t);
     return cudaGetLastError();
 }
-cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, const uint8_t* blob, cudaStream_t s) {
+cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s) {
+    k_resample_index<<<grid2((max_chunks + 63) / 64, n), 64, 0, s>>>(t, blob);
     const uint64_t blocks = (max_out + 127) / 128;
     k_resample<<<grid2(blocks ? blocks : 1, n), 128, 0, s>>>(t, blob, max_out);
     return cudaGetLastError();

@@ -8,6 +8,11 @@
 namespace tdg {
 
 cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, const uint8_t* blob, cudaStream_t s);
+// clock table rows [row0, depth) of one (sr, bl); per-chunk index ranges of every event-driven vertex of a pass
+cudaError_t launch_env_table(float* clock, uint32_t bl, uint32_t row0, uint32_t depth, float fsr, cudaStream_t s);
+cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s);
+// voices: a block = one tile of 1024 frames of one chunk; max_chunks = max over tasks of n_chunks * tiles(bl)
+static inline uint32_t voice_tiles(uint32_t bl) { return (bl + 1023u) / 1024u; }
 cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s);
 cudaError_t launch_norm_total(const NormPrefixTask* t, uint32_t n, float* reduce_buf, cudaStream_t s);
 cudaError_t launch_bp_total(const BpTask* t, uint32_t n, const uint8_t* blob, cudaStream_t s);
@@ -21,7 +26,7 @@ cudaError_t launch_bp_aggregate(const BpTask* t, uint32_t n, uint32_t max_tiles,
 cudaError_t launch_bp_carry(const BpTask* t, uint32_t n, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s);
-cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, const uint8_t* blob, cudaStream_t s);
+cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s);   // positions (k_resample_index), then the windows
 cudaError_t launch_deinterleave(const float* lin, uint64_t n_frames, uint32_t stride, uint32_t off_l, uint32_t off_r,
                                 uint32_t mix, float* out_l, float* out_r, cudaStream_t s);
 cudaError_t launch_absmax(const float* x, uint64_t n, int* out_bits, cudaStream_t s);

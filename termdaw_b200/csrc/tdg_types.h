@@ -48,7 +48,49 @@ struct TaskHdr {
     PanGain pg;
 };
 
-// ---- per-chunk tables -------------------------------------------------------------------------
+// ---- event records: the plan the host uploads is O(events), the per-chunk tables are built on the device ----
+// Every voice / envelope clock of the reference is a run of f32 additions of d = bl as f32 / sr as f32, one per
+// chunk, starting from -(i as f32 / sr as f32) at the frame offset i of the event that (re)started it
+// (extensions.rs:481-494,525-527 voices; :610-618,640-650 adsr slots).  Its value n chunks later depends on
+// (i, n) only: clock[n][i], ONE table per (sr, bl) for every vertex of every project on the device, built there
+// by k_env_table with the same sequential additions.  A clock source word names where a record's clock comes
+// from: bit 31 clear -> column i of the table; bit 31 set -> index into the task's explicit per-chunk array in
+// the plan blob (state carried in from an earlier pass: the scan before a render, tdg_play).
+static const uint32_t kEnvExplicit = 0x80000000u;
+static const uint32_t kNever = 0xffffffffu;
+struct VoiceRec {           // one voice of a Synth / SampSyn / DebugSine vertex over one pass, in Vec (push) order
+    float hz, vel;
+    uint32_t on_chunk, on_i;        // first sounding frame: pass chunk, frame offset
+    uint32_t off_chunk, off_i;      // first frame of its release phase; off_chunk == kNever: not released in this pass
+    uint32_t end_chunk, end_i;      // one past its last frame: chunk, offset in [0, bl]
+    float rel_t, relv0, relv1, relv2;   // release phase: rel_t and apply_ads(conf_o, rel_t) per oscillator (adsr.rs:89-92)
+    uint32_t envh, envr;            // clock source of the held / the release phase
+    uint32_t pm_end, sm_on;         // prefix max of end_chunk over records [0, v], suffix min of on_chunk over [v, n):
+                                    // both monotone, so the candidates of a chunk are one binary-searched index range
+};
+struct AdsrRec {            // Adsr vertex state from pass frame `start` on (extensions.rs:61-69)
+    uint64_t start;                 // chunk * bl + frame offset
+    uint32_t flags, pad;            // bit0: this single frame is passed through un-enveloped (extensions.rs:633-635)
+    uint32_t p_src, p_chunk;        // primary: clock source and the pass chunk its clock (re)started in
+    float pv, pr;                   //          vel, release_val
+    uint32_t g_src, g_chunk;        // ghost
+    float gv, gr;
+};
+struct MultiHit { int64_t start; float vel, pad; };                       // pass-relative first frame
+struct LerpHit { int64_t frame, pos_origin, cd_origin; float vel, pad; }; // see plan_sample_lerp
+
+// per-chunk index ranges into the records above, written by k_chunk_ranges (one thread per chunk, binary searches)
+struct alignas(8) Range2 { uint32_t x, y; };
+enum RangeKind : uint32_t { RK_VOICE = 0, RK_ADSR = 1, RK_MULTI = 2, RK_LERP = 3 };
+struct RangeTask {
+    uint32_t kind, n_chunks, chunk0, bl;
+    uint64_t recs_off;              // blob: VoiceRec[] / AdsrRec[] / MultiHit[] / LerpHit[]
+    uint32_t n_recs, pad;
+    int64_t len;                    // RK_MULTI: sample length
+    Range2* out;                     // [n_chunks] x = lo, y = hi (RK_ADSR: first, count; RK_LERP: x = base)
+};
+
+// ---- staged (shared-memory) per-chunk forms ------------------------------------------------------------
 struct AdsrSeg {            // Adsr vertex state valid from frame offset `ia` of its chunk (extensions.rs:61-69)
     uint32_t ia, flags;     // flags bit0: this single frame is passed through un-enveloped (extensions.rs:633-635)
     float pt, pv, pr, gt, gv, gr;   // primary (t, vel, release_val), ghost (t, vel, release_val)
@@ -59,8 +101,6 @@ struct VoiceSeg {           // one voice over frames [ia, ib) of one chunk, in v
     float relv0, relv1;     // released voices: apply_ads(conf, rel_t) of adsr.rs:89-92 for oscillator 0 / 1 (constant per
                             // voice, evaluated once by the host planner with the reference's own operations)
 };
-struct MultiHit { int64_t start; float vel, pad; };                       // pass-relative first frame
-struct LerpHit { int64_t frame, pos_origin, cd_origin; float vel, pad; }; // see plan_sample_lerp
 
 // ---- tasks ------------------------------------------------------------------------------------
 static const int kInlineInputs = 8;     // the reference's graphs rarely fan in wider; wider vertices read the blob table
@@ -74,8 +114,11 @@ struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan 
     AdsrK conf;
     float wet, fsr, rsr;    // fsr = sr as f32, rsr = 1/fsr
     uint32_t use_off, use_max, sr;
-    uint64_t seg_ptr_off;   // blob: uint32[n_chunks+1], indices into the AdsrSeg array
-    uint64_t seg_off;       // blob: AdsrSeg[]
+    uint64_t recs_off;      // FX_ADSR, blob: AdsrRec[n_recs] sorted by start (record 0 starts at pass frame 0)
+    uint64_t xenv_off;      // blob: float[] explicit clocks
+    const Range2* ranges;    // device scratch [n_chunks]: (first record, count) of every chunk (k_chunk_ranges)
+    const float* clock;     // [depth][bl] clock table of this (sr, bl)
+    uint32_t n_recs, chunk0; // chunk0: pass chunk of block 0 (time-sharded segments start late)
     float* peaks;           // FX_NORM_PEAK: [n_chunks] max |x| over L and R of the summed chunk
     uint32_t no_store, pad1; // FX_NORM_PEAK of the output vertex in a scan pass: only the peaks are needed
 };
@@ -103,13 +146,13 @@ struct NormScaleTask {      // buf *= 1/max, then pan + gain, in place
 struct LoopTask { TaskHdr h; const float* sl; const float* sr; uint64_t len, t0; };
 struct MultiTask {
     TaskHdr h; const float* sl; const float* sr; uint64_t len; uint64_t hits_off; uint32_t n_hits, pad;
-    uint64_t range_off;     // blob: uint2[n_chunks] = [lo, hi) of the hits that can sound in the chunk (host two-pointer
-                            // sweep; replaces two dependent binary searches at the head of every block)
+    const Range2* ranges;    // device scratch [n_chunks] = [lo, hi) of the hits that can sound in the chunk (k_chunk_ranges:
+                            // one thread per chunk does the two binary searches once, not every block at its head)
 };
 struct LerpTask {
     TaskHdr h; const float* sl; const float* sr; uint64_t len; uint64_t hits_off;
     uint32_t n_hits, lerp_len;
-    uint64_t base_off;      // blob: uint32[n_chunks] = index of the last hit at or before the chunk's first frame
+    const Range2* ranges;    // device scratch [n_chunks]: x = index of the last hit at or before the chunk's first frame
 };
 
 enum VoiceKind : uint32_t { VOICE_DEBUG_SINE = 0, VOICE_SYNTH = 1, VOICE_SAMPSYN = 2 };
@@ -118,9 +161,11 @@ struct VoiceTask {
     uint32_t kind, sr;
     float fsr, rsr;         // sr as f32 and its IEEE reciprocal
     uint64_t t0;            // graph time of pass frame 0 (time = (t0 + p) as f32 / sr as f32)
-    uint64_t seg_ptr_off;   // blob: uint32[n_chunks+1]
-    uint64_t seg_off;       // blob: VoiceSeg[]
-    uint64_t relv2_off;     // blob: float[] parallel to the segments: the same release start value for oscillator 2 (Synth)
+    uint64_t recs_off;      // blob: VoiceRec[n_recs] in push order
+    uint64_t xenv_off;      // blob: float[] explicit clocks (voices carried in from an earlier pass)
+    const Range2* ranges;    // device scratch [n_chunks]: candidate records [lo, hi) of every chunk (k_chunk_ranges)
+    const float* clock;     // [depth][bl] clock table of this (sr, bl)
+    uint32_t n_recs, chunk0; // chunk0: pass chunk of block 0
     // Synth (extensions.rs:44-50); shape constants of synth.rs:22-29 evaluated on the host:
     // sq_iz = 1/z, tf_add = (1-z)/2, tf_mul = 2/(1+z)
     float vol[3];           // square, topflat, triangle volumes
@@ -183,6 +228,8 @@ struct ResampleTask {       // rubato SincFixedIn restated: one output frame per
     const float* halo_l;
     const float* halo_r;
     uint64_t n_before;
+    double* idx;            // [total outputs] SincFixedIn's f64 position of every output: k_resample_index accumulates it
+                            // chunk by chunk with the reference's sequential `idx += t_ratio` (bit-exact positions)
 };
 static const int kResampleHalo = 512;   // 2 * sinc_len: the history SincFixedIn keeps in front of a chunk
 struct ResampleChunk { double last_index; uint64_t out_off; uint32_t n_out, pad; };

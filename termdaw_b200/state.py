@@ -149,6 +149,7 @@ class State:
         self.output_file = "outp.wav"
         self.output_vertex = ""
         self.cur_samples: List[Tuple[str, str, str]] = []
+        self.cur_resources: List[Tuple[str, str]] = []
         self.sample_index: Dict[str, int] = {}
         self.resource_index: Dict[str, int] = {}
         self.floww_index: Dict[str, int] = {}
@@ -170,16 +171,20 @@ class State:
             self.cs = set_length_chunks(self.psr, project.length_seconds, self.bl)
         if project.render_samplerate is not None: self.render_sr = project.render_samplerate
         if project.render_bitdepth is not None: self.bd = project.render_bitdepth
+        # (state.rs:80,165: the local starts as mem::take(&mut self.output_file), i.e. the PREVIOUS name, and is written
+        # back after the script ran: a script that does not call set_output_file keeps the previous name)
         if project.output_file is not None: self.output_file = project.output_file
         self.output_vertex = project.output_vertex
 
-        # samples: keep what did not change (state.rs:201-219).  The bank is append-only on the
-        # device; removed names are just dropped from the name map.
+        # samples: keep what did not change, drop what left the script or changed (state.rs:201-219;
+        # SampleBank::mark_dead + refresh, sample.rs:316-336): the device memory of a dropped sample is freed
         new = list(project.samples)
         for t in self.cur_samples:
             if t not in new:
                 self._say(f"Info: sample \"{t[0]}\" will be removed from the sample bank.")
-                self.sample_index.pop(t[0], None)
+                idx = self.sample_index.pop(t[0], None)
+                if idx is not None:
+                    c.sample_remove(idx)
         excluded = []
         for (name, path, mode) in new:
             if (name, path, mode) in self.cur_samples and name in self.sample_index:
@@ -197,15 +202,30 @@ class State:
         if excluded:
             return False                                                    # do_excluding!, state.rs:188-199
 
-        # resources (state.rs:222-237)
-        for (name, path) in project.resources:
-            if name in self.resource_index:
+        # resources: diffed as (name, path) tuples like the samples (state.rs:222-237): a resource that left the
+        # script is dropped, a changed path under the same name is reloaded
+        new_res = list(project.resources)
+        for t in self.cur_resources:
+            if t not in new_res:
+                self._say(f"Info: resource \"{t[0]}\" will be removed from the resource bank.")
+                idx = self.resource_index.pop(t[0], None)
+                if idx is not None:
+                    c.resource_remove(idx)
+        loaded = []
+        for (name, path) in new_res:
+            if (name, path) in self.cur_resources and name in self.resource_index:
+                loaded.append((name, path))
                 continue
             try:
+                if name in self.resource_index:
+                    raise TermdawError(-5, f"there is already a resource with name \"{name}\" present.")
                 self.resource_index[name] = c.resource_add(self.assets.blob(path))
+                loaded.append((name, path))
             except (OSError, TermdawError) as e:
                 self._say(str(e))
+                self.cur_resources = loaded
                 return False
+        self.cur_resources = loaded
 
         # flowws: always reloaded (state.rs:240-250)
         c.floww_reset()

@@ -184,3 +184,47 @@ def test_state_refresh_failure_modes(oracle):
     st3 = State(oracle, 48000, 256, assets=a)
     assert not st3.refresh(p3)
     st3.close()
+
+
+def test_refresh_diffs_samples_and_resources_like_the_reference(oracle):
+    """State::refresh diffs (name, path, mode) / (name, path) tuples against the previous refresh (state.rs:172-237):
+    what left the script is dropped from the bank (SampleBank::mark_dead + refresh, sample.rs:316-336), a changed
+    path under the same name is RELOADED, unchanged entries are kept.  The render after an edited refresh equals
+    a fresh State's render of the edited project."""
+    from helpers import run_project
+    from termdaw_b200 import synthetic as S
+    from termdaw_b200._capi import TermdawError
+
+    def project(table, with_kick):
+        p, a, s = S.config_3(0.004, voices=8)
+        a.blobs["other.wtb"] = S.wavetable_blob(999, 8, 128, 3.0)
+        p.resources[0] = ("table", table)
+        if not with_kick:
+            p.samples = [t for t in p.samples if t[0] != "sweep"]
+            p.samplelerps = [t for t in p.samplelerps if t[3] != "sweep"]
+            p.edges = [e for e in p.edges if e[0] != "l2"]
+        return p, a, s
+
+    p1, a, s = project("table.wtb", True)
+    st = State(oracle, s["psr"], s["bl"], assets=a)
+    assert st.refresh(p1), st.messages
+    sweep_idx = st.sample_index["sweep"]
+    assert st.ctx.sample_frames(sweep_idx) > 0
+    p2, _, _ = project("other.wtb", False)
+    st.messages.clear()
+    assert st.refresh(p2), st.messages
+    assert any("sample \"sweep\" will be removed" in m for m in st.messages)
+    assert any("resource \"table\" will be removed" in m for m in st.messages)
+    assert "sweep" not in st.sample_index and st.ctx.sample_frames(sweep_idx) == 0       # the slot is empty, memory returned
+    with pytest.raises(TermdawError):
+        st.ctx.add_sample_loop(1.0, 0.0, sweep_idx)                                      # a removed sample cannot be named
+    st.scan_exact()
+    edited = st.render().copy()
+    fresh = run_project(oracle, p2, a, s, taps=False)["pcm"]
+    assert np.array_equal(edited, fresh)                                                 # the NEW table is what sounds
+    unchanged = run_project(oracle, *project("table.wtb", False), taps=False)["pcm"]
+    assert not np.array_equal(edited, unchanged)
+    st.messages.clear()
+    assert st.refresh(p1), st.messages                                                   # and back: sweep is loaded again
+    assert st.sample_index["sweep"] != sweep_idx and st.ctx.sample_frames(st.sample_index["sweep"]) > 0
+    st.close()
