@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="duration scale of the workload")
     ap.add_argument("--cpu-sample", type=int, default=12, help="projects in the cpu_baseline sample (c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the `secondary` block of the default line (configs[3] time-sharded over the ranks, configs[2] on rank 0)")
+    ap.add_argument("--secondary-steps", type=int, default=3)
+    ap.add_argument("--secondary-scale", type=float, default=1.0, help="duration scale of the secondary workloads")
     ap.add_argument("--value-group", type=int, default=0,
                     help="projects per pipelined group for the device-resident `value` passes (0 = one launch sequence)")
     return ap.parse_args()
@@ -306,7 +310,7 @@ class BatchRunner:
                 "h2d": ev_bytes + s1["h2d_bytes"] + s2["h2d_bytes"], "d2h": s2["d2h_bytes"], "kstats": ks,
                 "algo": s1["algorithmic_bytes"] + s2["algorithmic_bytes"], "plan_ms": s1["plan_ms"] + s2["plan_ms"],
                 "reused_v": s2.get("reused_vertices", 0), "reused_b": s2.get("reused_bytes", 0),
-                "collectives": 0}
+                "voice_frames": s1.get("voice_frames", 0) + s2.get("voice_frames", 0), "collectives": 0}
 
     def close(self):
         for st, _, _ in self.states:
@@ -360,12 +364,89 @@ class TimeShardRunner:
                 "h2d": ev_bytes + s1["h2d_bytes"] + s2["h2d_bytes"], "d2h": s2["d2h_bytes"], "kstats": ks,
                 "algo": s1["algorithmic_bytes"] + s2["algorithmic_bytes"], "plan_ms": s1["plan_ms"] + s2["plan_ms"],
                 "reused_v": s2.get("reused_vertices", 0), "reused_b": s2.get("reused_bytes", 0),
-                "collectives": c.collectives() - col0}
+                "voice_frames": s1.get("voice_frames", 0) + s2.get("voice_frames", 0), "collectives": c.collectives() - col0}
 
     def close(self):
         self.ts.close()
         for st, _, _ in self.states:
             st.close()
+
+
+def run_secondary(lib, args, rank, local_rank, world, dist, torch, barrier, peak):
+    """The other two configurations BASELINE.json's north_star asks numbers for, measured inside the default run
+    (fewer steps): configs[3] — ONE 64-vertex, 3600 s graph sharded by TIME over the N ranks (strong scaling;
+    normalize peaks / band-pass state / resampler halo cross the segment boundaries through NCCL inside the
+    library) — and configs[2] — 512 wavetable voices for 600 s — on rank 0.  Same timing rules as the primary."""
+    import copy
+    out = {}
+    for wl in ("c4", "c3"):
+        a = copy.copy(args)
+        a.workload, a.scale, a.projects = wl, args.secondary_scale, 1
+        solo = wl == "c3"                                  # one GPU's worth of work: rank 0 runs it, the others wait
+        R = None
+        res = None
+        if not solo or rank == 0:
+            R = (TimeShardRunner(lib, a, rank, local_rank, world, dist) if wl == "c4"
+                 else BatchRunner(lib, a, 0, local_rank, 1, None))
+        sync = (lambda: torch.cuda.synchronize()) if solo else barrier
+        steps = max(1, args.secondary_steps)
+        if R is not None:
+            R.step(False)
+            sync()
+            dev_ms = plan_ms = 0.0
+            launches = algo = collectives = vframes = 0
+            kstats = {}
+            for _ in range(steps):
+                r = R.step(False)
+                dev_ms += r["device_ms"]; launches += r["launches"]; algo += r["algo"]; plan_ms += r["plan_ms"]
+                collectives += r["collectives"]; vframes += r.get("voice_frames", 0)
+                _merge_kstats(kstats, r["kstats"])
+            sync()
+            (R.states[0][0].ctx).set_profiling(False)
+            R.alloc_outs()
+            R.step(True)
+            sync()
+            t1 = time.perf_counter()
+            h2d = d2h = 0
+            for _ in range(steps):
+                r = R.step(True)
+                h2d += r["h2d"]; d2h += r["d2h"]
+            sync()
+            e2e_wall = time.perf_counter() - t1
+            t = torch.tensor([dev_ms, e2e_wall], dtype=torch.float64, device="cuda")
+            if dist is not None and not solo:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev_ms_max, e2e_max = t.tolist()
+            frames = R.total_frames_per_step
+            x = kstats.get("nccl_exchange", {"launches": 0, "ms": 0.0})
+            res = {
+                "workload": WORKLOAD_NAMES[wl], "n_gpus": 1 if solo else world, "scaling": "strong" if wl == "c4" else "single GPU",
+                "parallelism": R.parallelism, "steps": steps, "seconds": R.cs[0] * R.bl / PSR,
+                "value": frames * steps / (dev_ms_max / 1e3), "unit": "frames/s", "ms_per_step": dev_ms_max / steps,
+                "realtime_factor": frames * steps / (dev_ms_max / 1e3) / PSR,
+                "e2e": {"value": frames * steps / e2e_max, "unit": "frames/s", "ms_per_step": e2e_max / steps * 1e3,
+                        "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps},
+                "host_plan_ms_per_step": plan_ms / steps, "gpu_launches": launches,
+                "algorithmic_gb_per_step_this_rank": algo / steps / 1e9,
+                "whole_step_algorithmic_gbs_this_rank": algo / (dev_ms / 1e3) / 1e9 if dev_ms > 0 else 0.0,
+                "per_kernel_rank0": {k: {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] // steps,
+                                         "frac_of_hbm_peak": (v["bytes"] / (v["ms"] / 1e3) / 1e9 / peak) if v["ms"] > 0 else 0.0}
+                                     for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])[:8]},
+            }
+            if wl == "c4":
+                res["nccl_exchange_rounds_per_step"] = collectives // steps
+                res["nccl_exchange_ms_per_round_rank0"] = (x["ms"] / x["launches"]) if x["launches"] else None
+                res["nccl_exchange_ms_per_step_rank0"] = x["ms"] / steps
+            else:
+                res["voice_frames_per_step"] = vframes // steps
+                res["voice_frames_per_s"] = vframes / (dev_ms_max / 1e3)
+            R.close()
+        if not solo or dist is None:
+            pass
+        barrier()
+        if rank == 0:
+            out[wl] = res
+    return out
 
 
 def _claim_stdout():
@@ -549,8 +630,18 @@ def main():
             line["cpu_baseline"] = {"value": fr / dt, "unit": "frames/s", "cores": 1, "kind": "port", "cpu_model": cpu_model,
                                     "sample": sample + f" ({dt:.1f} s of CPU work; restatement of the reference, not the Rust build)",
                                     "host_cores_available": os.cpu_count()}
-        print_line(json.dumps(line))
     R.close()
+    if args.workload == "c5" and not args.no_secondary:
+        peak_gbs = 6532.9
+        try:
+            peak_gbs = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak_gbs)
+        except (OSError, ValueError):
+            pass
+        secondary = run_secondary(lib, args, rank, local_rank, world, dist, torch, barrier, peak_gbs)
+        if rank == 0:
+            line["secondary"] = secondary
+    if rank == 0:
+        print_line(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -195,7 +195,10 @@ struct Engine {
     uint64_t hwm_work = 0, hwm_blob = 0, hwm_pcm = 0;         // largest work arena / plan blob any lane or slot has needed
     uint64_t hwm_keep = 0;
     bool reuse = true;                           // render reads pass-invariant cones from the scan (TDG_PASS_REUSE=0 / tdg_set_pass_reuse)
-    uint64_t bp_l2_bytes = 48ull << 20;          // band-pass launch groups: inputs + outputs per group (TDG_BP_L2_MB, 0 = one launch triple per level)
+    // band-pass launch groups: inputs + outputs per group.  Measured on B200 (profiles/r02): with 48 MB groups the 512-project
+    // step has 735 launch triples whose one-block-per-filter carry kernels and short grids cost far more (28 ms) than the
+    // L2 hits save, so the default is one launch triple per level (0); the knob stays for single long renders (TDG_BP_L2_MB)
+    uint64_t bp_l2_bytes = 0;
     bool libm_sin = true;                        // oscillators evaluate glibc's sinf exactly (TDG_FAST_SIN=1 / tdg_set_oscillator_mode(ctx, 0): f32 polynomial, <= 2 ulp)
     WorkerPool* pool = nullptr;                  // planner threads (created on first batched pass)
     std::vector<Frag>* frags = nullptr;          // pooled per-project plan fragments (capacity is kept between jobs)
@@ -482,6 +485,7 @@ struct VPlan {
     std::vector<LerpHit> lhits;
     std::vector<float> xenv;            // explicit clocks, concatenated (state carried in from an earlier pass)
     uint64_t voice_frames = 0;
+    uint64_t seg_cap = 0;               // voices: upper bound of the per-chunk segments inside the emitted range
     uint32_t depth = 0;                 // rows of the clock table this vertex reads
     bool planned = false;
 };
@@ -525,7 +529,7 @@ static inline uint32_t patch_src(const PlanScratch& S, uint32_t src) {
 // a chunk), and both are replayed there with the reference's own sequence of f32 additions.
 static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, VPlan& out, PlanScratch& S) {
     std::vector<VoiceRec>& R = out.vrecs;
-    R.clear(); out.xenv.clear(); out.voice_frames = 0; out.depth = 0;
+    R.clear(); out.xenv.clear(); out.voice_frames = 0; out.depth = 0; out.seg_cap = 0;
     size_t n_x = 0;
     auto new_xclk = [&]() -> int { if (S.xc.size() <= n_x) S.xc.emplace_back(); S.xc[n_x].clear(); return (int)n_x++; };
     const float fsr = (float)pp.sr;
@@ -692,6 +696,9 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, VPlan
         if (r.off_chunk != kNever && !(r.envr & kEnvExplicit) && r.end_chunk >= r.off_chunk) out.depth = std::max(out.depth, r.end_chunk - r.off_chunk + 1);
         const uint64_t a = std::max<uint64_t>((uint64_t)r.on_chunk * pp.bl + r.on_i, e0), b = std::min<uint64_t>((uint64_t)r.end_chunk * pp.bl + r.end_i, e1);
         if (b > a) out.voice_frames += b - a;
+        // chunks of the emitted range the voice touches, + 1 where its release starts inside one of them
+        const uint64_t c_lo = std::max<uint64_t>(r.on_chunk, pp.emit0), c_hi = std::min<uint64_t>(r.end_chunk, pp.emit0 + pp.emit_n - 1);
+        if (pp.emit_n && c_hi >= c_lo) out.seg_cap += c_hi - c_lo + 1 + ((r.off_chunk != kNever && r.off_chunk >= c_lo && r.off_chunk <= c_hi) ? 1 : 0);
     }
     uint32_t sm = kNever;
     for (size_t q = R.size(); q-- > 0;) { sm = std::min(sm, R[q].on_chunk); R[q].sm_on = sm; }
@@ -775,6 +782,8 @@ struct PassReq {
     std::vector<int> last_use;
     std::vector<int64_t> buf_off, aux_off;   // work-arena byte offsets
     std::vector<int64_t> rng_off;            // per event-driven vertex: uint2[emit_n] written by k_chunk_ranges
+    std::vector<int64_t> seg_off;            // per voice vertex: seg_ptr[emit_n + 1], segs[cap][2] (float4), relv2[cap]
+    std::vector<uint64_t> seg_cap;
     uint64_t n_frames = 0, n_pad = 0;
     uint64_t pcm_off = 0, pcm_bytes = 0, err_off = 0, rs_off = 0, rs_total = 0, rs_idx_off = 0;
     bool resample = false;
@@ -839,10 +848,10 @@ struct Frag {
     HeapBlob blob; uint64_t base = 0;
     std::vector<LevelTasks> levels;
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
-    std::vector<RangeTask> ranges; uint32_t range_max = 0, resamp_chunks = 0;
+    std::vector<RangeTask> ranges; uint32_t range_max = 0, resamp_chunks = 0; bool any_voice = false;
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, algo = 0, reused_v = 0, reused_b = 0;
     void reset(size_t n_levels) {        // pooled on the engine: capacities survive from job to job
-        blob.v.clear(); base = 0; ranges.clear(); range_max = 0; resamp_chunks = 0;
+        blob.v.clear(); base = 0; ranges.clear(); range_max = 0; resamp_chunks = 0; any_voice = false;
         if (levels.size() > n_levels) levels.resize(n_levels);
         for (LevelTasks& L : levels) L.clear();
         levels.resize(n_levels);
@@ -876,7 +885,7 @@ struct PassJob {
     std::vector<LevelTasks> levels;
     std::vector<Off> offs;
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
-    std::vector<RangeTask> ranges; uint32_t range_max = 0, resamp_chunks = 0; uint64_t range_off = 0;
+    std::vector<RangeTask> ranges; uint32_t range_max = 0, resamp_chunks = 0; uint64_t range_off = 0; bool any_voice = false;
     std::vector<cudaEvent_t> clock_events;   // clock tables this job reads that were extended on another stream
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, quant_off = 0, resamp_off = 0;
     uint64_t algo_bytes_total = 0, reused_v = 0, reused_b = 0;
@@ -908,7 +917,7 @@ static int pass_plan(PassJob& J) {
         const int V = (int)x->verts.size();
         r.n_frames = r.emit_n * x->bl;
         r.n_pad = align_up(std::max<uint64_t>(r.n_frames, 1), kBpTile);
-        r.buf_off.assign(V, -1); r.aux_off.assign(V, -1); r.rng_off.assign(V, -1);
+        r.buf_off.assign(V, -1); r.aux_off.assign(V, -1); r.rng_off.assign(V, -1); r.seg_off.assign(V, -1); r.seg_cap.assign(V, 0);
         for (int v = 0; v < V; ++v) max_level = std::max(max_level, r.level[v]);
     }
     J.err_bytes = reqs.size() * 4;
@@ -1050,6 +1059,71 @@ static int pass_plan(PassJob& J) {
             r.pcm_off = pbump.alloc(align_up(r.pcm_bytes, 64) + 64);
         }
     }
+    const double tr_layout0 = now_ms();
+    if (!g->pool) {
+        g->pool = new WorkerPool();
+        // planner threads: the host's cores shared fairly between the ranks of this node (one process per GPU):
+        // 8 ranks x 31 threads on a 32-core host was what bounded the 8-GPU step (VERDICT r1)
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned local_world = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = (unsigned)std::max(1, atoi(e));
+        unsigned want = std::max(1u, std::min(hw / local_world, 32u));
+        if (const char* e = getenv("TDG_PLAN_THREADS")) want = (unsigned)std::max(1, atoi(e));
+        g->pool->start(want - 1);
+        g->frags = new std::vector<Frag>();
+        g->scratch = new std::vector<PlanScratch>(g->pool->workers());
+        g->vplans = new std::vector<std::vector<VPlan>>();
+    }
+    if (g->frags->size() < reqs.size()) g->frags->resize(reqs.size());
+    // ---- 2a. event plans: every event-driven vertex of every project is independent -> one work item each
+    // (a batch of small projects and one long 64-vertex project both spread over the planner threads)
+    if (g->vplans->size() < reqs.size()) g->vplans->resize(reqs.size());
+    std::vector<std::vector<VPlan>>& vplans_a = *g->vplans;
+    struct Item { uint32_t ri, v; };
+    std::vector<Item> items;
+    for (size_t ri = 0; ri < reqs.size(); ++ri) {
+        PassReq& r = reqs[ri];
+        Ctx* x = r.c;
+        const size_t V = x->verts.size();
+        if (vplans_a[ri].size() < V) vplans_a[ri].resize(V);
+        for (size_t v = 0; v < V; ++v) {
+            vplans_a[ri][v].planned = false;
+            if (r.level[v] < 0 || r.skip[v]) continue;
+            const HVertex& hv = x->verts[v];
+            const bool ev = (hv.kind == K_ADSR && !(hv.wet < 0.0001f)) || hv.kind == K_SAMPLE_MULTI || hv.kind == K_SAMPLE_LERP ||
+                            hv.kind == K_DEBUG_SINE || hv.kind == K_SYNTH || hv.kind == K_SAMPSYN;
+            if (ev) items.push_back({(uint32_t)ri, (uint32_t)v});
+        }
+    }
+    g->pool->parallel_for(items.size(), 64, [&](size_t q, unsigned w) {
+        PassReq& r = reqs[items[q].ri];
+        Ctx* x = r.c;
+        const uint32_t v = items[q].v;
+        HVertex& hv = x->verts[v];
+        VPlan& VP = vplans_a[items[q].ri][v];
+        PlanScratch& PS = (*g->scratch)[w];
+        const PassParams pp{r.is_scan ? 0 : x->fb_frame, r.is_scan ? 0 : x->t, r.total, r.emit0, r.emit_n, x->bl, x->sr};
+        // (true_normalize_scan: fb.set_time(0) and t = j*bl, graph.rs:228-231)
+        VP.depth = 0; VP.voice_frames = 0;
+        const double t_item = trace_on() ? now_ms() : 0.0;
+        switch (hv.kind) {
+            case K_ADSR: plan_adsr(hv, x->flowws[hv.floww], pp, VP, PS); break;
+            case K_SAMPLE_MULTI: plan_multi(hv, x->flowws[hv.floww], x->samples[hv.sample].frames, pp, VP.mhits); break;
+            case K_SAMPLE_LERP: plan_lerp(hv, x->flowws[hv.floww], pp, VP.lhits); break;
+            default: plan_voices(hv, x->flowws[hv.floww], pp, VP, PS); break;
+        }
+        VP.planned = true;
+        if (trace_on() && now_ms() - t_item > 5.0) fprintf(stderr, "[tdg] slow event plan: vertex %u kind %d %.2f ms (worker %u)\n", v, hv.kind, now_ms() - t_item, w);
+    });
+    // segment tables of the voice vertices (built on the device): their capacity is known once the events are planned
+    for (const Item& it : items) {
+        PassReq& r = reqs[it.ri];
+        const HVertex& hv = r.c->verts[it.v];
+        if (hv.kind != K_DEBUG_SINE && hv.kind != K_SYNTH && hv.kind != K_SAMPSYN) continue;
+        const uint64_t cap = std::max<uint64_t>(vplans_a[it.ri][it.v].seg_cap, 1);
+        r.seg_cap[it.v] = cap;
+        r.seg_off[it.v] = (int64_t)bump.alloc(align_up((r.emit_n + 1) * 4, 16) + cap * 32 + cap * 4 + 16);
+    }
     const double tr_layout = now_ms();
     g->hwm_work = std::max<uint64_t>(g->hwm_work, bump.off + 256);
     CU(ln.work.ensure(bump.off + 256, g->hwm_work));
@@ -1090,63 +1164,9 @@ static int pass_plan(PassJob& J) {
         }
     }
     const double tr_vstate = now_ms();
-    if (!g->pool) {
-        g->pool = new WorkerPool();
-        // planner threads: the host's cores shared fairly between the ranks of this node (one process per GPU):
-        // 8 ranks x 31 threads on a 32-core host was what bounded the 8-GPU step (VERDICT r1)
-        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        unsigned local_world = 1;
-        if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = (unsigned)std::max(1, atoi(e));
-        unsigned want = std::max(1u, std::min(hw / local_world, 32u));
-        if (const char* e = getenv("TDG_PLAN_THREADS")) want = (unsigned)std::max(1, atoi(e));
-        g->pool->start(want - 1);
-        g->frags = new std::vector<Frag>();
-        g->scratch = new std::vector<PlanScratch>(g->pool->workers());
-        g->vplans = new std::vector<std::vector<VPlan>>();
-    }
-    if (g->frags->size() < reqs.size()) g->frags->resize(reqs.size());
     Frag* frags = g->frags->data();
     const size_t n_frags = reqs.size();
-    // ---- 2a. event plans: every event-driven vertex of every project is independent -> one work item each
-    // (a batch of small projects and one long 64-vertex project both spread over the planner threads)
-    if (g->vplans->size() < reqs.size()) g->vplans->resize(reqs.size());
     std::vector<std::vector<VPlan>>& vplans = *g->vplans;
-    struct Item { uint32_t ri, v; };
-    std::vector<Item> items;
-    for (size_t ri = 0; ri < reqs.size(); ++ri) {
-        PassReq& r = reqs[ri];
-        Ctx* x = r.c;
-        const size_t V = x->verts.size();
-        if (vplans[ri].size() < V) vplans[ri].resize(V);
-        for (size_t v = 0; v < V; ++v) {
-            vplans[ri][v].planned = false;
-            if (r.level[v] < 0 || r.skip[v]) continue;
-            const HVertex& hv = x->verts[v];
-            const bool ev = (hv.kind == K_ADSR && !(hv.wet < 0.0001f)) || hv.kind == K_SAMPLE_MULTI || hv.kind == K_SAMPLE_LERP ||
-                            hv.kind == K_DEBUG_SINE || hv.kind == K_SYNTH || hv.kind == K_SAMPSYN;
-            if (ev) items.push_back({(uint32_t)ri, (uint32_t)v});
-        }
-    }
-    g->pool->parallel_for(items.size(), 64, [&](size_t q, unsigned w) {
-        PassReq& r = reqs[items[q].ri];
-        Ctx* x = r.c;
-        const uint32_t v = items[q].v;
-        HVertex& hv = x->verts[v];
-        VPlan& VP = vplans[items[q].ri][v];
-        PlanScratch& PS = (*g->scratch)[w];
-        const PassParams pp{r.is_scan ? 0 : x->fb_frame, r.is_scan ? 0 : x->t, r.total, r.emit0, r.emit_n, x->bl, x->sr};
-        // (true_normalize_scan: fb.set_time(0) and t = j*bl, graph.rs:228-231)
-        VP.depth = 0; VP.voice_frames = 0;
-        const double t_item = trace_on() ? now_ms() : 0.0;
-        switch (hv.kind) {
-            case K_ADSR: plan_adsr(hv, x->flowws[hv.floww], pp, VP, PS); break;
-            case K_SAMPLE_MULTI: plan_multi(hv, x->flowws[hv.floww], x->samples[hv.sample].frames, pp, VP.mhits); break;
-            case K_SAMPLE_LERP: plan_lerp(hv, x->flowws[hv.floww], pp, VP.lhits); break;
-            default: plan_voices(hv, x->flowws[hv.floww], pp, VP, PS); break;
-        }
-        VP.planned = true;
-        if (trace_on() && now_ms() - t_item > 5.0) fprintf(stderr, "[tdg] slow event plan: vertex %u kind %d %.2f ms (worker %u)\n", v, hv.kind, now_ms() - t_item, w);
-    });
     // ---- 2b. clock tables: one per (sr, bl), deep enough for the longest-lived clock of this job
     J.clock_events.clear();
     {
@@ -1179,7 +1199,6 @@ static int pass_plan(PassJob& J) {
             if (tb.ev_set) J.clock_events.push_back(tb.ev);
         }
     }
-    const double tr_events = now_ms();
     auto plan_one = [&](PassReq& r, Frag& F, std::vector<VPlan>& VPs) -> int {
         Ctx* x = r.c;
         F.reset((size_t)max_level + 1);
@@ -1372,15 +1391,26 @@ static int pass_plan(PassJob& J) {
                     t.h = h; t.sr = x->sr; t.t0 = pass_t0 + r.emit0 * x->bl;
                     t.fsr = (float)x->sr; t.rsr = 1.0f / t.fsr;
                     bool exotic = adsr_duration_exotic(t.fsr);
-                    t.recs_off = B.alloc(std::max<size_t>(VP.vrecs.size(), 1) * sizeof(VoiceRec));
-                    memcpy(B.at<uint8_t>(t.recs_off), VP.vrecs.data(), VP.vrecs.size() * sizeof(VoiceRec));
-                    t.xenv_off = B.alloc(std::max<size_t>(VP.xenv.size(), 1) * 4);
-                    memcpy(B.at<uint8_t>(t.xenv_off), VP.xenv.data(), VP.xenv.size() * 4);
-                    t.n_recs = (uint32_t)VP.vrecs.size(); t.chunk0 = (uint32_t)r.emit0; t.clock = clock;
-                    t.ranges = range_task(RK_VOICE, v, t.recs_off, VP.vrecs.size(), 0);
+                    // the records go up; the per-chunk segment table is built from them in device scratch
+                    const uint64_t recs_off = B.alloc(std::max<size_t>(VP.vrecs.size(), 1) * sizeof(VoiceRec));
+                    memcpy(B.at<uint8_t>(recs_off), VP.vrecs.data(), VP.vrecs.size() * sizeof(VoiceRec));
+                    const uint64_t xenv_off = B.alloc(std::max<size_t>(VP.xenv.size(), 1) * 4);
+                    memcpy(B.at<uint8_t>(xenv_off), VP.xenv.data(), VP.xenv.size() * 4);
+                    {
+                        uint8_t* sb = W + r.seg_off[v];
+                        uint32_t* seg_ptr = reinterpret_cast<uint32_t*>(sb);
+                        F4* segs = reinterpret_cast<F4*>(sb + align_up((r.emit_n + 1) * 4, 16));
+                        float* relv2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(segs) + r.seg_cap[v] * 32);
+                        (void)range_task(RK_VOICE, v, recs_off, VP.vrecs.size(), 0);
+                        RangeTask& rt = F.ranges.back();
+                        rt.seg_ptr = seg_ptr; rt.segs = segs; rt.relv2 = relv2; rt.clock = clock; rt.xenv_off = xenv_off;
+                        rt.debug_sine = hv.kind == K_DEBUG_SINE ? 1u : 0u;
+                        F.any_voice = true;
+                        t.seg_ptr = seg_ptr; t.segs = segs; t.relv2 = relv2;
+                    }
                     x->stats.voice_frames += VP.voice_frames;
                     const uint64_t vbytes = 8ull * r.n_frames + VP.vrecs.size() * sizeof(VoiceRec);
-                    const uint32_t nblk = nch * voice_tiles(x->bl);            // a block = one 1024-frame tile of one chunk
+                    const uint32_t nblk = nch;
                     if (hv.kind == K_DEBUG_SINE) { t.kind = VOICE_DEBUG_SINE; if (exotic) LT.dsine_exact = true; LT.dsine.v.push_back(t); LT.dsine.max_chunks = std::max(LT.dsine.max_chunks, nblk); LT.dsine.bytes += vbytes; }
                     else if (hv.kind == K_SYNTH) {
                         t.kind = VOICE_SYNTH;
@@ -1468,7 +1498,7 @@ static int pass_plan(PassJob& J) {
     std::vector<ResampleTask>& resamps = J.resamps; uint64_t &resamp_max = J.resamp_max, &resamp_bytes = J.resamp_bytes;
     uint64_t& algo_bytes_total = J.algo_bytes_total;
     quants.clear(); resamps.clear(); quant_max = quant_bytes = resamp_max = resamp_bytes = algo_bytes_total = 0;
-    J.reused_v = J.reused_b = 0; J.ranges.clear(); J.range_max = 0; J.resamp_chunks = 0;
+    J.reused_v = J.reused_b = 0; J.ranges.clear(); J.range_max = 0; J.resamp_chunks = 0; J.any_voice = false;
     {
         uint64_t tot = 0;
         for (size_t i = 0; i < n_frags; ++i) { Frag& F = frags[i]; F.base = align_up(tot, 256); tot = F.base + F.blob.v.size(); }
@@ -1488,9 +1518,6 @@ static int pass_plan(PassJob& J) {
                 for (FxTask& t : S.fx_norm.v) t.in_off += b;
                 for (MultiTask& t : S.multi.v) t.hits_off += b;
                 for (LerpTask& t : S.lerp.v) t.hits_off += b;
-                for (VoiceTask& t : S.dsine.v) { t.recs_off += b; t.xenv_off += b; }
-                for (VoiceTask& t : S.synth.v) { t.recs_off += b; t.xenv_off += b; }
-                for (VoiceTask& t : S.sampsyn.v) { t.recs_off += b; t.xenv_off += b; }
                 for (BpTask& t : S.bp.v) t.in_off += b;
                 append_list(Dst.fx, S.fx); append_list(Dst.fx_adsr, S.fx_adsr); append_list(Dst.fx_norm, S.fx_norm);
                 append_list(Dst.nprefix, S.nprefix); append_list(Dst.nscale, S.nscale);
@@ -1501,7 +1528,8 @@ static int pass_plan(PassJob& J) {
                 Dst.synth_exact |= S.synth_exact; Dst.sampsyn_exact |= S.sampsyn_exact;
                 Dst.bp_agg_bytes += S.bp_agg_bytes;
             }
-            for (RangeTask& t : F.ranges) { t.recs_off += b; J.ranges.push_back(t); }
+            for (RangeTask& t : F.ranges) { t.recs_off += b; t.xenv_off += b; J.ranges.push_back(t); }
+            J.any_voice = J.any_voice || F.any_voice;
             J.range_max = std::max(J.range_max, F.range_max); J.resamp_chunks = std::max(J.resamp_chunks, F.resamp_chunks);
             for (ResampleTask& t : F.resamps) { t.chunk_off += b; resamps.push_back(t); }
             for (QuantTask& t : F.quants) quants.push_back(t);
@@ -1543,9 +1571,9 @@ static int pass_plan(PassJob& J) {
     if (!sl.ensure_err(reqs.size())) return c->fail(TDG_ERR_CUDA, "pinned flag buffer allocation failed");
     J.t_planned = now_ms();
     if (trace_on())
-        fprintf(stderr, "[tdg] plan lane %d reqs %zu: layout %.2f arena %.2f vstate %.2f events %.2f (%zu vertices) tasks %.2f merge %.2f blobdev %.2f ms (blob %.1f MB)\n",
-                (int)(J.lane - g->lanes), reqs.size(), tr_layout - J.t_start, tr_arena - tr_layout, tr_vstate - tr_arena,
-                tr_events - tr_vstate, items.size(), tr_planned - tr_events, tr_merged - tr_planned, J.t_planned - tr_merged, B.size / 1e6);
+        fprintf(stderr, "[tdg] plan lane %d reqs %zu: layout %.2f arena %.2f vstate+clocks %.2f events %.2f (%zu vertices) tasks %.2f merge %.2f blobdev %.2f ms (blob %.1f MB)\n",
+                (int)(J.lane - g->lanes), reqs.size(), tr_layout0 - J.t_start, tr_arena - tr_layout, tr_vstate - tr_arena,
+                tr_layout - tr_layout0, items.size(), tr_planned - tr_vstate, tr_merged - tr_planned, J.t_planned - tr_merged, B.size / 1e6);
     return TDG_OK;
 }
 
@@ -1580,15 +1608,6 @@ static int pass_submit(PassJob& J) {
     CU(cudaEventRecord(sl.ev0, s));
     uint64_t &launches = J.launches, &collectives = J.collectives;
     launches = collectives = 0;
-    // per-chunk index ranges of every event-driven vertex of the pass: one launch, before the first level
-    if (!J.ranges.empty()) {
-        const size_t kMaxTasks = 65535;
-        for (size_t b0 = 0; b0 < J.ranges.size(); b0 += kMaxTasks) {
-            const uint32_t nb = (uint32_t)std::min(kMaxTasks, J.ranges.size() - b0);
-            CU(launch_chunk_ranges(reinterpret_cast<const RangeTask*>(D + J.range_off) + b0, nb, J.range_max, D, s));
-            ++launches;
-        }
-    }
     const int x_mode = reqs[0].x_mode;
     for (auto& r : reqs) if (r.x_mode != x_mode || (x_mode == 2 && reqs.size() != 1))
         return r.c->fail(TDG_ERR_INVALID, "time-sharded and plain passes cannot share a launch sequence");
@@ -1599,6 +1618,17 @@ static int pass_submit(PassJob& J) {
         while (sl.evpool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); sl.evpool.push_back(e); }
         return sl.evpool[i];
     };
+    // per-chunk index ranges of every event-driven vertex of the pass: one launch, before the first level
+    if (!J.ranges.empty()) {
+        const size_t kMaxTasks = 65535;
+        for (size_t b0 = 0; b0 < J.ranges.size(); b0 += kMaxTasks) {
+            const uint32_t nb = (uint32_t)std::min(kMaxTasks, J.ranges.size() - b0);
+            if (g->profiling) CU(cudaEventRecord(ev_at(2 * timed.size()), s));
+            CU(launch_chunk_ranges(reinterpret_cast<const RangeTask*>(D + J.range_off) + b0, nb, J.range_max, J.any_voice, D, s));
+            launches += J.any_voice ? 3 : 1;
+            if (g->profiling) { CU(cudaEventRecord(ev_at(2 * timed.size() + 1), s)); timed.push_back({KC_RANGES, 0}); }
+        }
+    }
 #define LAUNCH_SPLIT(cls, list, T, off, bytes_, expr) \
     for (size_t b0 = 0; b0 < (list).v.size(); b0 += kMaxY) { \
         const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, (list).v.size() - b0); \
@@ -1658,8 +1688,11 @@ static int pass_submit(PassJob& J) {
             if (x_mode == 2 && r0.x_stride[L]) {
                 NcclApi* na = nccl_api();
                 float* xb = reinterpret_cast<float*>(W + r0.x_off[L]);
+                // one exchange round of this level (timed as its own class: the time includes waiting for the slowest rank)
+                if (g->profiling) CU(cudaEventRecord(ev_at(2 * timed.size()), s));
                 NC(na->AllGather(xb + (size_t)r0.x_rank * r0.x_stride[L], xb, r0.x_stride[L], kNcclFloat32, r0.c->nccl_comm, s));
                 if (red && r0.x_norms[L]) NC(na->AllReduce(red, red, r0.x_norms[L], kNcclFloat32, kNcclMax, r0.c->nccl_comm, s));
+                if (g->profiling) { CU(cudaEventRecord(ev_at(2 * timed.size() + 1), s)); timed.push_back({KC_XCHG, (uint64_t)r0.x_ranks * r0.x_stride[L] * 4}); }
                 ++collectives;
             }
         }
@@ -1686,7 +1719,9 @@ static int pass_submit(PassJob& J) {
             const PassReq& r0 = reqs[0];
             NcclApi* na = nccl_api();
             float* hb = reinterpret_cast<float*>(W + r0.halo_off);
+            if (g->profiling) CU(cudaEventRecord(ev_at(2 * timed.size()), s));
             NC(na->AllGather(hb + (size_t)r0.x_rank * 2 * kResampleHalo, hb, 2 * kResampleHalo, kNcclFloat32, r0.c->nccl_comm, s));
+            if (g->profiling) { CU(cudaEventRecord(ev_at(2 * timed.size() + 1), s)); timed.push_back({KC_XCHG, (uint64_t)r0.x_ranks * 2 * kResampleHalo * 4}); }
             ++collectives;
         }
     }
@@ -2651,7 +2686,7 @@ int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; retur
 int tdg_set_pipeline_group(tdg_ctx* h, uint32_t projects_per_group) { h->c.eng->pipeline_group = projects_per_group; return TDG_OK; }
 int tdg_last_pass_kernel_stats(tdg_ctx* h, tdg_kernel_stat* out, int cap) {
     static const char* names[KC_COUNT] = {"k_sample_loop", "k_sample_multi", "k_sample_lerp", "k_voice<debug_sine>", "k_voice<synth>",
-        "k_voice<sampsyn>", "k_fx<sum>", "k_fx<adsr>", "k_fx<norm_peak>", "k_norm_prefix", "k_norm_scale", "k_bp_aggregate", "k_bp_carry", "k_bp_apply", "k_resample", "k_quantise"};
+        "k_voice<sampsyn>", "k_fx<sum>", "k_fx<adsr>", "k_fx<norm_peak>", "k_norm_prefix", "k_norm_scale", "k_bp_aggregate", "k_bp_carry", "k_bp_apply", "k_resample", "k_quantise", "nccl_exchange", "k_chunk_ranges"};
     int n = 0;
     for (int k = 0; k < KC_COUNT && n < cap; ++k) {
         const KStat& s = h->c.kstats[k];

@@ -92,6 +92,42 @@ template <typename P> __device__ __forceinline__ uint32_t first_true(uint32_t n,
     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (pred(m)) hi = m; else lo = m + 1; }
     return lo;
 }
+// The (up to two: held part, release part) segments a voice has inside pass chunk k (extensions.rs:481-496): returns
+// their number and, with `seg` given, writes them (VoiceSeg layout + the third oscillator's release start value).
+__device__ __forceinline__ uint32_t voice_segs_in_chunk(const VoiceRec& R, uint32_t k, uint32_t bl, const float* __restrict__ clock,
+                                                        const float* __restrict__ xenv, float4* __restrict__ seg, int debug_sine,
+                                                        float* __restrict__ relv2, uint32_t* written) {
+    (void)written;
+    if (!(R.on_chunk <= k && k <= R.end_chunk)) return 0;
+    uint32_t cnt = 0;
+    const uint32_t end_here = k == R.end_chunk ? R.end_i : bl;
+    if (k <= R.off_chunk) {                                          // held part (off_chunk == kNever: never released)
+        const uint32_t ia = k == R.on_chunk ? R.on_i : 0u;
+        const uint32_t ib = k == R.off_chunk ? R.off_i : end_here;
+        if (ib > ia) {
+            if (seg) {
+                const float env_t = debug_sine ? 0.0f : clock_at(R.envh, k - R.on_chunk, clock, bl, xenv);
+                seg[0] = make_float4(R.hz, R.vel, env_t, 0.0f);
+                seg[1] = make_float4(__uint_as_float(ia), __uint_as_float(ib), 0.0f, 0.0f);
+                relv2[0] = 0.0f;
+            }
+            cnt = 1;
+        }
+    }
+    if (R.off_chunk <= k) {                                          // release part
+        const uint32_t ia = k == R.off_chunk ? R.off_i : 0u;
+        if (end_here > ia) {
+            if (seg) {
+                const float env_t = clock_at(R.envr, k - R.off_chunk, clock, bl, xenv);
+                seg[2 * cnt] = make_float4(R.hz, R.vel, env_t, R.rel_t);
+                seg[2 * cnt + 1] = make_float4(__uint_as_float(ia), __uint_as_float(end_here), R.relv0, R.relv1);
+                relv2[cnt] = R.relv2;
+            }
+            ++cnt;
+        }
+    }
+    return cnt;
+}
 // The per-chunk index ranges of every event-driven vertex of a pass (voices, adsr, sample_multi, sample_lerp), one
 // thread per (task, chunk): the host uploads O(events) records, the O(chunks) tables are made here.
 __global__ void __launch_bounds__(256) k_chunk_ranges(const RangeTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
@@ -106,6 +142,10 @@ __global__ void __launch_bounds__(256) k_chunk_ranges(const RangeTask* __restric
         out.x = first_true(n, [&](uint32_t v) { return R[v].pm_end >= k; });
         out.y = first_true(n, [&](uint32_t v) { return R[v].sm_on > k; });
         if (out.y < out.x) out.y = out.x;
+        uint32_t cnt = 0;                                   // segments the chunk will hold: k_voice_seg_scan turns the counts into offsets
+        for (uint32_t v = out.x; v < out.y; ++v) cnt += voice_segs_in_chunk(R[v], k, T.bl, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
+        T.seg_ptr[kk + 1] = cnt;
+        if (kk == 0) T.seg_ptr[0] = 0;
     } else if (T.kind == RK_ADSR) {
         const AdsrRec* R = reinterpret_cast<const AdsrRec*>(blob + T.recs_off);
         const uint64_t c0 = (uint64_t)(T.chunk0 + kk) * T.bl;
@@ -124,6 +164,42 @@ __global__ void __launch_bounds__(256) k_chunk_ranges(const RangeTask* __restric
         out.x = first_true(n, [&](uint32_t v) { return H[v].frame > c0; }) - 1;                     // entries 0, 1: the carried pair
     }
     T.out[kk] = out;
+}
+
+// counts -> offsets: seg_ptr[0] = 0, seg_ptr[k + 1] = segments of chunks [0, k].  One block per voice task.
+__global__ void __launch_bounds__(1024) k_voice_seg_scan(const RangeTask* __restrict__ tasks) {
+    const RangeTask T = tasks[blockIdx.x];
+    if (T.kind != RK_VOICE) return;
+    __shared__ uint32_t part[1024];
+    const uint32_t n = T.n_chunks, tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t per = (n + nt - 1) / nt;
+    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; ++k) sum += T.seg_ptr[k + 1];
+    part[tid] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < nt; o <<= 1) {               // inclusive Hillis-Steele over per-thread sums
+        const uint32_t v = tid >= o ? part[tid - o] : 0u;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = tid > 0 ? part[tid - 1] : 0u;
+    for (uint32_t k = lo; k < hi; ++k) { run += T.seg_ptr[k + 1]; T.seg_ptr[k + 1] = run; }
+}
+// the segments themselves: one thread per chunk walks the chunk's candidate records in push order
+__global__ void __launch_bounds__(256) k_voice_seg_fill(const RangeTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    const RangeTask T = tasks[blockIdx.y];
+    if (T.kind != RK_VOICE) return;
+    const uint32_t kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= T.n_chunks) return;
+    const VoiceRec* R = reinterpret_cast<const VoiceRec*>(blob + T.recs_off);
+    const float* xenv = reinterpret_cast<const float*>(blob + T.xenv_off);
+    const uint32_t k = T.chunk0 + kk;
+    const Range2 rg = T.out[kk];
+    uint32_t at = T.seg_ptr[kk];
+    for (uint32_t v = rg.x; v < rg.y; ++v)
+        at += voice_segs_in_chunk(R[v], k, T.bl, T.clock, xenv, reinterpret_cast<float4*>(T.segs) + 2 * (size_t)at, (int)T.debug_sine, T.relv2 + at, nullptr);
 }
 
 // ------------------------------------------------------------------------------------ K4: fx
@@ -578,106 +654,47 @@ __device__ __forceinline__ float wavetable_eval(const float* __restrict__ tab, f
     return a + fy * (b - a);
 }
 
-// F = consecutive frames per thread; a block evaluates one tile of TDG_THREADS * F frames of one chunk.
+// F = consecutive frames per thread (register pressure: the three-oscillator synth body runs 2-wide)
 //
-// The chunk's voices are found on the device: the host uploads one VoiceRec per voice (O(events)); the block
-// takes the chunk's candidate range from k_chunk_ranges, and batch by batch (kVoiceBatch records) its threads
-// test one record each, build the (up to two: held part, release part) segments the voice has inside the chunk
-// with their clocks read from the clock table, and compact them in push order into shared memory (warp-shuffle
-// prefix sum).  Then every thread walks the staged segments (same shared address for the whole block: broadcast
-// reads) and sums its frames in that order — f32 summation order is part of the contract.
-static const int kVoiceBatch = 128;                 // candidate records per batch -> at most 256 staged segments
+// No block-wide staging and no barrier after the task load: every thread walks the chunk's segments
+// straight from the device-built segment table (k_voice_seg_fill: 32 B per segment, the same address for the
+// whole block, so each read is one L1-resident broadcast); the per-voice release start values come with it.
+// The barrier-per-batch version spent a quarter of its stall cycles waiting for the two warps that
+// staged and pre-evaluated the segments (profiles/: stall_barrier).
 // LIBM: sin is glibc's sinf restated in double precision (m_sinf_glibc: bit-exact against the reference's libm
 // call); false = the f32 Cody-Waite + minimax evaluation d_sin (<= 2 ulp, tdg_set_oscillator_mode(ctx, 0)).
 template <int KIND, bool EXACT, int F, bool LIBM>
 __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : TDG_SAMPSYN_MINB) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ VoiceTask T;
-    __shared__ float4 s_a[2 * kVoiceBatch];          // hz, vel, env_t, rel_t
-    __shared__ float4 s_b[2 * kVoiceBatch];          // ia, ib, relv0, relv1
-    __shared__ float s_r2[2 * kVoiceBatch];          // relv2
-    __shared__ uint32_t s_wsum[kVoiceBatch / 32];
     load_task(&T, tasks + blockIdx.y);
+    const uint32_t k = blockIdx.x;
+    if (k >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
-    const uint32_t tiles = (bl + TDG_THREADS * F - 1) / (TDG_THREADS * F);
-    const uint32_t kk = blockIdx.x / tiles, tile = blockIdx.x - kk * tiles;
-    if (kk >= T.h.n_chunks) return;
-    const uint32_t k = T.chunk0 + kk;                                            // pass chunk
-    const uint64_t p0 = (uint64_t)kk * bl;
-    const Range2 rg = T.ranges[kk];
-    const VoiceRec* __restrict__ recs = reinterpret_cast<const VoiceRec*>(blob + T.recs_off);
-    const float* __restrict__ xenv = reinterpret_cast<const float*>(blob + T.xenv_off);
+    const uint64_t p0 = (uint64_t)k * bl;
+    const uint32_t s_lo = T.seg_ptr[k], s_hi = T.seg_ptr[k + 1];
+    const float4* __restrict__ gsegs = reinterpret_cast<const float4*>(T.segs);
+    const float* __restrict__ grelv2 = T.relv2;
     const float* __restrict__ tab = T.table;
     const float fsr = T.fsr, rsr = T.rsr;
     const bool vec = (bl % F) == 0;
     const float n_phase_f = (float)T.n_phase, ymax = (float)(T.n_frames - 1);
     const int last_row_off = (int)((T.n_frames - 1) * T.n_phase);
-    const uint32_t i0 = tile * (TDG_THREADS * F) + threadIdx.x * F;
-    const bool active = i0 < bl;
-    float acc[F], time[F], off[F];
+    for (uint32_t base = 0; base < bl; base += TDG_THREADS * F) {
+        const uint32_t i0 = base + threadIdx.x * F;
+        if (i0 >= bl) break;
+        float acc[F], time[F], off[F];
 #pragma unroll
-    for (int j = 0; j < F; ++j) {
-        acc[j] = 0.0f;
-        time[j] = k_div<EXACT>((float)(T.t0 + p0 + i0 + j), fsr, rsr);          // (t + i) as f32 / sr as f32
-        off[j] = k_div<EXACT>((float)(i0 + j), fsr, rsr);                       // i as f32 / sr as f32
-    }
-    for (uint32_t b0 = rg.x; b0 < rg.y; b0 += kVoiceBatch) {
-        // ---- stage: one candidate record per thread -> 0, 1 or 2 segments, compacted in record order
-        uint32_t cnt = 0;
-        float4 a0, b0v, a1, b1v; float r20 = 0.0f, r21 = 0.0f;
-        if (threadIdx.x < kVoiceBatch && b0 + threadIdx.x < rg.y) {
-            const VoiceRec R = recs[b0 + threadIdx.x];
-            if (R.on_chunk <= k && k <= R.end_chunk) {
-                const uint32_t end_here = k == R.end_chunk ? R.end_i : bl;
-                if (k <= R.off_chunk) {                                          // held part (off_chunk == kNever: never released)
-                    const uint32_t ia = k == R.on_chunk ? R.on_i : 0u;
-                    const uint32_t ib = k == R.off_chunk ? R.off_i : end_here;
-                    if (ib > ia) {
-                        const float env_t = KIND == VOICE_DEBUG_SINE ? 0.0f : clock_at(R.envh, k - R.on_chunk, T.clock, bl, xenv);
-                        a0 = make_float4(R.hz, R.vel, env_t, 0.0f);
-                        b0v = make_float4(__uint_as_float(ia), __uint_as_float(ib), 0.0f, 0.0f);
-                        cnt = 1;
-                    }
-                }
-                if (R.off_chunk <= k) {                                          // release part
-                    const uint32_t ia = k == R.off_chunk ? R.off_i : 0u;
-                    if (end_here > ia) {
-                        const float env_t = clock_at(R.envr, k - R.off_chunk, T.clock, bl, xenv);
-                        const float4 a = make_float4(R.hz, R.vel, env_t, R.rel_t);
-                        const float4 bb = make_float4(__uint_as_float(ia), __uint_as_float(end_here), R.relv0, R.relv1);
-                        if (cnt) { a1 = a; b1v = bb; r21 = R.relv2; } else { a0 = a; b0v = bb; r20 = R.relv2; }
-                        ++cnt;
-                    }
-                }
-            }
+        for (int j = 0; j < F; ++j) {
+            acc[j] = 0.0f;
+            time[j] = k_div<EXACT>((float)(T.t0 + p0 + i0 + j), fsr, rsr);      // (t + i) as f32 / sr as f32
+            off[j] = k_div<EXACT>((float)(i0 + j), fsr, rsr);                   // i as f32 / sr as f32
         }
-        uint32_t n_stage = 0;
-        {
-            const uint32_t ln = threadIdx.x & 31, w = threadIdx.x >> 5;
-            uint32_t inc = cnt;
-            if (threadIdx.x < kVoiceBatch) {                                     // whole warps: kVoiceBatch is a multiple of 32
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d); if (ln >= (uint32_t)d) inc += up; }
-                if (ln == 31) s_wsum[w] = inc;
-            }
-            __syncthreads();                                                     // also: the previous batch's readers are done
-            uint32_t base = 0;
-#pragma unroll
-            for (int q = 0; q < kVoiceBatch / 32; ++q) { const uint32_t v = s_wsum[q]; if ((uint32_t)q < w) base += v; n_stage += v; }
-            if (cnt) {
-                const uint32_t pos = base + inc - cnt;
-                s_a[pos] = a0; s_b[pos] = b0v; s_r2[pos] = r20;
-                if (cnt > 1) { s_a[pos + 1] = a1; s_b[pos + 1] = b1v; s_r2[pos + 1] = r21; }
-            }
-            __syncthreads();
-        }
-        // ---- evaluate: every thread walks the staged segments in order
-        if (active) {
 #pragma unroll 1
-        for (uint32_t s = 0; s < n_stage; ++s) {
-            const float4 sb = s_b[s];                                             // ia, ib, relv0, relv1
+        for (uint32_t s = s_lo; s < s_hi; ++s) {
+            const float4 sb = __ldg(gsegs + 2 * (size_t)s + 1);                   // ia, ib, relv0, relv1
             const uint32_t ia = __float_as_uint(sb.x), ib = __float_as_uint(sb.y);
             if (i0 + F <= ia || i0 >= ib) continue;
-            const float4 sa = s_a[s];                                             // hz, vel, env_t, rel_t
+            const float4 sa = __ldg(gsegs + 2 * (size_t)s);                       // hz, vel, env_t, rel_t
             const float hz = sa.x, vel = sa.y, env_t = sa.z, rel_t = sa.w;
             const bool rel = rel_t != 0.0f;
             float smp[F];
@@ -705,7 +722,7 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
                         // release start value => the values just computed for oscillator 1 are oscillator 2's
                         const bool reuse = o == 2 && T.env12_same && T.vol[1] > 0.0f;
                         if (!reuse)
-                            flat = rel ? k_apply_r_n<EXACT, F>(T.env[o], et, o == 0 ? sb.z : o == 1 ? sb.w : s_r2[s], e)
+                            flat = rel ? k_apply_r_n<EXACT, F>(T.env[o], et, o == 0 ? sb.z : o == 1 ? sb.w : __ldg(grelv2 + s), e)
                                        : k_apply_ads_n<EXACT, F>(T.env[o], et, e);
                         // envelope sitting at exactly 0 (a percussive oscillator after its decay): every term is
                         // shape*vel*0*vol = +-0 for finite factors, and adding +-0 to the running sum changes nothing
@@ -736,22 +753,21 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
             for (int j = 0; j < F; ++j)
                 if (i0 + j >= ia && i0 + j < ib) acc[j] += smp[j];
         }
-        }
-    }
-    if (active) {
-        float l[F], r[F];
+        {
+            float l[F], r[F];
 #pragma unroll
-        for (int j = 0; j < F; ++j) { l[j] = acc[j]; r[j] = acc[j]; apply_pg(l[j], r[j], T.h.pg); }
-        float* ol = T.h.out_l + p0 + i0; float* orr = T.h.out_r + p0 + i0;
-        if (vec && F == 4) {
-            *reinterpret_cast<float4*>(ol) = make_float4(l[0], l[1], l[2], l[3]);
-            *reinterpret_cast<float4*>(orr) = make_float4(r[0], r[1], r[2], r[3]);
-        } else if (vec && F == 2) {
-            *reinterpret_cast<float2*>(ol) = make_float2(l[0], l[1]);
-            *reinterpret_cast<float2*>(orr) = make_float2(r[0], r[1]);
-        } else {
+            for (int j = 0; j < F; ++j) { l[j] = acc[j]; r[j] = acc[j]; apply_pg(l[j], r[j], T.h.pg); }
+            float* ol = T.h.out_l + p0 + i0; float* orr = T.h.out_r + p0 + i0;
+            if (vec && F == 4) {
+                *reinterpret_cast<float4*>(ol) = make_float4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<float4*>(orr) = make_float4(r[0], r[1], r[2], r[3]);
+            } else if (vec && F == 2) {
+                *reinterpret_cast<float2*>(ol) = make_float2(l[0], l[1]);
+                *reinterpret_cast<float2*>(orr) = make_float2(r[0], r[1]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < F; ++j) if (i0 + j < bl) { ol[j] = l[j]; orr[j] = r[j]; }
+                for (int j = 0; j < F; ++j) if (i0 + j < bl) { ol[j] = l[j]; orr[j] = r[j]; }
+            }
         }
     }
 }
@@ -1196,9 +1212,13 @@ cudaError_t launch_env_table(float* clock, uint32_t bl, uint32_t row0, uint32_t 
     k_env_table<<<(bl + 255) / 256, 256, 0, s>>>(clock, bl, row0, depth, fsr);
     return cudaGetLastError();
 }
-cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s) {
+cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, bool any_voice, const uint8_t* blob, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     k_chunk_ranges<<<grid2((max_chunks + 255) / 256, n), 256, 0, s>>>(t, blob);
+    if (any_voice) {                                     // voices: counts -> offsets -> segments
+        k_voice_seg_scan<<<n, 1024, 0, s>>>(t);
+        k_voice_seg_fill<<<grid2((max_chunks + 255) / 256, n), 256, 0, s>>>(t, blob);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s) {

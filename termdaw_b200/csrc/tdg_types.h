@@ -81,13 +81,22 @@ struct LerpHit { int64_t frame, pos_origin, cd_origin; float vel, pad; }; // see
 
 // per-chunk index ranges into the records above, written by k_chunk_ranges (one thread per chunk, binary searches)
 struct alignas(8) Range2 { uint32_t x, y; };
+struct alignas(16) F4 { float x, y, z, w; };        // float4 without the CUDA headers (this file is plain C++ too)
 enum RangeKind : uint32_t { RK_VOICE = 0, RK_ADSR = 1, RK_MULTI = 2, RK_LERP = 3 };
 struct RangeTask {
     uint32_t kind, n_chunks, chunk0, bl;
     uint64_t recs_off;              // blob: VoiceRec[] / AdsrRec[] / MultiHit[] / LerpHit[]
     uint32_t n_recs, pad;
     int64_t len;                    // RK_MULTI: sample length
-    Range2* out;                     // [n_chunks] x = lo, y = hi (RK_ADSR: first, count; RK_LERP: x = base)
+    Range2* out;                    // [n_chunks] x = lo, y = hi (RK_ADSR: first, count; RK_LERP: x = base)
+    // RK_VOICE: the per-chunk segment table k_voice walks, built on the device from the records
+    // (k_chunk_ranges counts, k_voice_seg_scan turns counts into offsets, k_voice_seg_fill writes the segments)
+    uint32_t* seg_ptr;              // [n_chunks + 1]
+    F4* segs;                       // [capacity][2]: (hz, vel, env_t, rel_t), (ia, ib, relv0, relv1)
+    float* relv2;                   // [capacity]
+    const float* clock;             // clock table of this (sr, bl)
+    uint64_t xenv_off;              // blob: explicit clocks
+    uint32_t debug_sine, pad2;
 };
 
 // ---- staged (shared-memory) per-chunk forms ------------------------------------------------------------
@@ -161,11 +170,10 @@ struct VoiceTask {
     uint32_t kind, sr;
     float fsr, rsr;         // sr as f32 and its IEEE reciprocal
     uint64_t t0;            // graph time of pass frame 0 (time = (t0 + p) as f32 / sr as f32)
-    uint64_t recs_off;      // blob: VoiceRec[n_recs] in push order
-    uint64_t xenv_off;      // blob: float[] explicit clocks (voices carried in from an earlier pass)
-    const Range2* ranges;    // device scratch [n_chunks]: candidate records [lo, hi) of every chunk (k_chunk_ranges)
-    const float* clock;     // [depth][bl] clock table of this (sr, bl)
-    uint32_t n_recs, chunk0; // chunk0: pass chunk of block 0
+    // per-chunk segment table in device scratch, built there from the VoiceRec records (RangeTask)
+    const uint32_t* seg_ptr; // [n_chunks + 1]
+    const F4* segs;          // [][2]: (hz, vel, env_t, rel_t), (ia, ib, relv0, relv1) in push order
+    const float* relv2;      // parallel: the release start value of oscillator 2 (Synth)
     // Synth (extensions.rs:44-50); shape constants of synth.rs:22-29 evaluated on the host:
     // sq_iz = 1/z, tf_add = (1-z)/2, tf_mul = 2/(1+z)
     float vol[3];           // square, topflat, triangle volumes

@@ -57,7 +57,7 @@ def test_bench_line_has_every_contract_key(monkeypatch, capfd):
     real_tensor = torch.tensor
     monkeypatch.setattr(torch, "tensor", lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items() if k != "device"}))
     monkeypatch.setattr(bench, "BatchRunner", _FakeRunner)
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "3", "--cpu-sample", "1", "--scale", "0.02"])
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "3", "--cpu-sample", "1", "--scale", "0.02", "--no-secondary"])
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         monkeypatch.delenv(k, raising=False)
     bench.main()
@@ -123,7 +123,7 @@ def test_bench_real_runner_on_the_emulated_library(monkeypatch, capfd, tmp_path)
     monkeypatch.setattr(torch, "tensor", lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items() if k != "device"}))
     monkeypatch.setattr(torch, "empty", lambda *a, **kw: real_empty(*a, **{k: v for k, v in kw.items() if k != "pin_memory"}))
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "1", "--warmup", "1", "--projects", "2", "--scale", "0.02",
-                                      "--cpu-sample", "1"])
+                                      "--cpu-sample", "1", "--secondary-scale", "0.001", "--secondary-steps", "1"])
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         monkeypatch.delenv(k, raising=False)
     bench.main()
@@ -131,6 +131,14 @@ def test_bench_real_runner_on_the_emulated_library(monkeypatch, capfd, tmp_path)
     assert len(out) == 1, out
     d = json.loads(out[0])
     assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
+    # the secondary block: configs[3] (time-sharded runner, one rank here) and configs[2] (512 voices) really ran
+    sec = d["secondary"]
+    assert set(sec) == {"c3", "c4"}
+    for wl in ("c3", "c4"):
+        assert sec[wl]["value"] > 0 and sec[wl]["e2e"]["value"] > 0 and sec[wl]["gpu_launches"] > 0, wl
+        assert sec[wl]["e2e"]["d2h_bytes_per_step"] > 0 and sec[wl]["host_plan_ms_per_step"] > 0
+    assert sec["c4"]["scaling"] == "strong" and sec["c4"]["nccl_exchange_rounds_per_step"] == 0       # one rank: nothing to exchange
+    assert sec["c3"]["voice_frames_per_s"] > 0 and sec["c3"]["voice_frames_per_step"] > 2 * 500 * 0.5 * 48000 * 0.6
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 2 * 29 * 1024 * 4
     assert d["config"]["projects_per_gpu"] == 2
     assert d["config"]["pass_reuse"]["vertices_read_from_scan_per_step"] > 0
