@@ -2320,8 +2320,22 @@ int tdg_add_sampsyn(tdg_ctx* h, float gain, float angle, int floww, const float*
         for (uint32_t p = 0; p < 1024; ++p) data[p] = sinf(6.2831855f * ((float)p / 1024.0f));
     }
     cudaSetDevice(c->eng->device);
-    CU(cudaMalloc(&tb.data, data.size() * 4));
-    CU(cudaMemcpy(tb.data, data.data(), data.size() * 4, cudaMemcpyHostToDevice));
+    // device layout (kernels.cu wavetable_eval): pairs[j][i] = (tab[j][i], tab[min(j + 1, last)][i]), i in [0, n_phase]
+    // with column n_phase repeating column 0: the four corners of a bilinear cell are two adjacent 8-byte loads
+    {
+        const size_t nf = tb.n_frames, np = tb.n_phase, stride = np + 1;
+        std::vector<float> pairs(nf * stride * 2);
+        for (size_t j = 0; j < nf; ++j) {
+            const size_t jn = std::min(j + 1, nf - 1);
+            for (size_t i = 0; i <= np; ++i) {
+                const size_t ii = i == np ? 0 : i;
+                pairs[(j * stride + i) * 2] = data[j * np + ii];
+                pairs[(j * stride + i) * 2 + 1] = data[jn * np + ii];
+            }
+        }
+        CU(cudaMalloc(&tb.data, pairs.size() * 4));
+        CU(cudaMemcpy(tb.data, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice));
+    }
     c->tables.push_back(tb);
     v.table = (int)c->tables.size() - 1;
     return add_vertex(c, v, gain, angle, 0.0f);

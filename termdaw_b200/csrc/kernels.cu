@@ -630,28 +630,32 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
 #endif
 
 // wavetable_act_state as DEFINED by the oracle (sampsyn is not vendored): bilinear in (time, phase).
-// floor / truncation use the conversion pipe (FRND / F2I / I2F: one issue slot each, and that pipe is
-// otherwise idle here); the table is read through the read-only path and stays L1 resident.
-__device__ __forceinline__ float wavetable_eval(const float* __restrict__ tab, float n_phase_f, int n_phase, float ymax,
-                                                int last_row_off, float fps, float hz, float t) {
+// Device layout of the table (tdg_add_sampsyn): pairs[j][i] = (tab[j][i], tab[min(j + 1, last)][i]) for
+// i in [0, n_phase], column n_phase repeating column 0.  The four corners of a cell are then two 8-byte loads at
+// consecutive addresses from ONE computed address (the phase wrap and the last-row clamp are in the layout), where
+// the row-major table needed four address computations, a wrap select and a row clamp per voice-frame.
+// floor / truncation use the conversion pipe (FRND / F2I / I2F); the table is read through the read-only path and
+// stays L1 resident.  Same values, same f32 operations in the same order as the oracle's definition.
+__device__ __forceinline__ float wavetable_eval(const float2* __restrict__ row, float n_phase_f, int n_phase, float fy, float hz, float t) {
     float ph = t * hz;
     ph = ph - floorf(ph);
     const float x = ph * n_phase_f;
     int i0 = __float2int_rz(x);
     if (i0 >= n_phase) i0 = n_phase - 1;
     const float fx = x - (float)i0;
-    int i1 = i0 + 1; if (i1 >= n_phase) i1 = 0;
+    const float2 c0 = __ldg(row + i0), c1 = __ldg(row + i0 + 1);          // (a0, b0), (a1, b1)
+    const float a = c0.x + fx * (c1.x - c0.x);
+    const float b = c0.y + fx * (c1.y - c0.y);
+    return a + fy * (b - a);
+}
+// the time axis of the table for one frame: row j0 = trunc(clamp(t * fps, 0, ymax)) and the weight towards row j0 + 1
+__device__ __forceinline__ int wavetable_row(float fps, float ymax, float t, float* fy) {
     float y = t * fps;
     if (!(y > 0.0f)) y = 0.0f;
     if (y > ymax) y = ymax;
     const int j0 = __float2int_rz(y);
-    const float fy = y - (float)j0;
-    const int r0 = j0 * n_phase;
-    const int r1 = min(r0 + n_phase, last_row_off);
-    const float a0 = __ldg(tab + r0 + i0), a1 = __ldg(tab + r0 + i1), b0 = __ldg(tab + r1 + i0), b1 = __ldg(tab + r1 + i1);
-    const float a = a0 + fx * (a1 - a0);
-    const float b = b0 + fx * (b1 - b0);
-    return a + fy * (b - a);
+    *fy = y - (float)j0;
+    return j0;
 }
 
 // F = consecutive frames per thread (register pressure: the three-oscillator synth body runs 2-wide)
@@ -674,11 +678,11 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
     const uint32_t s_lo = T.seg_ptr[k], s_hi = T.seg_ptr[k + 1];
     const float4* __restrict__ gsegs = reinterpret_cast<const float4*>(T.segs);
     const float* __restrict__ grelv2 = T.relv2;
-    const float* __restrict__ tab = T.table;
+    const float2* __restrict__ tab = reinterpret_cast<const float2*>(T.table);
     const float fsr = T.fsr, rsr = T.rsr;
     const bool vec = (bl % F) == 0;
     const float n_phase_f = (float)T.n_phase, ymax = (float)(T.n_frames - 1);
-    const int last_row_off = (int)((T.n_frames - 1) * T.n_phase);
+    const int row_stride = (int)T.n_phase + 1;
     for (uint32_t base = 0; base < bl; base += TDG_THREADS * F) {
         const uint32_t i0 = base + threadIdx.x * F;
         if (i0 >= bl) break;
@@ -744,14 +748,21 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
                     if (rel) k_apply_r_n<EXACT, F>(T.env[0], et, sb.z, e); else k_apply_ads_n<EXACT, F>(T.env[0], et, e);
 #pragma unroll
                     for (int j = 0; j < F; ++j) {
+                        float fy;
+                        const int jr = wavetable_row(T.fps, ymax, et[j] + rel_t, &fy);
                         const float g = vel * e[j] * T.amp_mul;
-                        smp[j] = wavetable_eval(tab, n_phase_f, (int)T.n_phase, ymax, last_row_off, T.fps, hz, et[j] + rel_t) * g;
+                        smp[j] = wavetable_eval(tab + (size_t)jr * row_stride, n_phase_f, (int)T.n_phase, fy, hz, et[j] + rel_t) * g;
                     }
                 }
             }
+            if (ia <= i0 && i0 + F <= ib) {                                    // the segment covers the whole run (nearly always)
 #pragma unroll
-            for (int j = 0; j < F; ++j)
-                if (i0 + j >= ia && i0 + j < ib) acc[j] += smp[j];
+                for (int j = 0; j < F; ++j) acc[j] += smp[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < F; ++j)
+                    if (i0 + j >= ia && i0 + j < ib) acc[j] += smp[j];
+            }
         }
         {
             float l[F], r[F];

@@ -87,22 +87,21 @@ TDG_HD uint32_t m_f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 // quadrant sign (the reference multiplies x by +-1.0 and picks the table with negated cosine coefficients: both
 // polynomials are exactly odd in that sign under round-to-nearest, so negating the result is the same value)
 TDG_HD float m_sinf_poly(double x, double x2, int n, bool neg) {
-    double r;
-    if ((n & 1) == 0) {
-        const double x3 = x * x2;
-        const double s1 = fma(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
-        const double x7 = x3 * x2;
-        const double s = fma(x3, -0x1.555545995a603p-3, x);
-        r = fma(x7, s1, s);
-    } else {
-        const double x4 = x2 * x2;
-        const double c2 = fma(x2, 0x1.99343027bf8c3p-16, -0x1.6c087e89a359dp-10);
-        const double c1 = fma(x2, -0x1.ffffffd0c621cp-2, 1.0);
-        const double x6 = x4 * x2;
-        const double c = fma(x4, 0x1.55553e1068f19p-5, c1);
-        r = fma(x6, c2, c);
-    }
-    const float f = (float)r;
+    // both polynomials in straight-line code, the quadrant picks the result: neighbouring frames of a warp sit in
+    // different quadrants, so a branch here is always divergent (both sides executed plus the reconvergence
+    // overhead); the operations of the side that is kept are exactly the reference's
+    const double x3 = x * x2;
+    const double s1 = fma(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+    const double x7 = x3 * x2;
+    const double s = fma(x3, -0x1.555545995a603p-3, x);
+    const double rs = fma(x7, s1, s);
+    const double x4 = x2 * x2;
+    const double c2 = fma(x2, 0x1.99343027bf8c3p-16, -0x1.6c087e89a359dp-10);
+    const double c1 = fma(x2, -0x1.ffffffd0c621cp-2, 1.0);
+    const double x6 = x4 * x2;
+    const double c = fma(x4, 0x1.55553e1068f19p-5, c1);
+    const double rc = fma(x6, c2, c);
+    const float f = (float)((n & 1) ? rc : rs);
     return neg ? -f : f;
 }
 TDG_HD float m_sinf_glibc(float y) {
