@@ -565,17 +565,33 @@ def main():
         # (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over one step at 64 projects,
         # beside the algorithmic bytes of the same launches) gives the traffic / algorithmic ratio of the
         # kernel; scaled to this run's algorithmic bytes per launch, like `achieved`
+        # profiles/ncu_classes.json (tools/ncu_class_summary.py over an `ncu --set full` capture of bench.py at 64
+        # projects; its `_label` names the commit it was taken on): per kernel class the measured DRAM bytes / the
+        # algorithmic bytes of the same launches (`ratio`), the DRAM-traffic fraction of the HBM peak and the
+        # issue-slot / pipe utilisations.  Scaled to this run's algorithmic bytes per launch, like `achieved`.
         traffic = traffic_detail = None
+        ncu = {}
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            traffic_detail = tr.get(dom)
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_classes.json")))
+            traffic_detail = ncu.get(dom)
             if traffic_detail and traffic_detail.get("ratio") is not None and kstats[dom]["launches"]:
                 traffic = traffic_detail["ratio"] * kstats[dom]["bytes"] / kstats[dom]["launches"]
         except (OSError, ValueError, KeyError):
             pass
-        # the voice kernels are bound by FP32 issue slots, not HBM: ncu's issue-slot utilisation of the committed
-        # capture (profiles/r01_s6_ncu_full_digest.md) is the meaningful fraction for them
-        issue_pct = {"k_voice<synth>": 86.3, "k_voice<sampsyn>": 77.3}.get(dom)
+        issue_pct = (ncu.get(dom) or {}).get("issue_pct")
+
+        def per_kernel_entry(k, v):
+            e = {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] // args.steps,
+                 "achieved_gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 else 0.0,
+                 "frac": (v["bytes"] / (v["ms"] / 1e3) / 1e9 / peak) if v["ms"] > 0 else 0.0}
+            n = ncu.get(k)
+            if n and v["ms"] > 0:
+                # the fraction of the HBM peak from DRAM traffic (a gather whose source sits in L2 must not read as
+                # > 1.0 of HBM): algorithmic fraction x measured DRAM / algorithmic ratio of the class
+                if n.get("ratio") is not None:
+                    e["dram_frac"] = e["frac"] * n["ratio"]
+                e["issue_slots_pct_ncu"] = n.get("issue_pct")
+            return e
         line = {
             "metric": "rendered frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
@@ -611,12 +627,11 @@ def main():
                          "traffic_source": traffic_detail,
                          "issue_slot_utilisation_pct_ncu": issue_pct, "peak_source": peak_src,
                          "share_of_step": kstats[dom]["ms"] / dev_ms,
-                         "note": "k_voice<*> kernels are FP32-issue bound, not HBM bound (DESIGN.md §5): their HBM "
-                                 "fraction is reported as the contract asks; every streaming kernel is listed in per_kernel",
-                         "per_kernel": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] // args.steps,
-                                            "achieved_gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 else 0.0,
-                                            "frac": (v["bytes"] / (v["ms"] / 1e3) / 1e9 / peak) if v["ms"] > 0 else 0.0}
-                                        for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}},
+                         "note": "k_voice<*> kernels are instruction-issue bound, not HBM bound (DESIGN.md §5): their HBM "
+                                 "fraction is reported as the contract asks; every streaming kernel is listed in per_kernel "
+                                 "(frac = algorithmic bytes / time / peak; dram_frac = the same from measured DRAM bytes)",
+                         "ncu_capture": ncu.get("_label"),
+                         "per_kernel": {k: per_kernel_entry(k, v) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}},
         }
         if world == 1 and not args.no_cpu_baseline:
             ccfgs, sample = cpu_sample_cfgs(args)

@@ -1119,8 +1119,10 @@ static int pass_plan(PassJob& J) {
     for (const Item& it : items) {
         PassReq& r = reqs[it.ri];
         const HVertex& hv = r.c->verts[it.v];
-        if (hv.kind != K_DEBUG_SINE && hv.kind != K_SYNTH && hv.kind != K_SAMPSYN) continue;
-        const uint64_t cap = std::max<uint64_t>(vplans_a[it.ri][it.v].seg_cap, 1);
+        if (hv.kind != K_DEBUG_SINE && hv.kind != K_SYNTH && hv.kind != K_SAMPSYN && hv.kind != K_ADSR) continue;
+        // adsr: one state per chunk plus one per state change inside a chunk (AdsrSeg is 32 B like a voice segment)
+        const uint64_t cap = hv.kind == K_ADSR ? r.emit_n + vplans_a[it.ri][it.v].arecs.size() + 1
+                                                : std::max<uint64_t>(vplans_a[it.ri][it.v].seg_cap, 1);
         r.seg_cap[it.v] = cap;
         r.seg_off[it.v] = (int64_t)bump.alloc(align_up((r.emit_n + 1) * 4, 16) + cap * 32 + cap * 4 + 16);
     }
@@ -1291,12 +1293,20 @@ static int pass_plan(PassJob& J) {
                         FxTask t = fx_task(FX_ADSR);
                         t.conf = make_adsr_k(hv.adsr); t.wet = hv.wet; t.use_off = hv.use_off; t.use_max = hv.use_max;
                         if (t.conf.exotic || adsr_duration_exotic(t.fsr)) LT.fx_adsr_exact = true;
-                        t.recs_off = B.alloc(VP.arecs.size() * sizeof(AdsrRec));
-                        memcpy(B.at<uint8_t>(t.recs_off), VP.arecs.data(), VP.arecs.size() * sizeof(AdsrRec));
-                        t.xenv_off = B.alloc(std::max<size_t>(VP.xenv.size(), 1) * 4);
-                        memcpy(B.at<uint8_t>(t.xenv_off), VP.xenv.data(), VP.xenv.size() * 4);
-                        t.n_recs = (uint32_t)VP.arecs.size(); t.chunk0 = (uint32_t)r.emit0; t.clock = clock;
-                        t.ranges = range_task(RK_ADSR, v, t.recs_off, VP.arecs.size(), 0);
+                        const uint64_t recs_off = B.alloc(VP.arecs.size() * sizeof(AdsrRec));
+                        memcpy(B.at<uint8_t>(recs_off), VP.arecs.data(), VP.arecs.size() * sizeof(AdsrRec));
+                        const uint64_t xenv_off = B.alloc(std::max<size_t>(VP.xenv.size(), 1) * 4);
+                        memcpy(B.at<uint8_t>(xenv_off), VP.xenv.data(), VP.xenv.size() * 4);
+                        {
+                            uint8_t* sb = W + r.seg_off[v];
+                            uint32_t* seg_ptr = reinterpret_cast<uint32_t*>(sb);
+                            F4* segs = reinterpret_cast<F4*>(sb + align_up((r.emit_n + 1) * 4, 16));
+                            (void)range_task(RK_ADSR, v, recs_off, VP.arecs.size(), 0);
+                            RangeTask& rt = F.ranges.back();
+                            rt.seg_ptr = seg_ptr; rt.segs = segs; rt.relv2 = nullptr; rt.clock = clock; rt.xenv_off = xenv_off;
+                            F.any_voice = true;
+                            t.seg_ptr = seg_ptr; t.segs = reinterpret_cast<const AdsrSeg*>(segs);
+                        }
                         LT.fx_adsr.v.push_back(t); LT.fx_adsr.max_chunks = std::max(LT.fx_adsr.max_chunks, nch);
                         LT.fx_adsr.bytes += io_bytes + VPs[v].arecs.size() * sizeof(AdsrRec);
                     }
@@ -1514,7 +1524,7 @@ static int pass_plan(PassJob& J) {
             for (size_t L = 0; L < F.levels.size(); ++L) {
                 LevelTasks& S = F.levels[L]; LevelTasks& Dst = levels[L];
                 for (FxTask& t : S.fx.v) t.in_off += b;
-                for (FxTask& t : S.fx_adsr.v) { t.in_off += b; t.recs_off += b; t.xenv_off += b; }
+                for (FxTask& t : S.fx_adsr.v) t.in_off += b;
                 for (FxTask& t : S.fx_norm.v) t.in_off += b;
                 for (MultiTask& t : S.multi.v) t.hits_off += b;
                 for (LerpTask& t : S.lerp.v) t.hits_off += b;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_chunk_ranges(const RangeTask* __restric
         out.x = first_true(n, [&](uint32_t v) { return R[v].pm_end >= k; });
         out.y = first_true(n, [&](uint32_t v) { return R[v].sm_on > k; });
         if (out.y < out.x) out.y = out.x;
-        uint32_t cnt = 0;                                   // segments the chunk will hold: k_voice_seg_scan turns the counts into offsets
+        uint32_t cnt = 0;                                   // segments the chunk will hold: k_seg_scan turns the counts into offsets
         for (uint32_t v = out.x; v < out.y; ++v) cnt += voice_segs_in_chunk(R[v], k, T.bl, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
         T.seg_ptr[kk + 1] = cnt;
         if (kk == 0) T.seg_ptr[0] = 0;
@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(256) k_chunk_ranges(const RangeTask* __restric
         const uint32_t a = first_true(n, [&](uint32_t v) { return R[v].start > c0; });            // record 0 starts at frame 0
         const uint32_t b = first_true(n, [&](uint32_t v) { return R[v].start >= c0 + T.bl; });
         out.x = a - 1; out.y = b - (a - 1);
+        T.seg_ptr[kk + 1] = out.y;                          // one envelope state per record active in the chunk
+        if (kk == 0) T.seg_ptr[0] = 0;
     } else if (T.kind == RK_MULTI) {
         const MultiHit* H = reinterpret_cast<const MultiHit*>(blob + T.recs_off);
         const int64_t c0 = (int64_t)kk * T.bl;                                                      // hits are relative to the emitted range
@@ -167,9 +169,9 @@ __global__ void __launch_bounds__(256) k_chunk_ranges(const RangeTask* __restric
 }
 
 // counts -> offsets: seg_ptr[0] = 0, seg_ptr[k + 1] = segments of chunks [0, k].  One block per voice task.
-__global__ void __launch_bounds__(1024) k_voice_seg_scan(const RangeTask* __restrict__ tasks) {
+__global__ void __launch_bounds__(1024) k_seg_scan(const RangeTask* __restrict__ tasks) {
     const RangeTask T = tasks[blockIdx.x];
-    if (T.kind != RK_VOICE) return;
+    if (T.kind != RK_VOICE && T.kind != RK_ADSR) return;
     __shared__ uint32_t part[1024];
     const uint32_t n = T.n_chunks, tid = threadIdx.x, nt = blockDim.x;
     const uint32_t per = (n + nt - 1) / nt;
@@ -188,16 +190,30 @@ __global__ void __launch_bounds__(1024) k_voice_seg_scan(const RangeTask* __rest
     for (uint32_t k = lo; k < hi; ++k) { run += T.seg_ptr[k + 1]; T.seg_ptr[k + 1] = run; }
 }
 // the segments themselves: one thread per chunk walks the chunk's candidate records in push order
-__global__ void __launch_bounds__(256) k_voice_seg_fill(const RangeTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(256) k_seg_fill(const RangeTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     const RangeTask T = tasks[blockIdx.y];
-    if (T.kind != RK_VOICE) return;
+    if (T.kind != RK_VOICE && T.kind != RK_ADSR) return;
     const uint32_t kk = blockIdx.x * blockDim.x + threadIdx.x;
     if (kk >= T.n_chunks) return;
-    const VoiceRec* R = reinterpret_cast<const VoiceRec*>(blob + T.recs_off);
     const float* xenv = reinterpret_cast<const float*>(blob + T.xenv_off);
     const uint32_t k = T.chunk0 + kk;
     const Range2 rg = T.out[kk];
     uint32_t at = T.seg_ptr[kk];
+    if (T.kind == RK_ADSR) {                            // Adsr vertex: the states the chunk passes through, clocks looked up
+        const AdsrRec* A = reinterpret_cast<const AdsrRec*>(blob + T.recs_off) + rg.x;
+        AdsrSeg* out = reinterpret_cast<AdsrSeg*>(T.segs) + at;
+        const uint64_t c0 = (uint64_t)k * T.bl;
+        for (uint32_t q = 0; q < rg.y; ++q) {
+            const AdsrRec R = A[q];
+            AdsrSeg sg;
+            sg.ia = R.start > c0 ? (uint32_t)(R.start - c0) : 0u; sg.flags = R.flags;
+            sg.pt = clock_at(R.p_src, k - R.p_chunk, T.clock, T.bl, xenv); sg.pv = R.pv; sg.pr = R.pr;
+            sg.gt = clock_at(R.g_src, k - R.g_chunk, T.clock, T.bl, xenv); sg.gv = R.gv; sg.gr = R.gr;
+            out[q] = sg;
+        }
+        return;
+    }
+    const VoiceRec* R = reinterpret_cast<const VoiceRec*>(blob + T.recs_off);
     for (uint32_t v = rg.x; v < rg.y; ++v)
         at += voice_segs_in_chunk(R[v], k, T.bl, T.clock, xenv, reinterpret_cast<float4*>(T.segs) + 2 * (size_t)at, (int)T.debug_sine, T.relv2 + at, nullptr);
 }
@@ -229,7 +245,6 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
 template <int MODE, bool VEC, bool EXACT>
 __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ FxTask T;
-    __shared__ AdsrSeg s_seg[MODE == FX_ADSR ? TDG_FX_SEGS : 1];
     load_task(&T, tasks + blockIdx.y);
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
     const uint32_t k = blockIdx.x;
@@ -268,35 +283,22 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB :
     bool have = false;
     uint32_t n_seg = 0;
     float maxmul = 0.0f, minmul = 0.0f;
-    const AdsrRec* recs = nullptr; const float* xenv = nullptr; uint32_t kabs = 0; uint64_t c0 = 0;
-    auto build_seg = [&](uint32_t q) {
-        const AdsrRec R = recs[q];
+    const AdsrSeg* __restrict__ segs = nullptr;
+    // state q of the chunk, straight from the device-built table (the same address for the whole block: one
+    // L1-resident broadcast per read, no staging and no barrier: the block's warps never wait for each other)
+    auto seg_ia = [&](uint32_t q) -> uint32_t { return __ldg(&segs[q].ia); };
+    auto seg_get = [&](uint32_t q) -> AdsrSeg {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(segs + q)), b = __ldg(reinterpret_cast<const float4*>(segs + q) + 1);
         AdsrSeg sg;
-        sg.ia = R.start > c0 ? (uint32_t)(R.start - c0) : 0u; sg.flags = R.flags;
-        sg.pt = clock_at(R.p_src, kabs - R.p_chunk, T.clock, bl, xenv); sg.pv = R.pv; sg.pr = R.pr;
-        sg.gt = clock_at(R.g_src, kabs - R.g_chunk, T.clock, bl, xenv); sg.gv = R.gv; sg.gr = R.gr;
+        sg.ia = __float_as_uint(a.x); sg.flags = __float_as_uint(a.y); sg.pt = a.z; sg.pv = a.w; sg.pr = b.x; sg.gt = b.y; sg.gv = b.z; sg.gr = b.w;
         return sg;
     };
-    // state s of the chunk: staged in shared memory; a chunk with more state changes than the staging area holds
-    // (a hit every few frames) reads the rest straight from the records
-    auto seg_ia = [&](uint32_t q) -> uint32_t {
-        if (q < (uint32_t)TDG_FX_SEGS) return s_seg[q].ia;
-        const uint64_t st = recs[q].start; return st > c0 ? (uint32_t)(st - c0) : 0u;
-    };
-    auto seg_get = [&](uint32_t q) -> AdsrSeg { if (q < (uint32_t)TDG_FX_SEGS) return s_seg[q]; return build_seg(q); };
     if (MODE == FX_ADSR) {
-        // the chunk's envelope states are built from the event records (index range from k_chunk_ranges, clocks
-        // from the table) into shared memory while the audio loads of the first run are already in flight
-        const Range2 rg = T.ranges[k];
-        n_seg = rg.y;
+        const uint32_t s_lo = T.seg_ptr[k];
+        n_seg = T.seg_ptr[k + 1] - s_lo;
+        segs = T.segs + s_lo;
         if (i_first < bl) { load_sum(i_first, l, r); have = true; }
         maxmul = T.use_max ? 1.0f : 0.0f; minmul = 1.0f - maxmul;
-        recs = reinterpret_cast<const AdsrRec*>(blob + T.recs_off) + rg.x;
-        xenv = reinterpret_cast<const float*>(blob + T.xenv_off);
-        kabs = T.chunk0 + k;
-        c0 = (uint64_t)kabs * bl;
-        for (uint32_t q = threadIdx.x; q < n_seg && q < (uint32_t)TDG_FX_SEGS; q += TDG_THREADS) s_seg[q] = build_seg(q);
-        __syncthreads();
     }
     float peak = 0.0f;
     for (uint32_t i = i_first; i < bl; i += TDG_THREADS * 4) {
@@ -661,7 +663,7 @@ __device__ __forceinline__ int wavetable_row(float fps, float ymax, float t, flo
 // F = consecutive frames per thread (register pressure: the three-oscillator synth body runs 2-wide)
 //
 // No block-wide staging and no barrier after the task load: every thread walks the chunk's segments
-// straight from the device-built segment table (k_voice_seg_fill: 32 B per segment, the same address for the
+// straight from the device-built segment table (k_seg_fill: 32 B per segment, the same address for the
 // whole block, so each read is one L1-resident broadcast); the per-voice release start values come with it.
 // The barrier-per-batch version spent a quarter of its stall cycles waiting for the two warps that
 // staged and pre-evaluated the segments (profiles/: stall_barrier).
@@ -1223,12 +1225,12 @@ cudaError_t launch_env_table(float* clock, uint32_t bl, uint32_t row0, uint32_t 
     k_env_table<<<(bl + 255) / 256, 256, 0, s>>>(clock, bl, row0, depth, fsr);
     return cudaGetLastError();
 }
-cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, bool any_voice, const uint8_t* blob, cudaStream_t s) {
+cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, bool any_segs, const uint8_t* blob, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     k_chunk_ranges<<<grid2((max_chunks + 255) / 256, n), 256, 0, s>>>(t, blob);
-    if (any_voice) {                                     // voices: counts -> offsets -> segments
-        k_voice_seg_scan<<<n, 1024, 0, s>>>(t);
-        k_voice_seg_fill<<<grid2((max_chunks + 255) / 256, n), 256, 0, s>>>(t, blob);
+    if (any_segs) {                                      // voices / adsr: counts -> offsets -> segments
+        k_seg_scan<<<n, 1024, 0, s>>>(t);
+        k_seg_fill<<<grid2((max_chunks + 255) / 256, n), 256, 0, s>>>(t, blob);
     }
     return cudaGetLastError();
 }

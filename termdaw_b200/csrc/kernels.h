@@ -10,7 +10,7 @@ namespace tdg {
 cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, const uint8_t* blob, cudaStream_t s);
 // clock table rows [row0, depth) of one (sr, bl); per-chunk index ranges of every event-driven vertex of a pass
 cudaError_t launch_env_table(float* clock, uint32_t bl, uint32_t row0, uint32_t depth, float fsr, cudaStream_t s);
-cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, bool any_voice, const uint8_t* blob, cudaStream_t s);   // + the voice segment tables
+cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, bool any_segs, const uint8_t* blob, cudaStream_t s);   // + the voice / adsr segment tables
 cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s);
 cudaError_t launch_norm_total(const NormPrefixTask* t, uint32_t n, float* reduce_buf, cudaStream_t s);
 cudaError_t launch_bp_total(const BpTask* t, uint32_t n, const uint8_t* blob, cudaStream_t s);

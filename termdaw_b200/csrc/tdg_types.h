@@ -89,17 +89,17 @@ struct RangeTask {
     uint32_t n_recs, pad;
     int64_t len;                    // RK_MULTI: sample length
     Range2* out;                    // [n_chunks] x = lo, y = hi (RK_ADSR: first, count; RK_LERP: x = base)
-    // RK_VOICE: the per-chunk segment table k_voice walks, built on the device from the records
-    // (k_chunk_ranges counts, k_voice_seg_scan turns counts into offsets, k_voice_seg_fill writes the segments)
+    // RK_VOICE / RK_ADSR: the per-chunk segment table k_voice / k_fx<adsr> walk, built on the device from the records
+    // (k_chunk_ranges counts, k_seg_scan turns counts into offsets, k_seg_fill writes the segments)
     uint32_t* seg_ptr;              // [n_chunks + 1]
-    F4* segs;                       // [capacity][2]: (hz, vel, env_t, rel_t), (ia, ib, relv0, relv1)
+    F4* segs;                       // RK_VOICE [capacity][2]: (hz, vel, env_t, rel_t), (ia, ib, relv0, relv1); RK_ADSR: AdsrSeg[capacity]
     float* relv2;                   // [capacity]
     const float* clock;             // clock table of this (sr, bl)
     uint64_t xenv_off;              // blob: explicit clocks
     uint32_t debug_sine, pad2;
 };
 
-// ---- staged (shared-memory) per-chunk forms ------------------------------------------------------------
+// ---- per-chunk forms (device-built) ---------------------------------------------------------------------
 struct AdsrSeg {            // Adsr vertex state valid from frame offset `ia` of its chunk (extensions.rs:61-69)
     uint32_t ia, flags;     // flags bit0: this single frame is passed through un-enveloped (extensions.rs:633-635)
     float pt, pv, pr, gt, gv, gr;   // primary (t, vel, release_val), ghost (t, vel, release_val)
@@ -123,11 +123,10 @@ struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan 
     AdsrK conf;
     float wet, fsr, rsr;    // fsr = sr as f32, rsr = 1/fsr
     uint32_t use_off, use_max, sr;
-    uint64_t recs_off;      // FX_ADSR, blob: AdsrRec[n_recs] sorted by start (record 0 starts at pass frame 0)
-    uint64_t xenv_off;      // blob: float[] explicit clocks
-    const Range2* ranges;    // device scratch [n_chunks]: (first record, count) of every chunk (k_chunk_ranges)
-    const float* clock;     // [depth][bl] clock table of this (sr, bl)
-    uint32_t n_recs, chunk0; // chunk0: pass chunk of block 0 (time-sharded segments start late)
+    // FX_ADSR: per-chunk envelope states in device scratch, built there from the AdsrRec records (RangeTask RK_ADSR:
+    // k_chunk_ranges counts, k_seg_scan offsets, k_seg_fill writes them with their clocks looked up)
+    const uint32_t* seg_ptr; // [n_chunks + 1]
+    const AdsrSeg* segs;
     float* peaks;           // FX_NORM_PEAK: [n_chunks] max |x| over L and R of the summed chunk
     uint32_t no_store, pad1; // FX_NORM_PEAK of the output vertex in a scan pass: only the peaks are needed
 };
