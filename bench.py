@@ -13,7 +13,8 @@ device (CUDA events around each pass's kernel sequence, max over ranks); `e2e` =
 the C ABI with host buffers (floww events re-uploaded, plan tables H2D, PCM D2H into pinned memory)
 on the host clock, with the library's default software pipelining of project groups.
 
-`--workload c4` is BASELINE.json configs[3], the single long 64-vertex graph: at N>1 it is sharded by
+`--workload c1|c2|c3` run BASELINE.json configs[0..2] on one GPU (c1 and c2 move 12-200 MB: launch-bound by
+construction); `--workload c4` is BASELINE.json configs[3], the single long 64-vertex graph: at N>1 it is sharded by
 TIME over the ranks (strong scaling; segment hand-off through NCCL inside the library).
 """
 from __future__ import annotations
@@ -39,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c1", "c2", "c3", "c4"])
     ap.add_argument("--projects", type=int, default=512, help="projects per GPU (c5)")
     ap.add_argument("--scale", type=float, default=1.0, help="duration scale of the workload")
     ap.add_argument("--cpu-sample", type=int, default=12, help="projects in the cpu_baseline sample (c5)")
@@ -60,6 +61,8 @@ def build_projects(args, rank: int):
     if args.workload == "c5":
         base = rank * args.projects
         return [S.config_5_project(base + i, args.scale) for i in range(args.projects)]
+    if args.workload == "c1":
+        return [S.config_1(args.scale)]
     if args.workload == "c2":
         return [S.config_2(args.scale)]
     if args.workload == "c3":
@@ -69,6 +72,7 @@ def build_projects(args, rank: int):
 
 WORKLOAD_NAMES = {
     "c5": "configs[4]: algorithmic-composition batch, 4096 projects x 30 s over 8 GPUs (512 projects per GPU shard)",
+    "c1": "configs[0]: README example, 2 sampleloops -> normalize, 3 s, rendered to 44.1 kHz 16-bit (sinc down-sampler)",
     "c2": "configs[1]: floww synth + ADSR -> band pass -> normalize, 60 s, 48 kHz, 24-bit",
     "c3": "configs[2]: wavetable synth 512 voices + 2 sample_lerp (44.1/96 kHz sources), 600 s",
     "c4": "configs[3]: 64-vertex mixed graph, 3600 s, 24-bit",
@@ -213,8 +217,8 @@ def cpu_sample_cfgs(args):
     if args.workload == "c5":
         return [S.config_5_project(i, args.scale) for i in range(args.cpu_sample)], \
             f"{args.cpu_sample} of the shard's projects, full 30 s each, scan + render"
-    frac = {"c2": 1.0, "c3": 0.004, "c4": 0.004}[args.workload]
-    cfg = {"c2": S.config_2, "c3": S.config_3, "c4": S.config_4}[args.workload](args.scale * frac)
+    frac = {"c1": 1.0, "c2": 1.0, "c3": 0.004, "c4": 0.004}[args.workload]
+    cfg = {"c1": S.config_1, "c2": S.config_2, "c3": S.config_3, "c4": S.config_4}[args.workload](args.scale * frac)
     return [cfg], f"first {frac:.3%} of the timeline, scan + render"
 
 

@@ -160,6 +160,11 @@ int tdg_normalize_scan(tdg_ctx* ctx, uint64_t chunks);
  * Ends like the reference: graph time rewound to 0, floww cursor NOT rewound (state.rs:575). */
 int tdg_render(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth,
                uint8_t* out_pcm, uint64_t cap_bytes, uint64_t* frames_written);
+/* Pinned host memory for PCM sinks (cudaHostAlloc / cudaFreeHost): the device->host copy of a render into such a
+ * buffer is asynchronous and runs at PCIe speed; the staging half of the WAV output stage (state.rs:508-531 hands
+ * every sample to hound one by one; here a file is one header + one pinned block, termdaw_b200/batch.py). */
+void* tdg_host_alloc(uint64_t bytes);
+void tdg_host_free(void* p);
 /* Upper bound of the PCM bytes tdg_render will write for these arguments. */
 uint64_t tdg_render_bound_bytes(tdg_ctx* ctx, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth);
 
@@ -171,6 +176,15 @@ uint64_t tdg_render_bound_bytes(tdg_ctx* ctx, uint64_t chunks, uint32_t render_s
  * `out_interleaved` receives chunks*buffer_len frames of (L, R) f32 pairs; may be NULL to only advance. */
 int tdg_play(tdg_ctx* ctx, uint64_t chunks, float* out_interleaved, uint64_t cap_frames,
              uint64_t* frames_written);
+/* The same feed without blocking the player (the render-ahead ring of ui_workflow.rs:195-210 kept full from a
+ * pinned host ring): tdg_play_begin queues `chunks` more chunks — one device pass on the playback lane,
+ * Sample::interleave on the device, an asynchronous copy into a pinned ring slot — and returns a ticket at once;
+ * transport and vertex state have advanced on return, so the next block can be begun immediately.
+ * tdg_play_wait blocks until that block has landed and hands out a pointer into the ring (chunks*buffer_len
+ * (L, R) f32 pairs; valid until 6 further begins).  At most 6 uncollected tickets per device
+ * (TDG_ERR_CAPACITY).  Any other pass of the context first waits for its queued playback work. */
+int tdg_play_begin(tdg_ctx* ctx, uint64_t chunks);
+int tdg_play_wait(tdg_ctx* ctx, int ticket, const float** interleaved, uint64_t* frames);
 
 /* Batched forms (independent projects): the same two calls over `n` contexts on
  * the same device, merged into one device schedule (one launch per DAG level and kernel class for

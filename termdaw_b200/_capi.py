@@ -131,6 +131,10 @@ class Library:
         "last_pass_stats": (C.c_int, [C.c_void_p, C.POINTER(PassStats)]),
         "set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
         "set_pass_reuse": (C.c_int, [C.c_void_p, C.c_int]),
+        "host_alloc": (C.c_void_p, [C.c_uint64]),
+        "host_free": (None, [C.c_void_p]),
+        "play_begin": (C.c_int, [C.c_void_p, C.c_uint64]),
+        "play_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(c_f32p), c_u64p]),
         "set_oscillator_mode": (C.c_int, [C.c_void_p, C.c_int]),
         "rewind_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(c_f32p), C.POINTER(c_f32p), C.POINTER(c_f32p),
                                   c_u64p, c_u32p]),
@@ -348,6 +352,16 @@ class Context:
         return out[: 2 * frames.value]
 
     # -- CUDA library only
+    def play_begin(self, chunks: int) -> int:
+        """tdg_play_begin: queue `chunks` more chunks of the playback feed; returns a ticket immediately."""
+        return self._chk(self.lib.play_begin(self.h, int(chunks)))
+
+    def play_wait(self, ticket: int) -> np.ndarray:
+        """tdg_play_wait: the block of that ticket from the pinned ring, copied into an array [frames, 2]."""
+        ptr, n = c_f32p(), C.c_uint64(0)
+        self._chk(self.lib.play_wait(self.h, int(ticket), C.byref(ptr), C.byref(n)))
+        return np.ctypeslib.as_array(ptr, shape=(n.value, 2)).copy()
+
     def scan_segment(self, total_chunks: int, chunk0: int, chunks: int, warmup_chunks: int):
         self._chk(self.lib.scan_segment(self.h, total_chunks, chunk0, chunks, warmup_chunks))
 

@@ -205,6 +205,13 @@ struct Engine {
     std::vector<PlanScratch>* scratch = nullptr; // per worker: event-table scratch vectors
     std::vector<std::vector<VPlan>>* vplans = nullptr;   // per request of a job x vertex: event plans (pooled)
     std::map<uint64_t, ClockTab> clocks;         // key: sr << 32 | bl
+    // asynchronous playback feed (tdg_play_begin / tdg_play_wait): its own lane, a ring of plan slots, one pinned
+    // host buffer per slot that the interleaved stream lands in
+    struct PlayJob* play_slot[kSlots] = {};
+    float* play_ring[kSlots] = {}; uint64_t play_ring_cap[kSlots] = {};
+    float* play_dev[kSlots] = {}; uint64_t play_dev_cap[kSlots] = {};
+    cudaEvent_t play_ev[kSlots] = {};
+    int play_next = 0;
     cudaEvent_t ev_batch0 = nullptr, ev_batch1[kLanes] = {}, ev_copy_end = nullptr;   // span of a pipelined call
 };
 static std::mutex g_mu;
@@ -1847,8 +1854,21 @@ static int pass_wait(PassJob& J) {
     return rc;
 }
 
+struct PlayJob { PassJob J; Ctx* c = nullptr; uint64_t frames = 0; bool waited = false; };
+static int drain_plays(Ctx* c) {
+    if (!c || c->plays_in_flight == 0) return TDG_OK;
+    Engine* g = c->eng;
+    cudaSetDevice(g->device);
+    for (int sl = 0; sl < kSlots; ++sl) {
+        PlayJob* pj = g->play_slot[sl];
+        if (!pj || pj->c != c || pj->waited) continue;
+        if (g->play_ev[sl]) cudaEventSynchronize(g->play_ev[sl]);
+    }
+    return TDG_OK;
+}
 static int run_pass(std::vector<PassReq>& reqs) {
     if (reqs.empty()) return TDG_OK;
+    for (auto& r : reqs) drain_plays(r.c);
     PassJob J;
     J.reqs.swap(reqs);
     J.lane = &J.reqs[0].c->eng->lanes[0];
@@ -1929,6 +1949,7 @@ static void publish_batch_stats(std::vector<PassJob>& jobs, const PassStats& tot
 
 static int run_pass_pipelined(std::vector<PassReq>& reqs) {
     if (reqs.empty()) return TDG_OK;
+    for (auto& r : reqs) drain_plays(r.c);
     Engine* g = reqs[0].c->eng;
     const size_t group = g->pipeline_group;
     if (group == 0 || reqs.size() <= group || reqs[0].x_mode != 0) return run_pass(reqs);
@@ -1951,6 +1972,7 @@ static int run_pass_pipelined(std::vector<PassReq>& reqs) {
 // lane works on group g+1, so the PCM of group g-1 crosses PCIe under the kernels of both passes.
 static int run_scan_render_pipelined(std::vector<PassReq>& scans, std::vector<PassReq>& renders) {
     Engine* g = renders[0].c->eng;
+    for (auto& r : renders) drain_plays(r.c);
     for (auto& r : renders) if (r.c->eng != g) return r.c->fail(TDG_ERR_INVALID, "all contexts of a batch must be on one device");
     cudaSetDevice(g->device);
     const size_t group = g->pipeline_group ? g->pipeline_group : renders.size();
@@ -2037,6 +2059,11 @@ void tdg_ctx_destroy(tdg_ctx* h) {
     Ctx* c = C_;
     cudaSetDevice(c->eng->device);
     cudaStreamSynchronize(c->eng->stream);
+    {                                      // playback tickets of this context die with it
+        Engine* g = c->eng;
+        cudaStreamSynchronize(g->lanes[kLanes - 1].stream);
+        for (int sl = 0; sl < kSlots; ++sl) if (g->play_slot[sl] && g->play_slot[sl]->c == c) { delete g->play_slot[sl]; g->play_slot[sl] = nullptr; }
+    }
     for (auto& s : c->samples) { if (s.l) cudaFree(s.l); }
     for (auto& t : c->tables) if (t.data) cudaFree(t.data);
     if (c->vstate_dev) cudaFree(c->vstate_dev);
@@ -2563,6 +2590,73 @@ int tdg_render(tdg_ctx* h, uint64_t chunks, uint32_t render_sr, uint32_t bitdept
 // them, so consecutive calls produce the stream the reference's per-chunk loop produces.  The output vertex's
 // planar f32 buffer is copied back and interleaved (L, R) on the host: the render-ahead ring of a player is
 // filled `chunks` at a time.
+// ---- asynchronous playback feed: the render-ahead of ui_workflow.rs:195-210 without blocking the player ---------------
+// tdg_play_begin queues `chunks` more chunks (one device pass on the playback lane, then Sample::interleave on the
+// device and a copy into a pinned ring slot, all stream ordered) and returns a ticket at once; the host-side transport
+// state has already advanced, so the next begin can be issued immediately.  tdg_play_wait blocks until that block
+// is in the ring and hands out a pointer to it (valid until kSlots further begins).  Any other pass of the context
+// first collects its outstanding tickets' device work (drain_plays).
+int tdg_play_begin(tdg_ctx* h, uint64_t chunks) {
+    Ctx* c = C_;
+    Engine* g = c->eng;
+    if (c->output < 0) return c->fail(TDG_ERR_NO_OUTPUT, "no output vertex");
+    if (chunks == 0) return c->fail(TDG_ERR_INVALID, "tdg_play_begin: zero chunks");
+    cudaSetDevice(g->device);
+    const int slot = g->play_next;
+    if (PlayJob* old = g->play_slot[slot]) {
+        if (!old->waited) return c->fail(TDG_ERR_CAPACITY, "playback ring full: collect older tickets with tdg_play_wait first");
+        delete old; g->play_slot[slot] = nullptr;
+    }
+    g->play_next = (slot + 1) % kSlots;
+    ++c->mut_gen;
+    PlayJob* pj = new PlayJob();
+    pj->c = c; pj->frames = chunks * c->bl;
+    pj->J.reqs.resize(1);
+    PassReq& r = pj->J.reqs[0];
+    r.c = c; r.is_scan = false; r.play = true; r.total = chunks; r.emit0 = 0; r.emit_n = chunks; r.keep0 = 0;
+    r.render_sr = c->sr; r.bd = 32;
+    pj->J.lane = &g->lanes[kLanes - 1]; pj->J.slot = slot;
+    int e = pass_plan(pj->J);
+    if (e == TDG_OK) e = pass_submit(pj->J);
+    if (e != TDG_OK) { cudaStreamSynchronize(pj->J.lane->stream); delete pj; return e; }
+    pass_end_state(pj->J);
+    // interleave on the device, then into the pinned ring slot; everything on the lane's stream, in order
+    cudaStream_t s = pj->J.lane->stream;
+    const uint64_t n = pj->frames;
+    if (g->play_dev_cap[slot] < n) {
+        if (g->play_dev[slot]) cudaFree(g->play_dev[slot]);
+        g->play_dev[slot] = nullptr; g->play_dev_cap[slot] = 0;
+        CU(cudaMalloc(&g->play_dev[slot], n * 8)); g->play_dev_cap[slot] = n;
+    }
+    if (g->play_ring_cap[slot] < n) {
+        if (g->play_ring[slot]) cudaFreeHost(g->play_ring[slot]);
+        g->play_ring[slot] = nullptr; g->play_ring_cap[slot] = 0;
+        CU(cudaHostAlloc(&g->play_ring[slot], n * 8, cudaHostAllocDefault)); g->play_ring_cap[slot] = n;
+    }
+    if (!g->play_ev[slot]) CU(cudaEventCreateWithFlags(&g->play_ev[slot], cudaEventDisableTiming));
+    const float* dl = reinterpret_cast<const float*>(pj->J.W + r.buf_off[c->output]);
+    CU(launch_interleave(dl, dl + r.n_pad, g->play_dev[slot], n, s));
+    CU(cudaMemcpyAsync(g->play_ring[slot], g->play_dev[slot], n * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(g->play_ev[slot], s));
+    g->play_slot[slot] = pj;
+    ++c->plays_in_flight; ++c->launches;
+    return slot;
+}
+int tdg_play_wait(tdg_ctx* h, int ticket, const float** interleaved, uint64_t* frames) {
+    Ctx* c = C_;
+    Engine* g = c->eng;
+    if (ticket < 0 || ticket >= kSlots || !g->play_slot[ticket] || g->play_slot[ticket]->c != c || g->play_slot[ticket]->waited)
+        return c->fail(TDG_ERR_INVALID, "unknown playback ticket");
+    PlayJob* pj = g->play_slot[ticket];
+    cudaSetDevice(g->device);
+    CU(cudaEventSynchronize(g->play_ev[ticket]));
+    const int e = pass_wait(pj->J);
+    pj->waited = true; --c->plays_in_flight;
+    if (interleaved) *interleaved = g->play_ring[ticket];
+    if (frames) *frames = pj->frames;
+    return e;
+}
+
 int tdg_play(tdg_ctx* h, uint64_t chunks, float* out_interleaved, uint64_t cap_frames, uint64_t* frames_written) {
     Ctx* c = C_;
     if (frames_written) *frames_written = 0;
@@ -2704,6 +2798,13 @@ int tdg_comm_destroy(tdg_ctx* h) {
 }
 uint64_t tdg_collectives(tdg_ctx* h) { return h ? h->c.collectives : 0; }
 
+// pinned host memory for the caller's PCM sinks (cudaHostAlloc): copies into it are asynchronous and run at PCIe speed
+void* tdg_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void tdg_host_free(void* p) { if (p) cudaFreeHost(p); }
 int tdg_set_pass_reuse(tdg_ctx* h, int on) { h->c.eng->reuse = on != 0; h->c.keep.valid = false; return TDG_OK; }
 int tdg_set_oscillator_mode(tdg_ctx* h, int libm_exact) { h->c.eng->libm_sin = libm_exact != 0; h->c.keep.valid = false; ++h->c.mut_gen; return TDG_OK; }
 int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; return TDG_OK; }

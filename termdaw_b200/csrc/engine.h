@@ -112,6 +112,7 @@ struct Ctx {
     void* nccl_comm = nullptr; int x_ranks = 1, x_rank = 0;      // time sharding over NCCL (tdg_comm_init_rank)
     uint64_t mut_gen = 0;                    // bumped by every call that edits the project or its transport state
     KeepRecord keep;
+    int plays_in_flight = 0;                 // tdg_play_begin tickets of this context not yet collected by tdg_play_wait
     int fail(int code, const std::string& m) { err = m; return code; }
 };
 

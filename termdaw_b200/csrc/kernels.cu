@@ -1182,6 +1182,11 @@ __global__ void __launch_bounds__(128) k_resample(const ResampleTask* __restrict
     T.out_r[g] = out[1];
 }
 
+// Sample::interleave (sample.rs:177-184) for the playback ring: planar L / R -> (L, R) pairs
+__global__ void __launch_bounds__(256) k_interleave(const float* __restrict__ l, const float* __restrict__ r, float2* __restrict__ out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float2(l[i], r[i]);
+}
 // ------------------------------------------------------------------------------------ sample loading
 // numeric part of SampleBank::add (sample.rs:275-303)
 __global__ void k_deinterleave(const float* __restrict__ lin, uint64_t n_frames, uint32_t stride, uint32_t off_l,
@@ -1312,6 +1317,11 @@ cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out,
     k_resample_index<<<grid2((max_chunks + 63) / 64, n), 64, 0, s>>>(t, blob);
     const uint64_t blocks = (max_out + 127) / 128;
     k_resample<<<grid2(blocks ? blocks : 1, n), 128, 0, s>>>(t, blob, max_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_interleave(const float* l, const float* r, float* out_pairs, uint64_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(l, r, reinterpret_cast<float2*>(out_pairs), n);
     return cudaGetLastError();
 }
 cudaError_t launch_deinterleave(const float* lin, uint64_t n_frames, uint32_t stride, uint32_t off_l, uint32_t off_r,

@@ -25,6 +25,7 @@ cudaError_t launch_bp_carry(const BpTask* t, uint32_t n, const uint8_t* blob, cu
 cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s);
 cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s);   // positions (k_resample_index), then the windows
+cudaError_t launch_interleave(const float* l, const float* r, float* out_pairs, uint64_t n, cudaStream_t s);
 cudaError_t launch_deinterleave(const float* lin, uint64_t n_frames, uint32_t stride, uint32_t off_l, uint32_t off_r,
                                 uint32_t mix, float* out_l, float* out_r, cudaStream_t s);
 cudaError_t launch_absmax(const float* x, uint64_t n, int* out_bits, cudaStream_t s);

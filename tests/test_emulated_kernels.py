@@ -110,6 +110,7 @@ def test_emu_play_seek_render_and_stream_feed(emulib, oracle):
     TPB.check_play_then_seek_and_render(emulib, oracle)
     TPB.check_stream_feed(emulib, oracle)
     TPB.test_play_errors(emulib)
+    TPB.check_async_play_ring(emulib, oracle)
 
 
 def test_emu_keep_arena_never_outgrows_free_memory(emulib, oracle, monkeypatch):

@@ -519,3 +519,35 @@ def test_refresh_drops_and_reloads_banks_on_the_device(gpulib):
     removed samples are freed, a changed resource path is reloaded (tests/test_host_frontend.py holds the body)."""
     import test_host_frontend as H
     H.test_refresh_diffs_samples_and_resources_like_the_reference(gpulib)
+
+
+# ------------------------------------------------------------------------------------ output stage: files from pinned staging
+def test_batch_render_to_files_overlapped_writer(gpulib, oracle, tmp_path):
+    """termdaw_b200.batch.render_projects_to_files: groups of projects rendered by the batched call into pinned staging
+    buffers (tdg_host_alloc) while a thread pool writes the previous group's WAV files.  Every file equals, byte for
+    byte, the file the one-project-at-a-time path writes (State.render_to_file), and its PCM the oracle's within 1 LSB."""
+    from termdaw_b200.batch import render_projects_to_files
+    from termdaw_b200.wav import read_wav
+    cfgs = [S.config_5_project(i, 0.03) for i in range(9)]
+    states = []
+    for p, a, s in cfgs:
+        st = State(gpulib, s["psr"], s["bl"], assets=a)
+        assert st.refresh(p), st.messages
+        states.append(st)
+    paths = [str(tmp_path / f"batch_{i}.wav") for i in range(len(states))]
+    render_projects_to_files(gpulib, states, paths, group=4, writers=3)
+    for st in states:
+        st.close()
+    for i, (p, a, s) in enumerate(cfgs):
+        st = State(gpulib, s["psr"], s["bl"], assets=a)
+        assert st.refresh(p), st.messages
+        st.scan_exact()
+        single = str(tmp_path / f"single_{i}.wav")
+        st.render_to_file(single)
+        st.close()
+        assert open(single, "rb").read() == open(paths[i], "rb").read(), i
+        want = run_project(oracle, p, a, s, taps=False)
+        got = read_wav(paths[i])
+        x = np.asarray(got.linear, np.float64)
+        y = pcm_to_int(want["pcm"], want["bd"]).astype(np.float64)
+        assert x.shape == y.shape and np.abs(x - y).max() <= 1, i

@@ -146,3 +146,40 @@ def test_play_errors(gpulib):
         st.ctx.floww_append(99, [0.5], [60.0], [1.0])
     assert st.ctx.play(0).size == 0
     st.close()
+
+
+def check_async_play_ring(lib, oracle):
+    """tdg_play_begin / tdg_play_wait: blocks queued ahead of the player (tickets), collected in order from the pinned
+    ring == the synchronous tdg_play stream == the oracle's chunk-at-a-time loop; a render issued while playback work
+    is still queued waits for it; the ring refuses a seventh uncollected ticket."""
+    from termdaw_b200._capi import TermdawError
+    cfg = S.config_5_project(3, 0.05)
+    want, _ = _stream(oracle, cfg, [1] * 30)
+    p, a, s = cfg
+    st = State(lib, s["psr"], s["bl"], assets=a)
+    try:
+        assert st.refresh(p), st.messages
+        plan = [4, 1, 7, 2, 11, 5]
+        tickets = [st.ctx.play_begin(n) for n in plan]               # six blocks in flight, nothing collected yet
+        assert st.ctx.get_time() == 30 * st.bl                        # the transport has already advanced
+        with pytest.raises(TermdawError):
+            st.ctx.play_begin(1)                                      # ring full
+        got = np.concatenate([st.ctx.play_wait(t).reshape(-1) for t in tickets])
+        _close(got, want)
+        with pytest.raises(TermdawError):
+            st.ctx.play_wait(tickets[0])                              # a ticket is collected once
+        t = st.ctx.play_begin(2)                                      # ... and the ring turns over
+        more = st.ctx.play_wait(t).reshape(-1)
+        assert more.size == 2 * 2 * st.bl
+        # a synchronous call after queued asynchronous ones continues the same stream
+        t = st.ctx.play_begin(3)
+        tail = st.ctx.play(2)
+        head = st.ctx.play_wait(t).reshape(-1)
+        want2, _ = _stream(oracle, cfg, [1] * 37)
+        _close(np.concatenate([got, more, head, tail]), want2)
+    finally:
+        st.close()
+
+
+def test_async_play_ring(gpulib, oracle):
+    check_async_play_ring(gpulib, oracle)
