@@ -199,6 +199,7 @@ struct Engine {
     // step has 735 launch triples whose one-block-per-filter carry kernels and short grids cost far more (28 ms) than the
     // L2 hits save, so the default is one launch triple per level (0); the knob stays for single long renders (TDG_BP_L2_MB)
     uint64_t bp_l2_bytes = 0;
+    bool bp_fused = true;                        // single-pass band pass where no exchange step is needed (TDG_BP_FUSED=0: three launches)
     bool libm_sin = true;                        // oscillators evaluate glibc's sinf exactly (TDG_FAST_SIN=1 / tdg_set_oscillator_mode(ctx, 0): f32 polynomial, <= 2 ulp)
     WorkerPool* pool = nullptr;                  // planner threads (created on first batched pass)
     std::vector<Frag>* frags = nullptr;          // pooled per-project plan fragments (capacity is kept between jobs)
@@ -251,6 +252,7 @@ static Engine* engine_get(int device, std::string* err) {
     if (const char* e = getenv("TDG_PASS_REUSE")) g->reuse = atoi(e) != 0;
     if (const char* e = getenv("TDG_FAST_SIN")) g->libm_sin = atoi(e) == 0;
     if (const char* e = getenv("TDG_BP_L2_MB")) g->bp_l2_bytes = (uint64_t)std::max(0, atoi(e)) << 20;
+    if (const char* e = getenv("TDG_BP_FUSED")) g->bp_fused = atoi(e) != 0;
     g->refs = 1;
     g_engines[device] = g;
     return g;
@@ -789,6 +791,7 @@ struct PassReq {
     std::vector<int> last_use;
     std::vector<int64_t> buf_off, aux_off;   // work-arena byte offsets
     std::vector<int64_t> rng_off;            // per event-driven vertex: uint2[emit_n] written by k_chunk_ranges
+    std::vector<int64_t> bps_off;            // per band-pass vertex: ticket + per-tile flags of the fused kernel, inside the job's zeroed sync region
     std::vector<int64_t> seg_off;            // per voice vertex: seg_ptr[emit_n + 1], segs[cap][2] (float4), relv2[cap]
     std::vector<uint64_t> seg_cap;
     uint64_t n_frames = 0, n_pad = 0;
@@ -894,6 +897,7 @@ struct PassJob {
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
     std::vector<RangeTask> ranges; uint32_t range_max = 0, resamp_chunks = 0; uint64_t range_off = 0; bool any_voice = false;
     std::vector<cudaEvent_t> clock_events;   // clock tables this job reads that were extended on another stream
+    uint64_t sync_off = 0, sync_bytes = 0;    // tickets + flags of the fused band-pass kernels of the job (work arena, zeroed at submit)
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, quant_off = 0, resamp_off = 0;
     uint64_t algo_bytes_total = 0, reused_v = 0, reused_b = 0;
     double t_start = 0, t_planned = 0, t_h2d_issued = 0, t_d2h0 = 0, t_submitted = 0;
@@ -914,7 +918,7 @@ static int pass_plan(PassJob& J) {
     g->epoch++;
 
     // ---- 1. graph analysis + work-arena layout -------------------------------------------------
-    Bump bump, pbump, kbump;
+    Bump bump, pbump, kbump, fbump;
     const int lane_index = (int)(J.lane - g->lanes);
     int& max_level = J.max_level;
     max_level = -1;
@@ -924,7 +928,7 @@ static int pass_plan(PassJob& J) {
         const int V = (int)x->verts.size();
         r.n_frames = r.emit_n * x->bl;
         r.n_pad = align_up(std::max<uint64_t>(r.n_frames, 1), kBpTile);
-        r.buf_off.assign(V, -1); r.aux_off.assign(V, -1); r.rng_off.assign(V, -1); r.seg_off.assign(V, -1); r.seg_cap.assign(V, 0);
+        r.buf_off.assign(V, -1); r.aux_off.assign(V, -1); r.rng_off.assign(V, -1); r.seg_off.assign(V, -1); r.seg_cap.assign(V, 0); r.bps_off.assign(V, -1);
         for (int v = 0; v < V; ++v) max_level = std::max(max_level, r.level[v]);
     }
     J.err_bytes = reqs.size() * 4;
@@ -1007,7 +1011,10 @@ static int pass_plan(PassJob& J) {
                 else r.buf_off[v] = (int64_t)bump.alloc(slot_bytes);
                 const HVertex& hv = x->verts[v];
                 if (hv.kind == K_NORMALIZE) r.aux_off[v] = (int64_t)bump.alloc(r.emit_n * 2 * 4 + 16);     // peaks, runmax
-                if (hv.kind == K_BANDPASS) r.aux_off[v] = (int64_t)bump.alloc((r.n_pad / kBpTile) * 12 * 4 + 16); // agg[8], carry[4]
+                if (hv.kind == K_BANDPASS) {
+                    r.aux_off[v] = (int64_t)bump.alloc((r.n_pad / kBpTile) * 12 * 4 + 16); // agg[8], carry[4]
+                    r.bps_off[v] = (int64_t)fbump.alloc((r.n_pad / kBpTile + 1) * 4);      // ticket, flags: one memset per job clears them all
+                }
                 if (hv.kind == K_ADSR || hv.kind == K_SAMPLE_MULTI || hv.kind == K_SAMPLE_LERP || hv.kind == K_DEBUG_SINE ||
                     hv.kind == K_SYNTH || hv.kind == K_SAMPSYN) r.rng_off[v] = (int64_t)bump.alloc(std::max<uint64_t>(r.emit_n, 1) * 8 + 16);
             }
@@ -1133,6 +1140,8 @@ static int pass_plan(PassJob& J) {
         r.seg_cap[it.v] = cap;
         r.seg_off[it.v] = (int64_t)bump.alloc(align_up((r.emit_n + 1) * 4, 16) + cap * 32 + cap * 4 + 16);
     }
+    J.sync_bytes = fbump.off;
+    J.sync_off = fbump.off ? bump.alloc(fbump.off + 256) : 0;
     const double tr_layout = now_ms();
     g->hwm_work = std::max<uint64_t>(g->hwm_work, bump.off + 256);
     CU(ln.work.ensure(bump.off + 256, g->hwm_work));
@@ -1336,6 +1345,7 @@ static int pass_plan(PassJob& J) {
                     t.state = x->vstate_dev + (size_t)v * 8 + 2;
                     t.agg = reinterpret_cast<float*>(W + r.aux_off[v]);
                     t.carry = t.agg + (size_t)(r.n_pad / kBpTile) * 8;
+                    t.sync = reinterpret_cast<uint32_t*>(W + J.sync_off + r.bps_off[v]);
                     t.x = Xchg{nullptr, 0, 0, 1, 0};
                     if (r.x_ranks > 1) {
                         const int L = r.level[v];
@@ -1621,6 +1631,7 @@ static int pass_submit(PassJob& J) {
     J.h2d_bytes = B.size;
     if (J.err_bytes) CU(cudaMemsetAsync(J.P + J.err_base, 0, J.err_bytes, s));      // TooWide flags of every request, contiguous
     for (cudaEvent_t e : J.clock_events) CU(cudaStreamWaitEvent(s, e, 0));          // clock rows appended on another lane's stream
+    if (J.sync_bytes) CU(cudaMemsetAsync(W + J.sync_off, 0, J.sync_bytes, s));       // tickets and flags of the fused band-pass kernels
     J.t_h2d_issued = now_ms();
     CU(cudaEventRecord(sl.ev0, s));
     uint64_t &launches = J.launches, &collectives = J.collectives;
@@ -1670,8 +1681,12 @@ static int pass_submit(PassJob& J) {
         // band pass = aggregate, carry, apply over the same inputs.  Without an exchange step in between the three
         // launches run over groups of filters whose inputs + outputs fit the L2 (bp_l2_bytes): the apply pass then
         // finds the inputs the aggregate pass just streamed in cache instead of fetching them from HBM again
-        const bool bp_grouped = !x_mode && g->bp_l2_bytes > 0 && T.bp.v.size() > 1;
-        if (bp_grouped) {
+        // no exchange step between aggregate and apply, pass short enough for the serial group chain: ONE launch
+        const bool bp_fused = !x_mode && g->bp_fused && !T.bp.v.empty() && T.bp.max_chunks <= kBpFusedMaxTiles;
+        const bool bp_grouped = !bp_fused && !x_mode && g->bp_l2_bytes > 0 && T.bp.v.size() > 1;
+        if (bp_fused) {
+            LAUNCH_SPLIT(KC_BP_APPLY, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_fused(tp, nb, T.bp.max_chunks, vec, D, s));
+        } else if (bp_grouped) {
             const size_t n = T.bp.v.size();
             auto io_of = [&](size_t q) { return 8ull * (T.bp.v[q].n_in + 1) * T.bp.v[q].h.n_frames; };
             for (size_t b0 = 0; b0 < n;) {
@@ -1715,7 +1730,7 @@ static int pass_submit(PassJob& J) {
         }
         LAUNCH_SPLIT(KC_NORM_PREFIX, T.nprefix, NormPrefixTask, offs[L].nprefix, T.nprefix.bytes, launch_norm_prefix(tp, nb, s));
         LAUNCH_SPLIT(KC_NORM_SCALE, T.nscale, NormScaleTask, offs[L].nscale, T.nscale.bytes, launch_norm_scale(tp, nb, T.nscale.max_chunks, vec, s));
-        if (!bp_grouped) {
+        if (!bp_grouped && !bp_fused) {
         LAUNCH_SPLIT(KC_BP_CARRY, T.bp, BpTask, offs[L].bp, (uint64_t)0, launch_bp_carry(tp, nb, D, s));
         LAUNCH_SPLIT(KC_BP_APPLY, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_apply(tp, nb, T.bp.max_chunks, vec, D, s));
         }

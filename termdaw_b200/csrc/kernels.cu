@@ -1004,6 +1004,118 @@ __global__ void __launch_bounds__(kBpThreads, TDG_BP_MINB) k_bp_apply(const BpTa
     if (T.x.ranks <= 1 && nv > 0 && p + nv == T.h.n_frames) { T.state[0] = ll; T.state[1] = lr; T.state[2] = hl; T.state[3] = hr; }
 }
 
+// Single pass: aggregate, look back, apply in ONE kernel — every input is read once (16 + 8*(indeg-1) bytes per frame
+// where the three-launch scan moves 24 + 16*(indeg-1)).  A block takes its tile from a per-filter ticket (tiles start
+// in ticket order, so everything a tile waits for belongs to a block that is already running), publishes the tile's
+// affine map, and finds the state entering the tile from (a) the state leaving the previous GROUP of kBpGroup tiles,
+// published by that group's last tile, pushed through (b) the maps of the tiles of its own group in front of it.
+// The composition is a fixed tree over the warp's lanes — which map meets which is decided by tile numbers alone,
+// never by timing — so the result is the same bits on every run (a free-running decoupled look-back would not be).
+// The cross-group chain is serial (n_tiles / 32 steps), hence kBpFusedMaxTiles.
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+template <bool VEC>
+__global__ void __launch_bounds__(kBpThreads, TDG_BP_MINB) k_bp_fused(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    __shared__ BpTask T;
+    __shared__ uint32_t s_tile;
+    __shared__ float s_carry[4];
+    load_task(&T, tasks + blockIdx.y);
+    if (blockIdx.x >= T.n_tiles) return;
+    if (threadIdx.x == 0) s_tile = atomicAdd(T.sync, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const float* const* ins = T.n_in <= (uint32_t)kInlineInputs ? T.ins : reinterpret_cast<const float* const*>(blob + T.in_off);
+    const uint64_t p = (uint64_t)tile * kBpTile + (uint64_t)threadIdx.x * 8;
+    const int nv = p >= T.h.n_frames ? 0 : (int)min((uint64_t)8, T.h.n_frames - p);
+    float xl[8], xr[8];
+    bp_load_run<VEC>(T, ins, p, nv, xl, xr);
+    const Aff mine = bp_fold_run(T, xl, xr, nv);
+    Aff total;
+    const Aff exc = block_aff_scan(mine, &total);
+    uint32_t* flags = T.sync + 1;
+    if (threadIdx.x < 32) {
+        const uint32_t ln = threadIdx.x;
+        if (ln == 0) {                                          // publish this tile's map, then the flag
+            float* a = T.agg + (size_t)tile * 8;
+            a[0] = total.b0; a[1] = total.b1; a[2] = total.b2; a[3] = total.b3; a[4] = total.al; a[5] = total.ah;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(flags + tile) = 1u;
+        }
+        const uint32_t base = (tile / kBpGroup) * kBpGroup, n_before = tile - base;
+        // lane q < n_before: the map of tile base + q (wait for its publication); the other lanes: identity
+        Aff m = aff_id();
+        if (ln < n_before) {
+            while (ld_flag(flags + base + ln) < 1u) {}
+            __threadfence();
+            const volatile float* a = T.agg + (size_t)(base + ln) * 8;
+            m = Aff{a[4], a[5], a[0], a[1], a[2], a[3]};
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {                      // inclusive composition over the lanes, fixed shape
+            const Aff up = aff_shfl_up(m, d);
+            if (ln >= (uint32_t)d) m = aff_then(up, m);
+        }
+        // lane 31 holds the map of tiles [base, tile) (identity lanes do not change it)
+        if (ln == 31) {
+            float st[4];
+            if (base == 0) {
+                if (T.first) {                                  // extensions.rs:664-670: seeded with frame 0 of the pass
+                    const float* const* gi = reinterpret_cast<const float* const*>(blob + T.in_off);
+                    float l0 = 0.0f, r0 = 0.0f;
+                    for (uint32_t q = 0; q < T.n_in; ++q) { l0 += gi[2 * q][0]; r0 += gi[2 * q + 1][0]; }
+                    st[0] = l0; st[1] = r0; st[2] = l0; st[3] = r0;
+                } else { st[0] = T.state[0]; st[1] = T.state[1]; st[2] = T.state[2]; st[3] = T.state[3]; }
+            } else {
+                while (ld_flag(flags + base - 1) < 2u) {}
+                __threadfence();
+                const volatile float* c = T.carry + (size_t)(base - 1) * 4;
+                st[0] = c[0]; st[1] = c[1]; st[2] = c[2]; st[3] = c[3];
+            }
+            const float c0 = fmaf(m.al, st[0], m.b0), c1 = fmaf(m.al, st[1], m.b1);
+            const float c2 = fmaf(m.ah, st[2], m.b2), c3 = fmaf(m.ah, st[3], m.b3);
+            s_carry[0] = c0; s_carry[1] = c1; s_carry[2] = c2; s_carry[3] = c3;
+            if ((tile + 1) % kBpGroup == 0 && tile + 1 < T.n_tiles) {   // the state leaving this group, for the next one
+                float* c = T.carry + (size_t)tile * 4;
+                c[0] = fmaf(total.al, c0, total.b0); c[1] = fmaf(total.al, c1, total.b1);
+                c[2] = fmaf(total.ah, c2, total.b2); c[3] = fmaf(total.ah, c3, total.b3);
+                __threadfence();
+                *reinterpret_cast<volatile uint32_t*>(flags + tile) = 2u;
+            }
+        }
+    }
+    __syncthreads();
+    float ll = fmaf(exc.al, s_carry[0], exc.b0), lr = fmaf(exc.al, s_carry[1], exc.b1);
+    float hl = fmaf(exc.ah, s_carry[2], exc.b2), hr = fmaf(exc.ah, s_carry[3], exc.b3);
+    const float lmul = T.lgamma == 0.0f ? 0.0f : 1.0f, hmul = T.hgamma == 0.0f ? 0.0f : 1.0f;
+    const float pass_mul = T.pass ? 1.0f : 0.0f, cut_mul = 1.0f - pass_mul;
+    float ol[8], orr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < nv) {                                           // extensions.rs:671-688
+            const float l = xl[j], r = xr[j];
+            ll = ll + T.lgamma * (l - ll); lr = lr + T.lgamma * (r - lr);
+            hl = hl + T.hgamma * (l - hl); hr = hr + T.hgamma * (r - hr);
+            const float cutl = (lmul * ll + hmul * (l - hl)) * 0.5f;
+            const float cutr = (lmul * lr + hmul * (r - hr)) * 0.5f;
+            const float passl = l - cutl;
+            const float passr = r - cutl;                       // sic (extensions.rs:685)
+            float a = cutl * cut_mul + passl * pass_mul;
+            float b = cutr * cut_mul + passr * pass_mul;
+            apply_pg(a, b, T.h.pg);
+            ol[j] = a; orr[j] = b;
+        } else { ol[j] = 0.0f; orr[j] = 0.0f; }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int nvh = max(0, min(4, nv - 4 * h));
+        if (nvh == 0) continue;
+        float a[4] = {ol[4 * h], ol[4 * h + 1], ol[4 * h + 2], ol[4 * h + 3]};
+        float b[4] = {orr[4 * h], orr[4 * h + 1], orr[4 * h + 2], orr[4 * h + 3]};
+        if (VEC && nvh == 4) { st4<true>(T.h.out_l, p + 4 * h, 4, a); st4<true>(T.h.out_r, p + 4 * h, 4, b); }
+        else { st4<false>(T.h.out_l, p + 4 * h, nvh, a); st4<false>(T.h.out_r, p + 4 * h, nvh, b); }
+    }
+    if (nv > 0 && p + nv == T.h.n_frames) { T.state[0] = ll; T.state[1] = lr; T.state[2] = hl; T.state[3] = hr; }
+}
+
 // ------------------------------------------------------------------------------------ K9b: quantise
 // (x * amplitude) as i16 | i32 (state.rs:517-532): toward zero, saturating, NaN -> 0; bytes laid out
 // as hound writes them (8-bit offset binary, 16/24/32-bit little endian, L then R).
@@ -1307,6 +1419,10 @@ cudaError_t launch_bp_carry(const BpTask* t, uint32_t n, const uint8_t* blob, cu
 }
 cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {
     TDG_VEC_DISPATCH(vec, k_bp_apply, <<<grid2(max_tiles, n), kBpThreads, 0, s>>>(t, blob));
+    return cudaGetLastError();
+}
+cudaError_t launch_bp_fused(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {
+    TDG_VEC_DISPATCH(vec, k_bp_fused, <<<grid2(max_tiles, n), kBpThreads, 0, s>>>(t, blob));
     return cudaGetLastError();
 }
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s) {

@@ -23,6 +23,8 @@ cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_
 cudaError_t launch_bp_aggregate(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_bp_carry(const BpTask* t, uint32_t n, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
+// ... or one launch (single pass with a deterministic grouped look-back) when no exchange step sits in between
+cudaError_t launch_bp_fused(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s);
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s);
 cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s);   // positions (k_resample_index), then the windows
 cudaError_t launch_interleave(const float* l, const float* r, float* out_pairs, uint64_t n, cudaStream_t s);

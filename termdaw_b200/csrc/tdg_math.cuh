@@ -82,6 +82,21 @@ static __constant__ uint32_t kInvPio4Dev[24] = TDG_INV_PIO4_WORDS;     // device
 #else
 #define TDG_INV_PIO4 kInvPio4Host
 #endif
+// the polynomial / reduction constants of __sincosf_table: on the device they are constant-bank operands of the DFMA /
+// DMUL instructions themselves (a 64-bit literal costs two extra moves per use: 7 % of the synth kernel's instructions)
+#define TDG_SINF_CONSTS {-0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7, -0x1.555545995a603p-3, 0x1.99343027bf8c3p-16, \
+                         -0x1.6c087e89a359dp-10, -0x1.ffffffd0c621cp-2, 0x1.55553e1068f19p-5, 0x1.45F306DC9C883p+23, \
+                         0x1.921FB54442D18p0, 0x1.921FB54442D18p-62}
+static const double kSinfConstHost[10] = TDG_SINF_CONSTS;
+#ifdef __NVCC__
+static __constant__ double kSinfConstDev[10] = TDG_SINF_CONSTS;
+#endif
+#ifdef __CUDA_ARCH__
+#define TDG_SC(i) kSinfConstDev[i]
+#else
+#define TDG_SC(i) kSinfConstHost[i]
+#endif
+enum { SC_S3 = 0, SC_S2, SC_S1, SC_C4, SC_C3, SC_C1, SC_C2, SC_HPI_INV, SC_HPI, SC_PI63 };
 TDG_HD uint32_t m_f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 // sinf_poly (sincosf.h): n even -> sine polynomial of x, n odd -> cosine polynomial of x2; `neg` folds in the
 // quadrant sign (the reference multiplies x by +-1.0 and picks the table with negated cosine coefficients: both
@@ -91,15 +106,15 @@ TDG_HD float m_sinf_poly(double x, double x2, int n, bool neg) {
     // different quadrants, so a branch here is always divergent (both sides executed plus the reconvergence
     // overhead); the operations of the side that is kept are exactly the reference's
     const double x3 = x * x2;
-    const double s1 = fma(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+    const double s1 = fma(x2, TDG_SC(SC_S3), TDG_SC(SC_S2));
     const double x7 = x3 * x2;
-    const double s = fma(x3, -0x1.555545995a603p-3, x);
+    const double s = fma(x3, TDG_SC(SC_S1), x);
     const double rs = fma(x7, s1, s);
     const double x4 = x2 * x2;
-    const double c2 = fma(x2, 0x1.99343027bf8c3p-16, -0x1.6c087e89a359dp-10);
-    const double c1 = fma(x2, -0x1.ffffffd0c621cp-2, 1.0);
+    const double c2 = fma(x2, TDG_SC(SC_C4), TDG_SC(SC_C3));
+    const double c1 = fma(x2, TDG_SC(SC_C1), 1.0);
     const double x6 = x4 * x2;
-    const double c = fma(x4, 0x1.55553e1068f19p-5, c1);
+    const double c = fma(x4, TDG_SC(SC_C2), c1);
     const double rc = fma(x6, c2, c);
     const float f = (float)((n & 1) ? rc : rs);
     return neg ? -f : f;
@@ -113,9 +128,9 @@ TDG_HD float m_sinf_glibc(float y) {
         return m_sinf_poly(x, x * x, 0, false);
     }
     if (top < 0x42fu) {                                              // |y| < 120: reduce_fast
-        const double r = x * 0x1.45F306DC9C883p+23;
+        const double r = x * TDG_SC(SC_HPI_INV);
         const int n = ((int32_t)r + 0x800000) >> 24;
-        x = fma(-(double)n, 0x1.921FB54442D18p0, x);
+        x = fma(-(double)n, TDG_SC(SC_HPI), x);
         const int m = n & 3;
         return m_sinf_poly(x, x * x, n, (n & 1) ? (m >> 1) != 0 : (m == 1 || m == 2));
     }
@@ -132,7 +147,7 @@ TDG_HD float m_sinf_glibc(float y) {
         res0 += res1;
         const uint64_t nn = (res0 + (1ULL << 61)) >> 62;
         res0 -= nn << 62;
-        x = (double)(int64_t)res0 * 0x1.921FB54442D18p-62;
+        x = (double)(int64_t)res0 * TDG_SC(SC_PI63);
         const int n = (int)nn, m = (n + sign) & 3;
         return m_sinf_poly(x, x * x, n, (n & 1) ? (m >> 1) != 0 : (m == 1 || m == 2));
     }

@@ -196,8 +196,9 @@ struct BpTask {             // band_pass_gen (extensions.rs:654-689) as a chunke
     uint32_t n_tiles;
     float* state;           // device-resident lprevl, lprevr, hprevl, hprevr (carried between passes)
     float* agg;             // [n_tiles][8] end state of each tile started from zero + decays
-    float* carry;           // [n_tiles][4] true state entering each tile
+    float* carry;           // [n_tiles][4] true state entering each tile (fused kernel: state LEAVING a group's last tile)
     Xchg x;                 // x.ranks > 1: slot = { al, ah, b0..b3 (segment map), init0..3 (rank 0 only) }
+    uint32_t* sync;         // fused single-pass kernel: [0] tile ticket, [1 + t] publication flag of tile t (zeroed per pass)
 };
 static const int kBpXchgFloats = 10;
 
@@ -244,5 +245,7 @@ struct ResampleChunk { double last_index; uint64_t out_off; uint32_t n_out, pad;
 static const int kBpFramesPerThread = 8;
 static const int kBpThreads = 256;
 static const int kBpTile = kBpFramesPerThread * kBpThreads;     // 2048 frames
+static const int kBpGroup = 32;                                 // fused kernel: tiles per look-back group (one warp lane each)
+static const uint32_t kBpFusedMaxTiles = 16384;                 // longer passes keep the three-launch scan (the group chain is serial)
 
 }  // namespace tdg

@@ -70,6 +70,7 @@ template <typename T> inline T shfl_t(T v, int a, int mode) {
 #define blockDim (emu::t_blockDim)
 #define gridDim (emu::t_gridDim)
 static inline void __syncthreads() { emu::syncthreads(); }
+static inline void __threadfence() {}                       // blocks run one after the other: every earlier store is visible
 template <typename T> inline T __shfl_up_sync(unsigned, T v, int d) { return emu::shfl_t(v, d, 0); }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::shfl_t(v, m, 1); }
 template <typename T> inline T __shfl_sync(unsigned, T v, int l) { return emu::shfl_t(v, l, 2); }
