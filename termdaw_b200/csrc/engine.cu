@@ -199,7 +199,7 @@ struct Engine {
     // step has 735 launch triples whose one-block-per-filter carry kernels and short grids cost far more (28 ms) than the
     // L2 hits save, so the default is one launch triple per level (0); the knob stays for single long renders (TDG_BP_L2_MB)
     uint64_t bp_l2_bytes = 0;
-    bool bp_fused = true;                        // single-pass band pass where no exchange step is needed (TDG_BP_FUSED=0: three launches)
+    bool bp_fused = false;                       // single-pass band pass where no exchange step is needed (TDG_BP_FUSED=1; default: three launches)
     bool libm_sin = true;                        // oscillators evaluate glibc's sinf exactly (TDG_FAST_SIN=1 / tdg_set_oscillator_mode(ctx, 0): f32 polynomial, <= 2 ulp)
     WorkerPool* pool = nullptr;                  // planner threads (created on first batched pass)
     std::vector<Frag>* frags = nullptr;          // pooled per-project plan fragments (capacity is kept between jobs)
@@ -1682,7 +1682,7 @@ static int pass_submit(PassJob& J) {
         // launches run over groups of filters whose inputs + outputs fit the L2 (bp_l2_bytes): the apply pass then
         // finds the inputs the aggregate pass just streamed in cache instead of fetching them from HBM again
         // no exchange step between aggregate and apply, pass short enough for the serial group chain: ONE launch
-        const bool bp_fused = !x_mode && g->bp_fused && !T.bp.v.empty() && T.bp.max_chunks <= kBpFusedMaxTiles;
+        const bool bp_fused = !x_mode && g->bp_fused && !T.bp.v.empty() && T.bp.max_chunks <= kBpFusedMaxTiles && T.bp.max_chunks <= 65535;
         const bool bp_grouped = !bp_fused && !x_mode && g->bp_l2_bytes > 0 && T.bp.v.size() > 1;
         if (bp_fused) {
             LAUNCH_SPLIT(KC_BP_APPLY, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_fused(tp, nb, T.bp.max_chunks, vec, D, s));

@@ -1018,8 +1018,11 @@ __global__ void __launch_bounds__(kBpThreads, TDG_BP_MINB) k_bp_fused(const BpTa
     __shared__ BpTask T;
     __shared__ uint32_t s_tile;
     __shared__ float s_carry[4];
-    load_task(&T, tasks + blockIdx.y);
-    if (blockIdx.x >= T.n_tiles) return;
+    // grid = (filters, tiles): consecutive blocks belong to DIFFERENT filters, so the blocks resident at any time
+    // advance many filters' group chains at once (with the tiles of one filter side by side the whole GPU waits
+    // on that filter's serial chain: measured 23 ms per step instead of 9.4)
+    load_task(&T, tasks + blockIdx.x);
+    if (blockIdx.y >= T.n_tiles) return;
     if (threadIdx.x == 0) s_tile = atomicAdd(T.sync, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -1422,7 +1425,7 @@ cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, boo
     return cudaGetLastError();
 }
 cudaError_t launch_bp_fused(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_bp_fused, <<<grid2(max_tiles, n), kBpThreads, 0, s>>>(t, blob));
+    TDG_VEC_DISPATCH(vec, k_bp_fused, <<<dim3(n, max_tiles ? max_tiles : 1, 1), kBpThreads, 0, s>>>(t, blob));
     return cudaGetLastError();
 }
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s) {

@@ -55,9 +55,26 @@ def main(out_json, out_md, label, raws, bench_log=None):
            "xu": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "lsu": "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
            "l2_hit": "lts__t_sector_hit_rate.pct", "l1_hit": "l1tex__t_sector_hit_rate.pct"}
     for raw in raws:
-        rows = list(csv.reader(open(raw)))
+        rows = list(csv.reader(open(raw, errors="replace")))
         hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
-        hdr, units, data = rows[hi], rows[hi + 1], rows[hi + 2:]
+        if "Metric Name" in rows[hi]:
+            # long format (`ncu --metrics ... --csv --log-file`): one row per (launch, metric) -> pivot to the wide raw-page form
+            c0 = {n: i for i, n in enumerate(rows[hi])}
+            names, wide, unit_of = [], {}, {}
+            for r in rows[hi + 1:]:
+                if len(r) < len(rows[hi]):
+                    continue
+                lid = r[c0["ID"]]
+                w = wide.setdefault(lid, {"Kernel Name": r[c0["Kernel Name"]]})
+                m = r[c0["Metric Name"]]
+                if m not in unit_of:
+                    unit_of[m] = r[c0["Metric Unit"]]; names.append(m)
+                w[m] = r[c0["Metric Value"]]
+            hdr = ["ID", "Kernel Name"] + names
+            units = ["", ""] + [unit_of[m] for m in names]
+            data = [[lid, w["Kernel Name"]] + [w.get(m, "0") for m in names] for lid, w in sorted(wide.items(), key=lambda kv: int(kv[0]))]
+        else:
+            hdr, units, data = rows[hi], rows[hi + 1], rows[hi + 2:]
         col = {n: i for i, n in enumerate(hdr)}
         rd, wr, tm = col["dram__bytes_read.sum"], col["dram__bytes_write.sum"], col["gpu__time_duration.sum"]
         if first_n is not None:
