@@ -1235,66 +1235,101 @@ __global__ void __launch_bounds__(64) k_resample_index(const ResampleTask* __res
     double* out = T.idx + C.out_off;
     for (uint32_t j = 0; j < C.n_out; ++j) { idx += T.t_ratio; out[j] = idx; }
 }
+// A block = 128 consecutive output frames.  Their 256-tap windows overlap almost entirely (the window start moves
+// by t_ratio ~ 1.1-2.2 input frames per output), so the block stages the span of input frames it touches in shared
+// memory once (both channels, the history / halo / leading-zero rules applied while staging) and every thread
+// runs its 4 x 256 multiply-adds from there; the two sinc rows of a frame are read as float4 and shared by both
+// channels.  Before: 2048 scalar global loads per output frame, the kernel sat on the load/store unit
+// (ncu: lg_throttle 83 stall cycles per issue, profiles/r02).  Accumulation order is SincFixedIn's: eight partial
+// sums over taps t, t+8, ..., added 0..7 at the end, per channel and per sub-phase.
+static const int kResampleSpan = 1024;               // staged input frames per block (128 * t_ratio + 257 <= 1024 up to t_ratio 5.9)
 __global__ void __launch_bounds__(128) k_resample(const ResampleTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint64_t n_out_total) {
+    __shared__ float s_l[kResampleSpan], s_r[kResampleSpan];
+    __shared__ long long s_min[4], s_max[4];
     const ResampleTask T = tasks[blockIdx.y];
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const ResampleChunk* ch = reinterpret_cast<const ResampleChunk*>(blob + T.chunk_off);
     if (T.n_chunks == 0) return;
     const uint64_t total = ch[T.n_chunks - 1].out_off + ch[T.n_chunks - 1].n_out;
-    if (g >= total || g >= n_out_total) return;
-    uint32_t a = 0, b = T.n_chunks;                  // last chunk with out_off <= g
-    while (b - a > 1) { uint32_t m = (a + b) >> 1; if (ch[m].out_off <= g) a = m; else b = m; }
-    const ResampleChunk C = ch[a];
-    const uint32_t j = (uint32_t)(g - C.out_off);
+    const uint64_t lim = total < n_out_total ? total : n_out_total;
+    if ((uint64_t)blockIdx.x * blockDim.x >= lim) return;           // whole block past the end (uniform)
+    const bool live = g < lim;
     const int sinc_len = 256, factor = 256;
-    (void)j;
-    const double idx = T.idx[g];
-    const double fl = floor(idx);
-    int64_t i0 = (int64_t)fl;
-    int64_t s0 = (int64_t)floor((idx - fl) * (double)factor);
-    int64_t i1 = i0, s1 = s0 + 1;
-    if (s1 >= factor) { s1 -= factor; i1 += 1; }
-    const double xf = idx * (double)factor;
-    const float frac = (float)(xf - floor(xf));
-    const int64_t base = (int64_t)a * (int64_t)T.chunk;
-    float out[2];
+    int64_t pos0 = 0, pos1 = 0, s0 = 0, s1 = 0;
+    float frac = 0.0f;
+    if (live) {
+        uint32_t a = 0, b = T.n_chunks;                  // last chunk with out_off <= g
+        while (b - a > 1) { uint32_t m = (a + b) >> 1; if (ch[m].out_off <= g) a = m; else b = m; }
+        const double idx = T.idx[g];
+        const double fl = floor(idx);
+        const int64_t i0 = (int64_t)fl;
+        s0 = (int64_t)floor((idx - fl) * (double)factor);
+        int64_t i1 = i0; s1 = s0 + 1;
+        if (s1 >= factor) { s1 -= factor; i1 += 1; }
+        const double xf = idx * (double)factor;
+        frac = (float)(xf - floor(xf));
+        const int64_t base = (int64_t)a * (int64_t)T.chunk;
+        pos0 = base + i0; pos1 = base + i1;
+    }
+    // span of stream positions the block's windows cover
+    long long lo = live ? (long long)pos0 : (long long)0x7fffffffffffffffLL, hi = live ? (long long)pos1 + sinc_len : (long long)(-0x7fffffffffffffffLL - 1);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const float* in = c == 0 ? T.in_l : T.in_r;
-        float pts[2];
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    lo = s_min[0]; hi = s_max[0];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int64_t pos = base + (q == 0 ? i0 : i1);
-            const float* sn = T.sincs + (size_t)(q == 0 ? s0 : s1) * sinc_len;
-            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (pos >= -(int64_t)T.n_before && pos + sinc_len <= (int64_t)T.n_in) {
-                // whole window inside this segment's buffer (warm-up chunks sit at negative offsets)
-                for (int t = 0; t < sinc_len; t += 8) {
+    for (int w = 1; w < 4; ++w) { lo = s_min[w] < lo ? s_min[w] : lo; hi = s_max[w] > hi ? s_max[w] : hi; }
+    // a stream position: inside this segment's buffer (warm-up chunks sit at negative offsets), in front of it the
+    // previous segment's tail (time sharding) or the zeros SincFixedIn's buffer starts with; behind the end nothing
+    auto fetch = [&](const float* in, const float* halo, int64_t ps) -> float {
+        if (ps >= -(int64_t)T.n_before) return ps < (int64_t)T.n_in ? __ldg(in + ps) : 0.0f;
+        if (halo && ps >= -(int64_t)kResampleHalo) return halo[kResampleHalo + ps];
+        return 0.0f;
+    };
+    const bool staged = hi - lo <= (long long)kResampleSpan;
+    if (staged) {
+        for (int k = threadIdx.x; k < (int)(hi - lo); k += 128) {
+            s_l[k] = fetch(T.in_l, T.halo_l, (int64_t)lo + k);
+            s_r[k] = fetch(T.in_r, T.halo_r, (int64_t)lo + k);
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    float pl[2], pr[2];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) acc[u] += __ldg(in + pos + t + u) * __ldg(sn + t + u);
-                }
-            } else {
-                // window reaches in front of the buffer: the previous segment's tail (time sharding) or the
-                // zeros SincFixedIn's buffer starts with; behind the end there is nothing (never reached:
-                // end_idx keeps the window inside the chunk)
-                const float* halo = c == 0 ? T.halo_l : T.halo_r;
-                for (int t = 0; t < sinc_len; t += 8) {
+    for (int q = 0; q < 2; ++q) {
+        const int64_t pos = q == 0 ? pos0 : pos1;
+        const float4* sn = reinterpret_cast<const float4*>(T.sincs + (size_t)(q == 0 ? s0 : s1) * sinc_len);
+        float al[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ar[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (staged) {
+            const float* wl = s_l + (pos - lo);
+            const float* wr = s_r + (pos - lo);
+            for (int t = 0; t < sinc_len; t += 8) {
+                const float4 c0 = __ldg(sn + (t >> 2)), c1 = __ldg(sn + (t >> 2) + 1);
+                const float cf[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int64_t ps = pos + t + u;
-                        float w = 0.0f;
-                        if (ps >= -(int64_t)T.n_before) { if (ps < (int64_t)T.n_in) w = __ldg(in + ps); }
-                        else if (halo && ps >= -(int64_t)kResampleHalo) w = halo[kResampleHalo + ps];
-                        acc[u] += w * __ldg(sn + t + u);
-                    }
+                for (int u = 0; u < 8; ++u) { al[u] += wl[t + u] * cf[u]; ar[u] += wr[t + u] * cf[u]; }
+            }
+        } else {
+            for (int t = 0; t < sinc_len; t += 8) {
+                const float4 c0 = __ldg(sn + (t >> 2)), c1 = __ldg(sn + (t >> 2) + 1);
+                const float cf[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    al[u] += fetch(T.in_l, T.halo_l, pos + t + u) * cf[u];
+                    ar[u] += fetch(T.in_r, T.halo_r, pos + t + u) * cf[u];
                 }
             }
-            pts[q] = acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7];
         }
-        out[c] = (1.0f - frac) * pts[0] + frac * pts[1];
+        pl[q] = al[0] + al[1] + al[2] + al[3] + al[4] + al[5] + al[6] + al[7];
+        pr[q] = ar[0] + ar[1] + ar[2] + ar[3] + ar[4] + ar[5] + ar[6] + ar[7];
     }
-    T.out_l[g] = out[0];
-    T.out_r[g] = out[1];
+    T.out_l[g] = (1.0f - frac) * pl[0] + frac * pl[1];
+    T.out_r[g] = (1.0f - frac) * pr[0] + frac * pr[1];
 }
 
 // Sample::interleave (sample.rs:177-184) for the playback ring: planar L / R -> (L, R) pairs

@@ -58,10 +58,11 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body);
 void syncthreads();
 uint32_t shfl(uint32_t v, int src_lane_or_delta, int mode);     // mode 0: up, 1: xor, 2: idx, 3: down
 template <typename T> inline T shfl_t(T v, int a, int mode) {
-    static_assert(sizeof(T) == 4, "4-byte shuffles only");
-    uint32_t u; memcpy(&u, &v, 4);
-    u = shfl(u, a, mode);
-    T r; memcpy(&r, &u, 4);
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "4- and 8-byte shuffles only");
+    uint32_t u[2] = {0, 0}; memcpy(u, &v, sizeof(T));
+    u[0] = shfl(u[0], a, mode);
+    if (sizeof(T) == 8) u[1] = shfl(u[1], a, mode);       // a 64-bit shuffle is two 32-bit ones (as in SASS)
+    T r; memcpy(&r, u, sizeof(T));
     return r;
 }
 }  // namespace emu
