@@ -82,11 +82,13 @@ static __constant__ uint32_t kInvPio4Dev[24] = TDG_INV_PIO4_WORDS;     // device
 #else
 #define TDG_INV_PIO4 kInvPio4Host
 #endif
-// the polynomial / reduction constants of __sincosf_table: on the device they are constant-bank operands of the DFMA /
-// DMUL instructions themselves (a 64-bit literal costs two extra moves per use: 7 % of the synth kernel's instructions)
-#define TDG_SINF_CONSTS {-0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7, -0x1.555545995a603p-3, 0x1.99343027bf8c3p-16, \
-                         -0x1.6c087e89a359dp-10, -0x1.ffffffd0c621cp-2, 0x1.55553e1068f19p-5, 0x1.45F306DC9C883p+23, \
-                         0x1.921FB54442D18p0, 0x1.921FB54442D18p-62}
+// the polynomial / reduction constants of __sincosf_table: the three coefficient pairs are stored (sine, cosine) side
+// by side so that the quadrant parity indexes them (one LDC.64 with a register offset each on the device)
+#define TDG_SINF_CONSTS {-0x1.555545995a603p-3, 0x1.55553e1068f19p-5,  /* S1 | C2 */ \
+                         0x1.1107605230bc4p-7, -0x1.6c087e89a359dp-10, /* S2 | C3 */ \
+                         -0x1.994eb3774cf24p-13, 0x1.99343027bf8c3p-16, /* S3 | C4 */ \
+                         -0x1.ffffffd0c621cp-2,                         /* C1 */ \
+                         0x1.45F306DC9C883p+23, 0x1.921FB54442D18p0, 0x1.921FB54442D18p-62}
 static const double kSinfConstHost[10] = TDG_SINF_CONSTS;
 #ifdef __NVCC__
 static __constant__ double kSinfConstDev[10] = TDG_SINF_CONSTS;
@@ -96,62 +98,60 @@ static __constant__ double kSinfConstDev[10] = TDG_SINF_CONSTS;
 #else
 #define TDG_SC(i) kSinfConstHost[i]
 #endif
-enum { SC_S3 = 0, SC_S2, SC_S1, SC_C4, SC_C3, SC_C1, SC_C2, SC_HPI_INV, SC_HPI, SC_PI63 };
+enum { SC_K1 = 0, SC_K2 = 2, SC_K3 = 4, SC_C1 = 6, SC_HPI_INV = 7, SC_HPI = 8, SC_PI63 = 9 };
 TDG_HD uint32_t m_f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
-// sinf_poly (sincosf.h): n even -> sine polynomial of x, n odd -> cosine polynomial of x2; `neg` folds in the
-// quadrant sign (the reference multiplies x by +-1.0 and picks the table with negated cosine coefficients: both
-// polynomials are exactly odd in that sign under round-to-nearest, so negating the result is the same value)
-TDG_HD float m_sinf_poly(double x, double x2, int n, bool neg) {
-    // both polynomials in straight-line code, the quadrant picks the result: neighbouring frames of a warp sit in
-    // different quadrants, so a branch here is always divergent (both sides executed plus the reconvergence
-    // overhead); the operations of the side that is kept are exactly the reference's
-    const double x3 = x * x2;
-    const double s1 = fma(x2, TDG_SC(SC_S3), TDG_SC(SC_S2));
-    const double x7 = x3 * x2;
-    const double s = fma(x3, TDG_SC(SC_S1), x);
-    const double rs = fma(x7, s1, s);
-    const double x4 = x2 * x2;
-    const double c2 = fma(x2, TDG_SC(SC_C4), TDG_SC(SC_C3));
+TDG_HD float m_bits_f32(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+// sinf_poly (sincosf.h): n even -> sine polynomial of x, n odd -> cosine polynomial of x2.  The two have the same
+// shape, so ONE chain evaluates whichever the quadrant asks for, with operands selected by the parity:
+//     sine:    x3 = x*x2;   x7 = x3*x2;  s1 = S2 + x2*S3;  s = x  + x3*S1;  return s + x7*s1
+//     cosine:  x4 = x2*x2;  x6 = x4*x2;  c2 = C3 + x2*C4;  c = c1 + x4*C2;  return c + x6*c2     (c1 = 1 + x2*C1)
+// i.e. p = u*x2 with u = x | x2, q = p*x2, a = K2 + x2*K3, r = base + p*K1 with base = x | c1, result r + q*a: seven
+// double operations instead of the twelve of both polynomials side by side (neighbouring frames of a warp sit in
+// different quadrants, so a branch would execute both sides anyway); the operations of the side that is kept are
+// exactly the reference's.  `negmask` (0 or 0x80000000) folds in the quadrant sign: the reference multiplies x by
+// +-1.0 and picks the table with negated cosine coefficients, and both polynomials are exactly odd in that sign under
+// round-to-nearest, so flipping the sign bit of the result is the same value.
+TDG_HD float m_sinf_poly(double x, uint32_t oddbit, uint32_t odd, uint32_t negmask) {   // oddbit != 0 <=> odd == 1
+    const double x2 = x * x;
+    const double u = oddbit ? x2 : x;
+    const double p = u * x2;
+    const double q = p * x2;
+    const double a = fma(x2, TDG_SC(SC_K3 + odd), TDG_SC(SC_K2 + odd));
     const double c1 = fma(x2, TDG_SC(SC_C1), 1.0);
-    const double x6 = x4 * x2;
-    const double c = fma(x4, TDG_SC(SC_C2), c1);
-    const double rc = fma(x6, c2, c);
-    const float f = (float)((n & 1) ? rc : rs);
-    return neg ? -f : f;
+    const double base = oddbit ? c1 : x;
+    const double r = fma(p, TDG_SC(SC_K1 + odd), base);
+    return m_bits_f32(m_f32_bits((float)fma(q, a, r)) ^ negmask);
 }
+// Quadrant bookkeeping: the reference's sign table {1,-1,-1,1}[(n + sign) & 3] together with its table switch on
+// (n + sign) & 2 reduces to "negate iff bit 1 of n differs from the sign of y" for both parities of n (n even:
+// sin(x * s) with s from the sign table; n odd: +-cos(x) by the table switch; (n + sign) carries into bit 1 exactly
+// when n is odd and y negative).  reduce_fast works on the signed x, so there it is bit 1 of n alone.
 TDG_HD float m_sinf_glibc(float y) {
     const uint32_t bits = m_f32_bits(y);
-    const uint32_t top = (bits >> 20) & 0x7ffu;                      // abstop12
-    double x = (double)y;
-    if (top < 0x3f4u) {                                              // |y| < pi/4 (abstop12(0x1.921FB6p-1f))
-        if (top < 0x398u) return y;                                  // |y| < 2^-12
-        return m_sinf_poly(x, x * x, 0, false);
-    }
-    if (top < 0x42fu) {                                              // |y| < 120: reduce_fast
-        const double r = x * TDG_SC(SC_HPI_INV);
-        const int n = ((int32_t)r + 0x800000) >> 24;
-        x = fma(-(double)n, TDG_SC(SC_HPI), x);
-        const int m = n & 3;
-        return m_sinf_poly(x, x * x, n, (n & 1) ? (m >> 1) != 0 : (m == 1 || m == 2));
-    }
-    if (top < 0x7f8u) {                                              // finite: reduce_large
+    const uint32_t top = bits & 0x7ff00000u;                         // abstop12, in place
+    if (top >= 0x42f00000u) {                                        // |y| >= 120 (every late-timeline argument)
+        if (top >= 0x7f800000u) return y - y;                        // inf / NaN -> NaN (__math_invalidf)
+        // reduce_large: y's 24-bit significand times a 96-bit window of the bits of 4/pi, kept to 64 bits
         const uint32_t* arr = &TDG_INV_PIO4[(bits >> 26) & 15];
-        const int shift = (int)((bits >> 23) & 7);
-        const int sign = (int)(bits >> 31);
-        uint32_t xi = (bits & 0xffffffu) | 0x800000u;
-        xi <<= shift;
-        uint64_t res0 = (uint64_t)(uint32_t)(xi * arr[0]);
-        const uint64_t res1 = (uint64_t)xi * arr[4];
-        const uint64_t res2 = (uint64_t)xi * arr[8];
-        res0 = (res2 >> 32) | (res0 << 32);
-        res0 += res1;
-        const uint64_t nn = (res0 + (1ULL << 61)) >> 62;
-        res0 -= nn << 62;
-        x = (double)(int64_t)res0 * TDG_SC(SC_PI63);
-        const int n = (int)nn, m = (n + sign) & 3;
-        return m_sinf_poly(x, x * x, n, (n & 1) ? (m >> 1) != 0 : (m == 1 || m == 2));
+        const uint32_t xi = ((bits & 0x7fffffu) | 0x800000u) << ((bits >> 23) & 7);
+        const uint32_t p0 = xi * arr[0];
+        const uint64_t r2 = (uint64_t)xi * arr[8];
+        const uint64_t res = (uint64_t)xi * arr[4] + (((uint64_t)p0 << 32) | (r2 >> 32));
+        uint32_t hi = (uint32_t)(res >> 32);
+        const uint32_t hq = hi + 0x20000000u;                        // n = hq >> 30 (quadrant, rounded to nearest)
+        hi -= hq & 0xc0000000u;                                      // res -= n << 62
+        const double x = (double)(int64_t)(((uint64_t)hi << 32) | (uint32_t)res) * TDG_SC(SC_PI63);
+        return m_sinf_poly(x, hq & 0x40000000u, (hq >> 30) & 1u, (hq ^ bits) & 0x80000000u);
     }
-    return y - y;                                                    // inf / NaN -> NaN (__math_invalidf)
+    double x = (double)y;
+    if (top < 0x3f400000u) {                                         // |y| < pi/4 (abstop12(0x1.921FB6p-1f))
+        if (top < 0x39800000u) return y;                             // |y| < 2^-12
+        return m_sinf_poly(x, 0u, 0u, 0u);
+    }
+    const double r = x * TDG_SC(SC_HPI_INV);                         // |y| < 120: reduce_fast
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    x = fma(-(double)n, TDG_SC(SC_HPI), x);
+    return m_sinf_poly(x, (uint32_t)n & 1u, (uint32_t)n & 1u, ((uint32_t)n << 30) & 0x80000000u);
 }
 
 // ---- AdsrK: host builder (plain C++, same f32 operations as the reference's expressions) ---------
