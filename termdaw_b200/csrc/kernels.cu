@@ -236,14 +236,23 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
     return 1.0f + T.wet * (adsr_vel - 1.0f);             // lerp(1.0, adsr_vel, wet)
 }
 
+// k_fx<adsr> is latency bound, not issue bound (ncu: issue slots 56 % busy, 7.7 stall cycles of long_scoreboard per
+// issue): a block's life is a chain of dependent loads (task -> segment range -> segment states) in front of a few
+// hundred instructions, and with one 4-frame run per thread only 16 KB of input + output were in flight per block.
+// Blocks of 128 threads own TWO runs per thread (frames i and i + 512 of a 1024-frame chunk) and load the inputs of
+// both before the first is evaluated: twice the bytes in flight per thread behind the same chain.
+#ifndef TDG_ADSR_THREADS
+#define TDG_ADSR_THREADS 128
+#endif
 #ifndef TDG_ADSR_MINB
-#define TDG_ADSR_MINB 5      // measured: 4 -> 9.0 ms, 5 -> 8.3 ms, 6 -> 8.5 ms per bench step
+#define TDG_ADSR_MINB 8      // 64 registers per thread
 #endif
 #ifndef TDG_BP_MINB
 #define TDG_BP_MINB 5        // measured: 4 -> 6.66 ms, 5 -> 6.48 ms, 6 -> 6.95 ms
 #endif
 template <int MODE, bool VEC, bool EXACT>
-__global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(MODE == FX_ADSR ? TDG_ADSR_THREADS : TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    constexpr uint32_t NT = MODE == FX_ADSR ? TDG_ADSR_THREADS : TDG_THREADS;
     __shared__ FxTask T;
     load_task(&T, tasks + blockIdx.y);
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
@@ -278,9 +287,9 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB :
             }
         }
     };
-    float l[4], r[4];
+    float l[4], r[4], l2[4], r2[4];
     const uint32_t i_first = threadIdx.x * 4;
-    bool have = false;
+    bool have = false, have2 = false;
     uint32_t n_seg = 0;
     float maxmul = 0.0f, minmul = 0.0f;
     const AdsrSeg* __restrict__ segs = nullptr;
@@ -298,10 +307,11 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB :
         n_seg = T.seg_ptr[k + 1] - s_lo;
         segs = T.segs + s_lo;
         if (i_first < bl) { load_sum(i_first, l, r); have = true; }
+        if (i_first + NT * 4 < bl) { load_sum(i_first + NT * 4, l2, r2); have2 = true; }
         maxmul = T.use_max ? 1.0f : 0.0f; minmul = 1.0f - maxmul;
     }
     float peak = 0.0f;
-    for (uint32_t i = i_first; i < bl; i += TDG_THREADS * 4) {
+    for (uint32_t i = i_first; i < bl; i += NT * 4) {
         const int nv = min(4u, bl - i);
         const uint64_t p = p0 + i;
         if (!have) load_sum(i, l, r);
@@ -372,6 +382,12 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB :
         if (MODE != FX_NORM_PEAK || !T.no_store) {
             st4<VEC>(T.h.out_l, p, nv, l);
             st4<VEC>(T.h.out_r, p, nv, r);
+        }
+        if (MODE == FX_ADSR && have2) {                      // the run loaded ahead becomes the current one
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { l[j] = l2[j]; r[j] = r2[j]; }
+            have = true; have2 = false;
+            if (i + 2 * NT * 4 < bl) { load_sum(i + 2 * NT * 4, l2, r2); have2 = true; }
         }
     }
     if (MODE == FX_NORM_PEAK) {
@@ -471,7 +487,10 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __r
         const int nv = min(4u, bl - i);
         // (a per-chunk phase table from the host was measured slower than this modulo: the extra dependent
         // load at the head of every block costs more than the arithmetic it saves)
-        uint64_t s = (T.t0 + p0 + i) % len;
+        const uint64_t at = T.t0 + p0 + i;
+        // 64-bit division is a ~60-instruction subroutine on the SM; a timeline shorter than 2^32 frames (24 h at
+        // 48 kHz) and a sample shorter than 2^32 frames take the 32-bit form
+        uint64_t s = ((at | len) >> 32) == 0 ? (uint64_t)((uint32_t)at % (uint32_t)len) : at % len;
         float l[4], r[4];
         if (s + 3 < len) {                                        // no wrap inside the run
             const float* __restrict__ pl = T.sl + s;
@@ -1004,47 +1023,123 @@ __global__ void __launch_bounds__(kBpThreads, TDG_BP_MINB) k_bp_apply(const BpTa
     if (T.x.ranks <= 1 && nv > 0 && p + nv == T.h.n_frames) { T.state[0] = ll; T.state[1] = lr; T.state[2] = hl; T.state[3] = hr; }
 }
 
-// Single pass: aggregate, look back, apply in ONE kernel — every input is read once (16 + 8*(indeg-1) bytes per frame
-// where the three-launch scan moves 24 + 16*(indeg-1)).  A block takes its tile from a per-filter ticket (tiles start
-// in ticket order, so everything a tile waits for belongs to a block that is already running), publishes the tile's
-// affine map, and finds the state entering the tile from (a) the state leaving the previous GROUP of kBpGroup tiles,
-// published by that group's last tile, pushed through (b) the maps of the tiles of its own group in front of it.
-// The composition is a fixed tree over the warp's lanes — which map meets which is decided by tile numbers alone,
-// never by timing — so the result is the same bits on every run (a free-running decoupled look-back would not be).
-// The cross-group chain is serial (n_tiles / 32 steps), hence kBpFusedMaxTiles.
+// Single pass: aggregate, look back, apply in ONE kernel — every input is read from HBM once (16 + 8*(indeg-1) bytes
+// per frame where the three-launch scan moves 24 + 16*(indeg-1)).
+//
+// A block owns a STRIP of kBpStrip = 8192 consecutive frames, 32 per thread:
+//   1. coalesced float4 loads of every input, summed in edge order, into shared memory (rows of 32 frames padded to 36
+//      words: the float4 stores of this phase and the float4 row reads of the next are both bank-conflict free);
+//   2. every thread folds ITS 32 consecutive frames from a zero state (the reference's operations), ONE block scan
+//      composes the 256 maps, thread 0 publishes the strip's map;
+//   3. warp 0 finds the state entering the strip: (a) the state leaving the previous GROUP of kBpGroup strips,
+//      published by that group's last strip, pushed through (b) the maps of the strips of its own group in front of
+//      it.  The composition is a fixed tree over the warp's lanes — which map meets which is decided by strip numbers
+//      alone, never by timing — so the result is the same bits on every run (a free-running decoupled look-back would
+//      not be).  Strips are handed out by a per-filter ticket: everything a strip waits for belongs to a block that
+//      is already running;
+//   4. every thread re-runs the reference's exact recurrence over its 32 frames from the carried-in state, writes the
+//      outputs back into its shared-memory row, and the block stores them with coalesced float4 writes.
+// Against the first version (2048-frame tiles, 8 frames per thread, inputs re-read from registers): one scan, one
+// ticket, one publication and one look-back per 8192 frames instead of four, and the serial cross-group chain is four
+// times shorter (n_strips / 32 steps; hence kBpFusedMaxTiles).
 __device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 template <bool VEC>
-__global__ void __launch_bounds__(kBpThreads, TDG_BP_MINB) k_bp_fused(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+#ifdef __NVCC__
+    extern __shared__ float4 s_dyn4[];
+    float* const s_l = reinterpret_cast<float*>(s_dyn4);
+#else
+    alignas(16) static float s_emu[2 * kBpThreads * kBpRow];     // tests/emu: one block in flight at a time
+    float* const s_l = s_emu;
+#endif
+    float* const s_r = s_l + kBpThreads * kBpRow;
     __shared__ BpTask T;
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_strip;
     __shared__ float s_carry[4];
-    // grid = (filters, tiles): consecutive blocks belong to DIFFERENT filters, so the blocks resident at any time
-    // advance many filters' group chains at once (with the tiles of one filter side by side the whole GPU waits
-    // on that filter's serial chain: measured 23 ms per step instead of 9.4)
+    // grid = (filters, strips): consecutive blocks belong to DIFFERENT filters, so the blocks resident at any time
+    // advance many filters' group chains at once (with the strips of one filter side by side the whole GPU waits
+    // on that filter's serial chain)
     load_task(&T, tasks + blockIdx.x);
-    if (blockIdx.y >= T.n_tiles) return;
-    if (threadIdx.x == 0) s_tile = atomicAdd(T.sync, 1u);
+    if (blockIdx.y >= (T.n_tiles + kBpStripTiles - 1) / kBpStripTiles) return;
+    if (threadIdx.x == 0) s_strip = atomicAdd(T.sync, 1u);
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t strip = s_strip;
     const float* const* ins = T.n_in <= (uint32_t)kInlineInputs ? T.ins : reinterpret_cast<const float* const*>(blob + T.in_off);
-    const uint64_t p = (uint64_t)tile * kBpTile + (uint64_t)threadIdx.x * 8;
-    const int nv = p >= T.h.n_frames ? 0 : (int)min((uint64_t)8, T.h.n_frames - p);
-    float xl[8], xr[8];
-    bp_load_run<VEC>(T, ins, p, nv, xl, xr);
-    const Aff mine = bp_fold_run(T, xl, xr, nv);
+    const uint64_t pb = (uint64_t)strip * kBpStrip;
+    const uint32_t n_here = (uint32_t)min((uint64_t)kBpStrip, T.h.n_frames - pb);                    // frames of the pass in this strip
+    const uint32_t n_cov = (uint32_t)min((uint64_t)kBpStrip, (uint64_t)T.n_tiles * kBpTile - pb);    // frames the (padded) buffers cover
+    // ---- 1. inputs -> shared memory (float4 q of the strip lands in row q / 8, words 4 * (q % 8) ..)
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float l[4][4], r[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { l[u][j] = 0.0f; r[u][j] = 0.0f; }
+        for (uint32_t a = 0; a < T.n_in; ++a) {
+            float x[4][4], y[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t f = 4u * (threadIdx.x + kBpThreads * (4 * half + u));
+                const int nv = f >= n_here ? 0 : (int)min(4u, n_here - f);
+                if (f < n_cov) { ld4<VEC>(ins[2 * a], pb + f, nv, x[u]); ld4<VEC>(ins[2 * a + 1], pb + f, nv, y[u]); }
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { x[u][j] = 0.0f; y[u][j] = 0.0f; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { l[u][j] += x[u][j]; r[u][j] += y[u][j]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t q = threadIdx.x + kBpThreads * (4 * half + u), w = (q >> 3) * kBpRow + 4 * (q & 7);
+            *reinterpret_cast<float4*>(s_l + w) = make_float4(l[u][0], l[u][1], l[u][2], l[u][3]);
+            *reinterpret_cast<float4*>(s_r + w) = make_float4(r[u][0], r[u][1], r[u][2], r[u][3]);
+        }
+    }
+    __syncthreads();
+    // ---- 2. the thread's 32 frames from a zero state
+    const uint32_t f0 = threadIdx.x * kBpFpt;
+    const int nv = f0 >= n_here ? 0 : (int)min((uint32_t)kBpFpt, n_here - f0);
+    float* const row_l = s_l + threadIdx.x * kBpRow;
+    float* const row_r = s_r + threadIdx.x * kBpRow;
+    Aff mine;
+    {
+        float ll = 0.0f, lr = 0.0f, hl = 0.0f, hr = 0.0f, al = 1.0f, ah = 1.0f;
+        const float dl = 1.0f - T.lgamma, dh = 1.0f - T.hgamma;
+#pragma unroll 2
+        for (int k = 0; k < kBpFpt / 4; ++k) {
+            if (4 * k >= nv) break;
+            const float4 a = *reinterpret_cast<const float4*>(row_l + 4 * k), b = *reinterpret_cast<const float4*>(row_r + 4 * k);
+            const float xl[4] = {a.x, a.y, a.z, a.w}, xr[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (4 * k + j < nv) {
+                    ll = ll + T.lgamma * (xl[j] - ll); lr = lr + T.lgamma * (xr[j] - lr);
+                    hl = hl + T.hgamma * (xl[j] - hl); hr = hr + T.hgamma * (xr[j] - hr);
+                    al *= dl; ah *= dh;
+                }
+            }
+        }
+        mine = Aff{al, ah, ll, lr, hl, hr};
+    }
     Aff total;
     const Aff exc = block_aff_scan(mine, &total);
+    // ---- 3. publish, look back
     uint32_t* flags = T.sync + 1;
     if (threadIdx.x < 32) {
         const uint32_t ln = threadIdx.x;
-        if (ln == 0) {                                          // publish this tile's map, then the flag
-            float* a = T.agg + (size_t)tile * 8;
+        if (ln == 0) {                                          // publish this strip's map, then the flag
+            float* a = T.agg + (size_t)strip * 8;
             a[0] = total.b0; a[1] = total.b1; a[2] = total.b2; a[3] = total.b3; a[4] = total.al; a[5] = total.ah;
             __threadfence();
-            *reinterpret_cast<volatile uint32_t*>(flags + tile) = 1u;
+            *reinterpret_cast<volatile uint32_t*>(flags + strip) = 1u;
         }
-        const uint32_t base = (tile / kBpGroup) * kBpGroup, n_before = tile - base;
-        // lane q < n_before: the map of tile base + q (wait for its publication); the other lanes: identity
+        const uint32_t base = (strip / kBpGroup) * kBpGroup, n_before = strip - base;
+        // lane q < n_before: the map of strip base + q (wait for its publication); the other lanes: identity
         Aff m = aff_id();
         if (ln < n_before) {
             while (ld_flag(flags + base + ln) < 1u) {}
@@ -1057,7 +1152,7 @@ __global__ void __launch_bounds__(kBpThreads, TDG_BP_MINB) k_bp_fused(const BpTa
             const Aff up = aff_shfl_up(m, d);
             if (ln >= (uint32_t)d) m = aff_then(up, m);
         }
-        // lane 31 holds the map of tiles [base, tile) (identity lanes do not change it)
+        // lane 31 holds the map of strips [base, strip) (identity lanes do not change it)
         if (ln == 31) {
             float st[4];
             if (base == 0) {
@@ -1076,47 +1171,63 @@ __global__ void __launch_bounds__(kBpThreads, TDG_BP_MINB) k_bp_fused(const BpTa
             const float c0 = fmaf(m.al, st[0], m.b0), c1 = fmaf(m.al, st[1], m.b1);
             const float c2 = fmaf(m.ah, st[2], m.b2), c3 = fmaf(m.ah, st[3], m.b3);
             s_carry[0] = c0; s_carry[1] = c1; s_carry[2] = c2; s_carry[3] = c3;
-            if ((tile + 1) % kBpGroup == 0 && tile + 1 < T.n_tiles) {   // the state leaving this group, for the next one
-                float* c = T.carry + (size_t)tile * 4;
+            if ((strip + 1) % kBpGroup == 0 && (uint64_t)(strip + 1) * kBpStrip < T.h.n_frames) {   // the state leaving this group, for the next one
+                float* c = T.carry + (size_t)strip * 4;
                 c[0] = fmaf(total.al, c0, total.b0); c[1] = fmaf(total.al, c1, total.b1);
                 c[2] = fmaf(total.ah, c2, total.b2); c[3] = fmaf(total.ah, c3, total.b3);
                 __threadfence();
-                *reinterpret_cast<volatile uint32_t*>(flags + tile) = 2u;
+                *reinterpret_cast<volatile uint32_t*>(flags + strip) = 2u;
             }
         }
     }
     __syncthreads();
-    float ll = fmaf(exc.al, s_carry[0], exc.b0), lr = fmaf(exc.al, s_carry[1], exc.b1);
-    float hl = fmaf(exc.ah, s_carry[2], exc.b2), hr = fmaf(exc.ah, s_carry[3], exc.b3);
-    const float lmul = T.lgamma == 0.0f ? 0.0f : 1.0f, hmul = T.hgamma == 0.0f ? 0.0f : 1.0f;
-    const float pass_mul = T.pass ? 1.0f : 0.0f, cut_mul = 1.0f - pass_mul;
-    float ol[8], orr[8];
+    // ---- 4. the exact recurrence from the carried-in state; outputs replace the inputs in the thread's row
+    {
+        float ll = fmaf(exc.al, s_carry[0], exc.b0), lr = fmaf(exc.al, s_carry[1], exc.b1);
+        float hl = fmaf(exc.ah, s_carry[2], exc.b2), hr = fmaf(exc.ah, s_carry[3], exc.b3);
+        const float lmul = T.lgamma == 0.0f ? 0.0f : 1.0f, hmul = T.hgamma == 0.0f ? 0.0f : 1.0f;
+        const float pass_mul = T.pass ? 1.0f : 0.0f, cut_mul = 1.0f - pass_mul;
+#pragma unroll 2
+        for (int k = 0; k < kBpFpt / 4; ++k) {
+            if (4 * k >= nv) break;
+            const float4 a4 = *reinterpret_cast<const float4*>(row_l + 4 * k), b4 = *reinterpret_cast<const float4*>(row_r + 4 * k);
+            const float xl[4] = {a4.x, a4.y, a4.z, a4.w}, xr[4] = {b4.x, b4.y, b4.z, b4.w};
+            float ol[4], orr[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (j < nv) {                                           // extensions.rs:671-688
-            const float l = xl[j], r = xr[j];
-            ll = ll + T.lgamma * (l - ll); lr = lr + T.lgamma * (r - lr);
-            hl = hl + T.hgamma * (l - hl); hr = hr + T.hgamma * (r - hr);
-            const float cutl = (lmul * ll + hmul * (l - hl)) * 0.5f;
-            const float cutr = (lmul * lr + hmul * (r - hr)) * 0.5f;
-            const float passl = l - cutl;
-            const float passr = r - cutl;                       // sic (extensions.rs:685)
-            float a = cutl * cut_mul + passl * pass_mul;
-            float b = cutr * cut_mul + passr * pass_mul;
-            apply_pg(a, b, T.h.pg);
-            ol[j] = a; orr[j] = b;
-        } else { ol[j] = 0.0f; orr[j] = 0.0f; }
+            for (int j = 0; j < 4; ++j) {
+                if (4 * k + j < nv) {                                   // extensions.rs:671-688
+                    const float l = xl[j], r = xr[j];
+                    ll = ll + T.lgamma * (l - ll); lr = lr + T.lgamma * (r - lr);
+                    hl = hl + T.hgamma * (l - hl); hr = hr + T.hgamma * (r - hr);
+                    const float cutl = (lmul * ll + hmul * (l - hl)) * 0.5f;
+                    const float cutr = (lmul * lr + hmul * (r - hr)) * 0.5f;
+                    const float passl = l - cutl;
+                    const float passr = r - cutl;                       // sic (extensions.rs:685)
+                    float a = cutl * cut_mul + passl * pass_mul;
+                    float b = cutr * cut_mul + passr * pass_mul;
+                    apply_pg(a, b, T.h.pg);
+                    ol[j] = a; orr[j] = b;
+                } else { ol[j] = 0.0f; orr[j] = 0.0f; }
+            }
+            *reinterpret_cast<float4*>(row_l + 4 * k) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+            *reinterpret_cast<float4*>(row_r + 4 * k) = make_float4(orr[0], orr[1], orr[2], orr[3]);
+        }
+        // the run holding the last frame of the pass leaves the state for the next pass
+        if (nv > 0 && pb + f0 + nv == T.h.n_frames) { T.state[0] = ll; T.state[1] = lr; T.state[2] = hl; T.state[3] = hr; }
     }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int nvh = max(0, min(4, nv - 4 * h));
-        if (nvh == 0) continue;
-        float a[4] = {ol[4 * h], ol[4 * h + 1], ol[4 * h + 2], ol[4 * h + 3]};
-        float b[4] = {orr[4 * h], orr[4 * h + 1], orr[4 * h + 2], orr[4 * h + 3]};
-        if (VEC && nvh == 4) { st4<true>(T.h.out_l, p + 4 * h, 4, a); st4<true>(T.h.out_r, p + 4 * h, 4, b); }
-        else { st4<false>(T.h.out_l, p + 4 * h, nvh, a); st4<false>(T.h.out_r, p + 4 * h, nvh, b); }
+    __syncthreads();
+    // ---- 5. shared memory -> output, coalesced
+#pragma unroll 4
+    for (int i = 0; i < kBpFpt / 4; ++i) {
+        const uint32_t q = threadIdx.x + kBpThreads * i, f = 4 * q;
+        if (f >= n_here) break;
+        const int nvq = (int)min(4u, n_here - f);
+        const uint32_t w = (q >> 3) * kBpRow + 4 * (q & 7);
+        const float4 a4 = *reinterpret_cast<const float4*>(s_l + w), b4 = *reinterpret_cast<const float4*>(s_r + w);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+        if (VEC && nvq == 4) { st4<true>(T.h.out_l, pb + f, 4, a); st4<true>(T.h.out_r, pb + f, 4, b); }
+        else { st4<false>(T.h.out_l, pb + f, nvq, a); st4<false>(T.h.out_r, pb + f, nvq, b); }
     }
-    if (nv > 0 && p + nv == T.h.n_frames) { T.state[0] = ll; T.state[1] = lr; T.state[2] = hl; T.state[3] = hr; }
 }
 
 // ------------------------------------------------------------------------------------ K9b: quantise
@@ -1369,8 +1480,8 @@ cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks
     const dim3 g = grid2(max_chunks, n);
     if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_SUM, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
     else if (mode == FX_ADSR) {
-        if (exact) { if (vec) k_fx<FX_ADSR, true, true><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, true><<<g, TDG_THREADS, 0, s>>>(t, blob); }
-        else { if (vec) k_fx<FX_ADSR, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
+        if (exact) { if (vec) k_fx<FX_ADSR, true, true><<<g, TDG_ADSR_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, true><<<g, TDG_ADSR_THREADS, 0, s>>>(t, blob); }
+        else { if (vec) k_fx<FX_ADSR, true, false><<<g, TDG_ADSR_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, false><<<g, TDG_ADSR_THREADS, 0, s>>>(t, blob); }
     }
     else { if (vec) k_fx<FX_NORM_PEAK, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_NORM_PEAK, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
     return cudaGetLastError();
@@ -1460,7 +1571,15 @@ cudaError_t launch_bp_apply(const BpTask* t, uint32_t n, uint32_t max_tiles, boo
     return cudaGetLastError();
 }
 cudaError_t launch_bp_fused(const BpTask* t, uint32_t n, uint32_t max_tiles, bool vec, const uint8_t* blob, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_bp_fused, <<<dim3(n, max_tiles ? max_tiles : 1, 1), kBpThreads, 0, s>>>(t, blob));
+    static bool attr_set = false;
+    if (!attr_set) {          // 72 KB of dynamic shared memory per block: opt in once (three blocks per SM)
+        cudaError_t e = cudaFuncSetAttribute(k_bp_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBpStripSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_bp_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBpStripSmem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const uint32_t max_strips = (max_tiles + kBpStripTiles - 1) / kBpStripTiles;
+    TDG_VEC_DISPATCH(vec, k_bp_fused, <<<dim3(n, max_strips ? max_strips : 1, 1), kBpThreads, kBpStripSmem, s>>>(t, blob));
     return cudaGetLastError();
 }
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s) {
