@@ -199,7 +199,7 @@ struct Engine {
     // step has 735 launch triples whose one-block-per-filter carry kernels and short grids cost far more (28 ms) than the
     // L2 hits save, so the default is one launch triple per level (0); the knob stays for single long renders (TDG_BP_L2_MB)
     uint64_t bp_l2_bytes = 0;
-    bool bp_fused = false;                       // single-pass band pass where no exchange step is needed (TDG_BP_FUSED=1; default: three launches)
+    bool bp_fused = true;                        // single-pass band pass (k_bp_fused) where no exchange step is needed and the pass is <= kBpFusedMaxTiles long; TDG_BP_FUSED=0: three launches
     bool libm_sin = true;                        // oscillators evaluate glibc's sinf exactly (TDG_FAST_SIN=1 / tdg_set_oscillator_mode(ctx, 0): f32 polynomial, <= 2 ulp)
     WorkerPool* pool = nullptr;                  // planner threads (created on first batched pass)
     std::vector<Frag>* frags = nullptr;          // pooled per-project plan fragments (capacity is kept between jobs)

@@ -236,30 +236,30 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
     return 1.0f + T.wet * (adsr_vel - 1.0f);             // lerp(1.0, adsr_vel, wet)
 }
 
-// k_fx<adsr> is latency bound, not issue bound (ncu: issue slots 56 % busy, 7.7 stall cycles of long_scoreboard per
-// issue): a block's life is a chain of dependent loads (task -> segment range -> segment states) in front of a few
-// hundred instructions, and with one 4-frame run per thread only 16 KB of input + output were in flight per block.
-// Blocks of 128 threads own TWO runs per thread (frames i and i + 512 of a 1024-frame chunk) and load the inputs of
-// both before the first is evaluated: twice the bytes in flight per thread behind the same chain.
-#ifndef TDG_ADSR_THREADS
-#define TDG_ADSR_THREADS 128
-#endif
+// (Blocks of 128 threads owning two 4-frame runs per thread, both loaded ahead, were measured at 12.7 ms per bench step
+// against 7.2 for this shape: the second pair of accumulators pushes the envelope code into local memory.)
 #ifndef TDG_ADSR_MINB
-#define TDG_ADSR_MINB 8      // 64 registers per thread
+#define TDG_ADSR_MINB 5      // measured: 4 -> 9.0 ms, 5 -> 8.3 ms, 6 -> 8.5 ms per bench step
+#endif
+#ifndef TDG_ADSR_CPB
+#define TDG_ADSR_CPB 1       // chunks per block of k_fx<adsr>
 #endif
 #ifndef TDG_BP_MINB
 #define TDG_BP_MINB 5        // measured: 4 -> 6.66 ms, 5 -> 6.48 ms, 6 -> 6.95 ms
 #endif
 template <int MODE, bool VEC, bool EXACT>
-__global__ void __launch_bounds__(MODE == FX_ADSR ? TDG_ADSR_THREADS : TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
-    constexpr uint32_t NT = MODE == FX_ADSR ? TDG_ADSR_THREADS : TDG_THREADS;
+__global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ FxTask T;
     load_task(&T, tasks + blockIdx.y);
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
-    const uint32_t k = blockIdx.x;
-    if (k >= T.h.n_chunks) return;
+    // the adsr variant walks TDG_ADSR_CPB consecutive chunks per block (see the gather kernels: the task load, its
+    // barrier and the block launch are paid once per group of chunks)
+    constexpr uint32_t CPB = MODE == FX_ADSR ? TDG_ADSR_CPB : 1;
+    const uint32_t kc0 = blockIdx.x * CPB;
+    if (kc0 >= T.h.n_chunks) return;
+    const uint32_t kc1 = CPB == 1 ? kc0 + 1 : min(kc0 + CPB, T.h.n_chunks);
     const uint32_t bl = T.h.bl;
-    const uint64_t p0 = (uint64_t)k * bl;
+    uint64_t p0 = 0;
     const bool staged = T.n_in <= (uint32_t)kInlineInputs;     // input pointers arrived with the task (shared memory)
     const float* const* ins = staged ? T.ins : reinterpret_cast<const float* const*>(blob + T.in_off);
     // sum_inputs for the four frames at chunk offset i (edge order: the f32 sum is order dependent)
@@ -287,11 +287,15 @@ __global__ void __launch_bounds__(MODE == FX_ADSR ? TDG_ADSR_THREADS : TDG_THREA
             }
         }
     };
-    float l[4], r[4], l2[4], r2[4];
+    float l[4], r[4];
     const uint32_t i_first = threadIdx.x * 4;
-    bool have = false, have2 = false;
-    uint32_t n_seg = 0;
     float maxmul = 0.0f, minmul = 0.0f;
+    if (MODE == FX_ADSR) { maxmul = T.use_max ? 1.0f : 0.0f; minmul = 1.0f - maxmul; }
+#pragma unroll 1
+    for (uint32_t k = kc0; k < kc1; ++k) {
+    p0 = (uint64_t)k * bl;
+    bool have = false;
+    uint32_t n_seg = 0;
     const AdsrSeg* __restrict__ segs = nullptr;
     // state q of the chunk, straight from the device-built table (the same address for the whole block: one
     // L1-resident broadcast per read, no staging and no barrier: the block's warps never wait for each other)
@@ -307,11 +311,9 @@ __global__ void __launch_bounds__(MODE == FX_ADSR ? TDG_ADSR_THREADS : TDG_THREA
         n_seg = T.seg_ptr[k + 1] - s_lo;
         segs = T.segs + s_lo;
         if (i_first < bl) { load_sum(i_first, l, r); have = true; }
-        if (i_first + NT * 4 < bl) { load_sum(i_first + NT * 4, l2, r2); have2 = true; }
-        maxmul = T.use_max ? 1.0f : 0.0f; minmul = 1.0f - maxmul;
     }
     float peak = 0.0f;
-    for (uint32_t i = i_first; i < bl; i += NT * 4) {
+    for (uint32_t i = i_first; i < bl; i += TDG_THREADS * 4) {
         const int nv = min(4u, bl - i);
         const uint64_t p = p0 + i;
         if (!have) load_sum(i, l, r);
@@ -383,16 +385,11 @@ __global__ void __launch_bounds__(MODE == FX_ADSR ? TDG_ADSR_THREADS : TDG_THREA
             st4<VEC>(T.h.out_l, p, nv, l);
             st4<VEC>(T.h.out_r, p, nv, r);
         }
-        if (MODE == FX_ADSR && have2) {                      // the run loaded ahead becomes the current one
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { l[j] = l2[j]; r[j] = r2[j]; }
-            have = true; have2 = false;
-            if (i + 2 * NT * 4 < bl) { load_sum(i + 2 * NT * 4, l2, r2); have2 = true; }
-        }
     }
     if (MODE == FX_NORM_PEAK) {
         peak = block_max(peak);
         if (threadIdx.x == 0) T.peaks[k] = peak;
+    }
     }
 }
 
@@ -473,16 +470,27 @@ __global__ void __launch_bounds__(TDG_THREADS) k_norm_scale(const NormScaleTask*
 }
 
 // ------------------------------------------------------------------------------------ K2: sample gathers
+// A chunk is 1024 frames: 8 KB of output per block behind a chain of dependent loads (task -> [range -> hits ->]
+// sample), and ncu shows these kernels waiting on exactly that chain (13-15 stall cycles of long_scoreboard per issue
+// at 85 % occupancy, DRAM 40-47 % busy).  A block therefore walks TDG_GATHER_CPB consecutive chunks of its vertex: the
+// task load, the barrier behind it and the block launch are paid once per 4 chunks, and the range of the next chunk is
+// fetched while the current one is evaluated.
+#ifndef TDG_GATHER_CPB
+#define TDG_GATHER_CPB 4
+#endif
 // sample_loop_gen (extensions.rs:331-341): buf[i] = sample[(t + i) % L]
 template <bool VEC>
 __global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __restrict__ tasks) {
     __shared__ LoopTask T;
     load_task(&T, tasks + blockIdx.y);
-    const uint32_t k = blockIdx.x;
-    if (k >= T.h.n_chunks) return;
+    const uint32_t kc0 = blockIdx.x * TDG_GATHER_CPB;
+    if (kc0 >= T.h.n_chunks) return;
+    const uint32_t kc1 = min(kc0 + (uint32_t)TDG_GATHER_CPB, T.h.n_chunks);
     const uint32_t bl = T.h.bl;
-    const uint64_t p0 = (uint64_t)k * bl;
     const uint64_t len = T.len;
+#pragma unroll 1
+    for (uint32_t k = kc0; k < kc1; ++k) {
+    const uint64_t p0 = (uint64_t)k * bl;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
         const int nv = min(4u, bl - i);
         // (a per-chunk phase table from the host was measured slower than this modulo: the extra dependent
@@ -508,6 +516,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __r
         st4<VEC>(T.h.out_l, p0 + i, nv, l);
         st4<VEC>(T.h.out_r, p0 + i, nv, r);
     }
+    }
 }
 
 // sample_multi_gen (extensions.rs:344-381): every live hit adds sample[pos]*vel in deque order.
@@ -517,15 +526,20 @@ template <bool VEC>
 __global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ MultiTask T;
     load_task(&T, tasks + blockIdx.y);
-    const uint32_t k = blockIdx.x;
-    if (k >= T.h.n_chunks) return;
+    const uint32_t kc0 = blockIdx.x * TDG_GATHER_CPB;
+    if (kc0 >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
-    const int64_t p0 = (int64_t)k * bl;
     const MultiHit* hits = reinterpret_cast<const MultiHit*>(blob + T.hits_off);
-    // candidates for this chunk: start > p0 - L  and  start <= p0 + bl - 1 (k_chunk_ranges)
-    const Range2 rg = T.ranges[k];
-    const uint32_t lo = rg.x, hi = rg.y;
+    // candidates for a chunk: start > p0 - L  and  start <= p0 + bl - 1 (k_chunk_ranges)
+    const uint32_t kc1 = min(kc0 + (uint32_t)TDG_GATHER_CPB, T.h.n_chunks);
+    Range2 rg_next = T.ranges[kc0];
     const int64_t len = (int64_t)T.len;
+#pragma unroll 1
+    for (uint32_t k = kc0; k < kc1; ++k) {
+    const Range2 rg = rg_next;
+    if (k + 1 < kc1) rg_next = T.ranges[k + 1];              // in flight while this chunk is evaluated
+    const int64_t p0 = (int64_t)k * bl;
+    const uint32_t lo = rg.x, hi = rg.y;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
         const int nv = min(4u, bl - i);
         float l[4] = {0.0f, 0.0f, 0.0f, 0.0f}, r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -553,6 +567,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* _
         st4<VEC>(T.h.out_l, (uint64_t)p0 + i, nv, l);
         st4<VEC>(T.h.out_r, (uint64_t)p0 + i, nv, r);
     }
+    }
 }
 
 // sample_lerp_gen (extensions.rs:384-421): primary = last hit at or before the frame, ghost = the
@@ -561,15 +576,20 @@ template <bool VEC>
 __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ LerpTask T;
     load_task(&T, tasks + blockIdx.y);
-    const uint32_t k = blockIdx.x;
-    if (k >= T.h.n_chunks) return;
+    const uint32_t kc0 = blockIdx.x * TDG_GATHER_CPB;
+    if (kc0 >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
-    const int64_t p0 = (int64_t)k * bl;
     const LerpHit* hits = reinterpret_cast<const LerpHit*>(blob + T.hits_off);
     // index of the last hit with frame <= p0 (entries 0 and 1 are the carried ghost / primary); k_chunk_ranges
-    const uint32_t base = T.ranges[k].x;
+    const uint32_t kc1 = min(kc0 + (uint32_t)TDG_GATHER_CPB, T.h.n_chunks);
+    uint32_t base_next = T.ranges[kc0].x;
     const int64_t lm1 = (int64_t)T.len - 1;
     const int64_t lerp_len = (int64_t)T.lerp_len;
+#pragma unroll 1
+    for (uint32_t k = kc0; k < kc1; ++k) {
+    const uint32_t base = base_next;
+    if (k + 1 < kc1) base_next = T.ranges[k + 1].x;          // in flight while this chunk is evaluated
+    const int64_t p0 = (int64_t)k * bl;
     for (uint32_t i = threadIdx.x * 4; i < bl; i += TDG_THREADS * 4) {
         const int nv = min(4u, bl - i);
         float l[4], r[4];
@@ -620,6 +640,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
         }
         st4<VEC>(T.h.out_l, (uint64_t)p0 + i, nv, l);
         st4<VEC>(T.h.out_r, (uint64_t)p0 + i, nv, r);
+    }
     }
 }
 
@@ -1043,6 +1064,20 @@ __global__ void __launch_bounds__(kBpThreads, TDG_BP_MINB) k_bp_apply(const BpTa
 // ticket, one publication and one look-back per 8192 frames instead of four, and the serial cross-group chain is four
 // times shorter (n_strips / 32 steps; hence kBpFusedMaxTiles).
 __device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+// 16 bytes global -> shared without passing through registers (LDGSTS; L2 only: the inputs are streamed once)
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+#ifdef __NVCC__
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+#else
+    memcpy(smem_dst, gsrc, 16);           // tests/emu
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifdef __NVCC__
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
 template <bool VEC>
 __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
 #ifdef __NVCC__
@@ -1068,7 +1103,50 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
     const uint64_t pb = (uint64_t)strip * kBpStrip;
     const uint32_t n_here = (uint32_t)min((uint64_t)kBpStrip, T.h.n_frames - pb);                    // frames of the pass in this strip
     const uint32_t n_cov = (uint32_t)min((uint64_t)kBpStrip, (uint64_t)T.n_tiles * kBpTile - pb);    // frames the (padded) buffers cover
-    // ---- 1. inputs -> shared memory (float4 q of the strip lands in row q / 8, words 4 * (q % 8) ..)
+    // ---- 1. inputs -> shared memory (float4 q of the strip lands in row q / 8, words 4 * (q % 8) ..).
+    // The first input goes straight from global to shared memory (cp.async, 16 bytes per request, no registers): the
+    // whole strip of a block — 64 KB — is in flight at once, which is what keeps HBM busy with three blocks per SM
+    // (with register loads in two halves of 32 KB the kernel sat at 0.6 of the HBM peak, latency bound).  Further
+    // inputs are added in edge order through registers.  The reference's sum starts from +0.0, so a -0.0 never
+    // survives it: the readers below add +0.0 to what they fetch, which is that same normalisation.
+    if (VEC) {
+#pragma unroll
+        for (int i = 0; i < kBpFpt / 4; ++i) {
+            const uint32_t q = threadIdx.x + kBpThreads * i, f = 4 * q, w = (q >> 3) * kBpRow + 4 * (q & 7);
+            if (f < n_cov) { cp_async16(s_l + w, ins[0] + pb + f); cp_async16(s_r + w, ins[1] + pb + f); }
+            else {
+                *reinterpret_cast<float4*>(s_l + w) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                *reinterpret_cast<float4*>(s_r + w) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        bool landed = false;
+        for (uint32_t a = 1; a < T.n_in; ++a) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float4 x[4], y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t f = 4u * (threadIdx.x + kBpThreads * (4 * half + u));
+                    if (f < n_cov) {
+                        x[u] = *reinterpret_cast<const float4*>(ins[2 * a] + pb + f);
+                        y[u] = *reinterpret_cast<const float4*>(ins[2 * a + 1] + pb + f);
+                    } else { x[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); y[u] = x[u]; }
+                }
+                if (!landed) { cp_async_wait_all(); landed = true; }        // this thread's own copies: no barrier needed
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t q = threadIdx.x + kBpThreads * (4 * half + u), w = (q >> 3) * kBpRow + 4 * (q & 7);
+                    float4 l = *reinterpret_cast<const float4*>(s_l + w), r = *reinterpret_cast<const float4*>(s_r + w);
+                    if (a == 1) { l.x += 0.0f; l.y += 0.0f; l.z += 0.0f; l.w += 0.0f; r.x += 0.0f; r.y += 0.0f; r.z += 0.0f; r.w += 0.0f; }
+                    l.x += x[u].x; l.y += x[u].y; l.z += x[u].z; l.w += x[u].w;
+                    r.x += y[u].x; r.y += y[u].y; r.z += y[u].z; r.w += y[u].w;
+                    *reinterpret_cast<float4*>(s_l + w) = l;
+                    *reinterpret_cast<float4*>(s_r + w) = r;
+                }
+            }
+        }
+        if (!landed) cp_async_wait_all();
+    } else {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         float l[4][4], r[4][4];
@@ -1082,11 +1160,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
             for (int u = 0; u < 4; ++u) {
                 const uint32_t f = 4u * (threadIdx.x + kBpThreads * (4 * half + u));
                 const int nv = f >= n_here ? 0 : (int)min(4u, n_here - f);
-                if (f < n_cov) { ld4<VEC>(ins[2 * a], pb + f, nv, x[u]); ld4<VEC>(ins[2 * a + 1], pb + f, nv, y[u]); }
-                else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { x[u][j] = 0.0f; y[u][j] = 0.0f; }
-                }
+                ld4<false>(ins[2 * a], pb + f, nv, x[u]); ld4<false>(ins[2 * a + 1], pb + f, nv, y[u]);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -1099,6 +1173,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
             *reinterpret_cast<float4*>(s_l + w) = make_float4(l[u][0], l[u][1], l[u][2], l[u][3]);
             *reinterpret_cast<float4*>(s_r + w) = make_float4(r[u][0], r[u][1], r[u][2], r[u][3]);
         }
+    }
     }
     __syncthreads();
     // ---- 2. the thread's 32 frames from a zero state
@@ -1114,7 +1189,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
         for (int k = 0; k < kBpFpt / 4; ++k) {
             if (4 * k >= nv) break;
             const float4 a = *reinterpret_cast<const float4*>(row_l + 4 * k), b = *reinterpret_cast<const float4*>(row_r + 4 * k);
-            const float xl[4] = {a.x, a.y, a.z, a.w}, xr[4] = {b.x, b.y, b.z, b.w};
+            const float xl[4] = {a.x + 0.0f, a.y + 0.0f, a.z + 0.0f, a.w + 0.0f}, xr[4] = {b.x + 0.0f, b.y + 0.0f, b.z + 0.0f, b.w + 0.0f};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (4 * k + j < nv) {
@@ -1191,7 +1266,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
         for (int k = 0; k < kBpFpt / 4; ++k) {
             if (4 * k >= nv) break;
             const float4 a4 = *reinterpret_cast<const float4*>(row_l + 4 * k), b4 = *reinterpret_cast<const float4*>(row_r + 4 * k);
-            const float xl[4] = {a4.x, a4.y, a4.z, a4.w}, xr[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float xl[4] = {a4.x + 0.0f, a4.y + 0.0f, a4.z + 0.0f, a4.w + 0.0f}, xr[4] = {b4.x + 0.0f, b4.y + 0.0f, b4.z + 0.0f, b4.w + 0.0f};
             float ol[4], orr[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -1480,8 +1555,9 @@ cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks
     const dim3 g = grid2(max_chunks, n);
     if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_SUM, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
     else if (mode == FX_ADSR) {
-        if (exact) { if (vec) k_fx<FX_ADSR, true, true><<<g, TDG_ADSR_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, true><<<g, TDG_ADSR_THREADS, 0, s>>>(t, blob); }
-        else { if (vec) k_fx<FX_ADSR, true, false><<<g, TDG_ADSR_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, false><<<g, TDG_ADSR_THREADS, 0, s>>>(t, blob); }
+        const dim3 ga = grid2((max_chunks + TDG_ADSR_CPB - 1) / TDG_ADSR_CPB, n);
+        if (exact) { if (vec) k_fx<FX_ADSR, true, true><<<ga, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, true><<<ga, TDG_THREADS, 0, s>>>(t, blob); }
+        else { if (vec) k_fx<FX_ADSR, true, false><<<ga, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, false><<<ga, TDG_THREADS, 0, s>>>(t, blob); }
     }
     else { if (vec) k_fx<FX_NORM_PEAK, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_NORM_PEAK, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
     return cudaGetLastError();
@@ -1517,15 +1593,15 @@ cudaError_t launch_norm_scale(const NormScaleTask* t, uint32_t n, uint32_t max_c
     return cudaGetLastError();
 }
 cudaError_t launch_sample_loop(const LoopTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_sample_loop, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t));
+    TDG_VEC_DISPATCH(vec, k_sample_loop, <<<grid2((max_chunks + TDG_GATHER_CPB - 1) / TDG_GATHER_CPB, n), TDG_THREADS, 0, s>>>(t));
     return cudaGetLastError();
 }
 cudaError_t launch_sample_multi(const MultiTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_sample_multi, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t, blob));
+    TDG_VEC_DISPATCH(vec, k_sample_multi, <<<grid2((max_chunks + TDG_GATHER_CPB - 1) / TDG_GATHER_CPB, n), TDG_THREADS, 0, s>>>(t, blob));
     return cudaGetLastError();
 }
 cudaError_t launch_sample_lerp(const LerpTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_sample_lerp, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t, blob));
+    TDG_VEC_DISPATCH(vec, k_sample_lerp, <<<grid2((max_chunks + TDG_GATHER_CPB - 1) / TDG_GATHER_CPB, n), TDG_THREADS, 0, s>>>(t, blob));
     return cudaGetLastError();
 }
 

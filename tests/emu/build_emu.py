@@ -79,7 +79,8 @@ def build(out_dir: str, verbose: bool = False) -> str:
         f.write(k)
     lib = os.path.join(out_dir, "libtermdaw_b200_emu.so")
     flags = ["-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-w",
-             "-D__CUDACC__", "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include")]
+             "-D__CUDACC__", "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+             *os.environ.get("TDG_DEFS", "").split()]          # tuning variants (same knob as csrc/build.py)
     try:
         if " fma " in open("/proc/cpuinfo").read():
             flags.append("-mfma")                          # fmaf() stays exact either way; this only makes it fast
