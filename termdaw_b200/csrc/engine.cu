@@ -200,6 +200,7 @@ struct Engine {
     // L2 hits save, so the default is one launch triple per level (0); the knob stays for single long renders (TDG_BP_L2_MB)
     uint64_t bp_l2_bytes = 0;
     bool bp_fused = true;                        // single-pass band pass (k_bp_fused) where no exchange step is needed and the pass is <= kBpFusedMaxTiles long; TDG_BP_FUSED=0: three launches
+    uint32_t bp_fused_max_tiles = kBpFusedMaxTiles;   // longer passes keep the three-launch scan (TDG_BP_FUSED_MAX_TILES)
     bool libm_sin = true;                        // oscillators evaluate glibc's sinf exactly (TDG_FAST_SIN=1 / tdg_set_oscillator_mode(ctx, 0): f32 polynomial, <= 2 ulp)
     WorkerPool* pool = nullptr;                  // planner threads (created on first batched pass)
     std::vector<Frag>* frags = nullptr;          // pooled per-project plan fragments (capacity is kept between jobs)
@@ -253,6 +254,7 @@ static Engine* engine_get(int device, std::string* err) {
     if (const char* e = getenv("TDG_FAST_SIN")) g->libm_sin = atoi(e) == 0;
     if (const char* e = getenv("TDG_BP_L2_MB")) g->bp_l2_bytes = (uint64_t)std::max(0, atoi(e)) << 20;
     if (const char* e = getenv("TDG_BP_FUSED")) g->bp_fused = atoi(e) != 0;
+    if (const char* e = getenv("TDG_BP_FUSED_MAX_TILES")) g->bp_fused_max_tiles = (uint32_t)std::max(1, std::min(65535 * kBpStripTiles, atoi(e)));
     g->refs = 1;
     g_engines[device] = g;
     return g;
@@ -1682,7 +1684,7 @@ static int pass_submit(PassJob& J) {
         // launches run over groups of filters whose inputs + outputs fit the L2 (bp_l2_bytes): the apply pass then
         // finds the inputs the aggregate pass just streamed in cache instead of fetching them from HBM again
         // no exchange step between aggregate and apply, pass short enough for the serial group chain: ONE launch
-        const bool bp_fused = !x_mode && g->bp_fused && !T.bp.v.empty() && T.bp.max_chunks <= kBpFusedMaxTiles && T.bp.max_chunks <= 65535;
+        const bool bp_fused = !x_mode && g->bp_fused && !T.bp.v.empty() && T.bp.max_chunks <= g->bp_fused_max_tiles;
         const bool bp_grouped = !bp_fused && !x_mode && g->bp_l2_bytes > 0 && T.bp.v.size() > 1;
         if (bp_fused) {
             LAUNCH_SPLIT(KC_BP_APPLY, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_fused(tp, nb, T.bp.max_chunks, vec, D, s));

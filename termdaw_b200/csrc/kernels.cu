@@ -242,7 +242,7 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
 #define TDG_ADSR_MINB 5      // measured: 4 -> 9.0 ms, 5 -> 8.3 ms, 6 -> 8.5 ms per bench step
 #endif
 #ifndef TDG_ADSR_CPB
-#define TDG_ADSR_CPB 1       // chunks per block of k_fx<adsr>
+#define TDG_ADSR_CPB 4       // chunks per block of k_fx<adsr>: measured 1 -> 7.19, 2 -> 6.65, 4 -> 6.24 ms per bench step
 #endif
 #ifndef TDG_BP_MINB
 #define TDG_BP_MINB 5        // measured: 4 -> 6.66 ms, 5 -> 6.48 ms, 6 -> 6.95 ms
@@ -473,10 +473,11 @@ __global__ void __launch_bounds__(TDG_THREADS) k_norm_scale(const NormScaleTask*
 // A chunk is 1024 frames: 8 KB of output per block behind a chain of dependent loads (task -> [range -> hits ->]
 // sample), and ncu shows these kernels waiting on exactly that chain (13-15 stall cycles of long_scoreboard per issue
 // at 85 % occupancy, DRAM 40-47 % busy).  A block therefore walks TDG_GATHER_CPB consecutive chunks of its vertex: the
-// task load, the barrier behind it and the block launch are paid once per 4 chunks, and the range of the next chunk is
-// fetched while the current one is evaluated.
+// task load, the barrier behind it and the block launch are paid once per group of chunks, and the range of the next
+// chunk is fetched while the current one is evaluated.  Measured per bench step (loop / multi / lerp): 1 chunk per block
+// 1.77 / 2.44 / 2.53 ms, 4: 1.52 / 1.70 / 1.60, 8: 1.51 / 1.62 / 1.44.
 #ifndef TDG_GATHER_CPB
-#define TDG_GATHER_CPB 4
+#define TDG_GATHER_CPB 8
 #endif
 // sample_loop_gen (extensions.rs:331-341): buf[i] = sample[(t + i) % L]
 template <bool VEC>
@@ -667,6 +668,9 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
 #ifndef TDG_SYNTH_MINB
 #define TDG_SYNTH_MINB 5        // min resident blocks per SM (register cap); measured per 256-project step: 2: 9.9, 3: 9.9, 4: 8.2, 5: 7.7, 6: 7.7 ms
 #endif
+#ifndef TDG_VOICE_CPB
+#define TDG_VOICE_CPB 1         // chunks per block of the voice kernels
+#endif
 #ifndef TDG_SAMPSYN_MINB
 #define TDG_SAMPSYN_MINB 5      // 4: 5.77, 5: 5.58, 6: 5.63 ms
 #endif
@@ -713,11 +717,10 @@ template <int KIND, bool EXACT, int F, bool LIBM>
 __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : TDG_SAMPSYN_MINB) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
     __shared__ VoiceTask T;
     load_task(&T, tasks + blockIdx.y);
-    const uint32_t k = blockIdx.x;
-    if (k >= T.h.n_chunks) return;
+    const uint32_t kc0 = blockIdx.x * TDG_VOICE_CPB;
+    if (kc0 >= T.h.n_chunks) return;
+    const uint32_t kc1 = TDG_VOICE_CPB == 1 ? kc0 + 1 : min(kc0 + (uint32_t)TDG_VOICE_CPB, T.h.n_chunks);
     const uint32_t bl = T.h.bl;
-    const uint64_t p0 = (uint64_t)k * bl;
-    const uint32_t s_lo = T.seg_ptr[k], s_hi = T.seg_ptr[k + 1];
     const float4* __restrict__ gsegs = reinterpret_cast<const float4*>(T.segs);
     const float* __restrict__ grelv2 = T.relv2;
     const float2* __restrict__ tab = reinterpret_cast<const float2*>(T.table);
@@ -725,6 +728,12 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
     const bool vec = (bl % F) == 0;
     const float n_phase_f = (float)T.n_phase, ymax = (float)(T.n_frames - 1);
     const int row_stride = (int)T.n_phase + 1;
+    uint32_t s_next = T.seg_ptr[kc0];
+#pragma unroll 1
+    for (uint32_t k = kc0; k < kc1; ++k) {
+    const uint64_t p0 = (uint64_t)k * bl;
+    const uint32_t s_lo = s_next, s_hi = T.seg_ptr[k + 1];
+    s_next = s_hi;
     for (uint32_t base = 0; base < bl; base += TDG_THREADS * F) {
         const uint32_t i0 = base + threadIdx.x * F;
         if (i0 >= bl) break;
@@ -823,6 +832,7 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
             }
         }
     }
+    }
 }
 
 // ------------------------------------------------------------------------------------ K7: band pass scan
@@ -844,7 +854,8 @@ __device__ __forceinline__ Aff aff_shfl_up(const Aff& a, int d) {
 }
 // exclusive prefix of per-thread maps over the block (thread order), plus the block total
 __device__ __forceinline__ Aff block_aff_scan(const Aff& mine, Aff* total) {
-    __shared__ Aff wtot[32];
+    static_assert(kBpThreads <= 256 && kBpFusedThreads <= 256, "wtot holds one map per warp");
+    __shared__ Aff wtot[8];
     const int ln = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     Aff inc = mine;
 #pragma unroll
@@ -1079,15 +1090,15 @@ __device__ __forceinline__ void cp_async_wait_all() {
 #endif
 }
 template <bool VEC>
-__global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(kBpFusedThreads, 768 / kBpFusedThreads) k_bp_fused(const BpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
 #ifdef __NVCC__
     extern __shared__ float4 s_dyn4[];
     float* const s_l = reinterpret_cast<float*>(s_dyn4);
 #else
-    alignas(16) static float s_emu[2 * kBpThreads * kBpRow];     // tests/emu: one block in flight at a time
+    alignas(16) static float s_emu[2 * kBpFusedThreads * kBpRow];     // tests/emu: one block in flight at a time
     float* const s_l = s_emu;
 #endif
-    float* const s_r = s_l + kBpThreads * kBpRow;
+    float* const s_r = s_l + kBpFusedThreads * kBpRow;
     __shared__ BpTask T;
     __shared__ uint32_t s_strip;
     __shared__ float s_carry[4];
@@ -1112,7 +1123,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
     if (VEC) {
 #pragma unroll
         for (int i = 0; i < kBpFpt / 4; ++i) {
-            const uint32_t q = threadIdx.x + kBpThreads * i, f = 4 * q, w = (q >> 3) * kBpRow + 4 * (q & 7);
+            const uint32_t q = threadIdx.x + kBpFusedThreads * i, f = 4 * q, w = (q >> 3) * kBpRow + 4 * (q & 7);
             if (f < n_cov) { cp_async16(s_l + w, ins[0] + pb + f); cp_async16(s_r + w, ins[1] + pb + f); }
             else {
                 *reinterpret_cast<float4*>(s_l + w) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1126,7 +1137,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
                 float4 x[4], y[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint32_t f = 4u * (threadIdx.x + kBpThreads * (4 * half + u));
+                    const uint32_t f = 4u * (threadIdx.x + kBpFusedThreads * (4 * half + u));
                     if (f < n_cov) {
                         x[u] = *reinterpret_cast<const float4*>(ins[2 * a] + pb + f);
                         y[u] = *reinterpret_cast<const float4*>(ins[2 * a + 1] + pb + f);
@@ -1135,7 +1146,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
                 if (!landed) { cp_async_wait_all(); landed = true; }        // this thread's own copies: no barrier needed
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint32_t q = threadIdx.x + kBpThreads * (4 * half + u), w = (q >> 3) * kBpRow + 4 * (q & 7);
+                    const uint32_t q = threadIdx.x + kBpFusedThreads * (4 * half + u), w = (q >> 3) * kBpRow + 4 * (q & 7);
                     float4 l = *reinterpret_cast<const float4*>(s_l + w), r = *reinterpret_cast<const float4*>(s_r + w);
                     if (a == 1) { l.x += 0.0f; l.y += 0.0f; l.z += 0.0f; l.w += 0.0f; r.x += 0.0f; r.y += 0.0f; r.z += 0.0f; r.w += 0.0f; }
                     l.x += x[u].x; l.y += x[u].y; l.z += x[u].z; l.w += x[u].w;
@@ -1158,7 +1169,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
             float x[4][4], y[4][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const uint32_t f = 4u * (threadIdx.x + kBpThreads * (4 * half + u));
+                const uint32_t f = 4u * (threadIdx.x + kBpFusedThreads * (4 * half + u));
                 const int nv = f >= n_here ? 0 : (int)min(4u, n_here - f);
                 ld4<false>(ins[2 * a], pb + f, nv, x[u]); ld4<false>(ins[2 * a + 1], pb + f, nv, y[u]);
             }
@@ -1169,7 +1180,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const uint32_t q = threadIdx.x + kBpThreads * (4 * half + u), w = (q >> 3) * kBpRow + 4 * (q & 7);
+            const uint32_t q = threadIdx.x + kBpFusedThreads * (4 * half + u), w = (q >> 3) * kBpRow + 4 * (q & 7);
             *reinterpret_cast<float4*>(s_l + w) = make_float4(l[u][0], l[u][1], l[u][2], l[u][3]);
             *reinterpret_cast<float4*>(s_r + w) = make_float4(r[u][0], r[u][1], r[u][2], r[u][3]);
         }
@@ -1294,7 +1305,7 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_bp_fused(const BpTask* __rest
     // ---- 5. shared memory -> output, coalesced
 #pragma unroll 4
     for (int i = 0; i < kBpFpt / 4; ++i) {
-        const uint32_t q = threadIdx.x + kBpThreads * i, f = 4 * q;
+        const uint32_t q = threadIdx.x + kBpFusedThreads * i, f = 4 * q;
         if (f >= n_here) break;
         const int nvq = (int)min(4u, n_here - f);
         const uint32_t w = (q >> 3) * kBpRow + 4 * (q & 7);
@@ -1380,15 +1391,21 @@ __device__ __forceinline__ void quantise_block(const QuantTask& T, uint64_t b0, 
         }
     }
 }
+#ifndef TDG_QUANT_CPB
+#define TDG_QUANT_CPB 1         // spans (chunks) per block
+#endif
 __global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __restrict__ tasks) {
     __shared__ QuantTask T;
     load_task(&T, tasks + blockIdx.y);
     const uint32_t span = T.span;
-    const uint64_t b0 = (uint64_t)blockIdx.x * span;
-    if (b0 >= T.n) return;
     bool wide = false;
+#pragma unroll 1
+    for (uint32_t c = 0; c < (uint32_t)TDG_QUANT_CPB; ++c) {
+    const uint64_t blk = (uint64_t)blockIdx.x * TDG_QUANT_CPB + c;
+    const uint64_t b0 = blk * span;
+    if (b0 >= T.n) break;
     if (T.runmax) {
-        const float f = 1.0f / T.runmax[T.chunk0 + blockIdx.x];      // scale(len, 1.0 / max) of this chunk
+        const float f = 1.0f / T.runmax[T.chunk0 + blk];             // scale(len, 1.0 / max) of this chunk
         switch (T.bd) {
             case 8: quantise_block<8, true>(T, b0, span, f, wide); break;
             case 16: quantise_block<16, true>(T, b0, span, f, wide); break;
@@ -1402,6 +1419,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __res
             case 24: quantise_block<24, false>(T, b0, span, 1.0f, wide); break;
             default: quantise_block<32, false>(T, b0, span, 1.0f, wide); break;
         }
+    }
     }
     if (wide) atomicOr(T.err, 1u);        // hound's TooWide (8/24 bit); padding lanes were zeroed, only real frames count
 }
@@ -1620,7 +1638,7 @@ static cudaError_t launch_voice_t(const VoiceTask* t, uint32_t n, uint32_t max_c
         if (e != cudaSuccess) return e;
         attr_set = g_voice_smem;
     }
-    kfn<<<grid2(max_chunks, n), TDG_THREADS, (size_t)g_voice_smem, s>>>(t, blob);
+    kfn<<<grid2((max_chunks + TDG_VOICE_CPB - 1) / TDG_VOICE_CPB, n), TDG_THREADS, (size_t)g_voice_smem, s>>>(t, blob);
     return cudaGetLastError();
 }
 cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool exact, bool libm_sin, const uint8_t* blob, cudaStream_t s) {
@@ -1655,11 +1673,11 @@ cudaError_t launch_bp_fused(const BpTask* t, uint32_t n, uint32_t max_tiles, boo
         attr_set = true;
     }
     const uint32_t max_strips = (max_tiles + kBpStripTiles - 1) / kBpStripTiles;
-    TDG_VEC_DISPATCH(vec, k_bp_fused, <<<dim3(n, max_strips ? max_strips : 1, 1), kBpThreads, kBpStripSmem, s>>>(t, blob));
+    TDG_VEC_DISPATCH(vec, k_bp_fused, <<<dim3(n, max_strips ? max_strips : 1, 1), kBpFusedThreads, kBpStripSmem, s>>>(t, blob));
     return cudaGetLastError();
 }
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s) {
-    k_quantise<<<grid2(max_blocks ? max_blocks : 1, n), TDG_THREADS, 0, s>>>(t);
+    k_quantise<<<grid2(max_blocks ? (max_blocks + TDG_QUANT_CPB - 1) / TDG_QUANT_CPB : 1, n), TDG_THREADS, 0, s>>>(t);
     return cudaGetLastError();
 }
 cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s) {

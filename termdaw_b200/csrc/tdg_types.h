@@ -245,11 +245,15 @@ struct ResampleChunk { double last_index; uint64_t out_off; uint32_t n_out, pad;
 static const int kBpFramesPerThread = 8;
 static const int kBpThreads = 256;
 static const int kBpTile = kBpFramesPerThread * kBpThreads;     // 2048 frames
-static const int kBpStripTiles = 4;                             // fused kernel: a block owns a strip of 4 tiles,
-static const int kBpStrip = kBpStripTiles * kBpTile;            //   8192 frames,
-static const int kBpFpt = kBpStrip / kBpThreads;                //   32 consecutive frames per thread,
+#ifndef TDG_BP_FUSED_THREADS
+#define TDG_BP_FUSED_THREADS 256
+#endif
+static const int kBpFusedThreads = TDG_BP_FUSED_THREADS;        // fused kernel: threads per block,
+static const int kBpFpt = 32;                                   //   32 consecutive frames per thread,
+static const int kBpStrip = kBpFusedThreads * kBpFpt;           //   a block owns a strip of 8192 frames
+static const int kBpStripTiles = kBpStrip / kBpTile;            //   (4 tiles of the three-launch scan),
 static const int kBpRow = kBpFpt + 4;                           //   staged in shared-memory rows padded to 36 words (conflict-free float4 access both ways)
-static const int kBpStripSmem = 2 * kBpThreads * kBpRow * 4;    //   72 KB per block
+static const int kBpStripSmem = 2 * kBpFusedThreads * kBpRow * 4;   //   72 KB per block
 static const int kBpGroup = 32;                                 // fused kernel: strips per look-back group (one warp lane each)
 static const uint32_t kBpFusedMaxTiles = 8192;                  // longer passes (> 350 s at 48 kHz) keep the three-launch scan (the group chain is serial)
 
