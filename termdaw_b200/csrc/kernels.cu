@@ -242,7 +242,7 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
 #define TDG_ADSR_MINB 5      // measured: 4 -> 9.0 ms, 5 -> 8.3 ms, 6 -> 8.5 ms per bench step
 #endif
 #ifndef TDG_ADSR_CPB
-#define TDG_ADSR_CPB 4       // chunks per block of k_fx<adsr>: measured 1 -> 7.19, 2 -> 6.65, 4 -> 6.24 ms per bench step
+#define TDG_ADSR_CPB 8       // chunks per block of k_fx<adsr>: measured 1 -> 7.19, 2 -> 6.65, 4 -> 6.24, 8 -> 6.03 ms per bench step
 #endif
 #ifndef TDG_BP_MINB
 #define TDG_BP_MINB 5        // measured: 4 -> 6.66 ms, 5 -> 6.48 ms, 6 -> 6.95 ms
@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
 #define TDG_SYNTH_MINB 5        // min resident blocks per SM (register cap); measured per 256-project step: 2: 9.9, 3: 9.9, 4: 8.2, 5: 7.7, 6: 7.7 ms
 #endif
 #ifndef TDG_VOICE_CPB
-#define TDG_VOICE_CPB 1         // chunks per block of the voice kernels
+#define TDG_VOICE_CPB 4         // chunks per block of the voice kernels: measured (synth / sampsyn) 1 -> 9.34 / 9.45, 2 -> 9.09 / 8.65, 4 -> 8.87 / 8.17 ms per bench step
 #endif
 #ifndef TDG_SAMPSYN_MINB
 #define TDG_SAMPSYN_MINB 5      // 4: 5.77, 5: 5.58, 6: 5.63 ms
@@ -1392,7 +1392,7 @@ __device__ __forceinline__ void quantise_block(const QuantTask& T, uint64_t b0, 
     }
 }
 #ifndef TDG_QUANT_CPB
-#define TDG_QUANT_CPB 1         // spans (chunks) per block
+#define TDG_QUANT_CPB 4         // spans (chunks) per block: 1 -> 1.59, 4 -> 1.53 ms per bench step
 #endif
 __global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __restrict__ tasks) {
     __shared__ QuantTask T;

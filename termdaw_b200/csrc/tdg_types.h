@@ -246,15 +246,16 @@ static const int kBpFramesPerThread = 8;
 static const int kBpThreads = 256;
 static const int kBpTile = kBpFramesPerThread * kBpThreads;     // 2048 frames
 #ifndef TDG_BP_FUSED_THREADS
-#define TDG_BP_FUSED_THREADS 256
+#define TDG_BP_FUSED_THREADS 128     // measured per bench step: 256 threads (3 blocks of 72 KB per SM) 6.68 ms, 128 threads (6 blocks of 36 KB) 6.18 ms
 #endif
 static const int kBpFusedThreads = TDG_BP_FUSED_THREADS;        // fused kernel: threads per block,
 static const int kBpFpt = 32;                                   //   32 consecutive frames per thread,
-static const int kBpStrip = kBpFusedThreads * kBpFpt;           //   a block owns a strip of 8192 frames
-static const int kBpStripTiles = kBpStrip / kBpTile;            //   (4 tiles of the three-launch scan),
+static const int kBpStrip = kBpFusedThreads * kBpFpt;           //   a block owns a strip of 4096 frames
+static const int kBpStripTiles = kBpStrip / kBpTile;            //   (2 tiles of the three-launch scan),
 static const int kBpRow = kBpFpt + 4;                           //   staged in shared-memory rows padded to 36 words (conflict-free float4 access both ways)
-static const int kBpStripSmem = 2 * kBpFusedThreads * kBpRow * 4;   //   72 KB per block
+static const int kBpStripSmem = 2 * kBpFusedThreads * kBpRow * 4;   //   36 KB per block
 static const int kBpGroup = 32;                                 // fused kernel: strips per look-back group (one warp lane each)
-static const uint32_t kBpFusedMaxTiles = 8192;                  // longer passes (> 350 s at 48 kHz) keep the three-launch scan (the group chain is serial)
+static const uint32_t kBpFusedMaxTiles = 65535u * kBpStripTiles; // grid limit; the serial group chain (n_strips / 32 steps of ~2.5 us) still beats the second read of the
+                                                                // three-launch scan on an hour-long pass (configs[3]: 15.5 vs 17.5 ms per step)
 
 }  // namespace tdg
