@@ -669,7 +669,11 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
 #define TDG_SYNTH_MINB 5        // min resident blocks per SM (register cap); measured per 256-project step: 2: 9.9, 3: 9.9, 4: 8.2, 5: 7.7, 6: 7.7 ms
 #endif
 #ifndef TDG_VOICE_CPB
-#define TDG_VOICE_CPB 4         // chunks per block of the voice kernels: measured (synth / sampsyn) 1 -> 9.34 / 9.45, 2 -> 9.09 / 8.65, 4 -> 8.87 / 8.17 ms per bench step
+#define TDG_VOICE_CPB 8         // chunks per block of the voice kernels: measured (synth / sampsyn) 1 -> 9.34 / 9.45, 2 -> 9.09 / 8.65, 4 -> 8.87 / 8.17,
+                                // 8 -> 8.76 / 7.91, 16 -> 8.72 / 7.82 ms per bench step
+#endif
+#ifndef TDG_VOICE_HOIST
+#define TDG_VOICE_HOIST 1
 #endif
 #ifndef TDG_SAMPSYN_MINB
 #define TDG_SAMPSYN_MINB 5      // 4: 5.77, 5: 5.58, 6: 5.63 ms
@@ -729,6 +733,14 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
     const float n_phase_f = (float)T.n_phase, ymax = (float)(T.n_frames - 1);
     const int row_stride = (int)T.n_phase + 1;
     uint32_t s_next = T.seg_ptr[kc0];
+    // i as f32 / sr as f32 does not depend on the chunk: with one run per thread and chunk (bl <= 1024) it is computed
+    // once per block instead of once per chunk
+    const bool one_run = TDG_VOICE_HOIST && bl <= (uint32_t)(TDG_THREADS * F);
+    float off[F];
+    if (one_run) {
+#pragma unroll
+        for (int j = 0; j < F; ++j) off[j] = k_div<EXACT>((float)(threadIdx.x * F + j), fsr, rsr);
+    }
 #pragma unroll 1
     for (uint32_t k = kc0; k < kc1; ++k) {
     const uint64_t p0 = (uint64_t)k * bl;
@@ -737,12 +749,12 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
     for (uint32_t base = 0; base < bl; base += TDG_THREADS * F) {
         const uint32_t i0 = base + threadIdx.x * F;
         if (i0 >= bl) break;
-        float acc[F], time[F], off[F];
+        float acc[F], time[F];
 #pragma unroll
         for (int j = 0; j < F; ++j) {
             acc[j] = 0.0f;
             time[j] = k_div<EXACT>((float)(T.t0 + p0 + i0 + j), fsr, rsr);      // (t + i) as f32 / sr as f32
-            off[j] = k_div<EXACT>((float)(i0 + j), fsr, rsr);                   // i as f32 / sr as f32
+            if (!one_run) off[j] = k_div<EXACT>((float)(i0 + j), fsr, rsr);     // i as f32 / sr as f32
         }
 #pragma unroll 1
         for (uint32_t s = s_lo; s < s_hi; ++s) {
