@@ -295,9 +295,9 @@ class BatchRunner:
         ev_bytes = rewind(self.states, reupload_flowws=e2e)
         self.rewind_ms = (time.perf_counter() - t_rw) * 1e3
         if e2e:
-            # the public batched call: scan + render of every project, groups of 64 projects pipelined over
-            # two streams (planning / kernels / PCM D2H of different groups overlap)
-            c0.set_pipeline_group(int(os.environ.get("TDG_E2E_GROUP", "64")))
+            # the public batched call: scan + render of every project, groups of 32 projects (the library's default)
+            # pipelined over two streams (planning / kernels / PCM D2H of different groups overlap)
+            c0.set_pipeline_group(int(os.environ.get("TDG_E2E_GROUP", "32")))
             normalize_render_many(self.lib, self.ctxs, self.cs, self.rsr, self.bds, want_pcm=True, outs=self.outs)
             s2, k2 = c0.last_pass_stats(), c0.last_pass_kernel_stats()
             s1, k1 = {k: 0 for k in s2}, {}

@@ -191,7 +191,7 @@ struct Engine {
     uint64_t epoch = 0;                          // bumped by every pass (taps of older passes are stale)
     int refs = 0;
     bool profiling = false;                      // CUDA events around every launch (per-class roofline)
-    uint32_t pipeline_group = 64;                // projects per pipelined group (0 = never pipeline)
+    uint32_t pipeline_group = 32;                // projects per pipelined group (0 = never pipeline); measured per 512-project call: 16 -> 68, 32 -> 65, 64 -> 69, 128 -> 79 ms
     uint64_t hwm_work = 0, hwm_blob = 0, hwm_pcm = 0;         // largest work arena / plan blob any lane or slot has needed
     uint64_t hwm_keep = 0;
     bool reuse = true;                           // render reads pass-invariant cones from the scan (TDG_PASS_REUSE=0 / tdg_set_pass_reuse)

@@ -241,6 +241,9 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
 #ifndef TDG_ADSR_MINB
 #define TDG_ADSR_MINB 5      // measured: 4 -> 9.0 ms, 5 -> 8.3 ms, 6 -> 8.5 ms per bench step
 #endif
+#ifndef TDG_FX_CPB
+#define TDG_FX_CPB 1         // chunks per block of k_fx<sum> / k_fx<norm_peak> (both already run at the HBM roof)
+#endif
 #ifndef TDG_ADSR_CPB
 #define TDG_ADSR_CPB 8       // chunks per block of k_fx<adsr>: measured 1 -> 7.19, 2 -> 6.65, 4 -> 6.24, 8 -> 6.03 ms per bench step
 #endif
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB :
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
     // the adsr variant walks TDG_ADSR_CPB consecutive chunks per block (see the gather kernels: the task load, its
     // barrier and the block launch are paid once per group of chunks)
-    constexpr uint32_t CPB = MODE == FX_ADSR ? TDG_ADSR_CPB : 1;
+    constexpr uint32_t CPB = MODE == FX_ADSR ? TDG_ADSR_CPB : TDG_FX_CPB;
     const uint32_t kc0 = blockIdx.x * CPB;
     if (kc0 >= T.h.n_chunks) return;
     const uint32_t kc1 = CPB == 1 ? kc0 + 1 : min(kc0 + CPB, T.h.n_chunks);
@@ -698,6 +701,20 @@ __device__ __forceinline__ float wavetable_eval(const float2* __restrict__ row, 
     const float b = c0.y + fx * (c1.y - c0.y);
     return a + fy * (b - a);
 }
+// The same cell on the table's LAST row, where a voice sits once its time has run past the table (y clamped to ymax:
+// j0 = last, fy = +0): both rows of the pair are the last row, so b is a bit for bit and the result is a + 0*(a - a)
+// (NaN for a non-finite a, exactly as a + fy*(b - a) would be).
+__device__ __forceinline__ float wavetable_eval_last(const float2* __restrict__ row, float n_phase_f, int n_phase, float hz, float t) {
+    float ph = t * hz;
+    ph = ph - floorf(ph);
+    const float x = ph * n_phase_f;
+    int i0 = __float2int_rz(x);
+    if (i0 >= n_phase) i0 = n_phase - 1;
+    const float fx = x - (float)i0;
+    const float a0 = __ldg(&row[i0].x), a1 = __ldg(&row[i0 + 1].x);
+    const float a = a0 + fx * (a1 - a0);
+    return a + 0.0f * (a - a);
+}
 // the time axis of the table for one frame: row j0 = trunc(clamp(t * fps, 0, ymax)) and the weight towards row j0 + 1
 __device__ __forceinline__ int wavetable_row(float fps, float ymax, float t, float* fy) {
     float y = t * fps;
@@ -809,12 +826,23 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
                     for (int j = 0; j < F; ++j) smp[j] *= T.amp_mul;
                 } else {                                                          // extensions.rs:560-571
                     if (rel) k_apply_r_n<EXACT, F>(T.env[0], et, sb.z, e); else k_apply_ads_n<EXACT, F>(T.env[0], et, e);
+                    // table time is non-decreasing over the run (f32 add and multiply by fps > 0 are monotonic): when the
+                    // first frame is already clamped to the last row, all of them are
+                    if (T.fps > 0.0f && (et[0] + rel_t) * T.fps >= ymax) {
+                        const float2* __restrict__ row = tab + (size_t)(T.n_frames - 1) * row_stride;
 #pragma unroll
-                    for (int j = 0; j < F; ++j) {
-                        float fy;
-                        const int jr = wavetable_row(T.fps, ymax, et[j] + rel_t, &fy);
-                        const float g = vel * e[j] * T.amp_mul;
-                        smp[j] = wavetable_eval(tab + (size_t)jr * row_stride, n_phase_f, (int)T.n_phase, fy, hz, et[j] + rel_t) * g;
+                        for (int j = 0; j < F; ++j) {
+                            const float g = vel * e[j] * T.amp_mul;
+                            smp[j] = wavetable_eval_last(row, n_phase_f, (int)T.n_phase, hz, et[j] + rel_t) * g;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < F; ++j) {
+                            float fy;
+                            const int jr = wavetable_row(T.fps, ymax, et[j] + rel_t, &fy);
+                            const float g = vel * e[j] * T.amp_mul;
+                            smp[j] = wavetable_eval(tab + (size_t)jr * row_stride, n_phase_f, (int)T.n_phase, fy, hz, et[j] + rel_t) * g;
+                        }
                     }
                 }
             }
@@ -1582,7 +1610,7 @@ static inline dim3 grid2(uint64_t x, uint32_t y) { return dim3((unsigned)(x ? x 
 #define TDG_VEC_DISPATCH(vec, K, ...) do { if (vec) K<true> __VA_ARGS__; else K<false> __VA_ARGS__; } while (0)
 
 cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, const uint8_t* blob, cudaStream_t s) {
-    const dim3 g = grid2(max_chunks, n);
+    const dim3 g = grid2((max_chunks + TDG_FX_CPB - 1) / TDG_FX_CPB, n);
     if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_SUM, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
     else if (mode == FX_ADSR) {
         const dim3 ga = grid2((max_chunks + TDG_ADSR_CPB - 1) / TDG_ADSR_CPB, n);
