@@ -701,20 +701,6 @@ __device__ __forceinline__ float wavetable_eval(const float2* __restrict__ row, 
     const float b = c0.y + fx * (c1.y - c0.y);
     return a + fy * (b - a);
 }
-// The same cell on the table's LAST row, where a voice sits once its time has run past the table (y clamped to ymax:
-// j0 = last, fy = +0): both rows of the pair are the last row, so b is a bit for bit and the result is a + 0*(a - a)
-// (NaN for a non-finite a, exactly as a + fy*(b - a) would be).
-__device__ __forceinline__ float wavetable_eval_last(const float2* __restrict__ row, float n_phase_f, int n_phase, float hz, float t) {
-    float ph = t * hz;
-    ph = ph - floorf(ph);
-    const float x = ph * n_phase_f;
-    int i0 = __float2int_rz(x);
-    if (i0 >= n_phase) i0 = n_phase - 1;
-    const float fx = x - (float)i0;
-    const float a0 = __ldg(&row[i0].x), a1 = __ldg(&row[i0 + 1].x);
-    const float a = a0 + fx * (a1 - a0);
-    return a + 0.0f * (a - a);
-}
 // the time axis of the table for one frame: row j0 = trunc(clamp(t * fps, 0, ymax)) and the weight towards row j0 + 1
 __device__ __forceinline__ int wavetable_row(float fps, float ymax, float t, float* fy) {
     float y = t * fps;
@@ -826,23 +812,15 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
                     for (int j = 0; j < F; ++j) smp[j] *= T.amp_mul;
                 } else {                                                          // extensions.rs:560-571
                     if (rel) k_apply_r_n<EXACT, F>(T.env[0], et, sb.z, e); else k_apply_ads_n<EXACT, F>(T.env[0], et, e);
-                    // table time is non-decreasing over the run (f32 add and multiply by fps > 0 are monotonic): when the
-                    // first frame is already clamped to the last row, all of them are
-                    if (T.fps > 0.0f && (et[0] + rel_t) * T.fps >= ymax) {
-                        const float2* __restrict__ row = tab + (size_t)(T.n_frames - 1) * row_stride;
+                    // (a shortcut for voices whose table time has run past the last row — j0 = last, fy = +0, b == a — was
+                    // measured SLOWER: configs[2] 58.1 -> 61.6 ms, the second inlined body costs more than the ten
+                    // instructions it saves)
 #pragma unroll
-                        for (int j = 0; j < F; ++j) {
-                            const float g = vel * e[j] * T.amp_mul;
-                            smp[j] = wavetable_eval_last(row, n_phase_f, (int)T.n_phase, hz, et[j] + rel_t) * g;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < F; ++j) {
-                            float fy;
-                            const int jr = wavetable_row(T.fps, ymax, et[j] + rel_t, &fy);
-                            const float g = vel * e[j] * T.amp_mul;
-                            smp[j] = wavetable_eval(tab + (size_t)jr * row_stride, n_phase_f, (int)T.n_phase, fy, hz, et[j] + rel_t) * g;
-                        }
+                    for (int j = 0; j < F; ++j) {
+                        float fy;
+                        const int jr = wavetable_row(T.fps, ymax, et[j] + rel_t, &fy);
+                        const float g = vel * e[j] * T.amp_mul;
+                        smp[j] = wavetable_eval(tab + (size_t)jr * row_stride, n_phase_f, (int)T.n_phase, fy, hz, et[j] + rel_t) * g;
                     }
                 }
             }
