@@ -1687,7 +1687,7 @@ static int pass_submit(PassJob& J) {
         const bool bp_fused = !x_mode && g->bp_fused && !T.bp.v.empty() && T.bp.max_chunks <= g->bp_fused_max_tiles;
         const bool bp_grouped = !bp_fused && !x_mode && g->bp_l2_bytes > 0 && T.bp.v.size() > 1;
         if (bp_fused) {
-            LAUNCH_SPLIT(KC_BP_APPLY, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_fused(tp, nb, T.bp.max_chunks, vec, D, s));
+            LAUNCH_SPLIT(KC_BP_FUSED, T.bp, BpTask, offs[L].bp, T.bp.bytes, launch_bp_fused(tp, nb, T.bp.max_chunks, vec, D, s));
         } else if (bp_grouped) {
             const size_t n = T.bp.v.size();
             auto io_of = [&](size_t q) { return 8ull * (T.bp.v[q].n_in + 1) * T.bp.v[q].h.n_frames; };
@@ -2828,7 +2828,7 @@ int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; retur
 int tdg_set_pipeline_group(tdg_ctx* h, uint32_t projects_per_group) { h->c.eng->pipeline_group = projects_per_group; return TDG_OK; }
 int tdg_last_pass_kernel_stats(tdg_ctx* h, tdg_kernel_stat* out, int cap) {
     static const char* names[KC_COUNT] = {"k_sample_loop", "k_sample_multi", "k_sample_lerp", "k_voice<debug_sine>", "k_voice<synth>",
-        "k_voice<sampsyn>", "k_fx<sum>", "k_fx<adsr>", "k_fx<norm_peak>", "k_norm_prefix", "k_norm_scale", "k_bp_aggregate", "k_bp_carry", "k_bp_apply", "k_resample", "k_quantise", "nccl_exchange", "k_chunk_ranges"};
+        "k_voice<sampsyn>", "k_fx<sum>", "k_fx<adsr>", "k_fx<norm_peak>", "k_norm_prefix", "k_norm_scale", "k_bp_aggregate", "k_bp_carry", "k_bp_apply", "k_resample", "k_quantise", "nccl_exchange", "k_chunk_ranges", "k_bp_fused"};
     int n = 0;
     for (int k = 0; k < KC_COUNT && n < cap; ++k) {
         const KStat& s = h->c.kstats[k];

@@ -54,7 +54,7 @@ struct HVertex {
 };
 
 enum KClass { KC_LOOP, KC_MULTI, KC_LERP, KC_DSINE, KC_SYNTH, KC_SAMPSYN, KC_FX_SUM, KC_FX_ADSR, KC_FX_NORM, KC_NORM_PREFIX, KC_NORM_SCALE,
-              KC_BP_AGG, KC_BP_CARRY, KC_BP_APPLY, KC_RESAMPLE, KC_QUANT, KC_XCHG, KC_RANGES, KC_COUNT };
+              KC_BP_AGG, KC_BP_CARRY, KC_BP_APPLY, KC_RESAMPLE, KC_QUANT, KC_XCHG, KC_RANGES, KC_BP_FUSED, KC_COUNT };
 struct KStat { uint64_t launches = 0, bytes = 0; double ms = 0; };
 
 struct PassStats {

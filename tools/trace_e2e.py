@@ -11,7 +11,7 @@ cfgs = [S.config_5_project(i, 1.0) for i in range(N)]
 states = make_states(lib, cfgs, 0)
 ctxs = [st.ctx for st, _, _ in states]; cs = [st.cs for st, _, _ in states]; rsr = [st.render_sr for st, _, _ in states]; bds = [st.bd for st, _, _ in states]
 outs = [torch.empty(int(lib.render_bound_bytes(c.h, n, r, b)), dtype=torch.uint8, pin_memory=True).numpy() for c, n, r, b in zip(ctxs, cs, rsr, bds)]
-for spec in os.environ.get("TDG_E2E_GROUPS", os.environ.get("TDG_E2E_GROUP", "64")).split(","):
+for spec in os.environ.get("TDG_E2E_GROUPS", os.environ.get("TDG_E2E_GROUP", "32")).split(","):
     grp, _, q = spec.partition(":")                    # "64:0.75" = groups of 64, geometric tail ratio 0.75
     grp = int(grp)
     if q:
