@@ -274,6 +274,8 @@ typedef struct tdg_pass_stats {
     uint64_t voice_frames;   /* voice-frames evaluated by the synth kernels                         */
     uint64_t reused_vertices;/* render after a scan: vertices read from the scan's resident buffers  */
     uint64_t reused_bytes;   /* ... and the algorithmic bytes their evaluation would have moved      */
+    uint64_t inlined_vertices;/* Sum vertices evaluated inside their consumer's kernel (no buffer)    */
+    uint64_t inlined_bytes;  /* ... and the write + read of the intermediate buffer not moved        */
 } tdg_pass_stats;
 int tdg_last_pass_stats(tdg_ctx* ctx, tdg_pass_stats* out);
 /* Per kernel class figures of the last pass (CUDA events around every launch on the context's
@@ -301,8 +303,17 @@ int tdg_set_oscillator_mode(tdg_ctx* ctx, int libm_exact);
 /* Batched calls (tdg_*_many) over more than `projects_per_group` projects are software-pipelined in
  * groups of that size over two streams: host planning of group g+1 and the PCM device->host copy of
  * group g-1 overlap the kernels of group g.  0 = one launch sequence for the whole batch (what the
- * per-kernel roofline numbers are measured on).  Default 64.  Device-wide setting. */
+ * per-kernel roofline numbers are measured on).  Default 32.  Device-wide setting. */
 int tdg_set_pipeline_group(tdg_ctx* ctx, uint32_t projects_per_group);
+/* Launch shaping (a tuning knob, no effect on results): the chunk kernels let one block walk up to 8 consecutive
+ * chunks of a vertex as long as the grid keeps at least `waves` waves of blocks (default 16; 0 = always the maximum,
+ * a huge value = always one chunk per block).  Process-wide.  The parity tests run under both extremes. */
+int tdg_set_launch_waves(uint32_t waves);
+/* Inlined sums (default on): a Sum vertex (add_sum: sum_inputs + pan + gain, extensions.rs:310-319) whose only consumer
+ * is a Sum, Normalize or Adsr vertex is evaluated inside that consumer's kernel — same operations, same order, same
+ * bits — instead of through a buffer of its own (16 bytes per frame less HBM traffic per inlined vertex).  Never with
+ * taps enabled.  0 restores one buffer and one launch per vertex.  Device-wide setting. */
+int tdg_set_inline_sums(tdg_ctx* ctx, int on);
 int tdg_last_pass_kernel_stats(tdg_ctx* ctx, tdg_kernel_stat* out, int cap);
 
 #ifdef __cplusplus

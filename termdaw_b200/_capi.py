@@ -37,7 +37,7 @@ class PassStats(C.Structure):
                 ("d2h_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("frames", C.c_uint64), ("voice_frames", C.c_uint64), ("reused_vertices", C.c_uint64),
-                ("reused_bytes", C.c_uint64)]
+                ("reused_bytes", C.c_uint64), ("inlined_vertices", C.c_uint64), ("inlined_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -140,6 +140,8 @@ class Library:
                                   c_u64p, c_u32p]),
         "reset_vertex_state": (C.c_int, [C.c_void_p]),
         "set_pipeline_group": (C.c_int, [C.c_void_p, C.c_uint32]),
+        "set_launch_waves": (C.c_int, [C.c_uint32]),
+        "set_inline_sums": (C.c_int, [C.c_void_p, C.c_int]),
         "last_pass_kernel_stats": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_int]),
     }
     # symbols only the oracle has (scalar maths for the reference's known-answer tests)
@@ -405,6 +407,9 @@ class Context:
     def set_oscillator_mode(self, libm_exact: bool = True):
         """tdg_set_oscillator_mode: True = glibc's sinf bit for bit (default), False = the 2-ulp f32 sine."""
         self._chk(self.lib.set_oscillator_mode(self.h, int(libm_exact)))
+
+    def set_inline_sums(self, on: bool):
+        self._chk(self.lib.set_inline_sums(self.h, 1 if on else 0))
 
     def set_pipeline_group(self, n: int):
         self._chk(self.lib.set_pipeline_group(self.h, int(n)))

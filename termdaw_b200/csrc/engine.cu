@@ -199,6 +199,7 @@ struct Engine {
     // step has 735 launch triples whose one-block-per-filter carry kernels and short grids cost far more (28 ms) than the
     // L2 hits save, so the default is one launch triple per level (0); the knob stays for single long renders (TDG_BP_L2_MB)
     uint64_t bp_l2_bytes = 0;
+    bool inline_sums = true;                     // Sum vertices with one k_fx consumer are evaluated inside that consumer (TDG_INLINE_SUMS=0: every vertex owns a buffer)
     bool bp_fused = true;                        // single-pass band pass (k_bp_fused) where no exchange step is needed and the pass is <= kBpFusedMaxTiles long; TDG_BP_FUSED=0: three launches
     uint32_t bp_fused_max_tiles = kBpFusedMaxTiles;   // longer passes keep the three-launch scan (TDG_BP_FUSED_MAX_TILES)
     bool libm_sin = true;                        // oscillators evaluate glibc's sinf exactly (TDG_FAST_SIN=1 / tdg_set_oscillator_mode(ctx, 0): f32 polynomial, <= 2 ulp)
@@ -254,6 +255,7 @@ static Engine* engine_get(int device, std::string* err) {
     if (const char* e = getenv("TDG_FAST_SIN")) g->libm_sin = atoi(e) == 0;
     if (const char* e = getenv("TDG_BP_L2_MB")) g->bp_l2_bytes = (uint64_t)std::max(0, atoi(e)) << 20;
     if (const char* e = getenv("TDG_BP_FUSED")) g->bp_fused = atoi(e) != 0;
+    if (const char* e = getenv("TDG_INLINE_SUMS")) g->inline_sums = atoi(e) != 0;
     if (const char* e = getenv("TDG_BP_FUSED_MAX_TILES")) g->bp_fused_max_tiles = (uint32_t)std::max(1, std::min(65535 * kBpStripTiles, atoi(e)));
     g->refs = 1;
     g_engines[device] = g;
@@ -805,6 +807,7 @@ struct PassReq {
     // pass-invariant cones (KeepRecord): vertices the render pass does not evaluate, and buffers living in the
     // lane's keep arena (written by the scan pass / read by the render pass)
     std::vector<char> skip;
+    std::vector<int> inl;              // per vertex: >= 0: a Sum vertex evaluated INSIDE that consumer's kernel (no buffer, no launch)
     std::vector<int64_t> keep_rel;     // per vertex: keep-arena offset, -1 = work arena
     std::vector<uint64_t> prefix;      // per vertex: chunks to evaluate (UINT64_MAX = all); < emit_n only for kept multi / lerp in a render
     bool keep_write = false, keep_read = false;
@@ -813,7 +816,8 @@ struct PassReq {
     uint32_t err_flag = 0;
 };
 
-template <typename T> struct TaskList { std::vector<T> v; uint32_t max_chunks = 0; uint64_t bytes = 0; void clear() { v.clear(); max_chunks = 0; bytes = 0; } };
+template <typename T> struct TaskList { std::vector<T> v; uint32_t max_chunks = 0; uint64_t bytes = 0; size_t n_plain = SIZE_MAX;   // fx lists: tasks [n_plain, size) have inlined inputs (grouped kernel variant)
+                                        void clear() { v.clear(); max_chunks = 0; bytes = 0; n_plain = SIZE_MAX; } };
 struct LevelTasks {
     TaskList<FxTask> fx, fx_adsr, fx_norm; TaskList<NormPrefixTask> nprefix; TaskList<NormScaleTask> nscale;
     TaskList<LoopTask> loop; TaskList<MultiTask> multi; TaskList<LerpTask> lerp;
@@ -861,14 +865,14 @@ struct Frag {
     std::vector<LevelTasks> levels;
     std::vector<QuantTask> quants; std::vector<ResampleTask> resamps;
     std::vector<RangeTask> ranges; uint32_t range_max = 0, resamp_chunks = 0; bool any_voice = false;
-    uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, algo = 0, reused_v = 0, reused_b = 0;
+    uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, algo = 0, reused_v = 0, reused_b = 0, inlined_v = 0, inlined_b = 0;
     void reset(size_t n_levels) {        // pooled on the engine: capacities survive from job to job
         blob.v.clear(); base = 0; ranges.clear(); range_max = 0; resamp_chunks = 0; any_voice = false;
         if (levels.size() > n_levels) levels.resize(n_levels);
         for (LevelTasks& L : levels) L.clear();
         levels.resize(n_levels);
         quants.clear(); resamps.clear();
-        quant_max = quant_bytes = resamp_max = resamp_bytes = algo = reused_v = reused_b = 0;
+        quant_max = quant_bytes = resamp_max = resamp_bytes = algo = reused_v = reused_b = inlined_v = inlined_b = 0;
     }
 };
 template <typename T> static void append_list(TaskList<T>& d, TaskList<T>& s) {
@@ -901,7 +905,7 @@ struct PassJob {
     std::vector<cudaEvent_t> clock_events;   // clock tables this job reads that were extended on another stream
     uint64_t sync_off = 0, sync_bytes = 0;    // tickets + flags of the fused band-pass kernels of the job (work arena, zeroed at submit)
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, quant_off = 0, resamp_off = 0;
-    uint64_t algo_bytes_total = 0, reused_v = 0, reused_b = 0;
+    uint64_t algo_bytes_total = 0, reused_v = 0, reused_b = 0, inlined_v = 0, inlined_b = 0;
     double t_start = 0, t_planned = 0, t_h2d_issued = 0, t_d2h0 = 0, t_submitted = 0;
     float dev_t0 = 0, dev_t1 = 0, dev_tdone = 0;      // device timeline relative to the batch start (trace only)
     uint64_t launches = 0, collectives = 0, d2h_bytes = 0, h2d_bytes = 0;
@@ -1004,8 +1008,36 @@ static int pass_plan(PassJob& J) {
                 K.lane = lane_index; K.mut_gen = x->mut_gen; K.total = r.total; K.n_pad = r.n_pad;
             }
         }
+        // ---- inlined sums.  A Sum vertex (extensions.rs:310-319 + pan + gain) with exactly one consumer that is itself a
+        // k_fx vertex (Sum, Normalize, Adsr) is evaluated inside that consumer's kernel: the consumer reads the sum's
+        // inputs, adds them in the sum's edge order from +0.0, applies the sum's pan and gain, and adds the result to its
+        // own running sum at the position of the edge — the reference's operations in the reference's order, without
+        // the 8 B/frame write and the 8 B/frame read of the intermediate buffer and without its launch.  One level deep
+        // only (an inlined sum's own inputs are real buffers); never for a buffer somebody else needs (taps, the kept
+        // frontier of a pass-invariant cone, the output).
+        r.inl.assign(V, -1);
+        if (g->inline_sums && !x->taps && x->output >= 0) {
+            std::vector<int> n_cons(V, 0), cons(V, -1);
+            for (int v = 0; v < V; ++v) if (r.level[v] >= 0) for (int u : x->verts[v].edges) { ++n_cons[u]; cons[u] = v; }
+            for (int L = 0; L <= max_level; ++L) for (int v : by_level[L]) {
+                const HVertex& hv = x->verts[v];
+                if (hv.kind != K_SUM || v == x->output || n_cons[v] != 1 || hv.edges.empty() || hv.edges.size() > 8) continue;
+                if (r.keep_rel[v] >= 0) continue;                                               // scan: kept for the render
+                if (r.keep_read && (K.inv[v] || K.off[v] >= 0)) continue;                       // render: read from the scan
+                const int cv = cons[v];
+                const HVertex& hc = x->verts[cv];
+                if (hc.kind != K_SUM && hc.kind != K_NORMALIZE && hc.kind != K_ADSR) continue;
+                if (r.keep_read && K.inv[cv]) continue;                                         // the consumer is not evaluated at all
+                bool nested = false;
+                for (int u : hv.edges) if (r.inl[u] >= 0) { nested = true; break; }
+                if (nested) continue;
+                r.inl[v] = cv;
+                for (int u : hv.edges) r.last_use[u] = std::max(r.last_use[u], r.level[cv]);   // its inputs live until the consumer has run
+            }
+        }
         for (int L = 0; L <= max_level; ++L) {
             for (int v : by_level[L]) {
+                if (r.inl[v] >= 0) continue;                                                            // no buffer of its own
                 if (r.keep_read && K.inv[v]) { r.skip[v] = 1; r.keep_rel[v] = K.off[v]; continue; }    // not evaluated; kept buffer if frontier
                 if (r.keep_read && K.off[v] >= 0 && (int)K.hz.size() == V) { r.keep_rel[v] = K.off[v]; r.prefix[v] = K.hz[v]; }   // only its head is redone
                 if (r.keep_rel[v] >= 0) { /* scan pass: this buffer lives in the keep arena */ }
@@ -1020,10 +1052,18 @@ static int pass_plan(PassJob& J) {
                 if (hv.kind == K_ADSR || hv.kind == K_SAMPLE_MULTI || hv.kind == K_SAMPLE_LERP || hv.kind == K_DEBUG_SINE ||
                     hv.kind == K_SYNTH || hv.kind == K_SAMPSYN) r.rng_off[v] = (int64_t)bump.alloc(std::max<uint64_t>(r.emit_n, 1) * 8 + 16);
             }
-            if (!x->taps)
-                for (int v : by_level[L])
-                    for (int u : x->verts[v].edges)
-                        if (!freed[u] && r.last_use[u] == L && u != x->output && r.buf_off[u] >= 0) { freed[u] = 1; free_slots.push_back((uint64_t)r.buf_off[u]); }
+            if (!x->taps) {
+                auto release = [&](int u) {
+                    if (!freed[u] && r.last_use[u] == L && u != x->output && r.buf_off[u] >= 0) { freed[u] = 1; free_slots.push_back((uint64_t)r.buf_off[u]); }
+                };
+                for (int v : by_level[L]) {
+                    if (r.inl[v] >= 0) continue;                 // its inputs are released by the consumer's level
+                    for (int u : x->verts[v].edges) {
+                        if (r.inl[u] == v) { for (int w : x->verts[u].edges) release(w); }
+                        else release(u);
+                    }
+                }
+            }
         }
         if (r.x_ranks > 1) {
             // exchange slots: per level [normalize peaks][band-pass maps]; identical on every rank
@@ -1244,6 +1284,7 @@ static int pass_plan(PassJob& J) {
             if (r.level[v] < 0) continue;
             HVertex& hv = x->verts[v];
             if (r.skip[v]) { ++F.reused_v; F.reused_b += 8ull * (hv.edges.size() + 1) * r.n_frames; continue; }   // the scan's buffer stands
+            if (r.inl[v] >= 0) { ++F.inlined_v; F.inlined_b += 16ull * r.n_frames; continue; }                  // evaluated inside its consumer: no write, no read back
             const uint64_t chunks_v = std::min<uint64_t>(r.prefix[v], r.emit_n);    // < emit_n: kept multi / lerp, head only
             const uint64_t frames_v = chunks_v * x->bl;
             LevelTasks& LT = levels[r.level[v]];
@@ -1253,21 +1294,39 @@ static int pass_plan(PassJob& J) {
             h.n_frames = r.n_frames; h.n_chunks = (uint32_t)chunks_v; h.bl = x->bl;
             h.pg = make_pg(hv.gain, hv.angle);
             const uint32_t nch = (uint32_t)chunks_v;
-            uint64_t in_off = 0;
+            uint64_t in_off = 0, grp_off = 0;
+            size_t n_pairs = hv.edges.size(), n_grp = 0;            // pointer pairs the kernel reads; groups (only with inlined inputs)
             if (hv.has_input()) {
-                in_off = B.alloc(std::max<size_t>(hv.edges.size(), 1) * 2 * sizeof(float*));
-                if (in_off == UINT64_MAX) return x->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
+                bool any_inl = false;
+                for (int u : hv.edges) if (r.inl[u] == v) { any_inl = true; break; }
+                if (any_inl) {
+                    n_pairs = 0; n_grp = hv.edges.size();
+                    for (int u : hv.edges) n_pairs += r.inl[u] == v ? x->verts[u].edges.size() : 1;
+                }
+                in_off = B.alloc(std::max<size_t>(n_pairs, 1) * 2 * sizeof(float*));
+                if (any_inl) grp_off = B.alloc(n_grp * sizeof(FxGroup));
+                if (in_off == UINT64_MAX || grp_off == UINT64_MAX) return x->fail(TDG_ERR_CUDA, "pinned plan buffer allocation failed");
                 const float** ip = B.at<const float*>(in_off);
+                FxGroup* gp = any_inl ? B.at<FxGroup>(grp_off) : nullptr;
+                size_t at = 0;
+                auto put = [&](int u) { const float* il = reinterpret_cast<const float*>(W + r.buf_off[u]); ip[2 * at] = il; ip[2 * at + 1] = il + r.n_pad; ++at; };
                 for (size_t a = 0; a < hv.edges.size(); ++a) {
-                    const float* il = reinterpret_cast<const float*>(W + r.buf_off[hv.edges[a]]);
-                    ip[2 * a] = il; ip[2 * a + 1] = il + r.n_pad;
+                    const int u = hv.edges[a];
+                    if (gp) {
+                        FxGroup& G = gp[a];
+                        G.first = (uint32_t)at; G.nested = r.inl[u] == v ? 1u : 0u; G.pad = 0;
+                        G.count = G.nested ? (uint32_t)x->verts[u].edges.size() : 1u;
+                        G.pg = G.nested ? make_pg(x->verts[u].gain, x->verts[u].angle) : PanGain{1.0f, 1.0f, 1.0f, 0};
+                    }
+                    if (r.inl[u] == v) for (int w : x->verts[u].edges) put(w); else put(u);
                 }
             }
-            const uint64_t io_bytes = 8ull * (hv.edges.size() + 1) * r.n_frames;
+            const uint64_t io_bytes = 8ull * (n_pairs + 1) * r.n_frames;
             auto fx_task = [&](uint32_t mode) {
                 FxTask t; memset(&t, 0, sizeof t);
-                t.h = h; t.mode = mode; t.n_in = (uint32_t)hv.edges.size(); t.in_off = in_off; t.sr = x->sr;
-                if (hv.edges.size() <= (size_t)kInlineInputs) memcpy(t.ins, B.at<const float*>(in_off), hv.edges.size() * 2 * sizeof(float*));
+                t.h = h; t.mode = mode; t.n_in = (uint32_t)n_pairs; t.in_off = in_off; t.sr = x->sr;
+                t.n_grp = (uint32_t)n_grp; t.grp_off = grp_off;
+                if (n_pairs <= (size_t)kInlineInputs) memcpy(t.ins, B.at<const float*>(in_off), n_pairs * 2 * sizeof(float*));
                 t.fsr = (float)x->sr; t.rsr = 1.0f / t.fsr;
                 return t;
             };
@@ -1527,7 +1586,7 @@ static int pass_plan(PassJob& J) {
     std::vector<ResampleTask>& resamps = J.resamps; uint64_t &resamp_max = J.resamp_max, &resamp_bytes = J.resamp_bytes;
     uint64_t& algo_bytes_total = J.algo_bytes_total;
     quants.clear(); resamps.clear(); quant_max = quant_bytes = resamp_max = resamp_bytes = algo_bytes_total = 0;
-    J.reused_v = J.reused_b = 0; J.ranges.clear(); J.range_max = 0; J.resamp_chunks = 0; J.any_voice = false;
+    J.reused_v = J.reused_b = J.inlined_v = J.inlined_b = 0; J.ranges.clear(); J.range_max = 0; J.resamp_chunks = 0; J.any_voice = false;
     {
         uint64_t tot = 0;
         for (size_t i = 0; i < n_frags; ++i) { Frag& F = frags[i]; F.base = align_up(tot, 256); tot = F.base + F.blob.v.size(); }
@@ -1542,9 +1601,9 @@ static int pass_plan(PassJob& J) {
             const uint64_t b = F.base;
             for (size_t L = 0; L < F.levels.size(); ++L) {
                 LevelTasks& S = F.levels[L]; LevelTasks& Dst = levels[L];
-                for (FxTask& t : S.fx.v) t.in_off += b;
-                for (FxTask& t : S.fx_adsr.v) t.in_off += b;
-                for (FxTask& t : S.fx_norm.v) t.in_off += b;
+                for (FxTask& t : S.fx.v) { t.in_off += b; t.grp_off += b; }
+                for (FxTask& t : S.fx_adsr.v) { t.in_off += b; t.grp_off += b; }
+                for (FxTask& t : S.fx_norm.v) { t.in_off += b; t.grp_off += b; }
                 for (MultiTask& t : S.multi.v) t.hits_off += b;
                 for (LerpTask& t : S.lerp.v) t.hits_off += b;
                 for (BpTask& t : S.bp.v) t.in_off += b;
@@ -1564,7 +1623,7 @@ static int pass_plan(PassJob& J) {
             for (QuantTask& t : F.quants) quants.push_back(t);
             quant_max = std::max(quant_max, F.quant_max); quant_bytes += F.quant_bytes;
             resamp_max = std::max(resamp_max, F.resamp_max); resamp_bytes += F.resamp_bytes;
-            algo_bytes_total += F.algo; J.reused_v += F.reused_v; J.reused_b += F.reused_b;
+            algo_bytes_total += F.algo; J.reused_v += F.reused_v; J.reused_b += F.reused_b; J.inlined_v += F.inlined_v; J.inlined_b += F.inlined_b;
         }
     }
     // task arrays go into the blob too: one H2D for the whole pass
@@ -1577,6 +1636,9 @@ static int pass_plan(PassJob& J) {
     };
     for (size_t L = 0; L < levels.size(); ++L) {
         LevelTasks& T = levels[L];
+        // tasks with inlined inputs go to the end of their list: they are launched with the grouped kernel variant
+        for (TaskList<FxTask>* tl : {&T.fx, &T.fx_adsr, &T.fx_norm})
+            tl->n_plain = (size_t)(std::stable_partition(tl->v.begin(), tl->v.end(), [](const FxTask& t) { return t.n_grp == 0; }) - tl->v.begin());
         offs[L].fx = put(T.fx.v.data(), T.fx.v.size() * sizeof(FxTask));
         offs[L].fx_adsr = put(T.fx_adsr.v.data(), T.fx_adsr.v.size() * sizeof(FxTask));
         offs[L].fx_norm = put(T.fx_norm.v.data(), T.fx_norm.v.size() * sizeof(FxTask));
@@ -1677,9 +1739,20 @@ static int pass_submit(PassJob& J) {
         LAUNCH_SPLIT(KC_SYNTH, T.synth, VoiceTask, offs[L].synth, T.synth.bytes, launch_voice(VOICE_SYNTH, tp, nb, T.synth.max_chunks, T.synth_exact, g->libm_sin, D, s));
         LAUNCH_SPLIT(KC_SAMPSYN, T.sampsyn, VoiceTask, offs[L].sampsyn, T.sampsyn.bytes,
                      launch_voice(VOICE_SAMPSYN, tp, nb, T.sampsyn.max_chunks, T.sampsyn_exact, false, D, s));
-        LAUNCH_SPLIT(KC_FX_SUM, T.fx, FxTask, offs[L].fx, T.fx.bytes, launch_fx(FX_SUM, tp, nb, T.fx.max_chunks, vec, false, D, s));
-        LAUNCH_SPLIT(KC_FX_ADSR, T.fx_adsr, FxTask, offs[L].fx_adsr, T.fx_adsr.bytes, launch_fx(FX_ADSR, tp, nb, T.fx_adsr.max_chunks, vec, T.fx_adsr_exact, D, s));
-        LAUNCH_SPLIT(KC_FX_NORM, T.fx_norm, FxTask, offs[L].fx_norm, T.fx_norm.bytes, launch_fx(FX_NORM_PEAK, tp, nb, T.fx_norm.max_chunks, vec, false, D, s));
+        // k_fx lists: plain tasks first, then (other kernel instantiation) the tasks that evaluate inlined Sum inputs
+#define LAUNCH_FX(cls, list, off, mode, exact) \
+        for (int grouped = 0; grouped < 2; ++grouped) { \
+            const size_t q0 = grouped ? std::min((list).n_plain, (list).v.size()) : 0, q1 = grouped ? (list).v.size() : std::min((list).n_plain, (list).v.size()); \
+            for (size_t b0 = q0; b0 < q1; b0 += kMaxY) { \
+                const uint32_t nb = (uint32_t)std::min<size_t>(kMaxY, q1 - b0); \
+                const FxTask* tp = reinterpret_cast<const FxTask*>(D + (off)) + b0; \
+                if (g->profiling) CU(cudaEventRecord(ev_at(2 * timed.size()), s)); \
+                CU(launch_fx(mode, tp, nb, (list).max_chunks, vec, exact, grouped != 0, D, s)); ++launches; \
+                if (g->profiling) { CU(cudaEventRecord(ev_at(2 * timed.size() + 1), s)); \
+                                    timed.push_back({cls, (list).bytes * nb / std::max<size_t>((list).v.size(), 1)}); } } }
+        LAUNCH_FX(KC_FX_SUM, T.fx, offs[L].fx, FX_SUM, false);
+        LAUNCH_FX(KC_FX_ADSR, T.fx_adsr, offs[L].fx_adsr, FX_ADSR, T.fx_adsr_exact);
+        LAUNCH_FX(KC_FX_NORM, T.fx_norm, offs[L].fx_norm, FX_NORM_PEAK, false);
         // band pass = aggregate, carry, apply over the same inputs.  Without an exchange step in between the three
         // launches run over groups of filters whose inputs + outputs fit the L2 (bp_l2_bytes): the apply pass then
         // finds the inputs the aggregate pass just streamed in cache instead of fetching them from HBM again
@@ -1865,7 +1938,7 @@ static int pass_wait(PassJob& J) {
         x->launches += launches;
         for (int k = 0; k < KC_COUNT; ++k) x->kstats[k] = ks[k];
         if (reqs.size() > 1) x->stats.algorithmic_bytes = algo_bytes_total;
-        x->stats.reused_vertices = J.reused_v; x->stats.reused_bytes = J.reused_b;
+        x->stats.reused_vertices = J.reused_v; x->stats.reused_bytes = J.reused_b; x->stats.inlined_vertices = J.inlined_v; x->stats.inlined_bytes = J.inlined_b;
         if (r.err_flag) rc = x->fail(TDG_ERR_TOO_WIDE, "sample too wide for bit depth (hound TooWide; the reference panics)");
     }
     return rc;
@@ -1948,6 +2021,7 @@ static int run_jobs_pipelined(Engine* g, std::vector<PassJob>& jobs, PassStats* 
         tot.plan_ms += J.t_planned - J.t_start; tot.h2d_ms += J.t_h2d_issued - J.t_planned;
         tot.h2d_bytes += J.h2d_bytes; tot.d2h_bytes += J.d2h_bytes; tot.kernel_launches += J.launches;
         tot.algorithmic_bytes += J.algo_bytes_total; tot.reused_vertices += J.reused_v; tot.reused_bytes += J.reused_b;
+        tot.inlined_vertices += J.inlined_v; tot.inlined_bytes += J.inlined_b;
         for (PassReq& r : J.reqs) { tot.frames += r.n_frames; }
         for (int q = 0; q < KC_COUNT; ++q) { ks_out[q].launches += J.ks[q].launches; ks_out[q].ms += J.ks[q].ms; ks_out[q].bytes += J.ks[q].bytes; }
     }
@@ -2825,6 +2899,8 @@ void tdg_host_free(void* p) { if (p) cudaFreeHost(p); }
 int tdg_set_pass_reuse(tdg_ctx* h, int on) { h->c.eng->reuse = on != 0; h->c.keep.valid = false; return TDG_OK; }
 int tdg_set_oscillator_mode(tdg_ctx* h, int libm_exact) { h->c.eng->libm_sin = libm_exact != 0; h->c.keep.valid = false; ++h->c.mut_gen; return TDG_OK; }
 int tdg_set_profiling(tdg_ctx* h, int on) { h->c.eng->profiling = on != 0; return TDG_OK; }
+int tdg_set_inline_sums(tdg_ctx* h, int on) { h->c.eng->inline_sums = on != 0; h->c.keep.valid = false; return TDG_OK; }
+int tdg_set_launch_waves(uint32_t waves) { set_launch_waves(waves); return TDG_OK; }
 int tdg_set_pipeline_group(tdg_ctx* h, uint32_t projects_per_group) { h->c.eng->pipeline_group = projects_per_group; return TDG_OK; }
 int tdg_last_pass_kernel_stats(tdg_ctx* h, tdg_kernel_stat* out, int cap) {
     static const char* names[KC_COUNT] = {"k_sample_loop", "k_sample_multi", "k_sample_lerp", "k_voice<debug_sine>", "k_voice<synth>",
@@ -2845,6 +2921,7 @@ int tdg_last_pass_stats(tdg_ctx* h, tdg_pass_stats* out) {
     out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes; out->kernel_launches = s.kernel_launches;
     out->algorithmic_bytes = s.algorithmic_bytes; out->frames = s.frames; out->voice_frames = s.voice_frames;
     out->reused_vertices = s.reused_vertices; out->reused_bytes = s.reused_bytes;
+    out->inlined_vertices = s.inlined_vertices; out->inlined_bytes = s.inlined_bytes;
     return TDG_OK;
 }
 

@@ -61,6 +61,7 @@ struct PassStats {
     double device_ms = 0, plan_ms = 0, h2d_ms = 0, d2h_ms = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0, kernel_launches = 0, algorithmic_bytes = 0, frames = 0, voice_frames = 0;
     uint64_t reused_vertices = 0, reused_bytes = 0;     // render pass: vertices (and their algorithmic bytes) taken from the scan pass
+    uint64_t inlined_vertices = 0, inlined_bytes = 0;   // Sum vertices evaluated inside their consumer's kernel, and the intermediate-buffer bytes not moved
 };
 
 // What a normalize scan leaves behind for the render that follows it (DESIGN.md "pass-invariant cones"):

@@ -250,17 +250,19 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
 #ifndef TDG_BP_MINB
 #define TDG_BP_MINB 5        // measured: 4 -> 6.66 ms, 5 -> 6.48 ms, 6 -> 6.95 ms
 #endif
-template <int MODE, bool VEC, bool EXACT>
-__global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+// GRP: the task list holds vertices some of whose inputs are inlined Sum vertices (FxGroup records; engine.cu "inlined
+// sums").  A separate instantiation, so that the plain kernels keep their register budget.
+template <int MODE, bool VEC, bool EXACT, bool GRP>
+__global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? (GRP ? 4 : TDG_ADSR_MINB) : GRP ? 5 : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ FxTask T;
     load_task(&T, tasks + blockIdx.y);
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
     // the adsr variant walks TDG_ADSR_CPB consecutive chunks per block (see the gather kernels: the task load, its
     // barrier and the block launch are paid once per group of chunks)
-    constexpr uint32_t CPB = MODE == FX_ADSR ? TDG_ADSR_CPB : TDG_FX_CPB;
-    const uint32_t kc0 = blockIdx.x * CPB;
+    constexpr uint32_t CPB = MODE == FX_ADSR ? TDG_ADSR_CPB : TDG_FX_CPB;      // compile-time maximum; cpb <= CPB is the launch's choice
+    const uint32_t kc0 = blockIdx.x * (CPB == 1 ? 1u : cpb);
     if (kc0 >= T.h.n_chunks) return;
-    const uint32_t kc1 = CPB == 1 ? kc0 + 1 : min(kc0 + CPB, T.h.n_chunks);
+    const uint32_t kc1 = CPB == 1 ? kc0 + 1 : min(kc0 + cpb, T.h.n_chunks);
     const uint32_t bl = T.h.bl;
     uint64_t p0 = 0;
     const bool staged = T.n_in <= (uint32_t)kInlineInputs;     // input pointers arrived with the task (shared memory)
@@ -271,7 +273,36 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? TDG_ADSR_MINB :
         const uint64_t p = p0 + i;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { l[j] = 0.0f; r[j] = 0.0f; }
-        if (staged) {
+        if (GRP) {
+            // some edges are inlined Sum vertices (FxGroup): an edge's value is either a buffer or the sum of a
+            // vertex's inputs from +0.0 in its edge order with its pan and gain applied — k_fx<FX_SUM>'s operations on
+            // that vertex, in registers — and the edges are added in this vertex's edge order as always
+            const FxGroup* __restrict__ G = reinterpret_cast<const FxGroup*>(blob + T.grp_off);
+            for (uint32_t q = 0; q < T.n_grp; ++q) {
+                const uint4 ga = __ldg(reinterpret_cast<const uint4*>(G + q));         // first, count, nested
+                float x[4], y[4];
+                if (!ga.z) {
+                    ld4<VEC>(ins[2 * ga.x], p, nv, x);
+                    ld4<VEC>(ins[2 * ga.x + 1], p, nv, y);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { x[j] = 0.0f; y[j] = 0.0f; }
+                    for (uint32_t b = 0; b < ga.y; ++b) {
+                        float u[4], w[4];
+                        ld4<VEC>(ins[2 * (ga.x + b)], p, nv, u);
+                        ld4<VEC>(ins[2 * (ga.x + b) + 1], p, nv, w);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { x[j] += u[j]; y[j] += w[j]; }
+                    }
+                    const float4 pf = __ldg(reinterpret_cast<const float4*>(G + q) + 1);
+                    PanGain pg; pg.l_amp = pf.x; pg.r_amp = pf.y; pg.gain = pf.z; pg.flags = __float_as_uint(pf.w);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) apply_pg(x[j], y[j], pg);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { l[j] += x[j]; r[j] += y[j]; }
+            }
+        } else if (staged) {
 #pragma unroll 2
             for (uint32_t a = 0; a < T.n_in; ++a) {
                 float x[4], y[4];
@@ -484,12 +515,12 @@ __global__ void __launch_bounds__(TDG_THREADS) k_norm_scale(const NormScaleTask*
 #endif
 // sample_loop_gen (extensions.rs:331-341): buf[i] = sample[(t + i) % L]
 template <bool VEC>
-__global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __restrict__ tasks) {
+__global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __restrict__ tasks, uint32_t cpb) {
     __shared__ LoopTask T;
     load_task(&T, tasks + blockIdx.y);
-    const uint32_t kc0 = blockIdx.x * TDG_GATHER_CPB;
+    const uint32_t kc0 = blockIdx.x * cpb;
     if (kc0 >= T.h.n_chunks) return;
-    const uint32_t kc1 = min(kc0 + (uint32_t)TDG_GATHER_CPB, T.h.n_chunks);
+    const uint32_t kc1 = min(kc0 + cpb, T.h.n_chunks);
     const uint32_t bl = T.h.bl;
     const uint64_t len = T.len;
 #pragma unroll 1
@@ -527,15 +558,15 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __r
 // All hits share one sample length, so the live set at frame p is the contiguous range of hits with
 // start in (p - L, p]; hits are sorted by start (push order).
 template <bool VEC>
-__global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ MultiTask T;
     load_task(&T, tasks + blockIdx.y);
-    const uint32_t kc0 = blockIdx.x * TDG_GATHER_CPB;
+    const uint32_t kc0 = blockIdx.x * cpb;
     if (kc0 >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
     const MultiHit* hits = reinterpret_cast<const MultiHit*>(blob + T.hits_off);
     // candidates for a chunk: start > p0 - L  and  start <= p0 + bl - 1 (k_chunk_ranges)
-    const uint32_t kc1 = min(kc0 + (uint32_t)TDG_GATHER_CPB, T.h.n_chunks);
+    const uint32_t kc1 = min(kc0 + cpb, T.h.n_chunks);
     Range2 rg_next = T.ranges[kc0];
     const int64_t len = (int64_t)T.len;
 #pragma unroll 1
@@ -577,15 +608,15 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* _
 // sample_lerp_gen (extensions.rs:384-421): primary = last hit at or before the frame, ghost = the
 // one before it, cross-faded while the countdown (reset by each hit) runs.
 template <bool VEC>
-__global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ LerpTask T;
     load_task(&T, tasks + blockIdx.y);
-    const uint32_t kc0 = blockIdx.x * TDG_GATHER_CPB;
+    const uint32_t kc0 = blockIdx.x * cpb;
     if (kc0 >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
     const LerpHit* hits = reinterpret_cast<const LerpHit*>(blob + T.hits_off);
     // index of the last hit with frame <= p0 (entries 0 and 1 are the carried ghost / primary); k_chunk_ranges
-    const uint32_t kc1 = min(kc0 + (uint32_t)TDG_GATHER_CPB, T.h.n_chunks);
+    const uint32_t kc1 = min(kc0 + cpb, T.h.n_chunks);
     uint32_t base_next = T.ranges[kc0].x;
     const int64_t lm1 = (int64_t)T.len - 1;
     const int64_t lerp_len = (int64_t)T.lerp_len;
@@ -721,12 +752,12 @@ __device__ __forceinline__ int wavetable_row(float fps, float ymax, float t, flo
 // LIBM: sin is glibc's sinf restated in double precision (m_sinf_glibc: bit-exact against the reference's libm
 // call); false = the f32 Cody-Waite + minimax evaluation d_sin (<= 2 ulp, tdg_set_oscillator_mode(ctx, 0)).
 template <int KIND, bool EXACT, int F, bool LIBM>
-__global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : TDG_SAMPSYN_MINB) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+__global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : TDG_SAMPSYN_MINB) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ VoiceTask T;
     load_task(&T, tasks + blockIdx.y);
-    const uint32_t kc0 = blockIdx.x * TDG_VOICE_CPB;
+    const uint32_t kc0 = blockIdx.x * cpb;
     if (kc0 >= T.h.n_chunks) return;
-    const uint32_t kc1 = TDG_VOICE_CPB == 1 ? kc0 + 1 : min(kc0 + (uint32_t)TDG_VOICE_CPB, T.h.n_chunks);
+    const uint32_t kc1 = min(kc0 + cpb, T.h.n_chunks);
     const uint32_t bl = T.h.bl;
     const float4* __restrict__ gsegs = reinterpret_cast<const float4*>(T.segs);
     const float* __restrict__ grelv2 = T.relv2;
@@ -1412,14 +1443,14 @@ __device__ __forceinline__ void quantise_block(const QuantTask& T, uint64_t b0, 
 #ifndef TDG_QUANT_CPB
 #define TDG_QUANT_CPB 4         // spans (chunks) per block: 1 -> 1.59, 4 -> 1.53 ms per bench step
 #endif
-__global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __restrict__ tasks) {
+__global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __restrict__ tasks, uint32_t cpb) {
     __shared__ QuantTask T;
     load_task(&T, tasks + blockIdx.y);
     const uint32_t span = T.span;
     bool wide = false;
 #pragma unroll 1
-    for (uint32_t c = 0; c < (uint32_t)TDG_QUANT_CPB; ++c) {
-    const uint64_t blk = (uint64_t)blockIdx.x * TDG_QUANT_CPB + c;
+    for (uint32_t c = 0; c < cpb; ++c) {
+    const uint64_t blk = (uint64_t)blockIdx.x * cpb + c;
     const uint64_t b0 = blk * span;
     if (b0 >= T.n) break;
     if (T.runmax) {
@@ -1585,17 +1616,35 @@ __global__ void k_scale_by_inv(float* __restrict__ x, uint64_t n, const float* _
 // ------------------------------------------------------------------------------------ launchers
 static inline dim3 grid2(uint64_t x, uint32_t y) { return dim3((unsigned)(x ? x : 1), y, 1); }   // zero-length pass: blocks find nothing to do
 
+// Chunks per block, chosen per launch: the compile-time maximum while the grid still has >= g_cpb_waves waves of blocks
+// (a block that walks 8 chunks is 8 times longer, and a grid of a few waves ends in a long tail: configs[2]'s one
+// 512-voice vertex went from 61.1 to 63.9 ms with a fixed 8), halved until it does.
+static uint64_t g_cpb_waves = []() -> uint64_t { const char* e = getenv("TDG_LAUNCH_WAVES"); return e ? (uint64_t)atoll(e) : 16; }();
+void set_launch_waves(uint32_t waves) { g_cpb_waves = waves; }
+static inline uint32_t pick_cpb(uint32_t cpb_max, uint32_t max_chunks, uint32_t n_tasks, uint32_t blocks_per_sm) {
+    static int n_sm = 0;
+    if (n_sm == 0) { int dev = 0; cudaDeviceProp pr; if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess) n_sm = pr.multiProcessorCount; else n_sm = 148; }
+    uint32_t cpb = cpb_max;
+    while (cpb > 1 && (uint64_t)((max_chunks + cpb - 1) / cpb) * n_tasks < g_cpb_waves * (uint64_t)n_sm * blocks_per_sm) cpb >>= 1;
+    return cpb;
+}
+
 #define TDG_VEC_DISPATCH(vec, K, ...) do { if (vec) K<true> __VA_ARGS__; else K<false> __VA_ARGS__; } while (0)
 
-cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, const uint8_t* blob, cudaStream_t s) {
-    const dim3 g = grid2((max_chunks + TDG_FX_CPB - 1) / TDG_FX_CPB, n);
-    if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_SUM, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
+template <bool GRP>
+static void launch_fx_t(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, const uint8_t* blob, cudaStream_t s) {
+    const uint32_t c1 = pick_cpb(TDG_FX_CPB, max_chunks, n, 6), ca = pick_cpb(TDG_ADSR_CPB, max_chunks, n, TDG_ADSR_MINB);
+    const dim3 g = grid2((max_chunks + c1 - 1) / c1, n);
+    if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); else k_fx<FX_SUM, false, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); }
     else if (mode == FX_ADSR) {
-        const dim3 ga = grid2((max_chunks + TDG_ADSR_CPB - 1) / TDG_ADSR_CPB, n);
-        if (exact) { if (vec) k_fx<FX_ADSR, true, true><<<ga, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, true><<<ga, TDG_THREADS, 0, s>>>(t, blob); }
-        else { if (vec) k_fx<FX_ADSR, true, false><<<ga, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_ADSR, false, false><<<ga, TDG_THREADS, 0, s>>>(t, blob); }
+        const dim3 ga = grid2((max_chunks + ca - 1) / ca, n);
+        if (exact) { if (vec) k_fx<FX_ADSR, true, true, GRP><<<ga, TDG_THREADS, 0, s>>>(t, blob, ca); else k_fx<FX_ADSR, false, true, GRP><<<ga, TDG_THREADS, 0, s>>>(t, blob, ca); }
+        else { if (vec) k_fx<FX_ADSR, true, false, GRP><<<ga, TDG_THREADS, 0, s>>>(t, blob, ca); else k_fx<FX_ADSR, false, false, GRP><<<ga, TDG_THREADS, 0, s>>>(t, blob, ca); }
     }
-    else { if (vec) k_fx<FX_NORM_PEAK, true, false><<<g, TDG_THREADS, 0, s>>>(t, blob); else k_fx<FX_NORM_PEAK, false, false><<<g, TDG_THREADS, 0, s>>>(t, blob); }
+    else { if (vec) k_fx<FX_NORM_PEAK, true, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); else k_fx<FX_NORM_PEAK, false, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); }
+}
+cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, bool grouped, const uint8_t* blob, cudaStream_t s) {
+    if (grouped) launch_fx_t<true>(mode, t, n, max_chunks, vec, exact, blob, s); else launch_fx_t<false>(mode, t, n, max_chunks, vec, exact, blob, s);
     return cudaGetLastError();
 }
 cudaError_t launch_env_table(float* clock, uint32_t bl, uint32_t row0, uint32_t depth, float fsr, cudaStream_t s) {
@@ -1629,15 +1678,18 @@ cudaError_t launch_norm_scale(const NormScaleTask* t, uint32_t n, uint32_t max_c
     return cudaGetLastError();
 }
 cudaError_t launch_sample_loop(const LoopTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_sample_loop, <<<grid2((max_chunks + TDG_GATHER_CPB - 1) / TDG_GATHER_CPB, n), TDG_THREADS, 0, s>>>(t));
+    const uint32_t cpb = pick_cpb(TDG_GATHER_CPB, max_chunks, n, 6);
+    TDG_VEC_DISPATCH(vec, k_sample_loop, <<<grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s>>>(t, cpb));
     return cudaGetLastError();
 }
 cudaError_t launch_sample_multi(const MultiTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_sample_multi, <<<grid2((max_chunks + TDG_GATHER_CPB - 1) / TDG_GATHER_CPB, n), TDG_THREADS, 0, s>>>(t, blob));
+    const uint32_t cpb = pick_cpb(TDG_GATHER_CPB, max_chunks, n, 6);
+    TDG_VEC_DISPATCH(vec, k_sample_multi, <<<grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s>>>(t, blob, cpb));
     return cudaGetLastError();
 }
 cudaError_t launch_sample_lerp(const LerpTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_sample_lerp, <<<grid2((max_chunks + TDG_GATHER_CPB - 1) / TDG_GATHER_CPB, n), TDG_THREADS, 0, s>>>(t, blob));
+    const uint32_t cpb = pick_cpb(TDG_GATHER_CPB, max_chunks, n, 6);
+    TDG_VEC_DISPATCH(vec, k_sample_lerp, <<<grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s>>>(t, blob, cpb));
     return cudaGetLastError();
 }
 
@@ -1656,7 +1708,8 @@ static cudaError_t launch_voice_t(const VoiceTask* t, uint32_t n, uint32_t max_c
         if (e != cudaSuccess) return e;
         attr_set = g_voice_smem;
     }
-    kfn<<<grid2((max_chunks + TDG_VOICE_CPB - 1) / TDG_VOICE_CPB, n), TDG_THREADS, (size_t)g_voice_smem, s>>>(t, blob);
+    const uint32_t cpb = pick_cpb(TDG_VOICE_CPB, max_chunks, n, 5);
+    kfn<<<grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, (size_t)g_voice_smem, s>>>(t, blob, cpb);
     return cudaGetLastError();
 }
 cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool exact, bool libm_sin, const uint8_t* blob, cudaStream_t s) {
@@ -1695,7 +1748,8 @@ cudaError_t launch_bp_fused(const BpTask* t, uint32_t n, uint32_t max_tiles, boo
     return cudaGetLastError();
 }
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s) {
-    k_quantise<<<grid2(max_blocks ? (max_blocks + TDG_QUANT_CPB - 1) / TDG_QUANT_CPB : 1, n), TDG_THREADS, 0, s>>>(t);
+    const uint32_t cpb = pick_cpb(TDG_QUANT_CPB, (uint32_t)std::min<uint64_t>(max_blocks, 0xffffffffu), n, 8);
+    k_quantise<<<grid2(max_blocks ? (max_blocks + cpb - 1) / cpb : 1, n), TDG_THREADS, 0, s>>>(t, cpb);
     return cudaGetLastError();
 }
 cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s) {

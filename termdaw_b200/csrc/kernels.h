@@ -7,7 +7,8 @@
 
 namespace tdg {
 
-cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, const uint8_t* blob, cudaStream_t s);
+void set_launch_waves(uint32_t waves);
+cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, bool grouped, const uint8_t* blob, cudaStream_t s);
 // clock table rows [row0, depth) of one (sr, bl); per-chunk index ranges of every event-driven vertex of a pass
 cudaError_t launch_env_table(float* clock, uint32_t bl, uint32_t row0, uint32_t depth, float fsr, cudaStream_t s);
 cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, bool any_segs, const uint8_t* blob, cudaStream_t s);   // + the voice / adsr segment tables

@@ -115,6 +115,11 @@ struct VoiceSeg {           // one voice over frames [ia, ib) of one chunk, in v
 static const int kInlineInputs = 8;     // the reference's graphs rarely fan in wider; wider vertices read the blob table
 enum FxMode : uint32_t { FX_SUM = 0, FX_ADSR = 1, FX_NORM_PEAK = 2 };
 
+// One input EDGE of a k_fx vertex when some of its inputs are inlined Sum vertices (engine.cu "inlined sums"): `count`
+// pointer pairs starting at pair `first`; nested = 1: they are the inputs of a Sum vertex whose output is that edge's
+// value — summed in order from +0.0, then that vertex's pan and gain (the operations of k_fx<FX_SUM>, in registers).
+struct FxGroup { uint32_t first, count, nested, pad; PanGain pg; };
+
 struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan + gain, one kernel
     TaskHdr h;
     uint32_t mode, n_in;
@@ -128,7 +133,8 @@ struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan 
     const uint32_t* seg_ptr; // [n_chunks + 1]
     const AdsrSeg* segs;
     float* peaks;           // FX_NORM_PEAK: [n_chunks] max |x| over L and R of the summed chunk
-    uint32_t no_store, pad1; // FX_NORM_PEAK of the output vertex in a scan pass: only the peaks are needed
+    uint32_t no_store, n_grp; // no_store: FX_NORM_PEAK of the output vertex in a scan pass: only the peaks are needed
+    uint64_t grp_off;       // blob: n_grp FxGroup records (n_grp = number of edges) when some inputs are inlined Sum vertices; n_grp = 0: plain pairs
 };
 
 // Time sharding: a pass split into `x_ranks` consecutive segments.  Every DAG level owns

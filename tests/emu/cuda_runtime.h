@@ -115,6 +115,7 @@ static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSu
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof *p); snprintf(p->name, sizeof p->name, "emulated sm_100 (tests/emu)"); p->major = 10; p->minor = 0;
     p->multiProcessorCount = 148; p->totalGlobalMem = (size_t)64 << 30; return cudaSuccess;

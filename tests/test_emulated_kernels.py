@@ -24,6 +24,7 @@ import test_golden as TG  # noqa: E402
 import test_gpu_parity as TP  # noqa: E402
 import test_pass_reuse as TR  # noqa: E402
 import test_timeshard as TS  # noqa: E402
+import test_inline_sums as TI  # noqa: E402
 
 
 @pytest.fixture(scope="session")
@@ -33,7 +34,21 @@ def emulib(tmp_path_factory):
     path = build_emu.build(str(tmp_path_factory.mktemp("tdg_emu")))
     lib = Library(path, "tdg_")
     assert lib.exported()
+    lib.set_launch_waves(0)          # the test projects are short: always walk the maximum number of chunks per block
     return lib
+
+
+# ---- inlined sums, chunks per block (tests/test_inline_sums.py) -------------------------------------------
+def test_emu_inlined_sums(emulib, oracle):
+    TI.check_sum_chain(emulib, oracle)
+    TI.check_batch_projects(emulib, oracle, indices=range(8), scale=0.03)
+
+
+def test_emu_chunks_per_block(emulib, oracle):
+    try:
+        TI.check_launch_waves(emulib, oracle, indices=(0, 3), scale=0.05)
+    finally:
+        emulib.set_launch_waves(0)
 
 
 # ---- parity against the oracle (tests/test_gpu_parity.py) ------------------------------------------------

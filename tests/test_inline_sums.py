@@ -1,0 +1,135 @@
+"""Inlined sums and launch shaping: two planner / launch decisions that must not change a single bit.
+
+* A Sum vertex whose only consumer is a Sum, Normalize or Adsr vertex is evaluated inside that consumer's kernel
+  (engine.cu "inlined sums", include/termdaw_b200.h tdg_set_inline_sums): PCM with the switch on == PCM with it
+  off, byte for byte, == the oracle (byte-exact where the graph holds no band pass), and the statistics say that
+  vertices were in fact inlined.
+* The chunk kernels let a block walk up to 8 consecutive chunks as long as the grid stays large
+  (tdg_set_launch_waves): 0 (always 8) and 2^31 (always 1) give the same bytes.
+
+The bodies take the library as an argument: tests/test_emulated_kernels.py runs them on the CPU-emulated build."""
+import numpy as np
+import pytest
+
+from termdaw_b200 import synthetic as S
+from termdaw_b200.state import Project, State
+from helpers import run_project, pcm_to_int
+
+pytestmark = pytest.mark.gpu
+
+
+def _render(lib, cfg, inline, passes=("scan", "render"), reuse=True):
+    p, a, s = cfg
+    st = State(lib, s["psr"], s["bl"], assets=a)
+    try:
+        assert st.refresh(p), st.messages
+        st.ctx.set_inline_sums(inline)
+        st.ctx.set_pass_reuse(reuse)
+        if "scan" in passes:
+            st.scan_exact()
+        pcm = st.render().copy()
+        return pcm, st.ctx.last_pass_stats(), st.bd
+    finally:
+        st.ctx.set_inline_sums(True)
+        st.ctx.set_pass_reuse(True)
+        st.close()
+
+
+def sum_chain_project(seconds=1.5):
+    """Sums feeding a sum, an adsr and the output normalize; a sum used twice (not inlinable); a one-input sum;
+    a sum of a sum (only the inner one is inlined); no band pass anywhere: everything is bit-exact."""
+    rng = np.random.default_rng(77)
+    a = S._shared_assets(rng, seconds, 2)
+    p = Project()
+    p.set_length(seconds)
+    p.set_render_samplerate(48000)
+    p.set_render_bitdepth(24)
+    for s in ("s_noise", "s_tone", "s_long"):
+        p.load_sample(s, s, "")
+    p.load_resource("table", "table")
+    for i in range(2):
+        p.load_midi_floww(f"hits{i}", f"hits{i}")
+        p.load_midi_floww(f"notes{i}", f"notes{i}")
+    p.add_sampleloop("l0", 0.7, 20.0, "s_noise")
+    p.add_sampleloop("l1", 1.3, -40.0, "s_tone")
+    p.add_sample_multi("m0", 0.9, 10.0, "s_long", "hits0", -1)
+    p.add_sample_lerp("r0", 0.8, -15.0, "s_tone", "hits1", -1, 40)
+    p.add_synth("y0", 0.6, 5.0, "notes0", 0.4, 0.3, S.HIT_ADSR, 1.0, 0.6, S.NOTE_ADSR, 0.5, S.NOTE_ADSR)
+    p.add_sampsyn("w0", 0.5, 0.0, "notes1", S.STD_ADSR, "table")
+    p.add_sum("s_a", 0.8, 30.0)        # l0 + m0           -> s_c
+    p.add_sum("s_b", 1.2, -60.0)       # r0 + y0 + w0      -> env
+    p.add_sum("s_c", 0.9, 0.0)         # s_a + l1          -> out
+    p.add_sum("s_one", 1.1, 12.0)      # w0                -> out
+    p.add_sum("s_two", 0.5, -5.0)      # m0, consumed by s_c AND env: two consumers, keeps its buffer
+    p.add_adsr("env", 1.0, 0.0, 0.7, "notes0", True, True, -1, [0.01, 0.1, 0.8, 0.1, 0.2, 0.05])
+    p.add_normalize("out", 1.0, 0.0)
+    for e in (("l0", "s_a"), ("m0", "s_a"), ("r0", "s_b"), ("y0", "s_b"), ("w0", "s_b"), ("s_a", "s_c"), ("l1", "s_c"),
+              ("w0", "s_one"), ("m0", "s_two"), ("s_two", "s_c"), ("s_two", "env"), ("s_b", "env"),
+              ("s_c", "out"), ("env", "out"), ("s_one", "out")):
+        p.connect(*e)
+    p.set_output("out")
+    return p, a, {"psr": S.PSR, "bl": S.BL, "flow": "B"}
+
+
+def check_sum_chain(lib, oracle):
+    cfg = sum_chain_project()
+    on, st_on, bd = _render(lib, cfg, True)
+    off, st_off, _ = _render(lib, cfg, False)
+    assert st_off["inlined_vertices"] == 0
+    # render pass: s_b -> env and s_one -> out always; s_a -> s_c or s_c -> out (one level deep: never both)
+    assert st_on["inlined_vertices"] >= 3, st_on
+    assert st_on["inlined_bytes"] > 0
+    assert np.array_equal(on, off)
+    want = run_project(oracle, *cfg, taps=False)
+    assert np.array_equal(pcm_to_int(on, bd), pcm_to_int(want["pcm"], want["bd"]))      # no band pass: byte exact
+    # without pass reuse (every vertex evaluated in both passes) and render only (flow A: running maximum)
+    on2, st2, _ = _render(lib, cfg, True, reuse=False)
+    assert np.array_equal(on2, on) and st2["inlined_vertices"] >= 3
+    a_on, _, _ = _render(lib, cfg, True, passes=("render",))
+    a_off, _, _ = _render(lib, cfg, False, passes=("render",))
+    assert np.array_equal(a_on, a_off)
+
+
+def check_batch_projects(lib, oracle, indices=range(12), scale=0.05):
+    inlined = 0
+    for i in indices:
+        cfg = S.config_5_project(i, scale)
+        on, st_on, bd = _render(lib, cfg, True)
+        off, _, _ = _render(lib, cfg, False)
+        assert np.array_equal(on, off), i
+        inlined += st_on["inlined_vertices"]
+        want = run_project(oracle, *cfg, taps=False)
+        x, y = pcm_to_int(on, bd), pcm_to_int(want["pcm"], want["bd"])
+        assert x.shape == y.shape and np.abs(x - y).max() <= 1, i                        # band-pass cones: the IIR scan's tolerance
+    assert inlined > 0
+
+
+def check_launch_waves(lib, oracle, indices=(0, 3, 5), scale=0.2):
+    """One chunk per block == eight chunks per block, for every chunk kernel (6 s projects: 282 chunks)."""
+    try:
+        for i in indices:
+            cfg = S.config_5_project(i, scale)
+            lib.set_launch_waves(0)
+            many, _, bd = _render(lib, cfg, True)
+            lib.set_launch_waves(1 << 31)
+            one, _, _ = _render(lib, cfg, True)
+            assert np.array_equal(many, one), i
+        cfg = sum_chain_project(3.0)
+        lib.set_launch_waves(0)
+        many, _, bd = _render(lib, cfg, True)
+        want = run_project(oracle, *cfg, taps=False)
+        assert np.array_equal(pcm_to_int(many, bd), pcm_to_int(want["pcm"], want["bd"]))
+    finally:
+        lib.set_launch_waves(16)
+
+
+def test_sum_chain_inlined_is_bit_identical(gpulib, oracle):
+    check_sum_chain(gpulib, oracle)
+
+
+def test_batch_projects_inlined_equal_not_inlined(gpulib, oracle):
+    check_batch_projects(gpulib, oracle)
+
+
+def test_chunks_per_block_do_not_change_a_bit(gpulib, oracle):
+    check_launch_waves(gpulib, oracle)
