@@ -255,8 +255,17 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
 template <int MODE, bool VEC, bool EXACT, bool GRP>
 __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? (GRP ? 4 : TDG_ADSR_MINB) : GRP ? 5 : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ FxTask T;
+    __shared__ __align__(16) FxGroup s_grp[GRP ? kFxGroupsStaged : 1];
     load_task(&T, tasks + blockIdx.y);
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
+    uint32_t n_grp_s = 0;                                // group records staged in shared memory (one dependent global load less per edge)
+    if (GRP && T.n_grp <= (uint32_t)kFxGroupsStaged) {
+        n_grp_s = T.n_grp;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(blob + T.grp_off);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_grp);
+        for (uint32_t w = threadIdx.x; w < n_grp_s * (uint32_t)(sizeof(FxGroup) / 4); w += blockDim.x) dst[w] = src[w];
+        __syncthreads();
+    }
     // the adsr variant walks TDG_ADSR_CPB consecutive chunks per block (see the gather kernels: the task load, its
     // barrier and the block launch are paid once per group of chunks)
     constexpr uint32_t CPB = MODE == FX_ADSR ? TDG_ADSR_CPB : TDG_FX_CPB;      // compile-time maximum; cpb <= CPB is the launch's choice
@@ -277,9 +286,9 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? (GRP ? 4 : TDG_
             // some edges are inlined Sum vertices (FxGroup): an edge's value is either a buffer or the sum of a
             // vertex's inputs from +0.0 in its edge order with its pan and gain applied — k_fx<FX_SUM>'s operations on
             // that vertex, in registers — and the edges are added in this vertex's edge order as always
-            const FxGroup* __restrict__ G = reinterpret_cast<const FxGroup*>(blob + T.grp_off);
+            const FxGroup* G = n_grp_s ? s_grp : reinterpret_cast<const FxGroup*>(blob + T.grp_off);
             for (uint32_t q = 0; q < T.n_grp; ++q) {
-                const uint4 ga = __ldg(reinterpret_cast<const uint4*>(G + q));         // first, count, nested
+                const uint4 ga = *reinterpret_cast<const uint4*>(G + q);               // first, count, nested
                 float x[4], y[4];
                 if (!ga.z) {
                     ld4<VEC>(ins[2 * ga.x], p, nv, x);
@@ -287,6 +296,7 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? (GRP ? 4 : TDG_
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { x[j] = 0.0f; y[j] = 0.0f; }
+#pragma unroll 2
                     for (uint32_t b = 0; b < ga.y; ++b) {
                         float u[4], w[4];
                         ld4<VEC>(ins[2 * (ga.x + b)], p, nv, u);
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? (GRP ? 4 : TDG_
 #pragma unroll
                         for (int j = 0; j < 4; ++j) { x[j] += u[j]; y[j] += w[j]; }
                     }
-                    const float4 pf = __ldg(reinterpret_cast<const float4*>(G + q) + 1);
+                    const float4 pf = *(reinterpret_cast<const float4*>(G + q) + 1);
                     PanGain pg; pg.l_amp = pf.x; pg.r_amp = pf.y; pg.gain = pf.z; pg.flags = __float_as_uint(pf.w);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) apply_pg(x[j], y[j], pg);

@@ -28,6 +28,7 @@
 #define __noinline__            /* empty: libstdc++ spells __attribute__((__noinline__)), which then reads __attribute__(()) */
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 #define __constant__
 #ifndef __restrict__
 #define __restrict__ __restrict
