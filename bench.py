@@ -314,6 +314,8 @@ class BatchRunner:
                 "h2d": ev_bytes + s1["h2d_bytes"] + s2["h2d_bytes"], "d2h": s2["d2h_bytes"], "kstats": ks,
                 "algo": s1["algorithmic_bytes"] + s2["algorithmic_bytes"], "plan_ms": s1["plan_ms"] + s2["plan_ms"],
                 "reused_v": s2.get("reused_vertices", 0), "reused_b": s2.get("reused_bytes", 0),
+                "inlined_v": s1.get("inlined_vertices", 0) + s2.get("inlined_vertices", 0),
+                "inlined_b": s1.get("inlined_bytes", 0) + s2.get("inlined_bytes", 0),
                 "voice_frames": s1.get("voice_frames", 0) + s2.get("voice_frames", 0), "collectives": 0}
 
     def close(self):
@@ -368,6 +370,8 @@ class TimeShardRunner:
                 "h2d": ev_bytes + s1["h2d_bytes"] + s2["h2d_bytes"], "d2h": s2["d2h_bytes"], "kstats": ks,
                 "algo": s1["algorithmic_bytes"] + s2["algorithmic_bytes"], "plan_ms": s1["plan_ms"] + s2["plan_ms"],
                 "reused_v": s2.get("reused_vertices", 0), "reused_b": s2.get("reused_bytes", 0),
+                "inlined_v": s1.get("inlined_vertices", 0) + s2.get("inlined_vertices", 0),
+                "inlined_b": s1.get("inlined_bytes", 0) + s2.get("inlined_bytes", 0),
                 "voice_frames": s1.get("voice_frames", 0) + s2.get("voice_frames", 0), "collectives": c.collectives() - col0}
 
     def close(self):
@@ -501,11 +505,12 @@ def main():
     sampler.start()
     t0 = time.perf_counter()
     dev_ms, launches, kstats, algo, plan_ms, collectives = 0.0, 0, {}, 0, 0.0, 0
-    reused_v = reused_b = 0
+    reused_v = reused_b = inlined_v = inlined_b = 0
     for _ in range(args.steps):
         r = R.step(False)
         dev_ms += r["device_ms"]; launches += r["launches"]; algo += r["algo"]; plan_ms += r["plan_ms"]
         reused_v += r.get("reused_v", 0); reused_b += r.get("reused_b", 0)
+        inlined_v += r.get("inlined_v", 0); inlined_b += r.get("inlined_b", 0)
         collectives += r["collectives"]
         _merge_kstats(kstats, r["kstats"])
     barrier()
@@ -616,9 +621,12 @@ def main():
                 # launched kernels move; SURVEY 8(d)'s both-passes-evaluate-everything figure is that plus the skipped
                 "pass_reuse": {"vertices_read_from_scan_per_step": reused_v // args.steps,
                                "algorithmic_gb_not_moved_per_step": reused_b / args.steps / 1e9,
-                               "survey_8d_algorithmic_gb_per_step": (algo + reused_b) / args.steps / 1e9,
+                               "survey_8d_algorithmic_gb_per_step": (algo + reused_b + inlined_b) / args.steps / 1e9,
                                "ms_per_step_with_reuse_off": dev_ms_off_max / off_steps,
                                "value_with_reuse_off": total_frames * off_steps / (dev_ms_off_max / 1e3)},
+                # Sum vertices evaluated inside their consumer's kernel (tdg_set_inline_sums): no buffer, no
+                # launch; the write + read of the intermediate buffer is not in algorithmic_gb_per_step either
+                "inlined_sums": {"vertices_per_step": inlined_v // args.steps, "gb_not_moved_per_step": inlined_b / args.steps / 1e9},
             },
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "realtime_factor": e2e_value / PSR,
