@@ -241,6 +241,12 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
 #ifndef TDG_ADSR_MINB
 #define TDG_ADSR_MINB 5      // measured: 4 -> 9.0 ms, 5 -> 8.3 ms, 6 -> 8.5 ms per bench step
 #endif
+#ifndef TDG_FXG_CPB
+#define TDG_FXG_CPB 4        // chunks per block of the grouped sum / norm_peak instantiations (longer chain at the head of a block: group records, pointer list)
+#endif
+#ifndef TDG_FXG_MINB
+#define TDG_FXG_MINB 5       // resident blocks per SM of the grouped sum / norm_peak instantiations
+#endif
 #ifndef TDG_FX_CPB
 #define TDG_FX_CPB 1         // chunks per block of k_fx<sum> / k_fx<norm_peak> (both already run at the HBM roof)
 #endif
@@ -253,29 +259,38 @@ __device__ __forceinline__ float adsr_frame_vel(const FxTask& T, const AdsrSeg& 
 // GRP: the task list holds vertices some of whose inputs are inlined Sum vertices (FxGroup records; engine.cu "inlined
 // sums").  A separate instantiation, so that the plain kernels keep their register budget.
 template <int MODE, bool VEC, bool EXACT, bool GRP>
-__global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? (GRP ? 4 : TDG_ADSR_MINB) : GRP ? 5 : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
+__global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? (GRP ? 4 : TDG_ADSR_MINB) : GRP ? TDG_FXG_MINB : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ FxTask T;
     __shared__ __align__(16) FxGroup s_grp[GRP ? kFxGroupsStaged : 1];
     load_task(&T, tasks + blockIdx.y);
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
+    __shared__ const float* s_ins[GRP ? 2 * kFxPairsStaged : 1];
     uint32_t n_grp_s = 0;                                // group records staged in shared memory (one dependent global load less per edge)
-    if (GRP && T.n_grp <= (uint32_t)kFxGroupsStaged) {
-        n_grp_s = T.n_grp;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(blob + T.grp_off);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(s_grp);
-        for (uint32_t w = threadIdx.x; w < n_grp_s * (uint32_t)(sizeof(FxGroup) / 4); w += blockDim.x) dst[w] = src[w];
+    bool ins_s = false;                                  // ... and the expanded pointer list, which usually outgrows the task's inline copy
+    if (GRP) {
+        if (T.n_grp <= (uint32_t)kFxGroupsStaged) {
+            n_grp_s = T.n_grp;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(blob + T.grp_off);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(s_grp);
+            for (uint32_t w = threadIdx.x; w < n_grp_s * (uint32_t)(sizeof(FxGroup) / 4); w += blockDim.x) dst[w] = src[w];
+        }
+        if (T.n_in > (uint32_t)kInlineInputs && T.n_in <= (uint32_t)kFxPairsStaged) {
+            ins_s = true;
+            const float* const* src = reinterpret_cast<const float* const*>(blob + T.in_off);
+            for (uint32_t w = threadIdx.x; w < 2 * T.n_in; w += blockDim.x) s_ins[w] = src[w];
+        }
         __syncthreads();
     }
     // the adsr variant walks TDG_ADSR_CPB consecutive chunks per block (see the gather kernels: the task load, its
     // barrier and the block launch are paid once per group of chunks)
-    constexpr uint32_t CPB = MODE == FX_ADSR ? TDG_ADSR_CPB : TDG_FX_CPB;      // compile-time maximum; cpb <= CPB is the launch's choice
+    constexpr uint32_t CPB = MODE == FX_ADSR ? TDG_ADSR_CPB : GRP ? TDG_FXG_CPB : TDG_FX_CPB;      // compile-time maximum; cpb <= CPB is the launch's choice
     const uint32_t kc0 = blockIdx.x * (CPB == 1 ? 1u : cpb);
     if (kc0 >= T.h.n_chunks) return;
     const uint32_t kc1 = CPB == 1 ? kc0 + 1 : min(kc0 + cpb, T.h.n_chunks);
     const uint32_t bl = T.h.bl;
     uint64_t p0 = 0;
     const bool staged = T.n_in <= (uint32_t)kInlineInputs;     // input pointers arrived with the task (shared memory)
-    const float* const* ins = staged ? T.ins : reinterpret_cast<const float* const*>(blob + T.in_off);
+    const float* const* ins = staged ? T.ins : ins_s ? s_ins : reinterpret_cast<const float* const*>(blob + T.in_off);
     // sum_inputs for the four frames at chunk offset i (edge order: the f32 sum is order dependent)
     auto load_sum = [&](uint32_t i, float (&l)[4], float (&r)[4]) {
         const int nv = min(4u, bl - i);
@@ -1643,7 +1658,7 @@ static inline uint32_t pick_cpb(uint32_t cpb_max, uint32_t max_chunks, uint32_t 
 
 template <bool GRP>
 static void launch_fx_t(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, const uint8_t* blob, cudaStream_t s) {
-    const uint32_t c1 = pick_cpb(TDG_FX_CPB, max_chunks, n, 6), ca = pick_cpb(TDG_ADSR_CPB, max_chunks, n, TDG_ADSR_MINB);
+    const uint32_t c1 = pick_cpb(GRP ? TDG_FXG_CPB : TDG_FX_CPB, max_chunks, n, 6), ca = pick_cpb(TDG_ADSR_CPB, max_chunks, n, TDG_ADSR_MINB);
     const dim3 g = grid2((max_chunks + c1 - 1) / c1, n);
     if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); else k_fx<FX_SUM, false, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); }
     else if (mode == FX_ADSR) {

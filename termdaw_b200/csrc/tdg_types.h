@@ -119,6 +119,7 @@ enum FxMode : uint32_t { FX_SUM = 0, FX_ADSR = 1, FX_NORM_PEAK = 2 };
 // pointer pairs starting at pair `first`; nested = 1: they are the inputs of a Sum vertex whose output is that edge's
 // value — summed in order from +0.0, then that vertex's pan and gain (the operations of k_fx<FX_SUM>, in registers).
 struct FxGroup { uint32_t first, count, nested, pad; PanGain pg; };
+static const int kFxPairsStaged = 32;       // ... and that many input pointer pairs
 static const int kFxGroupsStaged = 16;      // group records of a task staged in shared memory by the grouped kernel (more: read from the plan blob)
 
 struct FxTask {             // sum_inputs (+ adsr_gen | + per-chunk peak) + pan + gain, one kernel
