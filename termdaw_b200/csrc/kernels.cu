@@ -719,7 +719,9 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __r
 //   * the release start value apply_ads(conf, rel_t) of adsr.rs:89-92 is constant per segment and is
 //     evaluated once per (segment, oscillator) while the segments are staged in shared memory;
 //   * divisions by those constants use the exact-quotient FMA form (k_div) instead of MUFU.RCP +
-//     Newton + slow path; sin is a Cody-Waite + minimax evaluation on the FMA pipe (d_sin).
+//     Newton + slow path; sin is glibc's sinf restated (m_sinf_glibc, bit-exact) or, on request, a Cody-Waite +
+//     minimax evaluation on the FMA pipe (d_sin);
+//   * a block walks up to TDG_VOICE_CPB consecutive chunks (task load, barrier and block launch once per group).
 // Accumulators stay in registers across segment batches; one float4 store per channel at the end.
 #ifndef TDG_SYNTH_F
 #define TDG_SYNTH_F 4           // frames per thread of the synth kernel (tuning knob, see profiles/)
@@ -910,11 +912,13 @@ __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_M
 }
 
 // ------------------------------------------------------------------------------------ K7: band pass scan
-// y <- y + g*(x - y) is the affine map y -> (1-g)*y + g*x.  A thread owns 8 consecutive frames: it
-// folds them from a zero state (B) with decay A = (1-g)^8, a warp-shuffle scan composes the maps
-// across the block, tile aggregates are scanned across blocks, and the final pass re-runs the
-// reference's exact operation sequence from the carried-in state.  Only the carried-in state is
-// reassociated (tolerance in DESIGN.md); inside a run the arithmetic is the reference's.
+// y <- y + g*(x - y) is the affine map y -> (1-g)*y + g*x.  A thread owns a run of consecutive frames (8 in the
+// three-launch scan, 32 in k_bp_fused): it folds them from a zero state (B) with decay A = (1-g)^n, a warp-shuffle
+// scan composes the maps across the block, block aggregates are scanned across blocks (k_bp_carry, or the look-back
+// of k_bp_fused), and the final step re-runs the reference's exact operation sequence from the carried-in state.
+// Only the carried-in state is reassociated (tolerance in DESIGN.md); inside a run the arithmetic is the reference's.
+// k_bp_fused (below) is what a pass uses; k_bp_aggregate / k_bp_carry / k_bp_apply remain for time-sharded passes,
+// where the exchange step sits between aggregate and apply, and behind TDG_BP_FUSED=0.
 struct Aff { float al, ah, b0, b1, b2, b3; };       // (lprevl, lprevr) decay al; (hprevl, hprevr) decay ah
 __device__ __forceinline__ Aff aff_id() { return Aff{1.0f, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f}; }
 __device__ __forceinline__ Aff aff_then(const Aff& f, const Aff& g) {   // apply f first, then g
