@@ -129,6 +129,8 @@ def rewind(states, reupload_flowws: bool, _cache={}):
             "counts": (C.c_uint64 * max(m, 1))(*counts), "per": (C.c_uint32 * len(states))(*per), "keep": keep, "nbytes": nbytes}
     lib = states[0][0].ctx.lib
     k = packed
+    if reupload_flowws == "tables":          # the caller hands them to tdg_refresh_normalize_render_many itself
+        return k
     if reupload_flowws:
         rc = lib.rewind_many(k["hs"], len(states), k["t"], k["n"], k["v"], k["counts"], k["per"])
     else:
@@ -292,13 +294,23 @@ class BatchRunner:
         from termdaw_b200 import normalize_render_many, normalize_scan_many, render_many
         c0 = self.ctxs[0]
         t_rw = time.perf_counter()
-        ev_bytes = rewind(self.states, reupload_flowws=e2e)
+        fused_refresh = e2e and os.environ.get("TDG_E2E_FUSED_REFRESH", "1") != "0"
+        if fused_refresh:
+            k = rewind(self.states, reupload_flowws="tables")
+            ev_bytes = k["nbytes"]
+        else:
+            ev_bytes = rewind(self.states, reupload_flowws=e2e)
         self.rewind_ms = (time.perf_counter() - t_rw) * 1e3
         if e2e:
-            # the public batched call: scan + render of every project, groups of 32 projects (the library's default)
-            # pipelined over two streams (planning / kernels / PCM D2H of different groups overlap)
+            # the public batched call: refresh + scan + render of every project, groups of 32 projects (the library's
+            # default) pipelined over two streams (refresh + planning / kernels / PCM D2H of different groups overlap)
             c0.set_pipeline_group(int(os.environ.get("TDG_E2E_GROUP", "32")))
-            normalize_render_many(self.lib, self.ctxs, self.cs, self.rsr, self.bds, want_pcm=True, outs=self.outs)
+            if fused_refresh:
+                from termdaw_b200 import refresh_normalize_render_many
+                refresh_normalize_render_many(self.lib, self.ctxs, (k["t"], k["n"], k["v"], k["counts"], k["per"]), self.cs, self.rsr,
+                                              self.bds, want_pcm=True, outs=self.outs)
+            else:
+                normalize_render_many(self.lib, self.ctxs, self.cs, self.rsr, self.bds, want_pcm=True, outs=self.outs)
             s2, k2 = c0.last_pass_stats(), c0.last_pass_kernel_stats()
             s1, k1 = {k: 0 for k in s2}, {}
         else:
@@ -631,7 +643,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "realtime_factor": e2e_value / PSR,
                     "ms_per_step": e2e_max / args.steps * 1e3, "ms_each_step_rank0": [round(x[0], 2) if isinstance(x, tuple) else round(x, 2) for x in e2e_steps],
-                    "host_refresh_ms_each_step": [round(x[1], 2) for x in e2e_steps if isinstance(x, tuple)]},
+                    "host_refresh_ms_each_step": [round(x[1], 2) for x in e2e_steps if isinstance(x, tuple)],
+                    "refresh": ("inside the pipelined call (tdg_refresh_normalize_render_many): a group's refresh runs while the GPU renders the groups in front"
+                                if os.environ.get("TDG_E2E_FUSED_REFRESH", "1") != "0" else "tdg_rewind_many before the call")},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",

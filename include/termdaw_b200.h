@@ -143,6 +143,13 @@ float tdg_get_normalize_value(tdg_ctx* ctx, int vertex);            /* extension
  * tdg_reset_vertex_state + tdg_set_time(0) + tdg_floww_set_time(0) + tdg_reset_normalize. */
 int tdg_rewind_many(tdg_ctx** ctxs, int n, const float* const* t_sec, const float* const* note,
                     const float* const* vel, const uint64_t* counts, const uint32_t* flowws_per_ctx);
+/* tdg_rewind_many + tdg_normalize_render_many in one pipelined call: the refresh of a group of projects runs on the host
+ * while the GPU renders the groups in front of it.  Same results as the two calls in sequence (the projects of a batch
+ * are independent).  t == NULL: no floww reload, as in tdg_rewind_many. */
+int tdg_refresh_normalize_render_many(tdg_ctx** ctxs, int n, const float* const* t, const float* const* note,
+                                      const float* const* vel, const uint64_t* counts, const uint32_t* flowws_per_ctx,
+                                      const uint64_t* chunks, const uint32_t* render_sr, const uint32_t* bitdepth,
+                                      uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written);
 
 /* ---- transport ----------------------------------------------------------------------------------*/
 int tdg_set_time(tdg_ctx* ctx, uint64_t frame);                      /* Graph::set_time, graph.rs:123 */

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import os
 
-from ._capi import (Context, Library, TermdawError, comm_unique_id, normalize_render_many, normalize_scan_many, render_many,  # noqa: F401
+from ._capi import (Context, Library, TermdawError, comm_unique_id, normalize_render_many, normalize_scan_many, refresh_normalize_render_many, render_many,  # noqa: F401
                     render_segments_local, scan_segments_local, segment_output_frames)
 from .state import Assets, DecodedWav, Project, State, set_length_chunks  # noqa: F401
 

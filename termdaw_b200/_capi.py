@@ -138,6 +138,8 @@ class Library:
         "set_oscillator_mode": (C.c_int, [C.c_void_p, C.c_int]),
         "rewind_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(c_f32p), C.POINTER(c_f32p), C.POINTER(c_f32p),
                                   c_u64p, c_u32p]),
+        "refresh_normalize_render_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(c_f32p), C.POINTER(c_f32p), C.POINTER(c_f32p),
+                                                    c_u64p, c_u32p, c_u64p, c_u32p, c_u32p, C.POINTER(c_u8p), c_u64p, c_u64p]),
         "reset_vertex_state": (C.c_int, [C.c_void_p]),
         "set_pipeline_group": (C.c_int, [C.c_void_p, C.c_uint32]),
         "set_launch_waves": (C.c_int, [C.c_uint32]),
@@ -431,9 +433,17 @@ def normalize_render_many(lib: Library, ctxs, chunks, render_sr, bitdepth, want_
     return render_many(lib, ctxs, chunks, render_sr, bitdepth, want_pcm, outs, fn="normalize_render_many")
 
 
+def refresh_normalize_render_many(lib: Library, ctxs, flowws, chunks, render_sr, bitdepth, want_pcm: bool = True, outs=None):
+    """tdg_refresh_normalize_render_many: 'stop' + 'refresh' + normalize + render of a batch of unchanged projects in one
+    pipelined call.  `flowws` = (t, note, vel, counts, per_ctx): the flattened ctypes tables tdg_rewind_many takes
+    (arrays of float pointers, event counts, flowws per context), or None for no floww reload."""
+    pre = tuple(flowws) if flowws is not None else (None, None, None, None, None)
+    return render_many(lib, ctxs, chunks, render_sr, bitdepth, want_pcm, outs, fn="refresh_normalize_render_many", pre_args=pre)
+
+
 def render_many(lib: Library, ctxs: Sequence[Context], chunks: Sequence[int], render_sr: Sequence[int],
                 bitdepth: Sequence[int], want_pcm: bool = True, outs: Optional[Sequence[np.ndarray]] = None,
-                fn: str = "render_many"):
+                fn: str = "render_many", pre_args: tuple = ()):
     """tdg_render_many: one merged device schedule for `ctxs` (independent projects)."""
     call = getattr(lib, fn)
     n = len(ctxs)
@@ -449,9 +459,9 @@ def render_many(lib: Library, ctxs: Sequence[Context], chunks: Sequence[int], re
             outs = [np.empty(c, np.uint8) for c in caps]
         ptrs = (c_u8p * n)(*[_p(o, c_u8p) for o in outs])
         cp = (C.c_uint64 * n)(*caps)
-        rc = call(hs, n, ch, rs, bd, ptrs, cp, fw)
+        rc = call(hs, n, *pre_args, ch, rs, bd, ptrs, cp, fw)
     else:
-        rc = call(hs, n, ch, rs, bd, None, None, fw)
+        rc = call(hs, n, *pre_args, ch, rs, bd, None, None, fw)
     if rc < 0:
         msgs = [(lib.last_error(c.h) or b"").decode() for c in ctxs]
         raise TermdawError(rc, next((m for m in msgs if m), ""))

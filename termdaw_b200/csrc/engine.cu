@@ -906,6 +906,7 @@ struct PassJob {
     uint64_t sync_off = 0, sync_bytes = 0;    // tickets + flags of the fused band-pass kernels of the job (work arena, zeroed at submit)
     uint64_t quant_max = 0, quant_bytes = 0, resamp_max = 0, resamp_bytes = 0, quant_off = 0, resamp_off = 0;
     uint64_t algo_bytes_total = 0, reused_v = 0, reused_b = 0, inlined_v = 0, inlined_b = 0;
+    std::function<int()> pre;           // host work that must precede this job's planning (the group's refresh, tdg_refresh_normalize_render_many)
     double t_start = 0, t_planned = 0, t_h2d_issued = 0, t_d2h0 = 0, t_submitted = 0;
     float dev_t0 = 0, dev_t1 = 0, dev_tdone = 0;      // device timeline relative to the batch start (trace only)
     uint64_t launches = 0, collectives = 0, d2h_bytes = 0, h2d_bytes = 0;
@@ -1985,6 +1986,7 @@ static int run_jobs_pipelined(Engine* g, std::vector<PassJob>& jobs, PassStats* 
         PassJob& J = jobs[k];
         const int li = (int)(J.lane - g->lanes);
         if (PassJob* prev = last_in_slot[li][J.slot]) { rc = pass_wait(*prev); if (rc != TDG_OK) break; }
+        if (J.pre) { rc = J.pre(); if (rc != TDG_OK) break; }
         J.in_batch = true;
         rc = pass_plan(J);
         if (rc != TDG_OK) break;
@@ -2061,7 +2063,8 @@ static int run_pass_pipelined(std::vector<PassReq>& reqs) {
 // scan + render of every project in one pipelined call (the manual workflow's "normalize" then
 // "render", ui_workflow.rs:120-135): group g's two passes run back to back on one lane while the other
 // lane works on group g+1, so the PCM of group g-1 crosses PCIe under the kernels of both passes.
-static int run_scan_render_pipelined(std::vector<PassReq>& scans, std::vector<PassReq>& renders) {
+static int run_scan_render_pipelined(std::vector<PassReq>& scans, std::vector<PassReq>& renders,
+                                     const std::function<int(size_t, size_t)>& refresh_range = nullptr) {
     Engine* g = renders[0].c->eng;
     for (auto& r : renders) drain_plays(r.c);
     for (auto& r : renders) if (r.c->eng != g) return r.c->fail(TDG_ERR_INVALID, "all contexts of a batch must be on one device");
@@ -2100,6 +2103,14 @@ static int run_scan_render_pipelined(std::vector<PassReq>& scans, std::vector<Pa
         if (scans[i].c->output >= 0) jobs[2 * gi].reqs.push_back(std::move(scans[i]));     // graph.rs:225: no output, no scan
         jobs[2 * gi + 1].reqs.push_back(std::move(renders[i]));
     }
+    // the refresh of a group's projects (floww reload, vertex state, transport, normalize maxima) runs on the host right
+    // before the group's first pass is planned, i.e. while the GPU works on the groups in front of it
+    if (refresh_range)
+        for (size_t gi = 0; gi < n_groups; ++gi) {
+            const size_t i0 = start[gi], i1 = start[gi + 1];
+            PassJob& first_job = jobs[2 * gi].reqs.empty() ? jobs[2 * gi + 1] : jobs[2 * gi];
+            first_job.pre = [&refresh_range, i0, i1]() { return refresh_range(i0, i1); };
+        }
     std::vector<PassJob> live;
     live.reserve(jobs.size());
     int next_slot[kLanes] = {};
@@ -2575,23 +2586,30 @@ int tdg_set_time(tdg_ctx* h, uint64_t frame) { graph_set_time(C_, frame); return
 // exactly tdg_floww_reset + tdg_floww_add... + tdg_reset_vertex_state + tdg_set_time(0) +
 // tdg_floww_set_time(0) + tdg_reset_normalize on each, without 9 calls per project across the FFI.
 // Flowws are flattened: context i owns entries [sum(flowws_per_ctx[0..i)), +flowws_per_ctx[i]) of t/note/vel/counts.
+// 'stop' + 'refresh' of one unchanged project (ui_workflow.rs:153-160, state.rs:240-250,328-467); `at` = index of its first
+// floww in the flattened arrays
+static int rewind_one(tdg_ctx* h, const float* const* t, const float* const* note, const float* const* vel,
+                      const uint64_t* counts, uint32_t n_flowws, size_t at) {
+    if (t) {
+        if (int e = tdg_floww_reset(h)) return e;
+        for (uint32_t k = 0; k < n_flowws; ++k, ++at) {
+            const int id = tdg_floww_add(h, t[at], note[at], vel[at], counts[at]);
+            if (id < 0) return id;
+        }
+    }
+    if (int e = tdg_reset_vertex_state(h)) return e;
+    if (int e = tdg_set_time(h, 0)) return e;
+    if (int e = tdg_floww_set_time(h, 0)) return e;
+    return tdg_reset_normalize(h);
+}
 int tdg_rewind_many(tdg_ctx** hs, int n, const float* const* t, const float* const* note, const float* const* vel,
                     const uint64_t* counts, const uint32_t* flowws_per_ctx) {
     if (n < 0 || (n > 0 && !hs)) return TDG_ERR_INVALID;
     size_t at = 0;
     for (int i = 0; i < n; ++i) {
-        tdg_ctx* h = hs[i];
-        if (t && flowws_per_ctx) {
-            if (int e = tdg_floww_reset(h)) return e;
-            for (uint32_t k = 0; k < flowws_per_ctx[i]; ++k, ++at) {
-                const int id = tdg_floww_add(h, t[at], note[at], vel[at], counts[at]);
-                if (id < 0) return id;
-            }
-        }
-        if (int e = tdg_reset_vertex_state(h)) return e;
-        if (int e = tdg_set_time(h, 0)) return e;
-        if (int e = tdg_floww_set_time(h, 0)) return e;
-        if (int e = tdg_reset_normalize(h)) return e;
+        const bool reload = t && flowws_per_ctx;
+        if (int e = rewind_one(hs[i], reload ? t : nullptr, note, vel, counts, reload ? flowws_per_ctx[i] : 0, at)) return e;
+        if (reload) at += flowws_per_ctx[i];
     }
     return TDG_OK;
 }
@@ -2668,6 +2686,37 @@ int tdg_normalize_render_many(tdg_ctx** hs, int n, const uint64_t* chunks, const
         r.frames_written = frames_written ? frames_written + i : nullptr;
     }
     return run_scan_render_pipelined(scans, renders);
+}
+// refresh + normalize + render of a batch of unchanged projects in ONE pipelined call: tdg_rewind_many's work is done
+// group by group on the host while the GPU renders the groups in front (same results as the two calls in sequence)
+int tdg_refresh_normalize_render_many(tdg_ctx** hs, int n, const float* const* t, const float* const* note, const float* const* vel,
+                                      const uint64_t* counts, const uint32_t* flowws_per_ctx,
+                                      const uint64_t* chunks, const uint32_t* render_sr, const uint32_t* bitdepth,
+                                      uint8_t** out_pcm, const uint64_t* cap_bytes, uint64_t* frames_written) {
+    if (n <= 0) return TDG_OK;
+    if (!hs) return TDG_ERR_INVALID;
+    const bool reload = t && flowws_per_ctx;
+    std::vector<size_t> at(n + 1, 0);
+    if (reload) for (int i = 0; i < n; ++i) at[i + 1] = at[i] + flowws_per_ctx[i];
+    std::vector<PassReq> scans(n), renders(n);
+    for (int i = 0; i < n; ++i) {
+        Ctx* c = &hs[i]->c;
+        if (int e = valid_bd(c, bitdepth[i])) return e;
+        if (frames_written) frames_written[i] = 0;
+        PassReq& a = scans[i];
+        a.c = c; a.is_scan = true; a.total = chunks[i]; a.emit0 = 0; a.emit_n = chunks[i]; a.keep0 = 0;
+        PassReq& r = renders[i];
+        r.c = c; r.is_scan = false; r.total = chunks[i]; r.emit0 = 0; r.emit_n = chunks[i]; r.keep0 = 0;
+        r.render_sr = render_sr[i]; r.bd = bitdepth[i];
+        r.out = out_pcm ? out_pcm[i] : nullptr; r.cap = cap_bytes ? cap_bytes[i] : 0;
+        r.frames_written = frames_written ? frames_written + i : nullptr;
+    }
+    const std::function<int(size_t, size_t)> refresh = [&](size_t i0, size_t i1) -> int {
+        for (size_t i = i0; i < i1; ++i)
+            if (int e = rewind_one(hs[i], reload ? t : nullptr, note, vel, counts, reload ? flowws_per_ctx[i] : 0, at[i])) return e;
+        return TDG_OK;
+    };
+    return run_scan_render_pipelined(scans, renders, refresh);
 }
 int tdg_render(tdg_ctx* h, uint64_t chunks, uint32_t render_sr, uint32_t bitdepth, uint8_t* out_pcm, uint64_t cap_bytes,
                uint64_t* frames_written) {

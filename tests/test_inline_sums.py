@@ -123,6 +123,47 @@ def check_launch_waves(lib, oracle, indices=(0, 3, 5), scale=0.2):
         lib.set_launch_waves(16)
 
 
+def check_fused_refresh(lib, oracle, n=7, scale=0.04):
+    """tdg_refresh_normalize_render_many (the refresh of a group done while the GPU renders the groups in front) ==
+    tdg_rewind_many followed by tdg_normalize_render_many, bit for bit, repeatedly, with and without the floww reload."""
+    import bench
+    from termdaw_b200 import normalize_render_many, refresh_normalize_render_many
+    cfgs = [S.config_5_project(i, scale) for i in range(n)]
+    states = []
+    for p, a, s in cfgs:
+        st = State(lib, s["psr"], s["bl"], assets=a)
+        assert st.refresh(p), st.messages
+        states.append((st, p, a))
+    try:
+        ctxs = [st.ctx for st, _, _ in states]
+        args = ([st.cs for st, _, _ in states], [48000] * n, [16] * n)
+        ctxs[0].set_pipeline_group(3)                          # groups 3 + 3 + 1 (the taper may regroup: any grouping must do)
+        bench.rewind(states, reupload_flowws=True)
+        want = [x.copy() for x in normalize_render_many(lib, ctxs, *args)]
+        k = bench.rewind(states, reupload_flowws="tables")
+        tables = (k["t"], k["n"], k["v"], k["counts"], k["per"])
+        for fl in (tables, None, tables):
+            got = refresh_normalize_render_many(lib, ctxs, fl, *args)
+            for a, b in zip(want, got):
+                assert np.array_equal(a, b)
+        ctxs[0].set_pipeline_group(0)                          # one group: the refresh simply precedes the passes
+        got = refresh_normalize_render_many(lib, ctxs, tables, *args)
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+        for (p, a, s), pcm in zip(cfgs, want):
+            ref = run_project(oracle, p, a, s, taps=False)
+            x, y = pcm_to_int(pcm, 16), pcm_to_int(ref["pcm"], 16)
+            assert x.shape == y.shape and int(np.abs(x - y).max()) <= 1
+    finally:
+        states[0][0].ctx.set_pipeline_group(32)
+        for st, _, _ in states:
+            st.close()
+
+
+def test_fused_refresh_equals_rewind_then_render(gpulib, oracle):
+    check_fused_refresh(gpulib, oracle)
+
+
 def test_sum_chain_inlined_is_bit_identical(gpulib, oracle):
     check_sum_chain(gpulib, oracle)
 
