@@ -17,6 +17,9 @@
 namespace tdg {
 
 #define TDG_THREADS 256
+#ifndef TDG_PDL_DEFAULT
+#define TDG_PDL_DEFAULT 0
+#endif
 
 // ------------------------------------------------------------------------------------ helpers
 template <typename T>
@@ -26,6 +29,29 @@ __device__ __forceinline__ void load_task(T* dst, const T* src) {
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
     for (int i = threadIdx.x; i < (int)(sizeof(T) / 4); i += blockDim.x) d[i] = s[i];
     __syncthreads();
+}
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may become
+// resident while the kernel in front of it in the stream is still draining.  Every pass kernel lets its dependents
+// launch at once (they only fill SM slots the running grid no longer needs) and waits for the grid in front of it —
+// complete, memory flushed — right after it has fetched its task and BEFORE it touches anything a kernel produces.
+// Without the attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+// task fetch of a pass kernel: the task arrays are uploaded before the pass's first kernel, no kernel writes them
+template <typename T>
+__device__ __forceinline__ void load_task_pdl(T* dst, const T* src) {
+    pdl_launch_dependents();
+    load_task(dst, src);
+    pdl_wait();
 }
 
 __device__ __forceinline__ void apply_pg(float& l, float& r, const PanGain& pg) {
@@ -131,7 +157,9 @@ __device__ __forceinline__ uint32_t voice_segs_in_chunk(const VoiceRec& R, uint3
 // The per-chunk index ranges of every event-driven vertex of a pass (voices, adsr, sample_multi, sample_lerp), one
 // thread per (task, chunk): the host uploads O(events) records, the O(chunks) tables are made here.
 __global__ void __launch_bounds__(256) k_chunk_ranges(const RangeTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    pdl_launch_dependents();
     const RangeTask T = tasks[blockIdx.y];
+    pdl_wait();
     const uint32_t kk = blockIdx.x * blockDim.x + threadIdx.x;
     if (kk >= T.n_chunks) return;
     const uint32_t n = T.n_recs;
@@ -170,7 +198,9 @@ __global__ void __launch_bounds__(256) k_chunk_ranges(const RangeTask* __restric
 
 // counts -> offsets: seg_ptr[0] = 0, seg_ptr[k + 1] = segments of chunks [0, k].  One block per voice task.
 __global__ void __launch_bounds__(1024) k_seg_scan(const RangeTask* __restrict__ tasks) {
+    pdl_launch_dependents();
     const RangeTask T = tasks[blockIdx.x];
+    pdl_wait();
     if (T.kind != RK_VOICE && T.kind != RK_ADSR) return;
     __shared__ uint32_t part[1024];
     const uint32_t n = T.n_chunks, tid = threadIdx.x, nt = blockDim.x;
@@ -191,7 +221,9 @@ __global__ void __launch_bounds__(1024) k_seg_scan(const RangeTask* __restrict__
 }
 // the segments themselves: one thread per chunk walks the chunk's candidate records in push order
 __global__ void __launch_bounds__(256) k_seg_fill(const RangeTask* __restrict__ tasks, const uint8_t* __restrict__ blob) {
+    pdl_launch_dependents();
     const RangeTask T = tasks[blockIdx.y];
+    pdl_wait();
     if (T.kind != RK_VOICE && T.kind != RK_ADSR) return;
     const uint32_t kk = blockIdx.x * blockDim.x + threadIdx.x;
     if (kk >= T.n_chunks) return;
@@ -262,7 +294,7 @@ template <int MODE, bool VEC, bool EXACT, bool GRP>
 __global__ void __launch_bounds__(TDG_THREADS, MODE == FX_ADSR ? (GRP ? 4 : TDG_ADSR_MINB) : GRP ? TDG_FXG_MINB : 6) k_fx(const FxTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ FxTask T;
     __shared__ __align__(16) FxGroup s_grp[GRP ? kFxGroupsStaged : 1];
-    load_task(&T, tasks + blockIdx.y);
+    load_task_pdl(&T, tasks + blockIdx.y);
     if (T.mode != (uint32_t)MODE) return;                // one launch per mode over the same task list
     __shared__ const float* s_ins[GRP ? 2 * kFxPairsStaged : 1];
     uint32_t n_grp_s = 0;                                // group records staged in shared memory (one dependent global load less per edge)
@@ -468,7 +500,9 @@ __global__ void __launch_bounds__(256) k_norm_total(const NormPrefixTask* __rest
     }
 }
 __global__ void __launch_bounds__(1024) k_norm_prefix(const NormPrefixTask* __restrict__ tasks) {
+    pdl_launch_dependents();
     const NormPrefixTask T = tasks[blockIdx.x];
+    pdl_wait();
     __shared__ float part[1024];
     const uint32_t n = T.n_chunks, tid = threadIdx.x, nt = blockDim.x;
     const uint32_t per = (n + nt - 1) / nt;
@@ -510,7 +544,7 @@ __global__ void __launch_bounds__(1024) k_norm_prefix(const NormPrefixTask* __re
 template <bool VEC>
 __global__ void __launch_bounds__(TDG_THREADS) k_norm_scale(const NormScaleTask* __restrict__ tasks) {
     __shared__ NormScaleTask T;
-    load_task(&T, tasks + blockIdx.y);
+    load_task_pdl(&T, tasks + blockIdx.y);
     const uint32_t k = blockIdx.x;
     if (k >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
@@ -542,7 +576,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_norm_scale(const NormScaleTask*
 template <bool VEC>
 __global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __restrict__ tasks, uint32_t cpb) {
     __shared__ LoopTask T;
-    load_task(&T, tasks + blockIdx.y);
+    load_task_pdl(&T, tasks + blockIdx.y);
     const uint32_t kc0 = blockIdx.x * cpb;
     if (kc0 >= T.h.n_chunks) return;
     const uint32_t kc1 = min(kc0 + cpb, T.h.n_chunks);
@@ -585,7 +619,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_loop(const LoopTask* __r
 template <bool VEC>
 __global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ MultiTask T;
-    load_task(&T, tasks + blockIdx.y);
+    load_task_pdl(&T, tasks + blockIdx.y);
     const uint32_t kc0 = blockIdx.x * cpb;
     if (kc0 >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
@@ -635,7 +669,7 @@ __global__ void __launch_bounds__(TDG_THREADS) k_sample_multi(const MultiTask* _
 template <bool VEC>
 __global__ void __launch_bounds__(TDG_THREADS) k_sample_lerp(const LerpTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ LerpTask T;
-    load_task(&T, tasks + blockIdx.y);
+    load_task_pdl(&T, tasks + blockIdx.y);
     const uint32_t kc0 = blockIdx.x * cpb;
     if (kc0 >= T.h.n_chunks) return;
     const uint32_t bl = T.h.bl;
@@ -781,7 +815,7 @@ __device__ __forceinline__ int wavetable_row(float fps, float ymax, float t, flo
 template <int KIND, bool EXACT, int F, bool LIBM>
 __global__ void __launch_bounds__(TDG_THREADS, KIND == VOICE_SYNTH ? TDG_SYNTH_MINB : TDG_SAMPSYN_MINB) k_voice(const VoiceTask* __restrict__ tasks, const uint8_t* __restrict__ blob, uint32_t cpb) {
     __shared__ VoiceTask T;
-    load_task(&T, tasks + blockIdx.y);
+    load_task_pdl(&T, tasks + blockIdx.y);
     const uint32_t kc0 = blockIdx.x * cpb;
     if (kc0 >= T.h.n_chunks) return;
     const uint32_t kc1 = min(kc0 + cpb, T.h.n_chunks);
@@ -1183,7 +1217,7 @@ __global__ void __launch_bounds__(kBpFusedThreads, 768 / kBpFusedThreads) k_bp_f
     // grid = (filters, strips): consecutive blocks belong to DIFFERENT filters, so the blocks resident at any time
     // advance many filters' group chains at once (with the strips of one filter side by side the whole GPU waits
     // on that filter's serial chain)
-    load_task(&T, tasks + blockIdx.x);
+    load_task_pdl(&T, tasks + blockIdx.x);
     if (blockIdx.y >= (T.n_tiles + kBpStripTiles - 1) / kBpStripTiles) return;
     if (threadIdx.x == 0) s_strip = atomicAdd(T.sync, 1u);
     __syncthreads();
@@ -1474,7 +1508,7 @@ __device__ __forceinline__ void quantise_block(const QuantTask& T, uint64_t b0, 
 #endif
 __global__ void __launch_bounds__(TDG_THREADS) k_quantise(const QuantTask* __restrict__ tasks, uint32_t cpb) {
     __shared__ QuantTask T;
-    load_task(&T, tasks + blockIdx.y);
+    load_task_pdl(&T, tasks + blockIdx.y);
     const uint32_t span = T.span;
     bool wide = false;
 #pragma unroll 1
@@ -1645,6 +1679,26 @@ __global__ void k_scale_by_inv(float* __restrict__ x, uint64_t n, const float* _
 // ------------------------------------------------------------------------------------ launchers
 static inline dim3 grid2(uint64_t x, uint32_t y) { return dim3((unsigned)(x ? x : 1), y, 1); }   // zero-length pass: blocks find nothing to do
 
+// Launch of a pass kernel (one that calls pdl_wait before it reads what kernels produce) with programmatic stream
+// serialization: its blocks may become resident while the last wave of the kernel in front drains (TDG_PDL=0: plain launches).
+static bool g_pdl = []() { const char* e = getenv("TDG_PDL"); return e ? atoi(e) != 0 : TDG_PDL_DEFAULT != 0; }();
+template <typename... KArgs, typename... Args>
+static inline void pdl_launch(void (*k)(KArgs...), dim3 g, dim3 b, size_t smem, cudaStream_t s, Args... args) {
+#ifdef __NVCC__
+    if (g_pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
+        return;
+    }
+#endif
+    k<<<g, b, smem, s>>>(KArgs(args)...);
+}
+
 // Chunks per block, chosen per launch: the compile-time maximum while the grid still has >= g_cpb_waves waves of blocks
 // (a block that walks 8 chunks is 8 times longer, and a grid of a few waves ends in a long tail: configs[2]'s one
 // 512-voice vertex went from 61.1 to 63.9 ms with a fixed 8), halved until it does.
@@ -1664,13 +1718,13 @@ template <bool GRP>
 static void launch_fx_t(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, const uint8_t* blob, cudaStream_t s) {
     const uint32_t c1 = pick_cpb(GRP ? TDG_FXG_CPB : TDG_FX_CPB, max_chunks, n, 6), ca = pick_cpb(TDG_ADSR_CPB, max_chunks, n, TDG_ADSR_MINB);
     const dim3 g = grid2((max_chunks + c1 - 1) / c1, n);
-    if (mode == FX_SUM) { if (vec) k_fx<FX_SUM, true, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); else k_fx<FX_SUM, false, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); }
+    if (mode == FX_SUM) { if (vec) pdl_launch(k_fx<FX_SUM, true, false, GRP>, g, TDG_THREADS, 0, s, t, blob, c1); else pdl_launch(k_fx<FX_SUM, false, false, GRP>, g, TDG_THREADS, 0, s, t, blob, c1); }
     else if (mode == FX_ADSR) {
         const dim3 ga = grid2((max_chunks + ca - 1) / ca, n);
-        if (exact) { if (vec) k_fx<FX_ADSR, true, true, GRP><<<ga, TDG_THREADS, 0, s>>>(t, blob, ca); else k_fx<FX_ADSR, false, true, GRP><<<ga, TDG_THREADS, 0, s>>>(t, blob, ca); }
-        else { if (vec) k_fx<FX_ADSR, true, false, GRP><<<ga, TDG_THREADS, 0, s>>>(t, blob, ca); else k_fx<FX_ADSR, false, false, GRP><<<ga, TDG_THREADS, 0, s>>>(t, blob, ca); }
+        if (exact) { if (vec) pdl_launch(k_fx<FX_ADSR, true, true, GRP>, ga, TDG_THREADS, 0, s, t, blob, ca); else pdl_launch(k_fx<FX_ADSR, false, true, GRP>, ga, TDG_THREADS, 0, s, t, blob, ca); }
+        else { if (vec) pdl_launch(k_fx<FX_ADSR, true, false, GRP>, ga, TDG_THREADS, 0, s, t, blob, ca); else pdl_launch(k_fx<FX_ADSR, false, false, GRP>, ga, TDG_THREADS, 0, s, t, blob, ca); }
     }
-    else { if (vec) k_fx<FX_NORM_PEAK, true, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); else k_fx<FX_NORM_PEAK, false, false, GRP><<<g, TDG_THREADS, 0, s>>>(t, blob, c1); }
+    else { if (vec) pdl_launch(k_fx<FX_NORM_PEAK, true, false, GRP>, g, TDG_THREADS, 0, s, t, blob, c1); else pdl_launch(k_fx<FX_NORM_PEAK, false, false, GRP>, g, TDG_THREADS, 0, s, t, blob, c1); }
 }
 cudaError_t launch_fx(int mode, const FxTask* t, uint32_t n, uint32_t max_chunks, bool vec, bool exact, bool grouped, const uint8_t* blob, cudaStream_t s) {
     if (grouped) launch_fx_t<true>(mode, t, n, max_chunks, vec, exact, blob, s); else launch_fx_t<false>(mode, t, n, max_chunks, vec, exact, blob, s);
@@ -1683,15 +1737,15 @@ cudaError_t launch_env_table(float* clock, uint32_t bl, uint32_t row0, uint32_t 
 }
 cudaError_t launch_chunk_ranges(const RangeTask* t, uint32_t n, uint32_t max_chunks, bool any_segs, const uint8_t* blob, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    k_chunk_ranges<<<grid2((max_chunks + 255) / 256, n), 256, 0, s>>>(t, blob);
+    pdl_launch(k_chunk_ranges, grid2((max_chunks + 255) / 256, n), 256, 0, s, t, blob);
     if (any_segs) {                                      // voices / adsr: counts -> offsets -> segments
-        k_seg_scan<<<n, 1024, 0, s>>>(t);
-        k_seg_fill<<<grid2((max_chunks + 255) / 256, n), 256, 0, s>>>(t, blob);
+        pdl_launch(k_seg_scan, dim3(n), 1024, 0, s, t);
+        pdl_launch(k_seg_fill, grid2((max_chunks + 255) / 256, n), 256, 0, s, t, blob);
     }
     return cudaGetLastError();
 }
 cudaError_t launch_norm_prefix(const NormPrefixTask* t, uint32_t n, cudaStream_t s) {
-    k_norm_prefix<<<n, 1024, 0, s>>>(t);
+    pdl_launch(k_norm_prefix, dim3(n), 1024, 0, s, t);
     return cudaGetLastError();
 }
 cudaError_t launch_norm_total(const NormPrefixTask* t, uint32_t n, float* reduce_buf, cudaStream_t s) {
@@ -1703,22 +1757,22 @@ cudaError_t launch_bp_total(const BpTask* t, uint32_t n, const uint8_t* blob, cu
     return cudaGetLastError();
 }
 cudaError_t launch_norm_scale(const NormScaleTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s) {
-    TDG_VEC_DISPATCH(vec, k_norm_scale, <<<grid2(max_chunks, n), TDG_THREADS, 0, s>>>(t));
+    if (vec) pdl_launch(k_norm_scale<true>, grid2(max_chunks, n), TDG_THREADS, 0, s, t); else pdl_launch(k_norm_scale<false>, grid2(max_chunks, n), TDG_THREADS, 0, s, t);
     return cudaGetLastError();
 }
 cudaError_t launch_sample_loop(const LoopTask* t, uint32_t n, uint32_t max_chunks, bool vec, cudaStream_t s) {
     const uint32_t cpb = pick_cpb(TDG_GATHER_CPB, max_chunks, n, 6);
-    TDG_VEC_DISPATCH(vec, k_sample_loop, <<<grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s>>>(t, cpb));
+    if (vec) pdl_launch(k_sample_loop<true>, grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s, t, cpb); else pdl_launch(k_sample_loop<false>, grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s, t, cpb);
     return cudaGetLastError();
 }
 cudaError_t launch_sample_multi(const MultiTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
     const uint32_t cpb = pick_cpb(TDG_GATHER_CPB, max_chunks, n, 6);
-    TDG_VEC_DISPATCH(vec, k_sample_multi, <<<grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s>>>(t, blob, cpb));
+    if (vec) pdl_launch(k_sample_multi<true>, grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s, t, blob, cpb); else pdl_launch(k_sample_multi<false>, grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s, t, blob, cpb);
     return cudaGetLastError();
 }
 cudaError_t launch_sample_lerp(const LerpTask* t, uint32_t n, uint32_t max_chunks, bool vec, const uint8_t* blob, cudaStream_t s) {
     const uint32_t cpb = pick_cpb(TDG_GATHER_CPB, max_chunks, n, 6);
-    TDG_VEC_DISPATCH(vec, k_sample_lerp, <<<grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s>>>(t, blob, cpb));
+    if (vec) pdl_launch(k_sample_lerp<true>, grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s, t, blob, cpb); else pdl_launch(k_sample_lerp<false>, grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, 0, s, t, blob, cpb);
     return cudaGetLastError();
 }
 
@@ -1738,7 +1792,7 @@ static cudaError_t launch_voice_t(const VoiceTask* t, uint32_t n, uint32_t max_c
         attr_set = g_voice_smem;
     }
     const uint32_t cpb = pick_cpb(TDG_VOICE_CPB, max_chunks, n, 5);
-    kfn<<<grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, (size_t)g_voice_smem, s>>>(t, blob, cpb);
+    pdl_launch(kfn, grid2((max_chunks + cpb - 1) / cpb, n), TDG_THREADS, (size_t)g_voice_smem, s, t, blob, cpb);
     return cudaGetLastError();
 }
 cudaError_t launch_voice(int kind, const VoiceTask* t, uint32_t n, uint32_t max_chunks, bool exact, bool libm_sin, const uint8_t* blob, cudaStream_t s) {
@@ -1773,12 +1827,12 @@ cudaError_t launch_bp_fused(const BpTask* t, uint32_t n, uint32_t max_tiles, boo
         attr_set = true;
     }
     const uint32_t max_strips = (max_tiles + kBpStripTiles - 1) / kBpStripTiles;
-    TDG_VEC_DISPATCH(vec, k_bp_fused, <<<dim3(n, max_strips ? max_strips : 1, 1), kBpFusedThreads, kBpStripSmem, s>>>(t, blob));
+    if (vec) pdl_launch(k_bp_fused<true>, dim3(n, max_strips ? max_strips : 1, 1), kBpFusedThreads, kBpStripSmem, s, t, blob); else pdl_launch(k_bp_fused<false>, dim3(n, max_strips ? max_strips : 1, 1), kBpFusedThreads, kBpStripSmem, s, t, blob);
     return cudaGetLastError();
 }
 cudaError_t launch_quantise(const QuantTask* t, uint32_t n, uint64_t max_blocks, cudaStream_t s) {
     const uint32_t cpb = pick_cpb(TDG_QUANT_CPB, (uint32_t)std::min<uint64_t>(max_blocks, 0xffffffffu), n, 8);
-    k_quantise<<<grid2(max_blocks ? (max_blocks + cpb - 1) / cpb : 1, n), TDG_THREADS, 0, s>>>(t, cpb);
+    pdl_launch(k_quantise, grid2(max_blocks ? (max_blocks + cpb - 1) / cpb : 1, n), TDG_THREADS, 0, s, t, cpb);
     return cudaGetLastError();
 }
 cudaError_t launch_resample(const ResampleTask* t, uint32_t n, uint64_t max_out, uint32_t max_chunks, const uint8_t* blob, cudaStream_t s) {
