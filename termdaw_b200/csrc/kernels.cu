@@ -18,7 +18,7 @@ namespace tdg {
 
 #define TDG_THREADS 256
 #ifndef TDG_PDL_DEFAULT
-#define TDG_PDL_DEFAULT 0
+#define TDG_PDL_DEFAULT 1
 #endif
 
 // ------------------------------------------------------------------------------------ helpers
