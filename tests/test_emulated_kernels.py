@@ -44,6 +44,10 @@ def test_emu_inlined_sums(emulib, oracle):
     TI.check_batch_projects(emulib, oracle, indices=range(8), scale=0.03)
 
 
+def test_emu_random_dags(emulib, oracle):
+    TI.check_random_dags(emulib, oracle, seeds=range(16))
+
+
 def test_emu_fused_refresh(emulib, oracle):
     TI.check_fused_refresh(emulib, oracle, n=7, scale=0.03)
 

@@ -160,6 +160,85 @@ def check_fused_refresh(lib, oracle, n=7, scale=0.04):
             st.close()
 
 
+def random_dag_project(seed, seconds=0.35):
+    """A random DAG, NOT a tree: vertices with several consumers, the same producer connected twice to one consumer,
+    sums of sums, sums feeding band passes / adsrs / non-output normalizes, dangling (unreachable) vertices.  What the
+    planner's liveness and inlining rules must survive."""
+    rng = np.random.default_rng(seed)
+    a = S._shared_assets(rng, seconds, 2)
+    p = Project()
+    p.set_length(seconds)
+    p.set_render_samplerate(48000)
+    p.set_render_bitdepth(int(rng.choice([16, 24])))
+    for sm in ("s_noise", "s_tone", "s_long"):
+        p.load_sample(sm, sm, "")
+    p.load_resource("table", "table")
+    for i in range(2):
+        p.load_midi_floww(f"hits{i}", f"hits{i}")
+        p.load_midi_floww(f"notes{i}", f"notes{i}")
+    gens, fx = [], []
+    for i in range(int(rng.integers(3, 7))):
+        k = int(rng.integers(5)); name = f"g{i}"
+        gain, angle = float(rng.uniform(0.3, 1.4)), float(rng.uniform(-80, 80))
+        smp = ("s_noise", "s_tone", "s_long")[int(rng.integers(3))]
+        if k == 0: p.add_sampleloop(name, gain, angle, smp)
+        elif k == 1: p.add_sample_multi(name, gain, angle, smp, f"hits{int(rng.integers(2))}", -1)
+        elif k == 2: p.add_sample_lerp(name, gain, angle, smp, f"hits{int(rng.integers(2))}", -1, 40)
+        elif k == 3: p.add_synth(name, gain, angle, f"notes{int(rng.integers(2))}", 0.4, 0.3, S.HIT_ADSR, 1.0, 0.6, S.NOTE_ADSR, 0.5, S.NOTE_ADSR)
+        else: p.add_sampsyn(name, gain, angle, f"notes{int(rng.integers(2))}", S.STD_ADSR, "table")
+        gens.append(name)
+    has_bp = False
+    for i in range(int(rng.integers(4, 10))):
+        k = int(rng.choice([0, 0, 0, 1, 2, 3])); name = f"f{i}"
+        gain, angle = float(rng.choice([1.0, 0.7, 1.3])), float(rng.choice([0.0, 25.0, -50.0]))
+        if k == 0: p.add_sum(name, gain, angle)
+        elif k == 1: p.add_adsr(name, gain, angle, float(rng.choice([1.0, 0.6])), f"notes{int(rng.integers(2))}", True, True, -1, [0.01, 0.1, 0.8, 0.1, 0.2, 0.05])
+        elif k == 2: p.add_bandpass(name, gain, angle, 1.0, 1000.0, 200.0, True); has_bp = True
+        else: p.add_normalize(name, gain, angle)
+        fx.append(name)
+    p.add_normalize("out", 1.0, 0.0)
+    order = fx + ["out"]
+    for j, f in enumerate(fx):                                  # forward edges only: acyclic
+        for _ in range(int(rng.choice([1, 1, 1, 2, 3]))):       # several consumers
+            t = order[int(rng.integers(j + 1, len(order)))]
+            p.connect(f, t)
+            if rng.random() < 0.1:
+                p.connect(f, t)                                  # the same edge twice
+    for g in gens:
+        for _ in range(int(rng.choice([1, 1, 2]))):
+            p.connect(g, order[int(rng.integers(len(order)))])
+    for f in fx:                                                 # every effect gets at least one input
+        if not any(b == f for (_, b) in p.edges):
+            p.connect(gens[int(rng.integers(len(gens)))], f)
+    p.set_output("out")
+    return (p, a, {"psr": S.PSR, "bl": S.BL, "flow": "B"}), has_bp
+
+
+def check_random_dags(lib, oracle, seeds=range(24)):
+    inlined = 0
+    for seed in seeds:
+        cfg, has_bp = random_dag_project(1000 + seed)
+        on, st_on, bd = _render(lib, cfg, True)
+        off, _, _ = _render(lib, cfg, False)
+        assert np.array_equal(on, off), seed
+        on_a, _, _ = _render(lib, cfg, True, passes=("render",))
+        off_a, _, _ = _render(lib, cfg, False, passes=("render",))
+        assert np.array_equal(on_a, off_a), seed
+        inlined += st_on["inlined_vertices"]
+        want = run_project(oracle, *cfg, taps=False)
+        x, y = pcm_to_int(on, bd), pcm_to_int(want["pcm"], want["bd"])
+        assert x.shape == y.shape, seed
+        if has_bp:
+            assert np.abs(x - y).max() <= (1 if bd == 16 else 16), (seed, int(np.abs(x - y).max()))
+        else:
+            assert np.array_equal(x, y), seed
+    assert inlined > 0
+
+
+def test_random_dags_inlined_equal_not_inlined_equal_oracle(gpulib, oracle):
+    check_random_dags(gpulib, oracle)
+
+
 def test_fused_refresh_equals_rewind_then_render(gpulib, oracle):
     check_fused_refresh(gpulib, oracle)
 
