@@ -507,6 +507,8 @@ struct PlanScratch {                    // per planner thread
     // host copy of the clock table (tdg_types.h) of one (sr, bl), rows appended on demand: a voice's clock at its
     // note-off in O(1) instead of one addition per chunk it was held
     std::vector<float> hclk; uint32_t hclk_sr = 0, hclk_bl = 0, hclk_rows = 0;
+    std::vector<float> nv; std::vector<uint32_t> hit;   // plan_voices: the live voices' note values side by side (the per-event scan), the matches of one event
+    std::vector<std::pair<uint32_t, uint32_t>> drops;   // plan_voices: pending drops of released voices (chunk, index), a min-heap
     static const uint32_t kHostClockRows = 16384;
     float clock(uint32_t sr, uint32_t bl, uint32_t i, uint32_t n) {
         const float fsr = (float)sr, d = (float)bl / fsr;
@@ -573,7 +575,12 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, VPlan
     auto clock_of = [&](const SNote& n, uint32_t k) -> float {
         if (n.xclk >= 0) {
             std::vector<float>& x = S.xc[n.xclk];
-            while (x.size() <= k) x.push_back(x.back() + d);
+            if (x.size() <= k) {                                     // one growth, then the additions in a tight loop
+                size_t q = x.size();
+                x.resize((size_t)k + 1);
+                float e = x[q - 1];
+                for (; q <= k; ++q) { e += d; x[q] = e; }
+            }
             return x[k];
         }
         return S.clock(pp.sr, pp.bl, n.clk_i, k - n.clk_chunk);
@@ -598,18 +605,49 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, VPlan
             n.drop_chunk = drop_after(n.env_t, 0);
         }
     }
-    uint32_t next_drop = kNever;                                     // earliest pending drop chunk: nothing to purge before it
-    for (const SNote& n : v.notes) next_drop = std::min(next_drop, n.drop_chunk);
-    auto purge = [&](uint32_t k) {                                   // everything dropped at the end of a chunk < k
-        if (next_drop == kNever || next_drop >= k) return;
-        next_drop = kNever;
+    // Bookkeeping of the live voices during the replay.  The reference erases a voice from its Vec the moment it goes
+    // (`retain`, extensions.rs:485,528); here a voice that goes is only marked (its note value becomes +inf, which no
+    // note-off matches) and the vector is compacted — stably: the order of the survivors is the reference's — once
+    // half of it is dead and at the end of the pass.  A note-off looks for its voices in `nv`, the note values side by
+    // side (one vectorised scan over a few KB instead of a walk over 64-byte records), and the drops scheduled by
+    // released voices sit in a heap keyed by their chunk: per event O(live / SIMD width + log live) where erasing in
+    // place was O(live) per dropped voice — configs[2] re-strikes 512 held voices 15 000 times per pass.
+    std::vector<float>& nv = S.nv;
+    nv.resize(v.notes.size());
+    for (size_t q = 0; q < v.notes.size(); ++q) nv[q] = v.notes[q].note;
+    const float kDead = __builtin_inff();
+    size_t n_dead = 0;
+    std::vector<std::pair<uint32_t, uint32_t>>& heap = S.drops;      // (drop chunk, index in v.notes), min-heap
+    heap.clear();
+    auto heap_cmp = [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) { return a > b; };
+    auto schedule_drop = [&](uint32_t idx) {
+        if (v.notes[idx].drop_chunk == kNever) return;
+        heap.push_back({v.notes[idx].drop_chunk, idx}); std::push_heap(heap.begin(), heap.end(), heap_cmp);
+    };
+    for (size_t q = 0; q < v.notes.size(); ++q) schedule_drop((uint32_t)q);
+    auto kill = [&](uint32_t idx) { nv[idx] = kDead; ++n_dead; };
+    auto compact = [&]() {
+        if (n_dead == 0) return;
         size_t w = 0;
         for (size_t q = 0; q < v.notes.size(); ++q) {
-            SNote& n = v.notes[q];
-            if (n.drop_chunk != kNever && n.drop_chunk < k) close_rec(n.rec, n.drop_chunk, pp.bl);
-            else { next_drop = std::min(next_drop, n.drop_chunk); if (w != q) v.notes[w] = n; ++w; }
+            if (nv[q] == kDead) continue;
+            if (w != q) { v.notes[w] = v.notes[q]; nv[w] = nv[q]; }
+            ++w;
         }
-        v.notes.resize(w);
+        v.notes.resize(w); nv.resize(w); n_dead = 0;
+        heap.clear();
+        for (size_t q = 0; q < w; ++q) if (v.notes[q].drop_chunk != kNever) heap.push_back({v.notes[q].drop_chunk, (uint32_t)q});
+        std::make_heap(heap.begin(), heap.end(), heap_cmp);
+    };
+    auto purge = [&](uint32_t k) {                                   // everything dropped at the end of a chunk < k
+        while (!heap.empty() && heap.front().first < k) {
+            const uint32_t idx = heap.front().second, at = heap.front().first;
+            std::pop_heap(heap.begin(), heap.end(), heap_cmp); heap.pop_back();
+            if (nv[idx] == kDead || v.notes[idx].drop_chunk != at) continue;           // gone already / stale entry
+            close_rec(v.notes[idx].rec, at, pp.bl);
+            kill(idx);
+        }
+        if (n_dead > 64 && 2 * n_dead > v.notes.size()) compact();
     };
     EvCursor cur(&fl, pp.F0);
     for (uint64_t k64 = 0; k64 < pp.total; ++k64) {
@@ -641,24 +679,27 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, VPlan
                 const float hz = note_hz(note);
                 SNote n{note, vel, 0.0f, 0.0f, hz, open_rec(hz, vel, k, i, i), -1};
                 n.clk_chunk = k; n.clk_i = i; n.drop_chunk = kNever;
-                v.notes.push_back(n);
+                v.notes.push_back(n); nv.push_back(note);
                 return;
             }
             // retain (extensions.rs:485) drops the voices of this note that are already releasing; the others of this
-            // note start their release (extensions.rs:486-494).  One scan finds the note's voices (usually one).
+            // note start their release (extensions.rs:486-494).  One scan over the note values finds the note's
+            // voices (usually one), in list order.
             bool any_rel = false, any_held = false;
-            for (const SNote& n : v.notes) if (!(fabsf(n.note - note) > 0.001f)) { if (n.rel_t == 0.0f) any_held = true; else any_rel = true; }
-            if (any_rel) {
-                size_t w = 0;
-                for (size_t q = 0; q < v.notes.size(); ++q) {
-                    SNote& n = v.notes[q];
-                    if (fabsf(n.note - note) > 0.001f || n.rel_t == 0.0f) { if (w != q) v.notes[w] = n; ++w; }
-                    else close_rec(n.rec, k, i);
-                }
-                v.notes.resize(w);
-            }
-            if (any_held) for (SNote& n : v.notes) {
-                if (fabsf(n.note - note) > 0.001f || n.rel_t != 0.0f) continue;
+            std::vector<uint32_t>& hit = S.hit;
+            hit.clear();
+            { const float* pv = nv.data(); const size_t nn = nv.size();
+              for (size_t b0 = 0; b0 < nn; b0 += 32) {                      // branch-free per block of 32 (vectorises), indices only where a block matched
+                  const size_t b1 = std::min(nn, b0 + 32);
+                  unsigned any = 0;
+                  for (size_t q = b0; q < b1; ++q) any |= (unsigned)!(fabsf(pv[q] - note) > 0.001f);
+                  if (any) for (size_t q = b0; q < b1; ++q) if (!(fabsf(pv[q] - note) > 0.001f)) hit.push_back((uint32_t)q);
+              } }
+            for (uint32_t q : hit) { if (v.notes[q].rel_t == 0.0f) any_held = true; else any_rel = true; }
+            if (any_rel) for (uint32_t q : hit) if (v.notes[q].rel_t != 0.0f) { close_rec(v.notes[q].rec, k, i); kill(q); }
+            if (any_held) for (uint32_t hq : hit) {
+                SNote& n = v.notes[hq];
+                if (nv[hq] == kDead || n.rel_t != 0.0f) continue;
                 n.rel_t = clock_of(n, k) + fi;                              // env_t + i/sr
                 n.xclk = -1; n.clk_chunk = k; n.clk_i = i;                  // env_t = -(i/sr): the clock restarts, column i
                 // apply_r_rt's start value apply_ads(conf, rel_t) (adsr.rs:89-92): constant from here on
@@ -671,7 +712,7 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, VPlan
                     r.off_chunk = k; r.off_i = i; r.envr = i; r.rel_t = n.rel_t;
                     r.relv0 = n.relv[0]; r.relv1 = n.relv[1]; r.relv2 = n.relv[2];
                     n.drop_chunk = drop_after(-fi, k);
-                    next_drop = std::min(next_drop, n.drop_chunk);
+                    schedule_drop(hq);
                 } else {
                     // env_t + fi == 0.0 exactly (a note-off in the frame of its note-on): the voice still reads as
                     // held (rel_t == 0.0) but its clock restarted: a continuation record in its place
@@ -683,6 +724,7 @@ static void plan_voices(HVertex& v, const Floww& fl, const PassParams& pp, VPlan
         });
     }
     purge(total);
+    compact();
     for (DNote& n : v.dnotes) close_rec(n.rec, last, pp.bl);
     for (SNote& n : v.notes) {
         close_rec(n.rec, last, pp.bl);

@@ -48,6 +48,10 @@ def test_emu_random_dags(emulib, oracle):
     TI.check_random_dags(emulib, oracle, seeds=range(16))
 
 
+def test_emu_voice_planner_fuzz(emulib, oracle):
+    TI.check_voice_planner_fuzz(emulib, oracle, seeds=range(10))
+
+
 def test_emu_fused_refresh(emulib, oracle):
     TI.check_fused_refresh(emulib, oracle, n=7, scale=0.03)
 

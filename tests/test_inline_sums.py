@@ -239,6 +239,61 @@ def test_random_dags_inlined_equal_not_inlined_equal_oracle(gpulib, oracle):
     check_random_dags(gpulib, oracle)
 
 
+def adversarial_note_stream(rng, seconds):
+    """Few distinct notes (many re-strikes of one note, some while it is still releasing), two of them within the 0.001
+    matching tolerance of another, bursts of events in one frame, offs in the frame of their on, doubled ons."""
+    notes = rng.uniform(40, 80, 6)
+    notes = np.concatenate([notes, notes[:2] + 0.0005])
+    ev, t = [], 0.0
+    while t < seconds:
+        t += float(rng.choice([0.0, 0.001, 0.01, 0.05, 0.2]))
+        n = float(notes[int(rng.integers(len(notes)))])
+        ev.append((t, n, float(rng.uniform(0.2, 1.0))) if rng.random() < 0.5 else (t, n, 0.0))
+        if rng.random() < 0.15:
+            ev.append((t, n, 0.0))
+        if rng.random() < 0.1:
+            ev.append((t, n, float(rng.uniform(0.2, 1.0))))
+    ev.sort(key=lambda e: e[0])
+    a = np.array(ev, np.float32).reshape(-1, 3)
+    return a[:, 0].copy(), a[:, 1].copy(), a[:, 2].copy()
+
+
+def check_voice_planner_fuzz(lib, oracle, seeds=range(12)):
+    """The voice planner (engine.cu plan_voices: note matching over the side-by-side note values, lazily erased voices,
+    the drop heap) against the oracle's Vec / retain bookkeeping (extensions.rs:469-530): every tap and the PCM bit for bit,
+    scan + render (voices and clocks carried from one pass into the next)."""
+    from termdaw_b200.state import Assets
+    for seed in seeds:
+        rng = np.random.default_rng(seed)
+        seconds = float(rng.choice([0.6, 1.2, 2.5]))
+        a = Assets()
+        a.blobs["table"] = S.wavetable_blob(seed, 8, 64, 6.0)
+        a.flowws["n0"] = adversarial_note_stream(rng, seconds)
+        a.flowws["n1"] = adversarial_note_stream(rng, seconds)
+        p = Project()
+        p.set_length(seconds); p.set_render_samplerate(48000); p.set_render_bitdepth(24)
+        p.load_resource("table", "table"); p.load_midi_floww("n0", "n0"); p.load_midi_floww("n1", "n1")
+        rel = float(rng.choice([0.0, 0.02, 0.3]))
+        adsr = [0.01, 0.1, 0.8, 0.2, 0.2, rel]
+        p.add_synth("syn", 0.8, 10.0, "n0", 0.4, 0.3, S.HIT_ADSR, 1.0, 0.6, adsr, 0.5, adsr)
+        p.add_sampsyn("wt", 0.7, -20.0, "n1", [0.01, 1.0, 0.3, 1.0, 1.0, rel + 0.05], "table")
+        p.add_debug_sine("ds", 0.3, 0.0, "n0")
+        p.add_normalize("out", 1.0, 0.0)
+        for v in ("syn", "wt", "ds"):
+            p.connect(v, "out")
+        p.set_output("out")
+        cfg = (p, a, {"psr": 48000, "bl": int(rng.choice([256, 1024])), "flow": "B"})
+        got, want = run_project(lib, *cfg), run_project(oracle, *cfg)
+        assert np.array_equal(got["pcm"], want["pcm"]), seed
+        for name, (l, r) in want["taps"].items():
+            gl, gr = got["taps"][name]
+            assert np.array_equal(gl, l) and np.array_equal(gr, r), (seed, name)
+
+
+def test_voice_planner_against_adversarial_note_streams(gpulib, oracle):
+    check_voice_planner_fuzz(gpulib, oracle)
+
+
 def test_fused_refresh_equals_rewind_then_render(gpulib, oracle):
     check_fused_refresh(gpulib, oracle)
 
