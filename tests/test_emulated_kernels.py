@@ -24,7 +24,7 @@ import test_golden as TG  # noqa: E402
 import test_gpu_parity as TP  # noqa: E402
 import test_pass_reuse as TR  # noqa: E402
 import test_timeshard as TS  # noqa: E402
-import test_inline_sums as TI  # noqa: E402
+import test_planner_invariants as TI  # noqa: E402
 
 
 @pytest.fixture(scope="session")
@@ -38,7 +38,7 @@ def emulib(tmp_path_factory):
     return lib
 
 
-# ---- inlined sums, chunks per block (tests/test_inline_sums.py) -------------------------------------------
+# ---- inlined sums, chunks per block (tests/test_planner_invariants.py) -------------------------------------------
 def test_emu_inlined_sums(emulib, oracle):
     TI.check_sum_chain(emulib, oracle)
     TI.check_batch_projects(emulib, oracle, indices=range(8), scale=0.03)

@@ -1,4 +1,5 @@
-"""Inlined sums and launch shaping: two planner / launch decisions that must not change a single bit.
+"""Planner and launch decisions that must not change a single bit: inlined sums, chunks per block, the refresh pipelined
+inside the batched call, buffer liveness on arbitrary DAGs, the voice planner's bookkeeping.
 
 * A Sum vertex whose only consumer is a Sum, Normalize or Adsr vertex is evaluated inside that consumer's kernel
   (engine.cu "inlined sums", include/termdaw_b200.h tdg_set_inline_sums): PCM with the switch on == PCM with it
